@@ -1,0 +1,183 @@
+/*
+ * yad_b200.h - C ABI of the B200-native audio-activity-detection hot path.
+ *
+ * The reference (ches-001/YOLO-inspired-audio-activity-detection) is pure
+ * Python and has no FFI layer; every entry point below replaces a *library
+ * call site* of the reference (file:line relative to the reference root,
+ * "[ta]" = torchaudio 2.11, "[tv]" = torchvision 0.26).  The Python host
+ * package (yad_b200) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; the message is in
+ *     yad_last_error() (thread local).  No C++ exception crosses the ABI.
+ *   - every pointer is a DEVICE pointer owned by the caller (inputs, outputs
+ *     and workspaces); the library never allocates or frees device memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t / CUstream).
+ *   - no mutable global state after yad_init(): calls are re-entrant (the
+ *     reference shares one model across 10 threads, inference.py:212-236).
+ *   - no CPU fallback: unsupported shapes / architectures return an error.
+ *   - activations are NHWC ("pixel-major"): element (b,h,w,c) of a tensor with
+ *     channel pitch `ld` lives at ((b*H + h)*W + w)*ld + c.
+ */
+#ifndef YAD_B200_H_
+#define YAD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* yad_stream_t;              /* cudaStream_t */
+
+enum { YAD_F32 = 0, YAD_BF16 = 1 };       /* element types */
+enum { YAD_ACT_NONE = 0, YAD_ACT_RELU = 1, YAD_ACT_LRELU02 = 2 };
+
+enum {
+  YAD_OK = 0,
+  YAD_ERR_ARG = -1,        /* bad argument / unsupported shape */
+  YAD_ERR_CUDA = -2,       /* a CUDA runtime / driver call failed */
+  YAD_ERR_ARCH = -3,       /* device is not sm_100 */
+  YAD_ERR_WORKSPACE = -4   /* caller workspace too small */
+};
+
+int yad_version(void);
+const char* yad_last_error(void);
+/* Checks the device is compute capability 10.x, resolves cuTensorMapEncodeTiled,
+ * raises the dynamic shared-memory limits of the kernels.  Idempotent. */
+int yad_init(int device);
+
+/* ------------------------------------------------------------------ frontend
+ * Replaces, fused: torchaudio Resample (modules/_architecture.py:25-28,84 ->
+ * [ta] functional.py:1405-1431), MelSpectrogram (:30-33,98 -> torch.stft,
+ * abs().pow(2), matmul fb), MFCC (:34-37,99), AmplitudeToDB x2 (:29,100-101 ->
+ * [ta] functional.py:390-403) and scale_input (:103-105,182-189).
+ *
+ * Stage A: PCM -> mel power.  Polyphase resample (new_rate/orig_rate reduced to
+ * P/O; only the non-zero taps of each phase), Hann window, 1000-point real FFT,
+ * |X|^2, sparse mel filterbank.  n_fft = hop = 1000, 32 mels, center=False.
+ *   pcm        [B, L]                 f32
+ *   taps       [P/2][2][YAD_FE_TPQ]   f32  resampler.kernel rows of the phase pair (2u, 2u+1), both
+ *                                          cut to the pair's common window [tap_base[u], +YAD_FE_TPQ)
+ *                                          of the 2*width+O wide tap axis, zero padded
+ *   tap_base   [P/2]                  i32
+ *   window_len                        max(tap_base) + YAD_FE_TPQ (span of the padded signal one hop reads)
+ *   window     [1000]                 f32  analysis window
+ *   twiddle    [1000][2]              f32  exp(-2*pi*i*k/1000), built in fp64 by the host
+ *   fb_val [nnz] f32, fb_bin [nnz] i32, fb_start [33] i32   mel filterbank in CSR form over mel bands
+ *   mel        [B, 32, T]             f32  (T frames; T*1000 <= ceil(P*L/O))
+ */
+#define YAD_FE_TPQ 20
+int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
+                           const float* taps, const int32_t* tap_base, int32_t window_len,
+                           const float* window, const float* twiddle, const float* fb_val,
+                           const int32_t* fb_bin, const int32_t* fb_start, float* mel, int64_t T,
+                           yad_stream_t stream);
+
+/* Stage B: mel power [B,32,T] -> x_spectral [B,2,32,T] f32 (channel 0 = standardised
+ * dB-mel, channel 1 = standardised dB-of-MFCC).  One CTA per clip; T <= 1024.
+ * Optional taps (may be NULL): meldb, mfcc, mfdb, each [B,32,T] f32 (pre-standardise). */
+int yad_frontend_finish(const float* mel, int64_t B, int64_t T, const float* dct /*[32,32]*/,
+                        float top_db, int32_t standardise, float* x_spectral, float* tap_meldb,
+                        float* tap_mfcc, float* tap_mfdb, yad_stream_t stream);
+
+/* ------------------------------------------------------------------ convolutions
+ * Replace F.conv2d + batch_norm(eval) + activation (+ residual add) call sites:
+ * modules/_backbone.py:143-151, [tv] models/resnet.py:89-105, modules/_common.py:43-48,86-95.
+ * BatchNorm is folded into (weight, bias) by the host at pack time.
+ */
+typedef struct {
+  int32_t B, H, W;            /* input spatial */
+  int32_t Cin, ld_in;         /* input channels used / channel pitch (elements) */
+  int32_t Cout, ld_out;       /* output channels written / channel pitch */
+  int32_t co_off;             /* first output channel inside the pitch (concat-free writes) */
+  int32_t kh, kw, sh, sw, ph, pw;
+  int32_t act;                /* YAD_ACT_* */
+  int32_t ld_res;             /* residual channel pitch (0 = no residual) */
+} yad_conv_desc;
+
+/* Stem conv1 (2 -> 64, 7x7, stride 2, pad 3): reads x_spectral NCHW f32 directly,
+ * writes NHWC (out_dtype) [B, H/2, W/2, 64].  weight [7][7][2][64] f32 (tap-major). */
+int yad_conv_stem(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* weight,
+                  void* out, int32_t out_dtype, yad_stream_t stream);
+
+/* CUDA-core implicit GEMM (fp32 accumulate; in/out dtype f32 or bf16).
+ * weight [kh][kw][Cin][Cout_pad] in `dtype`; bias [Cout] f32; residual/out NHWC. */
+int yad_conv_simt(const yad_conv_desc* d, int32_t dtype, const void* in, const void* weight,
+                  int32_t ld_w, const float* bias, const void* residual, void* out, yad_stream_t stream);
+
+/* tcgen05 / TMEM implicit GEMM, bf16 in, fp32 accumulate in tensor memory, TMA-fed.
+ * Requirements: Cin % 64 == 0 (pad with zero channels), Cout_pad % 16 == 0, Cout_pad <= 256 per
+ * call tile (larger Cout is tiled over N by the grid), stride 1 or 2.
+ * weight [Cout_pad][kh*kw*Cin] bf16 (K-major, K ordered (kh, kw, cin)).
+ * out_dtype: YAD_BF16 or YAD_F32.  */
+int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad,
+                const float* bias, const void* residual, void* out, int32_t out_dtype,
+                yad_stream_t stream);
+
+/* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
+ * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5
+ * :173-174,181-182; cascaded max_pool2d k5 s1 p2 :207-209.  All write into a channel slice
+ * (co_off, ld_out) of the destination so torch.cat never materialises. */
+int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, int32_t C, int32_t ld_in,
+              void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
+int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
+                 int32_t up /*1: x2, 0: x0.5*/, void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
+/* in: slice [ci_off, ci_off+C) of a [B,W,ld] tensor; writes pool5, pool5^2, pool5^3 of it to channel
+ * slices co_off, co_off+C, co_off+2C of out. */
+int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
+                   void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
+
+/* ------------------------------------------------------------------ anchor decode
+ * Replaces get_scale_pred + combine (modules/_architecture.py:113-156).
+ * head_s [B, G_s, ld_s] (dtype) with A*(3+nc) valid channels; anchors_s [A] f32 in seconds.
+ * preds [B, sum_s G_s*A, 3+nc] f32, scale-major, row = g*A + a.
+ * center = ((sigmoid(tc)*2 - 0.5) + g) * stride_s / center_scaler ; width = (sigmoid(tw)*2)^2 * anchor
+ * both clipped to [0, duration]. */
+int yad_decode(const void* const* heads, const int32_t* G, const int32_t* ld, const int32_t* stride,
+               int32_t n_scales, int32_t dtype, const float* anchors /*[n_scales*A]*/, int32_t A, int32_t nc,
+               float center_scaler, float duration, int64_t B, float* preds, yad_stream_t stream);
+
+/* ------------------------------------------------------------------ segment NMS + post-processing
+ * Replaces inference.py:42-110 (process_model_outputs) incl. torchvision.ops.batched_nms
+ * ([tv] ops/boxes.py:48-120 -> torchvision::nms): class-agnostic per-clip greedy NMS on 1-D
+ * segments dressed as boxes of height _h; fp32 IoU; suppress iff iou > (double)thr; stable
+ * descending score order; NaN never suppresses.
+ *   preds      [B, P, 3+nc] f32 (P <= 1024)
+ *   keep       [B, P] i32   kept local indices in descending score order (first n_keep[b] valid)
+ *   n_keep     [B]    i32
+ *   conf/boxes [B, P] / [B, P, 2] f32  optional taps (may be NULL): confidence, clipped (x1,x2)
+ *   seg_rows   [B, P, 5] f32  per clip: rows passing conf > conf_thr, sorted by centre ascending,
+ *                             = [conf, obj_logit, label, start, end] (or centre,width if !start_end)
+ *   n_seg      [B] i32
+ */
+int yad_nms(const float* preds, int64_t B, int32_t P, int32_t nc, double iou_thr, float conf_thr,
+            float duration, float box_h, int32_t return_start_end, int32_t* keep, int32_t* n_keep,
+            float* conf, float* boxes, float* seg_rows, int32_t* n_seg, yad_stream_t stream);
+
+/* Compacts seg_rows/n_seg into the reference's return layout:
+ * segments [K,5] f32, batch_idxs [K] i64, total[0] = K (i64, device).  */
+int yad_compact_segments(const float* seg_rows, const int32_t* n_seg, int64_t B, int32_t P,
+                         float* segments, int64_t* batch_idxs, int64_t* total, yad_stream_t stream);
+
+/* ------------------------------------------------------------------ training-side (config 5)
+ * Anchor matching: dataset.py:286-365 (build_target_by_scale).  targets [T,4] f32 =
+ * (batch_idx, cls, centre_s, dur_s).  Outputs have capacity 3*A*T rows; rows are in the
+ * reference order (base matches anchor-major, then left-neighbour copies, then right).
+ * n_out[0] = M. */
+int yad_build_targets(const float* targets, int32_t T, const float* anchors, int32_t A, int32_t G,
+                      float anchor_t, float duration, float edge_t, int64_t* batch_idx, int64_t* grid_idx,
+                      int64_t* anchor_idx, int64_t* classes, float* cw, int32_t* n_out, yad_stream_t stream);
+
+/* Fused Adam (L2 weight decay) + EMA over a flat fp32 parameter arena:
+ * torch.optim.Adam (train.py:83-90, config.yaml:75-80) and smoothener/_ema.py:20-26.
+ * ema may be NULL.  step >= 1. */
+int yad_adam_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
+                      int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int32_t step, float ema_momentum, yad_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* YAD_B200_H_ */

@@ -1,0 +1,78 @@
+// Shared helpers for the yad_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/yad_b200.h"
+
+namespace yad {
+
+void set_error(const char* fmt, ...);
+
+#define YAD_CHECK_ARG(cond, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      yad::set_error(__VA_ARGS__);               \
+      return YAD_ERR_ARG;                        \
+    }                                            \
+  } while (0)
+
+#define YAD_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      yad::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return YAD_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define YAD_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      yad::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return YAD_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+// element load/store with fp32 math
+template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T> __device__ __forceinline__ void st_from_float(T* p, float v);
+template <> __device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == YAD_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == YAD_ACT_LRELU02) return v > 0.0f ? v : 0.2f * v;
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// driver entry point resolved by yad_init (no link-time libcuda dependency)
+void* tensor_map_encode_fn();
+int sm_count();
+
+}  // namespace yad

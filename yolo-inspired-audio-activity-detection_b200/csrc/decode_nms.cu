@@ -1,0 +1,350 @@
+// Anchor decode + 1-D segment NMS + post-processing (warp-level primitives, one CTA per clip).
+// Reference call sites: modules/_architecture.py:113-156 (get_scale_pred), inference.py:42-110
+// (process_model_outputs), torchvision ops/boxes.py:48-120 -> torchvision::nms.
+//
+// All IoU / box arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) so
+// that keep-sets are bit-exact against the fp32 CPU implementation given identical inputs.
+#include "common.cuh"
+
+namespace yad {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// ------------------------------------------------------------------------------------ decode
+struct DecodeParams {
+  const void* head[4];
+  int32_t G[4], ld[4], stride[4], row0[4];
+  float anchors[4 * 8];
+  int32_t n_scales, A, nc, rows_total;
+  float center_scaler, duration;
+};
+
+template <typename T>
+__global__ void decode_kernel(DecodeParams p, int64_t B, float* __restrict__ preds) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * p.rows_total) return;
+  const int64_t b = gid / p.rows_total;
+  const int row = (int)(gid % p.rows_total);
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < p.n_scales && row >= p.row0[i]) s = i;
+  const int local = row - p.row0[s];
+  const int g = local / p.A, a = local % p.A;
+  const int E = 3 + p.nc;
+  const T* h = reinterpret_cast<const T*>(p.head[s]) + ((int64_t)b * p.G[s] + g) * p.ld[s] + a * E;
+  float* o = preds + gid * E;
+  for (int j = 0; j < 1 + p.nc; ++j) o[j] = ld_as_float(h + j);
+  const float tc = ld_as_float(h + E - 2), tw = ld_as_float(h + E - 1);
+  // centers = ((sigmoid*2 - 0.5) + g) * stride / center_scaler      (_architecture.py:146-147)
+  float c = __fadd_rn(__fsub_rn(__fmul_rn(sigmoid_f(tc), 2.0f), 0.5f), (float)g);
+  c = __fdiv_rn(__fmul_rn(c, (float)p.stride[s]), p.center_scaler);
+  // widths = (sigmoid*2)^2 * anchor                                  (_architecture.py:150)
+  float w2 = __fmul_rn(sigmoid_f(tw), 2.0f);
+  float w = __fmul_rn(__fmul_rn(w2, w2), p.anchors[s * 8 + a]);
+  c = fminf(fmaxf(c, 0.0f), p.duration);
+  w = fminf(fmaxf(w, 0.0f), p.duration);
+  o[E - 2] = c;
+  o[E - 1] = w;
+}
+
+// ------------------------------------------------------------------------------------ NMS
+constexpr int NMS_THREADS = 256;
+constexpr int NMS_MAXP = 1024;
+
+__device__ __forceinline__ uint32_t sortable_bits(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// in-place ascending bitonic sort of n_pad (power of two) 64-bit keys in shared memory
+__device__ void bitonic_sort_u64(unsigned long long* keys, int n_pad) {
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NMS_THREADS)
+nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float conf_thr, float duration,
+           float box_h, int return_start_end, int32_t* __restrict__ keep_out, int32_t* __restrict__ n_keep_out,
+           float* __restrict__ conf_out, float* __restrict__ boxes_out, float* __restrict__ seg_rows,
+           int32_t* __restrict__ n_seg_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int E = 3 + nc;
+  const int W = (P + 31) >> 5;  // mask words per row
+  int n_pad = 32;
+  while (n_pad < P) n_pad <<= 1;
+
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);        // [n_pad]
+  float* s_conf = reinterpret_cast<float*>(keys + n_pad);                             // [P] original order
+  float* sx1 = s_conf + n_pad;                                                        // [P] sorted order
+  float* sx2 = sx1 + n_pad;
+  float* sarea = sx2 + n_pad;
+  int32_t* s_order = reinterpret_cast<int32_t*>(sarea + n_pad);                       // [P]
+  int32_t* s_keep = s_order + n_pad;                                                  // [P] kept sorted positions
+  uint32_t* mask = reinterpret_cast<uint32_t*>(s_keep + n_pad);                       // [P][W]
+  __shared__ int s_nkeep, s_nseg;
+
+  const float* pb = preds + (int64_t)b * P * E;
+  const float y2 = fminf(fmaxf(box_h, 0.0f), duration);  // coords.clip(0, sample_duration) also hits y2
+
+  // 1. boxes + confidence (inference.py:55-64)
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    if (i < P) {
+      const float* r = pb + (int64_t)i * E;
+      const float c = r[E - 2], w = r[E - 1];
+      const float hw = __fdiv_rn(w, 2.0f);
+      const float x1 = fminf(fmaxf(__fsub_rn(c, hw), 0.0f), duration);
+      const float x2 = fminf(fmaxf(__fadd_rn(c, hw), 0.0f), duration);
+      float mx = r[1];
+      for (int j = 1; j < nc; ++j) mx = fmaxf(mx, r[1 + j]);
+      float sum = 0.0f;
+      for (int j = 0; j < nc; ++j) sum = __fadd_rn(sum, expf(__fsub_rn(r[1 + j], mx)));
+      // softmax max element = exp(0) * (1/sum); confidence = class_score * objectness
+      const float cf = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoid_f(r[0]));
+      s_conf[i] = cf;
+      if (conf_out) conf_out[(int64_t)b * P + i] = cf;
+      if (boxes_out) {
+        boxes_out[((int64_t)b * P + i) * 2 + 0] = x1;
+        boxes_out[((int64_t)b * P + i) * 2 + 1] = x2;
+      }
+      // descending score, ascending index  ->  ascending key
+      keys[i] = ((unsigned long long)(~sortable_bits(cf)) << 32) | (unsigned)i;
+    } else {
+      keys[i] = ~0ull;
+    }
+  }
+  __syncthreads();
+  bitonic_sort_u64(keys, n_pad);
+
+  // 2. gather boxes in sorted order
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int o = (int)(keys[i] & 0xffffffffu);
+    s_order[i] = o;
+    const float* r = pb + (int64_t)o * E;
+    const float c = r[E - 2], w = r[E - 1];
+    const float hw = __fdiv_rn(w, 2.0f);
+    const float x1 = fminf(fmaxf(__fsub_rn(c, hw), 0.0f), duration);
+    const float x2 = fminf(fmaxf(__fadd_rn(c, hw), 0.0f), duration);
+    sx1[i] = x1;
+    sx2[i] = x2;
+    sarea[i] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, 0.0f));
+  }
+  __syncthreads();
+
+  // 3. suppression bit matrix: bit (i, j) set iff j > i and iou(i, j) > thr   (torchvision nms_kernel_impl)
+  const float hh = fmaxf(0.0f, __fsub_rn(y2, 0.0f));
+  for (int t = threadIdx.x; t < P * W; t += blockDim.x) {
+    const int i = t / W, wj = t % W;
+    uint32_t bits = 0;
+    const int j0 = wj << 5;
+    if (j0 + 31 > i) {
+      const float x1i = sx1[i], x2i = sx2[i], ai = sarea[i];
+      for (int k = 0; k < 32; ++k) {
+        const int j = j0 + k;
+        if (j > i && j < P) {
+          const float ww = fmaxf(0.0f, __fsub_rn(fminf(x2i, sx2[j]), fmaxf(x1i, sx1[j])));
+          const float inter = __fmul_rn(ww, hh);
+          const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, sarea[j]), inter));
+          if ((double)ovr > iou_thr) bits |= (1u << k);
+        }
+      }
+    }
+    mask[t] = bits;
+  }
+  __syncthreads();
+
+  // 4. greedy scan by one warp: lane l owns removed-word l
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    uint32_t removed = 0;
+    int nk = 0;
+    for (int i = 0; i < P; ++i) {
+      const uint32_t wrd = __shfl_sync(0xffffffffu, removed, i >> 5);
+      if (!((wrd >> (i & 31)) & 1u)) {
+        if (lane == 0) s_keep[nk] = i;
+        ++nk;
+        if (lane < W) removed |= mask[i * W + lane];
+      }
+    }
+    if (lane == 0) s_nkeep = nk;
+  }
+  __syncthreads();
+  const int nk = s_nkeep;
+  for (int i = threadIdx.x; i < P; i += blockDim.x)
+    keep_out[(int64_t)b * P + i] = (i < nk) ? s_order[s_keep[i]] : -1;
+  if (threadIdx.x == 0) n_keep_out[b] = nk;
+  if (seg_rows == nullptr) return;
+
+  // 5. confidence filter + per-clip sort by centre (inference.py:85-99)
+  if (threadIdx.x == 0) s_nseg = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    const int o = s_order[s_keep[i]];
+    if (s_conf[o] > conf_thr) {
+      const int slot = atomicAdd(&s_nseg, 1);
+      const float c = pb[(int64_t)o * E + E - 2];
+      // ascending centre; ties broken by keep rank (the reference's argsort is not declared stable)
+      keys[slot] = ((unsigned long long)sortable_bits(c) << 32) | (unsigned)i;
+    }
+  }
+  __syncthreads();
+  const int ns = s_nseg;
+  bitonic_sort_u64(keys, n_pad);
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    const int o = s_order[s_keep[(int)(keys[i] & 0xffffffffu)]];
+    const float* r = pb + (int64_t)o * E;
+    float* out = seg_rows + ((int64_t)b * P + i) * 5;
+    int label = 0;
+    float best = r[1];
+    for (int j = 1; j < nc; ++j)
+      if (r[1 + j] > best) {
+        best = r[1 + j];
+        label = j;
+      }
+    float c = r[E - 2], w = r[E - 1];
+    if (return_start_end) {  // inference.py:102-106: start = c - w/2 ; end = start + w ; clip
+      const float st = __fsub_rn(c, __fdiv_rn(w, 2.0f));
+      const float en = __fadd_rn(st, w);
+      c = fminf(fmaxf(st, 0.0f), duration);
+      w = fminf(fmaxf(en, 0.0f), duration);
+    }
+    out[0] = s_conf[o];
+    out[1] = r[0];
+    out[2] = (float)label;
+    out[3] = c;
+    out[4] = w;
+  }
+  if (threadIdx.x == 0) n_seg_out[b] = ns;
+}
+
+// single-CTA exclusive scan over per-clip counts + gather into the reference's return layout
+__global__ void compact_kernel(const float* __restrict__ seg_rows, const int32_t* __restrict__ n_seg, int64_t B,
+                               int P, float* __restrict__ segments, int64_t* __restrict__ batch_idxs,
+                               int64_t* __restrict__ total) {
+  __shared__ long long s_base;
+  __shared__ int s_part[32];
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t b0 = 0; b0 < B; b0 += blockDim.x) {
+    const int64_t b = b0 + threadIdx.x;
+    const int n = (b < B) ? n_seg[b] : 0;
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_part[w];
+    int chunk_total = 0;
+    for (int w = 0; w < nw; ++w) chunk_total += s_part[w];
+    const long long base = s_base + woff + incl - n;
+    for (int i = 0; i < n; ++i) {
+      const float* src = seg_rows + (b * P + i) * 5;
+      float* dst = segments + (base + i) * 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) dst[k] = src[k];
+      batch_idxs[base + i] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total[0] = s_base;
+}
+
+}  // namespace yad
+
+extern "C" {
+
+int yad_decode(const void* const* heads, const int32_t* G, const int32_t* ld, const int32_t* stride,
+               int32_t n_scales, int32_t dtype, const float* anchors, int32_t A, int32_t nc,
+               float center_scaler, float duration, int64_t B, float* preds, yad_stream_t stream) {
+  YAD_CHECK_ARG(n_scales >= 1 && n_scales <= 4, "yad_decode: n_scales=%d not in [1,4]", n_scales);
+  YAD_CHECK_ARG(A >= 1 && A <= 8, "yad_decode: A=%d not in [1,8]", A);
+  YAD_CHECK_ARG(nc >= 1 && B >= 0 && preds, "yad_decode: bad nc/B/preds");
+  YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_decode: bad dtype %d", dtype);
+  if (B == 0) return YAD_OK;
+  yad::DecodeParams p;
+  int rows = 0;
+  for (int s = 0; s < 4; ++s) {
+    p.head[s] = nullptr;
+    p.G[s] = p.ld[s] = p.stride[s] = p.row0[s] = 0;
+  }
+  for (int s = 0; s < n_scales; ++s) {
+    YAD_CHECK_ARG(heads[s] && G[s] > 0 && ld[s] >= A * (3 + nc), "yad_decode: scale %d: bad head/G/ld", s);
+    p.head[s] = heads[s];
+    p.G[s] = G[s];
+    p.ld[s] = ld[s];
+    p.stride[s] = stride[s];
+    p.row0[s] = rows;
+    rows += G[s] * A;
+    for (int a = 0; a < A; ++a) p.anchors[s * 8 + a] = anchors[s * A + a];
+  }
+  p.n_scales = n_scales;
+  p.A = A;
+  p.nc = nc;
+  p.rows_total = rows;
+  p.center_scaler = center_scaler;
+  p.duration = duration;
+  const int64_t n = B * rows;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (dtype == YAD_F32)
+    yad::decode_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(p, B, preds);
+  else
+    yad::decode_kernel<__nv_bfloat16><<<blocks, threads, 0, (cudaStream_t)stream>>>(p, B, preds);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_nms(const float* preds, int64_t B, int32_t P, int32_t nc, double iou_thr, float conf_thr,
+            float duration, float box_h, int32_t return_start_end, int32_t* keep, int32_t* n_keep,
+            float* conf, float* boxes, float* seg_rows, int32_t* n_seg, yad_stream_t stream) {
+  YAD_CHECK_ARG(preds && keep && n_keep, "yad_nms: null preds/keep/n_keep");
+  YAD_CHECK_ARG(P >= 1 && P <= yad::NMS_MAXP, "yad_nms: P=%d not in [1,%d]", P, yad::NMS_MAXP);
+  YAD_CHECK_ARG(nc >= 1 && nc <= 64, "yad_nms: nc=%d not in [1,64]", nc);
+  YAD_CHECK_ARG((seg_rows == nullptr) == (n_seg == nullptr), "yad_nms: seg_rows and n_seg go together");
+  if (B == 0) return YAD_OK;
+  int n_pad = 32;
+  while (n_pad < P) n_pad <<= 1;
+  const int W = (P + 31) / 32;
+  const size_t smem = (size_t)n_pad * 8 + (size_t)n_pad * 4 * 6 + (size_t)P * W * 4;
+  if (smem > 48 * 1024)
+    YAD_CUDA(cudaFuncSetAttribute(yad::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  yad::nms_kernel<<<(unsigned)B, yad::NMS_THREADS, smem, (cudaStream_t)stream>>>(
+      preds, P, nc, iou_thr, conf_thr, duration, box_h, return_start_end, keep, n_keep, conf, boxes, seg_rows,
+      n_seg);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_compact_segments(const float* seg_rows, const int32_t* n_seg, int64_t B, int32_t P, float* segments,
+                         int64_t* batch_idxs, int64_t* total, yad_stream_t stream) {
+  YAD_CHECK_ARG(seg_rows && n_seg && segments && batch_idxs && total, "yad_compact_segments: null pointer");
+  yad::compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_rows, n_seg, B, P, segments, batch_idxs, total);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+}  // extern "C"

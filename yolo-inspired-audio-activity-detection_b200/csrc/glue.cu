@@ -1,0 +1,137 @@
+// Neck glue on NHWC tensors (dtype f32 | bf16, fp32 math): H-mean, bilinear x2 / x0.5 along W,
+// cascaded 5-wide max pools.  Every kernel writes into a channel slice of its destination so the
+// reference's torch.cat calls (modules/_common.py:183,210,213,257-258) never materialise.
+#include "common.cuh"
+
+namespace yad {
+
+// adaptive_avg_pool2d(x, (1, W))  -  modules/_common.py:248-252
+template <typename T>
+__global__ void hmean_kernel(const T* __restrict__ in, int64_t B, int H, int W, int C, int ld_in,
+                             T* __restrict__ out, int ld_out, int co_off) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = B * W * C;
+  if (gid >= n) return;
+  const int c = (int)(gid % C);
+  const int64_t bw = gid / C;
+  const int w = (int)(bw % W);
+  const int64_t b = bw / W;
+  float acc = 0.0f;
+  for (int h = 0; h < H; ++h) acc += ld_as_float(in + ((b * H + h) * W + w) * (int64_t)ld_in + c);
+  st_from_float(out + (b * W + w) * (int64_t)ld_out + co_off + c, acc / (float)H);
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) along W only - modules/_common.py:173-174,181-182
+//   x2 : out[2k] = .75 x[k] + .25 x[max(k-1,0)] ; out[2k+1] = .75 x[k] + .25 x[min(k+1,W-1)]
+//   x.5: out[k]  = .5 x[2k] + .5 x[2k+1]
+template <typename T>
+__global__ void resize_w_kernel(const T* __restrict__ in, int64_t B, int W, int C, int ld_in, int ci_off, int up,
+                                T* __restrict__ out, int ld_out, int co_off) {
+  const int Wo = up ? 2 * W : W / 2;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = B * Wo * C;
+  if (gid >= n) return;
+  const int c = (int)(gid % C);
+  const int64_t bw = gid / C;
+  const int wo = (int)(bw % Wo);
+  const int64_t b = bw / Wo;
+  const T* row = in + b * W * (int64_t)ld_in + ci_off + c;
+  float v;
+  if (up) {
+    const int k = wo >> 1;
+    const int k2 = (wo & 1) ? min(k + 1, W - 1) : max(k - 1, 0);
+    // torch: w0 * x[i0] + w1 * x[i1] with i0 < i1 (lambda = .25 / .75)
+    const float a = ld_as_float(row + (int64_t)k * ld_in), nb = ld_as_float(row + (int64_t)k2 * ld_in);
+    v = (wo & 1) ? (0.75f * a + 0.25f * nb) : (0.25f * nb + 0.75f * a);
+  } else {
+    v = 0.5f * ld_as_float(row + (int64_t)(2 * wo) * ld_in) + 0.5f * ld_as_float(row + (int64_t)(2 * wo + 1) * ld_in);
+  }
+  st_from_float(out + (b * Wo + wo) * (int64_t)ld_out + co_off + c, v);
+}
+
+// three cascaded MaxPool2d(k=5, s=1, p=2) at H=1 == running max over windows of 5 / 9 / 13 (-inf padding)
+template <typename T>
+__global__ void sppf_kernel(const T* __restrict__ in, int64_t B, int W, int C, int ld_in, int ci_off,
+                            T* __restrict__ out, int ld_out, int co_off) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = B * W * C;
+  if (gid >= n) return;
+  const int c = (int)(gid % C);
+  const int64_t bw = gid / C;
+  const int w = (int)(bw % W);
+  const int64_t b = bw / W;
+  const T* row = in + b * W * (int64_t)ld_in + ci_off + c;
+  float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  for (int d = -6; d <= 6; ++d) {
+    const int x = w + d;
+    if (x < 0 || x >= W) continue;
+    const float v = ld_as_float(row + (int64_t)x * ld_in);
+    const int ad = d < 0 ? -d : d;
+    if (ad <= 2) m1 = fmaxf(m1, v);
+    if (ad <= 4) m2 = fmaxf(m2, v);
+    m3 = fmaxf(m3, v);
+  }
+  T* o = out + (b * W + w) * (int64_t)ld_out + co_off + c;
+  st_from_float(o, m1);
+  st_from_float(o + C, m2);
+  st_from_float(o + 2 * C, m3);
+}
+
+}  // namespace yad
+
+#define YAD_DISPATCH_DTYPE(dtype, KERNEL, ...)                                              \
+  if ((dtype) == YAD_F32) {                                                                 \
+    using T = float;                                                                        \
+    KERNEL<T><<<blocks, threads, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                   \
+  } else {                                                                                  \
+    using T = __nv_bfloat16;                                                                \
+    KERNEL<T><<<blocks, threads, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                   \
+  }
+
+extern "C" {
+
+int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, int32_t C, int32_t ld_in, void* out,
+              int32_t ld_out, int32_t co_off, yad_stream_t stream) {
+  YAD_CHECK_ARG(in && out && H >= 1 && W >= 1 && C >= 1 && ld_in >= C && ld_out >= co_off + C,
+                "yad_hmean: bad arguments");
+  YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_hmean: bad dtype %d", dtype);
+  const int64_t n = B * W * C;
+  if (n == 0) return YAD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  YAD_DISPATCH_DTYPE(dtype, yad::hmean_kernel, (const T*)in, B, H, W, C, ld_in, (T*)out, ld_out, co_off);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
+                 int32_t up, void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream) {
+  YAD_CHECK_ARG(in && out && W >= 1 && C >= 1 && ld_in >= ci_off + C && ld_out >= co_off + C,
+                "yad_resize_w: bad arguments");
+  YAD_CHECK_ARG(up || (W % 2 == 0), "yad_resize_w: x0.5 needs even W (got %d)", W);
+  YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_resize_w: bad dtype %d", dtype);
+  const int Wo = up ? 2 * W : W / 2;
+  const int64_t n = B * Wo * C;
+  if (n == 0) return YAD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  YAD_DISPATCH_DTYPE(dtype, yad::resize_w_kernel, (const T*)in, B, W, C, ld_in, ci_off, up, (T*)out, ld_out, co_off);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
+                   void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream) {
+  YAD_CHECK_ARG(in && out && W >= 1 && C >= 1 && ld_in >= ci_off + C && ld_out >= co_off + 3 * C,
+                "yad_sppf_pools: bad arguments");
+  YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_sppf_pools: bad dtype %d", dtype);
+  const int64_t n = B * W * C;
+  if (n == 0) return YAD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  YAD_DISPATCH_DTYPE(dtype, yad::sppf_kernel, (const T*)in, B, W, C, ld_in, ci_off, (T*)out, ld_out, co_off);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+}  // extern "C"
