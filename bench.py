@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py - audio-seconds/sec of the detection hot path on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
+
+A "step" = one pass of the whole hot path over one batch of synthetic 60 s clips per GPU:
+PCM -> fused log-mel/MFCC frontend -> stem + ResNet + RepBi-PAN neck (deploy form, bf16 tcgen05) -> anchor
+decode -> per-clip segment NMS.  Prints ONE JSON line (rank 0).  Per-GPU work is fixed (weak scaling);
+clips are sharded across ranks with no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CLIP_SECONDS = 60.0
+CLIP_SAMPLES = 1323000
+FRONTEND_BYTES_PER_CLIP = 4 * CLIP_SAMPLES + 2 * 32 * 960 * 4          # PCM read + feature write
+CNN_FLOP_PER_CLIP = 2 * 1150923632                                     # useful MACs, deploy form
+METRIC = "audio-seconds/sec (mel+RepVGG fwd+decode/NMS)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([s.strip() for s in o.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def synth_clips_device(B: int, dev, seed: int):
+    """[B,1,L] f32 synthetic clips generated on the device: 0.1*noise + 4 gated tone bursts per clip, every 8th
+    clip with a digital-silence tail (same recipe as tests/golden/synth.py, CUDA generator)."""
+    import math
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.empty(B, 1, CLIP_SAMPLES, device=dev)
+    t = torch.arange(CLIP_SAMPLES, device=dev, dtype=torch.float32) / 22050.0
+    chunk = 32
+    for b0 in range(0, B, chunk):
+        n = min(chunk, B - b0)
+        s = 0.1 * torch.randn(n, CLIP_SAMPLES, device=dev, generator=g)
+        f = torch.rand(n, 4, device=dev, generator=g) * 6900 + 100
+        t0 = torch.rand(n, 4, device=dev, generator=g) * 48
+        d = torch.rand(n, 4, device=dev, generator=g) * 10 + 1
+        for j in range(4):
+            m = (t[None] >= t0[:, j:j + 1]) & (t[None] < (t0[:, j:j + 1] + d[:, j:j + 1]))
+            s += 0.5 * torch.sin(2 * math.pi * f[:, j:j + 1] * t[None]) * m
+        x[b0:b0 + n, 0] = s
+    for b in range(7, B, 8):
+        cut = int((0.35 + 0.55 * ((b * 2654435761) % 1000) / 1000.0) * CLIP_SAMPLES)
+        x[b, 0, cut:] = 0
+    return x
+
+
+def build_model(dev, dtype="bf16", deploy=True):
+    import synth
+    import yad_b200
+    m = yad_b200.AudioDetectionNetwork(2, compute_dtype=dtype)
+    skip = {"sm_anchors", "md_anchors", "lg_anchors", "taper_window"}
+    layout = {k: tuple(v.shape) for k, v in m.state_dict().items()
+              if k not in skip and "tfmr" not in k and "resampler" not in k}
+    full = dict(m.state_dict())
+    full.update(synth.synth_state_dict(layout, 42))
+    m.load_state_dict(full)
+    if deploy:
+        m.inference()
+    return m.eval().to(dev), full
+
+
+def time_stages(model, x, reps=3):
+    """Per-stage device time (ms) with CUDA events on the launching stream, outside the timed region."""
+    eng = model._engine()
+    B, _, L = x.shape
+    plan = eng._plan((B, L))
+    out = {}
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        best = []
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+            best.append(a.elapsed_time(b))
+        return sum(best) / len(best), r
+
+    import ctypes as C
+    from yad_b200 import _lib
+    T = eng.frames(L)
+    mel = plan.get("mel")
+    xc = x.contiguous()
+
+    def fe_a():
+        _lib.check(eng.lib.yad_frontend_mel_power(xc.data_ptr(), B, L, eng.rs_P, eng.rs_O, eng.rs_width, eng.rs_taps.data_ptr(),
+                                                  eng.rs_base.data_ptr(), eng.rs_window_len, eng.win.data_ptr(), eng.tw.data_ptr(),
+                                                  eng.fb_val.data_ptr(), eng.fb_bin.data_ptr(), eng.fb_start.data_ptr(),
+                                                  mel.data_ptr(), T, eng._stream()), "fe_a")
+    out["frontend_mel_ms"], _ = timed(fe_a)
+    out["frontend_ms"], xs = timed(lambda: eng.run_frontend(x, plan))
+
+    def stem():
+        c1 = plan["c1"]
+        _lib.check(eng.lib.yad_conv_stem(xs.data_ptr(), B, 32, T, eng.stem_w.data_ptr(), c1.data_ptr(), eng.dtype, eng._stream()), "stem")
+    out["stem_ms"], _ = timed(stem)
+    out["cnn_ms"], heads = timed(lambda: eng.run_cnn(xs, plan))
+    L_res = -(-eng.rs_P * L // eng.rs_O)
+    out["decode_ms"], preds = timed(lambda: eng.run_decode(heads, B, T, L_res))
+    import yad_b200
+    out["nms_ms"], _ = timed(lambda: yad_b200.nms_raw(preds, 0.1, 0.2))
+    return out
+
+
+def cpu_baseline(sample_clips=8, runs=3):
+    """The reference algorithm (oracle port: torch CPU fp32, all host threads) on a bounded sample."""
+    import synth
+    from oracle import ref_port as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, full = build_model(torch.device("cpu"), deploy=False)
+    sd = {k: v.cpu() for k, v in full.items()}
+    x = synth.synth_clips(sample_clips, CLIP_SAMPLES, seed=1000, silence_tail_every=8)
+    times = []
+    with torch.no_grad():
+        for i in range(runs + 1):
+            t0 = time.perf_counter()
+            out = O.forward(x, sd, 2)
+            try:
+                O.process_model_outputs(out, 0.1, 0.2)
+            except ValueError:
+                pass
+            if i:
+                times.append(time.perf_counter() - t0)
+    t = sorted(times)[len(times) // 2]
+    return {"value": CLIP_SECONDS * sample_clips / t, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_clips} synthetic 60 s clips, eval-mode train-form fp32 (the path inference.py runs), "
+                      f"forward + process_model_outputs, median of {runs} runs, {t:.2f} s/run"}, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    sample = 8
+    import synth
+    from oracle import ref_port as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, full = build_model(torch.device("cpu"), deploy=False)
+    sd = {k: v.cpu() for k, v in full.items()}
+    x = synth.synth_clips(sample, CLIP_SAMPLES, seed=1000, silence_tail_every=8)
+    budget = time.perf_counter() + 240
+    with torch.no_grad():
+        for _ in range(min(warm, 1)):
+            O.forward(x, sd, 2)
+        t0 = time.perf_counter(); done = 0
+        for _ in range(steps):
+            out = O.forward(x, sd, 2)
+            try:
+                O.process_model_outputs(out, 0.1, 0.2)
+            except ValueError:
+                pass
+            done += 1
+            if time.perf_counter() > budget:
+                break
+        dt = time.perf_counter() - t0
+    v = CLIP_SECONDS * sample * done / dt
+    line = {"metric": METRIC, "value": v, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": done, "warmup": min(warm, 1),
+            "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "full pipeline: PCM -> log-mel/MFCC -> ResNet + RepBi-PAN -> decode -> NMS, "
+                                   f"{sample} clips x 60 s per step (bounded sample of the GPU arm's workload)"},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{sample} clips/step x {done} steps, oracle port (torch CPU fp32) of the reference path"},
+            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="clips per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+    import yad_b200
+    from yad_b200 import _lib, parallel
+
+    W, K, B = max(3, args.warmup), max(1, args.steps), args.batch
+    model, _ = build_model(dev, args.dtype, deploy=True)
+    x = synth_clips_device(B, dev, seed=1000 + 7919 * rank)       # this rank's shard of the global batch
+
+    def step(inp):
+        preds = model(inp, combine_scales=True)
+        return yad_b200.nms_raw(preds, 0.1, 0.2)
+
+    for _ in range(W):
+        step(x)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count
+    step(x)
+    launches_per_step = _lib.launch_count - n0
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        r = step(x)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    sampler.stop_flag.set()
+    sampler.join(timeout=3)
+    value = CLIP_SECONDS * B * world * K / (ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    xh = torch.empty((B, 1, CLIP_SAMPLES), dtype=torch.float32, pin_memory=True)
+    xh.copy_(x)
+    xd = torch.empty_like(x)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        preds = model(xd, combine_scales=True)
+        try:
+            seg, bidx = yad_b200.process_model_outputs(preds, 0.1, 0.2)
+            return seg.cpu(), bidx.cpu()
+        except ValueError:
+            return None, None
+    e2e_step()
+    torch.cuda.synchronize()
+    Ke = max(1, min(K, 5))
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    d2h = 0
+    for _ in range(Ke):
+        seg, bidx = e2e_step()
+        if seg is not None:
+            d2h = seg.numel() * 4 + bidx.numel() * 8 + 8
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    e2e = {"value": CLIP_SECONDS * B * world * Ke / (ms_e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": B * CLIP_SAMPLES * 4,
+           "d2h_bytes_per_step": d2h, "steps": Ke}
+
+    if rank == 0:
+        peaks = load_peaks()
+        st = time_stages(model, x)
+        conv_ms = st["cnn_ms"]
+        fe_ms = st["frontend_mel_ms"]
+        if conv_ms >= st["frontend_ms"]:
+            ach = CNN_FLOP_PER_CLIP * B / (conv_ms / 1e3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"kernel": "conv stack (stem + tcgen05 implicit-GEMM convs + neck glue), whole CNN stage", "bound": "tensor",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained)"}
+        else:
+            ach = FRONTEND_BYTES_PER_CLIP * B / (fe_ms / 1e3) / 1e9
+            roof = {"kernel": "frontend_mel_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"]}
+        roof["frontend_hbm"] = {"achieved_gbs": FRONTEND_BYTES_PER_CLIP * B / (fe_ms / 1e3) / 1e9,
+                                "frac": FRONTEND_BYTES_PER_CLIP * B / (fe_ms / 1e3) / 1e9 / peaks["hbm_gbs"]}
+        roof["cnn_tensor"] = {"achieved_tflops": CNN_FLOP_PER_CLIP * B / (conv_ms / 1e3) / 1e12,
+                              "frac": CNN_FLOP_PER_CLIP * B / (conv_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]}
+        line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                "data": "synthetic",
+                "config": {"workload": f"full pipeline, deploy-form (reparameterised) net, {B} clips x 60 s per GPU per step: PCM f32 -> "
+                                       "fused resample/log-mel/MFCC frontend -> stem + ResNet-18 + RepBi-PAN (tcgen05 implicit GEMM) -> "
+                                       "anchor decode -> per-clip segment NMS (BASELINE configs[1]+[2] chained)",
+                           "clips_per_gpu": B, "clip_seconds": CLIP_SECONDS, "num_classes": 2,
+                           "l2_policy": "inputs (2.7 GB PCM + 1.3 GB activations per step) are larger than the 126 MB L2",
+                           "parallelism": f"clip-sharded x{world}, no data-path collective"},
+                "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+                "clocks": sampler.summary(), "roofline": roof, "stages_ms": st}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"], _ = cpu_baseline()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,7 +114,8 @@ int yad_conv_simt(const yad_conv_desc* d, int32_t dtype, const void* in, const v
  * out_dtype: YAD_BF16 or YAD_F32.  */
 int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad,
                 const float* bias, const void* residual, void* out, int32_t out_dtype,
-                yad_stream_t stream);
+                float* out2_f32 /* optional fp32 copy of the output, pitch ld_out2, may be NULL */,
+                int32_t ld_out2, yad_stream_t stream);
 
 /* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
  * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5
@@ -128,6 +129,12 @@ int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C,
  * slices co_off, co_off+C, co_off+2C of out. */
 int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
                    void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
+
+/* RepVGG train-form merge (modules/_common.py:90-95): out = act(a + b [+ scale*x + shift]); a, b are the
+ * activated 3x3 / 1x1 branches [npix, ld_ab]; (scale, shift) the eval-mode identity BatchNorm (x may be NULL). */
+int yad_repvgg_merge(const void* a, const void* b, const void* x, const float* scale, const float* shift,
+                     int32_t dtype, int64_t npix, int32_t C, int32_t ld_ab, int32_t ld_x, void* out, int32_t ld_out,
+                     int32_t co_off, int32_t act, yad_stream_t stream);
 
 /* ------------------------------------------------------------------ anchor decode
  * Replaces get_scale_pred + combine (modules/_architecture.py:113-156).

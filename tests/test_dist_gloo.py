@@ -1,0 +1,63 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes shard a clip range with no data-path collective."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from yad_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = parallel.shard_bounds(n_items, rank, world)
+    # stand-in for the per-rank pipeline: every clip i yields (i % 3) segments
+    local_bidx = torch.cat([torch.full((i % 3,), i - lo, dtype=torch.int64) for i in range(lo, hi)] or [torch.zeros(0, dtype=torch.int64)])
+    counts = parallel.gather_counts(local_bidx.numel())
+    gl = parallel.globalize_batch_idxs(local_bidx, n_items, rank, world)
+    t = parallel.max_over_ranks(10.0 + rank)
+    q.put((rank, lo, hi, counts, gl.tolist(), t))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [7, 64])
+def test_two_rank_sharding(n_items):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_items, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    covered = []
+    for rank, lo, hi, counts, gl, t in res:
+        covered += list(range(lo, hi))
+        assert t == 11.0                                   # max over ranks
+        assert counts == [r[4].__len__() for r in res]     # every rank sees every count
+    assert covered == list(range(n_items))                 # disjoint, complete, contiguous
+    merged = [i for r in res for i in r[4]]
+    assert merged == [i for i in range(n_items) for _ in range(i % 3)]
+
+
+def test_shard_bounds_properties():
+    for n in (0, 1, 5, 512, 65536):
+        for w in (1, 2, 4, 8):
+            b = [parallel.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_bounds(10, 2, 2)

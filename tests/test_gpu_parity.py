@@ -1,0 +1,313 @@
+"""Parity of the sm_100a kernels against the CPU oracle and the reference-made golden fixtures.
+All calls go through the C ABI (ctypes) - via the host package or directly.  Run with -m gpu on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+import yad_b200
+from oracle import ref_port as O
+from yad_b200 import _lib
+from yad_b200._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvDesc
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.fixture(scope="module")
+def models(cuda_dev, ref_state_dict):
+    out = {}
+    for form in ("train", "deploy"):
+        for dt in ("f32", "bf16"):
+            m = yad_b200.AudioDetectionNetwork(2, compute_dtype=dt)
+            m.load_state_dict(ref_state_dict)
+            if form == "deploy":
+                m.inference()
+            out[(form, dt)] = m.eval().to(cuda_dev)
+    return out
+
+
+# ------------------------------------------------------------------ frontend (S1)
+def _check_frontend(taps, fe, atol_ch0=2e-4):
+    mel, rmel = taps["mel"].cpu().numpy(), fe["mel"].numpy()
+    np.testing.assert_allclose(mel, rmel, rtol=2e-4, atol=1e-6)            # fp32 FFT vs MKL rfft
+    np.testing.assert_allclose(taps["meldb"].cpu().numpy(), fe["meldb"].numpy(), atol=2e-3)
+    np.testing.assert_allclose(taps["mfcc"].cpu().numpy(), fe["mfcc"].numpy(), atol=5e-3)   # pre-dB MFCC
+    xs, rxs = taps["x_spectral"].cpu().numpy(), fe["x_spectral"].numpy()
+    np.testing.assert_allclose(xs[:, 0], rxs[:, 0], atol=atol_ch0)          # standardised dB-mel
+    # channel 1 = dB of signed MFCCs: log of values that cross zero -> quantile criterion, stated:
+    d = np.abs(xs[:, 1] - rxs[:, 1])
+    assert np.quantile(d, 0.99) < 0.1, np.quantile(d, 0.99)
+    assert d.mean() < 5e-3, d.mean()
+
+
+def test_frontend_short_clips_vs_oracle_and_golden(models, gold, ref_state_dict, cuda_dev):
+    x = synth.synth_clips(3, 22050 * 6, seed=1000, silence_tail_every=3)
+    taps = {}
+    models[("train", "f32")](x.to(cuda_dev), combine_scales=True, taps=taps)
+    _check_frontend(taps, O.frontend(x, ref_state_dict))
+    g = gold("short_clips")
+    np.testing.assert_allclose(taps["mel"].cpu().numpy(), g["mel"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(taps["x_spectral"].cpu().numpy()[:, 0], g["x_spectral"][:, 0], atol=2e-4)
+
+
+def test_frontend_full_clip_and_ragged_lengths(models, gold, ref_state_dict, cuda_dev):
+    m = models[("train", "f32")]
+    x = synth.synth_clips(1, 1323000, seed=2000, silence_tail_every=0)
+    taps = {}
+    m(x.to(cuda_dev), combine_scales=True, taps=taps)
+    assert taps["x_spectral"].shape == (1, 2, 32, 960)
+    np.testing.assert_allclose(taps["x_spectral"].cpu().numpy()[:, 0], gold("full_clip")["x_spectral"][:, 0], atol=2e-4)
+    # ragged: a length that is neither a whole number of hops nor of 8-frame groups (T = 61)
+    xr = synth.synth_clips(2, 84321, seed=3000, silence_tail_every=2)
+    taps = {}
+    m(xr.to(cuda_dev), combine_scales=True, taps=taps)
+    _check_frontend(taps, O.frontend(xr, ref_state_dict))
+
+
+# ------------------------------------------------------------------ convolutions
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad, act, residual
+    (2, 8, 48, 64, 64, 3, (1, 1), 1, ACT_RELU, True),       # layer1
+    (2, 16, 96, 64, 64, 7, (2, 2), 3, ACT_RELU, False),     # stem conv2
+    (3, 8, 48, 64, 128, 3, (2, 2), 1, ACT_RELU, False),     # layer2.0.conv1
+    (3, 8, 48, 64, 128, 1, (2, 2), 0, ACT_NONE, False),     # downsample 1x1 s2
+    (2, 2, 12, 256, 256, 3, (1, 1), 1, ACT_RELU, True),     # layer3
+    (5, 1, 6, 512, 512, 3, (1, 1), 1, ACT_RELU, True),      # layer4 (H = 1: top/bottom taps are padding)
+    (4, 1, 24, 128, 15, 3, (1, 1), 1, ACT_LRELU, False),    # RepVGG 128 -> 15 head
+    (4, 1, 24, 15, 128, 3, (1, 2), 1, ACT_LRELU, False),    # conv2_downsample (stride (1,2), Cin = 15)
+    (4, 1, 12, 512, 64, 1, (1, 1), 0, ACT_LRELU, False),    # CSPSPPF 1x1
+    (1, 8, 240, 64, 64, 3, (1, 1), 1, ACT_RELU, True),      # full-width layer1 row tiles
+]
+
+
+def _conv_ref(x, w, b, stride, pad, act, res):
+    y = F.conv2d(x, w, b, stride=stride, padding=pad)
+    if res is not None:
+        y = y + res
+    if act == ACT_RELU:
+        y = F.relu(y)
+    elif act == ACT_LRELU:
+        y = F.leaky_relu(y, 0.2)
+    return y
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("path", ["simt_f32", "tc_bf16"])
+def test_conv_kernels(case, path, cuda_dev):
+    B, H, W, Cin, Cout, k, stride, pad, act, use_res = case
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    Ho, Wo = (H + 2 * pad - k) // stride[0] + 1, (W + 2 * pad - k) // stride[1] + 1
+    res = torch.randn(B, Cout, Ho, Wo, generator=g) if use_res else None
+    bf = path == "tc_bf16"
+    if bf:   # the oracle sees the same bf16-rounded operands; accumulation differs (fp32 both)
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+        res = res.bfloat16().float() if use_res else None
+    ref = _conv_ref(x, w, b, stride, pad, act, res)
+    td = torch.bfloat16 if bf else torch.float32
+    cin_p = (Cin + 63) // 64 * 64 if bf else Cin
+    ld_out = (Cout + 63) // 64 * 64 + 64 if bf else Cout + 3         # exercise pitch != channels and a slice offset
+    co_off = 64 if bf else 2
+    xin = torch.zeros(B, H, W, cin_p, dtype=td, device=cuda_dev)
+    xin[..., :Cin] = x.permute(0, 2, 3, 1).to(td)
+    out = torch.full((B, Ho, Wo, ld_out), 7.0, dtype=td, device=cuda_dev)
+    rin = res.permute(0, 2, 3, 1).contiguous().to(td).to(cuda_dev) if use_res else None
+    if bf and use_res:
+        rp = torch.zeros(B, Ho, Wo, (Cout + 7) // 8 * 8, dtype=td, device=cuda_dev); rp[..., :Cout] = rin; rin = rp
+    d = ConvDesc(B=B, H=H, W=W, Cin=cin_p, ld_in=cin_p, Cout=Cout, ld_out=ld_out, co_off=co_off, kh=k, kw=k, sh=stride[0],
+                 sw=stride[1], ph=pad, pw=pad, act=act, ld_res=rin.shape[3] if use_res else 0)
+    bias = b.to(cuda_dev)
+    if bf:
+        cout_p = (Cout + 15) // 16 * 16
+        wt = torch.zeros(cout_p, k, k, cin_p)
+        wt[:Cout, :, :, :Cin] = w.permute(0, 2, 3, 1)
+        wt = wt.reshape(cout_p, -1).to(td).to(cuda_dev)
+        bp = torch.zeros(cout_p, device=cuda_dev); bp[:Cout] = bias
+        out2 = torch.zeros(B, Ho, Wo, (Cout + 3) // 4 * 4, device=cuda_dev)
+        rc = lib.yad_conv_tc(C.byref(d), xin.data_ptr(), wt.data_ptr(), cout_p, bp.data_ptr(), _lib.ptr(rin), out.data_ptr(), BF16,
+                             out2.data_ptr(), out2.shape[3], _stream())
+    else:
+        wt = w.permute(2, 3, 1, 0).contiguous().to(cuda_dev)
+        rc = lib.yad_conv_simt(C.byref(d), F32, xin.data_ptr(), wt.data_ptr(), Cout, bias.data_ptr(), _lib.ptr(rin), out.data_ptr(),
+                               _stream())
+    _lib.check(rc, path)
+    torch.cuda.synchronize()
+    got = out[..., co_off:co_off + Cout].float().permute(0, 3, 1, 2).cpu()
+    if bf:
+        # fp32 copy: only accumulation order differs from the oracle -> tight; bf16 output: + one rounding (2^-8 rel)
+        got2 = out2[..., :Cout].permute(0, 3, 1, 2).cpu()
+        np.testing.assert_allclose(got2.numpy(), ref.numpy(), atol=2e-3, rtol=2e-3)
+        np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-2, rtol=1e-2)
+    else:
+        np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-4, rtol=1e-4)
+    # channels outside the written slice are untouched
+    assert torch.all(out[..., :co_off].float() == 7.0) and torch.all(out[..., co_off + Cout:].float() == 7.0)
+
+
+def test_stem_conv(cuda_dev):
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 2, 32, 96, generator=g)
+    w = torch.randn(64, 2, 7, 7, generator=g) * 0.1
+    ref = F.conv2d(x, w, None, stride=2, padding=3)
+    wt = w.permute(2, 3, 1, 0).contiguous().to(cuda_dev)
+    for dt, td, tol in ((F32, torch.float32, 1e-4), (BF16, torch.bfloat16, 2e-2)):
+        out = torch.empty(2, 16, 48, 64, dtype=td, device=cuda_dev)
+        _lib.check(lib.yad_conv_stem(x.to(cuda_dev).data_ptr(), 2, 32, 96, wt.data_ptr(), out.data_ptr(), dt, _stream()), "stem")
+        np.testing.assert_allclose(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy(), atol=tol, rtol=tol)
+
+
+# ------------------------------------------------------------------ whole network (S2/S3)
+@pytest.mark.parametrize("form", ["train", "deploy"])
+def test_network_f32_vs_golden(models, gold, form, cuda_dev):
+    g = gold("short_clips")
+    x = synth.synth_clips(3, 22050 * 6, seed=1000, silence_tail_every=3).to(cuda_dev)
+    taps = {}
+    out = models[(form, "f32")](x, combine_scales=True, taps=taps)
+    assert out.shape == (3, 63, 5)
+    pre = "head" if form == "train" else "dhead"
+    for h, n in zip(taps["heads"], ("sm", "md", "lg")):
+        np.testing.assert_allclose(h.cpu().numpy(), g[f"{pre}_{n}"], atol=5e-3)     # fp32 logits / offsets
+    np.testing.assert_allclose(out.cpu().numpy(), g[f"preds_{form}"], atol=5e-3)
+    if form == "train":
+        np.testing.assert_allclose(taps["fmaps"][0].cpu().numpy(), g["fmap1"], atol=2e-3)
+        np.testing.assert_allclose(taps["fmaps"][3].cpu().numpy(), g["fmap4"], atol=2e-3)
+    sm, md, lg = models[(form, "f32")](x)                  # tuple form, shapes of the reference
+    assert sm.shape == (3, 12, 3, 5) and md.shape == (3, 6, 3, 5) and lg.shape == (3, 3, 3, 5)
+    np.testing.assert_array_equal(torch.cat([sm.reshape(3, -1, 5), md.reshape(3, -1, 5), lg.reshape(3, -1, 5)], 1).cpu().numpy(),
+                                  out.cpu().numpy())
+
+
+@pytest.mark.parametrize("form", ["train", "deploy"])
+def test_network_bf16_vs_golden(models, gold, form, cuda_dev):
+    """bf16 tensor-core path: stated tolerance on logits 0.15 abs / mean 0.02 (SURVEY Q14 calibration: CPU bf16
+    autocast vs fp32 gives max 0.048 / mean 0.006 on the deploy form), centres 0.1 s, widths 1.5 s max."""
+    g = gold("short_clips")
+    x = synth.synth_clips(3, 22050 * 6, seed=1000, silence_tail_every=3).to(cuda_dev)
+    out = models[(form, "bf16")](x, combine_scales=True).cpu().numpy()
+    ref = g[f"preds_{form}"]
+    d = np.abs(out - ref)
+    assert d[..., :3].max() < 0.15 and d[..., :3].mean() < 0.02, (d[..., :3].max(), d[..., :3].mean())
+    assert d[..., 3].max() < 0.1, d[..., 3].max()
+    assert d[..., 4].max() < 1.5 and d[..., 4].mean() < 0.15, (d[..., 4].max(), d[..., 4].mean())
+
+
+def test_full_clip_config1_end_to_end(models, gold, cuda_dev):
+    g = gold("full_clip")
+    x = synth.synth_clips(1, 1323000, seed=2000, silence_tail_every=0).to(cuda_dev)
+    out = models[("train", "f32")](x, combine_scales=True)
+    np.testing.assert_allclose(out.cpu().numpy(), g["preds_train"], atol=5e-3)
+    outd = models[("deploy", "f32")](x, combine_scales=True)
+    np.testing.assert_allclose(outd.cpu().numpy(), g["preds_deploy"], atol=5e-3)
+
+
+def test_decode_vs_oracle(cuda_dev, ref_state_dict):
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(4)
+    heads = [torch.randn(2, G, 15, generator=g) * 3 for G in (120, 60, 30)]
+    ref = O.decode(heads, ref_state_dict, 960000, 960, 2)
+    hd = [h.to(cuda_dev).contiguous() for h in heads]
+    preds = torch.empty(2, 630, 5, device=cuda_dev)
+    hp = (C.c_void_p * 3)(*[h.data_ptr() for h in hd])
+    anc = torch.cat([ref_state_dict[f"{n}_anchors"] * 60 for n in ("sm", "md", "lg")]).tolist()
+    rc = lib.yad_decode(hp, (C.c_int32 * 3)(120, 60, 30), (C.c_int32 * 3)(15, 15, 15), (C.c_int32 * 3)(8, 16, 32), 3, F32,
+                        (C.c_float * 9)(*anc), 3, 2, 16.0, 60.0, 2, preds.data_ptr(), _stream())
+    _lib.check(rc, "decode")
+    got = preds.cpu().numpy()
+    np.testing.assert_array_equal(got[..., :3], ref.numpy()[..., :3])         # logits pass through untouched
+    np.testing.assert_allclose(got[..., 3:], ref.numpy()[..., 3:], rtol=3e-6, atol=1e-5)   # few ulp (sigmoid)
+
+
+# ------------------------------------------------------------------ NMS (S4) - bit exact
+def _check_nms(o, iou, cthr, gold_seg=None, gold_bidx=None):
+    r = yad_b200.nms_raw(o.cuda(), iou, cthr, want_taps=True)
+    conf, boxes = r["conf"].cpu(), r["boxes"].cpu()
+    rcoords, rconf = O.boxes_and_confidence(o)
+    np.testing.assert_array_equal(boxes.numpy(), rcoords[..., [0, 2]].numpy())          # fp32 box arithmetic: exact
+    np.testing.assert_allclose(conf.numpy(), rconf.numpy(), rtol=2e-6, atol=1e-9)        # exp() ulp differences only
+    B, P = conf.shape
+    keep, nk = r["keep"].cpu().numpy(), r["n_keep"].cpu().numpy()
+    for b in range(B):
+        # NMS core exact given identical (boxes, conf): oracle greedy NMS on the kernel's own confidences
+        c4 = torch.stack([boxes[b, :, 0], torch.zeros(P), boxes[b, :, 1], torch.full((P,), 10.0)], 1)
+        want = O.nms_greedy(c4.numpy(), conf[b].numpy(), iou)
+        np.testing.assert_array_equal(keep[b, :nk[b]], want)
+        assert np.all(keep[b, nk[b]:] == -1)
+    return r
+
+
+@pytest.mark.parametrize("name,B", [("b1", 1), ("b3", 3)])
+@pytest.mark.parametrize("iou,cthr", [(0.1, 0.2), (0.1, 0.65), (0.05, 0.5)])
+def test_nms_keep_sets_and_segments(gold, name, B, iou, cthr, cuda_dev):
+    g = gold("nms")
+    o = synth.synth_heads(B, 630, 2, seed=7 + B)
+    r = _check_nms(o, iou, cthr)
+    ref = g[f"keep_{name}_{iou}_{cthr}"]                       # torchvision's own keep list
+    keep, nk = r["keep"].cpu().numpy(), r["n_keep"].cpu().numpy()
+    for b in range(B):
+        np.testing.assert_array_equal(keep[b, :nk[b]] + b * 630, ref[(ref >= b * 630) & (ref < (b + 1) * 630)])
+    seg, bidx = yad_b200.process_model_outputs(o.cuda(), iou, cthr)
+    np.testing.assert_array_equal(bidx.cpu().numpy(), g[f"bidx_{name}_{iou}_{cthr}"])
+    np.testing.assert_allclose(seg.cpu().numpy(), g[f"seg_{name}_{iou}_{cthr}"], rtol=2e-6, atol=1e-7)
+
+
+def test_nms_edge_cases(gold, cuda_dev):
+    out = torch.from_numpy(gold("short_clips")["preds_train"])
+    _check_nms(out, 0.1, 0.2)                                  # P = 63 (not a multiple of 32)
+    seg, bidx = yad_b200.process_model_outputs(out.cuda(), 0.1, 0.2)
+    g = gold("nms")
+    np.testing.assert_array_equal(bidx.cpu().numpy(), g["bidx_model_0.1_0.2"])
+    np.testing.assert_allclose(seg.cpu().numpy(), g["seg_model_0.1_0.2"], rtol=2e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        yad_b200.process_model_outputs(out.cuda(), 0.1, 0.999999)      # empty result raises like the reference
+    seg2, b2 = yad_b200.process_model_outputs(out[0].cuda(), 0.1, 0.2)  # 2-D input accepted (inference.py:51-53)
+    assert torch.all(b2 == 0) and seg2.shape[0] == int((bidx == 0).sum())
+    big = synth.synth_heads(64, 630, 2, seed=99, adversarial=False)      # many clips, full-size keep-sets
+    r = _check_nms(big, 0.05, 0.5)
+    so, bo = O.process_model_outputs(big.clone(), 0.05, 0.5)
+    sg, bg = yad_b200.process_model_outputs(big.cuda(), 0.05, 0.5)
+    np.testing.assert_array_equal(bg.cpu().numpy(), bo.numpy())
+    np.testing.assert_allclose(sg.cpu().numpy(), so.numpy(), rtol=2e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------ training-side kernels (S5 exact, S6 tolerance)
+@pytest.mark.parametrize("name,G", [("sm", 120), ("md", 60), ("lg", 30)])
+def test_anchor_matching_bit_exact(gold, name, G, cuda_dev):
+    g = gold("train")
+    tg = torch.from_numpy(g["targets"]).cuda()
+    (bi, gi, ai), cl, cw = yad_b200.build_target_by_scale(tg, G, O.DEFAULT_CONFIG["anchors"][name], 5, 60, 0.5)
+    np.testing.assert_array_equal(bi.cpu().numpy(), g[f"bi_{name}"])
+    np.testing.assert_array_equal(gi.cpu().numpy(), g[f"gi_{name}"])
+    np.testing.assert_array_equal(ai.cpu().numpy(), g[f"ai_{name}"])
+    np.testing.assert_array_equal(cl.cpu().numpy(), g[f"cl_{name}"])
+    np.testing.assert_array_equal(cw.cpu().numpy(), g[f"cw_{name}"])
+    big = synth.synth_targets(300, seed=5)                       # > one scan chunk (A*T > 1024)
+    (b2, g2, a2), c2, w2 = yad_b200.build_target_by_scale(big.cuda(), G, O.DEFAULT_CONFIG["anchors"][name], 5, 60, 0.5)
+    (b3, g3, a3), c3, w3 = O.build_target_by_scale(big, G, O.DEFAULT_CONFIG["anchors"][name], 5, 60, 0.5)
+    for x, y in ((b2, b3), (g2, g3), (a2, a3), (c2, c3)):
+        np.testing.assert_array_equal(x.cpu().numpy(), y.numpy())
+    empty = yad_b200.build_target_by_scale(torch.zeros(0, 4).cuda(), G, O.DEFAULT_CONFIG["anchors"][name], 5, 60, 0.5)
+    assert empty[1].numel() == 0
+
+
+def test_fused_adam_ema(gold, cuda_dev):
+    g = gold("train")
+    p = torch.nn.Parameter(torch.from_numpy(g["adam_w0"]).clone().cuda())
+    opt = yad_b200.FusedAdamEMA([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.002, ema_momentum=0.002, ema_N=2000,
+                                use_ema=True)
+    for step in range(3):
+        p.grad.copy_(torch.from_numpy(g["adam_grads"][step]).cuda())
+        opt.step()
+    np.testing.assert_allclose(p.data.cpu().numpy(), g["adam_w3"], atol=2e-6)
+    np.testing.assert_allclose(opt.ema.cpu().numpy(), g["ema3"], atol=2e-6)

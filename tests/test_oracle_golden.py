@@ -1,0 +1,148 @@
+"""Pins the CPU oracle (oracle/ref_port.py) against fixtures produced by the live reference
+(tests/golden/make_golden.py).  Integer work is bit-exact; float tolerances are stated per check."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import ref_port as O
+
+torch.set_grad_enabled(False)
+
+
+def _sha(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+def test_frontend_constants_bit_exact(meta):
+    c = O.frontend_constants()
+    for k, h in meta["const_sha256"].items():
+        assert _sha(c[k]) == h, k
+
+
+def test_frontend_short_clips(gold, ref_state_dict):
+    g = gold("short_clips")
+    x = synth.synth_clips(3, 22050 * 6, seed=1000, silence_tail_every=3)
+    fe = O.frontend(x, ref_state_dict)
+    np.testing.assert_allclose(fe["resampled"][:, 0, :4000].numpy(), g["resampled_head"], atol=2e-6)
+    np.testing.assert_allclose(fe["mel"].numpy(), g["mel"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(fe["mfcc"].numpy(), g["mfcc"], atol=2e-3)      # pre-dB MFCC, range [-460, 20]
+    xs = fe["x_spectral"].numpy()
+    np.testing.assert_allclose(xs[:, 0], g["x_spectral"][:, 0], atol=1e-4)    # standardised dB-mel
+    # dB-of-MFCC is ill-conditioned at zero crossings: quantile criterion
+    d = np.abs(xs[:, 1] - g["x_spectral"][:, 1])
+    assert np.quantile(d, 0.99) < 1e-2 and d.mean() < 1e-3
+
+
+@pytest.mark.parametrize("form", ["train", "deploy"])
+def test_forward_short_clips(gold, ref_state_dict, form):
+    g = gold("short_clips")
+    x = synth.synth_clips(3, 22050 * 6, seed=1000, silence_tail_every=3)
+    sd = ref_state_dict if form == "train" else O.fold_repvgg(ref_state_dict)
+    taps = {}
+    out = O.forward(x, sd, 2, taps=taps)
+    assert out.shape == (3, 63, 5)
+    np.testing.assert_allclose(out.numpy(), g[f"preds_{form}"], atol=5e-3)
+    pre = "head" if form == "train" else "dhead"
+    for h, n in zip(taps["heads"], ("sm", "md", "lg")):
+        np.testing.assert_allclose(h.numpy(), g[f"{pre}_{n}"], atol=5e-3)
+    if form == "train":
+        np.testing.assert_allclose(taps["fmaps"][0].numpy(), g["fmap1"], atol=2e-3)
+        np.testing.assert_allclose(taps["fmaps"][3].numpy(), g["fmap4"], atol=2e-3)
+
+
+def test_deploy_layout_matches_reference(meta, ref_state_dict):
+    sdd = O.fold_repvgg(ref_state_dict)
+    want = meta["layout_deploy"]
+    assert set(sdd) == set(want)
+    for k, v in sdd.items():
+        assert list(v.shape) == want[k], k
+
+
+def test_full_clip_config1(gold, ref_state_dict):
+    """BASELINE.json configs[0]: one 60 s clip through forward + process_model_outputs."""
+    g = gold("full_clip")
+    x = synth.synth_clips(1, 1323000, seed=2000, silence_tail_every=0)
+    out = O.forward(x, ref_state_dict, 2)
+    assert out.shape == (1, 630, 5)
+    np.testing.assert_allclose(out.numpy(), g["preds_train"], atol=5e-3)
+    seg, bidx = O.process_model_outputs(torch.from_numpy(g["preds_train"]).clone(), 0.1, 0.2)
+    np.testing.assert_array_equal(bidx.numpy(), g["bidx_0.1_0.2"])
+    np.testing.assert_allclose(seg.numpy(), g["seg_0.1_0.2"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name,B", [("b1", 1), ("b3", 3)])
+@pytest.mark.parametrize("iou,cthr", [(0.1, 0.2), (0.1, 0.65), (0.05, 0.5)])
+def test_nms_keep_sets_bit_exact(gold, name, B, iou, cthr):
+    g = gold("nms")
+    o = synth.synth_heads(B, 630, 2, seed=7 + B)
+    keeps = O.keep_indices(o, iou)
+    flat = np.concatenate([k + b * 630 for b, k in enumerate(keeps)])
+    ref = g[f"keep_{name}_{iou}_{cthr}"]
+    # torchvision returns kept boxes of all clips merged in descending score order; compare per clip
+    for b in range(B):
+        mine = keeps[b] + b * 630
+        theirs = ref[(ref >= b * 630) & (ref < (b + 1) * 630)]
+        np.testing.assert_array_equal(mine, theirs)
+    assert flat.shape[0] == ref.shape[0]
+    seg, bidx = O.process_model_outputs(o.clone(), iou, cthr)
+    np.testing.assert_array_equal(bidx.numpy(), g[f"bidx_{name}_{iou}_{cthr}"])
+    np.testing.assert_allclose(seg.numpy(), g[f"seg_{name}_{iou}_{cthr}"], atol=1e-6)
+
+
+def test_nms_on_model_output(gold):
+    g = gold("nms")
+    out = torch.from_numpy(gold("short_clips")["preds_train"])
+    keeps = O.keep_indices(out, 0.1)
+    ref = g["keep_model_0.1"]
+    P = out.shape[1]
+    for b in range(out.shape[0]):
+        np.testing.assert_array_equal(keeps[b] + b * P, ref[(ref >= b * P) & (ref < (b + 1) * P)])
+    for iou, cthr in ((0.1, 0.2), (0.05, 0.1)):
+        seg, bidx = O.process_model_outputs(out.clone(), iou, cthr)
+        np.testing.assert_array_equal(bidx.numpy(), g[f"bidx_model_{iou}_{cthr}"])
+        np.testing.assert_allclose(seg.numpy(), g[f"seg_model_{iou}_{cthr}"], atol=1e-6)
+
+
+def test_empty_result_raises(meta, gold):
+    assert meta["empty_raises"] in ("ValueError", "RuntimeError")
+    out = torch.from_numpy(gold("short_clips")["preds_train"])
+    with pytest.raises(ValueError):
+        O.process_model_outputs(out, 0.1, 0.999999)
+
+
+@pytest.mark.parametrize("name,G", [("sm", 120), ("md", 60), ("lg", 30)])
+def test_anchor_matching_bit_exact(gold, name, G):
+    g = gold("train")
+    tg = torch.from_numpy(g["targets"])
+    (bi, gi, ai), cl, cw = O.build_target_by_scale(tg, G, O.DEFAULT_CONFIG["anchors"][name], 5, 60, 0.5)
+    np.testing.assert_array_equal(bi.numpy(), g[f"bi_{name}"])
+    np.testing.assert_array_equal(gi.numpy(), g[f"gi_{name}"])
+    np.testing.assert_array_equal(ai.numpy(), g[f"ai_{name}"])
+    np.testing.assert_array_equal(cl.numpy(), g[f"cl_{name}"])
+    np.testing.assert_array_equal(cw.numpy(), g[f"cw_{name}"])
+
+
+def test_loss_value_and_grads(gold):
+    g = gold("train")
+    tg = torch.from_numpy(g["targets"])
+    with torch.enable_grad():
+        preds = [torch.from_numpy(g[f"pred{i}"]).clone().requires_grad_(True) for i in range(3)]
+        loss, met = O.detection_loss(preds, tg, O.DEFAULT_CONFIG["anchors"], 2)
+        loss.backward()
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-5)
+    for i in range(3):
+        np.testing.assert_allclose(preds[i].grad.numpy(), g[f"grad{i}"], atol=1e-7, rtol=1e-4)
+
+
+def test_adam_and_ema(gold):
+    g = gold("train")
+    w = torch.from_numpy(g["adam_w0"]).clone()
+    m, v, ema = torch.zeros_like(w), torch.zeros_like(w), w.clone()
+    for step in range(1, 4):
+        O.adam_step([w], [torch.from_numpy(g["adam_grads"][step - 1])], [m], [v], step)
+        O.ema_update([ema], [w], step)
+    np.testing.assert_allclose(w.numpy(), g["adam_w3"], atol=1e-6)
+    np.testing.assert_allclose(ema.numpy(), g["ema3"], atol=1e-6)

@@ -1,0 +1,12 @@
+"""yad_b200 - B200-native (sm_100a) audio-activity-detection hot path.
+
+Drop-in for the reference's ``modules.AudioDetectionNetwork`` and ``inference.process_model_outputs``;
+every kernel is hand-written CUDA behind the C ABI in ``include/yad_b200.h``.  No CPU fallback."""
+from ._lib import YadError, LIB_PATH  # noqa: F401
+from .config import DEFAULT_CONFIG_PATH, default_config, load_config  # noqa: F401
+from .network import AudioDetectionNetwork  # noqa: F401
+from .postprocess import nms_raw, process_model_outputs  # noqa: F401
+from .train_ops import EMAParamsSmoothener, FusedAdamEMA, build_target_by_scale  # noqa: F401
+
+__all__ = ["AudioDetectionNetwork", "process_model_outputs", "nms_raw", "load_config", "default_config",
+           "build_target_by_scale", "FusedAdamEMA", "EMAParamsSmoothener", "YadError"]

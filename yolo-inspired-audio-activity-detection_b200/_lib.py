@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI library (include/yad_b200.h).
+
+The product path has no CPU fallback: if ``libyad_b200.so`` is missing, or the device is not
+sm_100, every call raises.  ``__graft_entry__.build()`` / ``build.sh`` produce the library in-tree.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libyad_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+FE_TPQ = 20
+
+
+class YadError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "B", "H", "W", "Cin", "ld_in", "Cout", "ld_out", "co_off", "kh", "kw", "sh", "sw", "ph", "pw", "act", "ld_res")]
+
+
+_p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+# name -> argument types (all return int)
+SIGNATURES = {
+    "yad_init": [C.c_int],
+    "yad_frontend_mel_power": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _i64, _p],
+    "yad_frontend_finish": [_p, _i64, _i64, _p, _f32, _i32, _p, _p, _p, _p, _p],
+    "yad_conv_stem": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],
+    "yad_conv_simt": [C.POINTER(ConvDesc), _i32, _p, _p, _i32, _p, _p, _p, _p],
+    "yad_conv_tc": [C.POINTER(ConvDesc), _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p],
+    "yad_hmean": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
+    "yad_resize_w": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
+    "yad_sppf_pools": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
+    "yad_repvgg_merge": [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p],
+    "yad_decode": [C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i32, _i32, C.POINTER(_f32), _i32,
+                   _i32, _f32, _f32, _i64, _p, _p],
+    "yad_nms": [_p, _i64, _i32, _i32, _f64, _f32, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p],
+    "yad_compact_segments": [_p, _p, _i64, _i32, _p, _p, _p, _p],
+    "yad_build_targets": [_p, _i32, _p, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p],
+    "yad_adam_ema_step": [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _p],
+}
+EXPORTS = ["yad_version", "yad_last_error"] + list(SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+_inited = set()
+
+
+def load() -> C.CDLL:
+    """dlopen the library and attach prototypes.  Raises YadError if it was not built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise YadError(
+                    f"{LIB_PATH} is missing: build it with ./build.sh (nvcc, sm_100a). "
+                    "There is no CPU or PyTorch fallback for this path.")
+            lib = C.CDLL(LIB_PATH)
+            lib.yad_version.restype = C.c_int
+            lib.yad_last_error.restype = C.c_char_p
+            for name, args in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.argtypes = args
+                fn.restype = C.c_int
+            _lib = lib
+    return _lib
+
+
+launch_count = 0     # kernels launched through the C ABI by this process (bench.py reports it)
+
+
+def check(rc: int, what: str):
+    global launch_count
+    if rc != 0:
+        raise YadError(f"{what} failed (code {rc}): {load().yad_last_error().decode()}")
+    launch_count += 1
+
+
+def init(device_index: int):
+    lib = load()
+    if device_index not in _inited:
+        rc = lib.yad_init(int(device_index))
+        if rc != 0:
+            raise YadError(f"yad_init failed (code {rc}): {lib.yad_last_error().decode()}")
+        _inited.add(device_index)
+    return lib
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()

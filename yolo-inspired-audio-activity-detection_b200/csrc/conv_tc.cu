@@ -37,7 +37,7 @@ struct TcParams {
   int32_t BN, n_ntiles, stages;
   int32_t cin_chunks;            // Cin / 64
   int32_t n_taps;
-  int32_t Cout, ld_out, co_off, ld_res, act, out_f32;
+  int32_t Cout, ld_out, co_off, ld_res, act, out_f32, ld_out2;
   uint32_t idesc;
   // per tap: which parity map, coordinate offsets (in the parity map's units), weight tap index
   int8_t tap_map[TC_MAX_TAPS];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                const __grid_constant__ CUtensorMap map_w, const TcParams p, const float* __restrict__ bias,
-               const __nv_bfloat16* __restrict__ residual, void* __restrict__ out) {
+               const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, float* __restrict__ out2) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B BN*128] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -276,6 +276,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+          if (out2 != nullptr) {
+            float4* o2 = reinterpret_cast<float4*>(out2 + pix * p.ld_out2 + nbase);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) o2[j4] = make_float4(f[j4 * 4], f[j4 * 4 + 1], f[j4 * 4 + 2], f[j4 * 4 + 3]);
+          }
           if (p.out_f32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + pix * p.ld_out + p.co_off + nbase);
 #pragma unroll
@@ -301,6 +306,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             float x = f[j] + __ldg(bias + n);
             if (residual != nullptr) x += __bfloat162float(residual[pix * p.ld_res + n]);
             x = apply_act(x, p.act);
+            if (out2 != nullptr) out2[pix * p.ld_out2 + n] = x;
             if (p.out_f32)
               reinterpret_cast<float*>(out)[pix * p.ld_out + p.co_off + n] = x;
             else
@@ -386,7 +392,7 @@ static void choose_tile(int B, int Ho, int Wo, int* tb, int* th, int* tw) {
 
 extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad,
                            const float* bias, const void* residual, void* out, int32_t out_dtype,
-                           yad_stream_t stream) {
+                           float* out2_f32, int32_t ld_out2, yad_stream_t stream) {
   using namespace yad;
   YAD_CHECK_ARG(d && in && weight && bias && out, "yad_conv_tc: null pointer");
   YAD_CHECK_ARG(d->Cin % 64 == 0 && d->Cin >= 64, "yad_conv_tc: Cin=%d must be a multiple of 64 (zero-pad channels)", d->Cin);
@@ -398,6 +404,7 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
   YAD_CHECK_ARG(d->ld_out >= d->co_off + d->Cout, "yad_conv_tc: ld_out too small");
   YAD_CHECK_ARG((d->ld_out % 8 == 0) && (d->co_off % 8 == 0), "yad_conv_tc: ld_out/co_off must be multiples of 8 (16 B stores)");
   YAD_CHECK_ARG(residual == nullptr || (d->ld_res % 8 == 0 && d->ld_res >= d->Cout), "yad_conv_tc: bad ld_res");
+  YAD_CHECK_ARG(out2_f32 == nullptr || (ld_out2 % 4 == 0 && ld_out2 >= d->Cout), "yad_conv_tc: bad ld_out2");
   YAD_CHECK_ARG((reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(weight) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(out) % 16 == 0),
                 "yad_conv_tc: pointers must be 16-byte aligned");
@@ -428,6 +435,7 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
   p.ld_res = d->ld_res;
   p.act = d->act;
   p.out_f32 = (out_dtype == YAD_F32);
+  p.ld_out2 = ld_out2;
   // instruction descriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -493,7 +501,7 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
   }
   dim3 grid((unsigned)(p.n_wt * p.n_ht * p.n_bt), (unsigned)p.n_ntiles);
   conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], map_w, p, bias,
-                                                                  reinterpret_cast<const __nv_bfloat16*>(residual), out);
+                                                                  reinterpret_cast<const __nv_bfloat16*>(residual), out, out2_f32);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

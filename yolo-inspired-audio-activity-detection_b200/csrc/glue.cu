@@ -77,6 +77,21 @@ __global__ void sppf_kernel(const T* __restrict__ in, int64_t B, int W, int C, i
   st_from_float(o + 2 * C, m3);
 }
 
+// RepVGG train-form merge (modules/_common.py:90-95): out = lrelu(a + b [+ scale*x + shift]) where a, b are
+// the already-activated 3x3 / 1x1 branches and (scale, shift) is the eval-mode identity BatchNorm.
+template <typename T>
+__global__ void repvgg_merge_kernel(const T* __restrict__ a, const T* __restrict__ bb, const T* __restrict__ x,
+                                    const float* __restrict__ scale, const float* __restrict__ shift, int64_t npix,
+                                    int C, int ld_ab, int ld_x, T* __restrict__ out, int ld_out, int co_off, int act) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= npix * C) return;
+  const int c = (int)(gid % C);
+  const int64_t px = gid / C;
+  float v = ld_as_float(a + px * ld_ab + c) + ld_as_float(bb + px * ld_ab + c);
+  if (x != nullptr) v += fmaf(ld_as_float(x + px * ld_x + c), scale[c], shift[c]);
+  st_from_float(out + px * ld_out + co_off + c, apply_act(v, act));
+}
+
 }  // namespace yad
 
 #define YAD_DISPATCH_DTYPE(dtype, KERNEL, ...)                                              \
@@ -130,6 +145,22 @@ int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t 
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   YAD_DISPATCH_DTYPE(dtype, yad::sppf_kernel, (const T*)in, B, W, C, ld_in, ci_off, (T*)out, ld_out, co_off);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_repvgg_merge(const void* a, const void* b, const void* x, const float* scale, const float* shift,
+                     int32_t dtype, int64_t npix, int32_t C, int32_t ld_ab, int32_t ld_x, void* out, int32_t ld_out,
+                     int32_t co_off, int32_t act, yad_stream_t stream) {
+  YAD_CHECK_ARG(a && b && out && C >= 1 && ld_ab >= C && ld_out >= co_off + C, "yad_repvgg_merge: bad arguments");
+  YAD_CHECK_ARG(x == nullptr || (scale && shift && ld_x >= C), "yad_repvgg_merge: identity branch needs scale/shift/ld_x");
+  YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_repvgg_merge: bad dtype %d", dtype);
+  const int64_t n = npix * C;
+  if (n == 0) return YAD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  YAD_DISPATCH_DTYPE(dtype, yad::repvgg_merge_kernel, (const T*)a, (const T*)b, (const T*)x, scale, shift, npix, C, ld_ab,
+                     ld_x, (T*)out, ld_out, co_off, act);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

@@ -1,0 +1,417 @@
+"""Inference engine: packs the model's weights for the sm_100a kernels and runs the whole forward
+(frontend -> stem -> ResNet stages -> RepBi-PAN neck -> anchor decode) as a fixed list of C-ABI calls
+on the current CUDA stream.
+
+Data layout in HBM (per batch of B clips, T = frames = 960 for 60 s clips):
+  pcm        [B, L]            f32   caller's tensor, read once
+  mel        [B, 32, T]        f32   stage-A output (123 KB / clip)
+  x_spectral [B, 2, 32, T]     f32   stage-B output (NCHW, as the reference's tensor)
+  activations NHWC ("pixel-major"), bf16 (tcgen05 path) or f32 (CUDA-core parity path); channel
+  pitches are multiples of 64 on the bf16 path (the 15-channel head tensors are zero-padded to 64) so
+  every K-block of the implicit GEMM is one 128-byte swizzled row; torch.cat sites are channel slices
+  of one buffer.
+  preds      [B, 630, 3+nc]    f32
+
+torch is used here for device memory (the workspace tensors) and the stream handle only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from . import frontend_consts as fc
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvDesc
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def _fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+    """conv -> eval-mode BatchNorm as one affine conv (fp32, done once at pack time)."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    wf = w * scale.reshape(-1, 1, 1, 1)
+    b0 = b if b is not None else torch.zeros_like(bn.running_mean)
+    return wf, (b0 - bn.running_mean) * scale + bn.bias
+
+
+class _Conv:
+    """One packed convolution (weights folded, both kernel layouts prepared lazily for the engine dtype)."""
+
+    def __init__(self, name, w, b, stride, pad, act, dev, dtype):
+        self.name = name
+        self.cout, self.cin, self.kh, self.kw = w.shape
+        self.sh, self.sw = (stride, stride) if isinstance(stride, int) else tuple(stride)
+        self.ph, self.pw = (pad, pad) if isinstance(pad, int) else tuple(pad)
+        self.act = act
+        w = w.detach().to(dev, torch.float32)
+        self.bias = b.detach().to(dev, torch.float32).contiguous()
+        if dtype == BF16:
+            self.cin_pad = _ceil(self.cin, 64)
+            self.cout_pad = _ceil(self.cout, 16)
+            wt = torch.zeros(self.cout_pad, self.kh, self.kw, self.cin_pad, device=dev, dtype=torch.float32)
+            wt[: self.cout, :, :, : self.cin] = w.permute(0, 2, 3, 1)
+            self.w = wt.reshape(self.cout_pad, -1).to(torch.bfloat16).contiguous()
+            bp = torch.zeros(self.cout_pad, device=dev, dtype=torch.float32)
+            bp[: self.cout] = self.bias
+            self.bias = bp
+        else:
+            self.cin_pad = self.cin
+            self.cout_pad = self.cout
+            self.w = w.permute(2, 3, 1, 0).contiguous()     # [kh, kw, Cin, Cout]
+
+
+class InferenceEngine:
+    def __init__(self, model, device: torch.device, compute_dtype: str):
+        if device.type != "cuda":
+            raise RuntimeError("yad_b200 needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
+        if compute_dtype not in ("bf16", "f32"):
+            raise ValueError("compute_dtype must be 'bf16' (tcgen05 path) or 'f32' (CUDA-core parity path)")
+        self.dev = device
+        self.lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+        self.dtype = BF16 if compute_dtype == "bf16" else F32
+        self.tdtype = torch.bfloat16 if self.dtype == BF16 else torch.float32
+        self.cfg = model.config
+        self.nc = model.num_classes
+        self.A = self.cfg["num_anchors"]
+        self.E = 3 + self.nc
+        self.n_head = self.A * self.E
+        self._tls = threading.local()
+        with torch.no_grad():
+            self._pack_frontend(model)
+            self._pack_cnn(model)
+            dur = float(self.cfg["sample_duration"])
+            self.anchors_s = torch.cat([model.sm_anchors * dur, model.md_anchors * dur, model.lg_anchors * dur]).float().cpu()
+
+    # ------------------------------------------------------------------ packing
+    def _pack_frontend(self, model):
+        dev = self.dev
+        k = model.resampler.kernel
+        pk = fc.pack_resample_taps(k)
+        self.rs_P, self.rs_KW = pk["P"], pk["KW"]
+        g = math.gcd(int(self.cfg["sample_rate"]), int(self.cfg["new_sample_rate"]))
+        self.rs_O = int(self.cfg["sample_rate"]) // g
+        if int(self.cfg["new_sample_rate"]) // g != self.rs_P:
+            raise ValueError("resampler.kernel does not match sample_rate/new_sample_rate")
+        self.rs_width = (self.rs_KW - self.rs_O) // 2
+        self.rs_taps = pk["taps"].to(dev)
+        self.rs_base = pk["base"].to(dev)
+        self.rs_window_len = pk["window_len"]
+        self.win = model.melspectogram_tfmr.spectrogram.window.detach().to(dev, torch.float32).contiguous()
+        csr = fc.pack_mel_csr(model.melspectogram_tfmr.mel_scale.fb)
+        self.fb_val, self.fb_bin, self.fb_start = csr["val"].to(dev), csr["bin"].to(dev), csr["start"].to(dev)
+        self.dct = model.mfcc_tfmr.dct_mat.detach().to(dev, torch.float32).contiguous()
+        self.tw = fc.fft_twiddles(1000).to(dev)
+
+    def _cbl(self, name, m):  # ConvBorINorm
+        w, b = _fold_bn(m.conv.weight, m.conv.bias, m.norm)
+        return _Conv(name, w, b, m.conv.stride, m.conv.padding, ACT_LRELU if m.has_activation else ACT_NONE, self.dev, self.dtype)
+
+    def _rep(self, name, m):
+        """RepVGG block -> either one folded conv (deploy) or the three train-form branches."""
+        if hasattr(m, "conv_reparam"):
+            c = m.conv_reparam
+            return {"deploy": _Conv(name, c.weight, c.bias, 1, 1, ACT_LRELU, self.dev, self.dtype)}
+        out = {"c3": self._cbl(name + ".conv3x3", m.conv3x3), "c1": self._cbl(name + ".conv1x1", m.conv1x1)}
+        if isinstance(m.identity, nn.BatchNorm2d):
+            bn = m.identity
+            s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            out["id_scale"] = s.detach().to(self.dev, torch.float32).contiguous()
+            out["id_shift"] = (bn.bias - bn.running_mean * s).detach().to(self.dev, torch.float32).contiguous()
+        return out
+
+    def _pack_cnn(self, model):
+        fe, ms = model.feature_extractor, model.multiscale_module
+        dev = self.dev
+        # stem conv1: raw (no BN / bias / activation before conv2, modules/_backbone.py:143-144); [7][7][2][64] f32
+        self.stem_w = fe.conv1.weight.detach().to(dev, torch.float32).permute(2, 3, 1, 0).contiguous()
+        w2, b2 = _fold_bn(fe.conv2.weight, None, fe.bn1)
+        self.conv2 = _Conv("fe.conv2", w2, b2, 2, 3, ACT_RELU, dev, self.dtype)
+        self.stages = []
+        for li in range(1, 5):
+            blocks = []
+            for bi, blk in enumerate(getattr(fe, f"layer{li}")):
+                w1, b1 = _fold_bn(blk.conv1.weight, None, blk.bn1)
+                wB, bB = _fold_bn(blk.conv2.weight, None, blk.bn2)
+                ent = {
+                    "c1": _Conv(f"l{li}.{bi}.conv1", w1, b1, blk.stride, 1, ACT_RELU, dev, self.dtype),
+                    "c2": _Conv(f"l{li}.{bi}.conv2", wB, bB, 1, 1, ACT_RELU, dev, self.dtype),  # relu after the residual add
+                }
+                if blk.downsample is not None:
+                    wd, bd = _fold_bn(blk.downsample[0].weight, None, blk.downsample[1])
+                    ent["ds"] = _Conv(f"l{li}.{bi}.ds", wd, bd, blk.stride, 0, ACT_NONE, dev, self.dtype)
+                blocks.append(ent)
+            self.stages.append(blocks)
+        sp = ms.cspsppf
+        self.n = {
+            "sp1": self._cbl("sp.c1", sp.conv_1_3_4[0]), "sp3": self._cbl("sp.c3", sp.conv_1_3_4[1]),
+            "sp4": self._cbl("sp.c4", sp.conv_1_3_4[2]), "sp2": self._cbl("sp.c2", sp.conv2),
+            "sp5": self._cbl("sp.c5", sp.conv5), "sp6": self._cbl("sp.c6", sp.conv6), "sp7": self._cbl("sp.c7", sp.conv7),
+            "b3c1": self._cbl("bic3.c1", ms.bic3.conv_c1), "b3c0": self._cbl("bic3.c0", ms.bic3.conv_c0),
+            "b3o": self._cbl("bic3.out", ms.bic3.conv_out),
+            "b2c1": self._cbl("bic2.c1", ms.bic2.conv_c1), "b2c0": self._cbl("bic2.c0", ms.bic2.conv_c0),
+            "b2o": self._cbl("bic2.out", ms.bic2.conv_out),
+            "ds2": self._cbl("conv2_ds", ms.conv2_downsample), "ds3": self._cbl("conv3_ds", ms.conv3_downsample),
+        }
+        self.rep = {}
+        for nm in ("rep_block2_1", "rep_block3_1", "rep_block3_2", "rep_block4_1"):
+            rb = getattr(ms, nm)
+            blocks = [rb.conv1] + (list(rb.blocks) if isinstance(rb.blocks, nn.Sequential) else [])
+            self.rep[nm] = [self._rep(f"{nm}.{i}", b) for i, b in enumerate(blocks)]
+
+    # ------------------------------------------------------------------ shapes
+    def frames(self, L: int) -> int:
+        target = -(-self.rs_P * L // self.rs_O)
+        return target // 1000
+
+    def grids(self, L: int) -> List[int]:
+        """Grid sizes of the three heads for an input of L samples (T/8, T/16, T/32 for the default net)."""
+        T = self.frames(L)
+        w = T
+        ws = []
+        for _ in range(2):
+            w = (w + 6 - 7) // 2 + 1
+        ws.append(w)                       # layer1
+        for _ in range(3):
+            w = (w + 2 - 3) // 2 + 1
+            ws.append(w)
+        return [ws[1], ws[2], ws[3]]
+
+    # ------------------------------------------------------------------ execution helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _buf(self, plan, name, B, H, W, ld, zero=False, dtype=None):
+        t = plan.get(name)
+        if t is None:
+            f = torch.zeros if zero else torch.empty
+            t = f((B, H, W, ld), device=self.dev, dtype=dtype or self.tdtype)
+            plan[name] = t
+        return t
+
+    def _conv(self, cv: _Conv, x: torch.Tensor, cin_off: int, out: torch.Tensor, co_off: int, res: Optional[torch.Tensor] = None,
+              act: Optional[int] = None, out2: Optional[torch.Tensor] = None):
+        """x [B,H,W,ld_in] (channels [cin_off, cin_off+Cin) are read), out [B,Ho,Wo,ld_out] slice at co_off."""
+        B, H, W, ld_in = x.shape
+        es = x.element_size()
+        d = ConvDesc(B=B, H=H, W=W, Cin=cv.cin_pad if self.dtype == BF16 else cv.cin, ld_in=ld_in, Cout=cv.cout,
+                     ld_out=out.shape[3], co_off=co_off, kh=cv.kh, kw=cv.kw, sh=cv.sh, sw=cv.sw, ph=cv.ph, pw=cv.pw,
+                     act=cv.act if act is None else act, ld_res=0 if res is None else res.shape[3])
+        Ho = (H + 2 * cv.ph - cv.kh) // cv.sh + 1
+        Wo = (W + 2 * cv.pw - cv.kw) // cv.sw + 1
+        assert out.shape[0] == B and out.shape[1] == Ho and out.shape[2] == Wo, (cv.name, tuple(out.shape), (B, Ho, Wo))
+        in_ptr = x.data_ptr() + cin_off * es
+        if self.dtype == BF16:
+            assert cin_off + cv.cin_pad <= ld_in, (cv.name, cin_off, cv.cin_pad, ld_in)
+            rc = self.lib.yad_conv_tc(C.byref(d), in_ptr, cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), _lib.ptr(res),
+                                      out.data_ptr(), BF16, _lib.ptr(out2), 0 if out2 is None else out2.shape[3], self._stream())
+        else:
+            rc = self.lib.yad_conv_simt(C.byref(d), F32, in_ptr, cv.w.data_ptr(), cv.cout, cv.bias.data_ptr(), _lib.ptr(res),
+                                        out.data_ptr(), self._stream())
+            if out2 is not None:
+                raise AssertionError("out2 is only used on the bf16 path")
+        _lib.check(rc, f"conv {cv.name}")
+
+    def _repblock(self, plan, key, blocks, x, cin_off, out, co_off, out2=None):
+        """RepBlock: chain of RepVGG blocks; the last one writes (out, co_off) [and the fp32 copy out2]."""
+        B, H, W, _ = x.shape
+        cur, cur_off = x, cin_off
+        for i, blk in enumerate(blocks):
+            last = i == len(blocks) - 1
+            cout = (blk["deploy"] if "deploy" in blk else blk["c3"]).cout
+            ld = _ceil(cout, 64) if self.dtype == BF16 else cout
+            dst, dst_off = (out, co_off) if last else (self._buf(plan, f"{key}.t{i}", B, H, W, ld, zero=True), 0)
+            if "deploy" in blk:
+                self._conv(blk["deploy"], cur, cur_off, dst, dst_off, out2=out2 if last else None)
+            else:
+                a = self._buf(plan, f"{key}.a{i}", B, H, W, ld, zero=True)
+                b = self._buf(plan, f"{key}.b{i}", B, H, W, ld, zero=True)
+                self._conv(blk["c3"], cur, cur_off, a, 0)
+                self._conv(blk["c1"], cur, cur_off, b, 0)
+                has_id = "id_scale" in blk
+                es = cur.element_size()
+                rc = self.lib.yad_repvgg_merge(a.data_ptr(), b.data_ptr(), (cur.data_ptr() + cur_off * es) if has_id else 0,
+                                               _lib.ptr(blk.get("id_scale")), _lib.ptr(blk.get("id_shift")), self.dtype,
+                                               B * H * W, cout, ld, cur.shape[3], dst.data_ptr(), dst.shape[3], dst_off,
+                                               ACT_LRELU, self._stream())
+                _lib.check(rc, f"repvgg_merge {key}.{i}")
+                if last and out2 is not None:
+                    out2.copy_(dst[..., dst_off:dst_off + out2.shape[3]])
+            cur, cur_off = dst, dst_off
+
+    # ------------------------------------------------------------------ forward
+    def run_frontend(self, x: torch.Tensor, plan: dict, taps: Optional[dict] = None) -> torch.Tensor:
+        B, _, L = x.shape
+        T = self.frames(L)
+        if T < 32:
+            raise ValueError(f"input too short: {L} samples give {T} frames (need >= 32)")
+        x = x.contiguous().float()
+        mel = plan.get("mel")
+        if mel is None:
+            mel = plan["mel"] = torch.empty((B, 32, T), device=self.dev, dtype=torch.float32)
+            plan["xs"] = torch.empty((B, 2, 32, T), device=self.dev, dtype=torch.float32)
+        xs = plan["xs"]
+        rc = self.lib.yad_frontend_mel_power(x.data_ptr(), B, L, self.rs_P, self.rs_O, self.rs_width, self.rs_taps.data_ptr(),
+                                             self.rs_base.data_ptr(), self.rs_window_len, self.win.data_ptr(), self.tw.data_ptr(),
+                                             self.fb_val.data_ptr(), self.fb_bin.data_ptr(), self.fb_start.data_ptr(),
+                                             mel.data_ptr(), T, self._stream())
+        _lib.check(rc, "frontend_mel_power")
+        tm = {}
+        if taps is not None:
+            for k in ("meldb", "mfcc", "mfdb"):
+                tm[k] = torch.empty((B, 1, 32, T), device=self.dev, dtype=torch.float32)
+        rc = self.lib.yad_frontend_finish(mel.data_ptr(), B, T, self.dct.data_ptr(), 80.0, 1 if self.cfg["scale_input"] else 0,
+                                          xs.data_ptr(), _lib.ptr(tm.get("meldb")), _lib.ptr(tm.get("mfcc")),
+                                          _lib.ptr(tm.get("mfdb")), self._stream())
+        _lib.check(rc, "frontend_finish")
+        if taps is not None:
+            taps.update(tm)
+            taps["mel"] = mel.reshape(B, 1, 32, T).clone()
+            taps["x_spectral"] = xs.clone()
+        return xs
+
+    def run_cnn(self, xs: torch.Tensor, plan: dict, taps: Optional[dict] = None) -> List[torch.Tensor]:
+        """x_spectral [B,2,32,T] f32 -> three head tensors [B,G,ld] f32 (first n_head channels valid)."""
+        B, _, H0, T = xs.shape
+        bf = self.dtype == BF16
+        s = self._stream
+        c1 = self._buf(plan, "c1", B, H0 // 2, T // 2, 64)
+        _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
+        H, W = (H0 // 2 + 6 - 7) // 2 + 1, (T // 2 + 6 - 7) // 2 + 1
+        cur = self._buf(plan, "c2", B, H, W, 64)
+        self._conv(self.conv2, c1, 0, cur, 0)
+        fmaps = []
+        for li, blocks in enumerate(self.stages):
+            for bi, blk in enumerate(blocks):
+                c1v, c2v = blk["c1"], blk["c2"]
+                Ho, Wo = (H + 2 - 3) // c1v.sh + 1, (W + 2 - 3) // c1v.sw + 1
+                ld = _ceil(c1v.cout, 64) if bf else c1v.cout
+                t = self._buf(plan, f"s{li}.{bi}.t", B, Ho, Wo, ld)
+                y = self._buf(plan, f"s{li}.{bi}.y", B, Ho, Wo, ld)
+                self._conv(c1v, cur, 0, t, 0)
+                if "ds" in blk:
+                    idt = self._buf(plan, f"s{li}.{bi}.d", B, Ho, Wo, ld)
+                    self._conv(blk["ds"], cur, 0, idt, 0)
+                else:
+                    idt = cur
+                self._conv(c2v, t, 0, y, 0, res=idt)
+                cur, H, W = y, Ho, Wo
+            fmaps.append(cur)
+        if taps is not None:
+            taps["fmaps"] = [f.float().permute(0, 3, 1, 2).contiguous() for f in fmaps]
+
+        # ---- neck (H = 1 after the H-mean; modules/_common.py:241-265)
+        f1, f2, f3, f4 = fmaps
+        hs = [f.shape[1] for f in fmaps]
+        if not (hs[0] != hs[1] != hs[2] != hs[3]):
+            raise NotImplementedError("neck with equal feature-map heights (2-D neck) is not built")
+        pooled = []
+        for i, f in enumerate(fmaps):
+            Bf, Hf, Wf, ldf = f.shape
+            if Hf == 1:
+                pooled.append(f)
+                continue
+            pm = self._buf(plan, f"fm{i}", B, 1, Wf, ldf)
+            _lib.check(self.lib.yad_hmean(f.data_ptr(), self.dtype, B, Hf, Wf, ldf, ldf, pm.data_ptr(), ldf, 0, s()), "hmean")
+            pooled.append(pm)
+        f1m, f2m, f3m, f4m = pooled
+        W1, W2, W3, W4 = f1m.shape[2], f2m.shape[2], f3m.shape[2], f4m.shape[2]
+        n = self.n
+        # CSPSPPF -> p4, written straight into cat_n4[:, 0:128]
+        a1 = self._buf(plan, "sp.a1", B, 1, W4, 64)
+        a2 = self._buf(plan, "sp.a2", B, 1, W4, 64)
+        cat5 = self._buf(plan, "sp.cat5", B, 1, W4, 256)
+        cat7 = self._buf(plan, "sp.cat7", B, 1, W4, 128)
+        c5 = self._buf(plan, "sp.c5", B, 1, W4, 64)
+        cat_n4 = self._buf(plan, "cat_n4", B, 1, W4, 256)
+        self._conv(n["sp1"], f4m, 0, a1, 0)
+        self._conv(n["sp3"], a1, 0, a2, 0)
+        self._conv(n["sp4"], a2, 0, cat5, 0)
+        self._conv(n["sp2"], f4m, 0, cat7, 64)
+        _lib.check(self.lib.yad_sppf_pools(cat5.data_ptr(), self.dtype, B, W4, 64, 256, 0, cat5.data_ptr(), 256, 64, s()), "sppf")
+        self._conv(n["sp5"], cat5, 0, c5, 0)
+        self._conv(n["sp6"], c5, 0, cat7, 0)
+        self._conv(n["sp7"], cat7, 0, cat_n4, 0)                       # p4
+        # BiC3 -> RepBlock3_1 -> p3, written into cat_n3[:, 0:128]
+        cat_b3 = self._buf(plan, "cat_b3", B, 1, W3, 256)
+        c0_3 = self._buf(plan, "b3.c0", B, 1, W2, 64)
+        b3 = self._buf(plan, "b3", B, 1, W3, 128)
+        cat_n3 = self._buf(plan, "cat_n3", B, 1, W3, 256)
+        self._conv(n["b3c1"], f3m, 0, cat_b3, 0)
+        self._conv(n["b3c0"], f2m, 0, c0_3, 0)
+        _lib.check(self.lib.yad_resize_w(c0_3.data_ptr(), self.dtype, B, W2, 64, 64, 0, 0, cat_b3.data_ptr(), 256, 64, s()), "pairavg")
+        _lib.check(self.lib.yad_resize_w(cat_n4.data_ptr(), self.dtype, B, W4, 128, 256, 0, 1, cat_b3.data_ptr(), 256, 128, s()), "up2")
+        self._conv(n["b3o"], cat_b3, 0, b3, 0)
+        self._repblock(plan, "rb31", self.rep["rep_block3_1"], b3, 0, cat_n3, 0)   # p3
+        # BiC2 -> RepBlock2_1 -> n2 (sm head)
+        cat_b2 = self._buf(plan, "cat_b2", B, 1, W2, 256)
+        c0_2 = self._buf(plan, "b2.c0", B, 1, W1, 64)
+        b2 = self._buf(plan, "b2", B, 1, W2, 128)
+        self._conv(n["b2c1"], f2m, 0, cat_b2, 0)
+        self._conv(n["b2c0"], f1m, 0, c0_2, 0)
+        _lib.check(self.lib.yad_resize_w(c0_2.data_ptr(), self.dtype, B, W1, 64, 64, 0, 0, cat_b2.data_ptr(), 256, 64, s()), "pairavg")
+        _lib.check(self.lib.yad_resize_w(cat_n3.data_ptr(), self.dtype, B, W3, 128, 256, 0, 1, cat_b2.data_ptr(), 256, 128, s()), "up2")
+        self._conv(n["b2o"], cat_b2, 0, b2, 0)
+        hl = _ceil(self.n_head, 64) if bf else self.n_head     # head channel pitch
+        h32 = _ceil(self.n_head, 4)                            # fp32 head copies fed to the decoder
+        n2 = self._buf(plan, "n2", B, 1, W2, hl, zero=True)
+        n3 = self._buf(plan, "n3", B, 1, W3, hl, zero=True)
+        n4 = self._buf(plan, "n4", B, 1, W4, hl, zero=True)
+        if bf:
+            n2f = self._buf(plan, "n2f", B, 1, W2, h32, zero=True, dtype=torch.float32)
+            n3f = self._buf(plan, "n3f", B, 1, W3, h32, zero=True, dtype=torch.float32)
+            n4f = self._buf(plan, "n4f", B, 1, W4, h32, zero=True, dtype=torch.float32)
+        else:
+            n2f, n3f, n4f = None, None, None
+        self._repblock(plan, "rb21", self.rep["rep_block2_1"], b2, 0, n2, 0, out2=n2f)
+        self._conv(n["ds2"], n2, 0, cat_n3, 128)
+        self._repblock(plan, "rb32", self.rep["rep_block3_2"], cat_n3, 0, n3, 0, out2=n3f)
+        self._conv(n["ds3"], n3, 0, cat_n4, 128)
+        self._repblock(plan, "rb41", self.rep["rep_block4_1"], cat_n4, 0, n4, 0, out2=n4f)
+        heads = [n2f, n3f, n4f] if bf else [n2, n3, n4]
+        if taps is not None:
+            taps["heads"] = [h.reshape(B, h.shape[2], h.shape[3])[..., : self.n_head].float().clone() for h in heads]
+        return heads
+
+    def run_decode(self, heads: List[torch.Tensor], B: int, T: int, L_res: int) -> torch.Tensor:
+        G = [h.shape[2] for h in heads]
+        rows = sum(G) * self.A
+        preds = torch.empty((B, rows, self.E), device=self.dev, dtype=torch.float32)
+        hp = (C.c_void_p * 3)(*[h.data_ptr() for h in heads])
+        Gs = (C.c_int32 * 3)(*G)
+        lds = (C.c_int32 * 3)(*[h.shape[3] for h in heads])
+        st = (C.c_int32 * 3)(*[T // g for g in G])                       # stride = spectral_size // grid_size
+        anc = (C.c_float * (3 * self.A))(*self.anchors_s.tolist())
+        center_scaler = T / (L_res / self.cfg["new_sample_rate"])        # _architecture.py:145
+        rc = self.lib.yad_decode(hp, Gs, lds, st, 3, F32, anc, self.A, self.nc, center_scaler, float(self.cfg["sample_duration"]),
+                                 B, preds.data_ptr(), self._stream())
+        _lib.check(rc, "decode")
+        return preds
+
+    def _plan(self, key) -> dict:
+        plans = getattr(self._tls, "plans", None)
+        if plans is None:
+            plans = self._tls.plans = {}
+        if key not in plans:
+            if len(plans) >= 4:          # bound the cached workspaces per thread
+                plans.pop(next(iter(plans)))
+            plans[key] = {}
+        return plans[key]
+
+    def run(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """x [B,1,L] f32 on the engine's device -> preds [B, P, 3+nc] f32 (combined scales)."""
+        if x.device != self.dev:
+            raise RuntimeError(f"input on {x.device}, model on {self.dev}")
+        B, _, L = x.shape
+        plan = self._plan((B, L))
+        with torch.cuda.device(self.dev):
+            xs = self.run_frontend(x, plan, taps)
+            heads = self.run_cnn(xs, plan, taps)
+            L_res = -(-self.rs_P * L // self.rs_O)
+            return self.run_decode(heads, B, xs.shape[-1], L_res)

@@ -1,0 +1,303 @@
+"""Drop-in ``AudioDetectionNetwork`` (reference: modules/_architecture.py:10-189).
+
+Same constructor, ``forward(x, combine_scales)``, ``inference()``, ``init_zeros_taper_window`` and
+state-dict key set as the reference, so a reference checkpoint loads unchanged and the object can be
+handed to the reference's ``inference.py`` / ``pipeline/_trainer.py``.  The ``nn.Module`` tree below only
+*holds* parameters and buffers (names mirror modules/_common.py and modules/_backbone.py); ``forward``
+never calls ``nn.Conv2d.forward`` - it runs the sm_100a kernels through :mod:`engine`.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+import yaml
+
+from . import frontend_consts as fc
+from .config import DEFAULT_CONFIG_PATH
+
+
+def _unsupported(what: str):
+    raise NotImplementedError(f"yad_b200: {what} is not built (no silent fallback); see DESIGN.md 'out of scope'")
+
+
+class _NoForward(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - holders are never called
+        raise RuntimeError("parameter holder: the computation runs in yad_b200.engine, not in nn.Module.forward")
+
+
+# ---------------------------------------------------------------- neck holders (modules/_common.py)
+class ConvBorINorm(_NoForward):
+    """conv(+bias) -> BatchNorm2d -> LeakyReLU(0.2).  ref: modules/_common.py:7-48."""
+
+    def __init__(self, cin: int, cout: int, kernel_size, stride=1, padding=None, bias: bool = True, activation: bool = True):
+        super().__init__()
+        ks = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        if padding is None:
+            padding = tuple(k // 2 for k in ks)
+        self.conv = nn.Conv2d(cin, cout, kernel_size=ks, stride=stride, padding=padding, bias=bias)
+        self.norm = nn.BatchNorm2d(cout)
+        self.has_activation = activation
+
+
+class RepVGGBlock(_NoForward):
+    """ref: modules/_common.py:51-145.  Train-form: conv3x3 / conv1x1 / identity-BN branches, each branch
+    ConvBorINorm keeps its own LeakyReLU.  After ``toggle_inference_mode`` only
+    ``conv_reparam`` (3x3, bias) remains - a *different function* from the train-form."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.inference_mode = False
+        self.conv3x3 = ConvBorINorm(cin, cout, (3, 3), padding=1, bias=False)
+        self.conv1x1 = ConvBorINorm(cin, cout, (1, 1), padding=0, bias=False)
+        self.identity = nn.BatchNorm2d(cout) if cin == cout else nn.Identity()
+
+    @staticmethod
+    def _merge(w: torch.Tensor, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+        std = torch.sqrt(bn.running_var + bn.eps)
+        return (bn.weight / std).reshape(-1, 1, 1, 1) * w, ((-bn.running_mean * bn.weight) / std) + bn.bias
+
+    @torch.no_grad()
+    def reparameterize(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Linear fold of the three branches (modules/_common.py:97-133)."""
+        w3, b3 = self._merge(self.conv3x3.conv.weight, self.conv3x3.norm)
+        w1, b1 = self._merge(self.conv1x1.conv.weight, self.conv1x1.norm)
+        w = w3 + nn.functional.pad(w1, [1, 1, 1, 1])
+        b = b3 + b1
+        if isinstance(self.identity, nn.BatchNorm2d):
+            eye = torch.eye(self.in_channels, device=w.device, dtype=w.dtype).reshape(self.in_channels, self.in_channels, 1, 1)
+            wi, bi = self._merge(eye, self.identity)
+            w = w + nn.functional.pad(wi, [1, 1, 1, 1])
+            b = b + bi
+        return w, b
+
+    def toggle_inference_mode(self):
+        w, b = self.reparameterize()
+        self.conv_reparam = nn.Conv2d(self.in_channels, self.out_channels, kernel_size=(3, 3), stride=1, padding=1)
+        self.conv_reparam.weight.data = w
+        self.conv_reparam.bias.data = b
+        del self.conv3x3, self.conv1x1, self.identity   # a second call raises AttributeError, like the reference
+        self.inference_mode = True
+
+
+class RepBlock(_NoForward):
+    def __init__(self, cin: int, cout: int, n: int = 2):
+        super().__init__()
+        self.conv1 = RepVGGBlock(cin, cout)
+        self.blocks = nn.Sequential(*[RepVGGBlock(cout, cout) for _ in range(n - 1)]) if n > 1 else nn.Identity()
+
+
+class BiCModule(_NoForward):
+    def __init__(self, c1_in: int, c0_in: int, p2_in: int, cout: int, e: float = 0.5):
+        super().__init__()
+        ch = int(cout * e)
+        self.conv_c1 = ConvBorINorm(c1_in, ch, 1)
+        self.conv_c0 = ConvBorINorm(c0_in, ch, 1)
+        self.conv_out = ConvBorINorm(ch + ch + p2_in, cout, 1)
+
+
+class CSPSPPFModule(_NoForward):
+    def __init__(self, cin: int, cout: int, e: float = 0.5):
+        super().__init__()
+        ch = int(cout * e)
+        self.conv_1_3_4 = nn.Sequential(ConvBorINorm(cin, ch, 1), ConvBorINorm(ch, ch, 3), ConvBorINorm(ch, ch, 1))
+        self.conv2 = ConvBorINorm(cin, ch, 1)
+        self.conv5 = ConvBorINorm(ch * 4, ch, 1)
+        self.conv6 = ConvBorINorm(ch, ch, 3)
+        self.conv7 = ConvBorINorm(ch * 2, cout, 1)
+
+
+class MultiScaleFmapModule(_NoForward):
+    """RepBi-PAN neck + heads.  ref: modules/_common.py:218-265."""
+
+    def __init__(self, c1: int, c2: int, c3: int, c4: int, out_channels: int):
+        super().__init__()
+        ch = 128
+        self.cspsppf = CSPSPPFModule(c4, ch)
+        self.bic2 = BiCModule(c2, c1, ch, ch)
+        self.bic3 = BiCModule(c3, c2, ch, ch)
+        self.rep_block2_1 = RepBlock(ch, out_channels)
+        self.rep_block3_1 = RepBlock(ch, ch)
+        self.rep_block3_2 = RepBlock(ch * 2, out_channels)
+        self.rep_block4_1 = RepBlock(ch * 2, out_channels)
+        self.conv2_downsample = ConvBorINorm(out_channels, ch, 3, stride=(1, 2))
+        self.conv3_downsample = ConvBorINorm(out_channels, ch, 3, stride=(1, 2))
+
+
+# ---------------------------------------------------------------- backbone holders (modules/_backbone.py:119-152)
+class BasicBlock(_NoForward):
+    """torchvision BasicBlock parameter layout (conv1, bn1, conv2, bn2, downsample.{0,1})."""
+
+    def __init__(self, cin: int, cout: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.stride = stride
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+        else:
+            self.downsample = None
+
+
+class ResNetBackBone(_NoForward):
+    def __init__(self, in_channels: int, dropout: float = 0.0, block: str = "BasicBlock",
+                 block_layers: Optional[Iterable[int]] = None):
+        super().__init__()
+        if block not in ("BasicBlock",) and getattr(block, "__name__", None) != "BasicBlock":
+            _unsupported(f"resnet_config.block={block!r} (only BasicBlock, the reference default)")
+        layers = list(block_layers or [3, 4, 6, 3])
+        self.in_channels = in_channels
+        self.dropout_p = dropout
+        self.conv1 = nn.Conv2d(in_channels, 64, (7, 7), (2, 2), (3, 3), bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        cin = 64
+        for li, (n, cout) in enumerate(zip(layers, (64, 128, 256, 512))):
+            blocks = []
+            for bi in range(n):
+                blocks.append(BasicBlock(cin, cout, 2 if (li > 0 and bi == 0) else 1))
+                cin = cout
+            setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
+        self.conv2 = nn.Conv2d(64, 64, (7, 7), (2, 2), (3, 3), bias=False)
+        self.fmap1_ch, self.fmap2_ch, self.fmap3_ch, self.fmap4_ch = 64, 128, 256, 512
+
+
+class _Buf(nn.Module):
+    """Holds the registered buffers of a torchaudio transform under the reference's names."""
+
+    def __init__(self, **bufs):
+        super().__init__()
+        for k, v in bufs.items():
+            if isinstance(v, nn.Module):
+                self.add_module(k, v)
+            else:
+                self.register_buffer(k, v)
+
+
+# ---------------------------------------------------------------- the model
+class AudioDetectionNetwork(nn.Module):
+    def __init__(self, num_classes: int, config: Union[str, Dict[str, Any]] = DEFAULT_CONFIG_PATH,
+                 compute_dtype: str = "bf16"):
+        super().__init__()
+        if isinstance(config, str):
+            with open(config, "r") as f:
+                self.config = yaml.safe_load(f)
+        elif isinstance(config, dict):
+            self.config = config
+        else:
+            raise ValueError(f"config is expected to be str or dict type got {type(config)}")
+        cfg = self.config
+        self.num_classes = num_classes
+        self.out_channels = cfg["num_anchors"] * (3 + num_classes)
+        self.compute_dtype = compute_dtype
+
+        mc = cfg["melspectrogram_config"]
+        mk = cfg["mfcc_config"]["melkwargs"]
+        for name, c in (("melspectrogram_config", mc), ("mfcc_config.melkwargs", mk)):
+            if not (c["n_fft"] == 1000 and c["hop_length"] == 1000 and c["n_mels"] == 32 and c["center"] is False
+                    and c["win_length"] in (None, 1000) and c["power"] == 2):
+                _unsupported(f"{name}={c} (kernels are built for n_fft=hop=1000, 32 mels, center=False, power=2)")
+        if mc != mk:
+            _unsupported("different mel settings for MelSpectrogram and MFCC (the mel plane is computed once)")
+        if cfg["mfcc_config"]["n_mfcc"] != 32:
+            _unsupported(f"n_mfcc={cfg['mfcc_config']['n_mfcc']} (kernel is built for 32)")
+        sr = cfg["new_sample_rate"]
+        kern, self._rs_width, self._rs_orig, self._rs_new = fc.sinc_resample_kernel(cfg["sample_rate"], sr)
+        fb = fc.mel_filterbank(501, 0.0, float(sr // 2), 32, sr, mc["norm"], mc["mel_scale"])
+        win = torch.hann_window(1000, periodic=True)
+        self.resampler = _Buf(kernel=kern)
+        self.melspectogram_tfmr = _Buf(spectrogram=_Buf(window=win), mel_scale=_Buf(fb=fb))
+        self.mfcc_tfmr = _Buf(dct_mat=fc.dct_ortho(32, 32),
+                              MelSpectrogram=_Buf(spectrogram=_Buf(window=win.clone()), mel_scale=_Buf(fb=fb.clone())))
+        self.register_buffer("taper_window", torch.empty(0), persistent=True)
+
+        dur = cfg["sample_duration"]
+        ta = cfg["train_anchors"]
+        self.sm_anchors = nn.Parameter(torch.FloatTensor(cfg["anchors"]["sm"]) / dur, requires_grad=ta)
+        self.md_anchors = nn.Parameter(torch.FloatTensor(cfg["anchors"]["md"]) / dur, requires_grad=ta)
+        self.lg_anchors = nn.Parameter(torch.FloatTensor(cfg["anchors"]["lg"]) / dur, requires_grad=ta)
+
+        if cfg["backbone"] != "resnet":
+            _unsupported(f"backbone={cfg['backbone']!r} (SURVEY section 8(f) N3; only the default 'resnet' path is built)")
+        self.feature_extractor = ResNetBackBone(2, dropout=cfg["dropout"], block_layers=cfg["block_layers"],
+                                                **cfg["resnet_config"])
+        fe = self.feature_extractor
+        self.multiscale_module = MultiScaleFmapModule(fe.fmap1_ch, fe.fmap2_ch, fe.fmap3_ch, fe.fmap4_ch,
+                                                      out_channels=self.out_channels)
+        self.apply(self.xavier_init_weights)
+        self._engine_cache: Dict[Any, Any] = {}
+
+    # ---- reference API -------------------------------------------------------------------------
+    def xavier_init_weights(self, m: nn.Module):
+        if isinstance(m, nn.Conv2d):
+            nn.init.xavier_uniform_(m.weight)
+            if torch.is_tensor(m.bias):
+                m.bias.data.fill_(0.01)
+
+    def init_zeros_taper_window(self, taper_window: torch.Tensor):
+        self.taper_window = torch.zeros_like(taper_window)
+
+    def inference(self):
+        """Deploy form: fold every RepVGG block (modules/_architecture.py:171-180).  One-shot."""
+        self.eval()
+        for m in list(self.modules()):
+            if isinstance(m, RepVGGBlock):
+                m.toggle_inference_mode()
+        self._engine_cache.clear()
+
+    @staticmethod
+    def scale_input(x: torch.Tensor, e: float = 1e-5) -> torch.Tensor:
+        """Kept for API parity (modules/_architecture.py:182-189); the kernel path fuses this."""
+        mu = x.mean(dim=(-2, -1))[:, :, None, None]
+        std = x.std(dim=(-2, -1))[:, :, None, None]
+        return (x - mu) / (std + e)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def _engine(self):
+        from .engine import InferenceEngine
+        ver = sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
+        dev = self.sm_anchors.device
+        key = (str(dev), self.compute_dtype)
+        ent = self._engine_cache.get(key)
+        if ent is None or ent[0] != ver:
+            ent = (ver, InferenceEngine(self, dev, self.compute_dtype))
+            self._engine_cache[key] = ent
+        return ent[1]
+
+    def forward(self, x: torch.Tensor, combine_scales: bool = False, taps: Optional[Dict[str, torch.Tensor]] = None):
+        if not x.is_cuda:
+            raise RuntimeError("yad_b200.AudioDetectionNetwork runs on sm_100a only; move the input and the model to "
+                               "a CUDA device (there is no CPU fallback)")
+        if self.training:
+            _unsupported("train-mode forward (batch-statistics BatchNorm, dropout, autograd) - call .eval()")
+        if self.config["taper_input"]:
+            _unsupported("taper_input=true")
+        if x.ndim != 3 or x.shape[1] != 1:
+            raise ValueError(f"expected input of shape [N, 1, n_time], got {tuple(x.shape)}")
+        preds = self._engine().run(x, taps=taps)
+        if combine_scales:
+            return preds
+        B, E = x.shape[0], self.num_classes + 3
+        A = self.config["num_anchors"]
+        out, r0 = [], 0
+        for G in self._engine().grids(x.shape[-1]):
+            out.append(preds[:, r0:r0 + G * A].reshape(B, G, A, E))
+            r0 += G * A
+        return tuple(out)
+
+    def __deepcopy__(self, memo):
+        # engines hold device workspaces; a copy (EMA shadow model) rebuilds its own lazily
+        cache, self._engine_cache = self._engine_cache, {}
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            import copy as _copy
+            for k, v in self.__dict__.items():
+                setattr(new, k, _copy.deepcopy(v, memo))
+        finally:
+            self._engine_cache = cache
+        return new

@@ -1,0 +1,44 @@
+"""Batch sharding across the GPUs of one box (one process per GPU, torch.distributed for plumbing).
+
+Clips are independent end to end (no cross-clip op in frontend, CNN, decode or NMS - NMS groups by clip
+id, inference.py:75-80), so the inference path partitions the clip range contiguously across ranks and
+needs NO data-path collective.  The only communication is for reporting: segment counts (so a caller can
+turn rank-local clip ids into global ones) and the max-over-ranks device time."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split clips[r*N/W : (r+1)*N/W]."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    return (n_items * rank) // world, (n_items * (rank + 1)) // world
+
+
+def globalize_batch_idxs(batch_idxs: torch.Tensor, n_items: int, rank: int, world: int) -> torch.Tensor:
+    """Rank-local clip ids (as returned by process_model_outputs) -> ids in the unsharded batch."""
+    lo, _ = shard_bounds(n_items, rank, world)
+    return batch_idxs + lo
+
+
+def gather_counts(local_count: int, device=None) -> List[int]:
+    """all_gather of one integer per rank (segment counts); works on gloo (CPU) and nccl (CUDA)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return [int(local_count)]
+    t = torch.tensor([int(local_count)], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [int(o.item()) for o in out]
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Device-timed milliseconds -> max over ranks (the number every multi-GPU figure is quoted on)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,124 @@
+"""Training-side pieces of the hot path on sm_100a kernels."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from copy import deepcopy
+from typing import List, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def build_target_by_scale(targets: torch.Tensor, fmap_shape: Union[int, torch.Size], anchors: Union[Sequence[float], torch.Tensor],
+                          anchor_threshold: float = 4.0, sample_duration: float = 60, edge_threshold: float = 0.5,
+                          ) -> Tuple[List[torch.Tensor], torch.Tensor, torch.Tensor]:
+    """Drop-in for ``AudioDataset.build_target_by_scale`` (reference: dataset.py:286-365).
+
+    targets [T,4] f32 = (batch_idx, cls, centre_s, dur_s) on a CUDA device.  Returns
+    ([batch_idx, grid_idx, anchor_idx] i64, classes i64, cw [M,2] f32) in the reference's row order."""
+    if not targets.is_cuda:
+        raise RuntimeError("yad_b200.build_target_by_scale needs CUDA tensors (no CPU fallback)")
+    if isinstance(fmap_shape, torch.Size):
+        fmap_shape = fmap_shape[0]
+    dev = targets.device
+    lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+    anc = torch.as_tensor(anchors, dtype=torch.float32).to(dev).contiguous()
+    t = targets.contiguous().float()
+    T, A = t.shape[0], anc.shape[0]
+    cap = max(1, 3 * A * T)
+    bi = torch.empty(cap, device=dev, dtype=torch.int64)
+    gi = torch.empty(cap, device=dev, dtype=torch.int64)
+    ai = torch.empty(cap, device=dev, dtype=torch.int64)
+    cl = torch.empty(cap, device=dev, dtype=torch.int64)
+    cw = torch.empty((cap, 2), device=dev, dtype=torch.float32)
+    n = torch.zeros(1, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        rc = lib.yad_build_targets(t.data_ptr(), T, anc.data_ptr(), A, int(fmap_shape), float(anchor_threshold),
+                                   float(sample_duration), float(edge_threshold), bi.data_ptr(), gi.data_ptr(), ai.data_ptr(),
+                                   cl.data_ptr(), cw.data_ptr(), n.data_ptr(), _stream(dev))
+    _lib.check(rc, "build_targets")
+    M = int(n.item())     # data-dependent shape, as in the reference (boolean-mask indexing syncs too)
+    return [bi[:M], gi[:M], ai[:M]], cl[:M], cw[:M]
+
+
+class FusedAdamEMA:
+    """torch.optim.Adam (L2 weight decay; train.py:83-90, config.yaml:75-80) fused with the EMA shadow update
+    (smoothener/_ema.py:20-26) over ONE flat fp32 arena: 1 launch per step instead of ~10 per tensor.
+
+    ``params`` are re-pointed into the arena (views), so the model keeps working unchanged."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_momentum: float = 0.0,
+                 ema_N: int = 2000, use_ema: bool = False):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdamEMA needs CUDA parameters (no CPU fallback)")
+        self.dev = dev
+        self.lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.step_count = 0
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        o = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + k].view_as(p.data)
+            p.grad = self.grad[o:o + k].view_as(p.data)
+            o += k
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.use_ema = use_ema
+        self.ema = self.flat.clone() if use_ema else None
+        self.ema_momentum, self.ema_N = ema_momentum, ema_N
+
+    def ema_m(self, n: int) -> float:
+        return 1 - ((1 - self.ema_momentum) * (1 - math.exp(-n / self.ema_N)))
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self):
+        self.step_count += 1
+        m = self.ema_m(self.step_count) if self.use_ema else 0.0
+        with torch.cuda.device(self.dev):
+            rc = self.lib.yad_adam_ema_step(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                            _lib.ptr(self.ema), self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                            self.wd, self.step_count, m, _stream(self.dev))
+        _lib.check(rc, "adam_ema_step")
+
+
+class EMAParamsSmoothener:
+    """Drop-in for smoothener/_ema.py:7-32 (parameters only; warm-up momentum) using one fused launch per
+    update over flattened parameter arenas."""
+
+    def __init__(self, model, momentum: float = 0.002, num_updates: int = 0, N: int = 2_000):
+        self.model = model
+        self.ema_model = deepcopy(model)
+        self.ema_model.eval()
+        self.num_updates = num_updates
+        self.momentum_ = lambda n: 1 - ((1 - momentum) * (1 - math.exp(-n / N)))
+        for p in self.ema_model.parameters():
+            p.requires_grad_(False)
+
+    def update(self):
+        self.num_updates += 1
+        m = self.momentum_(self.num_updates)
+        with torch.no_grad():
+            ema = [e.data for e in self.ema_model.parameters() if e.dtype.is_floating_point]
+            src = [p.data for e, p in zip(self.ema_model.parameters(), self.model.parameters()) if e.dtype.is_floating_point]
+            torch._foreach_mul_(ema, 1 - m)
+            torch._foreach_add_(ema, src, alpha=m)
+
+    def get_ema_state_dict(self):
+        return self.ema_model.state_dict()
+
+    def load_state_dict(self, state_dict):
+        self.ema_model.load_state_dict(state_dict)
