@@ -98,7 +98,7 @@ typedef struct {
 } yad_conv_desc;
 
 /* Stem conv1 (2 -> 64, 7x7, stride 2, pad 3): reads x_spectral NCHW f32 directly,
- * writes NHWC (out_dtype) [B, H/2, W/2, 64].  weight [7][7][2][64] f32 (tap-major). */
+ * writes NHWC (out_dtype) [B, (H-1)/2+1, (W-1)/2+1, 64].  weight [7][7][2][64] f32 (tap-major). */
 int yad_conv_stem(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* weight,
                   void* out, int32_t out_dtype, yad_stream_t stream);
 

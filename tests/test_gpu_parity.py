@@ -230,6 +230,21 @@ def test_decode_vs_oracle(cuda_dev, ref_state_dict):
 
 
 # ------------------------------------------------------------------ NMS (S4) - bit exact
+def _canon(seg, bidx):
+    """The reference orders a clip's segments with an argsort that is not declared stable (inference.py:95), so rows
+    whose sort key (centre) ties - the planted zero-width twins - have no defined order: sort such runs by confidence."""
+    seg, bidx = np.array(seg), np.asarray(bidx)
+    i = 0
+    while i < len(seg):
+        j = i + 1
+        while j < len(seg) and bidx[j] == bidx[i] and seg[j, 3] == seg[i, 3] and seg[j, 4] == seg[i, 4]:
+            j += 1
+        if j - i > 1:
+            seg[i:j] = seg[i:j][np.argsort(seg[i:j, 0], kind="stable")]
+        i = j
+    return seg
+
+
 def _check_nms(o, iou, cthr, gold_seg=None, gold_bidx=None):
     r = yad_b200.nms_raw(o.cuda(), iou, cthr, want_taps=True)
     conf, boxes = r["conf"].cpu(), r["boxes"].cpu()
@@ -259,7 +274,8 @@ def test_nms_keep_sets_and_segments(gold, name, B, iou, cthr, cuda_dev):
         np.testing.assert_array_equal(keep[b, :nk[b]] + b * 630, ref[(ref >= b * 630) & (ref < (b + 1) * 630)])
     seg, bidx = yad_b200.process_model_outputs(o.cuda(), iou, cthr)
     np.testing.assert_array_equal(bidx.cpu().numpy(), g[f"bidx_{name}_{iou}_{cthr}"])
-    np.testing.assert_allclose(seg.cpu().numpy(), g[f"seg_{name}_{iou}_{cthr}"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(_canon(seg.cpu().numpy(), bidx.cpu().numpy()),
+                               _canon(g[f"seg_{name}_{iou}_{cthr}"], g[f"bidx_{name}_{iou}_{cthr}"]), rtol=2e-6, atol=1e-7)
 
 
 def test_nms_edge_cases(gold, cuda_dev):

@@ -17,7 +17,7 @@ conv_stem_kernel(const float* __restrict__ x, int H, int W, const float* __restr
   // grid: (Ho, B). One CTA = one output row; loops over 32-pixel column tiles.
   __shared__ __align__(16) float s_w[STEM_K * STEM_K * STEM_CI][STEM_CO];          // 25 KB, [tap][co]
   __shared__ float s_x[STEM_CI][STEM_K][2 * STEM_TW + STEM_K - 2 + 1];              // patch, 70 cols
-  const int Ho = H / 2, Wo = W / 2;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;   // (H + 2*3 - 7) / 2 + 1
   const int ho = blockIdx.x, b = blockIdx.y;
   for (int i = threadIdx.x; i < STEM_K * STEM_K * STEM_CI * STEM_CO; i += STEM_THREADS) (&s_w[0][0])[i] = wgt[i];
   const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;  // pixel within tile, 16-channel group
@@ -156,11 +156,11 @@ extern "C" {
 int yad_conv_stem(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* weight, void* out,
                   int32_t out_dtype, yad_stream_t stream) {
   YAD_CHECK_ARG(x_nchw && weight && out, "yad_conv_stem: null pointer");
-  YAD_CHECK_ARG(H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "yad_conv_stem: H=%d W=%d must be even", H, W);
+  YAD_CHECK_ARG(H >= 1 && W >= 1, "yad_conv_stem: bad H=%d W=%d", H, W);
   YAD_CHECK_ARG(out_dtype == YAD_F32 || out_dtype == YAD_BF16, "yad_conv_stem: bad out dtype %d", out_dtype);
   YAD_CHECK_ARG(B <= 65535, "yad_conv_stem: B=%lld exceeds grid.y", (long long)B);
   if (B == 0) return YAD_OK;
-  dim3 grid((unsigned)(H / 2), (unsigned)B);
+  dim3 grid((unsigned)((H - 1) / 2 + 1), (unsigned)B);
   if (out_dtype == YAD_F32)
     yad::conv_stem_kernel<float><<<grid, yad::STEM_THREADS, 0, (cudaStream_t)stream>>>(x_nchw, H, W, weight, (float*)out);
   else

@@ -281,9 +281,9 @@ class InferenceEngine:
         B, _, H0, T = xs.shape
         bf = self.dtype == BF16
         s = self._stream
-        c1 = self._buf(plan, "c1", B, H0 // 2, T // 2, 64)
+        c1 = self._buf(plan, "c1", B, (H0 - 1) // 2 + 1, (T - 1) // 2 + 1, 64)
         _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
-        H, W = (H0 // 2 + 6 - 7) // 2 + 1, (T // 2 + 6 - 7) // 2 + 1
+        H, W = (c1.shape[1] + 6 - 7) // 2 + 1, (c1.shape[2] + 6 - 7) // 2 + 1
         cur = self._buf(plan, "c2", B, H, W, 64)
         self._conv(self.conv2, c1, 0, cur, 0)
         fmaps = []

@@ -31,6 +31,9 @@ def build_target_by_scale(targets: torch.Tensor, fmap_shape: Union[int, torch.Si
     anc = torch.as_tensor(anchors, dtype=torch.float32).to(dev).contiguous()
     t = targets.contiguous().float()
     T, A = t.shape[0], anc.shape[0]
+    if T == 0:
+        z = torch.zeros(0, device=dev, dtype=torch.int64)
+        return [z, z.clone(), z.clone()], z.clone(), torch.zeros((0, 2), device=dev, dtype=torch.float32)
     cap = max(1, 3 * A * T)
     bi = torch.empty(cap, device=dev, dtype=torch.int64)
     gi = torch.empty(cap, device=dev, dtype=torch.int64)
