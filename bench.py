@@ -139,13 +139,17 @@ def time_stages(model, x, reps=3):
         _lib.check(eng.lib.yad_frontend_mel_power(xc.data_ptr(), B, L, eng.rs_P, eng.rs_O, eng.rs_width, eng.rs_taps.data_ptr(),
                                                   eng.rs_base.data_ptr(), eng.rs_window_len, eng.win.data_ptr(), eng.tw.data_ptr(),
                                                   eng.fb_val.data_ptr(), eng.fb_bin.data_ptr(), eng.fb_start.data_ptr(),
-                                                  mel.data_ptr(), T, eng._stream()), "fe_a")
+                                                  eng.fb_val.numel(), mel.data_ptr(), T, eng._stream()), "fe_a")
     out["frontend_mel_ms"], _ = timed(fe_a)
     out["frontend_ms"], xs = timed(lambda: eng.run_frontend(x, plan))
 
     def stem():
         c1 = plan["c1"]
-        _lib.check(eng.lib.yad_conv_stem(xs.data_ptr(), B, 32, T, eng.stem_w.data_ptr(), c1.data_ptr(), eng.dtype, eng._stream()), "stem")
+        if eng.dtype == _lib.BF16:
+            _lib.check(eng.lib.yad_conv_stem_tc(xs.data_ptr(), B, 32, T, eng.stem_w_tc.data_ptr(), c1.data_ptr(), eng.stem_flags,
+                                                eng._stream()), "stem_tc")
+        else:
+            _lib.check(eng.lib.yad_conv_stem(xs.data_ptr(), B, 32, T, eng.stem_w.data_ptr(), c1.data_ptr(), eng.dtype, eng._stream()), "stem")
     out["stem_ms"], _ = timed(stem)
     out["cnn_ms"], heads = timed(lambda: eng.run_cnn(xs, plan))
     L_res = -(-eng.rs_P * L // eng.rs_O)

@@ -65,15 +65,16 @@ int yad_init(int device);
  *   window_len                        max(tap_base) + YAD_FE_TPQ (span of the padded signal one hop reads)
  *   window     [1000]                 f32  analysis window
  *   twiddle    [1000][2]              f32  exp(-2*pi*i*k/1000), built in fp64 by the host
- *   fb_val [nnz] f32, fb_bin [nnz] i32, fb_start [33] i32   mel filterbank in CSR form over mel bands
+ *   fb_val [nnz] f32, fb_bin [nnz] i32, fb_start [33] i32   mel filterbank in CSR form over mel bands; the
+ *                                          bins of one band must be contiguous (triangular filters are)
  *   mel        [B, 32, T]             f32  (T frames; T*1000 <= ceil(P*L/O))
  */
 #define YAD_FE_TPQ 20
 int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
                            const float* taps, const int32_t* tap_base, int32_t window_len,
                            const float* window, const float* twiddle, const float* fb_val,
-                           const int32_t* fb_bin, const int32_t* fb_start, float* mel, int64_t T,
-                           yad_stream_t stream);
+                           const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
+                           int64_t T, yad_stream_t stream);
 
 /* Stage B: mel power [B,32,T] -> x_spectral [B,2,32,T] f32 (channel 0 = standardised
  * dB-mel, channel 1 = standardised dB-of-MFCC).  One CTA per clip; T <= 1024.
@@ -101,6 +102,13 @@ typedef struct {
  * writes NHWC (out_dtype) [B, (H-1)/2+1, (W-1)/2+1, 64].  weight [7][7][2][64] f32 (tap-major). */
 int yad_conv_stem(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* weight,
                   void* out, int32_t out_dtype, yad_stream_t stream);
+
+/* The same stem on the tcgen05 tensor cores (bf16 operands, fp32 accumulate, bf16 NHWC output).  The CTA builds the
+ * im2col A tile itself (C = 2 defeats TMA) in the no-swizzle K-major UMMA layout.
+ * weight_packed: bf16 [64][112] (K index = kh*16 + kw*2 + c, zero for kw = 7) stored as 8x8 core matrices:
+ * element (n, k) at byte (n/8)*1792 + (k/8)*128 + (n%8)*16 + (k%8)*2.  flags: bit 0 = debug (swap LBO/SBO). */
+int yad_conv_stem_tc(const float* x_nchw, int64_t B, int32_t H, int32_t W, const void* weight_packed,
+                     void* out_bf16, int32_t flags, yad_stream_t stream);
 
 /* CUDA-core implicit GEMM (fp32 accumulate; in/out dtype f32 or bf16).
  * weight [kh][kw][Cin][Cout_pad] in `dtype`; bias [Cout] f32; residual/out NHWC. */

@@ -170,6 +170,26 @@ def test_stem_conv(cuda_dev):
         np.testing.assert_allclose(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy(), atol=tol, rtol=tol)
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 96), (1, 32, 960), (3, 32, 61), (2, 7, 300)])
+def test_stem_conv_tensor_core(shape, cuda_dev):
+    """tcgen05 stem vs F.conv2d on the same bf16-rounded operands (fp32 accumulate both; one bf16 output rounding)."""
+    lib = _lib.init(0)
+    B, H, W = shape
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, 2, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(64, 2, 7, 7, generator=g) * 0.1).bfloat16().float()
+    ref = F.conv2d(x, w, None, stride=2, padding=3)
+    wk = torch.zeros(64, 7, 16)
+    wk[:, :, :14] = w.permute(0, 2, 3, 1).reshape(64, 7, 14)
+    wp = wk.reshape(8, 8, 14, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16).to(cuda_dev)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.full((B, Ho, Wo, 64), 7.0, dtype=torch.bfloat16, device=cuda_dev)
+    flags = int(__import__("os").environ.get("YAD_STEM_FLAGS", "0"))
+    _lib.check(lib.yad_conv_stem_tc(x.to(cuda_dev).data_ptr(), B, H, W, wp.data_ptr(), out.data_ptr(), flags, _stream()), "stem_tc")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy(), atol=2e-2, rtol=1e-2)
+
+
 # ------------------------------------------------------------------ whole network (S2/S3)
 @pytest.mark.parametrize("form", ["train", "deploy"])
 def test_network_f32_vs_golden(models, gold, form, cuda_dev):

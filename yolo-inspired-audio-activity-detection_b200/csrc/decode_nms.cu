@@ -85,7 +85,7 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int E = 3 + nc;
-  const int W = (P + 31) >> 5;  // mask words per row
+  const int W = (P + 31) >> 5;  // alive-mask words
   int n_pad = 32;
   while (n_pad < P) n_pad <<= 1;
 
@@ -96,9 +96,10 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
   float* sarea = sx2 + n_pad;
   int32_t* s_order = reinterpret_cast<int32_t*>(sarea + n_pad);                       // [P]
   int32_t* s_keep = s_order + n_pad;                                                  // [P] kept sorted positions
-  uint32_t* mask = reinterpret_cast<uint32_t*>(s_keep + n_pad);                       // [P][W]
-  __shared__ int s_nkeep, s_nseg;
+  __shared__ uint32_t s_alive[NMS_MAXP / 32];
+  __shared__ int s_nseg;
 
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const float* pb = preds + (int64_t)b * P * E;
   const float y2 = fminf(fmaxf(box_h, 0.0f), duration);  // coords.clip(0, sample_duration) also hits y2
 
@@ -128,6 +129,10 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
       keys[i] = ~0ull;
     }
   }
+  for (int w = threadIdx.x; w < NMS_MAXP / 32; w += blockDim.x) {
+    const int lo = w << 5;
+    s_alive[w] = (lo + 32 <= P) ? 0xffffffffu : (lo >= P ? 0u : ((1u << (P - lo)) - 1u));
+  }
   __syncthreads();
   bitonic_sort_u64(keys, n_pad);
 
@@ -146,54 +151,52 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
   }
   __syncthreads();
 
-  // 3. suppression bit matrix: bit (i, j) set iff j > i and iou(i, j) > thr   (torchvision nms_kernel_impl)
+  // 3. greedy scan (torchvision nms_kernel_impl): pick the next alive box i in score order, then the whole CTA
+  //    evaluates row i on the fly - lane k of a warp tests box j = 32*w + k, so shared-memory reads are
+  //    conflict-free and only the rows of KEPT boxes are ever computed (no P x P matrix).
   const float hh = fmaxf(0.0f, __fsub_rn(y2, 0.0f));
-  for (int t = threadIdx.x; t < P * W; t += blockDim.x) {
-    const int i = t / W, wj = t % W;
-    uint32_t bits = 0;
-    const int j0 = wj << 5;
-    if (j0 + 31 > i) {
-      const float x1i = sx1[i], x2i = sx2[i], ai = sarea[i];
-      for (int k = 0; k < 32; ++k) {
-        const int j = j0 + k;
-        if (j > i && j < P) {
-          const float ww = fmaxf(0.0f, __fsub_rn(fminf(x2i, sx2[j]), fmaxf(x1i, sx1[j])));
-          const float inter = __fmul_rn(ww, hh);
-          const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, sarea[j]), inter));
-          if ((double)ovr > iou_thr) bits |= (1u << k);
-        }
+  int nk = 0, cur = 0;
+  while (true) {
+    // every warp finds the same next alive index >= cur
+    uint32_t wrd = (lane < W) ? s_alive[lane] : 0u;
+    const int cw = cur >> 5;
+    if (lane < cw) wrd = 0u;
+    if (lane == cw) wrd &= ~((1u << (cur & 31)) - 1u);
+    const unsigned nz = __ballot_sync(0xffffffffu, wrd != 0u);
+    if (nz == 0u) break;
+    const int fw = __ffs(nz) - 1;
+    const uint32_t fword = __shfl_sync(0xffffffffu, wrd, fw);
+    const int i = (fw << 5) + (__ffs(fword) - 1);
+    if (threadIdx.x == 0) s_keep[nk] = i;
+    ++nk;
+    const float x1i = sx1[i], x2i = sx2[i], ai = sarea[i];
+    __syncthreads();   // all warps have read s_alive before anyone clears bits
+    for (int w = (i >> 5) + warp; w < W; w += nwarps) {
+      const int j = (w << 5) + lane;
+      bool sup = false;
+      if (j > i && j < P) {
+        const float ww = fmaxf(0.0f, __fsub_rn(fminf(x2i, sx2[j]), fmaxf(x1i, sx1[j])));
+        const float inter = __fmul_rn(ww, hh);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, sarea[j]), inter));
+        sup = (double)ovr > iou_thr;   // NaN (two zero-area boxes) compares false: never suppresses
       }
+      const unsigned bits = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0 && bits) s_alive[w] &= ~bits;
     }
-    mask[t] = bits;
+    __syncthreads();
+    cur = i + 1;
   }
-  __syncthreads();
-
-  // 4. greedy scan by one warp: lane l owns removed-word l
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    uint32_t removed = 0;
-    int nk = 0;
-    for (int i = 0; i < P; ++i) {
-      const uint32_t wrd = __shfl_sync(0xffffffffu, removed, i >> 5);
-      if (!((wrd >> (i & 31)) & 1u)) {
-        if (lane == 0) s_keep[nk] = i;
-        ++nk;
-        if (lane < W) removed |= mask[i * W + lane];
-      }
-    }
-    if (lane == 0) s_nkeep = nk;
-  }
-  __syncthreads();
-  const int nk = s_nkeep;
   for (int i = threadIdx.x; i < P; i += blockDim.x)
     keep_out[(int64_t)b * P + i] = (i < nk) ? s_order[s_keep[i]] : -1;
   if (threadIdx.x == 0) n_keep_out[b] = nk;
   if (seg_rows == nullptr) return;
 
-  // 5. confidence filter + per-clip sort by centre (inference.py:85-99)
+  // 4. confidence filter + per-clip sort by centre (inference.py:85-99)
   if (threadIdx.x == 0) s_nseg = 0;
+  int n_pad2 = 32;
+  while (n_pad2 < nk) n_pad2 <<= 1;
   __syncthreads();
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) keys[i] = ~0ull;
+  for (int i = threadIdx.x; i < n_pad2; i += blockDim.x) keys[i] = ~0ull;
   __syncthreads();
   for (int i = threadIdx.x; i < nk; i += blockDim.x) {
     const int o = s_order[s_keep[i]];
@@ -206,7 +209,7 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
   }
   __syncthreads();
   const int ns = s_nseg;
-  bitonic_sort_u64(keys, n_pad);
+  bitonic_sort_u64(keys, n_pad2);
   for (int i = threadIdx.x; i < ns; i += blockDim.x) {
     const int o = s_order[s_keep[(int)(keys[i] & 0xffffffffu)]];
     const float* r = pb + (int64_t)o * E;
@@ -329,7 +332,8 @@ int yad_nms(const float* preds, int64_t B, int32_t P, int32_t nc, double iou_thr
   int n_pad = 32;
   while (n_pad < P) n_pad <<= 1;
   const int W = (P + 31) / 32;
-  const size_t smem = (size_t)n_pad * 8 + (size_t)n_pad * 4 * 6 + (size_t)P * W * 4;
+  const size_t smem = (size_t)n_pad * 8 + (size_t)n_pad * 4 * 6;
+  (void)W;
   if (smem > 48 * 1024)
     YAD_CUDA(cudaFuncSetAttribute(yad::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   yad::nms_kernel<<<(unsigned)B, yad::NMS_THREADS, smem, (cudaStream_t)stream>>>(

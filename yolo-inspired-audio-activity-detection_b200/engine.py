@@ -83,6 +83,7 @@ class InferenceEngine:
         self.E = 3 + self.nc
         self.n_head = self.A * self.E
         self._tls = threading.local()
+        self.stem_flags = int(__import__('os').environ.get('YAD_STEM_FLAGS', '0'))
         with torch.no_grad():
             self._pack_frontend(model)
             self._pack_cnn(model)
@@ -131,6 +132,11 @@ class InferenceEngine:
         dev = self.dev
         # stem conv1: raw (no BN / bias / activation before conv2, modules/_backbone.py:143-144); [7][7][2][64] f32
         self.stem_w = fe.conv1.weight.detach().to(dev, torch.float32).permute(2, 3, 1, 0).contiguous()
+        if self.dtype == BF16:
+            # tensor-core stem: [64][K=112] bf16, K = kh*16 + kw*2 + c, stored as 8x8 core matrices (no-swizzle K-major)
+            wk = torch.zeros(64, 7, 16, device=dev, dtype=torch.float32)
+            wk[:, :, :14] = fe.conv1.weight.detach().to(dev, torch.float32).permute(0, 2, 3, 1).reshape(64, 7, 14)
+            self.stem_w_tc = wk.reshape(8, 8, 14, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
         w2, b2 = _fold_bn(fe.conv2.weight, None, fe.bn1)
         self.conv2 = _Conv("fe.conv2", w2, b2, 2, 3, ACT_RELU, dev, self.dtype)
         self.stages = []
@@ -260,7 +266,7 @@ class InferenceEngine:
         rc = self.lib.yad_frontend_mel_power(x.data_ptr(), B, L, self.rs_P, self.rs_O, self.rs_width, self.rs_taps.data_ptr(),
                                              self.rs_base.data_ptr(), self.rs_window_len, self.win.data_ptr(), self.tw.data_ptr(),
                                              self.fb_val.data_ptr(), self.fb_bin.data_ptr(), self.fb_start.data_ptr(),
-                                             mel.data_ptr(), T, self._stream())
+                                             self.fb_val.numel(), mel.data_ptr(), T, self._stream())
         _lib.check(rc, "frontend_mel_power")
         tm = {}
         if taps is not None:
@@ -282,7 +288,11 @@ class InferenceEngine:
         bf = self.dtype == BF16
         s = self._stream
         c1 = self._buf(plan, "c1", B, (H0 - 1) // 2 + 1, (T - 1) // 2 + 1, 64)
-        _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
+        if bf:
+            _lib.check(self.lib.yad_conv_stem_tc(xs.data_ptr(), B, H0, T, self.stem_w_tc.data_ptr(), c1.data_ptr(), self.stem_flags, s()),
+                       "conv_stem_tc")
+        else:
+            _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
         H, W = (c1.shape[1] + 6 - 7) // 2 + 1, (c1.shape[2] + 6 - 7) // 2 + 1
         cur = self._buf(plan, "c2", B, H, W, 64)
         self._conv(self.conv2, c1, 0, cur, 0)
