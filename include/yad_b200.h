@@ -55,21 +55,21 @@ int yad_init(int device);
  * [ta] functional.py:390-403) and scale_input (:103-105,182-189).
  *
  * Stage A: PCM -> mel power.  Polyphase resample (new_rate/orig_rate reduced to
- * P/O; only the non-zero taps of each phase), Hann window, 1000-point real FFT,
+ * P/O, P % 4 == 0; only the non-zero taps of each phase), Hann window, 1000-point real FFT,
  * |X|^2, sparse mel filterbank.  n_fft = hop = 1000, 32 mels, center=False.
  *   pcm        [B, L]                 f32
- *   taps       [P/2][2][YAD_FE_TPQ]   f32  resampler.kernel rows of the phase pair (2u, 2u+1), both
- *                                          cut to the pair's common window [tap_base[u], +YAD_FE_TPQ)
+ *   taps       [P/4][4][YAD_FE_QW]    f32  resampler.kernel rows of the phase quad (4u .. 4u+3), all four
+ *                                          cut to the quad's common window [tap_base[u], +YAD_FE_QW)
  *                                          of the 2*width+O wide tap axis, zero padded
- *   tap_base   [P/2]                  i32
- *   window_len                        max(tap_base) + YAD_FE_TPQ (span of the padded signal one hop reads)
+ *   tap_base   [P/4]                  i32
+ *   window_len                        max(tap_base) + YAD_FE_QW (span of the padded signal one hop reads)
  *   window     [1000]                 f32  analysis window
  *   twiddle    [1000][2]              f32  exp(-2*pi*i*k/1000), built in fp64 by the host
  *   fb_val [nnz] f32, fb_bin [nnz] i32, fb_start [33] i32   mel filterbank in CSR form over mel bands; the
  *                                          bins of one band must be contiguous (triangular filters are)
  *   mel        [B, 32, T]             f32  (T frames; T*1000 <= ceil(P*L/O))
  */
-#define YAD_FE_TPQ 20
+#define YAD_FE_QW 22
 int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
                            const float* taps, const int32_t* tap_base, int32_t window_len,
                            const float* window, const float* twiddle, const float* fb_val,

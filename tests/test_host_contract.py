@@ -87,14 +87,14 @@ def test_resample_tap_packing_reconstructs_kernel(model):
     k = model.resampler.kernel
     pk = fc.pack_resample_taps(k)
     P, KW = pk["P"], pk["KW"]
-    dense = np.zeros((P, KW + _lib.FE_TPQ), np.float32)
+    dense = np.zeros((P, KW + _lib.FE_QW), np.float32)
     taps, base = pk["taps"].numpy(), pk["base"].numpy()
-    for u in range(P // 2):
-        dense[2 * u, base[u]: base[u] + _lib.FE_TPQ] = taps[u, 0]
-        dense[2 * u + 1, base[u]: base[u] + _lib.FE_TPQ] = taps[u, 1]
+    for u in range(P // 4):
+        for i in range(4):
+            dense[4 * u + i, base[u]: base[u] + _lib.FE_QW] = taps[u, i]
     np.testing.assert_array_equal(dense[:, :KW], k[:, 0].numpy())
     assert np.all(dense[:, KW:] == 0)
-    assert pk["window_len"] == int(base.max()) + _lib.FE_TPQ
+    assert pk["window_len"] == int(base.max()) + _lib.FE_QW
 
 
 def test_mel_csr_reconstructs_filterbank(model):

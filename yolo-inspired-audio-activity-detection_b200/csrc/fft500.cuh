@@ -1,0 +1,107 @@
+// 500-point complex FFT building blocks kept in registers (host+device so that tools/fft_selftest.cu can run
+// the exact butterfly / index code on the CPU).
+//
+// 1000-point real FFT of one STFT frame (torch.stft inside torchaudio Spectrogram, [ta] functional.py:123) =
+// 500-point complex FFT of z[n] = x[2n] + i x[2n+1] followed by an "untangle" pass.  500 = 25 x 20:
+//   pass A: thread (n2 in 0..19) loads z[20 n1 + n2], n1 = 0..24, runs a 25-point DFT (5 x 5) in registers and
+//           multiplies by W_500^(n2 k1);
+//   pass B: thread (k1 in 0..24) loads the 20 values Y[k1][n2], runs a 20-point DFT (4 x 5) in registers;
+//           X[k1 + 25 k2] comes out.
+// All butterfly indices are compile-time so the 25 / 20 complex values never leave the register file.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace yad {
+
+#define YAD_HD __host__ __device__ __forceinline__
+
+struct cf32 {
+  float x, y;
+};
+YAD_HD cf32 cmake(float x, float y) {
+  cf32 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+YAD_HD cf32 cadd(cf32 a, cf32 b) { return cmake(a.x + b.x, a.y + b.y); }
+YAD_HD cf32 csub(cf32 a, cf32 b) { return cmake(a.x - b.x, a.y - b.y); }
+YAD_HD cf32 cmulc(cf32 a, float br, float bi) { return cmake(a.x * br - a.y * bi, a.x * bi + a.y * br); }
+
+// forward 5-point DFT of (v0..v4), in place: v_q <- sum_r v_r exp(-2 pi i r q / 5)
+YAD_HD void dft5(cf32& v0, cf32& v1, cf32& v2, cf32& v3, cf32& v4) {
+  const float c1 = 0.30901699437494745f, c2 = -0.80901699437494745f;
+  const float s1 = 0.95105651629515353f, s2 = 0.58778525229247314f;
+  const cf32 t1 = cadd(v1, v4), t2 = cadd(v2, v3), t3 = csub(v1, v4), t4 = csub(v2, v3);
+  const cf32 m1 = cmake(v0.x + c1 * t1.x + c2 * t2.x, v0.y + c1 * t1.y + c2 * t2.y);
+  const cf32 m2 = cmake(v0.x + c2 * t1.x + c1 * t2.x, v0.y + c2 * t1.y + c1 * t2.y);
+  const cf32 n1 = cmake(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+  const cf32 n2 = cmake(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+  v0 = cmake(v0.x + t1.x + t2.x, v0.y + t1.y + t2.y);
+  v1 = cmake(m1.x + n1.y, m1.y - n1.x);  // m1 - i n1
+  v2 = cmake(m2.x + n2.y, m2.y - n2.x);  // m2 - i n2
+  v3 = cmake(m2.x - n2.y, m2.y + n2.x);  // m2 + i n2
+  v4 = cmake(m1.x - n1.y, m1.y + n1.x);  // m1 + i n1
+}
+
+// forward 4-point DFT, in place
+YAD_HD void dft4(cf32& v0, cf32& v1, cf32& v2, cf32& v3) {
+  const cf32 a = cadd(v0, v2), b = csub(v0, v2), c = cadd(v1, v3), d = csub(v1, v3);
+  v0 = cadd(a, c);
+  v1 = cmake(b.x + d.y, b.y - d.x);  // b - i d
+  v2 = csub(a, c);
+  v3 = cmake(b.x - d.y, b.y + d.x);  // b + i d
+}
+
+// cos / sin of 2 pi e / N as compile-time friendly constants (evaluated in double by the compiler)
+#define YAD_TW_COS(e, N) ((float)__builtin_cos(6.283185307179586476925286766559 * (double)(e) / (double)(N)))
+#define YAD_TW_SIN(e, N) ((float)__builtin_sin(6.283185307179586476925286766559 * (double)(e) / (double)(N)))
+
+// 25-point forward DFT.  Input v[n1] (natural order).  Output: bin k = a + 5 b (a, b in 0..4) is left in v[5 a + b].
+template <int NV>
+YAD_HD void dft25(cf32 (&v)[NV]) {
+  static_assert(NV >= 25, "dft25 needs 25 values");
+#pragma unroll
+  for (int n2 = 0; n2 < 5; ++n2) dft5(v[n2], v[5 + n2], v[10 + n2], v[15 + n2], v[20 + n2]);
+  // now v[5 a + n2] = sum_{n1} x[5 n1 + n2] W5^(n1 a); twiddle by W25^(n2 a)
+#define YAD_T25(a, n2) v[5 * a + n2] = cmulc(v[5 * a + n2], YAD_TW_COS((a) * (n2), 25), -YAD_TW_SIN((a) * (n2), 25));
+  YAD_T25(1, 1) YAD_T25(1, 2) YAD_T25(1, 3) YAD_T25(1, 4)
+  YAD_T25(2, 1) YAD_T25(2, 2) YAD_T25(2, 3) YAD_T25(2, 4)
+  YAD_T25(3, 1) YAD_T25(3, 2) YAD_T25(3, 3) YAD_T25(3, 4)
+  YAD_T25(4, 1) YAD_T25(4, 2) YAD_T25(4, 3) YAD_T25(4, 4)
+#undef YAD_T25
+#pragma unroll
+  for (int a = 0; a < 5; ++a) dft5(v[5 * a], v[5 * a + 1], v[5 * a + 2], v[5 * a + 3], v[5 * a + 4]);
+}
+
+// 20-point forward DFT.  Input v[n] natural order (n = 5 n1 + n2, n1 in 0..3, n2 in 0..4).
+// Output: bin k = a + 4 b (a in 0..3, b in 0..4) is left in v[5 a + b].
+template <int NV>
+YAD_HD void dft20(cf32 (&v)[NV]) {
+  static_assert(NV >= 20, "dft20 needs 20 values");
+#pragma unroll
+  for (int n2 = 0; n2 < 5; ++n2) dft4(v[n2], v[5 + n2], v[10 + n2], v[15 + n2]);
+  // v[5 a + n2] = sum_{n1} x[5 n1 + n2] W4^(n1 a); twiddle by W20^(n2 a)
+#define YAD_T20(a, n2) v[5 * a + n2] = cmulc(v[5 * a + n2], YAD_TW_COS((a) * (n2), 20), -YAD_TW_SIN((a) * (n2), 20));
+  YAD_T20(1, 1) YAD_T20(1, 2) YAD_T20(1, 3) YAD_T20(1, 4)
+  YAD_T20(2, 1) YAD_T20(2, 2) YAD_T20(2, 3) YAD_T20(2, 4)
+  YAD_T20(3, 1) YAD_T20(3, 2) YAD_T20(3, 3) YAD_T20(3, 4)
+#undef YAD_T20
+#pragma unroll
+  for (int a = 0; a < 4; ++a) dft5(v[5 * a], v[5 * a + 1], v[5 * a + 2], v[5 * a + 3], v[5 * a + 4]);
+}
+
+// Frame-buffer layouts (units: cf32 = 2 floats).  The three layouts alias the same shared-memory buffer, separated by
+// barriers; their frame strides are chosen so that consecutive work items (which straddle frames inside a warp) keep
+// walking through distinct banks (see frontend.cu).
+constexpr int FFT_NZ = 500;           // complex points per frame
+constexpr int FFT_Z_STRIDE = 500;     // natural-order frames (input z and output spectrum): 1000 words = 8 (mod 32)
+constexpr int FFT_Y_PITCH = 21;       // Y[k1][n2] row pitch
+constexpr int FFT_Y_STRIDE = 525;     // 25 rows x 21: 1050 words = 26 (mod 32)
+
+// pass A, work item (frame-local n2): register r (= 5 a + b after dft25) holds k1 = a + 5 b
+YAD_HD int passA_k1_of_reg(int r) { return (r / 5) + 5 * (r % 5); }
+// pass B, register r (= 5 a + b after dft20) holds k2 = a + 4 b
+YAD_HD int passB_k2_of_reg(int r) { return (r / 5) + 4 * (r % 5); }
+
+}  // namespace yad

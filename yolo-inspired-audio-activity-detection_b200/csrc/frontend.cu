@@ -1,29 +1,40 @@
 // Fused log-mel / MFCC frontend for sm_100a.
 //
-// Stage A (frontend_mel_kernel): raw PCM -> mel power, one CTA per run of 8-frame groups of one clip:
-//   coalesced HBM reads of the PCM span -> shared memory -> sparse polyphase resample (only the
-//   non-zero taps of torchaudio's Hann-windowed sinc bank) fused with the Hann analysis window ->
-//   1000-point real FFT as a 500-point complex Stockham FFT (radix 5,5,5,4) entirely in shared memory
-//   -> |X|^2 -> sparse (CSR) mel filterbank -> [B, 32, T] mel power.
-//   The 16 kHz signal, the frames and the spectrum never touch HBM.
+// Stage A (frontend_mel_kernel): raw PCM -> mel power.  One 512-thread CTA per run of 8-frame groups of one clip,
+// warp-specialised into two roles that overlap through double-buffered shared memory:
+//   resample warps (8): 16-byte cp.async staging of the PCM span (one group ahead) -> sparse polyphase resample
+//     (only the non-zero taps of torchaudio's Hann-windowed sinc bank; one QUAD of adjacent phases per thread with
+//     its 4 x 22 taps resident in registers for the whole kernel) fused with the Hann analysis window -> frame buffer;
+//   FFT warps (8): 1000-point real FFT as a 500-point complex FFT = 25 x 20 with both factors done in registers
+//     (fft500.cuh; two shared-memory exchanges instead of four radix passes) -> untangle + |X|^2 -> sparse (CSR)
+//     mel filterbank -> [B, 32, T] mel power.
+//   The 16 kHz signal, the frames and the spectrum never touch HBM; PCM is read exactly once.
 // Stage B (frontend_finish_kernel): per clip global reductions that the reference chains
 //   (modules/_architecture.py:98-105): dB with a per-clip top_db floor, DCT-II (MFCC), a second dB with
 //   its own per-clip floor, per-(clip, channel) mean / unbiased-std standardisation.
-//   Streams the 123 KB mel plane of its clip (L2 resident) five times instead of staging it.
+//   Streams the 123 KB mel plane of its clip (L2 resident) instead of staging it.
 //
 // Reference call sites: torchaudio Resample ([ta] functional.py:1405-1431), torch.stft + abs().pow(2)
 // ([ta] functional.py:123,144), MelScale matmul ([ta] transforms/_transforms.py:417), amplitude_to_DB
 // ([ta] functional.py:390-403), MFCC ([ta] transforms/_transforms.py:709-718), scale_input
 // (modules/_architecture.py:182-189).
 #include "common.cuh"
+#include "fft500.cuh"
 
 namespace yad {
 
 constexpr int FE_NFFT = 1000;
-constexpr int FE_FR = 8;          // frames per group
+constexpr int FE_FR = 8;            // frames per group
 constexpr int FE_NMEL = 32;
-constexpr int FE_TPQ = YAD_FE_TPQ; // taps per phase over the pair's common window (zero padded)
-constexpr int FE_THREADS = 320;
+constexpr int FE_QW = YAD_FE_QW;    // taps per phase over the quad's common window (zero padded)
+constexpr int FE_ROLE = 256;        // threads per role
+constexpr int FE_THREADS = 2 * FE_ROLE;
+constexpr int FE_FR_WORDS = FE_FR * 2 * FFT_Y_STRIDE;   // frame buffer (floats): the widest of the three layouts
+constexpr int FE_P_STRIDE = 505;    // power-spectrum row pitch (odd: frames land in distinct banks)
+constexpr int FE_NPAIR = FE_FR * 251;
+
+// named barriers (0 is __syncthreads)
+constexpr int BAR_RS = 1, BAR_FT = 2, BAR_FULL0 = 3, BAR_EMPTY0 = 5;
 
 struct FeParams {
   int64_t B, L, T;
@@ -33,71 +44,11 @@ struct FeParams {
   int32_t n_groups;  // ceil(T / FE_FR)
   int32_t groups_per_cta;
   int32_t fb_nnz_pad;  // mel CSR values, rounded up to a multiple of 4
+  int32_t nquad, nslice;
 };
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// One in-place decimation-in-frequency pass of radix R over FE_FR independent 500-point transforms.
-// Block size Nb = R * sub: v[r] = x[blk*Nb + n1 + sub*r]; y = DFT_R(v); x[.. + sub*q] = y[q] * W_Nb^(n1*q).
-// Reads and writes hit the same addresses (consecutive threads <-> consecutive n1: conflict-free); after the
-// four passes (5,5,5,4) bin k = q1 + 5 q2 + 25 q3 + 125 q4 sits at position 100 q1 + 20 q2 + 4 q3 + q4.
-template <int R>
-__device__ __forceinline__ void fft_pass_dif(float2* __restrict__ x, const float2* __restrict__ tw, int Nb) {
-  constexpr int N = 500, NBF = N / R;      // butterflies per frame
-  const int sub = Nb / R;
-  const int mul = 1000 / Nb;                // W_Nb = W_1000^mul
-  for (int item = threadIdx.x; item < FE_FR * NBF; item += blockDim.x) {
-    const int f = item / NBF, j = item - f * NBF;
-    const int blk = j / sub, n1 = j - blk * sub;
-    float2* px = x + f * N + blk * Nb + n1;
-    float2 v[R], y[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = px[r * sub];
-    if (R == 5) {
-      const float c1 = 0.30901699437494745f, c2 = -0.80901699437494745f;
-      const float s1 = 0.95105651629515353f, s2 = 0.58778525229247314f;
-      const float2 t1 = make_float2(v[1].x + v[4].x, v[1].y + v[4].y);
-      const float2 t2 = make_float2(v[2].x + v[3].x, v[2].y + v[3].y);
-      const float2 t3 = make_float2(v[1].x - v[4].x, v[1].y - v[4].y);
-      const float2 t4 = make_float2(v[2].x - v[3].x, v[2].y - v[3].y);
-      const float2 m1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-      const float2 m2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-      const float2 n1v = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-      const float2 n2v = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-      y[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
-      y[1] = make_float2(m1.x + n1v.y, m1.y - n1v.x);   // m1 - i n1
-      y[2] = make_float2(m2.x + n2v.y, m2.y - n2v.x);   // m2 - i n2
-      y[3 % R] = make_float2(m2.x - n2v.y, m2.y + n2v.x);   // m2 + i n2
-      y[4 % R] = make_float2(m1.x - n1v.y, m1.y + n1v.x);   // m1 + i n1
-    } else {
-      const float2 a = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
-      const float2 b = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-      const float2 c = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
-      const float2 d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-      y[0] = make_float2(a.x + c.x, a.y + c.y);
-      y[1] = make_float2(b.x + d.y, b.y - d.x);          // b - i d
-      y[2] = make_float2(a.x - c.x, a.y - c.y);
-      y[3] = make_float2(b.x - d.y, b.y + d.x);          // b + i d
-    }
-    px[0] = y[0];
-    if (sub > 1) {
-#pragma unroll
-      for (int q = 1; q < R; ++q) px[q * sub] = cmul(y[q], tw[n1 * q * mul]);
-    } else {
-#pragma unroll
-      for (int q = 1; q < R; ++q) px[q * sub] = y[q];
-    }
-  }
-}
-
-__device__ __forceinline__ int fft_pos(int k) {   // digit-reversed location of bin k after the DIF passes
-  const int q1 = k % 5, r1 = k / 5;
-  const int q2 = r1 % 5, r2 = r1 / 5;
-  const int q3 = r2 % 5, q4 = r2 / 5;
-  return 100 * q1 + 20 * q2 + 4 * q3 + q4;
-}
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -106,16 +57,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Stage the zero-padded PCM span of group g: element i of the span is xpad[x0 + i] = x[x0 + i] (zero outside [0, L)).
+// Stage the zero-padded PCM span of one group: element i of the span is xpad[x0 + i] = x[x0 + i] (zero outside [0, L)).
 // Fast path (clip base 16 B aligned, L % 4 == 0): 16-byte cp.async with zero fill, destination shifted by
 // (x0 mod 4) floats so that global and shared addresses are congruent mod 16.  Returns that shift.
+// Called by the FE_ROLE resample threads only (rt = thread index inside the role).
 __device__ __forceinline__ int fe_stage_async(float* s_x, const float* __restrict__ xb, int64_t x0, int SX, int64_t L,
-                                              bool fast) {
+                                              bool fast, int rt) {
   if (fast) {
     const int shift = (int)(((x0 % 4) + 4) % 4);
     const int nchunk = (shift + SX + 3) >> 2;
     const int64_t g0 = x0 - shift;                      // multiple of 4
-    for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
+    for (int c = rt; c < nchunk; c += FE_ROLE) {
       const int64_t gi = g0 + 4 * (int64_t)c;
       const bool ok = gi >= 0 && gi + 4 <= L;
       cp_async16(s_x + 4 * c, xb + (ok ? gi : 0), ok ? 16 : 0);
@@ -123,14 +75,14 @@ __device__ __forceinline__ int fe_stage_async(float* s_x, const float* __restric
     cp_async_commit();
     return shift;
   }
-  for (int i = threadIdx.x; i < SX; i += blockDim.x) {
+  for (int i = rt; i < SX; i += FE_ROLE) {
     const int64_t src = x0 + i;
     s_x[i] = (src >= 0 && src < L) ? __ldg(xb + src) : 0.0f;
   }
   return 0;
 }
 
-__global__ void __launch_bounds__(FE_THREADS, 2)
+__global__ void __launch_bounds__(FE_THREADS, 1)
 frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float* __restrict__ taps,
                     const int32_t* __restrict__ tap_base, const float* __restrict__ window,
                     const float* __restrict__ twiddle, const float* __restrict__ fb_val,
@@ -138,125 +90,179 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
                     float* __restrict__ mel) {
   extern __shared__ __align__(16) float fe_smem[];
   const int sxp = (p.SX + 8 + 3) & ~3;
-  float* s_x = fe_smem;                                      // staged PCM span (prefetched one group ahead)
-  float* s_fr = s_x + sxp;                                   // FE_FR windowed frames; FFT and power in place
-  float2* s_tw = reinterpret_cast<float2*>(s_fr + FE_FR * FE_NFFT);  // exp(-2 pi i k / 1000)
-  float* s_win = reinterpret_cast<float*>(s_tw + FE_NFFT);
+  float* s_x = fe_smem;                                      // [2][sxp] staged PCM spans
+  float* s_fr = s_x + 2 * sxp;                               // [2][FE_FR_WORDS] frames / FFT exchange
+  float* s_P = s_fr + 2 * FE_FR_WORDS;                       // [FE_FR][FE_P_STRIDE] power spectrum (bins 0..500)
+  float2* s_tw = reinterpret_cast<float2*>(s_P + ((FE_FR * FE_P_STRIDE + 3) & ~3));   // exp(-2 pi i k / 1000), 16 B aligned
+  float2* s_twA = s_tw + FE_NFFT;                            // [25 regs][20 n2] pass-A twiddles W_500^(n2 k1(r))
+  float* s_win = reinterpret_cast<float*>(s_twA + 500);      // [1000] analysis window
   float* s_fbv = s_win + FE_NFFT;                            // mel filterbank values, CSR over bands
   int* s_fbs = reinterpret_cast<int*>(s_fbv + p.fb_nnz_pad); // [33] row starts, then [32] first bin of each band
-  int* s_pos = s_fbs + 2 * FE_NMEL + 4;                      // [501] digit-reversed position of bin k (500 -> 0)
 
   const int tid = threadIdx.x;
+  const int role = tid >> 8;          // 0: resample, 1: FFT / mel
+  const int rt = tid & (FE_ROLE - 1);
   const int64_t b = blockIdx.y;
   const float* xb = pcm + b * p.L;
   const bool fast = ((p.L & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
   const int g_first = blockIdx.x * p.groups_per_cta;
   if (g_first >= p.n_groups) return;
-  int shift = fe_stage_async(s_x, xb, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast);
+  const int n_my = min(p.groups_per_cta, p.n_groups - g_first);
 
-  for (int i = tid; i < FE_NFFT; i += blockDim.x) {
+  int shift = 0;
+  if (role == 0) shift = fe_stage_async(s_x, xb, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt);
+
+  for (int i = tid; i < FE_NFFT; i += FE_THREADS) {
     s_tw[i] = make_float2(twiddle[2 * i], twiddle[2 * i + 1]);
     s_win[i] = window[i];
   }
+  for (int i = tid; i < 500; i += FE_THREADS) {
+    const int r = i / 20, n2 = i - r * 20;
+    const int e = (2 * n2 * passA_k1_of_reg(r)) % 1000;
+    s_twA[i] = make_float2(twiddle[2 * e], twiddle[2 * e + 1]);
+  }
   const int nnz = fb_start[FE_NMEL];
-  for (int i = tid; i < nnz; i += blockDim.x) s_fbv[i] = fb_val[i];
+  for (int i = tid; i < nnz; i += FE_THREADS) s_fbv[i] = fb_val[i];
   if (tid <= FE_NMEL) s_fbs[tid] = fb_start[tid];
   if (tid < FE_NMEL) s_fbs[FE_NMEL + 1 + tid] = fb_bin[fb_start[tid]];   // bins of a band are contiguous
-  for (int i = tid; i <= 500; i += blockDim.x) s_pos[i] = fft_pos(i % 500);
+  __syncthreads();
 
-  // resample role: one pair of adjacent phases per thread, hop slices interleaved across the block
-  const int npair = p.P >> 1;
-  const int nsl = blockDim.x / npair;
-  const int pair = tid % npair, sl = tid / npair;
-  const bool rs_active = sl < nsl;
-  float t0[FE_TPQ], t1[FE_TPQ];
-  int base = 0;
-  if (rs_active) {
-    base = tap_base[pair];
+  if (role == 0) {
+    // ===================================================================== resample role
+    // One quad of adjacent phases per thread; consecutive lanes take every second quad so that their x windows are
+    // ~11 words apart (an odd stride: conflict-free shared-memory reads).
+    const int half = (p.nquad + 1) >> 1;
+    const int qi = rt % p.nquad, sl = rt / p.nquad;
+    const int quad = qi < half ? 2 * qi : 2 * (qi - half) + 1;
+    const bool active = sl < p.nslice;
+    float tq[4][FE_QW];
+    int base = 0;
+    if (active) {
+      base = tap_base[quad];
 #pragma unroll
-    for (int j = 0; j < FE_TPQ; ++j) {
-      t0[j] = taps[(pair * 2 + 0) * FE_TPQ + j];
-      t1[j] = taps[(pair * 2 + 1) * FE_TPQ + j];
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < FE_QW; ++j) tq[i][j] = __ldg(taps + (quad * 4 + i) * FE_QW + j);
     }
-  }
-  float2* zf = reinterpret_cast<float2*>(s_fr);
-
-  for (int gi = 0; gi < p.groups_per_cta; ++gi) {
-    const int g = g_first + gi;
-    if (g >= p.n_groups) break;
-    cp_async_wait_all();
-    __syncthreads();  // staged span + tables visible; previous group's mel reads of s_fr are done
-    // ---- 1. polyphase resample * Hann window -> frames
-    if (rs_active) {
-      for (int h = sl; h < p.HG; h += nsl) {
-        const float* xs = s_x + shift + h * p.O + base;
-        float a0 = 0.0f, a1 = 0.0f;
+    for (int gi = 0; gi < n_my; ++gi) {
+      const int buf = gi & 1;
+      cp_async_wait_all();
+      bar_sync(BAR_RS, FE_ROLE);   // span of this group landed for every thread; nobody still reads the other buffer
+      int shift_next = 0;
+      if (gi + 1 < n_my)
+        shift_next = fe_stage_async(s_x + (buf ^ 1) * sxp, xb, (int64_t)(g_first + gi + 1) * p.HG * p.O - p.width, p.SX,
+                                    p.L, fast, rt);
+      if (gi >= 2) bar_sync(BAR_EMPTY0 + buf, FE_THREADS);   // FFT role released this frame buffer
+      if (active) {
+        const float* sx = s_x + buf * sxp + shift + base;
+        float* fr = s_fr + buf * FE_FR_WORDS;
+        for (int h = sl; h < p.HG; h += p.nslice) {
+          const float* xs = sx + h * p.O;
+          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < FE_TPQ; ++j) {
-          const float xv = xs[j];
-          a0 = fmaf(t0[j], xv, a0);
-          a1 = fmaf(t1[j], xv, a1);
+          for (int j = 0; j < FE_QW; ++j) {
+            const float xv = xs[j];
+            a0 = fmaf(tq[0][j], xv, a0);
+            a1 = fmaf(tq[1][j], xv, a1);
+            a2 = fmaf(tq[2][j], xv, a2);
+            a3 = fmaf(tq[3][j], xv, a3);
+          }
+          const int o = h * p.P + 4 * quad;
+          const int f = o / FE_NFFT, pos = o - f * FE_NFFT;
+          const float4 w = *reinterpret_cast<const float4*>(s_win + pos);
+          *reinterpret_cast<float4*>(fr + f * (2 * FFT_Z_STRIDE) + pos) = make_float4(a0 * w.x, a1 * w.y, a2 * w.z, a3 * w.w);
         }
-        const int o = h * p.P + 2 * pair;
-        const int pos = o % FE_NFFT;
-        *reinterpret_cast<float2*>(s_fr + o) = make_float2(a0 * s_win[pos], a1 * s_win[pos + 1]);
       }
+      __threadfence_block();
+      bar_arrive(BAR_FULL0 + buf, FE_THREADS);
+      shift = shift_next;
     }
-    __syncthreads();
-    // ---- 2. prefetch the next group's PCM span (s_x is free now); lands while the FFT runs
-    if (gi + 1 < p.groups_per_cta && g + 1 < p.n_groups)
-      shift = fe_stage_async(s_x, xb, (int64_t)(g + 1) * p.HG * p.O - p.width, p.SX, p.L, fast);
-    // ---- 3. in-place 500-point complex FFT of z[n] = x[2n] + i x[2n+1]
-    fft_pass_dif<5>(zf, s_tw, 500);
-    __syncthreads();
-    fft_pass_dif<5>(zf, s_tw, 100);
-    __syncthreads();
-    fft_pass_dif<5>(zf, s_tw, 20);
-    __syncthreads();
-    fft_pass_dif<4>(zf, s_tw, 4);
-    __syncthreads();
-    // ---- 4. real-FFT untangle + power, in place: X[k] = E + W^k O ; X[500-k] = conj(E - W^k O).
-    //         The pair (k, 500-k) is owned by one thread; P[k] overwrites Z[k].x, P[500-k] overwrites Z[500-k].x;
-    //         bin 500 (= bin 0's partner) goes to Z[0].y.
-    for (int item = tid; item < FE_FR * 251; item += blockDim.x) {
-      const int f = item / 251, k = item - f * 251;
-      const int pk = s_pos[k], pq = s_pos[500 - k];
-      float2* zb = zf + f * 500;
-      const float2 zk = zb[pk];
-      const float2 zq = zb[pq];
-      const float2 zn = make_float2(zq.x, -zq.y);
-      const float2 E = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
-      const float2 D = make_float2(zk.x - zn.x, zk.y - zn.y);
-      const float2 Od = make_float2(0.5f * D.y, -0.5f * D.x);   // -i/2 * D
-      const float2 Tt = cmul(s_tw[k], Od);
-      const float pr = E.x + Tt.x, pi = E.y + Tt.y, qr = E.x - Tt.x, qi = E.y - Tt.y;
-      const float Pk = pr * pr + pi * pi, Pq = qr * qr + qi * qi;
-      if (k == 0) {
-        zb[pk] = make_float2(Pk, Pq);
-      } else {
-        zb[pk].x = Pk;
-        zb[pq].x = Pq;     // k == 250: same location, same value
+  } else {
+    // ===================================================================== FFT / mel role
+    const bool actA = rt < FE_FR * 20, actB = rt < FE_FR * 25;
+    const int fA = rt / 20, n2 = rt - fA * 20;
+    const int fB = rt / 25, k1 = rt - fB * 25;
+    for (int gi = 0; gi < n_my; ++gi) {
+      const int buf = gi & 1;
+      const int g = g_first + gi;
+      cf32* zf = reinterpret_cast<cf32*>(s_fr + buf * FE_FR_WORDS);
+      bar_sync(BAR_FULL0 + buf, FE_THREADS);
+      // ---- pass A: 25-point DFTs over n1 (stride 20), twiddle W_500^(n2 k1)
+      cf32 v[25];
+      if (actA) {
+        const cf32* src = zf + fA * FFT_Z_STRIDE + n2;
+#pragma unroll
+        for (int n1 = 0; n1 < 25; ++n1) v[n1] = src[20 * n1];
+        dft25(v);
+        const cf32* twa = reinterpret_cast<const cf32*>(s_twA) + n2;
+#pragma unroll
+        for (int r = 1; r < 25; ++r) {
+          const cf32 t = twa[r * 20];
+          v[r] = cmulc(v[r], t.x, t.y);
+        }
       }
-    }
-    __syncthreads();
-    // ---- 5. sparse mel filterbank (band m covers the contiguous bins [bin0, bin0 + len))
-    for (int item = tid; item < FE_FR * FE_NMEL; item += blockDim.x) {
-      const int m = item / FE_FR, f = item - m * FE_FR;
-      const int64_t t = (int64_t)g * FE_FR + f;
-      if (t < p.T) {
-        const float2* zb = zf + f * 500;
+      bar_sync(BAR_FT, FE_ROLE);      // every pass-A load is done: the buffer can change layout
+      if (actA) {
+        cf32* dst = zf + fA * FFT_Y_STRIDE + n2;
+#pragma unroll
+        for (int r = 0; r < 25; ++r) dst[passA_k1_of_reg(r) * FFT_Y_PITCH] = v[r];
+      }
+      bar_sync(BAR_FT, FE_ROLE);
+      // ---- pass B: 20-point DFTs over n2; X[k1 + 25 k2] in natural order
+      if (actB) {
+        const cf32* src = zf + fB * FFT_Y_STRIDE + k1 * FFT_Y_PITCH;
+#pragma unroll
+        for (int j = 0; j < 20; ++j) v[j] = src[j];
+        dft20(v);
+      }
+      bar_sync(BAR_FT, FE_ROLE);
+      if (actB) {
+        cf32* dst = zf + fB * FFT_Z_STRIDE + k1;
+#pragma unroll
+        for (int r = 0; r < 20; ++r) dst[25 * passB_k2_of_reg(r)] = v[r];
+      }
+      bar_sync(BAR_FT, FE_ROLE);
+      // ---- real-FFT untangle + power: X[k] = E + W^k O ; X[500-k] = conj(E - W^k O); one thread owns the pair
+      for (int item = rt; item < FE_NPAIR; item += FE_ROLE) {
+        const int f = item / 251, k = item - f * 251;
+        const cf32* zb = zf + f * FFT_Z_STRIDE;
+        const cf32 zk = zb[k];
+        const cf32 zq = zb[k == 0 ? 0 : 500 - k];
+        const cf32 zn = cmake(zq.x, -zq.y);
+        const cf32 E = cmake(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
+        const cf32 D = cmake(zk.x - zn.x, zk.y - zn.y);
+        const cf32 Od = cmake(0.5f * D.y, -0.5f * D.x);   // -i/2 * D
+        const float2 w = s_tw[k];
+        const cf32 Tt = cmulc(Od, w.x, w.y);
+        const float pr = E.x + Tt.x, pi = E.y + Tt.y, qr = E.x - Tt.x, qi = E.y - Tt.y;
+        float* pp = s_P + f * FE_P_STRIDE;
+        pp[k] = pr * pr + pi * pi;
+        pp[500 - k] = qr * qr + qi * qi;
+      }
+      bar_sync(BAR_FT, FE_ROLE);      // power spectrum complete; the frame buffer is no longer read
+      if (gi + 2 < n_my) {
+        __threadfence_block();
+        bar_arrive(BAR_EMPTY0 + buf, FE_THREADS);
+      }
+      // ---- sparse mel filterbank (band m covers the contiguous bins [bin0, bin0 + len)); thread = (frame, band)
+      {
+        const int f = rt & (FE_FR - 1), m = rt >> 3;
+        const int64_t t = (int64_t)g * FE_FR + f;
+        const float* pp = s_P + f * FE_P_STRIDE + s_fbs[FE_NMEL + 1 + m];
         const int s0 = s_fbs[m], e0 = s_fbs[m + 1];
-        int bin = s_fbs[FE_NMEL + 1 + m];
-        float acc = 0.0f;
-        for (int i = s0; i < e0; ++i, ++bin) {
-          const float pw = (bin == 500) ? zb[0].y : zb[s_pos[bin]].x;
-          acc = fmaf(pw, s_fbv[i], acc);
+        const float* fv = s_fbv + s0;
+        const int len = e0 - s0;
+        float acc0 = 0.0f, acc1 = 0.0f;
+        int i = 0;
+        for (; i + 1 < len; i += 2) {
+          acc0 = fmaf(pp[i], fv[i], acc0);
+          acc1 = fmaf(pp[i + 1], fv[i + 1], acc1);
         }
-        mel[(b * FE_NMEL + m) * p.T + t] = acc;
+        if (i < len) acc0 = fmaf(pp[i], fv[i], acc0);
+        if (t < p.T) mel[(b * FE_NMEL + m) * p.T + t] = acc0 + acc1;
       }
     }
   }
-  cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------ stage B
@@ -370,11 +376,12 @@ frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __
 
 static size_t fe_smem_bytes(int SX, int nnz_pad) {
   const int sxp = (SX + 8 + 3) & ~3;
-  return (size_t)(sxp + FE_FR * FE_NFFT + 2 * FE_NFFT + FE_NFFT + nnz_pad + 2 * FE_NMEL + 4 + 504) * sizeof(float);
+  return (size_t)(2 * sxp + 2 * FE_FR_WORDS + ((FE_FR * FE_P_STRIDE + 3) & ~3) + 2 * FE_NFFT + 1000 + FE_NFFT + nnz_pad +
+                  2 * FE_NMEL + 4) * sizeof(float);
 }
 
 int init_frontend_attrs() {
-  cudaError_t e = cudaFuncSetAttribute(frontend_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(frontend_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(frontend_mel_kernel) failed: %s", cudaGetErrorString(e));
     return YAD_ERR_CUDA;
@@ -393,11 +400,11 @@ int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, in
   using namespace yad;
   YAD_CHECK_ARG(pcm && taps && tap_base && window && twiddle && fb_val && fb_bin && fb_start && mel,
                 "yad_frontend_mel_power: null pointer");
-  YAD_CHECK_ARG(P >= 2 && P % 2 == 0 && P / 2 <= FE_THREADS, "yad_frontend_mel_power: P=%d must be even and <= %d", P,
-                2 * FE_THREADS);
+  YAD_CHECK_ARG(P >= 4 && P % 4 == 0 && P / 4 <= FE_ROLE, "yad_frontend_mel_power: P=%d must be a multiple of 4 and <= %d", P,
+                4 * FE_ROLE);
   YAD_CHECK_ARG((FE_FR * FE_NFFT) % P == 0, "yad_frontend_mel_power: %d-sample frame groups must be whole hops of P=%d",
                 FE_FR * FE_NFFT, P);
-  YAD_CHECK_ARG(O >= 1 && width >= 0 && window_len >= FE_TPQ, "yad_frontend_mel_power: bad O/width/window_len");
+  YAD_CHECK_ARG(O >= 1 && width >= 0 && window_len >= FE_QW, "yad_frontend_mel_power: bad O/width/window_len");
   YAD_CHECK_ARG(B >= 0 && B <= 65535 && L >= 1 && T >= 1, "yad_frontend_mel_power: bad B/L/T");
   YAD_CHECK_ARG(fb_nnz >= 1 && fb_nnz <= 16384, "yad_frontend_mel_power: bad fb_nnz=%d", fb_nnz);
   // frames must exist in the resampled signal: T*1000 <= ceil(P*L/O)
@@ -412,14 +419,21 @@ int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, in
   p.O = O;
   p.width = width;
   p.HG = FE_FR * FE_NFFT / P;
-  p.SX = (p.HG - 1) * O + window_len;   // window_len = max(tap_base) + FE_TPQ
+  p.SX = (p.HG - 1) * O + window_len;   // window_len = max(tap_base) + FE_QW
   p.n_groups = (int)((T + FE_FR - 1) / FE_FR);
-  p.groups_per_cta = 4;
+  p.nquad = P / 4;
+  p.nslice = FE_ROLE / p.nquad;
+  if (p.nslice > p.HG) p.nslice = p.HG;
+  // runs of groups per CTA: long enough to amortise the table / tap loads, short enough for >= ~8 CTAs per SM overall
+  const int nsm = sm_count() > 0 ? sm_count() : 148;
+  int64_t gpc = (B * (int64_t)p.n_groups) / ((int64_t)nsm * 8);
+  if (gpc < 1) gpc = 1;
+  if (gpc > 40) gpc = 40;
+  if (gpc > p.n_groups) gpc = p.n_groups;
+  p.groups_per_cta = (int)gpc;
   p.fb_nnz_pad = (fb_nnz + 3) & ~3;
   const size_t smem = fe_smem_bytes(p.SX, p.fb_nnz_pad);
-  YAD_CHECK_ARG(smem <= 200 * 1024, "yad_frontend_mel_power: staging span too large (%zu B)", smem);
-  if (smem > 48 * 1024)
-    YAD_CUDA(cudaFuncSetAttribute(frontend_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  YAD_CHECK_ARG(smem <= 226 * 1024, "yad_frontend_mel_power: staging span too large (%zu B of shared memory)", smem);
   dim3 grid((unsigned)((p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta), (unsigned)B);
   frontend_mel_kernel<<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, window, twiddle, fb_val,
                                                                         fb_bin, fb_start, mel);

@@ -11,7 +11,7 @@ from typing import Dict, Tuple
 import numpy as np
 import torch
 
-from ._lib import FE_TPQ
+from ._lib import FE_QW
 
 
 def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6,
@@ -57,23 +57,23 @@ def dct_ortho(n_mfcc: int, n_mels: int) -> torch.Tensor:
 
 
 def pack_resample_taps(kernel: torch.Tensor) -> Dict[str, object]:
-    """resampler.kernel [P,1,KW] -> per phase-pair taps over the pair's common window (kernel ABI)."""
+    """resampler.kernel [P,1,KW] -> per phase-quad taps over the quad's common window (kernel ABI)."""
     k = kernel.detach().to("cpu", torch.float32)[:, 0, :].numpy()
     P, KW = k.shape
-    if P % 2:
-        raise NotImplementedError(f"odd number of resample phases ({P}) is not supported by the kernel")
-    taps = np.zeros((P // 2, 2, FE_TPQ), np.float32)
-    base = np.zeros((P // 2,), np.int32)
-    for u in range(P // 2):
-        nz = np.nonzero((k[2 * u] != 0) | (k[2 * u + 1] != 0))[0]
+    if P % 4:
+        raise NotImplementedError(f"a number of resample phases that is not a multiple of 4 ({P}) is not supported by the kernel")
+    taps = np.zeros((P // 4, 4, FE_QW), np.float32)
+    base = np.zeros((P // 4,), np.int32)
+    for u in range(P // 4):
+        nz = np.nonzero((k[4 * u: 4 * u + 4] != 0).any(axis=0))[0]
         lo, hi = (int(nz[0]), int(nz[-1]) + 1) if nz.size else (0, 1)
-        if hi - lo > FE_TPQ:
+        if hi - lo > FE_QW:
             raise NotImplementedError(
-                f"resample phase pair {u} spans {hi - lo} taps > {FE_TPQ}: this sample-rate pair is not supported")
+                f"resample phase quad {u} spans {hi - lo} taps > {FE_QW}: this sample-rate pair is not supported")
         base[u] = lo
-        seg = k[2 * u: 2 * u + 2, lo:min(lo + FE_TPQ, KW)]
+        seg = k[4 * u: 4 * u + 4, lo:min(lo + FE_QW, KW)]
         taps[u, :, : seg.shape[1]] = seg
-    return {"taps": torch.from_numpy(taps), "base": torch.from_numpy(base), "window_len": int(base.max()) + FE_TPQ,
+    return {"taps": torch.from_numpy(taps), "base": torch.from_numpy(base), "window_len": int(base.max()) + FE_QW,
             "P": P, "KW": KW}
 
 
