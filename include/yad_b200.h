@@ -96,6 +96,11 @@ typedef struct {
   int32_t kh, kw, sh, sw, ph, pw;
   int32_t act;                /* YAD_ACT_* */
   int32_t ld_res;             /* residual channel pitch (0 = no residual) */
+  /* Optional pixel strides (in pixels; all three 0 = dense NHWC): element (b,h,w,c) of the input lives at
+   * (b*in_sb + h*in_sh + w*in_sw)*ld_in + c, of the output / residual at (b*out_sb + h*out_sh + w*out_sw)*ld + c.
+   * Used to read / write the halo-padded "flat" layout of yad_conv_flat.  yad_conv_tc needs in_sw <= in_sh <= in_sb. */
+  int32_t in_sw, in_sh, in_sb;
+  int32_t out_sw, out_sh, out_sb;
 } yad_conv_desc;
 
 /* Stem conv1 (2 -> 64, 7x7, stride 2, pad 3): reads x_spectral NCHW f32 directly,
@@ -125,12 +130,35 @@ int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int3
                 float* out2_f32 /* optional fp32 copy of the output, pitch ld_out2, may be NULL */,
                 int32_t ld_out2, yad_stream_t stream);
 
+/* Patch-resident tcgen05 implicit GEMM for stride-1 'same' convolutions on the FLAT halo-padded layout:
+ * pixel (b,h,w) of an activation lives at flat index f = (b*Wp + w)*Hp + h (h fastest), channel pitch ld; cells with
+ * h >= H or w >= W are the (shared) zero halo: they are read as padding and never written, so the caller zero-fills
+ * the buffer once.  Hp - H / Wp - W must cover the filter reach (taps that can only see padding, e.g. the top and
+ * bottom rows of a 3x3 at H = 1, are skipped and need no halo).  Every tap is then a constant shift in f, so a CTA
+ * loads each input pixel once per tile instead of once per tap.  in / out / residual share the geometry.
+ * Requirements: Cin % 64 == 0, Cout % 32 == 0, cout_pad % 64 == 0 (weight rows / bias zero padded), bf16 in and out.
+ * weight [cout_pad][kh*kw*Cin] bf16, K ordered (kh, kw, cin) as for yad_conv_tc.  flags: 0 (bit 0 = debug: non-zero
+ * descriptor base_offset, kept to document the measured hardware behaviour). */
+typedef struct {
+  int32_t B, H, W;            /* image size */
+  int32_t Hp, Wp;             /* padded pitches */
+  int32_t Cin, ld_in;
+  int32_t Cout, ld_out, co_off;
+  int32_t kh, kw, ph, pw;     /* 'same' convolution: kh = 2*ph + 1, kw = 2*pw + 1 */
+  int32_t act;                /* YAD_ACT_* */
+  int32_t ld_res;             /* residual channel pitch (0 = no residual) */
+} yad_flat_desc;
+int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
+                  const void* residual, void* out, int32_t flags, yad_stream_t stream);
+
 /* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
  * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5
  * :173-174,181-182; cascaded max_pool2d k5 s1 p2 :207-209.  All write into a channel slice
  * (co_off, ld_out) of the destination so torch.cat never materialises. */
+/* yad_hmean input pixel strides (in pixels): element (b,h,w,c) at (b*in_sb + h*in_sh + w*in_sw)*ld_in + c; pass
+ * (W, 1, H*W) ... i.e. in_sh = W, in_sw = 1, in_sb = H*W for dense NHWC.  Output is dense [B, W, ld_out]. */
 int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, int32_t C, int32_t ld_in,
-              void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
+              int32_t in_sw, int32_t in_sh, int32_t in_sb, void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
 int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
                  int32_t up /*1: x2, 0: x0.5*/, void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
 /* in: slice [ci_off, ci_off+C) of a [B,W,ld] tensor; writes pool5, pool5^2, pool5^3 of it to channel

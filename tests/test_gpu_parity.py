@@ -190,6 +190,61 @@ def test_stem_conv_tensor_core(shape, cuda_dev):
     np.testing.assert_allclose(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy(), atol=2e-2, rtol=1e-2)
 
 
+FLAT_CASES = [
+    # B, H, W, Cin, Cout, k, act, residual
+    (2, 8, 48, 64, 64, 3, ACT_RELU, True),        # layer1
+    (3, 4, 24, 128, 128, 3, ACT_RELU, True),      # layer2
+    (2, 2, 12, 256, 256, 3, ACT_RELU, True),      # layer3
+    (5, 1, 6, 512, 512, 3, ACT_RELU, True),       # layer4 (H = 1: rows -1 / +1 of the filter only see padding)
+    (1, 8, 240, 64, 64, 3, ACT_RELU, False),      # full-width layer1
+    (4, 1, 24, 128, 128, 3, ACT_LRELU, False),    # neck RepVGG (deploy form)
+    (2, 4, 24, 64, 128, 1, ACT_NONE, False),      # 1x1
+    (37, 8, 30, 64, 64, 3, ACT_RELU, True),       # many super-tiles per CTA, ragged last tile
+]
+
+
+def _to_flat(x, Hp, Wp, ld, dev):
+    """NCHW fp32 -> flat halo-padded bf16 [B, Wp, Hp, ld] (pixel (b,h,w) at (b*Wp + w)*Hp + h)."""
+    B, Cc, H, W = x.shape
+    buf = torch.zeros(B, Wp, Hp, ld, dtype=torch.bfloat16)
+    buf[:, :W, :H, :Cc] = x.permute(0, 3, 2, 1).to(torch.bfloat16)
+    return buf.to(dev)
+
+
+@pytest.mark.parametrize("case", FLAT_CASES)
+def test_conv_flat(case, cuda_dev):
+    """Patch-resident tcgen05 conv on the flat layout vs F.conv2d on the same bf16-rounded operands."""
+    B, H, W, Cin, Cout, k, act, use_res = case
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(B, Cout, H, W, generator=g).bfloat16().float() if use_res else None
+    ref = _conv_ref(x, w, b, 1, k // 2, act, res)
+    Hp, Wp = (H + k // 2 if H > 1 else 1), W + k // 2
+    ld_out, co_off = Cout + 64, 64
+    xin = _to_flat(x, Hp, Wp, Cin, cuda_dev)
+    rin = _to_flat(res, Hp, Wp, Cout, cuda_dev) if use_res else None
+    out = torch.full((B, Wp, Hp, ld_out), 7.0, dtype=torch.bfloat16, device=cuda_dev)
+    cout_p = (Cout + 63) // 64 * 64
+    wt = torch.zeros(cout_p, k, k, Cin)
+    wt[:Cout] = w.permute(0, 2, 3, 1)
+    wt = wt.reshape(cout_p, -1).to(torch.bfloat16).to(cuda_dev)
+    bp = torch.zeros(cout_p, device=cuda_dev); bp[:Cout] = b.to(cuda_dev)
+    d = _lib.FlatDesc(B=B, H=H, W=W, Hp=Hp, Wp=Wp, Cin=Cin, ld_in=Cin, Cout=Cout, ld_out=ld_out, co_off=co_off, kh=k, kw=k,
+                      ph=k // 2, pw=k // 2, act=act, ld_res=Cout if use_res else 0)
+    flags = int(__import__("os").environ.get("YAD_FLAT_FLAGS", "0"))   # 1 = set base_offset in the A descriptor: fails on B200
+    _lib.check(lib.yad_conv_flat(C.byref(d), xin.data_ptr(), wt.data_ptr(), cout_p, bp.data_ptr(), _lib.ptr(rin), out.data_ptr(),
+                                 flags, _stream()), "conv_flat")
+    torch.cuda.synchronize()
+    got = out[:, :W, :H, co_off:co_off + Cout].float().permute(0, 3, 2, 1).cpu()
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-2, rtol=1e-2)
+    # halo cells and channels outside the slice are never written
+    assert torch.all(out[:, W:].float() == 7.0) and torch.all(out[:, :, H:].float() == 7.0)
+    assert torch.all(out[..., :co_off].float() == 7.0)
+
+
 # ------------------------------------------------------------------ whole network (S2/S3)
 @pytest.mark.parametrize("form", ["train", "deploy"])
 def test_network_f32_vs_golden(models, gold, form, cuda_dev):

@@ -23,7 +23,13 @@ class YadError(RuntimeError):
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
-        "B", "H", "W", "Cin", "ld_in", "Cout", "ld_out", "co_off", "kh", "kw", "sh", "sw", "ph", "pw", "act", "ld_res")]
+        "B", "H", "W", "Cin", "ld_in", "Cout", "ld_out", "co_off", "kh", "kw", "sh", "sw", "ph", "pw", "act", "ld_res",
+        "in_sw", "in_sh", "in_sb", "out_sw", "out_sh", "out_sb")]
+
+
+class FlatDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "B", "H", "W", "Hp", "Wp", "Cin", "ld_in", "Cout", "ld_out", "co_off", "kh", "kw", "ph", "pw", "act", "ld_res")]
 
 
 _p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -37,7 +43,8 @@ SIGNATURES = {
     "yad_conv_stem_tc": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],
     "yad_conv_simt": [C.POINTER(ConvDesc), _i32, _p, _p, _i32, _p, _p, _p, _p],
     "yad_conv_tc": [C.POINTER(ConvDesc), _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p],
-    "yad_hmean": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
+    "yad_conv_flat": [C.POINTER(FlatDesc), _p, _p, _i32, _p, _p, _p, _i32, _p],
+    "yad_hmean": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_resize_w": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_sppf_pools": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_repvgg_merge": [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p],

@@ -22,6 +22,7 @@ void* tensor_map_encode_fn() { return g_encode; }
 int sm_count() { return g_sm_count; }
 
 int init_conv_tc_attrs();   // conv_tc.cu
+int init_conv_flat_attrs(); // conv_flat.cu
 int init_frontend_attrs();  // frontend.cu
 
 }  // namespace yad
@@ -56,6 +57,8 @@ int yad_init(int device) {
   }
   yad::g_encode = fn;
   int rc = yad::init_conv_tc_attrs();
+  if (rc) return rc;
+  rc = yad::init_conv_flat_attrs();
   if (rc) return rc;
   rc = yad::init_frontend_attrs();
   if (rc) return rc;

@@ -1,0 +1,370 @@
+// Patch-resident tcgen05 / TMEM implicit-GEMM convolution for stride-1 convs on "flat" (halo-padded) activations.
+//
+// Replaces F.conv2d + folded BatchNorm + activation (+ residual) for the 3x3 stride-1 convolutions of the
+// reference's ResNet stages (torchvision resnet.py:89-105 via modules/_backbone.py:148-151).
+//
+// Why a second conv kernel: the tap-by-tap implicit GEMM of conv_tc.cu re-reads every input element from L2 once per
+// filter tap (9x for a 3x3); with Cout = 64..128 that makes the layer L2-bandwidth bound at ~1/4 of the tensor peak.
+// Here the activations live in HBM in a flat, halo-padded layout
+//     f = (b * Wp + w) * Hp + h        (h fastest; cells with h >= H or w >= W are zero and are never written)
+// so that for a stride-1 conv EVERY filter tap is a constant shift in f:  in[f + dw * Hp + dh].  One CTA therefore
+// loads a contiguous patch of pixels [f0 + min_off, f0 + 128 * MT + max_off) ONCE per 64-channel chunk (plain 2-D
+// TMA, 128-byte swizzled rows) and issues the MMAs of all taps from it by shifting the start address of the A-operand
+// shared-memory descriptor by whole 128-byte rows.  Measured on B200: the tensor core applies the 128B-swizzle XOR to
+// the absolute shared-memory address bits, exactly like the TMA unit that wrote the patch, so a start address on any
+// 128-byte row reads the right data with the descriptor's base_offset field left at 0 (setting it to (addr >> 7) & 7
+// scrambles the rows; tests/test_gpu_parity.py::test_conv_flat runs both ways via YAD_FLAT_FLAGS).
+// Because h is the fastest index and H is small (8, 4, 2, 1), the halo of a 3x3 is only Hp + 1 pixels.
+// Weights stream through their own ring, one [BN x 64] block per (tap, chunk), shared by the MT accumulators.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias / residual / activation -> global), TMEM accumulators double-buffered
+// so the epilogue of super-tile i overlaps the MMAs of super-tile i + 1.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <string.h>
+
+namespace yad {
+
+constexpr int FL_THREADS = 192;
+constexpr int FL_MAX_STEPS = 64;
+constexpr int FL_MAX_RING = 8;
+constexpr int FL_BOX_ROWS = 64;    // pixel rows per TMA box of the patch (8 KB)
+
+struct FlatParams {
+  int64_t F;                    // flat pixels = B * Wp * Hp
+  int32_t H, W, Hp, Wp;
+  int32_t MT, BN, n_ntiles, n_super;   // n_super = M super-tiles * n_ntiles
+  int32_t n_steps;
+  int32_t NA, NW;               // ring depths
+  int32_t patch_rows, patch_bytes, w_bytes;
+  int32_t min_off;
+  int32_t Cout, ld_out, co_off, ld_res, act;
+  uint32_t idesc;
+  int32_t flags;                // bit 0: debug - set the descriptor base_offset to (addr >> 7) & 7 (wrong on B200)
+  int16_t step_off[FL_MAX_STEPS];     // flat pixel shift of the tap
+  int16_t step_chunk[FL_MAX_STEPS];   // 64-channel chunk
+  int8_t step_first[FL_MAX_STEPS];    // first step of its chunk (load a new patch)
+  int8_t step_last[FL_MAX_STEPS];     // last step of its chunk (release the patch)
+  int32_t step_wk[FL_MAX_STEPS];      // K offset of the [BN x 64] weight block
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major SWIZZLE_128B descriptor whose start may sit on any 128-byte row of a 1024-byte swizzle atom
+__device__ __forceinline__ uint64_t make_sw128_desc_row(uint32_t smem_addr, bool with_base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (with_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(FL_THREADS, 1)
+conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ FlatParams p, const float* __restrict__ bias,
+                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sm_a = smem;                                       // [NA][patch_bytes]
+  uint8_t* sm_w = sm_a + (size_t)p.NA * p.patch_bytes;        // [NW][w_bytes]
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sm_w + (size_t)p.NW * p.w_bytes);
+  uint64_t* empty_a = full_a + FL_MAX_RING;
+  uint64_t* full_w = empty_a + FL_MAX_RING;
+  uint64_t* empty_w = full_w + FL_MAX_RING;
+  uint64_t* tmem_full = empty_w + FL_MAX_RING;                // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                       // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [n_ntiles * BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncout_pad = p.n_ntiles * p.BN;
+  for (int i = threadIdx.x; i < ncout_pad; i += FL_THREADS) s_bias[i] = bias[i];
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    for (int s = 0; s < FL_MAX_RING; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&empty_a[s], 1);
+      mbar_init(&full_w[s], 1);
+      mbar_init(&empty_w[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int rows_per_super = 128 * p.MT;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t ia = 0, iw = 0;
+      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
+        const int64_t f0 = (int64_t)mtile * rows_per_super;
+        const int n0 = nt * p.BN;
+        for (int s = 0; s < p.n_steps; ++s) {
+          if (p.step_first[s]) {
+            const uint32_t slot = ia % p.NA;
+            if (ia >= (uint32_t)p.NA) mbar_wait(&empty_a[slot], ((ia / p.NA) - 1) & 1);
+            uint8_t* dst = sm_a + (size_t)slot * p.patch_bytes;
+            mbar_expect_tx(&full_a[slot], (uint32_t)p.patch_bytes);
+            const int c0 = p.step_chunk[s] * 64;
+            const int r0 = (int)(f0 + p.min_off);
+            for (int i = 0; i < p.patch_rows / FL_BOX_ROWS; ++i)
+              tma_load_2d(&map_a, &full_a[slot], dst + i * (FL_BOX_ROWS * 128), c0, r0 + i * FL_BOX_ROWS);
+            ++ia;
+          }
+          const uint32_t slot = iw % p.NW;
+          if (iw >= (uint32_t)p.NW) mbar_wait(&empty_w[slot], ((iw / p.NW) - 1) & 1);
+          mbar_expect_tx(&full_w[slot], (uint32_t)p.w_bytes);
+          tma_load_2d(&map_w, &full_w[slot], sm_w + (size_t)slot * p.w_bytes, p.step_wk[s], n0);
+          ++iw;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      uint32_t ia = 0, iw = 0, it = 0;
+      const bool with_bo = (p.flags & 1) != 0;
+      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++it) {
+        const uint32_t as = it & 1;
+        if (it >= 2) mbar_wait(&tmem_empty[as], ((it >> 1) - 1) & 1);
+        tc_fence_after();
+        uint32_t a_base = 0, a_slot = 0;
+        for (int s = 0; s < p.n_steps; ++s) {
+          if (p.step_first[s]) {
+            a_slot = ia % p.NA;
+            mbar_wait(&full_a[a_slot], (ia / p.NA) & 1);
+            a_base = smem_u32(sm_a + (size_t)a_slot * p.patch_bytes);
+            ++ia;
+          }
+          const uint32_t w_slot = iw % p.NW;
+          mbar_wait(&full_w[w_slot], (iw / p.NW) & 1);
+          ++iw;
+          tc_fence_after();
+          const uint32_t wb = smem_u32(sm_w + (size_t)w_slot * p.w_bytes);
+          const uint32_t row0 = (uint32_t)(p.step_off[s] - p.min_off);
+          for (int mt = 0; mt < p.MT; ++mt) {
+            const uint32_t a_addr = a_base + (row0 + 128u * mt) * 128u;
+            const uint32_t d_tmem = tmem_base + (as * p.MT + mt) * p.BN;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, make_sw128_desc_row(a_addr + k * 32, with_bo), make_sw128_desc_row(wb + k * 32, false),
+                        p.idesc, (s > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_w[w_slot]);
+          if (p.step_last[s]) umma_commit(&empty_a[a_slot]);
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, one TMEM lane quadrant each =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint32_t it = 0;
+    for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++it) {
+      const uint32_t as = it & 1;
+      const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
+      const int n0 = nt * p.BN;
+      mbar_wait(&tmem_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int64_t f = (int64_t)mtile * rows_per_super + 128 * mt + r;
+        const int h = (int)(f % p.Hp);
+        const int w = (int)((f / p.Hp) % p.Wp);
+        const bool row_ok = f < p.F && h < p.H && w < p.W;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
+          tmem_ld_wait();
+          const int nbase = n0 + c0;
+          if (row_ok && nbase < p.Cout) {
+            float x[32];
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + nbase);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = bp[j4];
+              x[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
+              x[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+              x[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
+              x[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+            }
+            if (residual != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(residual + f * p.ld_res + nbase);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 u = __ldg(rp + j4);
+                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  x[j4 * 8 + e * 2 + 0] += __uint_as_float(ww[e] << 16);
+                  x[j4 * 8 + e * 2 + 1] += __uint_as_float(ww[e] & 0xffff0000u);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act);
+            uint4* op = reinterpret_cast<uint4*>(out + f * p.ld_out + p.co_off + nbase);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint32_t ww[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+                ww[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              op[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);   // conv_tc.cu
+
+int init_conv_flat_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_flat_kernel) failed: %s", cudaGetErrorString(e));
+    return YAD_ERR_CUDA;
+  }
+  return YAD_OK;
+}
+
+}  // namespace yad
+
+extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad,
+                             const float* bias, const void* residual, void* out, int32_t flags, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(d && in && weight && bias && out, "yad_conv_flat: null pointer");
+  YAD_CHECK_ARG(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->Hp >= d->H && d->Wp >= d->W, "yad_conv_flat: bad geometry");
+  YAD_CHECK_ARG(d->Cin % 64 == 0 && d->Cin >= 64, "yad_conv_flat: Cin=%d must be a multiple of 64", d->Cin);
+  YAD_CHECK_ARG(d->ld_in % 8 == 0 && d->ld_in >= d->Cin, "yad_conv_flat: bad ld_in=%d", d->ld_in);
+  YAD_CHECK_ARG(cout_pad % 64 == 0 && cout_pad >= d->Cout && d->Cout % 32 == 0,
+                "yad_conv_flat: Cout=%d must be a multiple of 32 and cout_pad=%d a multiple of 64", d->Cout, cout_pad);
+  YAD_CHECK_ARG(d->ld_out % 8 == 0 && d->co_off % 8 == 0 && d->ld_out >= d->co_off + d->Cout, "yad_conv_flat: bad ld_out/co_off");
+  YAD_CHECK_ARG(residual == nullptr || (d->ld_res % 8 == 0 && d->ld_res >= d->Cout), "yad_conv_flat: bad ld_res");
+  YAD_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 49 && d->ph >= 0 && d->pw >= 0 && d->ph < d->kh && d->pw < d->kw,
+                "yad_conv_flat: bad kernel/padding");
+  YAD_CHECK_ARG(d->kh - 1 - d->ph == d->ph && d->kw - 1 - d->pw == d->pw, "yad_conv_flat: only 'same' (output size = input size) convs");
+  YAD_CHECK_ARG((reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(weight) % 16 == 0) &&
+                    (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (reinterpret_cast<uintptr_t>(residual) % 16 == 0),
+                "yad_conv_flat: pointers must be 16-byte aligned");
+
+  FlatParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = d->H;
+  p.W = d->W;
+  p.Hp = d->Hp;
+  p.Wp = d->Wp;
+  p.F = (int64_t)d->B * d->Wp * d->Hp;
+  YAD_CHECK_ARG(p.F < (int64_t)1 << 31, "yad_conv_flat: tensor too large (%lld pixels)", (long long)p.F);
+  // taps: skip those that only ever see padding; the rest must be covered by the halo
+  int taps_dh[49], taps_dw[49], taps_idx[49], n_taps = 0, reach_h = 0, reach_w = 0;
+  for (int kh = 0; kh < d->kh; ++kh) {
+    const int dh = kh - d->ph;
+    if (dh <= -d->H || dh >= d->H) continue;
+    for (int kw = 0; kw < d->kw; ++kw) {
+      const int dw = kw - d->pw;
+      if (dw <= -d->W || dw >= d->W) continue;
+      taps_dh[n_taps] = dh;
+      taps_dw[n_taps] = dw;
+      taps_idx[n_taps] = kh * d->kw + kw;
+      reach_h = dh < 0 ? (-dh > reach_h ? -dh : reach_h) : (dh > reach_h ? dh : reach_h);
+      reach_w = dw < 0 ? (-dw > reach_w ? -dw : reach_w) : (dw > reach_w ? dw : reach_w);
+      ++n_taps;
+    }
+  }
+  YAD_CHECK_ARG(d->Hp - d->H >= reach_h && d->Wp - d->W >= reach_w,
+                "yad_conv_flat: halo (%d,%d) smaller than the filter reach (%d,%d)", d->Hp - d->H, d->Wp - d->W, reach_h, reach_w);
+  const int n_chunks = d->Cin / 64;
+  YAD_CHECK_ARG(n_taps * n_chunks <= FL_MAX_STEPS, "yad_conv_flat: %d taps x %d chunks exceed %d steps", n_taps, n_chunks, FL_MAX_STEPS);
+  int min_off = 0, max_off = 0, ns = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    for (int t = 0; t < n_taps; ++t, ++ns) {
+      const int off = taps_dw[t] * d->Hp + taps_dh[t];
+      min_off = off < min_off ? off : min_off;
+      max_off = off > max_off ? off : max_off;
+      p.step_off[ns] = (int16_t)off;
+      p.step_chunk[ns] = (int16_t)c;
+      p.step_first[ns] = (t == 0);
+      p.step_last[ns] = (t == n_taps - 1);
+      p.step_wk[ns] = taps_idx[t] * d->Cin + c * 64;
+    }
+  }
+  p.n_steps = ns;
+  p.min_off = min_off;
+  p.BN = cout_pad % 128 == 0 ? 128 : 64;
+  p.n_ntiles = cout_pad / p.BN;
+  p.MT = 256 / p.BN;                      // 2 accumulator stages x MT x BN = 512 TMEM columns
+  const int rows_per_super = 128 * p.MT;
+  const int patch_rows_raw = rows_per_super + max_off - min_off;
+  p.patch_rows = (patch_rows_raw + FL_BOX_ROWS - 1) / FL_BOX_ROWS * FL_BOX_ROWS;
+  p.patch_bytes = p.patch_rows * 128;
+  p.w_bytes = p.BN * 128;
+  const int64_t n_mtiles = (p.F + rows_per_super - 1) / rows_per_super;
+  p.n_super = (int)(n_mtiles * p.n_ntiles);
+  p.Cout = d->Cout;
+  p.ld_out = d->ld_out;
+  p.co_off = d->co_off;
+  p.ld_res = d->ld_res;
+  p.act = d->act;
+  p.flags = flags;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // shared-memory budget: barriers + bias + alignment slack, then the two rings
+  const size_t fixed = 1024 + (4 * FL_MAX_RING + 4) * 8 + 16 + (size_t)cout_pad * 4 + 64;
+  const size_t budget = 227 * 1024 - fixed;
+  p.NA = n_chunks > 1 ? 3 : 2;
+  while (p.NA > 1 && (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes > budget) --p.NA;
+  YAD_CHECK_ARG((size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes <= budget, "yad_conv_flat: patch of %d rows does not fit", p.patch_rows);
+  p.NW = (int)((budget - (size_t)p.NA * p.patch_bytes) / p.w_bytes);
+  if (p.NW > FL_MAX_RING) p.NW = FL_MAX_RING;
+  const size_t smem = fixed + (size_t)p.NA * p.patch_bytes + (size_t)p.NW * p.w_bytes;
+
+  CUtensorMap map_a, map_w;
+  {
+    const uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)p.F};
+    const uint64_t strides[1] = {(uint64_t)d->ld_in * 2};
+    const uint32_t box[2] = {64u, (uint32_t)FL_BOX_ROWS};
+    int rc = encode_map_bf16(&map_a, in, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d->kh * d->kw * d->Cin, (uint64_t)cout_pad};
+    const uint64_t strides[1] = {(uint64_t)d->kh * d->kw * d->Cin * 2};
+    const uint32_t box[2] = {64u, (uint32_t)p.BN};
+    int rc = encode_map_bf16(&map_w, weight, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const int nsm = sm_count() > 0 ? sm_count() : 148;
+  const int grid = p.n_super < nsm ? p.n_super : nsm;
+  conv_flat_kernel<<<grid, FL_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p, bias,
+                                                                   reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                                   reinterpret_cast<__nv_bfloat16*>(out));
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}

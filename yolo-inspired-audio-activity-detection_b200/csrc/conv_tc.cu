@@ -45,6 +45,7 @@ struct TcParams {
   int8_t tap_dh[TC_MAX_TAPS];
   int8_t tap_widx[TC_MAX_TAPS];
   int32_t cin;                   // K elements per tap in the packed weight
+  int32_t osw, osh, osb;         // output pixel strides
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
@@ -161,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int bl = r / (p.tw * p.th);
     const int ow = w0 + wl, oh = h0 + hl, ob = b0 + bl;
     const bool row_ok = (r < rows) && (ow < p.Wo) && (oh < p.Ho) && (ob < p.B);
-    const int64_t pix = ((int64_t)ob * p.Ho + oh) * p.Wo + ow;
+    const int64_t pix = (int64_t)ob * p.osb + (int64_t)oh * p.osh + (int64_t)ow * p.osw;
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -239,7 +240,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box) {
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(tensor_map_encode_fn());
   if (!fn) {
@@ -324,6 +325,10 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
   const int Ho = (d->H + 2 * d->ph - d->kh) / d->sh + 1;
   const int Wo = (d->W + 2 * d->pw - d->kw) / d->sw + 1;
   YAD_CHECK_ARG(Ho >= 1 && Wo >= 1 && d->B >= 1, "yad_conv_tc: empty output");
+  const bool in_dense = d->in_sw == 0 && d->in_sh == 0 && d->in_sb == 0;
+  const bool out_dense = d->out_sw == 0 && d->out_sh == 0 && d->out_sb == 0;
+  const int64_t isw = in_dense ? 1 : d->in_sw, ish = in_dense ? d->W : d->in_sh, isb = in_dense ? (int64_t)d->H * d->W : d->in_sb;
+  YAD_CHECK_ARG(isw >= 1 && ish >= isw && isb >= ish, "yad_conv_tc: input pixel strides must satisfy 1 <= in_sw <= in_sh <= in_sb");
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -349,6 +354,9 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
   p.act = d->act;
   p.out_f32 = (out_dtype == YAD_F32);
   p.ld_out2 = ld_out2;
+  p.osw = out_dense ? 1 : d->out_sw;
+  p.osh = out_dense ? Wo : d->out_sh;
+  p.osb = out_dense ? Ho * Wo : d->out_sb;
   // instruction descriptor: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -390,15 +398,15 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
     for (int prw = 0; prw < d->sw; ++prw) {
       const int mi = prh * d->sw + prw;
       const int Wm = (d->W - prw + d->sw - 1) / d->sw, Hm = (d->H - prh + d->sh - 1) / d->sh;
-      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in) + ((int64_t)prh * d->W + prw) * d->ld_in;
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in) + ((int64_t)prh * ish + prw * isw) * d->ld_in;
       if (Wm <= 0 || Hm <= 0) {  // parity class with no element (e.g. H == 1, odd rows): alias map 0, never referenced
         maps[mi] = maps[0];
         continue;
       }
       const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)Wm, (uint64_t)Hm, (uint64_t)d->B};
-      const uint64_t strides[3] = {(uint64_t)d->sw * d->ld_in * 2, (uint64_t)d->sh * d->W * d->ld_in * 2,
-                                   (uint64_t)d->H * d->W * d->ld_in * 2};
-      int rc = encode_map(&maps[mi], base, 4, dims, strides, box);
+      const uint64_t strides[3] = {(uint64_t)d->sw * isw * d->ld_in * 2, (uint64_t)d->sh * ish * d->ld_in * 2,
+                                   (uint64_t)isb * d->ld_in * 2};
+      int rc = encode_map_bf16(&maps[mi], base, 4, dims, strides, box);
       if (rc) return rc;
     }
   }
@@ -409,7 +417,7 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
     const uint64_t dims[2] = {(uint64_t)d->kh * d->kw * d->Cin, (uint64_t)cout_pad};
     const uint64_t strides[1] = {(uint64_t)d->kh * d->kw * d->Cin * 2};
     const uint32_t bx[2] = {64u, (uint32_t)BN};
-    int rc = encode_map(&map_w, weight, 2, dims, strides, bx);
+    int rc = encode_map_bf16(&map_w, weight, 2, dims, strides, bx);
     if (rc) return rc;
   }
   dim3 grid((unsigned)(p.n_wt * p.n_ht * p.n_bt), (unsigned)p.n_ntiles);

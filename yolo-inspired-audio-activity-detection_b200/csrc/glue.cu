@@ -7,8 +7,8 @@ namespace yad {
 
 // adaptive_avg_pool2d(x, (1, W))  -  modules/_common.py:248-252
 template <typename T>
-__global__ void hmean_kernel(const T* __restrict__ in, int64_t B, int H, int W, int C, int ld_in,
-                             T* __restrict__ out, int ld_out, int co_off) {
+__global__ void hmean_kernel(const T* __restrict__ in, int64_t B, int H, int W, int C, int ld_in, int64_t isw, int64_t ish,
+                             int64_t isb, T* __restrict__ out, int ld_out, int co_off) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = B * W * C;
   if (gid >= n) return;
@@ -17,7 +17,7 @@ __global__ void hmean_kernel(const T* __restrict__ in, int64_t B, int H, int W, 
   const int w = (int)(bw % W);
   const int64_t b = bw / W;
   float acc = 0.0f;
-  for (int h = 0; h < H; ++h) acc += ld_as_float(in + ((b * H + h) * W + w) * (int64_t)ld_in + c);
+  for (int h = 0; h < H; ++h) acc += ld_as_float(in + (b * isb + h * ish + w * isw) * (int64_t)ld_in + c);
   st_from_float(out + (b * W + w) * (int64_t)ld_out + co_off + c, acc / (float)H);
 }
 
@@ -105,8 +105,8 @@ __global__ void repvgg_merge_kernel(const T* __restrict__ a, const T* __restrict
 
 extern "C" {
 
-int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, int32_t C, int32_t ld_in, void* out,
-              int32_t ld_out, int32_t co_off, yad_stream_t stream) {
+int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, int32_t C, int32_t ld_in, int32_t in_sw,
+              int32_t in_sh, int32_t in_sb, void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream) {
   YAD_CHECK_ARG(in && out && H >= 1 && W >= 1 && C >= 1 && ld_in >= C && ld_out >= co_off + C,
                 "yad_hmean: bad arguments");
   YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_hmean: bad dtype %d", dtype);
@@ -114,7 +114,8 @@ int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, in
   if (n == 0) return YAD_OK;
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-  YAD_DISPATCH_DTYPE(dtype, yad::hmean_kernel, (const T*)in, B, H, W, C, ld_in, (T*)out, ld_out, co_off);
+  YAD_DISPATCH_DTYPE(dtype, yad::hmean_kernel, (const T*)in, B, H, W, C, ld_in, (int64_t)in_sw, (int64_t)in_sh, (int64_t)in_sb,
+                     (T*)out, ld_out, co_off);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

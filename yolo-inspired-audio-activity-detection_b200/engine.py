@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import _lib
 from . import frontend_consts as fc
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvDesc
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, BF16, F32, ConvDesc, FlatDesc
 
 
 def _ceil(a: int, b: int) -> int:
@@ -58,6 +58,8 @@ class _Conv:
             wt = torch.zeros(self.cout_pad, self.kh, self.kw, self.cin_pad, device=dev, dtype=torch.float32)
             wt[: self.cout, :, :, : self.cin] = w.permute(0, 2, 3, 1)
             self.w = wt.reshape(self.cout_pad, -1).to(torch.bfloat16).contiguous()
+            # the same filter with its taps ordered (kw, kh): used when a conv is run with the roles of H and W swapped
+            self.w_t = wt.permute(0, 2, 1, 3).reshape(self.cout_pad, -1).to(torch.bfloat16).contiguous() if self.kh * self.kw > 1 else self.w
             bp = torch.zeros(self.cout_pad, device=dev, dtype=torch.float32)
             bp[: self.cout] = self.bias
             self.bias = bp
@@ -224,6 +226,41 @@ class InferenceEngine:
                 raise AssertionError("out2 is only used on the bf16 path")
         _lib.check(rc, f"conv {cv.name}")
 
+    # ---- flat (halo-padded, h-fastest) layout of the bf16 backbone: tensor [B, Wp, Hp, ld], see include/yad_b200.h
+    @staticmethod
+    def _flat_geom(H: int, W: int) -> Tuple[int, int]:
+        return (H + 1 if H > 1 else 1), W + 1
+
+    def _flat_buf(self, plan, name, B, H, W, ld):
+        t = plan.get(name)
+        if t is None:
+            Hp, Wp = self._flat_geom(H, W)
+            t = plan[name] = torch.zeros((B, Wp, Hp, ld), device=self.dev, dtype=torch.bfloat16)   # halo stays zero forever
+        return t
+
+    def _conv_flat(self, cv: _Conv, x: torch.Tensor, H: int, W: int, out: torch.Tensor, res: Optional[torch.Tensor] = None):
+        """Stride-1 'same' conv, flat in -> flat out (same geometry), patch-resident tcgen05 kernel."""
+        B, Wp, Hp, ld_in = x.shape
+        assert out.shape[:3] == x.shape[:3] and cv.sh == 1 and cv.sw == 1
+        d = FlatDesc(B=B, H=H, W=W, Hp=Hp, Wp=Wp, Cin=cv.cin_pad, ld_in=ld_in, Cout=cv.cout, ld_out=out.shape[3], co_off=0,
+                     kh=cv.kh, kw=cv.kw, ph=cv.ph, pw=cv.pw, act=cv.act, ld_res=0 if res is None else res.shape[3])
+        rc = self.lib.yad_conv_flat(C.byref(d), x.data_ptr(), cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), _lib.ptr(res),
+                                    out.data_ptr(), 0, self._stream())
+        _lib.check(rc, f"conv_flat {cv.name}")
+
+    def _conv_flat_s2(self, cv: _Conv, x: torch.Tensor, H: int, W: int, out: torch.Tensor, Ho: int, Wo: int):
+        """Strided conv, flat in -> flat out: the tap-by-tap kernel run with the roles of H and W swapped (so that the
+        input pixel strides are ascending for its 4-D tensor map), transposed filter taps."""
+        B, Wp, Hp, ld_in = x.shape
+        _, Wpo, Hpo, ld_out = out.shape
+        d = ConvDesc(B=B, H=W, W=H, Cin=cv.cin_pad, ld_in=ld_in, Cout=cv.cout, ld_out=ld_out, co_off=0, kh=cv.kw, kw=cv.kh,
+                     sh=cv.sw, sw=cv.sh, ph=cv.pw, pw=cv.ph, act=cv.act, ld_res=0,
+                     in_sw=1, in_sh=Hp, in_sb=Wp * Hp, out_sw=1, out_sh=Hpo, out_sb=Wpo * Hpo)
+        assert (W + 2 * cv.pw - cv.kw) // cv.sw + 1 == Wo and (H + 2 * cv.ph - cv.kh) // cv.sh + 1 == Ho
+        rc = self.lib.yad_conv_tc(C.byref(d), x.data_ptr(), cv.w_t.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), 0, out.data_ptr(),
+                                  BF16, 0, 0, self._stream())
+        _lib.check(rc, f"conv(s2, flat) {cv.name}")
+
     def _repblock(self, plan, key, blocks, x, cin_off, out, co_off, out2=None):
         """RepBlock: chain of RepVGG blocks; the last one writes (out, co_off) [and the fp32 copy out2]."""
         B, H, W, _ = x.shape
@@ -294,41 +331,78 @@ class InferenceEngine:
         else:
             _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
         H, W = (c1.shape[1] + 6 - 7) // 2 + 1, (c1.shape[2] + 6 - 7) // 2 + 1
-        cur = self._buf(plan, "c2", B, H, W, 64)
-        self._conv(self.conv2, c1, 0, cur, 0)
-        fmaps = []
-        for li, blocks in enumerate(self.stages):
-            for bi, blk in enumerate(blocks):
-                c1v, c2v = blk["c1"], blk["c2"]
-                Ho, Wo = (H + 2 - 3) // c1v.sh + 1, (W + 2 - 3) // c1v.sw + 1
-                ld = _ceil(c1v.cout, 64) if bf else c1v.cout
-                t = self._buf(plan, f"s{li}.{bi}.t", B, Ho, Wo, ld)
-                y = self._buf(plan, f"s{li}.{bi}.y", B, Ho, Wo, ld)
-                self._conv(c1v, cur, 0, t, 0)
-                if "ds" in blk:
-                    idt = self._buf(plan, f"s{li}.{bi}.d", B, Ho, Wo, ld)
-                    self._conv(blk["ds"], cur, 0, idt, 0)
-                else:
-                    idt = cur
-                self._conv(c2v, t, 0, y, 0, res=idt)
-                cur, H, W = y, Ho, Wo
-            fmaps.append(cur)
-        if taps is not None:
-            taps["fmaps"] = [f.float().permute(0, 3, 1, 2).contiguous() for f in fmaps]
+        fmaps, geoms = [], []
+        if bf:
+            # backbone activations live in the flat halo-padded layout [B, Wp, Hp, ld] (conv_flat.cu)
+            cur = self._flat_buf(plan, "c2", B, H, W, 64)
+            Hp, Wp = self._flat_geom(H, W)
+            cv = self.conv2
+            d = ConvDesc(B=B, H=c1.shape[1], W=c1.shape[2], Cin=cv.cin_pad, ld_in=64, Cout=cv.cout, ld_out=64, co_off=0, kh=cv.kh,
+                         kw=cv.kw, sh=cv.sh, sw=cv.sw, ph=cv.ph, pw=cv.pw, act=cv.act, ld_res=0, out_sw=Hp, out_sh=1, out_sb=Wp * Hp)
+            _lib.check(self.lib.yad_conv_tc(C.byref(d), c1.data_ptr(), cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), 0,
+                                            cur.data_ptr(), BF16, 0, 0, s()), "conv fe.conv2")
+            for li, blocks in enumerate(self.stages):
+                for bi, blk in enumerate(blocks):
+                    c1v, c2v = blk["c1"], blk["c2"]
+                    Ho, Wo = (H + 2 - 3) // c1v.sh + 1, (W + 2 - 3) // c1v.sw + 1
+                    ld = _ceil(c1v.cout, 64)
+                    t = self._flat_buf(plan, f"s{li}.{bi}.t", B, Ho, Wo, ld)
+                    y = self._flat_buf(plan, f"s{li}.{bi}.y", B, Ho, Wo, ld)
+                    if c1v.sh == 1 and c1v.sw == 1:
+                        self._conv_flat(c1v, cur, H, W, t)
+                    else:
+                        self._conv_flat_s2(c1v, cur, H, W, t, Ho, Wo)
+                    if "ds" in blk:
+                        idt = self._flat_buf(plan, f"s{li}.{bi}.d", B, Ho, Wo, ld)
+                        self._conv_flat_s2(blk["ds"], cur, H, W, idt, Ho, Wo)
+                    else:
+                        idt = cur
+                    self._conv_flat(c2v, t, Ho, Wo, y, res=idt)
+                    cur, H, W = y, Ho, Wo
+                fmaps.append(cur)
+                geoms.append((H, W))
+            if taps is not None:
+                taps["fmaps"] = [f[:, :w_, :h_, :].float().permute(0, 3, 2, 1).contiguous() for f, (h_, w_) in zip(fmaps, geoms)]
+        else:
+            cur = self._buf(plan, "c2", B, H, W, 64)
+            self._conv(self.conv2, c1, 0, cur, 0)
+            for li, blocks in enumerate(self.stages):
+                for bi, blk in enumerate(blocks):
+                    c1v, c2v = blk["c1"], blk["c2"]
+                    Ho, Wo = (H + 2 - 3) // c1v.sh + 1, (W + 2 - 3) // c1v.sw + 1
+                    ld = c1v.cout
+                    t = self._buf(plan, f"s{li}.{bi}.t", B, Ho, Wo, ld)
+                    y = self._buf(plan, f"s{li}.{bi}.y", B, Ho, Wo, ld)
+                    self._conv(c1v, cur, 0, t, 0)
+                    if "ds" in blk:
+                        idt = self._buf(plan, f"s{li}.{bi}.d", B, Ho, Wo, ld)
+                        self._conv(blk["ds"], cur, 0, idt, 0)
+                    else:
+                        idt = cur
+                    self._conv(c2v, t, 0, y, 0, res=idt)
+                    cur, H, W = y, Ho, Wo
+                fmaps.append(cur)
+                geoms.append((H, W))
+            if taps is not None:
+                taps["fmaps"] = [f.float().permute(0, 3, 1, 2).contiguous() for f in fmaps]
 
         # ---- neck (H = 1 after the H-mean; modules/_common.py:241-265)
-        f1, f2, f3, f4 = fmaps
-        hs = [f.shape[1] for f in fmaps]
+        hs = [g_[0] for g_ in geoms]
         if not (hs[0] != hs[1] != hs[2] != hs[3]):
             raise NotImplementedError("neck with equal feature-map heights (2-D neck) is not built")
         pooled = []
-        for i, f in enumerate(fmaps):
-            Bf, Hf, Wf, ldf = f.shape
-            if Hf == 1:
+        for i, (f, (Hf, Wf)) in enumerate(zip(fmaps, geoms)):
+            ldf = f.shape[3]
+            if Hf == 1 and not bf:
                 pooled.append(f)
                 continue
             pm = self._buf(plan, f"fm{i}", B, 1, Wf, ldf)
-            _lib.check(self.lib.yad_hmean(f.data_ptr(), self.dtype, B, Hf, Wf, ldf, ldf, pm.data_ptr(), ldf, 0, s()), "hmean")
+            if bf:
+                Hpf, Wpf = self._flat_geom(Hf, Wf)
+                isw, ish, isb = Hpf, 1, Wpf * Hpf
+            else:
+                isw, ish, isb = 1, Wf, Hf * Wf
+            _lib.check(self.lib.yad_hmean(f.data_ptr(), self.dtype, B, Hf, Wf, ldf, ldf, isw, ish, isb, pm.data_ptr(), ldf, 0, s()), "hmean")
             pooled.append(pm)
         f1m, f2m, f3m, f4m = pooled
         W1, W2, W3, W4 = f1m.shape[2], f2m.shape[2], f3m.shape[2], f4m.shape[2]
