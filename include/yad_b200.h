@@ -137,8 +137,7 @@ int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int3
  * bottom rows of a 3x3 at H = 1, are skipped and need no halo).  Every tap is then a constant shift in f, so a CTA
  * loads each input pixel once per tile instead of once per tap.  in / out / residual share the geometry.
  * Requirements: Cin % 64 == 0, Cout % 32 == 0, cout_pad % 64 == 0 (weight rows / bias zero padded), bf16 in and out.
- * weight [cout_pad][kh*kw*Cin] bf16, K ordered (kh, kw, cin) as for yad_conv_tc.  flags: 0 (bit 0 = debug: non-zero
- * descriptor base_offset, kept to document the measured hardware behaviour). */
+ * weight [cout_pad][kh*kw*Cin] bf16, K ordered (kh, kw, cin) as for yad_conv_tc.  flags: reserved, 0. */
 typedef struct {
   int32_t B, H, W;            /* image size */
   int32_t Hp, Wp;             /* padded pitches */

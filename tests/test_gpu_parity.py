@@ -234,7 +234,7 @@ def test_conv_flat(case, cuda_dev):
     bp = torch.zeros(cout_p, device=cuda_dev); bp[:Cout] = b.to(cuda_dev)
     d = _lib.FlatDesc(B=B, H=H, W=W, Hp=Hp, Wp=Wp, Cin=Cin, ld_in=Cin, Cout=Cout, ld_out=ld_out, co_off=co_off, kh=k, kw=k,
                       ph=k // 2, pw=k // 2, act=act, ld_res=Cout if use_res else 0)
-    flags = int(__import__("os").environ.get("YAD_FLAT_FLAGS", "0"))   # 1 = set base_offset in the A descriptor: fails on B200
+    flags = 0
     _lib.check(lib.yad_conv_flat(C.byref(d), xin.data_ptr(), wt.data_ptr(), cout_p, bp.data_ptr(), _lib.ptr(rin), out.data_ptr(),
                                  flags, _stream()), "conv_flat")
     torch.cuda.synchronize()

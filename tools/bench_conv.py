@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Micro-benchmark of yad_conv_flat on the backbone's layer shapes (CUDA-event timed, L2 flushed between runs)."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import yad_b200  # noqa: E402,F401
+from yad_b200 import _lib  # noqa: E402
+
+SHAPES = {  # name: (H, W, Cin, Cout, k)
+    "layer1": (8, 240, 64, 64, 3), "layer2": (4, 120, 128, 128, 3), "layer3": (2, 60, 256, 256, 3), "layer4": (1, 30, 512, 512, 3),
+    "l1_1x1": (8, 240, 64, 64, 1), "l2_1x1": (4, 120, 128, 128, 1),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--shapes", default="layer1,layer2,layer3,layer4,l1_1x1,l2_1x1")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    lib = _lib.init(0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for name in a.shapes.split(","):
+        H, W, Cin, Cout, k = SHAPES[name]
+        B = a.batch
+        Hp, Wp = (H + k // 2 if H > 1 else 1), W + k // 2
+        x = torch.randn(B, Wp, Hp, Cin, device=dev).to(torch.bfloat16)
+        w = (torch.randn(Cout, k * k * Cin, device=dev) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+        bias = torch.zeros(Cout, device=dev)
+        res = torch.randn(B, Wp, Hp, Cout, device=dev).to(torch.bfloat16) if a.res else None
+        out = torch.zeros(B, Wp, Hp, Cout, device=dev, dtype=torch.bfloat16)
+        d = _lib.FlatDesc(B=B, H=H, W=W, Hp=Hp, Wp=Wp, Cin=Cin, ld_in=Cin, Cout=Cout, ld_out=Cout, co_off=0, kh=k, kw=k, ph=k // 2,
+                          pw=k // 2, act=1, ld_res=Cout if a.res else 0)
+        ts = []
+        for i in range(6):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.yad_conv_flat(C.byref(d), x.data_ptr(), w.data_ptr(), Cout, bias.data_ptr(), _lib.ptr(res), out.data_ptr(),
+                                         a.flags, st), "conv_flat")
+            e1.record()
+            torch.cuda.synchronize()
+            if i:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+        t = sorted(ts)[len(ts) // 2]
+        useful = B * H * W * Cout * Cin * (k * k if H > 1 else k) / 1e6
+        print(f"{name:8s} B={B} flags={a.flags} res={a.res}: {t:8.1f} us  useful {2 * useful / t / 1e6:7.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()

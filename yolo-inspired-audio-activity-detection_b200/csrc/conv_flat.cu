@@ -13,12 +13,14 @@
 // shared-memory descriptor by whole 128-byte rows.  Measured on B200: the tensor core applies the 128B-swizzle XOR to
 // the absolute shared-memory address bits, exactly like the TMA unit that wrote the patch, so a start address on any
 // 128-byte row reads the right data with the descriptor's base_offset field left at 0 (setting it to (addr >> 7) & 7
-// scrambles the rows; tests/test_gpu_parity.py::test_conv_flat runs both ways via YAD_FLAT_FLAGS).
+// scrambled the rows: 7 of 8 parity cases failed with it and all pass without, round-1 logs), at no cost in MMA rate
+// (tools/micro/mma_rate.cu: 48 / 64 / 128 cycles per MMA at N = 64 / 128 / 256 with or without the row shift).
 // Because h is the fastest index and H is small (8, 4, 2, 1), the halo of a 3x3 is only Hp + 1 pixels.
 // Weights stream through their own ring, one [BN x 64] block per (tap, chunk), shared by the MT accumulators.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> bias / residual / activation -> global), TMEM accumulators double-buffered
+// warps 2..9 = epilogue (tcgen05.ld -> bias / residual / activation -> global; two warps per TMEM lane quadrant, each
+// taking every second 32-column chunk; the residual of the next chunk is prefetched), TMEM accumulators double-buffered
 // so the epilogue of super-tile i overlaps the MMAs of super-tile i + 1.
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -26,7 +28,8 @@
 
 namespace yad {
 
-constexpr int FL_THREADS = 192;
+constexpr int FL_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int FL_EPI_THREADS = 256;
 constexpr int FL_MAX_STEPS = 64;
 constexpr int FL_MAX_RING = 8;
 constexpr int FL_BOX_ROWS = 64;    // pixel rows per TMA box of the patch (8 KB)
@@ -41,7 +44,9 @@ struct FlatParams {
   int32_t min_off;
   int32_t Cout, ld_out, co_off, ld_res, act;
   uint32_t idesc;
-  int32_t flags;                // bit 0: debug - set the descriptor base_offset to (addr >> 7) & 7 (wrong on B200)
+  int32_t flags;                // reserved (0)
+  uint32_t step_mma[FL_MAX_STEPS];    // MMA warp: bits 0..15 = first patch row of the tap in 16-byte units, bit 30 = first
+                                      // step of its chunk, bit 31 = last step of its chunk
   int16_t step_off[FL_MAX_STEPS];     // flat pixel shift of the tap
   int16_t step_chunk[FL_MAX_STEPS];   // 64-channel chunk
   int8_t step_first[FL_MAX_STEPS];    // first step of its chunk (load a new patch)
@@ -53,16 +58,59 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// K-major SWIZZLE_128B descriptor whose start may sit on any 128-byte row of a 1024-byte swizzle atom
-__device__ __forceinline__ uint64_t make_sw128_desc_row(uint32_t smem_addr, bool with_base_offset) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  if (with_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-  d |= (uint64_t)2 << 61;
-  return d;
+// K-major SWIZZLE_128B shared-memory descriptor = (FL_DESC_HI << 32) | lo, lo = (address >> 4) | LBO field (1 << 16);
+// high word: SBO = 1024 B (8 rows x 128 B), descriptor version 1, SWIZZLE_128B, base_offset 0.  The start address may sit
+// on any 128-byte row of a swizzle atom (see the header comment): shifting by r rows adds 8 * r to lo, by 16 K-elements 2.
+constexpr uint32_t FL_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)FL_DESC_HI << 32) | (uint64_t)lo; }
+
+// The MMA warp's loop, specialised on the tile shape so that all 4 * MT descriptors of a step are immediates off two
+// uniform registers.  A single warp runs this latency-bound scalar code for the whole CTA: every instruction saved here
+// is tensor-pipe time gained (B200: 48 / 64 cycles per M=128 MMA at N = 64 / 128).
+template <int MT, int BN>
+__device__ __forceinline__ void flat_mma_loop(const FlatParams& p, uint8_t* sm_a, uint8_t* sm_w, uint64_t* full_a,
+                                              uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty) {
+  uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, as = 0, acc_phase = 0, a_cur = 0, a_lo0 = 0;
+  const uint32_t w_lo0 = desc_lo(smem_u32(sm_w));
+  const uint32_t a_base_lo = desc_lo(smem_u32(sm_a));
+  const uint32_t a_slot_units = (uint32_t)p.patch_bytes >> 4;
+  constexpr uint32_t W_UNITS = BN * 128 / 16;
+  const int n_steps = p.n_steps;
+  for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+    mbar_wait(&tmem_empty[as], acc_phase ^ 1);      // epilogue drained this accumulator stage (free on the first lap)
+    tc_fence_after();
+    const uint32_t d0 = as * (MT * BN);
+    for (int s = 0; s < n_steps; ++s) {
+      const uint32_t sm = p.step_mma[s];
+      if (sm & (1u << 30)) {
+        a_cur = a_slot;
+        mbar_wait(&full_a[a_cur], a_phase);
+        a_lo0 = a_base_lo + a_cur * a_slot_units;
+        if (++a_slot == (uint32_t)p.NA) { a_slot = 0; a_phase ^= 1; }
+      }
+      mbar_wait(&full_w[w_slot], w_phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo0 + (sm & 0xFFFFu);
+        const uint32_t b_lo = w_lo0 + w_slot * W_UNITS;
+        const uint32_t acc0 = s > 0 ? 1u : 0u;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d0 + mt * BN, desc64(a_lo + mt * 1024 + 2 * k), desc64(b_lo + 2 * k), p.idesc, k > 0 ? 1u : acc0);
+        }
+        umma_commit(&empty_w[w_slot]);
+        if (sm & (1u << 31)) umma_commit(&empty_a[a_cur]);
+        if (s == n_steps - 1) umma_commit(&tmem_full[as]);
+      }
+      __syncwarp();
+      if (++w_slot == (uint32_t)p.NW) { w_slot = 0; w_phase ^= 1; }
+    }
+    if ((as ^= 1) == 0) acc_phase ^= 1;
+  }
 }
 
 __global__ void __launch_bounds__(FL_THREADS, 1)
@@ -97,7 +145,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], FL_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -107,135 +155,137 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int rows_per_super = 128 * p.MT;
+  const int n_boxes = p.patch_rows / FL_BOX_ROWS;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t ia = 0, iw = 0;
+      // ring state kept as (slot, phase) counters: no integer division on this latency-bound single-thread path.
+      // Waiting on parity (phase ^ 1) of a fresh mbarrier returns at once, so the first lap needs no special case.
+      uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0;
       for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
         const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
         const int64_t f0 = (int64_t)mtile * rows_per_super;
         const int n0 = nt * p.BN;
         for (int s = 0; s < p.n_steps; ++s) {
           if (p.step_first[s]) {
-            const uint32_t slot = ia % p.NA;
-            if (ia >= (uint32_t)p.NA) mbar_wait(&empty_a[slot], ((ia / p.NA) - 1) & 1);
-            uint8_t* dst = sm_a + (size_t)slot * p.patch_bytes;
-            mbar_expect_tx(&full_a[slot], (uint32_t)p.patch_bytes);
+            mbar_wait(&empty_a[a_slot], a_phase ^ 1);
+            uint8_t* dst = sm_a + (size_t)a_slot * p.patch_bytes;
+            mbar_expect_tx(&full_a[a_slot], (uint32_t)p.patch_bytes);
             const int c0 = p.step_chunk[s] * 64;
             const int r0 = (int)(f0 + p.min_off);
-            for (int i = 0; i < p.patch_rows / FL_BOX_ROWS; ++i)
-              tma_load_2d(&map_a, &full_a[slot], dst + i * (FL_BOX_ROWS * 128), c0, r0 + i * FL_BOX_ROWS);
-            ++ia;
+            for (int i = 0; i < n_boxes; ++i)
+              tma_load_2d(&map_a, &full_a[a_slot], dst + i * (FL_BOX_ROWS * 128), c0, r0 + i * FL_BOX_ROWS);
+            if (++a_slot == (uint32_t)p.NA) { a_slot = 0; a_phase ^= 1; }
           }
-          const uint32_t slot = iw % p.NW;
-          if (iw >= (uint32_t)p.NW) mbar_wait(&empty_w[slot], ((iw / p.NW) - 1) & 1);
-          mbar_expect_tx(&full_w[slot], (uint32_t)p.w_bytes);
-          tma_load_2d(&map_w, &full_w[slot], sm_w + (size_t)slot * p.w_bytes, p.step_wk[s], n0);
-          ++iw;
+          mbar_wait(&empty_w[w_slot], w_phase ^ 1);
+          mbar_expect_tx(&full_w[w_slot], (uint32_t)p.w_bytes);
+          tma_load_2d(&map_w, &full_w[w_slot], sm_w + (size_t)w_slot * p.w_bytes, p.step_wk[s], n0);
+          if (++w_slot == (uint32_t)p.NW) { w_slot = 0; w_phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      uint32_t ia = 0, iw = 0, it = 0;
-      const bool with_bo = (p.flags & 1) != 0;
-      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++it) {
-        const uint32_t as = it & 1;
-        if (it >= 2) mbar_wait(&tmem_empty[as], ((it >> 1) - 1) & 1);
-        tc_fence_after();
-        uint32_t a_base = 0, a_slot = 0;
-        for (int s = 0; s < p.n_steps; ++s) {
-          if (p.step_first[s]) {
-            a_slot = ia % p.NA;
-            mbar_wait(&full_a[a_slot], (ia / p.NA) & 1);
-            a_base = smem_u32(sm_a + (size_t)a_slot * p.patch_bytes);
-            ++ia;
-          }
-          const uint32_t w_slot = iw % p.NW;
-          mbar_wait(&full_w[w_slot], (iw / p.NW) & 1);
-          ++iw;
-          tc_fence_after();
-          const uint32_t wb = smem_u32(sm_w + (size_t)w_slot * p.w_bytes);
-          const uint32_t row0 = (uint32_t)(p.step_off[s] - p.min_off);
-          for (int mt = 0; mt < p.MT; ++mt) {
-            const uint32_t a_addr = a_base + (row0 + 128u * mt) * 128u;
-            const uint32_t d_tmem = tmem_base + (as * p.MT + mt) * p.BN;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, make_sw128_desc_row(a_addr + k * 32, with_bo), make_sw128_desc_row(wb + k * 32, false),
-                        p.idesc, (s > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_w[w_slot]);
-          if (p.step_last[s]) umma_commit(&empty_a[a_slot]);
-        }
-        umma_commit(&tmem_full[as]);
-      }
-    }
+    // ===================== MMA issuer =====================
+    // The whole warp walks the (warp-uniform) loops so that every descriptor / TMEM address stays in uniform
+    // registers; one elected lane issues the tcgen05.mma / commit instructions.  All 512 TMEM columns are ours, so the
+    // allocation starts at column 0 and accumulator addresses are plain constants.
+    if (tmem_base != 0) __trap();
+    if (p.MT == 4)
+      flat_mma_loop<4, 64>(p, sm_a, sm_w, full_a, empty_a, full_w, empty_w, tmem_full, tmem_empty);
+    else
+      flat_mma_loop<2, 128>(p, sm_a, sm_w, full_a, empty_a, full_w, empty_w, tmem_full, tmem_empty);
   } else {
-    // ===================== epilogue: 4 warps, one TMEM lane quadrant each =====================
+    // ===================== epilogue: 8 warps; TMEM lane quadrant = warp % 4, column-chunk parity = (warp - 2) / 4 =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    uint32_t it = 0;
-    for (int st = blockIdx.x; st < p.n_super; st += gridDim.x, ++it) {
-      const uint32_t as = it & 1;
+    const int chunks_per_acc = p.BN >> 6;            // 32-column chunks handled by this warp per accumulator (1 or 2)
+    const int n_items = p.MT * chunks_per_acc;       // work items per super-tile: (mt, chunk)
+    const uint32_t Hp = (uint32_t)p.Hp, Wp = (uint32_t)p.Wp;
+    uint32_t as = 0, acc_phase = 0;
+    for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
       const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
       const int n0 = nt * p.BN;
-      mbar_wait(&tmem_full[as], (it >> 1) & 1);
+      const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
+      // residual prefetch for item 0 (independent of the accumulator): hides the HBM latency behind the barrier wait
+      uint4 rq[4];
+      auto item_geom = [&](int j, uint32_t& f, int& nbase, bool& ok) {
+        const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
+        f = fbase + 128u * (uint32_t)mt;
+        const uint32_t col = f / Hp, h = f - col * Hp, w = col % Wp;
+        nbase = n0 + 32 * (2 * cj + half);
+        ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W && nbase < p.Cout;
+      };
+      auto load_res = [&](uint32_t f, int nbase, bool ok) {
+        if (residual != nullptr && ok) {
+          const uint4* rp = reinterpret_cast<const uint4*>(residual + (int64_t)f * p.ld_res + nbase);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) rq[j4] = __ldg(rp + j4);
+        }
+      };
+      uint32_t f_cur;
+      int nb_cur;
+      bool ok_cur;
+      item_geom(0, f_cur, nb_cur, ok_cur);
+      load_res(f_cur, nb_cur, ok_cur);
+      mbar_wait(&tmem_full[as], acc_phase);
       tc_fence_after();
-      for (int mt = 0; mt < p.MT; ++mt) {
-        const int64_t f = (int64_t)mtile * rows_per_super + 128 * mt + r;
-        const int h = (int)(f % p.Hp);
-        const int w = (int)((f / p.Hp) % p.Wp);
-        const bool row_ok = f < p.F && h < p.H && w < p.W;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
-          tmem_ld_wait();
-          const int nbase = n0 + c0;
-          if (row_ok && nbase < p.Cout) {
-            float x[32];
-            const float4* bp = reinterpret_cast<const float4*>(s_bias + nbase);
+      for (int j = 0; j < n_items; ++j) {
+        const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
+        const int c0 = 32 * (2 * cj + half);
+        uint32_t v[32];
+        tmem_ld32(((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
+        tmem_ld_wait();
+        float x[32];
+        if (ok_cur) {
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + nb_cur);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b4 = bp[j4];
-              x[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
-              x[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
-              x[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
-              x[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
-            }
-            if (residual != nullptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(residual + f * p.ld_res + nbase);
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint4 u = __ldg(rp + j4);
-                const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  x[j4 * 8 + e * 2 + 0] += __uint_as_float(ww[e] << 16);
-                  x[j4 * 8 + e * 2 + 1] += __uint_as_float(ww[e] & 0xffff0000u);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act);
-            uint4* op = reinterpret_cast<uint4*>(out + f * p.ld_out + p.co_off + nbase);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = bp[j4];
+            x[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
+            x[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+            x[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
+            x[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+          }
+          if (residual != nullptr) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              uint32_t ww[4];
+              const uint32_t ww[4] = {rq[j4].x, rq[j4].y, rq[j4].z, rq[j4].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
-                ww[e] = *reinterpret_cast<uint32_t*>(&h2);
+                x[j4 * 8 + e * 2 + 0] += __uint_as_float(ww[e] << 16);
+                x[j4 * 8 + e * 2 + 1] += __uint_as_float(ww[e] & 0xffff0000u);
               }
-              op[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
             }
+          }
+        }
+        const uint32_t f_st = f_cur;
+        const int nb_st = nb_cur;
+        const bool ok_st = ok_cur;
+        if (j + 1 < n_items) {       // prefetch the next item's residual before the stores of this one
+          item_geom(j + 1, f_cur, nb_cur, ok_cur);
+          load_res(f_cur, nb_cur, ok_cur);
+        }
+        if (ok_st) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) x[jj] = apply_act(x[jj], p.act);
+          uint4* op = reinterpret_cast<uint4*>(out + (int64_t)f_st * p.ld_out + p.co_off + nb_st);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint32_t ww[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+              ww[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            op[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
+      if ((as ^= 1) == 0) acc_phase ^= 1;
     }
   }
   tc_fence_before();
@@ -261,6 +311,7 @@ extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void*
                              const float* bias, const void* residual, void* out, int32_t flags, yad_stream_t stream) {
   using namespace yad;
   YAD_CHECK_ARG(d && in && weight && bias && out, "yad_conv_flat: null pointer");
+  YAD_CHECK_ARG(flags == 0, "yad_conv_flat: flags must be 0");
   YAD_CHECK_ARG(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->Hp >= d->H && d->Wp >= d->W, "yad_conv_flat: bad geometry");
   YAD_CHECK_ARG(d->Cin % 64 == 0 && d->Cin >= 64, "yad_conv_flat: Cin=%d must be a multiple of 64", d->Cin);
   YAD_CHECK_ARG(d->ld_in % 8 == 0 && d->ld_in >= d->Cin, "yad_conv_flat: bad ld_in=%d", d->ld_in);
@@ -316,6 +367,9 @@ extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void*
       p.step_wk[ns] = taps_idx[t] * d->Cin + c * 64;
     }
   }
+  for (int i = 0; i < ns; ++i)
+    p.step_mma[i] = (uint32_t)((p.step_off[i] - min_off) * 8) | (p.step_first[i] ? 1u << 30 : 0u) | (p.step_last[i] ? 1u << 31 : 0u);
+  YAD_CHECK_ARG((max_off - min_off) * 8 < 65536, "yad_conv_flat: filter reach too large");
   p.n_steps = ns;
   p.min_off = min_off;
   p.BN = cout_pad % 128 == 0 ? 128 : 64;

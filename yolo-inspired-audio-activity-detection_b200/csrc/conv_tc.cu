@@ -114,29 +114,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.tb * p.th * p.tw * 128 + b_stage_bytes);
-      int it = 0;
+      uint32_t s = 0, phase = 0;     // ring (slot, phase): no integer division on the single-thread path
       for (int tap = 0; tap < p.n_taps; ++tap) {
         const int mi = p.tap_map[tap];
         const CUtensorMap* ma = mi == 0 ? &map_a0 : (mi == 1 ? &map_a1 : (mi == 2 ? &map_a2 : &map_a3));
         const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap];
         const int kbase = p.tap_widx[tap] * p.cin;
-        for (int cc = 0; cc < p.cin_chunks; ++cc, ++it) {
-          const int s = it % S;
-          if (it >= S) mbar_wait(&empty_bar[s], ((it / S) - 1) & 1);
+        for (int cc = 0; cc < p.cin_chunks; ++cc) {
+          mbar_wait(&empty_bar[s], phase ^ 1);      // free on the first lap
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + TC_A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], tx_bytes);
           tma_load_4d(ma, &full_bar[s], sa, cc * TC_BK, cw, ch, b0);
           tma_load_2d(&map_w, &full_bar[s], sb, kbase + cc * TC_BK, n0);
+          if (++s == (uint32_t)S) { s = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
+      uint32_t s = 0, phase = 0;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % S;
-        mbar_wait(&full_bar[s], (it / S) & 1);
+        mbar_wait(&full_bar[s], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sb = sa + TC_A_STAGE_BYTES;
@@ -148,6 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
         umma_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
         if (it == n_iters - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        if (++s == (uint32_t)S) { s = 0; phase ^= 1; }
       }
     }
   } else {
