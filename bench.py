@@ -146,7 +146,7 @@ def time_stages(model, x, reps=3):
     def stem():
         c1 = plan["c1"]
         if eng.dtype == _lib.BF16:
-            _lib.check(eng.lib.yad_conv_stem_tc(xs.data_ptr(), B, 32, T, eng.stem_w_tc.data_ptr(), c1.data_ptr(), eng.stem_flags,
+            _lib.check(eng.lib.yad_conv_stem_tc(xs.data_ptr(), B, 32, T, eng.stem_w_tc.data_ptr(), c1.data_ptr(), c1.shape[2], c1.shape[1],
                                                 eng._stream()), "stem_tc")
         else:
             _lib.check(eng.lib.yad_conv_stem(xs.data_ptr(), B, 32, T, eng.stem_w.data_ptr(), c1.data_ptr(), eng.dtype, eng._stream()), "stem")

@@ -108,12 +108,17 @@ typedef struct {
 int yad_conv_stem(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* weight,
                   void* out, int32_t out_dtype, yad_stream_t stream);
 
-/* The same stem on the tcgen05 tensor cores (bf16 operands, fp32 accumulate, bf16 NHWC output).  The CTA builds the
- * im2col A tile itself (C = 2 defeats TMA) in the no-swizzle K-major UMMA layout.
+/* The same stem on the tcgen05 tensor cores (bf16 operands, fp32 accumulate, bf16 output).  The CTA keeps the raw
+ * channel-interleaved input patch in shared memory and the UMMA descriptor reads overlapping 32-byte windows of it
+ * (no-swizzle K-major layout with LBO = 16 B): no im2col copy.
  * weight_packed: bf16 [64][112] (K index = kh*16 + kw*2 + c, zero for kw = 7) stored as 8x8 core matrices:
- * element (n, k) at byte (n/8)*1792 + (k/8)*128 + (n%8)*16 + (k%8)*2.  flags: bit 0 = debug (swap LBO/SBO). */
+ * element (n, k) at byte (n/8)*1792 + (k/8)*128 + (n%8)*16 + (k%8)*2.
+ * Output: s2d_hp = s2d_wp = 0 -> dense NHWC [B, Ho, Wo, 64].  Otherwise the space-to-depth FLAT layout that lets the next
+ * 7x7 stride-2 conv run as a stride-1 conv (yad_conv_flat_taps): pixel (b, ho, wo) goes to flat index
+ * (b*s2d_wp + wo/2)*s2d_hp + ho/2 of a 256-channel tensor, channel block ((ho%2)*2 + wo%2)*64; the caller zero-fills
+ * the buffer once (halo cells are never written). */
 int yad_conv_stem_tc(const float* x_nchw, int64_t B, int32_t H, int32_t W, const void* weight_packed,
-                     void* out_bf16, int32_t flags, yad_stream_t stream);
+                     void* out_bf16, int32_t s2d_hp, int32_t s2d_wp, yad_stream_t stream);
 
 /* CUDA-core implicit GEMM (fp32 accumulate; in/out dtype f32 or bf16).
  * weight [kh][kw][Cin][Cout_pad] in `dtype`; bias [Cout] f32; residual/out NHWC. */
@@ -146,9 +151,19 @@ typedef struct {
   int32_t kh, kw, ph, pw;     /* 'same' convolution: kh = 2*ph + 1, kw = 2*pw + 1 */
   int32_t act;                /* YAD_ACT_* */
   int32_t ld_res;             /* residual channel pitch (0 = no residual) */
+  int32_t Hp_out, Wp_out;     /* pitches of out / residual (0, 0 = same as the input) */
 } yad_flat_desc;
 int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
                   const void* residual, void* out, int32_t flags, yad_stream_t stream);
+/* The same kernel with an explicit step list (kh/kw/ph/pw of d are ignored): step i reads the input channels
+ * [64*chunk[i], 64*chunk[i]+64) at the flat shift dw[i]*Hp + dh[i] and multiplies them with the [cout_pad x 64] block
+ * at K offset wk[i] of weight [cout_pad][k_total].  Steps must be grouped by ascending chunk; at most 64 steps.
+ * This is how the stem's 7x7 stride-2 conv2 (modules/_backbone.py:144) runs as a stride-1 conv: its input is the
+ * space-to-depth output of yad_conv_stem_tc (4 parity planes x 64 channels), tap (kh, kw) = plane ((kh-3)&1, (kw-3)&1)
+ * shifted by (floor((kh-3)/2), floor((kw-3)/2)). */
+int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* chunk, const int32_t* dh, const int32_t* dw,
+                       const int32_t* wk, int64_t k_total, const void* in, const void* weight, int32_t cout_pad,
+                       const float* bias, const void* residual, void* out, yad_stream_t stream);
 
 /* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
  * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5

@@ -184,8 +184,7 @@ def test_stem_conv_tensor_core(shape, cuda_dev):
     wp = wk.reshape(8, 8, 14, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16).to(cuda_dev)
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.full((B, Ho, Wo, 64), 7.0, dtype=torch.bfloat16, device=cuda_dev)
-    flags = int(__import__("os").environ.get("YAD_STEM_FLAGS", "0"))
-    _lib.check(lib.yad_conv_stem_tc(x.to(cuda_dev).data_ptr(), B, H, W, wp.data_ptr(), out.data_ptr(), flags, _stream()), "stem_tc")
+    _lib.check(lib.yad_conv_stem_tc(x.to(cuda_dev).data_ptr(), B, H, W, wp.data_ptr(), out.data_ptr(), 0, 0, _stream()), "stem_tc")
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy(), atol=2e-2, rtol=1e-2)
 

@@ -29,7 +29,8 @@ class ConvDesc(C.Structure):
 
 class FlatDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
-        "B", "H", "W", "Hp", "Wp", "Cin", "ld_in", "Cout", "ld_out", "co_off", "kh", "kw", "ph", "pw", "act", "ld_res")]
+        "B", "H", "W", "Hp", "Wp", "Cin", "ld_in", "Cout", "ld_out", "co_off", "kh", "kw", "ph", "pw", "act", "ld_res",
+        "Hp_out", "Wp_out")]
 
 
 _p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -40,10 +41,12 @@ SIGNATURES = {
     "yad_frontend_mel_power": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
     "yad_frontend_finish": [_p, _i64, _i64, _p, _f32, _i32, _p, _p, _p, _p, _p],
     "yad_conv_stem": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],
-    "yad_conv_stem_tc": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],
+    "yad_conv_stem_tc": [_p, _i64, _i32, _i32, _p, _p, _i32, _i32, _p],
     "yad_conv_simt": [C.POINTER(ConvDesc), _i32, _p, _p, _i32, _p, _p, _p, _p],
     "yad_conv_tc": [C.POINTER(ConvDesc), _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p],
     "yad_conv_flat": [C.POINTER(FlatDesc), _p, _p, _i32, _p, _p, _p, _i32, _p],
+    "yad_conv_flat_taps": [C.POINTER(FlatDesc), _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i64, _p, _p,
+                           _i32, _p, _p, _p, _p],
     "yad_hmean": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_resize_w": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_sppf_pools": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],

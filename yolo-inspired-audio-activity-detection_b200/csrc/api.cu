@@ -24,6 +24,7 @@ int sm_count() { return g_sm_count; }
 int init_conv_tc_attrs();   // conv_tc.cu
 int init_conv_flat_attrs(); // conv_flat.cu
 int init_frontend_attrs();  // frontend.cu
+int init_conv_stem_tc_attrs();  // conv_stem_tc.cu
 
 }  // namespace yad
 
@@ -59,6 +60,8 @@ int yad_init(int device) {
   int rc = yad::init_conv_tc_attrs();
   if (rc) return rc;
   rc = yad::init_conv_flat_attrs();
+  if (rc) return rc;
+  rc = yad::init_conv_stem_tc_attrs();
   if (rc) return rc;
   rc = yad::init_frontend_attrs();
   if (rc) return rc;

@@ -37,6 +37,8 @@ constexpr int FL_BOX_ROWS = 64;    // pixel rows per TMA box of the patch (8 KB)
 struct FlatParams {
   int64_t F;                    // flat pixels = B * Wp * Hp
   int32_t H, W, Hp, Wp;
+  int32_t Hpo, Wpo;             // output / residual pitches (same image size)
+  int32_t remap;                // 1 when (Hpo, Wpo) != (Hp, Wp)
   int32_t MT, BN, n_ntiles, n_super;   // n_super = M super-tiles * n_ntiles
   int32_t n_steps;
   int32_t NA, NW;               // ring depths
@@ -210,12 +212,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
       // residual prefetch for item 0 (independent of the accumulator): hides the HBM latency behind the barrier wait
       uint4 rq[4];
+      // item j -> (output flat index, first channel, valid); the output may use other pitches than the input
       auto item_geom = [&](int j, uint32_t& f, int& nbase, bool& ok) {
         const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
         f = fbase + 128u * (uint32_t)mt;
-        const uint32_t col = f / Hp, h = f - col * Hp, w = col % Wp;
+        const uint32_t col = f / Hp, h = f - col * Hp, bb = col / Wp, w = col - bb * Wp;
         nbase = n0 + 32 * (2 * cj + half);
         ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W && nbase < p.Cout;
+        if (p.remap) f = (bb * (uint32_t)p.Wpo + w) * (uint32_t)p.Hpo + h;
       };
       auto load_res = [&](uint32_t f, int nbase, bool ok) {
         if (residual != nullptr && ok) {
@@ -307,11 +311,64 @@ int init_conv_flat_attrs() {
 
 }  // namespace yad
 
-extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad,
-                             const float* bias, const void* residual, void* out, int32_t flags, yad_stream_t stream) {
-  using namespace yad;
+namespace yad {
+
+// common launcher: the caller has filled the geometry / epilogue fields and the step lists (grouped by chunk)
+static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const void* in, int cin_total, int ld_in,
+                       const void* weight, int64_t k_total, int cout_pad, const float* bias, const void* residual, void* out,
+                       yad_stream_t stream) {
+  for (int i = 0; i < p.n_steps; ++i)
+    p.step_mma[i] = (uint32_t)((p.step_off[i] - p.min_off) * 8) | (p.step_first[i] ? 1u << 30 : 0u) | (p.step_last[i] ? 1u << 31 : 0u);
+  YAD_CHECK_ARG((max_off - p.min_off) * 8 < 65536, "yad_conv_flat: filter reach too large");
+  p.BN = cout_pad % 128 == 0 ? 128 : 64;
+  p.n_ntiles = cout_pad / p.BN;
+  p.MT = 256 / p.BN;                      // 2 accumulator stages x MT x BN = 512 TMEM columns
+  const int rows_per_super = 128 * p.MT;
+  const int patch_rows_raw = rows_per_super + max_off - p.min_off;
+  p.patch_rows = (patch_rows_raw + FL_BOX_ROWS - 1) / FL_BOX_ROWS * FL_BOX_ROWS;
+  p.patch_bytes = p.patch_rows * 128;
+  p.w_bytes = p.BN * 128;
+  const int64_t n_mtiles = (p.F + rows_per_super - 1) / rows_per_super;
+  p.n_super = (int)(n_mtiles * p.n_ntiles);
+  p.flags = 0;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // shared-memory budget: barriers + bias + alignment slack, then the two rings
+  const size_t fixed = 1024 + (4 * FL_MAX_RING + 4) * 8 + 16 + (size_t)cout_pad * 4 + 64;
+  const size_t budget = 227 * 1024 - fixed;
+  p.NA = n_chunks_distinct > 1 ? 3 : 2;
+  while (p.NA > 1 && (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes > budget) --p.NA;
+  YAD_CHECK_ARG((size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes <= budget, "yad_conv_flat: patch of %d rows does not fit", p.patch_rows);
+  p.NW = (int)((budget - (size_t)p.NA * p.patch_bytes) / p.w_bytes);
+  if (p.NW > FL_MAX_RING) p.NW = FL_MAX_RING;
+  const size_t smem = fixed + (size_t)p.NA * p.patch_bytes + (size_t)p.NW * p.w_bytes;
+
+  CUtensorMap map_a, map_w;
+  {
+    const uint64_t dims[2] = {(uint64_t)cin_total, (uint64_t)p.F};
+    const uint64_t strides[1] = {(uint64_t)ld_in * 2};
+    const uint32_t box[2] = {64u, (uint32_t)FL_BOX_ROWS};
+    int rc = encode_map_bf16(&map_a, in, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)cout_pad};
+    const uint64_t strides[1] = {(uint64_t)k_total * 2};
+    const uint32_t box[2] = {64u, (uint32_t)p.BN};
+    int rc = encode_map_bf16(&map_w, weight, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const int nsm = sm_count() > 0 ? sm_count() : 148;
+  const int grid = p.n_super < nsm ? p.n_super : nsm;
+  conv_flat_kernel<<<grid, FL_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p, bias,
+                                                                   reinterpret_cast<const __nv_bfloat16*>(residual),
+                                                                   reinterpret_cast<__nv_bfloat16*>(out));
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+static int check_flat_common(const yad_flat_desc* d, const void* in, const void* weight, int cout_pad, const float* bias,
+                             const void* residual, const void* out, FlatParams& p) {
   YAD_CHECK_ARG(d && in && weight && bias && out, "yad_conv_flat: null pointer");
-  YAD_CHECK_ARG(flags == 0, "yad_conv_flat: flags must be 0");
   YAD_CHECK_ARG(d->B >= 1 && d->H >= 1 && d->W >= 1 && d->Hp >= d->H && d->Wp >= d->W, "yad_conv_flat: bad geometry");
   YAD_CHECK_ARG(d->Cin % 64 == 0 && d->Cin >= 64, "yad_conv_flat: Cin=%d must be a multiple of 64", d->Cin);
   YAD_CHECK_ARG(d->ld_in % 8 == 0 && d->ld_in >= d->Cin, "yad_conv_flat: bad ld_in=%d", d->ld_in);
@@ -319,21 +376,41 @@ extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void*
                 "yad_conv_flat: Cout=%d must be a multiple of 32 and cout_pad=%d a multiple of 64", d->Cout, cout_pad);
   YAD_CHECK_ARG(d->ld_out % 8 == 0 && d->co_off % 8 == 0 && d->ld_out >= d->co_off + d->Cout, "yad_conv_flat: bad ld_out/co_off");
   YAD_CHECK_ARG(residual == nullptr || (d->ld_res % 8 == 0 && d->ld_res >= d->Cout), "yad_conv_flat: bad ld_res");
-  YAD_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 49 && d->ph >= 0 && d->pw >= 0 && d->ph < d->kh && d->pw < d->kw,
-                "yad_conv_flat: bad kernel/padding");
-  YAD_CHECK_ARG(d->kh - 1 - d->ph == d->ph && d->kw - 1 - d->pw == d->pw, "yad_conv_flat: only 'same' (output size = input size) convs");
   YAD_CHECK_ARG((reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(weight) % 16 == 0) &&
                     (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (reinterpret_cast<uintptr_t>(residual) % 16 == 0),
                 "yad_conv_flat: pointers must be 16-byte aligned");
-
-  FlatParams p;
+  const int Hpo = d->Hp_out > 0 ? d->Hp_out : d->Hp, Wpo = d->Wp_out > 0 ? d->Wp_out : d->Wp;
+  YAD_CHECK_ARG(Hpo >= d->H && Wpo >= d->W, "yad_conv_flat: output pitches smaller than the image");
   memset(&p, 0, sizeof(p));
   p.H = d->H;
   p.W = d->W;
   p.Hp = d->Hp;
   p.Wp = d->Wp;
+  p.Hpo = Hpo;
+  p.Wpo = Wpo;
+  p.remap = (Hpo != d->Hp || Wpo != d->Wp) ? 1 : 0;
   p.F = (int64_t)d->B * d->Wp * d->Hp;
-  YAD_CHECK_ARG(p.F < (int64_t)1 << 31, "yad_conv_flat: tensor too large (%lld pixels)", (long long)p.F);
+  YAD_CHECK_ARG(p.F < (int64_t)1 << 31 && (int64_t)d->B * Wpo * Hpo < (int64_t)1 << 31, "yad_conv_flat: tensor too large");
+  p.Cout = d->Cout;
+  p.ld_out = d->ld_out;
+  p.co_off = d->co_off;
+  p.ld_res = d->ld_res;
+  p.act = d->act;
+  return YAD_OK;
+}
+
+}  // namespace yad
+
+extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad,
+                             const float* bias, const void* residual, void* out, int32_t flags, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(flags == 0, "yad_conv_flat: flags must be 0");
+  FlatParams p;
+  int rc = check_flat_common(d, in, weight, cout_pad, bias, residual, out, p);
+  if (rc) return rc;
+  YAD_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 49 && d->ph >= 0 && d->pw >= 0 && d->ph < d->kh && d->pw < d->kw,
+                "yad_conv_flat: bad kernel/padding");
+  YAD_CHECK_ARG(d->kh - 1 - d->ph == d->ph && d->kw - 1 - d->pw == d->pw, "yad_conv_flat: only 'same' (output size = input size) convs");
   // taps: skip those that only ever see padding; the rest must be covered by the halo
   int taps_dh[49], taps_dw[49], taps_idx[49], n_taps = 0, reach_h = 0, reach_w = 0;
   for (int kh = 0; kh < d->kh; ++kh) {
@@ -367,58 +444,40 @@ extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void*
       p.step_wk[ns] = taps_idx[t] * d->Cin + c * 64;
     }
   }
-  for (int i = 0; i < ns; ++i)
-    p.step_mma[i] = (uint32_t)((p.step_off[i] - min_off) * 8) | (p.step_first[i] ? 1u << 30 : 0u) | (p.step_last[i] ? 1u << 31 : 0u);
-  YAD_CHECK_ARG((max_off - min_off) * 8 < 65536, "yad_conv_flat: filter reach too large");
   p.n_steps = ns;
   p.min_off = min_off;
-  p.BN = cout_pad % 128 == 0 ? 128 : 64;
-  p.n_ntiles = cout_pad / p.BN;
-  p.MT = 256 / p.BN;                      // 2 accumulator stages x MT x BN = 512 TMEM columns
-  const int rows_per_super = 128 * p.MT;
-  const int patch_rows_raw = rows_per_super + max_off - min_off;
-  p.patch_rows = (patch_rows_raw + FL_BOX_ROWS - 1) / FL_BOX_ROWS * FL_BOX_ROWS;
-  p.patch_bytes = p.patch_rows * 128;
-  p.w_bytes = p.BN * 128;
-  const int64_t n_mtiles = (p.F + rows_per_super - 1) / rows_per_super;
-  p.n_super = (int)(n_mtiles * p.n_ntiles);
-  p.Cout = d->Cout;
-  p.ld_out = d->ld_out;
-  p.co_off = d->co_off;
-  p.ld_res = d->ld_res;
-  p.act = d->act;
-  p.flags = flags;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  // shared-memory budget: barriers + bias + alignment slack, then the two rings
-  const size_t fixed = 1024 + (4 * FL_MAX_RING + 4) * 8 + 16 + (size_t)cout_pad * 4 + 64;
-  const size_t budget = 227 * 1024 - fixed;
-  p.NA = n_chunks > 1 ? 3 : 2;
-  while (p.NA > 1 && (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes > budget) --p.NA;
-  YAD_CHECK_ARG((size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes <= budget, "yad_conv_flat: patch of %d rows does not fit", p.patch_rows);
-  p.NW = (int)((budget - (size_t)p.NA * p.patch_bytes) / p.w_bytes);
-  if (p.NW > FL_MAX_RING) p.NW = FL_MAX_RING;
-  const size_t smem = fixed + (size_t)p.NA * p.patch_bytes + (size_t)p.NW * p.w_bytes;
+  return launch_flat(p, n_chunks, max_off, in, d->Cin, d->ld_in, weight, (int64_t)d->kh * d->kw * d->Cin, cout_pad, bias, residual,
+                     out, stream);
+}
 
-  CUtensorMap map_a, map_w;
-  {
-    const uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)p.F};
-    const uint64_t strides[1] = {(uint64_t)d->ld_in * 2};
-    const uint32_t box[2] = {64u, (uint32_t)FL_BOX_ROWS};
-    int rc = encode_map_bf16(&map_a, in, 2, dims, strides, box);
-    if (rc) return rc;
+extern "C" int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* chunk, const int32_t* dh,
+                                  const int32_t* dw, const int32_t* wk, int64_t k_total, const void* in, const void* weight,
+                                  int32_t cout_pad, const float* bias, const void* residual, void* out, yad_stream_t stream) {
+  using namespace yad;
+  FlatParams p;
+  int rc = check_flat_common(d, in, weight, cout_pad, bias, residual, out, p);
+  if (rc) return rc;
+  YAD_CHECK_ARG(chunk && dh && dw && wk && n_steps >= 1 && n_steps <= FL_MAX_STEPS, "yad_conv_flat_taps: bad step list (1..%d steps)",
+                FL_MAX_STEPS);
+  int min_off = 0, max_off = 0, n_distinct = 0;
+  for (int i = 0; i < n_steps; ++i) {
+    YAD_CHECK_ARG(chunk[i] >= 0 && chunk[i] * 64 + 64 <= d->Cin, "yad_conv_flat_taps: step %d reads chunk %d outside Cin=%d", i, chunk[i], d->Cin);
+    YAD_CHECK_ARG(i == 0 || chunk[i] >= chunk[i - 1], "yad_conv_flat_taps: steps must be grouped by ascending chunk");
+    YAD_CHECK_ARG(wk[i] >= 0 && wk[i] % 8 == 0 && (int64_t)wk[i] + 64 <= k_total, "yad_conv_flat_taps: bad weight offset in step %d", i);
+    const int adh = dh[i] < 0 ? -dh[i] : dh[i], adw = dw[i] < 0 ? -dw[i] : dw[i];
+    YAD_CHECK_ARG(adh <= d->Hp - d->H && adw <= d->Wp - d->W, "yad_conv_flat_taps: step %d reaches (%d,%d) beyond the halo (%d,%d)", i,
+                  dh[i], dw[i], d->Hp - d->H, d->Wp - d->W);
+    const int off = dw[i] * d->Hp + dh[i];
+    min_off = off < min_off ? off : min_off;
+    max_off = off > max_off ? off : max_off;
+    p.step_off[i] = (int16_t)off;
+    p.step_chunk[i] = (int16_t)chunk[i];
+    p.step_first[i] = (i == 0 || chunk[i] != chunk[i - 1]);
+    p.step_last[i] = (i == n_steps - 1 || chunk[i + 1] != chunk[i]);
+    p.step_wk[i] = wk[i];
+    if (p.step_first[i]) ++n_distinct;
   }
-  {
-    const uint64_t dims[2] = {(uint64_t)d->kh * d->kw * d->Cin, (uint64_t)cout_pad};
-    const uint64_t strides[1] = {(uint64_t)d->kh * d->kw * d->Cin * 2};
-    const uint32_t box[2] = {64u, (uint32_t)p.BN};
-    int rc = encode_map_bf16(&map_w, weight, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  const int nsm = sm_count() > 0 ? sm_count() : 148;
-  const int grid = p.n_super < nsm ? p.n_super : nsm;
-  conv_flat_kernel<<<grid, FL_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p, bias,
-                                                                   reinterpret_cast<const __nv_bfloat16*>(residual),
-                                                                   reinterpret_cast<__nv_bfloat16*>(out));
-  YAD_LAUNCH_CHECK();
-  return YAD_OK;
+  p.n_steps = n_steps;
+  p.min_off = min_off;
+  return launch_flat(p, n_distinct, max_off, in, d->Cin, d->ld_in, weight, k_total, cout_pad, bias, residual, out, stream);
 }

@@ -85,7 +85,6 @@ class InferenceEngine:
         self.E = 3 + self.nc
         self.n_head = self.A * self.E
         self._tls = threading.local()
-        self.stem_flags = int(__import__('os').environ.get('YAD_STEM_FLAGS', '0'))
         with torch.no_grad():
             self._pack_frontend(model)
             self._pack_cnn(model)
@@ -141,6 +140,17 @@ class InferenceEngine:
             self.stem_w_tc = wk.reshape(8, 8, 14, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
         w2, b2 = _fold_bn(fe.conv2.weight, None, fe.bn1)
         self.conv2 = _Conv("fe.conv2", w2, b2, 2, 3, ACT_RELU, dev, self.dtype)
+        if self.dtype == BF16:
+            # conv2 over the space-to-depth stem output: tap (kh, kw) reads parity plane ((kh-3)&1, (kw-3)&1) shifted by
+            # (floor((kh-3)/2), floor((kw-3)/2)); steps grouped by plane
+            steps = []
+            for kh in range(7):
+                for kw in range(7):
+                    a, b_ = (kh - 3) // 2, (kw - 3) // 2
+                    steps.append((((kh - 3) - 2 * a) * 2 + ((kw - 3) - 2 * b_), a, b_, (kh * 7 + kw) * 64))
+            steps.sort(key=lambda t: t[0])
+            arr = lambda i: (C.c_int32 * len(steps))(*[t[i] for t in steps])   # noqa: E731
+            self.conv2_steps = (arr(0), arr(1), arr(2), arr(3))
         self.stages = []
         for li in range(1, 5):
             blocks = []
@@ -324,23 +334,28 @@ class InferenceEngine:
         B, _, H0, T = xs.shape
         bf = self.dtype == BF16
         s = self._stream
-        c1 = self._buf(plan, "c1", B, (H0 - 1) // 2 + 1, (T - 1) // 2 + 1, 64)
-        if bf:
-            _lib.check(self.lib.yad_conv_stem_tc(xs.data_ptr(), B, H0, T, self.stem_w_tc.data_ptr(), c1.data_ptr(), self.stem_flags, s()),
-                       "conv_stem_tc")
-        else:
-            _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
-        H, W = (c1.shape[1] + 6 - 7) // 2 + 1, (c1.shape[2] + 6 - 7) // 2 + 1
+        H1, W1 = (H0 - 1) // 2 + 1, (T - 1) // 2 + 1          # conv1 output
+        H, W = (H1 + 6 - 7) // 2 + 1, (W1 + 6 - 7) // 2 + 1     # conv2 output
         fmaps, geoms = [], []
         if bf:
-            # backbone activations live in the flat halo-padded layout [B, Wp, Hp, ld] (conv_flat.cu)
+            # conv1 writes the space-to-depth flat layout [B, W2+2, H2+2, 4 parity planes x 64]; conv2 (7x7 stride 2) then is a
+            # stride-1 flat conv with 49 (plane, shift) steps; backbone activations stay in the flat layout (conv_flat.cu)
+            H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
+            assert (H2, W2) == (H, W)
+            c1 = plan.get("c1")
+            if c1 is None:
+                c1 = plan["c1"] = torch.zeros((B, W2 + 2, H2 + 2, 256), device=self.dev, dtype=torch.bfloat16)
+            _lib.check(self.lib.yad_conv_stem_tc(xs.data_ptr(), B, H0, T, self.stem_w_tc.data_ptr(), c1.data_ptr(), H2 + 2, W2 + 2, s()),
+                       "conv_stem_tc")
             cur = self._flat_buf(plan, "c2", B, H, W, 64)
             Hp, Wp = self._flat_geom(H, W)
             cv = self.conv2
-            d = ConvDesc(B=B, H=c1.shape[1], W=c1.shape[2], Cin=cv.cin_pad, ld_in=64, Cout=cv.cout, ld_out=64, co_off=0, kh=cv.kh,
-                         kw=cv.kw, sh=cv.sh, sw=cv.sw, ph=cv.ph, pw=cv.pw, act=cv.act, ld_res=0, out_sw=Hp, out_sh=1, out_sb=Wp * Hp)
-            _lib.check(self.lib.yad_conv_tc(C.byref(d), c1.data_ptr(), cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), 0,
-                                            cur.data_ptr(), BF16, 0, 0, s()), "conv fe.conv2")
+            d = FlatDesc(B=B, H=H2, W=W2, Hp=H2 + 2, Wp=W2 + 2, Cin=256, ld_in=256, Cout=cv.cout, ld_out=64, co_off=0, kh=1, kw=1,
+                         ph=0, pw=0, act=cv.act, ld_res=0, Hp_out=Hp, Wp_out=Wp)
+            ch, dh, dw, wk = self.conv2_steps
+            _lib.check(self.lib.yad_conv_flat_taps(C.byref(d), len(ch), ch, dh, dw, wk, cv.kh * cv.kw * cv.cin_pad, c1.data_ptr(),
+                                                   cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), 0, cur.data_ptr(), s()),
+                       "conv fe.conv2 (flat, space-to-depth)")
             for li, blocks in enumerate(self.stages):
                 for bi, blk in enumerate(blocks):
                     c1v, c2v = blk["c1"], blk["c2"]
@@ -364,6 +379,8 @@ class InferenceEngine:
             if taps is not None:
                 taps["fmaps"] = [f[:, :w_, :h_, :].float().permute(0, 3, 2, 1).contiguous() for f, (h_, w_) in zip(fmaps, geoms)]
         else:
+            c1 = self._buf(plan, "c1", B, H1, W1, 64)
+            _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
             cur = self._buf(plan, "c2", B, H, W, 64)
             self._conv(self.conv2, c1, 0, cur, 0)
             for li, blocks in enumerate(self.stages):
