@@ -227,6 +227,21 @@ int yad_build_targets(const float* targets, int32_t T, const float* anchors, int
                       float anchor_t, float duration, float edge_t, int64_t* batch_idx, int64_t* grid_idx,
                       int64_t* anchor_idx, int64_t* classes, float* cw, int32_t* n_out, yad_stream_t stream);
 
+/* Detection loss of ONE scale: modules/_loss.py:115-228 (AudioDetectionLoss.loss_fn + compute_ciou) for the default
+ * train_config (multi_label BCE class loss with label smoothing, BCEWithLogits objectness, no focal loss).
+ *   pred [B, G, A, 3+nc] f32 (decoded predictions: obj, cls.., centre_s, width_s); matches (bi, gi, ai, cl i64, cw [M,2] f32)
+ *   as produced by yad_build_targets, M known to the host.
+ * Outputs: grad [B, G, A, 3+nc] f32 (overwritten) = d(box_w * box + conf_scale * conf + class_w * cls) / d pred, where
+ * conf_scale = conf_w * the scale's weight (4 / 2 / 1); acc [8] f64 sums: {sum(1-ciou), sum ciou, sum BCE objectness over all
+ * cells, sum BCE class, sum sigmoid(obj) over matches, sum sigmoid(obj) over cells with t_conf == 0, count of those cells,
+ * count of matches whose class != ignore_index}; confusion [nc][nc] i32 (target class x argmax class) for the
+ * accuracy / precision / recall / f1 metrics.  Duplicate (b,g,a) matches: the last one owns t_conf (index_put_ order, Q12),
+ * all of them receive box / class gradients.  Workspaces: owner_ws [B*G*A] i32, ciou_ws [M] f32. */
+int yad_loss_scale(const float* pred, int64_t B, int32_t G, int32_t A, int32_t nc, const int64_t* bi, const int64_t* gi,
+                   const int64_t* ai, const int64_t* cl, const float* cw, int32_t M, float box_w, float conf_scale,
+                   float class_w, float label_smoothing, int64_t ignore_index, int32_t* owner_ws, float* ciou_ws,
+                   int32_t* confusion, double* acc, float* grad, yad_stream_t stream);
+
 /* Fused Adam (L2 weight decay) + EMA over a flat fp32 parameter arena:
  * torch.optim.Adam (train.py:83-90, config.yaml:75-80) and smoothener/_ema.py:20-26.
  * ema may be NULL.  step >= 1. */

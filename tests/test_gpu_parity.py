@@ -403,3 +403,63 @@ def test_fused_adam_ema(gold, cuda_dev):
         opt.step()
     np.testing.assert_allclose(p.data.cpu().numpy(), g["adam_w3"], atol=2e-6)
     np.testing.assert_allclose(opt.ema.cpu().numpy(), g["ema3"], atol=2e-6)
+
+
+# ------------------------------------------------------------------ detection loss
+def _loss_module():
+    lc = dict(yad_b200.default_config()["train_config"]["loss_config"])
+    return yad_b200.AudioDetectionLoss(yad_b200.default_config()["anchors"], 2, **lc)
+
+
+def test_detection_loss_vs_reference_golden(gold, cuda_dev):
+    """Loss value and d loss / d preds of the CUDA kernels vs the values the live reference produced (fixtures)."""
+    g = gold("train")
+    tg = torch.from_numpy(g["targets"]).to(cuda_dev)
+    with torch.enable_grad():
+        preds = [torch.from_numpy(g[f"pred{i}"]).to(cuda_dev).requires_grad_(True) for i in range(3)]
+        loss, met = _loss_module()(preds, tg)
+        loss.backward()
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=2e-6)          # tolerance: fp32 sums in fp64 accumulators
+    for i in range(3):
+        np.testing.assert_allclose(preds[i].grad.cpu().numpy(), g[f"grad{i}"], atol=2e-7, rtol=2e-4)
+    assert set(met) == {"aggregate_loss", "mean_ciou", "conf_loss", "avg_pos_conf", "avg_neg_conf", "class_loss", "accuracy", "f1",
+                        "precision", "recall"}
+
+
+@pytest.mark.parametrize("seed,B,T", [(0, 4, 23), (1, 16, 200), (2, 3, 0), (3, 32, 900)])
+def test_detection_loss_vs_oracle(seed, B, T, cuda_dev):
+    """Random predictions / targets (incl. duplicates, ignore labels, the no-target case) vs the CPU oracle."""
+    gen = torch.Generator().manual_seed(seed)
+    preds = []
+    for G in (120, 60, 30):
+        p = torch.randn(B, G, 3, 5, generator=gen)
+        p[..., 3] = torch.rand(B, G, 3, generator=gen) * 60
+        p[..., 4] = torch.rand(B, G, 3, generator=gen) * 20 + 0.05
+        preds.append(p)
+    tg = torch.zeros(T, 4)
+    if T:
+        tg[:, 0] = torch.randint(0, B, (T,), generator=gen).float()
+        tg[:, 1] = torch.randint(0, 2, (T,), generator=gen).float()
+        tg[::7, 1] = -100.0                                   # ignore_index rows
+        tg[:, 2] = torch.rand(T, generator=gen) * 60
+        tg[:, 3] = torch.rand(T, generator=gen) * 12 + 0.2
+        if T > 10:
+            tg[5] = tg[4]                                     # exact duplicate -> duplicate (b,g,a) keys
+    with torch.enable_grad():
+        ref_p = [p.clone().requires_grad_(True) for p in preds]
+        ref_loss, ref_met = O.detection_loss(ref_p, tg, O.DEFAULT_CONFIG["anchors"], 2)
+        if ref_loss.requires_grad:
+            ref_loss.backward()
+        cu_p = [p.to(cuda_dev).requires_grad_(True) for p in preds]
+        loss, met = _loss_module()(cu_p, tg.to(cuda_dev))
+        loss.backward()
+    # the oracle (like the reference) reduces in fp32, the kernels in fp64: up to ~1e-5 relative on 10^5-term means
+    np.testing.assert_allclose(float(loss), float(ref_loss), rtol=5e-5)
+    for a, b in zip(cu_p, ref_p):
+        rg = b.grad.numpy() if b.grad is not None else np.zeros(tuple(b.shape), np.float32)
+        np.testing.assert_allclose(a.grad.cpu().numpy(), rg, atol=3e-7, rtol=5e-4)
+    for k in ("mean_ciou", "conf_loss", "class_loss", "avg_pos_conf", "avg_neg_conf"):
+        if ref_met[k] == ref_met[k]:
+            np.testing.assert_allclose(met[k], ref_met[k], rtol=2e-5, atol=1e-7)
+        else:
+            assert met[k] != met[k]

@@ -149,3 +149,21 @@ def test_grid_sizes(model):
     assert InferenceEngine.frames(e, 1323000) == 960
     assert InferenceEngine.grids(e, 1323000) == [120, 60, 30]
     assert InferenceEngine.grids(e, 22050 * 6) == [12, 6, 3]
+
+
+def test_macro_metrics_match_sklearn():
+    """The loss module's accuracy / macro precision / recall / f1 (from the device confusion matrix) vs sklearn, which is what
+    the reference calls (modules/_loss.py:167-173)."""
+    from sklearn.metrics import accuracy_score, f1_score, precision_score, recall_score
+    from yad_b200.train_ops import _macro_metrics
+    import warnings
+    rng = np.random.default_rng(0)
+    for nc, n in ((2, 50), (5, 200), (4, 7)):
+        yt, yp = rng.integers(0, nc, n), rng.integers(0, max(1, nc - 1), n)      # some classes never predicted
+        cm = np.zeros((nc, nc), np.int64)
+        np.add.at(cm, (yt, yp), 1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = (accuracy_score(yt, yp), f1_score(yt, yp, average="macro"), precision_score(yt, yp, average="macro"),
+                    recall_score(yt, yp, average="macro"))
+        np.testing.assert_allclose(_macro_metrics(cm), want, rtol=1e-12)

@@ -56,6 +56,7 @@ SIGNATURES = {
     "yad_nms": [_p, _i64, _i32, _i32, _f64, _f32, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p],
     "yad_compact_segments": [_p, _p, _i64, _i32, _p, _p, _p, _p],
     "yad_build_targets": [_p, _i32, _p, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p],
+    "yad_loss_scale": [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _f32, _f32, _f32, _f32, _i64, _p, _p, _p, _p, _p, _p],
     "yad_adam_ema_step": [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _p],
 }
 EXPORTS = ["yad_version", "yad_last_error"] + list(SIGNATURES)

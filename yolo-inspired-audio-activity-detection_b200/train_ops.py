@@ -50,6 +50,121 @@ def build_target_by_scale(targets: torch.Tensor, fmap_shape: Union[int, torch.Si
     return [bi[:M], gi[:M], ai[:M]], cl[:M], cw[:M]
 
 
+class _DetectionLossFn(torch.autograd.Function):
+    """loss = f(preds); the kernels return d loss / d preds, so backward is a scale by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, mod, targets, *preds):
+        loss, grads, metrics = mod._run(preds, targets)
+        ctx.save_for_backward(*grads)
+        mod._last_metrics = metrics
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None) + tuple(g * t for t in ctx.saved_tensors)
+
+
+class AudioDetectionLoss(torch.nn.Module):
+    """Drop-in for the reference ``AudioDetectionLoss`` (modules/_loss.py:39-191) on sm_100a kernels: same constructor,
+    ``forward((sm, md, lg), targets) -> (loss, metrics dict)`` with the same 10 metric keys; ``loss`` is differentiable
+    with respect to the three prediction tensors (CUDA, fp32).  Built: the default train_config (``multi_label=True``,
+    no focal loss); the other branches raise NotImplementedError."""
+
+    SCALE_W = (4.0, 2.0, 1.0)
+
+    def __init__(self, anchors_dict, num_classes, anchor_t=4.0, edge_t=0.5, sample_duration=60, box_w=1.0, conf_w=1.0,
+                 class_w=1.0, multi_label=False, class_weights=None, label_smoothing=0, batch_scale_loss=False, alpha=None,
+                 gamma=None, ignore_index=-100):
+        super().__init__()
+        if not multi_label:
+            raise NotImplementedError("yad_b200.AudioDetectionLoss: only multi_label=True (the reference train_config) is built")
+        if alpha and gamma:
+            raise NotImplementedError("yad_b200.AudioDetectionLoss: the focal-loss objectness variant is not built")
+        self.anchors_dict, self.num_classes = anchors_dict, int(num_classes)
+        self.anchor_t, self.edge_t, self.sample_duration = anchor_t, edge_t, sample_duration
+        self.box_w, self.conf_w, self.class_w = float(box_w), float(conf_w), float(class_w)
+        self.label_smoothing, self.batch_scale_loss, self.ignore_index = float(label_smoothing), bool(batch_scale_loss), int(ignore_index)
+        self._last_metrics = {}
+
+    def _run(self, preds, targets):
+        dev = preds[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("yad_b200.AudioDetectionLoss needs CUDA tensors (no CPU fallback)")
+        lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        nc = self.num_classes
+        bscale = float(preds[-1].shape[0]) if self.batch_scale_loss else 1.0
+        accs = torch.zeros((3, 8), device=dev, dtype=torch.float64)
+        confs = torch.zeros((3, nc, nc), device=dev, dtype=torch.int32)
+        grads, Ms, Ns = [], [], []
+        with torch.cuda.device(dev):
+            for s, (p, name) in enumerate(zip(preds, ("sm", "md", "lg"))):
+                p = p.detach().contiguous().float()
+                B, G, A, E = p.shape
+                if E != 3 + nc:
+                    raise ValueError(f"prediction tensor has {E} channels, expected {3 + nc}")
+                (bi, gi, ai), cl, cw = build_target_by_scale(targets, G, self.anchors_dict[name], self.anchor_t,
+                                                             self.sample_duration, self.edge_t)
+                M = int(bi.shape[0])
+                owner = torch.empty(B * G * A, device=dev, dtype=torch.int32)
+                ciou = torch.empty(max(M, 1), device=dev, dtype=torch.float32)
+                g = torch.empty_like(p)
+                rc = lib.yad_loss_scale(p.data_ptr(), B, G, A, nc, _lib.ptr(bi), _lib.ptr(gi), _lib.ptr(ai), _lib.ptr(cl), _lib.ptr(cw),
+                                        M, self.box_w * bscale, self.conf_w * self.SCALE_W[s] * bscale, self.class_w * bscale,
+                                        self.label_smoothing, self.ignore_index, owner.data_ptr(), ciou.data_ptr(),
+                                        confs[s].data_ptr(), accs[s].data_ptr(), g.data_ptr(), _stream(dev))
+                _lib.check(rc, f"loss_scale {name}")
+                grads.append(g)
+                Ms.append(M)
+                Ns.append(B * G * A)
+        a = accs.cpu().numpy()            # one 192-byte read; the reference syncs on every .item() too
+        cm = confs.cpu().numpy()
+        nan = float("nan")
+        lbox = lconf = lcls = 0.0
+        met = {k: 0.0 for k in ("mean_ciou", "conf_loss", "avg_pos_conf", "avg_neg_conf", "class_loss", "accuracy", "f1", "precision", "recall")}
+        for s in range(3):
+            M, N, nvalid = Ms[s], Ns[s], a[s, 7]
+            box = a[s, 0] / M if M else nan
+            conf = a[s, 2] / N
+            cls = a[s, 3] / (nvalid * nc) if nvalid else nan
+            lbox += 0.0 if box != box else box          # handle_nan (modules/_loss.py:178)
+            lconf += self.SCALE_W[s] * conf
+            lcls += 0.0 if cls != cls else cls
+            met["mean_ciou"] += (a[s, 1] / M if M else nan) / 3
+            met["conf_loss"] += conf / 3
+            met["avg_pos_conf"] += (a[s, 4] / M if M else nan) / 3
+            met["avg_neg_conf"] += (a[s, 5] / a[s, 6] if a[s, 6] else nan) / 3
+            met["class_loss"] += cls / 3
+            acc_, f1_, pr_, rc_ = _macro_metrics(cm[s]) if nvalid else (nan, nan, nan, nan)
+            met["accuracy"] += acc_ / 3
+            met["f1"] += f1_ / 3
+            met["precision"] += pr_ / 3
+            met["recall"] += rc_ / 3
+        loss_v = (self.box_w * lbox + self.conf_w * lconf + self.class_w * lcls) * bscale
+        met = {"aggregate_loss": float(loss_v), **{k: float(v) for k, v in met.items()}}
+        return torch.tensor(loss_v, device=dev, dtype=torch.float32), grads, met
+
+    def forward(self, preds, targets):
+        loss = _DetectionLossFn.apply(self, targets, *preds)
+        return loss, dict(self._last_metrics)
+
+
+def _macro_metrics(cm):
+    """accuracy and sklearn's macro precision / recall / f1 (labels = those present in targets or predictions,
+    zero_division -> 0) from a confusion matrix [target, predicted]."""
+    import numpy as np
+    cm = np.asarray(cm, dtype=np.float64)
+    tot = cm.sum()
+    tp = np.diag(cm)
+    sup_t, sup_p = cm.sum(1), cm.sum(0)
+    present = (sup_t + sup_p) > 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        prec = np.where(sup_p > 0, tp / sup_p, 0.0)
+        rec = np.where(sup_t > 0, tp / sup_t, 0.0)
+        f1 = np.where(prec + rec > 0, 2 * prec * rec / (prec + rec), 0.0)
+    return tp.sum() / tot, f1[present].mean(), prec[present].mean(), rec[present].mean()
+
+
 class FusedAdamEMA:
     """torch.optim.Adam (L2 weight decay; train.py:83-90, config.yaml:75-80) fused with the EMA shadow update
     (smoothener/_ema.py:20-26) over ONE flat fp32 arena: 1 launch per step instead of ~10 per tensor.
