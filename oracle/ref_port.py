@@ -578,8 +578,13 @@ def detection_loss(preds: Sequence[Tensor], targets: Tensor, anchors_dict: Dict[
         ciou = compute_ciou(mp[:, -2:], cw)
         box = (1 - ciou).mean()
         t_conf = torch.zeros(p.shape[:-1], dtype=p.dtype)
-        # duplicate (b,g,a) keys: last writer wins on CPU (index_put_, non-accumulating) - Q12
-        t_conf[bi, gi, ai] = ciou.detach()
+        # duplicate (b,g,a) keys (Q12): torch's non-accumulating index_put_ is "last writer wins" while it runs serially
+        # (small M, e.g. the golden fixture) and order-undefined once it parallelises (M > ~4096 on CPU, always on CUDA).
+        # The oracle pins the serial rule explicitly: the LAST match of a cell owns t_conf.
+        keys = ((bi * p.shape[1] + gi) * p.shape[2] + ai).numpy()
+        _, first_rev = np.unique(keys[::-1], return_index=True)
+        last = torch.from_numpy(np.sort(len(keys) - 1 - first_rev).astype(np.int64))
+        t_conf[bi[last], gi[last], ai[last]] = ciou.detach()[last]
         conf = F.binary_cross_entropy_with_logits(p[..., 0], t_conf)
         m = cl != ignore_index
         pcls = mp[:, 1:1 + num_classes][m]
