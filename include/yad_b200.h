@@ -69,7 +69,7 @@ int yad_init(int device);
  *                                          bins of one band must be contiguous (triangular filters are)
  *   mel        [B, 32, T]             f32  (T frames; T*1000 <= ceil(P*L/O))
  */
-#define YAD_FE_QW 22
+#define YAD_FE_QW 21
 int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
                            const float* taps, const int32_t* tap_base, int32_t window_len,
                            const float* window, const float* twiddle, const float* fb_val,

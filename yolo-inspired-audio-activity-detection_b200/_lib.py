@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libyad_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-FE_QW = 22
+FE_QW = 21
 
 
 class YadError(RuntimeError):

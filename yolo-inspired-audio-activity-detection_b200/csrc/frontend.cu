@@ -4,7 +4,7 @@
 // warp-specialised into two roles that overlap through double-buffered shared memory:
 //   resample warps (8): 16-byte cp.async staging of the PCM span (one group ahead) -> sparse polyphase resample
 //     (only the non-zero taps of torchaudio's Hann-windowed sinc bank; one QUAD of adjacent phases per thread with
-//     its 4 x 22 taps resident in registers for the whole kernel) fused with the Hann analysis window -> frame buffer;
+//     its 4 x 21 taps resident in registers for the whole kernel) fused with the Hann analysis window -> frame buffer;
 //   FFT warps (8): 1000-point real FFT as a 500-point complex FFT = 25 x 20 with both factors done in registers
 //     (fft500.cuh; two shared-memory exchanges instead of four radix passes) -> untangle + |X|^2 -> sparse (CSR)
 //     mel filterbank -> [B, 32, T] mel power.
@@ -29,8 +29,9 @@ constexpr int FE_NMEL = 32;
 constexpr int FE_QW = YAD_FE_QW;    // taps per phase over the quad's common window (zero padded)
 constexpr int FE_ROLE = 256;        // threads per role
 constexpr int FE_THREADS = 2 * FE_ROLE;
-constexpr int FE_FR_WORDS = FE_FR * 2 * FFT_Y_STRIDE;   // frame buffer (floats): the widest of the three layouts
-constexpr int FE_P_STRIDE = 505;    // power-spectrum row pitch (odd: frames land in distinct banks)
+constexpr int FE_FR_WORDS = FE_FR * 2 * FFT_Z_STRIDE;   // frame buffer (floats): frames in, spectrum out (natural order)
+constexpr int FE_Y_WORDS = FE_FR * 2 * FFT_Y_STRIDE;    // pass-A -> pass-B exchange buffer
+constexpr int FE_P_STRIDE = 516;    // power-spectrum row pitch (= 4 mod 32: 8 frames x 4 adjacent bins hit 32 distinct banks)
 constexpr int FE_NPAIR = FE_FR * 251;
 
 // named barriers (0 is __syncthreads)
@@ -92,7 +93,8 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
   const int sxp = (p.SX + 8 + 3) & ~3;
   float* s_x = fe_smem;                                      // [2][sxp] staged PCM spans
   float* s_fr = s_x + 2 * sxp;                               // [2][FE_FR_WORDS] frames / FFT exchange
-  float* s_P = s_fr + 2 * FE_FR_WORDS;                       // [FE_FR][FE_P_STRIDE] power spectrum (bins 0..500)
+  float* s_Y = s_fr + 2 * FE_FR_WORDS;                       // [FE_FR][25][21] complex: pass-A output in pass-B order
+  float* s_P = s_Y + FE_Y_WORDS;                             // [FE_FR][FE_P_STRIDE] power spectrum (bins 0..500)
   float2* s_tw = reinterpret_cast<float2*>(s_P + ((FE_FR * FE_P_STRIDE + 3) & ~3));   // exp(-2 pi i k / 1000), 16 B aligned
   float2* s_twA = s_tw + FE_NFFT;                            // [25 regs][20 n2] pass-A twiddles W_500^(n2 k1(r))
   float* s_win = reinterpret_cast<float*>(s_twA + 500);      // [1000] analysis window
@@ -186,6 +188,7 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
       const int buf = gi & 1;
       const int g = g_first + gi;
       cf32* zf = reinterpret_cast<cf32*>(s_fr + buf * FE_FR_WORDS);
+      cf32* yf = reinterpret_cast<cf32*>(s_Y);
       bar_sync(BAR_FULL0 + buf, FE_THREADS);
       // ---- pass A: 25-point DFTs over n1 (stride 20), twiddle W_500^(n2 k1)
       cf32 v[25];
@@ -201,22 +204,18 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
           v[r] = cmulc(v[r], t.x, t.y);
         }
       }
-      bar_sync(BAR_FT, FE_ROLE);      // every pass-A load is done: the buffer can change layout
-      if (actA) {
-        cf32* dst = zf + fA * FFT_Y_STRIDE + n2;
+      if (actA) {      // Y lives in its own buffer: no hazard with the other threads' frame loads
+        cf32* dst = yf + fA * FFT_Y_STRIDE + n2;
 #pragma unroll
         for (int r = 0; r < 25; ++r) dst[passA_k1_of_reg(r) * FFT_Y_PITCH] = v[r];
       }
-      bar_sync(BAR_FT, FE_ROLE);
+      bar_sync(BAR_FT, FE_ROLE);      // Y complete; every frame load of pass A is done (the spectrum may overwrite the frames)
       // ---- pass B: 20-point DFTs over n2; X[k1 + 25 k2] in natural order
       if (actB) {
-        const cf32* src = zf + fB * FFT_Y_STRIDE + k1 * FFT_Y_PITCH;
+        const cf32* src = yf + fB * FFT_Y_STRIDE + k1 * FFT_Y_PITCH;
 #pragma unroll
         for (int j = 0; j < 20; ++j) v[j] = src[j];
         dft20(v);
-      }
-      bar_sync(BAR_FT, FE_ROLE);
-      if (actB) {
         cf32* dst = zf + fB * FFT_Z_STRIDE + k1;
 #pragma unroll
         for (int r = 0; r < 20; ++r) dst[25 * passB_k2_of_reg(r)] = v[r];
@@ -244,22 +243,38 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
         __threadfence_block();
         bar_arrive(BAR_EMPTY0 + buf, FE_THREADS);
       }
-      // ---- sparse mel filterbank (band m covers the contiguous bins [bin0, bin0 + len)); thread = (frame, band)
+      // ---- sparse mel filterbank (band m covers the contiguous bins [bin0, bin0 + len)).  Warp w owns the bands
+      //      {w, 15-w, 16+w, 31-w} (equal total length per warp); lane = (frame, sub): the 4 subs of a frame split a band's
+      //      bins 4-way and are summed with two shuffles.  P pitch = 4 (mod 32): conflict-free reads.
       {
-        const int f = rt & (FE_FR - 1), m = rt >> 3;
+        const int wq = rt >> 5, ln = rt & 31;
+        const int f = ln & (FE_FR - 1), sub = ln >> 3;
         const int64_t t = (int64_t)g * FE_FR + f;
-        const float* pp = s_P + f * FE_P_STRIDE + s_fbs[FE_NMEL + 1 + m];
-        const int s0 = s_fbs[m], e0 = s_fbs[m + 1];
-        const float* fv = s_fbv + s0;
-        const int len = e0 - s0;
-        float acc0 = 0.0f, acc1 = 0.0f;
-        int i = 0;
-        for (; i + 1 < len; i += 2) {
-          acc0 = fmaf(pp[i], fv[i], acc0);
-          acc1 = fmaf(pp[i + 1], fv[i + 1], acc1);
+        const float* pf = s_P + f * FE_P_STRIDE;
+        float mine = 0.0f;
+        int my_band = 0;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int m = q4 == 0 ? wq : (q4 == 1 ? 15 - wq : (q4 == 2 ? 16 + wq : 31 - wq));
+          const int s0 = s_fbs[m], len = s_fbs[m + 1] - s0;
+          const float* pp = pf + s_fbs[FE_NMEL + 1 + m];
+          const float* fv = s_fbv + s0;
+          float acc0 = 0.0f, acc1 = 0.0f;
+          int i = sub;
+          for (; i + 4 < len; i += 8) {
+            acc0 = fmaf(pp[i], fv[i], acc0);
+            acc1 = fmaf(pp[i + 4], fv[i + 4], acc1);
+          }
+          if (i < len) acc0 = fmaf(pp[i], fv[i], acc0);
+          float a = acc0 + acc1;
+          a += __shfl_xor_sync(0xffffffffu, a, 8);
+          a += __shfl_xor_sync(0xffffffffu, a, 16);
+          if (q4 == sub) {
+            mine = a;
+            my_band = m;
+          }
         }
-        if (i < len) acc0 = fmaf(pp[i], fv[i], acc0);
-        if (t < p.T) mel[(b * FE_NMEL + m) * p.T + t] = acc0 + acc1;
+        if (t < p.T) mel[(b * FE_NMEL + my_band) * p.T + t] = mine;
       }
     }
   }
@@ -376,7 +391,7 @@ frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __
 
 static size_t fe_smem_bytes(int SX, int nnz_pad) {
   const int sxp = (SX + 8 + 3) & ~3;
-  return (size_t)(2 * sxp + 2 * FE_FR_WORDS + ((FE_FR * FE_P_STRIDE + 3) & ~3) + 2 * FE_NFFT + 1000 + FE_NFFT + nnz_pad +
+  return (size_t)(2 * sxp + 2 * FE_FR_WORDS + FE_Y_WORDS + ((FE_FR * FE_P_STRIDE + 3) & ~3) + 2 * FE_NFFT + 1000 + FE_NFFT + nnz_pad +
                   2 * FE_NMEL + 4) * sizeof(float);
 }
 
