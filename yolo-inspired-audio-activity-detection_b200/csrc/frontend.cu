@@ -245,33 +245,53 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
       }
       // ---- sparse mel filterbank (band m covers the contiguous bins [bin0, bin0 + len)).  Warp w owns the bands
       //      {w, 15-w, 16+w, 31-w} (equal total length per warp); lane = (frame, sub): the 4 subs of a frame split a band's
-      //      bins 4-way and are summed with two shuffles.  P pitch = 4 (mod 32): conflict-free reads.
+      //      bins 4-way (8 independent loads in flight per lane) and are summed with two shuffles.
+      //      P pitch = 4 (mod 32): the 8 frames x 4 adjacent bins of a warp hit 32 distinct banks.
+      //      (Deferring this pass to the three warps that idle during the next group's pass A was tried: 18 % slower.)
       {
         const int wq = rt >> 5, ln = rt & 31;
         const int f = ln & (FE_FR - 1), sub = ln >> 3;
         const int64_t t = (int64_t)g * FE_FR + f;
-        const float* pf = s_P + f * FE_P_STRIDE;
+        const float* pf = s_P + f * FE_P_STRIDE + sub;
+        int bm[4], bs[4], bl[4], bb[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          bm[q4] = q4 == 0 ? wq : (q4 == 1 ? 15 - wq : (q4 == 2 ? 16 + wq : 31 - wq));
+          bs[q4] = s_fbs[bm[q4]];
+          bl[q4] = s_fbs[bm[q4] + 1] - bs[q4];
+          bb[q4] = s_fbs[FE_NMEL + 1 + bm[q4]];
+        }
         float mine = 0.0f;
         int my_band = 0;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const int m = q4 == 0 ? wq : (q4 == 1 ? 15 - wq : (q4 == 2 ? 16 + wq : 31 - wq));
-          const int s0 = s_fbs[m], len = s_fbs[m + 1] - s0;
-          const float* pp = pf + s_fbs[FE_NMEL + 1 + m];
-          const float* fv = s_fbv + s0;
-          float acc0 = 0.0f, acc1 = 0.0f;
-          int i = sub;
-          for (; i + 4 < len; i += 8) {
-            acc0 = fmaf(pp[i], fv[i], acc0);
-            acc1 = fmaf(pp[i + 4], fv[i + 4], acc1);
+          const float* pp = pf + bb[q4];
+          const float* fv = s_fbv + bs[q4] + sub;
+          const int len = bl[q4] - sub;            // entries of this sub: idx = 4 j, 4 j < len
+          float a0 = 0.0f, a1 = 0.0f;
+          for (int base = 0; base < bl[q4]; base += 32) {      // warp-uniform trip count
+            float pv[8], wv[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int idx = base + 4 * jj;
+              const bool ok = idx < len;
+              const int ic = ok ? idx : 0;          // unconditional loads from a safe address, select on the value
+              pv[jj] = pp[ic];
+              const float wl = fv[ic];
+              wv[jj] = ok ? wl : 0.0f;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; jj += 2) {
+              a0 = fmaf(pv[jj], wv[jj], a0);
+              a1 = fmaf(pv[jj + 1], wv[jj + 1], a1);
+            }
           }
-          if (i < len) acc0 = fmaf(pp[i], fv[i], acc0);
-          float a = acc0 + acc1;
+          float a = a0 + a1;
           a += __shfl_xor_sync(0xffffffffu, a, 8);
           a += __shfl_xor_sync(0xffffffffu, a, 16);
           if (q4 == sub) {
             mine = a;
-            my_band = m;
+            my_band = bm[q4];
           }
         }
         if (t < p.T) mel[(b * FE_NMEL + my_band) * p.T + t] = mine;
