@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="clips per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end pipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -287,16 +288,9 @@ def main():
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     xh = torch.empty((B, 1, CLIP_SAMPLES), dtype=torch.float32, pin_memory=True)
     xh.copy_(x)
-    xd = torch.empty_like(x)
-
     def e2e_step():
-        xd.copy_(xh, non_blocking=True)
-        preds = model(xd, combine_scales=True)
-        try:
-            seg, bidx = yad_b200.process_model_outputs(preds, 0.1, 0.2)
-            return seg.cpu(), bidx.cpu()
-        except ValueError:
-            return None, None
+        # public host-buffer API: chunked, double-buffered H2D copy overlapped with the forward, one D2H of the segments
+        return yad_b200.run_host_batch(model, xh, 0.1, 0.2, chunk=args.e2e_chunk)
     e2e_step()
     torch.cuda.synchronize()
     Ke = max(1, min(K, 5))

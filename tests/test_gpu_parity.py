@@ -463,3 +463,13 @@ def test_detection_loss_vs_oracle(seed, B, T, cuda_dev):
             np.testing.assert_allclose(met[k], ref_met[k], rtol=2e-5, atol=1e-7)
         else:
             assert met[k] != met[k]
+
+
+def test_host_pipeline_equals_direct_call(models, cuda_dev):
+    """run_host_batch (chunked, double-buffered H2D) returns exactly what model(x) + process_model_outputs returns."""
+    m = models[("deploy", "bf16")]
+    x = synth.synth_clips(5, 22050 * 6, seed=4000, silence_tail_every=3)
+    seg_d, bidx_d = yad_b200.process_model_outputs(m(x.to(cuda_dev), combine_scales=True), 0.1, 0.2)
+    seg_h, bidx_h = yad_b200.run_host_batch(m, x.pin_memory(), 0.1, 0.2, chunk=2)
+    np.testing.assert_array_equal(bidx_h.numpy(), bidx_d.cpu().numpy())
+    np.testing.assert_array_equal(seg_h.numpy(), seg_d.cpu().numpy())

@@ -319,7 +319,7 @@ __device__ __forceinline__ Tv block_reduce(Tv v, Tv* scratch, Op op, Tv ident) {
   return r;
 }
 
-__global__ void __launch_bounds__(FB_THREADS)
+__global__ void __launch_bounds__(FB_THREADS, 4)   // 4 CTAs / SM: 512 clips fit one wave
 frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __restrict__ dct, float top_db,
                        int standardise, float* __restrict__ xs, float* __restrict__ tap_meldb,
                        float* __restrict__ tap_mfcc, float* __restrict__ tap_mfdb) {
