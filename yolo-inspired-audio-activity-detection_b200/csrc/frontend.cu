@@ -243,58 +243,29 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
         __threadfence_block();
         bar_arrive(BAR_EMPTY0 + buf, FE_THREADS);
       }
-      // ---- sparse mel filterbank (band m covers the contiguous bins [bin0, bin0 + len)).  Warp w owns the bands
-      //      {w, 15-w, 16+w, 31-w} (equal total length per warp); lane = (frame, sub): the 4 subs of a frame split a band's
-      //      bins 4-way (8 independent loads in flight per lane) and are summed with two shuffles.
-      //      P pitch = 4 (mod 32): the 8 frames x 4 adjacent bins of a warp hit 32 distinct banks.
-      //      (Deferring this pass to the three warps that idle during the next group's pass A was tried: 18 % slower.)
+      // ---- sparse mel filterbank (band m covers the contiguous bins [bin0, bin0 + len)); thread = (frame, band), the 4
+      //      bands of a warp are adjacent (similar lengths); 4 independent loads in flight per lane.
+      //      (Tried and measured slower: a 4-way split of every band across lanes with shuffle reduction - 2.3x the
+      //      instructions; deferring the pass to the warps that idle during the next group's pass A - 18 % slower.)
       {
-        const int wq = rt >> 5, ln = rt & 31;
-        const int f = ln & (FE_FR - 1), sub = ln >> 3;
+        const int f = rt & (FE_FR - 1), m = rt >> 3;
         const int64_t t = (int64_t)g * FE_FR + f;
-        const float* pf = s_P + f * FE_P_STRIDE + sub;
-        int bm[4], bs[4], bl[4], bb[4];
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          bm[q4] = q4 == 0 ? wq : (q4 == 1 ? 15 - wq : (q4 == 2 ? 16 + wq : 31 - wq));
-          bs[q4] = s_fbs[bm[q4]];
-          bl[q4] = s_fbs[bm[q4] + 1] - bs[q4];
-          bb[q4] = s_fbs[FE_NMEL + 1 + bm[q4]];
+        const float* pp = s_P + f * FE_P_STRIDE + s_fbs[FE_NMEL + 1 + m];
+        const int s0 = s_fbs[m], e0 = s_fbs[m + 1];
+        const float* fv = s_fbv + s0;
+        const int len = e0 - s0;
+        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+        int i = 0;
+        for (; i + 3 < len; i += 4) {
+          const float p0 = pp[i], p1 = pp[i + 1], p2 = pp[i + 2], p3 = pp[i + 3];
+          const float w0 = fv[i], w1 = fv[i + 1], w2 = fv[i + 2], w3 = fv[i + 3];
+          acc0 = fmaf(p0, w0, acc0);
+          acc1 = fmaf(p1, w1, acc1);
+          acc2 = fmaf(p2, w2, acc2);
+          acc3 = fmaf(p3, w3, acc3);
         }
-        float mine = 0.0f;
-        int my_band = 0;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float* pp = pf + bb[q4];
-          const float* fv = s_fbv + bs[q4] + sub;
-          const int len = bl[q4] - sub;            // entries of this sub: idx = 4 j, 4 j < len
-          float a0 = 0.0f, a1 = 0.0f;
-          for (int base = 0; base < bl[q4]; base += 32) {      // warp-uniform trip count
-            float pv[8], wv[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const int idx = base + 4 * jj;
-              const bool ok = idx < len;
-              const int ic = ok ? idx : 0;          // unconditional loads from a safe address, select on the value
-              pv[jj] = pp[ic];
-              const float wl = fv[ic];
-              wv[jj] = ok ? wl : 0.0f;
-            }
-#pragma unroll
-            for (int jj = 0; jj < 8; jj += 2) {
-              a0 = fmaf(pv[jj], wv[jj], a0);
-              a1 = fmaf(pv[jj + 1], wv[jj + 1], a1);
-            }
-          }
-          float a = a0 + a1;
-          a += __shfl_xor_sync(0xffffffffu, a, 8);
-          a += __shfl_xor_sync(0xffffffffu, a, 16);
-          if (q4 == sub) {
-            mine = a;
-            my_band = bm[q4];
-          }
-        }
-        if (t < p.T) mel[(b * FE_NMEL + my_band) * p.T + t] = mine;
+        for (; i < len; ++i) acc0 = fmaf(pp[i], fv[i], acc0);
+        if (t < p.T) mel[(b * FE_NMEL + m) * p.T + t] = (acc0 + acc1) + (acc2 + acc3);
       }
     }
   }
