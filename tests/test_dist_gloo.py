@@ -61,3 +61,32 @@ def test_shard_bounds_properties():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         parallel.shard_bounds(10, 2, 2)
+
+
+def _ar_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)          # rank r holds (r+1) * arange
+    parallel.allreduce_mean_(g, bucket_bytes=1024)                    # 4 buckets
+    q.put((rank, g.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce():
+    """The train step's only collective: mean of the flat gradient arena over the data-parallel ranks."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ar_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (torch.arange(1000, dtype=torch.float32) * 1.5).tolist()
+    for _, got in res:
+        assert got == want
+    assert parallel.allreduce_mean_(torch.ones(4)).tolist() == [1.0] * 4     # not initialised: no-op

@@ -42,3 +42,20 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def allreduce_mean_(flat: torch.Tensor, bucket_bytes: int = 32 << 20) -> torch.Tensor:
+    """Data-parallel gradient averaging over a FLAT arena (one all-reduce of the 48.5 MB fp32 gradient
+    per train step, NCCL over NVLink on GPU tensors, gloo on CPU tensors).  The arena is reduced in place in buckets of
+    ``bucket_bytes`` issued back to back (async ops, one wait at the end) so that NCCL pipelines them; with NVSwitch the
+    cost is launch latency + bytes / bus bandwidth, not per-link.  No-op when torch.distributed is not initialised."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    world = dist.get_world_size()
+    n = flat.numel()
+    per = max(1, bucket_bytes // flat.element_size())
+    works = [dist.all_reduce(flat[o:min(o + per, n)], op=dist.ReduceOp.SUM, async_op=True) for o in range(0, n, per)]
+    for w in works:
+        w.wait()
+    flat.div_(world)
+    return flat

@@ -203,6 +203,11 @@ class FusedAdamEMA:
     def zero_grad(self):
         self.grad.zero_()
 
+    def allreduce_grads(self):
+        """Average the flat gradient arena across the data-parallel ranks (one bucketed NCCL all-reduce)."""
+        from .parallel import allreduce_mean_
+        allreduce_mean_(self.grad)
+
     def step(self):
         self.step_count += 1
         m = self.ema_m(self.step_count) if self.use_ema else 0.0
