@@ -305,15 +305,16 @@ frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __
   auto fmax_op = [](float a, float c) { return fmaxf(a, c); };
   auto dadd_op = [](double a, double c) { return a + c; };
 
-  // pass 1: per-clip max of dB(mel)  -> first top_db floor
-  float mx = -INFINITY;
+  // pass 1: per-clip max of dB(mel) -> first top_db floor.  10 log10(max(., 1e-10)) is monotonic, so the maximum of the
+  //         dB plane is the dB of the maximum: no logarithm in this pass (bit-identical result).
+  float mx = 0.0f;
   for (int64_t t = threadIdx.x; t < T; t += blockDim.x)
-    for (int m = 0; m < FE_NMEL; ++m) mx = fmaxf(mx, to_db(mb[m * T + t]));
-  const float floor1 = block_reduce<float>(mx, s_redf, fmax_op, -INFINITY) - top_db;
+    for (int m = 0; m < FE_NMEL; ++m) mx = fmaxf(mx, mb[m * T + t]);
+  const float floor1 = to_db(block_reduce<float>(mx, s_redf, fmax_op, 0.0f)) - top_db;
 
-  // pass 2: MFCC column (DCT-II of the clamped dB-mel column, computed ONCE and parked in o1), its dB maximum,
-  //         and the moments of the dB-mel plane.  Every later pass touches only frames this thread wrote.
-  float mx2 = -INFINITY;
+  // pass 2: clamped dB-mel (parked in o0), MFCC column (DCT-II of the clamped dB-mel column, parked in o1), the MFCC
+  //         maximum and the moments of the dB-mel plane.  Every later pass touches only frames this thread wrote.
+  float mxf = -INFINITY;
   double s0 = 0.0, q0 = 0.0;
   for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
     float mf[FE_NMEL];
@@ -321,6 +322,7 @@ frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __
     for (int k = 0; k < FE_NMEL; ++k) mf[k] = 0.0f;
     for (int m = 0; m < FE_NMEL; ++m) {
       const float x = fmaxf(to_db(mb[m * T + t]), floor1);
+      o0[m * T + t] = x;
       s0 += (double)x;
       q0 += (double)x * (double)x;
       const float4* dr = reinterpret_cast<const float4*>(s_dct + m * FE_NMEL);
@@ -337,26 +339,28 @@ frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __
     for (int k = 0; k < FE_NMEL; ++k) {
       o1[k * T + t] = mf[k];
       if (tap_mfcc) tap_mfcc[(b * FE_NMEL + k) * T + t] = mf[k];
-      mx2 = fmaxf(mx2, to_db(mf[k]));
+      mxf = fmaxf(mxf, mf[k]);
     }
   }
-  const float floor2 = block_reduce<float>(mx2, s_redf, fmax_op, -INFINITY) - top_db;
+  const float floor2 = to_db(block_reduce<float>(mxf, s_redf, fmax_op, -INFINITY)) - top_db;   // dB of the max = max of the dB
   const double n_el = (double)FE_NMEL * (double)T;
   const double S0 = block_reduce<double>(s0, s_redd, dadd_op, 0.0);
   const double Q0 = block_reduce<double>(q0, s_redd, dadd_op, 0.0);
   const float mu0 = (float)(S0 / n_el);
 
-  // pass 3: moments of the clamped dB(MFCC) plane (fp64 accumulators: sum and sum of squares)
+  // pass 3: clamped dB(MFCC) (replaces the raw MFCC in o1) and its moments (fp64 accumulators: sum and sum of squares)
+  double s1 = 0.0, q1 = 0.0;
+  for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
+    for (int k = 0; k < FE_NMEL; ++k) {
+      const float yf = fmaxf(to_db(o1[k * T + t]), floor2);
+      o1[k * T + t] = yf;
+      const double y = (double)yf;
+      s1 += y;
+      q1 += y * y;
+    }
+  }
   float mu1 = 0.0f, sd0 = 1.0f, sd1 = 1.0f;
   if (standardise) {
-    double s1 = 0.0, q1 = 0.0;
-    for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
-      for (int k = 0; k < FE_NMEL; ++k) {
-        const double y = (double)fmaxf(to_db(o1[k * T + t]), floor2);
-        s1 += y;
-        q1 += y * y;
-      }
-    }
     const double S1 = block_reduce<double>(s1, s_redd, dadd_op, 0.0);
     const double Q1 = block_reduce<double>(q1, s_redd, dadd_op, 0.0);
     mu1 = (float)(S1 / n_el);
@@ -364,18 +368,18 @@ frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __
     sd0 = (float)sqrt(fmax(Q0 - S0 * S0 / n_el, 0.0) / (n_el - 1.0));
     sd1 = (float)sqrt(fmax(Q1 - S1 * S1 / n_el, 0.0) / (n_el - 1.0));
   }
-  // pass 4: write x_spectral [B, 2, 32, T] (+ optional taps)
+  // pass 4: standardise in place (+ optional taps); no transcendental left
   const float den0 = sd0 + 1e-5f, den1 = sd1 + 1e-5f;
   for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
     for (int m = 0; m < FE_NMEL; ++m) {
-      const float x = fmaxf(to_db(mb[m * T + t]), floor1);
+      const float x = o0[m * T + t];
       if (tap_meldb) tap_meldb[(b * FE_NMEL + m) * T + t] = x;
-      o0[m * T + t] = standardise ? __fdiv_rn(x - mu0, den0) : x;
+      if (standardise) o0[m * T + t] = __fdiv_rn(x - mu0, den0);
     }
     for (int k = 0; k < FE_NMEL; ++k) {
-      const float y = fmaxf(to_db(o1[k * T + t]), floor2);
+      const float y = o1[k * T + t];
       if (tap_mfdb) tap_mfdb[(b * FE_NMEL + k) * T + t] = y;
-      o1[k * T + t] = standardise ? __fdiv_rn(y - mu1, den1) : y;
+      if (standardise) o1[k * T + t] = __fdiv_rn(y - mu1, den1);
     }
   }
 }
