@@ -242,6 +242,49 @@ int yad_loss_scale(const float* pred, int64_t B, int32_t G, int32_t A, int32_t n
                    float class_w, float label_smoothing, int64_t ignore_index, int32_t* owner_ws, float* ciou_ws,
                    int32_t* confusion, double* acc, float* grad, yad_stream_t stream);
 
+/* ------------------------------------------------------------------ train-mode network (fp32, NHWC rows x channels)
+ * What autograd does for TrainerPipeline.__feed (pipeline/_trainer.py:94-108): the backward of F.conv2d, BatchNorm2d in
+ * training mode, the activations, the neck glue and the anchor decode.  Correctness-first CUDA-core kernels. */
+
+/* Data gradient of the convolution described by d (the FORWARD descriptor): dX [B,H,W,ld_in] = dx_in (may be NULL) +
+ * sum_taps dY[B,Ho,Wo,ld_out slice co_off] * W.  weight_t: [kh][kw][Cout][Cin] f32. */
+int yad_conv_dgrad(const yad_conv_desc* d, const float* dy, const float* weight_t, const float* dx_in, float* dx,
+                   yad_stream_t stream);
+/* Weight gradient: dw [kh][kw][Cin][Cout] f32 += X^T dY (fp32 atomics); dbias_ws [Cout] f64 += column sums of dY (may be NULL). */
+int yad_conv_wgrad(const yad_conv_desc* d, const float* x, const float* dy, float* dw, double* dbias_ws, yad_stream_t stream);
+/* BatchNorm2d, training mode, over N rows x C channels: batch mean / biased variance (fp64 sums), y = act((x - mean) * invstd
+ * * gamma + beta); running statistics updated in place with `momentum` and the unbiased variance (may be NULL).
+ * ws: [2*C] f64 scratch. */
+int yad_bn_train_fwd(const float* x, int32_t ld_x, int64_t N, int32_t C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, int32_t act, float* y, int32_t ld_y,
+                     float* save_mean, float* save_invstd, double* ws, yad_stream_t stream);
+/* Its backward, the activation's included: g = dy * act'(y); dx (overwritten) = gamma * invstd * (g - mean(g) - xhat * mean(g xhat));
+ * dgamma += sum g xhat; dbeta += sum g. */
+int yad_bn_train_bwd(const float* x, int32_t ld_x, const float* y, int32_t ld_y, const float* dy, int32_t ld_dy, int64_t N, int32_t C,
+                     const float* gamma, const float* save_mean, const float* save_invstd, int32_t act, float* dx, int32_t ld_dx,
+                     float* dgamma, float* dbeta, double* ws, yad_stream_t stream);
+/* y = act(a + b [+ c]) and its backward (g = dy * act'(y) ACCUMULATED into da, db, dc; any of them may be NULL). */
+int yad_add_act(const float* a, int32_t ld_a, const float* b, int32_t ld_b, const float* c, int32_t ld_c, int64_t N, int32_t C,
+                int32_t act, float* y, int32_t ld_y, yad_stream_t stream);
+int yad_add_act_bwd(const float* y, int32_t ld_y, const float* dy, int32_t ld_dy, int64_t N, int32_t C, int32_t act, float* da,
+                    int32_t ld_a, float* db, int32_t ld_b, float* dc, int32_t ld_c, yad_stream_t stream);
+/* Dropout with a counter-based mask: y = (accumulate ? y : 0) + x * keep(seed, i) / (1 - p); calling it on dy gives the backward. */
+int yad_dropout(const float* x, int64_t n, float p, uint64_t seed, int32_t accumulate, float* y, yad_stream_t stream);
+/* Backward of yad_hmean / yad_resize_w (gradients ACCUMULATED into din) and MaxPool(5,1,2) along W forward / backward
+ * (first maximum of the window receives the gradient, accumulated with atomics). */
+int yad_hmean_bwd(const float* dout, int32_t ld_o, int64_t B, int32_t H, int32_t W, int32_t C, float* din, int32_t ld_i,
+                  yad_stream_t stream);
+int yad_resize_w_bwd(const float* dout, int32_t ld_o, int64_t B, int32_t W, int32_t C, int32_t up, float* din, int32_t ld_i,
+                     yad_stream_t stream);
+int yad_maxpool5_w(const float* x, int32_t ld_x, int64_t B, int32_t W, int32_t C, float* y, int32_t ld_y, yad_stream_t stream);
+int yad_maxpool5_w_bwd(const float* x, int32_t ld_x, const float* dy, int32_t ld_dy, int64_t B, int32_t W, int32_t C, float* dx,
+                       int32_t ld_dx, yad_stream_t stream);
+/* Backward of yad_decode for one scale: head [B,G,ld_h] f32, dpred [B,G,A,3+nc]; dhead (overwritten, first A*(3+nc) channels),
+ * danchor_s [A] += d loss / d anchor (in seconds). */
+int yad_decode_bwd(const float* head, int32_t ld_h, const float* dpred, int64_t B, int32_t G, int32_t A, int32_t nc,
+                   const float* anchors_s, float stride_over_scaler, float duration, float* dhead, int32_t ld_dh, float* danchor_s,
+                   yad_stream_t stream);
+
 /* Fused Adam (L2 weight decay) + EMA over a flat fp32 parameter arena:
  * torch.optim.Adam (train.py:83-90, config.yaml:75-80) and smoothener/_ema.py:20-26.
  * ema may be NULL.  step >= 1. */

@@ -1,0 +1,188 @@
+"""Train-mode kernels against PyTorch fp32 autograd of the same ops (run with -m gpu on a B200)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import yad_b200  # noqa: F401
+from oracle import ref_port as O
+from yad_b200 import _lib
+from yad_b200._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ConvDesc
+
+pytestmark = pytest.mark.gpu
+# the PyTorch reference must really be fp32: cuDNN convolutions default to TF32 (10-bit mantissa) on this GPU
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _act(y, act):
+    return F.relu(y) if act == ACT_RELU else (F.leaky_relu(y, 0.2) if act == ACT_LRELU else y)
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, (kh, kw), (sh, sw), (ph, pw)
+    (2, 8, 24, 64, 64, (3, 3), (1, 1), (1, 1)),
+    (2, 8, 24, 64, 128, (3, 3), (2, 2), (1, 1)),
+    (2, 8, 24, 64, 128, (1, 1), (2, 2), (0, 0)),
+    (2, 16, 48, 64, 64, (7, 7), (2, 2), (3, 3)),
+    (3, 1, 24, 15, 128, (3, 3), (1, 2), (1, 1)),
+    (2, 32, 40, 2, 64, (7, 7), (2, 2), (3, 3)),
+    (3, 1, 12, 128, 15, (3, 3), (1, 1), (1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_backward(case, cuda_dev):
+    B, H, W, Cin, Cout, k, s, p = case
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(abs(hash(case)) % 9973)
+    x = torch.randn(B, Cin, H, W, generator=g).to(cuda_dev).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, *k, generator=g) / (Cin * k[0] * k[1]) ** 0.5).to(cuda_dev).requires_grad_(True)
+    b = torch.randn(Cout, generator=g).to(cuda_dev).requires_grad_(True)
+    y = F.conv2d(x, w, b, stride=s, padding=p)
+    dy = torch.randn(y.shape, generator=g).to(cuda_dev)
+    y.backward(dy)
+    Ho, Wo = y.shape[2], y.shape[3]
+    d = ConvDesc(B=B, H=H, W=W, Cin=Cin, ld_in=Cin, Cout=Cout, ld_out=Cout + 8, co_off=8, kh=k[0], kw=k[1], sh=s[0], sw=s[1],
+                 ph=p[0], pw=p[1], act=ACT_NONE, ld_res=0)
+    xh = x.detach().permute(0, 2, 3, 1).contiguous()
+    dyh = torch.zeros(B, Ho, Wo, Cout + 8, device=cuda_dev)
+    dyh[..., 8:] = dy.permute(0, 2, 3, 1)
+    wt = w.detach().permute(2, 3, 0, 1).contiguous()                  # [kh][kw][Cout][Cin]
+    prev = torch.randn(B, H, W, Cin, generator=g).to(cuda_dev)        # an existing gradient to accumulate onto
+    dx = torch.empty_like(prev)
+    _lib.check(lib.yad_conv_dgrad(C.byref(d), dyh.data_ptr(), wt.data_ptr(), prev.data_ptr(), dx.data_ptr(), _stream()), "dgrad")
+    dw = torch.zeros(k[0], k[1], Cin, Cout, device=cuda_dev)
+    db = torch.zeros(Cout, device=cuda_dev, dtype=torch.float64)
+    _lib.check(lib.yad_conv_wgrad(C.byref(d), xh.data_ptr(), dyh.data_ptr(), dw.data_ptr(), db.data_ptr(), _stream()), "wgrad")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose((dx - prev).permute(0, 3, 1, 2).cpu().numpy(), x.grad.cpu().numpy(), atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(dw.permute(3, 2, 0, 1).cpu().numpy(), w.grad.cpu().numpy(), atol=2e-3, rtol=1e-4)
+    np.testing.assert_allclose(db.cpu().numpy(), b.grad.double().cpu().numpy(), atol=1e-4, rtol=1e-5)
+
+
+@pytest.mark.parametrize("act", [ACT_NONE, ACT_RELU, ACT_LRELU])
+@pytest.mark.parametrize("N,Cc", [(2 * 8 * 24, 64), (5000, 15), (37, 128)])
+def test_batchnorm_train_fwd_bwd(act, N, Cc, cuda_dev):
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(N + Cc + act)
+    x = (torch.randn(N, Cc, generator=g) * 2 + 0.5).to(cuda_dev).requires_grad_(True)
+    gamma = (torch.rand(Cc, generator=g) + 0.5).to(cuda_dev).requires_grad_(True)
+    beta = torch.randn(Cc, generator=g).to(cuda_dev).requires_grad_(True)
+    rm, rv = torch.randn(Cc, generator=g).to(cuda_dev), (torch.rand(Cc, generator=g) + 0.5).to(cuda_dev)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y_ref = _act(F.batch_norm(x, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5), act)
+    dy = torch.randn(N, Cc, generator=g).to(cuda_dev)
+    y_ref.backward(dy)
+    ld = Cc + 4
+    xb = torch.zeros(N, ld, device=cuda_dev); xb[:, :Cc] = x.detach()
+    y = torch.zeros(N, ld, device=cuda_dev)
+    sm, si = torch.empty(Cc, device=cuda_dev), torch.empty(Cc, device=cuda_dev)
+    ws = torch.empty(2 * Cc, device=cuda_dev, dtype=torch.float64)
+    _lib.check(lib.yad_bn_train_fwd(xb.data_ptr(), ld, N, Cc, gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1, rm.data_ptr(), rv.data_ptr(),
+                                    act, y.data_ptr(), ld, sm.data_ptr(), si.data_ptr(), ws.data_ptr(), _stream()), "bn fwd")
+    dx = torch.zeros(N, ld, device=cuda_dev)
+    dg, dbt = torch.ones(Cc, device=cuda_dev), torch.ones(Cc, device=cuda_dev)        # accumulate onto ones
+    dyb = torch.zeros(N, ld, device=cuda_dev); dyb[:, :Cc] = dy
+    _lib.check(lib.yad_bn_train_bwd(xb.data_ptr(), ld, y.data_ptr(), ld, dyb.data_ptr(), ld, N, Cc, gamma.data_ptr(), sm.data_ptr(),
+                                    si.data_ptr(), act, dx.data_ptr(), ld, dg.data_ptr(), dbt.data_ptr(), ws.data_ptr(), _stream()), "bn bwd")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y[:, :Cc].cpu().numpy(), y_ref.detach().cpu().numpy(), atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(rm.cpu().numpy(), rm_ref.cpu().numpy(), atol=1e-6, rtol=1e-5)
+    np.testing.assert_allclose(rv.cpu().numpy(), rv_ref.cpu().numpy(), atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(dx[:, :Cc].cpu().numpy(), x.grad.cpu().numpy(), atol=2e-5, rtol=2e-4)
+    np.testing.assert_allclose((dg - 1).cpu().numpy(), gamma.grad.cpu().numpy(), atol=2e-3, rtol=2e-4)
+    np.testing.assert_allclose((dbt - 1).cpu().numpy(), beta.grad.cpu().numpy(), atol=2e-3, rtol=2e-4)
+
+
+def test_add_act_and_glue_backward(cuda_dev):
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cc = 3, 4, 12, 64
+    # act(a + b + c)
+    a, b, c = [torch.randn(B * W, Cc, generator=g).to(cuda_dev).requires_grad_(True) for _ in range(3)]
+    y_ref = F.leaky_relu(a + b + c, 0.2)
+    dy = torch.randn(B * W, Cc, generator=g).to(cuda_dev)
+    y_ref.backward(dy)
+    y = torch.empty(B * W, Cc, device=cuda_dev)
+    _lib.check(lib.yad_add_act(a.data_ptr(), Cc, b.data_ptr(), Cc, c.data_ptr(), Cc, B * W, Cc, ACT_LRELU, y.data_ptr(), Cc, _stream()), "add")
+    da, db, dc = [torch.zeros(B * W, Cc, device=cuda_dev) for _ in range(3)]
+    _lib.check(lib.yad_add_act_bwd(y.data_ptr(), Cc, dy.data_ptr(), Cc, B * W, Cc, ACT_LRELU, da.data_ptr(), Cc, db.data_ptr(), Cc,
+                                   dc.data_ptr(), Cc, _stream()), "add bwd")
+    np.testing.assert_allclose(y.cpu().numpy(), y_ref.detach().cpu().numpy(), atol=1e-6)
+    for got, ref in ((da, a), (db, b), (dc, c)):
+        np.testing.assert_allclose(got.cpu().numpy(), ref.grad.cpu().numpy(), atol=1e-6)
+    # H-mean
+    x = torch.randn(B, Cc, H, W, generator=g).to(cuda_dev).requires_grad_(True)
+    F.adaptive_avg_pool2d(x, (1, W)).backward(dyo := torch.randn(B, Cc, 1, W, generator=g).to(cuda_dev))
+    din = torch.zeros(B, H, W, Cc, device=cuda_dev)
+    do = dyo.permute(0, 2, 3, 1).contiguous()
+    _lib.check(lib.yad_hmean_bwd(do.data_ptr(), Cc, B, H, W, Cc, din.data_ptr(), Cc, _stream()), "hmean bwd")
+    np.testing.assert_allclose(din.permute(0, 3, 1, 2).cpu().numpy(), x.grad.cpu().numpy(), atol=1e-6)
+    # bilinear x2 / x0.5 along W
+    for up, sf in ((1, (1, 2)), (0, (1, 0.5))):
+        x = torch.randn(B, Cc, 1, W, generator=g).to(cuda_dev).requires_grad_(True)
+        yr = F.interpolate(x, scale_factor=sf, mode="bilinear")
+        dyo = torch.randn(yr.shape, generator=g).to(cuda_dev)
+        yr.backward(dyo)
+        din = torch.zeros(B, 1, W, Cc, device=cuda_dev)
+        do = dyo.permute(0, 2, 3, 1).contiguous()
+        _lib.check(lib.yad_resize_w_bwd(do.data_ptr(), Cc, B, W, Cc, up, din.data_ptr(), Cc, _stream()), "resize bwd")
+        np.testing.assert_allclose(din.permute(0, 3, 1, 2).cpu().numpy(), x.grad.cpu().numpy(), atol=1e-6)
+    # MaxPool(5,1,2) along W
+    x = torch.randn(B, Cc, 1, W, generator=g).to(cuda_dev).requires_grad_(True)
+    yr = F.max_pool2d(x, kernel_size=5, stride=1, padding=2)
+    dyo = torch.randn(yr.shape, generator=g).to(cuda_dev)
+    yr.backward(dyo)
+    xh = x.detach().permute(0, 2, 3, 1).contiguous()
+    yh = torch.empty_like(xh)
+    _lib.check(lib.yad_maxpool5_w(xh.data_ptr(), Cc, B, W, Cc, yh.data_ptr(), Cc, _stream()), "maxpool")
+    dxh = torch.zeros_like(xh)
+    do = dyo.permute(0, 2, 3, 1).contiguous()
+    _lib.check(lib.yad_maxpool5_w_bwd(xh.data_ptr(), Cc, do.data_ptr(), Cc, B, W, Cc, dxh.data_ptr(), Cc, _stream()), "maxpool bwd")
+    np.testing.assert_allclose(yh.permute(0, 3, 1, 2).cpu().numpy(), yr.detach().cpu().numpy(), atol=0)
+    np.testing.assert_allclose(dxh.permute(0, 3, 1, 2).cpu().numpy(), x.grad.cpu().numpy(), atol=1e-6)
+
+
+def test_dropout_mask(cuda_dev):
+    lib = _lib.init(0)
+    n = 1 << 20
+    x = torch.ones(n, device=cuda_dev)
+    y = torch.empty(n, device=cuda_dev)
+    _lib.check(lib.yad_dropout(x.data_ptr(), n, 0.4, 1234, 0, y.data_ptr(), _stream()), "dropout")
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - 0.6) < 3e-3 and torch.all((y == 0) | ((y - 1 / 0.6).abs() < 1e-6))
+    y2 = torch.zeros(n, device=cuda_dev)
+    _lib.check(lib.yad_dropout(x.data_ptr(), n, 0.4, 1234, 1, y2.data_ptr(), _stream()), "dropout")     # same seed -> same mask
+    assert torch.equal(y, y2)
+    _lib.check(lib.yad_dropout(x.data_ptr(), n, 0.0, 7, 0, y.data_ptr(), _stream()), "dropout p=0")
+    assert torch.all(y == 1)
+
+
+def test_decode_backward(cuda_dev):
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(9)
+    B, G, A, nc = 3, 12, 3, 2
+    E = 3 + nc
+    with torch.enable_grad():
+        head = (torch.randn(B, G, A * E, generator=g) * 2).requires_grad_(True)
+        anc = torch.tensor([0.02, 0.05, 0.4]).requires_grad_(True)
+        pred = O.decode_scale(head, anc * 60.0, 96000, 96, nc)          # 6 s clips: 96 frames
+        dp = torch.randn(pred.shape, generator=g)
+        pred.backward(dp)
+    ld = 16
+    hb = torch.zeros(B, G, ld, device=cuda_dev); hb[..., : A * E] = head.detach().to(cuda_dev)
+    dh = torch.zeros(B, G, ld, device=cuda_dev)
+    da = torch.zeros(A, device=cuda_dev)
+    anc_s = (anc.detach() * 60.0).to(cuda_dev)
+    stride_over_scaler = (96 // G) / (96 / (96000 / 16000))
+    _lib.check(lib.yad_decode_bwd(hb.data_ptr(), ld, dp.to(cuda_dev).contiguous().data_ptr(), B, G, A, nc, anc_s.data_ptr(),
+                                  stride_over_scaler, 60.0, dh.data_ptr(), ld, da.data_ptr(), _stream()), "decode bwd")
+    np.testing.assert_allclose(dh[..., : A * E].cpu().numpy(), head.grad.numpy(), atol=1e-5, rtol=1e-4)
+    np.testing.assert_allclose((da * 60.0).cpu().numpy(), anc.grad.numpy(), atol=1e-4, rtol=1e-4)

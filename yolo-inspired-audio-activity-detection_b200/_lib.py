@@ -57,6 +57,18 @@ SIGNATURES = {
     "yad_compact_segments": [_p, _p, _i64, _i32, _p, _p, _p, _p],
     "yad_build_targets": [_p, _i32, _p, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p],
     "yad_loss_scale": [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _f32, _f32, _f32, _f32, _i64, _p, _p, _p, _p, _p, _p],
+    "yad_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "yad_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "yad_bn_train_fwd": [_p, _i32, _i64, _i32, _p, _p, _f32, _f32, _p, _p, _i32, _p, _i32, _p, _p, _p, _p],
+    "yad_bn_train_bwd": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p],
+    "yad_add_act": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p],
+    "yad_add_act_bwd": [_p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _i32, _p, _i32, _p],
+    "yad_dropout": [_p, _i64, _f32, C.c_uint64, _i32, _p, _p],
+    "yad_hmean_bwd": [_p, _i32, _i64, _i32, _i32, _i32, _p, _i32, _p],
+    "yad_resize_w_bwd": [_p, _i32, _i64, _i32, _i32, _i32, _p, _i32, _p],
+    "yad_maxpool5_w": [_p, _i32, _i64, _i32, _i32, _p, _i32, _p],
+    "yad_maxpool5_w_bwd": [_p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p],
+    "yad_decode_bwd": [_p, _i32, _p, _i64, _i32, _i32, _i32, _p, _f32, _f32, _p, _i32, _p, _p],
     "yad_adam_ema_step": [_p, _p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _p],
 }
 EXPORTS = ["yad_version", "yad_last_error"] + list(SIGNATURES)

@@ -66,7 +66,12 @@ conv_stem_kernel(const float* __restrict__ x, int H, int W, const float* __restr
 // ------------------------------------------------------------------------------------ generic
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
 
-template <typename T>
+// DGRAD = false: out[b,ho,wo,:] = sum_taps in[b, ho*s + k - p, ...] W[tap]           (d.H, d.W = input size, Ho, Wo = output size)
+// DGRAD = true : the data gradient of that conv in gather form.  `in` is dY [B, d.H, d.W, d.Cin] (d.H, d.W, d.Cin hold the
+//                FORWARD output size / channels), `out` is dX [B, Ho, Wo, d.Cout] (Ho, Wo, d.Cout = forward input size /
+//                channels), wgt is [kh][kw][Cout_fwd][Cin_fwd]; pixel (hi, wi) of dX receives tap (kh, kw) from
+//                dY[(hi + p - kh) / s] when that division is exact and in range.
+template <typename T, bool DGRAD>
 __global__ void __launch_bounds__(SG_THREADS)
 conv_simt_kernel(const yad_conv_desc d, int Ho, int Wo, const T* __restrict__ in, const T* __restrict__ wgt, int ld_w,
                  const float* __restrict__ bias, const T* __restrict__ res, T* __restrict__ out) {
@@ -98,8 +103,18 @@ conv_simt_kernel(const yad_conv_desc d, int Ho, int Wo, const T* __restrict__ in
 
   for (int kh = 0; kh < d.kh; ++kh) {
     for (int kw = 0; kw < d.kw; ++kw) {
-      const int hi = aho * d.sh + kh - d.ph, wi = awo * d.sw + kw - d.pw;
-      const bool pix_ok = a_ok && hi >= 0 && hi < d.H && wi >= 0 && wi < d.W;
+      int hi, wi;
+      bool pix_ok;
+      if (DGRAD) {
+        const int th = aho + d.ph - kh, tw = awo + d.pw - kw;
+        hi = th / d.sh;
+        wi = tw / d.sw;
+        pix_ok = a_ok && th >= 0 && tw >= 0 && hi * d.sh == th && wi * d.sw == tw && hi < d.H && wi < d.W;
+      } else {
+        hi = aho * d.sh + kh - d.ph;
+        wi = awo * d.sw + kw - d.pw;
+        pix_ok = a_ok && hi >= 0 && hi < d.H && wi >= 0 && wi < d.W;
+      }
       const T* ap = in + (((int64_t)ab * d.H + hi) * d.W + wi) * d.ld_in;
       const T* wp = wgt + (int64_t)(kh * d.kw + kw) * d.Cin * ld_w;
       for (int c0 = 0; c0 < d.Cin; c0 += SG_BK) {
@@ -141,7 +156,7 @@ conv_simt_kernel(const yad_conv_desc d, int Ho, int Wo, const T* __restrict__ in
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= d.Cout) continue;
-      float v = acc[i][j] + bias[n];
+      float v = acc[i][j] + (bias != nullptr ? bias[n] : 0.0f);
       if (res != nullptr) v += ld_as_float(res + m * d.ld_res + n);
       v = apply_act(v, d.act);
       st_from_float(out + m * d.ld_out + d.co_off + n, v);
@@ -172,7 +187,7 @@ int yad_conv_stem(const float* x_nchw, int64_t B, int32_t H, int32_t W, const fl
 
 int yad_conv_simt(const yad_conv_desc* d, int32_t dtype, const void* in, const void* weight, int32_t ld_w,
                   const float* bias, const void* residual, void* out, yad_stream_t stream) {
-  YAD_CHECK_ARG(d && in && weight && bias && out, "yad_conv_simt: null pointer");
+  YAD_CHECK_ARG(d && in && weight && out, "yad_conv_simt: null pointer");
   YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_conv_simt: bad dtype %d", dtype);
   YAD_CHECK_ARG(d->Cin >= 1 && d->ld_in >= d->Cin && d->Cout >= 1 && ld_w >= d->Cout && d->ld_out >= d->co_off + d->Cout,
                 "yad_conv_simt: inconsistent channel counts");
@@ -185,12 +200,40 @@ int yad_conv_simt(const yad_conv_desc* d, int32_t dtype, const void* in, const v
   const int64_t M = (int64_t)d->B * Ho * Wo;
   dim3 grid((unsigned)((M + yad::SG_BM - 1) / yad::SG_BM), (unsigned)((d->Cout + yad::SG_BN - 1) / yad::SG_BN));
   if (dtype == YAD_F32)
-    yad::conv_simt_kernel<float><<<grid, yad::SG_THREADS, 0, (cudaStream_t)stream>>>(
+    yad::conv_simt_kernel<float, false><<<grid, yad::SG_THREADS, 0, (cudaStream_t)stream>>>(
         *d, Ho, Wo, (const float*)in, (const float*)weight, ld_w, bias, (const float*)residual, (float*)out);
   else
-    yad::conv_simt_kernel<__nv_bfloat16><<<grid, yad::SG_THREADS, 0, (cudaStream_t)stream>>>(
+    yad::conv_simt_kernel<__nv_bfloat16, false><<<grid, yad::SG_THREADS, 0, (cudaStream_t)stream>>>(
         *d, Ho, Wo, (const __nv_bfloat16*)in, (const __nv_bfloat16*)weight, ld_w, bias,
         (const __nv_bfloat16*)residual, (__nv_bfloat16*)out);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_conv_dgrad(const yad_conv_desc* d, const float* dy, const float* weight_t, const float* dx_in, float* dx,
+                   yad_stream_t stream) {
+  YAD_CHECK_ARG(d && dy && weight_t && dx, "yad_conv_dgrad: null pointer");
+  YAD_CHECK_ARG(d->sh >= 1 && d->sw >= 1 && d->kh >= 1 && d->kw >= 1 && d->Cin >= 1 && d->Cout >= 1, "yad_conv_dgrad: bad descriptor");
+  const int Ho = (d->H + 2 * d->ph - d->kh) / d->sh + 1;
+  const int Wo = (d->W + 2 * d->pw - d->kw) / d->sw + 1;
+  YAD_CHECK_ARG(Ho >= 1 && Wo >= 1, "yad_conv_dgrad: empty output");
+  YAD_CHECK_ARG(d->ld_in >= d->Cin && d->ld_out >= d->co_off + d->Cout, "yad_conv_dgrad: bad pitches");
+  if (d->B == 0) return YAD_OK;
+  // the kernel's view: "input" = dY [B, Ho, Wo, Cout] (pitch ld_out, channel slice co_off), "output" = dX [B, H, W, Cin]
+  yad_conv_desc k = *d;
+  k.H = Ho;
+  k.W = Wo;
+  k.Cin = d->Cout;
+  k.ld_in = d->ld_out;
+  k.Cout = d->Cin;
+  k.ld_out = d->ld_in;
+  k.co_off = 0;
+  k.act = YAD_ACT_NONE;
+  k.ld_res = dx_in != nullptr ? d->ld_in : 0;
+  const int64_t M = (int64_t)d->B * d->H * d->W;
+  dim3 grid((unsigned)((M + yad::SG_BM - 1) / yad::SG_BM), (unsigned)((d->Cin + yad::SG_BN - 1) / yad::SG_BN));
+  yad::conv_simt_kernel<float, true><<<grid, yad::SG_THREADS, 0, (cudaStream_t)stream>>>(
+      k, d->H, d->W, dy + d->co_off, weight_t, d->Cin, nullptr, dx_in, dx);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }
