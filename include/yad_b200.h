@@ -258,11 +258,11 @@ int yad_conv_wgrad(const yad_conv_desc* d, const float* x, const float* dy, floa
 int yad_bn_train_fwd(const float* x, int32_t ld_x, int64_t N, int32_t C, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, int32_t act, float* y, int32_t ld_y,
                      float* save_mean, float* save_invstd, double* ws, yad_stream_t stream);
-/* Its backward, the activation's included: g = dy * act'(y); dx (overwritten) = gamma * invstd * (g - mean(g) - xhat * mean(g xhat));
+/* Its backward, the activation's included: g = dy * act'(y); dx (overwritten, or += when accumulate) = gamma * invstd * (g - mean(g) - xhat * mean(g xhat));
  * dgamma += sum g xhat; dbeta += sum g. */
 int yad_bn_train_bwd(const float* x, int32_t ld_x, const float* y, int32_t ld_y, const float* dy, int32_t ld_dy, int64_t N, int32_t C,
                      const float* gamma, const float* save_mean, const float* save_invstd, int32_t act, float* dx, int32_t ld_dx,
-                     float* dgamma, float* dbeta, double* ws, yad_stream_t stream);
+                     int32_t accumulate, float* dgamma, float* dbeta, double* ws, yad_stream_t stream);
 /* y = act(a + b [+ c]) and its backward (g = dy * act'(y) ACCUMULATED into da, db, dc; any of them may be NULL). */
 int yad_add_act(const float* a, int32_t ld_a, const float* b, int32_t ld_b, const float* c, int32_t ld_c, int64_t N, int32_t C,
                 int32_t act, float* y, int32_t ld_y, yad_stream_t stream);
@@ -284,6 +284,12 @@ int yad_maxpool5_w_bwd(const float* x, int32_t ld_x, const float* dy, int32_t ld
 int yad_decode_bwd(const float* head, int32_t ld_h, const float* dpred, int64_t B, int32_t G, int32_t A, int32_t nc,
                    const float* anchors_s, float stride_over_scaler, float duration, float* dhead, int32_t ld_dh, float* danchor_s,
                    yad_stream_t stream);
+
+/* out (dense, row-major over sizes[4]) (+)= in[sum_k i_k * in_strides[k]] (element strides): weight re-packing between the
+ * OIHW master layout and the kernels' layouts, NCHW -> NHWC, gradient un-packing.  yad_add_f64_to_f32: out[i] += (float)a[i]. */
+int yad_permute4(const float* in, const int64_t* in_strides, float* out, const int32_t* sizes, int32_t accumulate,
+                 yad_stream_t stream);
+int yad_add_f64_to_f32(const double* a, int32_t n, float* out, yad_stream_t stream);
 
 /* Fused Adam (L2 weight decay) + EMA over a flat fp32 parameter arena:
  * torch.optim.Adam (train.py:83-90, config.yaml:75-80) and smoothener/_ema.py:20-26.

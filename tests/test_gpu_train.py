@@ -91,7 +91,7 @@ def test_batchnorm_train_fwd_bwd(act, N, Cc, cuda_dev):
     dg, dbt = torch.ones(Cc, device=cuda_dev), torch.ones(Cc, device=cuda_dev)        # accumulate onto ones
     dyb = torch.zeros(N, ld, device=cuda_dev); dyb[:, :Cc] = dy
     _lib.check(lib.yad_bn_train_bwd(xb.data_ptr(), ld, y.data_ptr(), ld, dyb.data_ptr(), ld, N, Cc, gamma.data_ptr(), sm.data_ptr(),
-                                    si.data_ptr(), act, dx.data_ptr(), ld, dg.data_ptr(), dbt.data_ptr(), ws.data_ptr(), _stream()), "bn bwd")
+                                    si.data_ptr(), act, dx.data_ptr(), ld, 0, dg.data_ptr(), dbt.data_ptr(), ws.data_ptr(), _stream()), "bn bwd")
     torch.cuda.synchronize()
     np.testing.assert_allclose(y[:, :Cc].cpu().numpy(), y_ref.detach().cpu().numpy(), atol=2e-5, rtol=1e-5)
     np.testing.assert_allclose(rm.cpu().numpy(), rm_ref.cpu().numpy(), atol=1e-6, rtol=1e-5)

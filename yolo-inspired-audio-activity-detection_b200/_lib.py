@@ -60,7 +60,9 @@ SIGNATURES = {
     "yad_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "yad_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "yad_bn_train_fwd": [_p, _i32, _i64, _i32, _p, _p, _f32, _f32, _p, _p, _i32, _p, _i32, _p, _p, _p, _p],
-    "yad_bn_train_bwd": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p],
+    "yad_bn_train_bwd": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p, _p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p],
+    "yad_permute4": [_p, C.POINTER(_i64), _p, C.POINTER(_i32), _i32, _p],
+    "yad_add_f64_to_f32": [_p, _i32, _p, _p],
     "yad_add_act": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p],
     "yad_add_act_bwd": [_p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _i32, _p, _i32, _p],
     "yad_dropout": [_p, _i64, _f32, C.c_uint64, _i32, _p, _p],

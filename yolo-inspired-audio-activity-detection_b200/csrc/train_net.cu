@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(TN_THREADS)
 bn_bwd_apply_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ y, int ld_y, const float* __restrict__ dy,
                     int ld_dy, int64_t N, int C, const float* __restrict__ gamma, const float* __restrict__ mean,
                     const float* __restrict__ invstd, int act, const double* __restrict__ sum_g, const double* __restrict__ sum_gx,
-                    float* __restrict__ dx, int ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    float* __restrict__ dx, int ld_dx, int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int64_t n = N * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -177,7 +177,8 @@ bn_bwd_apply_kernel(const float* __restrict__ x, int ld_x, const float* __restri
     const float g = dy[r * ld_dy + c] * act_grad(y[r * ld_y + c], act);
     const float xh = (x[r * ld_x + c] - mean[c]) * invstd[c];
     const float sg = (float)(sum_g[c] / (double)N), sgx = (float)(sum_gx[c] / (double)N);
-    dx[r * ld_dx + c] = gamma[c] * invstd[c] * (g - sg - xh * sgx);
+    const float v = gamma[c] * invstd[c] * (g - sg - xh * sgx);
+    dx[r * ld_dx + c] = accumulate ? dx[r * ld_dx + c] + v : v;
     if (r == 0) {
       dgamma[c] += (float)sum_gx[c];
       dbeta[c] += (float)sum_g[c];
@@ -335,6 +336,32 @@ decode_bwd_kernel(const float* __restrict__ head, int ld_h, const float* __restr
   }
 }
 
+// out (dense, row-major over sizes[4]) (+)= in[sum_k i_k * in_stride_k]: weight re-packing, NCHW <-> NHWC, gradient un-packing
+struct Perm4 {
+  int32_t n[4];
+  int64_t s[4];
+};
+__global__ void __launch_bounds__(TN_THREADS)
+permute4_kernel(const float* __restrict__ in, const Perm4 p, int accumulate, float* __restrict__ out) {
+  const int64_t total = (int64_t)p.n[0] * p.n[1] * p.n[2] * p.n[3];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int i3 = (int)(r % p.n[3]);
+    r /= p.n[3];
+    const int i2 = (int)(r % p.n[2]);
+    r /= p.n[2];
+    const int i1 = (int)(r % p.n[1]);
+    const int i0 = (int)(r / p.n[1]);
+    const float v = in[i0 * p.s[0] + i1 * p.s[1] + i2 * p.s[2] + i3 * p.s[3]];
+    out[i] = accumulate ? out[i] + v : v;
+  }
+}
+// fp64 accumulator -> fp32 parameter gradient (+=)
+__global__ void add_f64_to_f32_kernel(const double* __restrict__ a, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += (float)a[i];
+}
+
 static inline unsigned ew_blocks(int64_t n) {
   int64_t b = (n + TN_THREADS - 1) / TN_THREADS;
   const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 16;
@@ -389,7 +416,7 @@ int yad_bn_train_fwd(const float* x, int32_t ld_x, int64_t N, int32_t C, const f
 
 int yad_bn_train_bwd(const float* x, int32_t ld_x, const float* y, int32_t ld_y, const float* dy, int32_t ld_dy, int64_t N, int32_t C,
                      const float* gamma, const float* save_mean, const float* save_invstd, int32_t act, float* dx, int32_t ld_dx,
-                     float* dgamma, float* dbeta, double* ws /* [2*C] */, yad_stream_t stream) {
+                     int32_t accumulate, float* dgamma, float* dbeta, double* ws /* [2*C] */, yad_stream_t stream) {
   using namespace yad;
   YAD_CHECK_ARG(x && y && dy && gamma && save_mean && save_invstd && dx && dgamma && dbeta && ws && N >= 1 && C >= 1,
                 "yad_bn_train_bwd: bad arguments");
@@ -399,7 +426,7 @@ int yad_bn_train_bwd(const float* x, int32_t ld_x, const float* y, int32_t ld_y,
   col_reduce_kernel<1><<<g, TN_THREADS, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, N, C, save_mean, save_invstd, act, ws, ws + C);
   YAD_LAUNCH_CHECK();
   bn_bwd_apply_kernel<<<ew_blocks(N * C), TN_THREADS, 0, st>>>(x, ld_x, y, ld_y, dy, ld_dy, N, C, gamma, save_mean, save_invstd, act, ws,
-                                                              ws + C, dx, ld_dx, dgamma, dbeta);
+                                                              ws + C, dx, ld_dx, accumulate, dgamma, dbeta);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }
@@ -481,6 +508,31 @@ int yad_decode_bwd(const float* head, int32_t ld_h, const float* dpred, int64_t 
   if (B == 0) return YAD_OK;
   decode_bwd_kernel<<<ew_blocks(B * G * A), TN_THREADS, 0, (cudaStream_t)stream>>>(head, ld_h, dpred, B, G, A, 3 + nc, anchors_s,
                                                                                   stride_over_scaler, duration, dhead, ld_dh, danchor_s);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_permute4(const float* in, const int64_t* in_strides, float* out, const int32_t* sizes, int32_t accumulate,
+                 yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(in && in_strides && out && sizes, "yad_permute4: null pointer");
+  Perm4 p;
+  int64_t total = 1;
+  for (int k = 0; k < 4; ++k) {
+    YAD_CHECK_ARG(sizes[k] >= 1, "yad_permute4: bad size");
+    p.n[k] = sizes[k];
+    p.s[k] = in_strides[k];
+    total *= sizes[k];
+  }
+  permute4_kernel<<<ew_blocks(total), TN_THREADS, 0, (cudaStream_t)stream>>>(in, p, accumulate, out);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_add_f64_to_f32(const double* a, int32_t n, float* out, yad_stream_t stream) {
+  YAD_CHECK_ARG(a && out && n >= 0, "yad_add_f64_to_f32: bad arguments");
+  if (n == 0) return YAD_OK;
+  yad::add_f64_to_f32_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, n, out);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }
