@@ -218,9 +218,12 @@ def frontend(x: Tensor, consts: Dict[str, Tensor], config: Dict = DEFAULT_CONFIG
 # --------------------------------------------------------------------------
 # CNN (ref: modules/_backbone.py:119-152, modules/_common.py, [tv] models/resnet.py:59-105)
 # --------------------------------------------------------------------------
+_BN_TRAINING = [False]     # set by forward_train: BatchNorm2d in train() mode (batch statistics, running stats updated in place)
+
+
 def _bn(sd: Dict[str, Tensor], p: str, x: Tensor) -> Tensor:
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"],
-                        sd[p + ".bias"], False, 0.1, 1e-5)
+                        sd[p + ".bias"], _BN_TRAINING[0], 0.1, 1e-5)
 
 
 def _cbl(sd, p, x, stride=1, act=True):
@@ -399,6 +402,20 @@ def forward(x: Tensor, sd: Dict[str, Tensor], num_classes: int, config: Dict = D
         taps["fmaps"] = fmaps
         taps["heads"] = heads
     return decode(heads, sd, fe["resampled"].shape[-1], xs.shape[-1], num_classes, config, combine_scales)
+
+
+def forward_train(x: Tensor, sd: Dict[str, Tensor], num_classes: int, config: Dict = DEFAULT_CONFIG):
+    """AudioDetectionNetwork.forward in train() mode with dropout = 0 (ref: modules/_architecture.py:78-130 as driven by
+    pipeline/_trainer.py:98-104): every BatchNorm2d normalises with the batch statistics and updates ``sd``'s running
+    statistics in place (momentum 0.1, unbiased variance).  Differentiable (torch autograd) with respect to every
+    floating-point entry of ``sd`` that requires grad.  Returns the three per-scale prediction tensors."""
+    if config.get("dropout", 0):
+        raise ValueError("the oracle's train-mode forward is deterministic: set dropout to 0")
+    _BN_TRAINING[0] = True
+    try:
+        return forward(x, sd, num_classes, config, combine_scales=False)
+    finally:
+        _BN_TRAINING[0] = False
 
 
 # --------------------------------------------------------------------------

@@ -186,3 +186,128 @@ def test_decode_backward(cuda_dev):
                                   stride_over_scaler, 60.0, dh.data_ptr(), ld, da.data_ptr(), _stream()), "decode bwd")
     np.testing.assert_allclose(dh[..., : A * E].cpu().numpy(), head.grad.numpy(), atol=1e-5, rtol=1e-4)
     np.testing.assert_allclose((da * 60.0).cpu().numpy(), anc.grad.numpy(), atol=1e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------ the train-mode network (rows a1 / a17)
+def _train_model(ref_state_dict, cuda_dev, dropout=0.0):
+    cfg = yad_b200.default_config()
+    cfg["dropout"] = dropout
+    m = yad_b200.AudioDetectionNetwork(2, config=cfg)
+    m.load_state_dict(ref_state_dict)
+    return m.to(cuda_dev).train()
+
+
+def _loss_fn():
+    cfg = yad_b200.default_config()
+    return yad_b200.AudioDetectionLoss(cfg["anchors"], 2, sample_duration=60, **cfg["train_config"]["loss_config"])
+
+
+def _rel_l2(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a - b).norm() / max(float(b.norm()), 1e-12))
+
+
+def test_train_network_forward_backward_vs_oracle_and_reference(gold, ref_state_dict, cuda_dev):
+    """Train-mode CNN + decode on the oracle's own x_spectral (so that the ill-conditioned MFCC-dB channel of the frontend
+    does not blur the comparison): predictions, loss, the gradient of EVERY parameter and the BatchNorm running statistics
+    against (1) the oracle's autograd in fp64 on the CPU and (2) what the live reference produced in fp32 (train_net.npz).
+
+    Gradient tolerance: with 2 clips the batch statistics of the coarse layers come from 16-64 rows, and ReLU / max-pool
+    decisions that sit within rounding of a tie flip between any two fp32 implementations; the reference's OWN fp32
+    gradients differ from the fp64 ones by 6e-5 (neck, layer4) rising to 7e-3 (layer1, the stem) on this fixture, and so do
+    ours (tools/diag_train_grads.py prints both columns).  Hence: relative L2 error < 3e-2 for every parameter (a wrong
+    kernel gives O(1)), < 5e-4 for everything that back-propagates before the first such flip (neck + layer4)."""
+    import train_helpers as TH
+    from yad_b200.train_engine import run_train_forward
+    g = gold("train_net")
+    x, tg = TH.train_inputs()
+    preds_o, loss_o, grads_o, sd_o, xs = TH.oracle_train_step(ref_state_dict, x, tg, dtype=torch.float64)
+    m = _train_model(ref_state_dict, cuda_dev)
+    L_res = -(-320 * x.shape[-1] // 441)
+    with torch.enable_grad():
+        preds = run_train_forward(m, m._train_engine(), xs.to(cuda_dev).contiguous(), xs.shape[-1], L_res)
+        loss, _ = _loss_fn()(preds, tg.to(cuda_dev))
+        loss.backward()
+    torch.cuda.synchronize()
+    for i in range(3):
+        np.testing.assert_allclose(preds[i].detach().cpu().numpy(), preds_o[i].numpy(), atol=1e-3, rtol=1e-4)
+        np.testing.assert_allclose(preds[i].detach().cpu().numpy(), g[f"pred{i}"], atol=1e-3, rtol=1e-4)
+    np.testing.assert_allclose(float(loss), float(loss_o), rtol=2e-5)
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=2e-5)
+    params = dict(m.named_parameters())
+    assert sorted(params) == sorted(grads_o)
+    ref_stats = {str(n): s for n, s in zip(g["grad_names"], g["grad_stats"])}
+    worst = ("", 0.0)
+    for k, p in params.items():
+        assert p.grad is not None, k
+        go = grads_o[k]
+        scale = float(go.norm())
+        if scale < 1e-9:      # conv biases in front of a batch-statistics BatchNorm (exactly zero gradient), unmatched anchors
+            assert float(p.grad.double().norm()) < 1e-4, k
+            continue
+        r = _rel_l2(p.grad.cpu(), go)
+        worst = max(worst, (k, r), key=lambda t: t[1])
+        tight = k.startswith("multiscale_module.") or ".layer4." in k or k.endswith("_anchors")
+        assert r < (5e-4 if tight else 3e-2), (k, r)
+        np.testing.assert_allclose(TH.grad_stats(p.grad)[1], ref_stats[k][1], rtol=1e-3 if tight else 3e-2, err_msg=k)   # live reference
+    for k in [k for k in g if k.startswith("grad:")]:
+        tight = k[5:].startswith("multiscale_module.") or k.endswith("_anchors")
+        if np.abs(g[k]).max() < 1e-6:       # zero-gradient parameter: the reference holds rounding noise, checked above
+            continue
+        np.testing.assert_allclose(params[k[5:]].grad.cpu().numpy(), g[k], rtol=5e-3,
+                                   atol=(1e-3 if tight else 5e-2) * np.abs(g[k]).max(), err_msg=k)
+    sd = m.state_dict()
+    for k in [k[3:] for k in g if k.startswith("rm:")]:
+        np.testing.assert_allclose(sd[k + ".running_mean"].cpu().numpy(), g["rm:" + k], atol=2e-6)
+        np.testing.assert_allclose(sd[k + ".running_var"].cpu().numpy(), g["rv:" + k], rtol=2e-5)
+        assert int(sd[k + ".num_batches_tracked"]) == int(g["nbt:" + k]) == 1
+    print("worst relative gradient error:", worst)
+
+
+def test_train_forward_end_to_end_and_eval_after(gold, ref_state_dict, cuda_dev):
+    """model.train(); model(x) from PCM through the GPU frontend: loss within 2e-3 of the reference's; no_grad works;
+    eval() afterwards uses the updated running statistics (engine re-packs)."""
+    import train_helpers as TH
+    g = gold("train_net")
+    x, tg = TH.train_inputs()
+    m = _train_model(ref_state_dict, cuda_dev)
+    xd = x.to(cuda_dev)
+    with torch.no_grad():
+        p0 = m(xd, combine_scales=True)
+    assert p0.shape == (2, (32 + 16 + 8) * 3, 5) and not p0.requires_grad
+    m.load_state_dict(ref_state_dict)
+    with torch.enable_grad():
+        preds = m(xd)
+        loss, met = _loss_fn()(preds, tg.to(cuda_dev))
+        loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-3 * float(g["loss"])
+    assert set(met) >= {"aggregate_loss", "mean_ciou", "conf_loss", "class_loss", "f1"}
+    rm_before = ref_state_dict["feature_extractor.bn1.running_mean"]
+    assert not torch.allclose(m.feature_extractor.bn1.running_mean.cpu(), rm_before)
+    m.eval()
+    with torch.no_grad():
+        pe = m(xd, combine_scales=True)
+    assert torch.isfinite(pe).all()
+
+
+def test_train_steps_reduce_loss_with_dropout(ref_state_dict, cuda_dev):
+    """Five fused Adam + EMA steps on one batch (dropout 0.4 as in config.yaml): the loss goes down, gradients live in the
+    flat arena, the EMA shadow moves."""
+    import train_helpers as TH
+    x, tg = TH.train_inputs()
+    m = _train_model(ref_state_dict, cuda_dev, dropout=0.4)
+    opt = yad_b200.FusedAdamEMA(m.parameters(), lr=1e-3, weight_decay=0.002, ema_momentum=0.002, use_ema=True)
+    loss_fn = _loss_fn()
+    xd, tgd = x.to(cuda_dev), tg.to(cuda_dev)
+    losses = []
+    ema0 = opt.ema.clone()
+    for _ in range(5):
+        with torch.enable_grad():
+            loss, _ = loss_fn(m(xd), tgd)
+            loss.backward()
+        assert float(opt.grad.abs().sum()) > 0
+        opt.step()
+        opt.zero_grad()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
+    assert not torch.equal(ema0, opt.ema)

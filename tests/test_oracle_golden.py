@@ -146,3 +146,28 @@ def test_adam_and_ema(gold):
         O.ema_update([ema], [w], step)
     np.testing.assert_allclose(w.numpy(), g["adam_w3"], atol=1e-6)
     np.testing.assert_allclose(ema.numpy(), g["ema3"], atol=1e-6)
+
+
+def test_train_mode_forward_backward_vs_live_reference(gold, ref_state_dict):
+    """Oracle train-mode network (batch-statistics BatchNorm) + loss + autograd == what the live reference produced
+    (tests/golden/make_golden_train.py): predictions, loss, every parameter's gradient (norm + samples), running stats."""
+    import train_helpers as TH
+    g = gold("train_net")
+    x, tg = TH.train_inputs()
+    np.testing.assert_array_equal(tg.numpy(), g["targets"])
+    preds, loss, grads, sd, _ = TH.oracle_train_step(ref_state_dict, x, tg)
+    for i in range(3):
+        np.testing.assert_allclose(preds[i].numpy(), g[f"pred{i}"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-6)
+    names = [str(n) for n in g["grad_names"]]
+    assert sorted(names) == sorted(grads)
+    for n, st in zip(names, g["grad_stats"]):
+        mine = TH.grad_stats(grads[n])
+        np.testing.assert_allclose(mine[1], st[1], rtol=1e-4, atol=1e-9, err_msg=n)                   # L2 norm
+        np.testing.assert_allclose(mine[2:], st[2:], rtol=1e-3, atol=1e-5 * max(st[1], 1e-6), err_msg=n)   # samples
+    for k in [k for k in g if k.startswith("grad:")]:
+        ref = g[k]
+        np.testing.assert_allclose(grads[k[5:]].numpy(), ref, rtol=1e-3, atol=1e-5 * np.abs(ref).max(), err_msg=k)
+    for k in [k[3:] for k in g if k.startswith("rm:")]:
+        np.testing.assert_allclose(sd[k + ".running_mean"].numpy(), g["rm:" + k], atol=1e-6)
+        np.testing.assert_allclose(sd[k + ".running_var"].numpy(), g["rv:" + k], rtol=1e-5)

@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     return _lib
 
 
+param_epoch = 0      # bumped whenever a kernel rewrites parameters behind autograd's version counters (FusedAdamEMA.step)
 launch_count = 0     # kernels launched through the C ABI by this process (bench.py reports it)
 
 

@@ -70,7 +70,7 @@ class _Conv:
 
 
 class InferenceEngine:
-    def __init__(self, model, device: torch.device, compute_dtype: str):
+    def __init__(self, model, device: torch.device, compute_dtype: str, frontend_only: bool = False):
         if device.type != "cuda":
             raise RuntimeError("yad_b200 needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
         if compute_dtype not in ("bf16", "f32"):
@@ -87,6 +87,8 @@ class InferenceEngine:
         self._tls = threading.local()
         with torch.no_grad():
             self._pack_frontend(model)
+            if frontend_only:      # train mode: the CNN runs in train_engine.py on the live parameters
+                return
             self._pack_cnn(model)
             dur = float(self.cfg["sample_duration"])
             self.anchors_s = torch.cat([model.sm_anchors * dur, model.md_anchors * dur, model.lg_anchors * dur]).float().cpu()

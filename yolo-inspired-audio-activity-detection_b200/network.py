@@ -256,31 +256,60 @@ class AudioDetectionNetwork(nn.Module):
         return (x - mu) / (std + e)
 
     # ---- forward -------------------------------------------------------------------------------
-    def _engine(self):
+    def _engine(self, frontend_only: bool = False):
         from .engine import InferenceEngine
-        ver = sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
         dev = self.sm_anchors.device
-        key = (str(dev), self.compute_dtype)
+        if frontend_only:      # train mode: only the (parameter-free) frontend is packed; buffers decide staleness
+            ver = sum(b._version for b in self.buffers() if b.dtype.is_floating_point and b.ndim > 1)
+            key = (str(dev), "frontend")
+        else:
+            from . import _lib
+            ver = (sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers()), _lib.param_epoch)
+            key = (str(dev), self.compute_dtype)
         ent = self._engine_cache.get(key)
         if ent is None or ent[0] != ver:
-            ent = (ver, InferenceEngine(self, dev, self.compute_dtype))
+            ent = (ver, InferenceEngine(self, dev, self.compute_dtype, frontend_only=frontend_only))
             self._engine_cache[key] = ent
         return ent[1]
+
+    def _train_engine(self):
+        from .train_engine import TrainEngine
+        dev = self.sm_anchors.device
+        key = (str(dev), "train")
+        eng = self._engine_cache.get(key)
+        if eng is None:
+            eng = self._engine_cache[key] = TrainEngine(self, dev)
+        return eng
+
+    def _forward_train(self, x: torch.Tensor):
+        """train() mode (pipeline/_trainer.py:98-104): batch-statistics BatchNorm, dropout, differentiable w.r.t. every
+        parameter.  fp32 throughout, like the reference's training."""
+        from .train_engine import run_train_forward
+        fe = self._engine(frontend_only=True)
+        B, _, L = x.shape
+        with torch.no_grad(), torch.cuda.device(fe.dev):
+            xs = fe.run_frontend(x, {})
+        L_res = -(-fe.rs_P * L // fe.rs_O)
+        with torch.cuda.device(fe.dev):
+            return run_train_forward(self, self._train_engine(), xs, xs.shape[-1], L_res)
 
     def forward(self, x: torch.Tensor, combine_scales: bool = False, taps: Optional[Dict[str, torch.Tensor]] = None):
         if not x.is_cuda:
             raise RuntimeError("yad_b200.AudioDetectionNetwork runs on sm_100a only; move the input and the model to "
                                "a CUDA device (there is no CPU fallback)")
-        if self.training:
-            _unsupported("train-mode forward (batch-statistics BatchNorm, dropout, autograd) - call .eval()")
         if self.config["taper_input"]:
             _unsupported("taper_input=true")
         if x.ndim != 3 or x.shape[1] != 1:
             raise ValueError(f"expected input of shape [N, 1, n_time], got {tuple(x.shape)}")
+        B, E = x.shape[0], self.num_classes + 3
+        if self.training:
+            sm, md, lg = self._forward_train(x)
+            if combine_scales:
+                return torch.cat([p.reshape(B, -1, E) for p in (sm, md, lg)], dim=1)
+            return sm, md, lg
         preds = self._engine().run(x, taps=taps)
         if combine_scales:
             return preds
-        B, E = x.shape[0], self.num_classes + 3
         A = self.config["num_anchors"]
         out, r0 = [], 0
         for G in self._engine().grids(x.shape[-1]):

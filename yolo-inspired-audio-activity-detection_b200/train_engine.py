@@ -1,0 +1,392 @@
+"""Train-mode forward and backward of the network: what autograd does for
+``TrainerPipeline.__feed`` (reference: pipeline/_trainer.py:94-108) when the model is in ``train()`` mode -
+batch-statistics BatchNorm with running-stat updates, dropout, the train-form RepVGG branches, and the gradient of
+every parameter including the three anchor parameters (modules/_architecture.py:39-41).
+
+The graph is the reference's (modules/_backbone.py:142-152, torchvision resnet.py:89-105, modules/_common.py:43-48,
+86-95,179-185,204-215,241-265, modules/_architecture.py:132-156); every node is one or two C-ABI calls on fp32 NHWC
+tensors and records a closure on a tape, the backward replays the tape in reverse.  torch supplies device memory, the
+stream and the autograd hook (`_TrainFn`), nothing else.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, F32, ConvDesc
+
+
+class _T:
+    """A channel slice [off, off + C) of an fp32 NHWC buffer [B, H, W, ld]."""
+    __slots__ = ("buf", "off", "C")
+
+    def __init__(self, buf: torch.Tensor, off: int = 0, C: Optional[int] = None):
+        self.buf, self.off = buf, off
+        self.C = buf.shape[3] - off if C is None else C
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + 4 * self.off
+
+    @property
+    def ld(self) -> int:
+        return self.buf.shape[3]
+
+    @property
+    def B(self):
+        return self.buf.shape[0]
+
+    @property
+    def H(self):
+        return self.buf.shape[1]
+
+    @property
+    def W(self):
+        return self.buf.shape[2]
+
+    @property
+    def rows(self) -> int:
+        return self.buf.shape[0] * self.buf.shape[1] * self.buf.shape[2]
+
+
+class TrainEngine:
+    def __init__(self, model, device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("yad_b200 train mode needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
+        self.dev = device
+        self.lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+        self.model = model
+        self.cfg = model.config
+        self.nc = model.num_classes
+        self.A = self.cfg["num_anchors"]
+        self.E = 3 + self.nc
+        self._wcache: Dict[int, tuple] = {}
+        self._step = 0
+        for m in model.modules():
+            if hasattr(m, "conv_reparam"):
+                raise NotImplementedError("yad_b200: train-mode forward of the deploy (re-parameterised) form is not built")
+
+    # ------------------------------------------------------------------ helpers
+    def _s(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _new(self, B, H, W, Cc, zero=False) -> _T:
+        f = torch.zeros if zero else torch.empty
+        return _T(f((B, H, W, Cc), device=self.dev, dtype=torch.float32))
+
+    def _grad(self, t: _T) -> _T:
+        """Gradient slice matching ``t`` (one zero-initialised buffer per activation buffer; every backward accumulates)."""
+        key = t.buf.data_ptr()
+        g = self._grads.get(key)
+        if g is None:
+            g = self._grads[key] = torch.zeros_like(t.buf)
+        return _T(g, t.off, t.C)
+
+    @staticmethod
+    def _pgrad(p: torch.Tensor) -> torch.Tensor:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        return p.grad
+
+    def _permute(self, src_ptr: int, strides, out: torch.Tensor, sizes, accumulate: bool):
+        st = (C.c_int64 * 4)(*strides)
+        sz = (C.c_int32 * 4)(*sizes)
+        _lib.check(self.lib.yad_permute4(src_ptr, st, out.data_ptr(), sz, 1 if accumulate else 0, self._s()), "permute4")
+
+    def _packed(self, w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """OIHW master weight -> ([kh][kw][Cin][Cout] for the forward / wgrad, [kh][kw][Cout][Cin] for the dgrad)."""
+        ent = self._wcache.get(id(w))
+        ver = (w._version, _lib.param_epoch, w.data_ptr())
+        if ent is not None and ent[0] == ver:
+            return ent[1], ent[2]
+        O, I, kh, kw = w.shape
+        wf = torch.empty((kh, kw, I, O), device=self.dev, dtype=torch.float32)
+        wt = torch.empty((kh, kw, O, I), device=self.dev, dtype=torch.float32)
+        wd = w.detach()
+        if not wd.is_contiguous():
+            wd = wd.contiguous()
+        self._permute(wd.data_ptr(), (kw, 1, kh * kw, I * kh * kw), wf, (kh, kw, I, O), False)
+        self._permute(wd.data_ptr(), (kw, 1, I * kh * kw, kh * kw), wt, (kh, kw, O, I), False)
+        self._wcache[id(w)] = (ver, wf, wt)
+        return wf, wt
+
+    # ------------------------------------------------------------------ nodes (forward + recorded backward)
+    def conv(self, x: _T, conv: nn.Conv2d, out: Optional[_T] = None, need_dx: bool = True) -> _T:
+        w, b = conv.weight, conv.bias
+        O, I, kh, kw = w.shape
+        sh, sw = conv.stride
+        ph, pw = conv.padding
+        assert x.C == I, (x.C, I)
+        Ho, Wo = (x.H + 2 * ph - kh) // sh + 1, (x.W + 2 * pw - kw) // sw + 1
+        if out is None:
+            out = self._new(x.B, Ho, Wo, O)
+        assert (out.B, out.H, out.W, out.C) == (x.B, Ho, Wo, O)
+        wf, wt = self._packed(w)
+        d = ConvDesc(B=x.B, H=x.H, W=x.W, Cin=I, ld_in=x.ld, Cout=O, ld_out=out.ld, co_off=0, kh=kh, kw=kw, sh=sh, sw=sw,
+                     ph=ph, pw=pw, act=ACT_NONE, ld_res=0)
+        _lib.check(self.lib.yad_conv_simt(C.byref(d), F32, x.ptr, wf.data_ptr(), O, _lib.ptr(b), 0, out.ptr, self._s()), "conv fwd")
+        if self._tape is not None:
+            def bwd():
+                dy = self._grad(out)
+                dwk = torch.zeros_like(wf)
+                bws = torch.zeros(O, device=self.dev, dtype=torch.float64) if b is not None else None
+                _lib.check(self.lib.yad_conv_wgrad(C.byref(d), x.ptr, dy.ptr, dwk.data_ptr(), _lib.ptr(bws), self._s()), "conv wgrad")
+                self._permute(dwk.data_ptr(), (1, O, kw * I * O, I * O), self._pgrad(w), (O, I, kh, kw), True)
+                if b is not None:
+                    _lib.check(self.lib.yad_add_f64_to_f32(bws.data_ptr(), O, self._pgrad(b).data_ptr(), self._s()), "bias grad")
+                if need_dx:
+                    dx = self._grad(x)
+                    _lib.check(self.lib.yad_conv_dgrad(C.byref(d), dy.ptr, wt.data_ptr(), dx.ptr, dx.ptr, self._s()), "conv dgrad")
+            self._tape.append(bwd)
+        return out
+
+    def bn(self, x: _T, bn: nn.BatchNorm2d, act: int, out: Optional[_T] = None) -> _T:
+        Cc, N = x.C, x.rows
+        if out is None:
+            out = self._new(x.B, x.H, x.W, Cc)
+        sm = torch.empty(2 * Cc, device=self.dev, dtype=torch.float32)
+        mean, invstd = sm[:Cc], sm[Cc:]
+        ws = torch.empty(2 * Cc, device=self.dev, dtype=torch.float64)
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        _lib.check(self.lib.yad_bn_train_fwd(x.ptr, x.ld, N, Cc, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), mom,
+                                             bn.running_mean.data_ptr(), bn.running_var.data_ptr(), act, out.ptr, out.ld,
+                                             mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), self._s()), "bn fwd")
+        self._bn_counters.append(bn.num_batches_tracked)
+        if self._tape is not None:
+            def bwd():
+                dy, dx = self._grad(out), self._grad(x)
+                _lib.check(self.lib.yad_bn_train_bwd(x.ptr, x.ld, out.ptr, out.ld, dy.ptr, dy.ld, N, Cc, bn.weight.data_ptr(),
+                                                     mean.data_ptr(), invstd.data_ptr(), act, dx.ptr, dx.ld, 1,
+                                                     self._pgrad(bn.weight).data_ptr(), self._pgrad(bn.bias).data_ptr(),
+                                                     ws.data_ptr(), self._s()), "bn bwd")
+            self._tape.append(bwd)
+        return out
+
+    def cbl(self, x: _T, m, out: Optional[_T] = None) -> _T:
+        """ConvBorINorm (modules/_common.py:43-48): conv(+bias) -> BatchNorm (batch statistics) -> LeakyReLU(0.2)."""
+        return self.bn(self.conv(x, m.conv), m.norm, ACT_LRELU if m.has_activation else ACT_NONE, out)
+
+    def add_act(self, a: _T, b: _T, c: Optional[_T], act: int, out: Optional[_T] = None) -> _T:
+        if out is None:
+            out = self._new(a.B, a.H, a.W, a.C)
+        N, Cc = a.rows, a.C
+        _lib.check(self.lib.yad_add_act(a.ptr, a.ld, b.ptr, b.ld, 0 if c is None else c.ptr, 0 if c is None else c.ld, N, Cc, act,
+                                        out.ptr, out.ld, self._s()), "add_act")
+        if self._tape is not None:
+            def bwd():
+                dy = self._grad(out)
+                da, db = self._grad(a), self._grad(b)
+                dc = self._grad(c) if c is not None else None
+                _lib.check(self.lib.yad_add_act_bwd(out.ptr, out.ld, dy.ptr, dy.ld, N, Cc, act, da.ptr, da.ld, db.ptr, db.ld,
+                                                    0 if dc is None else dc.ptr, 0 if dc is None else dc.ld, self._s()), "add_act bwd")
+            self._tape.append(bwd)
+        return out
+
+    def dropout(self, x: _T, p: float) -> _T:
+        if p <= 0.0:
+            return x
+        assert x.off == 0 and x.C == x.ld
+        out = self._new(x.B, x.H, x.W, x.C)
+        seed = (int(torch.initial_seed()) * 1000003 + self._step) & ((1 << 63) - 1)
+        n = x.buf.numel()
+        _lib.check(self.lib.yad_dropout(x.ptr, n, p, seed, 0, out.ptr, self._s()), "dropout")
+        if self._tape is not None:
+            def bwd():
+                _lib.check(self.lib.yad_dropout(self._grad(out).ptr, n, p, seed, 1, self._grad(x).ptr, self._s()), "dropout bwd")
+            self._tape.append(bwd)
+        return out
+
+    def hmean(self, x: _T) -> _T:
+        """adaptive_avg_pool2d(H -> 1), modules/_common.py:248-252."""
+        if x.H == 1:
+            return x
+        assert x.off == 0 and x.C == x.ld
+        B, H, W, Cc = x.B, x.H, x.W, x.C
+        out = self._new(B, 1, W, Cc)
+        _lib.check(self.lib.yad_hmean(x.ptr, F32, B, H, W, Cc, Cc, 1, W, H * W, out.ptr, Cc, 0, self._s()), "hmean")
+        if self._tape is not None:
+            def bwd():
+                _lib.check(self.lib.yad_hmean_bwd(self._grad(out).ptr, Cc, B, H, W, Cc, self._grad(x).ptr, Cc, self._s()), "hmean bwd")
+            self._tape.append(bwd)
+        return out
+
+    def resize_w(self, x: _T, up: bool, out: _T) -> _T:
+        """F.interpolate(scale_factor=(1, 2 | 0.5), bilinear), modules/_common.py:181-182."""
+        B, W, Cc = x.B, x.W, x.C
+        assert out.C == Cc and out.W == (2 * W if up else W // 2)
+        _lib.check(self.lib.yad_resize_w(x.buf.data_ptr(), F32, B, W, Cc, x.ld, x.off, 1 if up else 0, out.buf.data_ptr(), out.ld,
+                                         out.off, self._s()), "resize_w")
+        if self._tape is not None:
+            def bwd():
+                dy, dx = self._grad(out), self._grad(x)
+                _lib.check(self.lib.yad_resize_w_bwd(dy.ptr, dy.ld, B, W, Cc, 1 if up else 0, dx.ptr, dx.ld, self._s()), "resize_w bwd")
+            self._tape.append(bwd)
+        return out
+
+    def maxpool5(self, x: _T, out: _T) -> _T:
+        B, W, Cc = x.B, x.W, x.C
+        _lib.check(self.lib.yad_maxpool5_w(x.ptr, x.ld, B, W, Cc, out.ptr, out.ld, self._s()), "maxpool5")
+        if self._tape is not None:
+            def bwd():
+                dy, dx = self._grad(out), self._grad(x)
+                _lib.check(self.lib.yad_maxpool5_w_bwd(x.ptr, x.ld, dy.ptr, dy.ld, B, W, Cc, dx.ptr, dx.ld, self._s()), "maxpool5 bwd")
+            self._tape.append(bwd)
+        return out
+
+    def repvgg(self, x: _T, m, out: Optional[_T] = None) -> _T:
+        """Train-form RepVGG block (modules/_common.py:86-95): lrelu(cbl3x3(x) + cbl1x1(x) [+ bn(x)])."""
+        a = self.cbl(x, m.conv3x3)
+        b = self.cbl(x, m.conv1x1)
+        c = self.bn(x, m.identity, ACT_NONE) if isinstance(m.identity, nn.BatchNorm2d) else None
+        return self.add_act(a, b, c, ACT_LRELU, out)
+
+    def repblock(self, x: _T, rb, out: Optional[_T] = None) -> _T:
+        blocks = [rb.conv1] + (list(rb.blocks) if isinstance(rb.blocks, nn.Sequential) else [])
+        for i, blk in enumerate(blocks):
+            x = self.repvgg(x, blk, out if i == len(blocks) - 1 else None)
+        return x
+
+    def basic_block(self, x: _T, blk) -> _T:
+        t = self.bn(self.conv(x, blk.conv1), blk.bn1, ACT_RELU)
+        u = self.bn(self.conv(t, blk.conv2), blk.bn2, ACT_NONE)
+        idt = x if blk.downsample is None else self.bn(self.conv(x, blk.downsample[0]), blk.downsample[1], ACT_NONE)
+        return self.add_act(u, idt, None, ACT_RELU)
+
+    # ------------------------------------------------------------------ the graph
+    def forward(self, xs: torch.Tensor, T: int, L_res: int, record: bool):
+        """x_spectral [B,2,32,T] f32 (frontend output, not differentiable: it has no parameters) -> (preds per scale
+        [B,G,A,E], tape)."""
+        model = self.model
+        fe, ms = model.feature_extractor, model.multiscale_module
+        self._tape: Optional[List[Callable[[], None]]] = [] if record else None
+        self._grads: Dict[int, torch.Tensor] = {}
+        self._bn_counters: List[torch.Tensor] = []
+        self._step += 1
+        B, Cin, H0, _ = xs.shape
+        x0 = self._new(B, H0, T, Cin)
+        self._permute(xs.data_ptr(), (Cin * H0 * T, T, 1, H0 * T), x0.buf, (B, H0, T, Cin), False)     # NCHW -> NHWC
+        x = self.conv(x0, fe.conv1, need_dx=False)
+        x = self.conv(x, fe.conv2)
+        x = self.bn(x, fe.bn1, ACT_RELU)
+        x = self.dropout(x, float(fe.dropout_p))
+        fmaps = []
+        for li in range(1, 5):
+            for blk in getattr(fe, f"layer{li}"):
+                x = self.basic_block(x, blk)
+            fmaps.append(x)
+        hs = [f.H for f in fmaps]
+        if not (hs[0] != hs[1] != hs[2] != hs[3]):
+            raise NotImplementedError("neck with equal feature-map heights (2-D neck) is not built")
+        f1, f2, f3, f4 = [self.hmean(f) for f in fmaps]
+        W1, W2, W3, W4 = f1.W, f2.W, f3.W, f4.W
+        nh = self.A * self.E
+        # CSPSPPF (modules/_common.py:204-215); torch.cat sites are channel slices of one buffer
+        sp = ms.cspsppf
+        ch = sp.conv2.conv.out_channels
+        cat5 = self._new(B, 1, W4, 4 * ch)
+        cat7 = self._new(B, 1, W4, 2 * ch)
+        cat_n4 = self._new(B, 1, W4, 2 * 128)
+        x1 = self.cbl(self.cbl(self.cbl(f4, sp.conv_1_3_4[0]), sp.conv_1_3_4[1]), sp.conv_1_3_4[2], _T(cat5.buf, 0, ch))
+        self.cbl(f4, sp.conv2, _T(cat7.buf, ch, ch))
+        p1 = self.maxpool5(x1, _T(cat5.buf, ch, ch))
+        p2 = self.maxpool5(p1, _T(cat5.buf, 2 * ch, ch))
+        self.maxpool5(p2, _T(cat5.buf, 3 * ch, ch))
+        self.cbl(self.cbl(cat5, sp.conv5), sp.conv6, _T(cat7.buf, 0, ch))
+        p4 = self.cbl(cat7, sp.conv7, _T(cat_n4.buf, 0, 128))
+        # BiC3 -> RepBlock3_1 -> p3
+        cat_b3 = self._new(B, 1, W3, 256)
+        cat_n3 = self._new(B, 1, W3, 256)
+        self.cbl(f3, ms.bic3.conv_c1, _T(cat_b3.buf, 0, 64))
+        self.resize_w(self.cbl(f2, ms.bic3.conv_c0), False, _T(cat_b3.buf, 64, 64))
+        self.resize_w(p4, True, _T(cat_b3.buf, 128, 128))
+        p3 = self.repblock(self.cbl(cat_b3, ms.bic3.conv_out), ms.rep_block3_1, _T(cat_n3.buf, 0, 128))
+        # BiC2 -> RepBlock2_1 -> n2
+        cat_b2 = self._new(B, 1, W2, 256)
+        self.cbl(f2, ms.bic2.conv_c1, _T(cat_b2.buf, 0, 64))
+        self.resize_w(self.cbl(f1, ms.bic2.conv_c0), False, _T(cat_b2.buf, 64, 64))
+        self.resize_w(p3, True, _T(cat_b2.buf, 128, 128))
+        n2 = self.repblock(self.cbl(cat_b2, ms.bic2.conv_out), ms.rep_block2_1)
+        self.cbl(n2, ms.conv2_downsample, _T(cat_n3.buf, 128, 128))
+        n3 = self.repblock(cat_n3, ms.rep_block3_2)
+        self.cbl(n3, ms.conv3_downsample, _T(cat_n4.buf, 128, 128))
+        n4 = self.repblock(cat_n4, ms.rep_block4_1)
+        if self._bn_counters:
+            torch._foreach_add_(self._bn_counters, 1)
+            _lib.param_epoch += 1      # running statistics were rewritten by the kernels: packed eval engines are stale
+        # anchor decode (modules/_architecture.py:132-156), one call per scale
+        dur = float(self.cfg["sample_duration"])
+        anchors = [model.sm_anchors, model.md_anchors, model.lg_anchors]
+        anc_s = torch.stack([a.detach() for a in anchors]).float() * dur          # [3, A] seconds, device
+        anc_h = anc_s.cpu()
+        center_scaler = T / (L_res / self.cfg["new_sample_rate"])
+        preds, heads = [], (n2, n3, n4)
+        for s, h in enumerate(heads):
+            G = h.W
+            assert h.C == nh
+            p = torch.empty((B, G, self.A, self.E), device=self.dev, dtype=torch.float32)
+            hp = (C.c_void_p * 1)(h.ptr)
+            anc = (C.c_float * self.A)(*anc_h[s].tolist())
+            _lib.check(self.lib.yad_decode(hp, (C.c_int32 * 1)(G), (C.c_int32 * 1)(h.ld), (C.c_int32 * 1)(T // G), 1, F32, anc, self.A,
+                                           self.nc, center_scaler, dur, B, p.data_ptr(), self._s()), "decode")
+            preds.append(p)
+        state = None
+        if record:
+            state = {"tape": self._tape, "grads": self._grads, "heads": heads, "anc_s": anc_s, "anchors": anchors,
+                     "strides": [T // h.W for h in heads], "center_scaler": center_scaler, "dur": dur, "B": B}
+        self._tape, self._grads = None, {}
+        return preds, state
+
+    def backward(self, state, dpreds: List[Optional[torch.Tensor]]):
+        """Accumulates d loss / d parameter into every ``p.grad`` (allocated when missing)."""
+        self._grads = state["grads"]
+        self._tape = None
+        dur, B = state["dur"], state["B"]
+        danc = torch.zeros_like(state["anc_s"])
+        for s, (h, dp) in enumerate(zip(state["heads"], dpreds)):
+            if dp is None:
+                continue
+            dp = dp.contiguous().float()
+            dh = self._grad(h)
+            _lib.check(self.lib.yad_decode_bwd(h.ptr, h.ld, dp.data_ptr(), B, h.W, self.A, self.nc, state["anc_s"][s].data_ptr(),
+                                               float(state["strides"][s]) / float(state["center_scaler"]), dur, dh.ptr, dh.ld,
+                                               danc[s].data_ptr(), self._s()), "decode bwd")
+        for s, a in enumerate(state["anchors"]):
+            if a.requires_grad:
+                self._pgrad(a).add_(danc[s], alpha=dur)
+        for fn in reversed(state["tape"]):
+            fn()
+        state["tape"].clear()
+        state["grads"].clear()
+        self._grads = {}
+
+
+class _TrainFn(torch.autograd.Function):
+    """autograd hook: forward runs the kernels and keeps the tape; backward replays it and writes the parameter
+    gradients straight into ``p.grad`` (the ``params`` inputs only exist so that autograd calls backward)."""
+
+    @staticmethod
+    def forward(ctx, eng: TrainEngine, xs: torch.Tensor, T: int, L_res: int, *params):
+        record = any(ctx.needs_input_grad[4:])
+        preds, state = eng.forward(xs, T, L_res, record)
+        ctx.eng, ctx.state = eng, state
+        return tuple(preds)
+
+    @staticmethod
+    def backward(ctx, *dpreds):
+        if ctx.state is None or not ctx.state["tape"]:
+            raise RuntimeError("yad_b200: backward through the same train-mode forward twice is not supported")
+        with torch.no_grad():
+            ctx.eng.backward(ctx.state, list(dpreds))
+        return (None,) * len(ctx.needs_input_grad)
+
+
+def run_train_forward(model, eng: TrainEngine, xs: torch.Tensor, T: int, L_res: int):
+    eng._params = [p for p in model.parameters() if p.requires_grad]
+    if torch.is_grad_enabled() and eng._params:
+        return _TrainFn.apply(eng, xs, T, L_res, *eng._params)
+    preds, _ = eng.forward(xs, T, L_res, False)
+    return tuple(preds)

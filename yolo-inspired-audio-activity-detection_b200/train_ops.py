@@ -216,6 +216,7 @@ class FusedAdamEMA:
                                             _lib.ptr(self.ema), self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
                                             self.wd, self.step_count, m, _stream(self.dev))
         _lib.check(rc, "adam_ema_step")
+        _lib.param_epoch += 1        # the packed-weight caches of the engines key on this
 
 
 class EMAParamsSmoothener:
