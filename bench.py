@@ -227,6 +227,153 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_METRIC = "audio-seconds/sec (train step: fwd + YOLO loss + bwd + Adam + EMA, DP gradient all-reduce)"
+TRAIN_FLOP_PER_CLIP = 3 * 2 * 1514.2e6          # ~3x the train-form forward (1 514.2 nominal MMAC)
+
+
+def cpu_baseline_train(sample_clips=4, runs=3):
+    """The reference's train step (oracle port: torch CPU fp32 autograd, all host threads) on a bounded sample: train-mode
+    forward (dropout 0: the oracle is deterministic) + loss + backward + Adam + EMA for `sample_clips` clips."""
+    import synth
+    from oracle import ref_port as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, full = build_model(torch.device("cpu"), deploy=False)
+    sd = {k: v.cpu().clone() for k, v in full.items()}
+    names = [k for k, v in sd.items() if v.dtype.is_floating_point and (k.endswith((".weight", ".bias")) or k.endswith("_anchors"))
+             and "tfmr" not in k]
+    x = synth.synth_clips(sample_clips, CLIP_SAMPLES, seed=2000, silence_tail_every=8)
+    tg = synth.synth_targets(sample_clips, seed=11)
+    cfg = dict(O.DEFAULT_CONFIG, dropout=0.0)
+    m = {k: torch.zeros_like(sd[k]) for k in names}
+    v = {k: torch.zeros_like(sd[k]) for k in names}
+    ema = {k: sd[k].clone() for k in names}
+    times = []
+    for it in range(runs + 1):
+        t0 = time.perf_counter()
+        with torch.enable_grad():
+            for k in names:
+                sd[k] = sd[k].detach().requires_grad_(True)
+            loss, _ = O.detection_loss(O.forward_train(x, sd, 2, cfg), tg, O.DEFAULT_CONFIG["anchors"], 2)
+            loss.backward()
+        with torch.no_grad():
+            ps = [sd[k] for k in names]
+            O.adam_step(ps, [p.grad for p in ps], [m[k] for k in names], [v[k] for k in names], it + 1)
+            O.ema_update([ema[k] for k in names], ps, it + 1)
+        if it:
+            times.append(time.perf_counter() - t0)
+    t = sorted(times)[len(times) // 2]
+    return {"value": CLIP_SECONDS * sample_clips / t, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_clips} synthetic 60 s clips per step, oracle port of the reference train step (train-mode forward, loss, "
+                      f"autograd backward, Adam, EMA; torch CPU fp32), median of {runs} steps, {t:.2f} s/step"}
+
+
+def run_train(args):
+    """BASELINE configs[4]: the data-parallel train step of pipeline/_trainer.py:94-108 - H2D is outside `value` (batch resident
+    in HBM) and inside `e2e`; gradients are averaged with ONE bucketed NCCL all-reduce over the flat 48.5 MB arena."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import synth
+    import yad_b200
+    from yad_b200 import _lib, parallel
+    cfg = yad_b200.default_config()
+    tc = cfg["train_config"]
+    B = args.batch if args.batch != 512 else int(tc["batch_size"])          # 32 clips per GPU (config.yaml:59)
+    W, K = max(3, args.warmup), max(1, args.steps)
+    torch.manual_seed(42)
+    model, _ = build_model(dev, "bf16", deploy=False)
+    model.train()
+    oc, ec = tc["optimizer_config"], tc["ema_config"]
+    opt = yad_b200.FusedAdamEMA(model.parameters(), lr=oc["lr"], betas=tuple(oc["betas"]), eps=oc["eps"], weight_decay=oc["weight_decay"],
+                                ema_momentum=ec["momentum"], ema_N=ec["N"], use_ema=True)
+    loss_fn = yad_b200.AudioDetectionLoss(cfg["anchors"], 2, sample_duration=cfg["sample_duration"], **tc["loss_config"])
+    x = synth_clips_device(B, dev, seed=2000 + 7919 * rank)
+    tg = synth.synth_targets(B, seed=11 + rank).to(dev)
+    ar_ms = []
+
+    def step(xd, tgd):
+        with torch.enable_grad():
+            loss, met = loss_fn(model(xd), tgd)
+            loss.backward()
+        if world > 1:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); opt.allreduce_grads(); b.record()
+            ar_ms.append((a, b))
+        opt.step()
+        opt.zero_grad()
+        return met
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(W):
+        step(x, tg)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count
+    met = step(x, tg)
+    launches = _lib.launch_count - n0
+    ar_ms.clear()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        met = step(x, tg)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    ar = sum(a.elapsed_time(b) for a, b in ar_ms) / max(1, len(ar_ms)) if ar_ms else 0.0
+    # end to end: pinned host PCM + targets -> device every step, loss metrics back (the loss's own 192-byte read)
+    xh = torch.empty((B, 1, CLIP_SAMPLES), dtype=torch.float32, pin_memory=True); xh.copy_(x)
+    th = tg.cpu().pin_memory()
+    Ke = max(1, min(K, 5))
+    step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(Ke):
+        met = step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True))
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
+    sampler.stop_flag.set(); sampler.join(timeout=3)
+    if rank == 0:
+        peaks = load_peaks()
+        value = CLIP_SECONDS * B * world * K / (ms / 1e3)
+        tfl = TRAIN_FLOP_PER_CLIP * B / (ms / K / 1e3) / 1e12
+        line = {"metric": TRAIN_METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"train step (BASELINE configs[4]): {B} clips x 60 s per GPU, train-form net in train() mode "
+                                       "(batch-stat BatchNorm, dropout 0.4), fp32 CUDA-core convolutions, YOLO loss, backward, fused Adam + EMA; "
+                                       "one bucketed NCCL all-reduce of the 48.5 MB fp32 gradient arena per step when N > 1",
+                           "clips_per_gpu": B, "clip_seconds": CLIP_SECONDS, "num_classes": 2,
+                           "l2_policy": "per-step working set (169 MB PCM + 1.5 GB activations / gradients) is larger than the 126 MB L2",
+                           "parallelism": f"data-parallel x{world}"},
+                "e2e": {"value": CLIP_SECONDS * B * world * Ke / (ms_e / 1e3), "unit": "audio-s/s",
+                        "h2d_bytes_per_step": B * CLIP_SAMPLES * 4 + th.numel() * 4, "d2h_bytes_per_step": 3 * 8 * 8 + 3 * 4 * 4, "steps": Ke},
+                "gpu_launches": launches * K, "launches_per_step": launches, "clocks": sampler.summary(),
+                "roofline": {"kernel": "conv_simt_kernel / conv_wgrad_kernel (fp32 CUDA cores)", "bound": "fp32", "achieved": tfl,
+                             "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s", "frac": tfl / (148 * 128 * 2 * 1.965e9 / 1e12),
+                             "traffic": None, "note": "whole-step useful conv FLOPs (3 x train-form forward) / step time; peak = 148 SMs x "
+                                                      "128 FP32 lanes x 2 x 1.965 GHz (the fp32 convolutions do not use the tensor cores)"},
+                "allreduce_ms": ar, "loss": met.get("aggregate_loss"), "cpu_baseline": None}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_train()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -235,11 +382,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="clips per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer: the headline metric (BASELINE configs[1]+[2]); train: the data-parallel train step (configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end pipeline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
