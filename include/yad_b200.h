@@ -291,6 +291,42 @@ int yad_permute4(const float* in, const int64_t* in_strides, float* out, const i
                  yad_stream_t stream);
 int yad_add_f64_to_f32(const double* a, int32_t n, float* out, yad_stream_t stream);
 
+/* ------------------------------------------------------------------ TF32 tensor-core convolutions of the train step
+ * fp32 NHWC tensors, tf32 operands, fp32 accumulation in tensor memory (tcgen05.mma kind::tf32): what cuDNN runs for the
+ * reference's F.conv2d forward / backward on a GPU by default (torch.backends.cudnn.allow_tf32).
+ *
+ * yad_corr_tf32: generic tap-list correlation
+ *     out[b,i,j,n] (+)= bias[n] + sum_t sum_c in[b, i*sh + tap_dh[t], j*sw + tap_dw[t], c] * weight[n][tap_k[t] + c]
+ * in: dense NHWC [B,H,W,ld_in] (Cin % 32 == 0, zero-padded channels); weight [cout_pad][k_total] f32 (K-major); out pixel
+ * (b,i,j) at (b*out_sb + i*out_sh + j*out_sw)*ld_out (all three 0 = dense [B,Ho,Wo,ld_out]); bias may be NULL.  The host
+ * builds from it the forward conv, the data gradient of a stride-1 conv (flipped taps, transposed weight) and of a
+ * stride-2 conv (one call per output parity class).
+ * yad_wgrad_tf32: dw[tap_dst[t]][ci][co] += sum_{b,i,j} x[b, i*sh + tap_dh[t], j*sw + tap_dw[t], ci] * dy[b,i,j,co]
+ * x [B,H,W,ld_in], dy [B,Ho,Wo,ld_out] dense with ld % 32 == 0 (pad channels must hold finite values); dw [taps][Cin][Cout]. */
+typedef struct {
+  int32_t B, H, W;            /* input spatial */
+  int32_t Cin, ld_in;
+  int32_t Ho, Wo;             /* output spatial (explicit) */
+  int32_t Cout, ld_out;
+  int32_t sh, sw;             /* input step per output pixel: 1 or 2 */
+  int32_t out_sw, out_sh, out_sb;
+  int32_t n_taps;
+  int32_t act;                /* YAD_ACT_* */
+  int32_t accumulate;         /* out += instead of out = */
+  int32_t whole_rows;         /* out is a dense buffer of which this call owns every channel of the pitch: lets a small
+                                 problem zero-fill it and split the K loop over CTAs (fp32 red.add of partial sums) */
+} yad_corr_desc;
+int yad_corr_tf32(const yad_corr_desc* d, const int32_t* tap_dh, const int32_t* tap_dw, const int32_t* tap_k, const float* in,
+                  const float* weight, int32_t cout_pad, int64_t k_total, const float* bias, float* out, yad_stream_t stream);
+int yad_wgrad_tf32(const yad_corr_desc* d, const int32_t* tap_dh, const int32_t* tap_dw, const int32_t* tap_dst, const float* x,
+                   const float* dy, float* dw, yad_stream_t stream);
+/* im2col of the stem conv1 (C -> 64, 7x7, stride 2, pad 3): x NCHW f32 [B,C,H,W] -> patches [B,(H-1)/2+1,(W-1)/2+1,K] with
+ * k = (kh*7 + kw)*C + c, zero for k >= 49*C (K a multiple of 32): conv1 and its weight gradient then run as a 1x1 conv on the
+ * TF32 kernels. */
+int yad_stem_im2col(const float* x_nchw, int64_t B, int32_t C, int32_t H, int32_t W, int32_t K, float* patches, yad_stream_t stream);
+/* ws[c] += sum over N rows of x[r*ld + c] (fp64): bias gradients. */
+int yad_colsum_f64(const float* x, int32_t ld, int64_t N, int32_t C, double* ws, yad_stream_t stream);
+
 /* Fused Adam (L2 weight decay) + EMA over a flat fp32 parameter arena:
  * torch.optim.Adam (train.py:83-90, config.yaml:75-80) and smoothener/_ema.py:20-26.
  * ema may be NULL.  step >= 1. */

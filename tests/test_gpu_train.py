@@ -189,10 +189,10 @@ def test_decode_backward(cuda_dev):
 
 
 # ------------------------------------------------------------------ the train-mode network (rows a1 / a17)
-def _train_model(ref_state_dict, cuda_dev, dropout=0.0):
+def _train_model(ref_state_dict, cuda_dev, dropout=0.0, train_dtype="f32"):
     cfg = yad_b200.default_config()
     cfg["dropout"] = dropout
-    m = yad_b200.AudioDetectionNetwork(2, config=cfg)
+    m = yad_b200.AudioDetectionNetwork(2, config=cfg, train_dtype=train_dtype)
     m.load_state_dict(ref_state_dict)
     return m.to(cuda_dev).train()
 
@@ -290,12 +290,13 @@ def test_train_forward_end_to_end_and_eval_after(gold, ref_state_dict, cuda_dev)
     assert torch.isfinite(pe).all()
 
 
-def test_train_steps_reduce_loss_with_dropout(ref_state_dict, cuda_dev):
+@pytest.mark.parametrize("train_dtype", ["f32", "tf32"])
+def test_train_steps_reduce_loss_with_dropout(train_dtype, ref_state_dict, cuda_dev):
     """Five fused Adam + EMA steps on one batch (dropout 0.4 as in config.yaml): the loss goes down, gradients live in the
     flat arena, the EMA shadow moves."""
     import train_helpers as TH
     x, tg = TH.train_inputs()
-    m = _train_model(ref_state_dict, cuda_dev, dropout=0.4)
+    m = _train_model(ref_state_dict, cuda_dev, dropout=0.4, train_dtype=train_dtype)
     opt = yad_b200.FusedAdamEMA(m.parameters(), lr=1e-3, weight_decay=0.002, ema_momentum=0.002, use_ema=True)
     loss_fn = _loss_fn()
     xd, tgd = x.to(cuda_dev), tg.to(cuda_dev)
@@ -311,3 +312,114 @@ def test_train_steps_reduce_loss_with_dropout(ref_state_dict, cuda_dev):
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
     assert not torch.equal(ema0, opt.ema)
+
+
+# ------------------------------------------------------------------ TF32 tensor-core convolutions (csrc/conv_tf32.cu)
+TF32_CASES = [
+    # B, H, W, Cin, Cout, (kh, kw), (sh, sw), (ph, pw)
+    (2, 8, 24, 64, 64, (3, 3), (1, 1), (1, 1)),
+    (2, 8, 24, 64, 128, (3, 3), (2, 2), (1, 1)),
+    (2, 8, 24, 64, 128, (1, 1), (2, 2), (0, 0)),
+    (2, 16, 48, 64, 64, (7, 7), (2, 2), (3, 3)),
+    (3, 1, 24, 15, 128, (3, 3), (1, 2), (1, 1)),
+    (3, 1, 12, 128, 15, (3, 3), (1, 1), (1, 1)),
+    (3, 1, 30, 15, 15, (1, 1), (1, 1), (0, 0)),
+    (4, 1, 30, 512, 64, (1, 1), (1, 1), (0, 0)),
+    (3, 2, 60, 256, 256, (3, 3), (1, 1), (1, 1)),
+    (2, 7, 37, 96, 160, (3, 3), (1, 1), (1, 1)),
+    (5, 4, 21, 128, 256, (3, 3), (2, 2), (1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", TF32_CASES)
+def test_conv_tf32_forward_dgrad_wgrad(case, ref_state_dict, cuda_dev):
+    """tcgen05 kind::tf32 forward / data gradient / weight gradient (through TrainEngine.conv, i.e. with the host-side tap
+    lists and weight packing) against fp32 PyTorch autograd.  TF32 keeps 10 mantissa bits per operand: tolerance 2e-3 of
+    the tensor's scale (cuDNN's default TF32 convolutions differ from fp32 by the same amount)."""
+    from yad_b200.train_engine import _T
+    B, H, W, Cin, Cout, k, s, p = case
+    g = torch.Generator().manual_seed(abs(hash(case)) % 9973)
+    conv = torch.nn.Conv2d(Cin, Cout, k, s, p, bias=True).to(cuda_dev)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (Cin * k[0] * k[1]) ** 0.5)
+        conv.bias.copy_(torch.randn(Cout, generator=g))
+    x = torch.randn(B, Cin, H, W, generator=g).to(cuda_dev).requires_grad_(True)
+    y = F.conv2d(x, conv.weight, conv.bias, stride=s, padding=p)
+    dy = torch.randn(y.shape, generator=g).to(cuda_dev)
+    gw, gb, gx = torch.autograd.grad(y, (conv.weight, conv.bias, x), dy)
+    m = _train_model(ref_state_dict, cuda_dev, train_dtype="tf32")
+    eng = m._train_engine()
+    eng._tape, eng._grads, eng._bn_counters = [], {}, []
+    xt = eng._new(B, H, W, Cin)
+    xt.buf[..., :Cin] = x.detach().permute(0, 2, 3, 1)
+    out = eng.conv(xt, conv)
+    assert eng._conv_tf32.__name__ and len(eng._plans) == 1      # the tensor-core path ran
+    torch.cuda.synchronize()
+    tol = lambda ref: 2e-3 * float(ref.abs().max())          # noqa: E731
+    np.testing.assert_allclose(out.buf[..., :Cout].permute(0, 3, 1, 2).cpu().numpy(), y.detach().cpu().numpy(), atol=tol(y))
+    if out.ld > Cout:
+        assert float(out.buf[..., Cout:].abs().max()) == 0.0       # pad channels stay zero
+    prev = torch.randn(B, H, W, Cin, generator=g).to(cuda_dev)     # an existing gradient to accumulate onto
+    eng._grad(out).buf[..., :Cout] = dy.permute(0, 2, 3, 1)
+    eng._grad(xt).buf[..., :Cin] = prev
+    conv.weight.grad = torch.ones_like(conv.weight)
+    conv.bias.grad = None
+    for fn in reversed(eng._tape):
+        fn()
+    torch.cuda.synchronize()
+    dx = eng._grad(xt).buf
+    np.testing.assert_allclose((dx[..., :Cin] - prev).permute(0, 3, 1, 2).cpu().numpy(), gx.cpu().numpy(), atol=tol(gx))
+    if xt.ld > Cin:
+        assert float(dx[..., Cin:].abs().max()) == 0.0
+    np.testing.assert_allclose((conv.weight.grad - 1).cpu().numpy(), gw.cpu().numpy(), atol=tol(gw))
+    np.testing.assert_allclose(conv.bias.grad.cpu().numpy(), gb.cpu().numpy(), rtol=1e-4, atol=1e-4)
+    eng._tape, eng._grads = None, {}
+
+
+def test_train_network_tf32_vs_cudnn_tf32_yardstick(gold, ref_state_dict, cuda_dev):
+    """The default train mode (tcgen05 kind::tf32 convolutions).  With 2 clips this fixture is hypersensitive to operand
+    rounding (batch statistics over 16-64 rows): PyTorch's OWN TF32 convolutions (cuDNN, torch's default for fp32 training)
+    move the gradients of the oracle by 25 % (median, relative L2 vs fp64) on it.  So the yardstick is measured, not assumed:
+    the oracle runs on the GPU with allow_tf32 and our error against the fp64 oracle must not exceed 1.5x its error (median
+    and maximum over the parameters); the loss must agree with fp64 to 2e-3."""
+    import train_helpers as TH
+    from yad_b200.train_engine import run_train_forward
+    x, tg = TH.train_inputs()
+    preds_o, loss_o, grads_o, _, xs = TH.oracle_train_step(ref_state_dict, x, tg, dtype=torch.float64)
+    # yardstick: oracle CNN on the GPU with cuDNN TF32, decode + loss on the CPU
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        sdc = {k: v.to(cuda_dev) for k, v in ref_state_dict.items()}
+        names = TH.param_names(sdc)
+        with torch.enable_grad():
+            for k in names:
+                sdc[k].requires_grad_(True)
+            O._BN_TRAINING[0] = True
+            try:
+                heads = O.neck(sdc, O.backbone(sdc, xs.to(cuda_dev), TH.TRAIN_CFG["block_layers"]))
+            finally:
+                O._BN_TRAINING[0] = False
+            sd_cpu = {k: v.cpu() for k, v in sdc.items()}       # differentiable copies: anchors keep their graph
+            L_res = -(-320 * x.shape[-1] // 441)
+            pr = O.decode([h.cpu() for h in heads], sd_cpu, L_res, xs.shape[-1], 2, TH.TRAIN_CFG, combine_scales=False)
+            loss_y, _ = O.detection_loss(pr, tg, O.DEFAULT_CONFIG["anchors"], 2)
+            loss_y.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    live = [k for k in names if float(grads_o[k].norm()) > 1e-9 and not k.endswith("_anchors")]
+    err_y = sorted(_rel_l2(sdc[k].grad.cpu(), grads_o[k]) for k in live)
+    m = _train_model(ref_state_dict, cuda_dev, train_dtype="tf32")
+    with torch.enable_grad():
+        preds = run_train_forward(m, m._train_engine(), xs.to(cuda_dev).contiguous(), xs.shape[-1], L_res)
+        loss, _ = _loss_fn()(preds, tg.to(cuda_dev))
+        loss.backward()
+    assert abs(float(loss) - float(loss_o)) < 2e-3 * float(loss_o), (float(loss), float(loss_o))
+    params = dict(m.named_parameters())
+    err = sorted(_rel_l2(params[k].grad.cpu(), grads_o[k]) for k in live)
+    med, med_y = err[len(err) // 2], err_y[len(err_y) // 2]
+    print(f"tf32 gradient error vs fp64: ours median {med:.3f} max {err[-1]:.3f}; cuDNN TF32 median {med_y:.3f} max {err_y[-1]:.3f}")
+    assert med <= 1.5 * med_y + 1e-3 and err[-1] <= 1.5 * err_y[-1] + 1e-3
+    for k in names:
+        if float(grads_o[k].norm()) <= 1e-9:
+            assert float(params[k].grad.double().norm()) < 1e-3, k

@@ -35,7 +35,7 @@ l64, g64 = oracle_from_xs(sd, xs32, torch.float64)
 l32, g32 = oracle_from_xs(sd, xs32, torch.float32)
 dev = torch.device("cuda", 0)
 cfg = yad_b200.default_config(); cfg["dropout"] = 0.0
-m = yad_b200.AudioDetectionNetwork(2, config=cfg); m.load_state_dict(sd); m = m.to(dev).train()
+m = yad_b200.AudioDetectionNetwork(2, config=cfg, train_dtype=(sys.argv[1] if len(sys.argv) > 1 else "f32")); m.load_state_dict(sd); m = m.to(dev).train()
 lf = yad_b200.AudioDetectionLoss(cfg["anchors"], 2, sample_duration=60, **cfg["train_config"]["loss_config"])
 with torch.enable_grad():
     preds = run_train_forward(m, m._train_engine(), xs32.to(dev).contiguous(), 256, 256146)
@@ -44,3 +44,29 @@ print("loss f64 %.8f o32 %.8f gpu %.8f" % (l64, l32, float(loss)))
 rel = lambda a, b: float((a.double().cpu().reshape(-1) - b.double().reshape(-1)).norm() / max(float(b.double().norm()), 1e-30))
 for k, p in m.named_parameters():
     print(f"{k:70s} |g| {float(g64[k].norm()):.3e}  gpu-f64 {rel(p.grad, g64[k]):.2e}  o32-f64 {rel(g32[k], g64[k]):.2e}")
+
+# ---- yardstick: the ORACLE itself on the GPU with cuDNN's TF32 convolutions (torch default) vs fp32
+def oracle_cuda(allow):
+    torch.backends.cudnn.allow_tf32 = allow
+    sdc = {k: v.to(dev) for k, v in sd.items()}
+    names = TH.param_names(sdc)
+    with torch.enable_grad():
+        for k in names: sdc[k].requires_grad_(True)
+        O._BN_TRAINING[0] = True
+        heads = O.neck(sdc, O.backbone(sdc, xs32.to(dev), (2, 2, 2, 2)))
+        O._BN_TRAINING[0] = False
+        import types
+        return heads, sdc, names
+try:
+    for allow in (False, True):
+        heads, sdc, names = oracle_cuda(allow)
+        # decode + loss on the CPU oracle (index ops); move heads to CPU keeping the graph
+        preds = O.decode([h.cpu() for h in heads], {k: v.cpu() if not v.requires_grad else v.cpu() for k, v in sdc.items()}, 256146, 256, 2, TH.TRAIN_CFG, combine_scales=False)
+        loss, _ = O.detection_loss(preds, tg, O.DEFAULT_CONFIG["anchors"], 2)
+        loss.backward()
+        errs = {k: rel(sdc[k].grad, g64[k]) for k in names if sdc[k].grad is not None and float(g64[k].norm()) > 1e-9}
+        ks = ["feature_extractor.conv1.weight", "feature_extractor.layer2.0.conv1.weight", "feature_extractor.layer4.1.conv2.weight",
+              "multiscale_module.cspsppf.conv7.conv.weight", "multiscale_module.rep_block4_1.blocks.0.conv1x1.norm.bias"]
+        print("torch-cuda allow_tf32=%s loss %.6f" % (allow, float(loss)), {k.split("module.")[-1]: "%.2e" % errs[k] for k in ks}, "median %.2e max %.2e" % (sorted(errs.values())[len(errs) // 2], max(errs.values())))
+except Exception as e:
+    import traceback; traceback.print_exc()

@@ -17,14 +17,21 @@ tg = synth.synth_targets(B, seed=11).to(dev)
 ev = lambda: torch.cuda.Event(enable_timing=True)
 for it in range(steps + 2):
     e = [ev() for _ in range(5)]
+    import time as _t
+    torch.cuda.synchronize()
+    c0 = _t.perf_counter()
     e[0].record()
     with torch.enable_grad():
         preds = m(x)
+        c1 = _t.perf_counter()
         e[1].record()
         loss, met = loss_fn(preds, tg)
+        c2 = _t.perf_counter()
         e[2].record()
         loss.backward()
+        c3 = _t.perf_counter()
         e[3].record()
+    print(f"   cpu: fwd {1e3*(c1-c0):.2f} loss {1e3*(c2-c1):.2f} bwd {1e3*(c3-c2):.2f} ms")
     opt.step(); opt.zero_grad()
     e[4].record()
     torch.cuda.synchronize()

@@ -27,6 +27,12 @@ class ConvDesc(C.Structure):
         "in_sw", "in_sh", "in_sb", "out_sw", "out_sh", "out_sb")]
 
 
+class CorrDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "B", "H", "W", "Cin", "ld_in", "Ho", "Wo", "Cout", "ld_out", "sh", "sw", "out_sw", "out_sh", "out_sb", "n_taps", "act",
+        "accumulate", "whole_rows")]
+
+
 class FlatDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "B", "H", "W", "Hp", "Wp", "Cin", "ld_in", "Cout", "ld_out", "co_off", "kh", "kw", "ph", "pw", "act", "ld_res",
@@ -61,6 +67,10 @@ SIGNATURES = {
     "yad_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "yad_bn_train_fwd": [_p, _i32, _i64, _i32, _p, _p, _f32, _f32, _p, _p, _i32, _p, _i32, _p, _p, _p, _p],
     "yad_bn_train_bwd": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p, _p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p],
+    "yad_corr_tf32": [C.POINTER(CorrDesc), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _p, _p, _i32, _i64, _p, _p, _p],
+    "yad_wgrad_tf32": [C.POINTER(CorrDesc), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _p, _p, _p, _p],
+    "yad_stem_im2col": [_p, _i64, _i32, _i32, _i32, _i32, _p, _p],
+    "yad_colsum_f64": [_p, _i32, _i64, _i32, _p, _p],
     "yad_permute4": [_p, C.POINTER(_i64), _p, C.POINTER(_i32), _i32, _p],
     "yad_add_f64_to_f32": [_p, _i32, _p, _p],
     "yad_add_act": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p],

@@ -362,6 +362,27 @@ __global__ void add_f64_to_f32_kernel(const double* __restrict__ a, int n, float
   if (i < n) out[i] += (float)a[i];
 }
 
+// im2col of the stem conv1 (2 -> 64, 7x7, stride 2, pad 3; modules/_backbone.py:127,143): patches[b,ho,wo,k], k = (kh*7 + kw)*C + c
+// for k < 49*C, zero above (K padded to a multiple of 32 so that the TF32 tensor-core kernels can treat conv1 as a 1x1 conv)
+__global__ void __launch_bounds__(TN_THREADS)
+stem_im2col_kernel(const float* __restrict__ x, int64_t B, int C, int H, int W, int Ho, int Wo, int K, float* __restrict__ out) {
+  const int64_t n = B * Ho * Wo * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int64_t p = i / K;
+    float v = 0.0f;
+    if (k < 49 * C) {
+      const int c = k % C, t = k / C;
+      const int kh = t / 7, kw = t % 7;
+      const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho);
+      const int64_t b = p / ((int64_t)Wo * Ho);
+      const int hi = 2 * ho + kh - 3, wi = 2 * wo + kw - 3;
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[((b * C + c) * H + hi) * W + wi];
+    }
+    out[i] = v;
+  }
+}
+
 static inline unsigned ew_blocks(int64_t n) {
   int64_t b = (n + TN_THREADS - 1) / TN_THREADS;
   const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 16;
@@ -525,6 +546,26 @@ int yad_permute4(const float* in, const int64_t* in_strides, float* out, const i
     total *= sizes[k];
   }
   permute4_kernel<<<ew_blocks(total), TN_THREADS, 0, (cudaStream_t)stream>>>(in, p, accumulate, out);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_stem_im2col(const float* x_nchw, int64_t B, int32_t C, int32_t H, int32_t W, int32_t K, float* patches, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x_nchw && patches && C >= 1 && H >= 1 && W >= 1 && K >= 49 * C, "yad_stem_im2col: bad arguments");
+  if (B == 0) return YAD_OK;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  stem_im2col_kernel<<<ew_blocks(B * Ho * Wo * K), TN_THREADS, 0, (cudaStream_t)stream>>>(x_nchw, B, C, H, W, Ho, Wo, K, patches);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_colsum_f64(const float* x, int32_t ld, int64_t N, int32_t C, double* ws, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x && ws && N >= 0 && C >= 1 && ld >= C, "yad_colsum_f64: bad arguments");
+  if (N == 0) return YAD_OK;
+  dim3 g((unsigned)((C + 31) / 32), (unsigned)(N >= 4096 ? 64 : 8));
+  col_reduce_kernel<2><<<g, TN_THREADS, 0, (cudaStream_t)stream>>>(x, ld, nullptr, 0, nullptr, 0, N, C, nullptr, nullptr, 0, ws, nullptr);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

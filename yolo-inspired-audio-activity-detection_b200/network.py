@@ -180,8 +180,9 @@ class _Buf(nn.Module):
 # ---------------------------------------------------------------- the model
 class AudioDetectionNetwork(nn.Module):
     def __init__(self, num_classes: int, config: Union[str, Dict[str, Any]] = DEFAULT_CONFIG_PATH,
-                 compute_dtype: str = "bf16"):
+                 compute_dtype: str = "bf16", train_dtype: str = "tf32"):
         super().__init__()
+        self.train_dtype = train_dtype      # convolutions of train() mode: "tf32" (tcgen05, cuDNN's default for fp32 training) | "f32"
         if isinstance(config, str):
             with open(config, "r") as f:
                 self.config = yaml.safe_load(f)
@@ -275,10 +276,10 @@ class AudioDetectionNetwork(nn.Module):
     def _train_engine(self):
         from .train_engine import TrainEngine
         dev = self.sm_anchors.device
-        key = (str(dev), "train")
+        key = (str(dev), "train", self.train_dtype)
         eng = self._engine_cache.get(key)
         if eng is None:
-            eng = self._engine_cache[key] = TrainEngine(self, dev)
+            eng = self._engine_cache[key] = TrainEngine(self, dev, self.train_dtype)
         return eng
 
     def _forward_train(self, x: torch.Tensor):

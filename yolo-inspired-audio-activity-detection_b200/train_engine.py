@@ -17,7 +17,15 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, F32, ConvDesc
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, F32, ConvDesc, CorrDesc
+
+
+def _c16(v: int) -> int:
+    return (v + 15) // 16 * 16
+
+
+def _c32(v: int) -> int:
+    return (v + 31) // 32 * 32
 
 
 class _T:
@@ -54,7 +62,10 @@ class _T:
 
 
 class TrainEngine:
-    def __init__(self, model, device: torch.device):
+    def __init__(self, model, device: torch.device, conv_mode: str = "tf32"):
+        if conv_mode not in ("tf32", "f32"):
+            raise ValueError("train conv_mode must be 'tf32' (tcgen05 tensor cores, cuDNN's default for fp32 training) or 'f32'")
+        self.conv_mode = conv_mode
         if device.type != "cuda":
             raise RuntimeError("yad_b200 train mode needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
         self.dev = device
@@ -64,7 +75,8 @@ class TrainEngine:
         self.nc = model.num_classes
         self.A = self.cfg["num_anchors"]
         self.E = 3 + self.nc
-        self._wcache: Dict[int, tuple] = {}
+        self._wcache: Dict[object, tuple] = {}
+        self._plans: Dict[tuple, dict] = {}
         self._step = 0
         for m in model.modules():
             if hasattr(m, "conv_reparam"):
@@ -75,8 +87,11 @@ class TrainEngine:
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _new(self, B, H, W, Cc, zero=False) -> _T:
-        f = torch.zeros if zero else torch.empty
-        return _T(f((B, H, W, Cc), device=self.dev, dtype=torch.float32))
+        """Fresh activation buffer.  Channel counts that are not a multiple of 32 (the 15-channel head tensors) get a
+        zero-filled pitch of 32 so that the TF32 kernels can read whole 128-byte rows."""
+        ld = Cc if Cc % 32 == 0 or Cc < 8 else (Cc + 31) // 32 * 32
+        f = torch.zeros if (zero or ld != Cc) else torch.empty
+        return _T(f((B, H, W, ld), device=self.dev, dtype=torch.float32), 0, Cc)
 
     def _grad(self, t: _T) -> _T:
         """Gradient slice matching ``t`` (one zero-initialised buffer per activation buffer; every backward accumulates)."""
@@ -116,8 +131,13 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ nodes (forward + recorded backward)
     def conv(self, x: _T, conv: nn.Conv2d, out: Optional[_T] = None, need_dx: bool = True) -> _T:
-        w, b = conv.weight, conv.bias
-        O, I, kh, kw = w.shape
+        I = conv.weight.shape[1]
+        if self.conv_mode == "tf32" and I >= 8 and x.off == 0 and x.ld % 32 == 0 and (I % 32 == 0 or x.ld == _c32(I)):
+            return self._conv_tf32(x, conv, out, need_dx)
+        return self._conv_f32(x, conv, out, need_dx)
+
+    def _conv_geom(self, x: _T, conv: nn.Conv2d, out: Optional[_T]):
+        O, I, kh, kw = conv.weight.shape
         sh, sw = conv.stride
         ph, pw = conv.padding
         assert x.C == I, (x.C, I)
@@ -125,6 +145,20 @@ class TrainEngine:
         if out is None:
             out = self._new(x.B, Ho, Wo, O)
         assert (out.B, out.H, out.W, out.C) == (x.B, Ho, Wo, O)
+        return O, I, kh, kw, sh, sw, ph, pw, Ho, Wo, out
+
+    def _wgrad_finish(self, w, b, dwk, dy: _T, O, I, kh, kw):
+        """dwk [kh][kw][Cin][Cout] -> += OIHW .grad; bias gradient = column sums of dY."""
+        self._permute(dwk.data_ptr(), (1, O, kw * I * O, I * O), self._pgrad(w), (O, I, kh, kw), True)
+        if b is not None:
+            bws = torch.zeros(O, device=self.dev, dtype=torch.float64)
+            _lib.check(self.lib.yad_colsum_f64(dy.ptr, dy.ld, dy.rows, O, bws.data_ptr(), self._s()), "bias grad (column sums)")
+            _lib.check(self.lib.yad_add_f64_to_f32(bws.data_ptr(), O, self._pgrad(b).data_ptr(), self._s()), "bias grad")
+
+    def _conv_f32(self, x: _T, conv: nn.Conv2d, out: Optional[_T], need_dx: bool) -> _T:
+        """fp32 CUDA-core path (parity mode; always used for the 2-channel stem conv1)."""
+        w, b = conv.weight, conv.bias
+        O, I, kh, kw, sh, sw, ph, pw, Ho, Wo, out = self._conv_geom(x, conv, out)
         wf, wt = self._packed(w)
         d = ConvDesc(B=x.B, H=x.H, W=x.W, Cin=I, ld_in=x.ld, Cout=O, ld_out=out.ld, co_off=0, kh=kh, kw=kw, sh=sh, sw=sw,
                      ph=ph, pw=pw, act=ACT_NONE, ld_res=0)
@@ -133,14 +167,116 @@ class TrainEngine:
             def bwd():
                 dy = self._grad(out)
                 dwk = torch.zeros_like(wf)
-                bws = torch.zeros(O, device=self.dev, dtype=torch.float64) if b is not None else None
-                _lib.check(self.lib.yad_conv_wgrad(C.byref(d), x.ptr, dy.ptr, dwk.data_ptr(), _lib.ptr(bws), self._s()), "conv wgrad")
-                self._permute(dwk.data_ptr(), (1, O, kw * I * O, I * O), self._pgrad(w), (O, I, kh, kw), True)
-                if b is not None:
-                    _lib.check(self.lib.yad_add_f64_to_f32(bws.data_ptr(), O, self._pgrad(b).data_ptr(), self._s()), "bias grad")
+                _lib.check(self.lib.yad_conv_wgrad(C.byref(d), x.ptr, dy.ptr, dwk.data_ptr(), 0, self._s()), "conv wgrad")
+                self._wgrad_finish(w, b, dwk, dy, O, I, kh, kw)
                 if need_dx:
                     dx = self._grad(x)
                     _lib.check(self.lib.yad_conv_dgrad(C.byref(d), dy.ptr, wt.data_ptr(), dx.ptr, dx.ptr, self._s()), "conv dgrad")
+            self._tape.append(bwd)
+        return out
+
+    def _packed_tf32(self, w: torch.Tensor, cin_pad: int, coutk: int):
+        """OIHW master weight -> K-major fp32 operands of the TF32 kernels: forward [ceil16(O)][kh*kw*cin_pad] and data
+        gradient [ceil16(I)][kh*kw*coutk] (un-flipped taps; the tap list carries the geometry)."""
+        key = ("tf32", id(w))
+        ver = (w._version, _lib.param_epoch, w.data_ptr(), cin_pad, coutk)
+        ent = self._wcache.get(key)
+        if ent is not None and ent[0] == ver:
+            return ent[1], ent[2]
+        O, I, kh, kw = w.shape
+        wd = w.detach()
+        if ent is not None and ent[1].shape == (_c16(O), kh, kw, cin_pad) and ent[2].shape == (_c16(I), kh, kw, coutk):
+            wf, wt = ent[1], ent[2]          # pad entries are already zero
+        else:
+            wf = torch.zeros((_c16(O), kh, kw, cin_pad), device=self.dev, dtype=torch.float32)
+            wt = torch.zeros((_c16(I), kh, kw, coutk), device=self.dev, dtype=torch.float32)
+        wf[:O, :, :, :I].copy_(wd.permute(0, 2, 3, 1))
+        wt[:I, :, :, :O].copy_(wd.permute(1, 2, 3, 0))
+        self._wcache[key] = (ver, wf, wt)
+        return wf, wt
+
+    def _conv_tf32(self, x: _T, conv: nn.Conv2d, out: Optional[_T], need_dx: bool) -> _T:
+        """tcgen05 kind::tf32 path: forward, data gradient (one correlation per output stride-parity class) and weight
+        gradient (MN-major operands) - see csrc/conv_tf32.cu."""
+        w, b = conv.weight, conv.bias
+        O, I, kh, kw, sh, sw, ph, pw, Ho, Wo, out = self._conv_geom(x, conv, out)
+        cin_pad = _c32(I)
+        plan = self._plans.get((id(conv), x.B, x.H, x.W, x.ld, out.ld))
+        if plan is None:
+            arr = lambda v: (C.c_int32 * len(v))(*v)      # noqa: E731
+            taps = [(a, c) for a in range(kh) for c in range(kw)]
+            plan = {"fwd": (arr([a - ph for a, _ in taps]), arr([c - pw for _, c in taps]), arr([(a * kw + c) * cin_pad for a, c in taps])),
+                    "dst": arr([a * kw + c for a, c in taps]), "dgrad": []}
+            coutk = _c32(O)
+            for rh in range(sh):
+                for rw in range(sw):
+                    Hc, Wc = (x.H - rh + sh - 1) // sh, (x.W - rw + sw - 1) // sw
+                    tp = [(a, c) for a, c in taps if (rh + ph - a) % sh == 0 and (rw + pw - c) % sw == 0]
+                    if Hc <= 0 or Wc <= 0:
+                        continue
+                    plan["dgrad"].append((rh, rw, Hc, Wc, len(tp), arr([(rh + ph - a) // sh for a, _ in tp]),
+                                          arr([(rw + pw - c) // sw for _, c in tp]), arr([(a * kw + c) * coutk for a, c in tp])))
+            self._plans[(id(conv), x.B, x.H, x.W, x.ld, out.ld)] = plan
+        assert out.off % 4 == 0
+        coutk = _c32(O)
+        wf, wt = self._packed_tf32(w, cin_pad, coutk)
+        d = CorrDesc(B=x.B, H=x.H, W=x.W, Cin=cin_pad, ld_in=x.ld, Ho=Ho, Wo=Wo, Cout=O, ld_out=out.ld, sh=sh, sw=sw, out_sw=0,
+                     out_sh=0, out_sb=0, n_taps=kh * kw, act=ACT_NONE, accumulate=0,
+                     whole_rows=1 if (out.off == 0 and out.ld in (O, _c32(O))) else 0)
+        fdh, fdw, fk = plan["fwd"]
+        _lib.check(self.lib.yad_corr_tf32(C.byref(d), fdh, fdw, fk, x.ptr, wf.data_ptr(), wf.shape[0], kh * kw * cin_pad, _lib.ptr(b),
+                                          out.ptr, self._s()), "conv fwd (tf32)")
+        if self._tape is not None:
+            def bwd():
+                dy = self._grad(out)
+                assert dy.off == 0 and dy.ld == coutk, "conv outputs are whole buffers with a 32-channel pitch"
+                dwk = torch.zeros((kh, kw, I, O), device=self.dev, dtype=torch.float32)
+                dg = CorrDesc(B=x.B, H=x.H, W=x.W, Cin=I, ld_in=x.ld, Ho=Ho, Wo=Wo, Cout=O, ld_out=dy.ld, sh=sh, sw=sw, out_sw=0,
+                              out_sh=0, out_sb=0, n_taps=kh * kw, act=ACT_NONE, accumulate=0)
+                _lib.check(self.lib.yad_wgrad_tf32(C.byref(dg), fdh, fdw, plan["dst"], x.ptr, dy.ptr, dwk.data_ptr(), self._s()), "conv wgrad (tf32)")
+                self._wgrad_finish(w, b, dwk, dy, O, I, kh, kw)
+                if need_dx:
+                    dx = self._grad(x)
+                    for rh, rw, Hc, Wc, nt, tdh, tdw, tk in plan["dgrad"]:
+                        if nt == 0:
+                            continue      # no tap reaches this parity class: its gradient is zero
+                        dd = CorrDesc(B=x.B, H=Ho, W=Wo, Cin=coutk, ld_in=dy.ld, Ho=Hc, Wo=Wc, Cout=I, ld_out=dx.ld, sh=1, sw=1,
+                                      out_sw=sw, out_sh=sh * x.W, out_sb=x.H * x.W, n_taps=nt, act=ACT_NONE, accumulate=1)
+                        _lib.check(self.lib.yad_corr_tf32(C.byref(dd), tdh, tdw, tk, dy.ptr, wt.data_ptr(), wt.shape[0], kh * kw * coutk,
+                                                          0, dx.ptr + 4 * (rh * x.W + rw) * dx.ld, self._s()), "conv dgrad (tf32)")
+            self._tape.append(bwd)
+        return out
+
+    def stem_tf32(self, xs: torch.Tensor, conv: nn.Conv2d) -> _T:
+        """conv1 (2 -> 64, 7x7, stride 2, no bias; modules/_backbone.py:143) on the tensor cores: im2col to K = 128 (98 real
+        taps x channels) and a 1x1 TF32 conv; its weight gradient is the 1x1 TF32 wgrad on the same patches."""
+        w = conv.weight
+        O, I, kh, kw = w.shape
+        assert (kh, kw) == (7, 7) and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (3, 3) and conv.bias is None
+        B, _, H, W = xs.shape
+        K = _c32(kh * kw * I)
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        patches = _T(torch.empty((B, Ho, Wo, K), device=self.dev, dtype=torch.float32))
+        _lib.check(self.lib.yad_stem_im2col(xs.data_ptr(), B, I, H, W, K, patches.ptr, self._s()), "stem im2col")
+        key = ("stem", id(w))
+        ver = (w._version, _lib.param_epoch, w.data_ptr())
+        ent = self._wcache.get(key)
+        if ent is None or ent[0] != ver:
+            wf = ent[1] if ent is not None else torch.zeros((_c16(O), K), device=self.dev, dtype=torch.float32)
+            wf[:O, :kh * kw * I].copy_(w.detach().permute(0, 2, 3, 1).reshape(O, -1))
+            self._wcache[key] = ent = (ver, wf)
+        wf = ent[1]
+        out = self._new(B, Ho, Wo, O)
+        z = (C.c_int32 * 1)(0)
+        d = CorrDesc(B=B, H=Ho, W=Wo, Cin=K, ld_in=K, Ho=Ho, Wo=Wo, Cout=O, ld_out=out.ld, sh=1, sw=1, out_sw=0, out_sh=0, out_sb=0,
+                     n_taps=1, act=ACT_NONE, accumulate=0, whole_rows=0)
+        _lib.check(self.lib.yad_corr_tf32(C.byref(d), z, z, z, patches.ptr, wf.data_ptr(), wf.shape[0], K, 0, out.ptr, self._s()), "stem conv1 (tf32)")
+        if self._tape is not None:
+            def bwd():
+                dy = self._grad(out)
+                dwk = torch.zeros((K, O), device=self.dev, dtype=torch.float32)
+                _lib.check(self.lib.yad_wgrad_tf32(C.byref(d), z, z, z, patches.ptr, dy.ptr, dwk.data_ptr(), self._s()), "stem wgrad (tf32)")
+                self._wgrad_finish(w, None, dwk, dy, O, I, kh, kw)       # rows 0..97 of dwk are [kh][kw][Cin][Cout]
             self._tape.append(bwd)
         return out
 
@@ -267,9 +403,12 @@ class TrainEngine:
         self._bn_counters: List[torch.Tensor] = []
         self._step += 1
         B, Cin, H0, _ = xs.shape
-        x0 = self._new(B, H0, T, Cin)
-        self._permute(xs.data_ptr(), (Cin * H0 * T, T, 1, H0 * T), x0.buf, (B, H0, T, Cin), False)     # NCHW -> NHWC
-        x = self.conv(x0, fe.conv1, need_dx=False)
+        if self.conv_mode == "tf32":
+            x = self.stem_tf32(xs, fe.conv1)
+        else:
+            x0 = self._new(B, H0, T, Cin)
+            self._permute(xs.data_ptr(), (Cin * H0 * T, T, 1, H0 * T), x0.buf, (B, H0, T, Cin), False)     # NCHW -> NHWC
+            x = self.conv(x0, fe.conv1, need_dx=False)
         x = self.conv(x, fe.conv2)
         x = self.bn(x, fe.bn1, ACT_RELU)
         x = self.dropout(x, float(fe.dropout_p))
