@@ -288,6 +288,7 @@ def run_train(args):
     torch.manual_seed(42)
     model, _ = build_model(dev, "bf16", deploy=False)
     model.train()
+    model.train_graphs = not args.no_graphs       # frontend + forward and the backward replayed from two CUDA graphs
     oc, ec = tc["optimizer_config"], tc["ema_config"]
     opt = yad_b200.FusedAdamEMA(model.parameters(), lr=oc["lr"], betas=tuple(oc["betas"]), eps=oc["eps"], weight_decay=oc["weight_decay"],
                                 ema_momentum=ec["momentum"], ema_N=ec["N"], use_ema=True)
@@ -350,10 +351,11 @@ def run_train(args):
         value = CLIP_SECONDS * B * world * K / (ms / 1e3)
         tfl = TRAIN_FLOP_PER_CLIP * B / (ms / K / 1e3) / 1e12
         line = {"metric": TRAIN_METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32",
                 "data": "synthetic",
                 "config": {"workload": f"train step (BASELINE configs[4]): {B} clips x 60 s per GPU, train-form net in train() mode "
-                                       "(batch-stat BatchNorm, dropout 0.4), fp32 CUDA-core convolutions, YOLO loss, backward, fused Adam + EMA; "
+                                       "(batch-stat BatchNorm, dropout 0.4), fp32 tensors with TF32 tcgen05 convolutions (cuDNN's default for fp32 training), "
+                                       "YOLO loss, backward, fused Adam + EMA, forward / backward replayed from CUDA graphs; "
                                        "one bucketed NCCL all-reduce of the 48.5 MB fp32 gradient arena per step when N > 1",
                            "clips_per_gpu": B, "clip_seconds": CLIP_SECONDS, "num_classes": 2,
                            "l2_policy": "per-step working set (169 MB PCM + 1.5 GB activations / gradients) is larger than the 126 MB L2",
@@ -361,10 +363,11 @@ def run_train(args):
                 "e2e": {"value": CLIP_SECONDS * B * world * Ke / (ms_e / 1e3), "unit": "audio-s/s",
                         "h2d_bytes_per_step": B * CLIP_SAMPLES * 4 + th.numel() * 4, "d2h_bytes_per_step": 3 * 8 * 8 + 3 * 4 * 4, "steps": Ke},
                 "gpu_launches": launches * K, "launches_per_step": launches, "clocks": sampler.summary(),
-                "roofline": {"kernel": "conv_simt_kernel / conv_wgrad_kernel (fp32 CUDA cores)", "bound": "fp32", "achieved": tfl,
-                             "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s", "frac": tfl / (148 * 128 * 2 * 1.965e9 / 1e12),
-                             "traffic": None, "note": "whole-step useful conv FLOPs (3 x train-form forward) / step time; peak = 148 SMs x "
-                                                      "128 FP32 lanes x 2 x 1.965 GHz (the fp32 convolutions do not use the tensor cores)"},
+                "roofline": {"kernel": "corr_tf32_kernel / wgrad_tf32_kernel (tcgen05 kind::tf32)", "bound": "tensor", "achieved": tfl,
+                             "peak": peaks["bf16_tflops_sustained"] / 2, "unit": "TFLOP/s", "frac": tfl / (peaks["bf16_tflops_sustained"] / 2),
+                             "traffic": None, "note": "whole-step useful conv FLOPs (3 x train-form forward) / step time; peak = half the "
+                                                      "measured sustained bf16 rate (TF32 runs at half the bf16 MMA rate); at 32 clips per GPU "
+                                                      "the step is bound by memory / launch latency of ~900 small kernels, not by the MMAs"},
                 "allreduce_ms": ar, "loss": met.get("aggregate_loss"), "cpu_baseline": None}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_train()
@@ -385,6 +388,7 @@ def main():
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer: the headline metric (BASELINE configs[1]+[2]); train: the data-parallel train step (configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="train workload: launch kernel by kernel instead of replaying CUDA graphs")
     ap.add_argument("--e2e-chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end pipeline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -196,6 +196,12 @@ int yad_decode(const void* const* heads, const int32_t* G, const int32_t* ld, co
                int32_t n_scales, int32_t dtype, const float* anchors /*[n_scales*A]*/, int32_t A, int32_t nc,
                float center_scaler, float duration, int64_t B, float* preds, yad_stream_t stream);
 
+/* yad_decode with the anchors read from DEVICE memory ([n_scales*A] f32, seconds): train mode, where the anchors are
+ * parameters that change every step (modules/_architecture.py:39-41) and the launch is replayed from a CUDA graph. */
+int yad_decode_dev(const void* const* heads, const int32_t* G, const int32_t* ld, const int32_t* stride,
+                   int32_t n_scales, int32_t dtype, const float* anchors_dev, int32_t A, int32_t nc,
+                   float center_scaler, float duration, int64_t B, float* preds, yad_stream_t stream);
+
 /* ------------------------------------------------------------------ segment NMS + post-processing
  * Replaces inference.py:42-110 (process_model_outputs) incl. torchvision.ops.batched_nms
  * ([tv] ops/boxes.py:48-120 -> torchvision::nms): class-agnostic per-clip greedy NMS on 1-D
@@ -270,6 +276,10 @@ int yad_add_act_bwd(const float* y, int32_t ld_y, const float* dy, int32_t ld_dy
                     int32_t ld_a, float* db, int32_t ld_b, float* dc, int32_t ld_c, yad_stream_t stream);
 /* Dropout with a counter-based mask: y = (accumulate ? y : 0) + x * keep(seed, i) / (1 - p); calling it on dy gives the backward. */
 int yad_dropout(const float* x, int64_t n, float p, uint64_t seed, int32_t accumulate, float* y, yad_stream_t stream);
+/* The same with the effective seed = seed + *seed_dev (a device-resident step counter, so that a captured CUDA graph draws a new
+ * mask on every replay). */
+int yad_dropout_dev(const float* x, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, int32_t accumulate, float* y,
+                    yad_stream_t stream);
 /* Backward of yad_hmean / yad_resize_w (gradients ACCUMULATED into din) and MaxPool(5,1,2) along W forward / backward
  * (first maximum of the window receives the gradient, accumulated with atomics). */
 int yad_hmean_bwd(const float* dout, int32_t ld_o, int64_t B, int32_t H, int32_t W, int32_t C, float* din, int32_t ld_i,

@@ -423,3 +423,41 @@ def test_train_network_tf32_vs_cudnn_tf32_yardstick(gold, ref_state_dict, cuda_d
     for k in names:
         if float(grads_o[k].norm()) <= 1e-9:
             assert float(params[k].grad.double().norm()) < 1e-3, k
+
+
+def test_train_step_cuda_graphs_equal_eager(ref_state_dict, cuda_dev):
+    """model.train_graphs = True: the third call of a shape captures frontend + forward and the backward into CUDA graphs,
+    later calls replay them.  Same predictions / loss / gradients as the eager path (dropout 0; fp32 red.add order differs)."""
+    import train_helpers as TH
+    x, tg = TH.train_inputs()
+    xd, tgd = x.to(cuda_dev), tg.to(cuda_dev)
+    out = {}
+    for mode in ("eager", "graph"):
+        m = _train_model(ref_state_dict, cuda_dev, train_dtype="tf32")
+        opt = yad_b200.FusedAdamEMA(m.parameters(), lr=1e-3, weight_decay=0.002)
+        m.train_graphs = mode == "graph"
+        loss_fn = _loss_fn()
+        rec = []
+        for it in range(5):
+            m.load_state_dict(ref_state_dict)          # same parameters AND running statistics at every iteration
+            with torch.enable_grad():
+                preds = m(xd)
+                loss, _ = loss_fn(preds, tgd)
+                loss.backward()
+            rec.append((float(loss), opt.grad.clone(), m.feature_extractor.bn1.running_mean.clone(),
+                        int(m.feature_extractor.bn1.num_batches_tracked)))
+            opt.zero_grad()
+        out[mode] = rec
+        if mode == "graph":
+            assert any(e["g"] is not None for e in m._train_engine()._graphs.values()), "the graphs were not captured"
+    print("losses eager", [r[0] for r in out["eager"]], "graph", [r[0] for r in out["graph"]])
+    print("grad rel: eager3-vs-eager4", _rel_l2(out["eager"][3][1].cpu(), out["eager"][4][1].cpu()), "graph3-vs-eager3",
+          _rel_l2(out["graph"][3][1].cpu(), out["eager"][3][1].cpu()))
+    for it in (3, 4):        # replayed iterations
+        le, ge, re_, _ = out["eager"][it]
+        lg, gg, rg, nb = out["graph"][it]
+        assert abs(le - lg) < 1e-6 * abs(le), (le, lg)     # the forward is bit-reproducible (no split-K atomics in it)
+        # backward: fp32 red.add order (wgrad, split-K dgrad) varies; TF32 operand truncation turns that 1e-7 noise into ~1e-3
+        assert _rel_l2(gg.cpu(), ge.cpu()) < 1e-2
+        np.testing.assert_allclose(rg.cpu().numpy(), re_.cpu().numpy(), atol=1e-5)
+    assert out["graph"][4][3] == 1                          # load_state_dict reset the counter, the replay incremented it

@@ -9,7 +9,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device("cuda", 0)
 cfg = yad_b200.default_config()
 torch.manual_seed(42)
-m = yad_b200.AudioDetectionNetwork(2, config=cfg).to(dev).train()
+m = yad_b200.AudioDetectionNetwork(2, config=cfg, train_dtype=(sys.argv[3] if len(sys.argv) > 3 else "tf32")).to(dev).train()
+m.train_graphs = len(sys.argv) > 4 and sys.argv[4] == "graph"
 opt = yad_b200.FusedAdamEMA(m.parameters(), lr=1e-3, weight_decay=0.002, ema_momentum=0.002, use_ema=True)
 loss_fn = yad_b200.AudioDetectionLoss(cfg["anchors"], 2, sample_duration=60, **cfg["train_config"]["loss_config"])
 x = (torch.randn(B, 1, 1323000, device=dev) * 0.1)

@@ -59,6 +59,8 @@ SIGNATURES = {
     "yad_repvgg_merge": [_p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p],
     "yad_decode": [C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i32, _i32, C.POINTER(_f32), _i32,
                    _i32, _f32, _f32, _i64, _p, _p],
+    "yad_decode_dev": [C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i32, _i32, _p, _i32,
+                       _i32, _f32, _f32, _i64, _p, _p],
     "yad_nms": [_p, _i64, _i32, _i32, _f64, _f32, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p, _p],
     "yad_compact_segments": [_p, _p, _i64, _i32, _p, _p, _p, _p],
     "yad_build_targets": [_p, _i32, _p, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p],
@@ -76,6 +78,7 @@ SIGNATURES = {
     "yad_add_act": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p],
     "yad_add_act_bwd": [_p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p, _i32, _p, _i32, _p],
     "yad_dropout": [_p, _i64, _f32, C.c_uint64, _i32, _p, _p],
+    "yad_dropout_dev": [_p, _i64, _f32, C.c_uint64, _p, _i32, _p, _p],
     "yad_hmean_bwd": [_p, _i32, _i64, _i32, _i32, _i32, _p, _i32, _p],
     "yad_resize_w_bwd": [_p, _i32, _i64, _i32, _i32, _i32, _p, _i32, _p],
     "yad_maxpool5_w": [_p, _i32, _i64, _i32, _i32, _p, _i32, _p],

@@ -15,6 +15,7 @@ struct DecodeParams {
   const void* head[4];
   int32_t G[4], ld[4], stride[4], row0[4];
   float anchors[4 * 8];
+  const float* anchors_dev;     // optional [n_scales * A] on the device (train mode: the anchors are parameters)
   int32_t n_scales, A, nc, rows_total;
   float center_scaler, duration;
 };
@@ -41,7 +42,7 @@ __global__ void decode_kernel(DecodeParams p, int64_t B, float* __restrict__ pre
   c = __fdiv_rn(__fmul_rn(c, (float)p.stride[s]), p.center_scaler);
   // widths = (sigmoid*2)^2 * anchor                                  (_architecture.py:150)
   float w2 = __fmul_rn(sigmoid_f(tw), 2.0f);
-  float w = __fmul_rn(__fmul_rn(w2, w2), p.anchors[s * 8 + a]);
+  float w = __fmul_rn(__fmul_rn(w2, w2), p.anchors_dev != nullptr ? p.anchors_dev[s * p.A + a] : p.anchors[s * 8 + a]);
   c = fminf(fmaxf(c, 0.0f), p.duration);
   w = fminf(fmaxf(w, 0.0f), p.duration);
   o[E - 2] = c;
@@ -280,8 +281,8 @@ __global__ void compact_kernel(const float* __restrict__ seg_rows, const int32_t
 
 extern "C" {
 
-int yad_decode(const void* const* heads, const int32_t* G, const int32_t* ld, const int32_t* stride,
-               int32_t n_scales, int32_t dtype, const float* anchors, int32_t A, int32_t nc,
+static int decode_impl(const void* const* heads, const int32_t* G, const int32_t* ld, const int32_t* stride,
+               int32_t n_scales, int32_t dtype, const float* anchors, const float* anchors_dev, int32_t A, int32_t nc,
                float center_scaler, float duration, int64_t B, float* preds, yad_stream_t stream) {
   YAD_CHECK_ARG(n_scales >= 1 && n_scales <= 4, "yad_decode: n_scales=%d not in [1,4]", n_scales);
   YAD_CHECK_ARG(A >= 1 && A <= 8, "yad_decode: A=%d not in [1,8]", A);
@@ -302,8 +303,9 @@ int yad_decode(const void* const* heads, const int32_t* G, const int32_t* ld, co
     p.stride[s] = stride[s];
     p.row0[s] = rows;
     rows += G[s] * A;
-    for (int a = 0; a < A; ++a) p.anchors[s * 8 + a] = anchors[s * A + a];
+    for (int a = 0; a < A; ++a) p.anchors[s * 8 + a] = anchors != nullptr ? anchors[s * A + a] : 0.0f;
   }
+  p.anchors_dev = anchors_dev;
   p.n_scales = n_scales;
   p.A = A;
   p.nc = nc;
@@ -319,6 +321,20 @@ int yad_decode(const void* const* heads, const int32_t* G, const int32_t* ld, co
     yad::decode_kernel<__nv_bfloat16><<<blocks, threads, 0, (cudaStream_t)stream>>>(p, B, preds);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
+}
+
+int yad_decode(const void* const* heads, const int32_t* G, const int32_t* ld, const int32_t* stride,
+               int32_t n_scales, int32_t dtype, const float* anchors, int32_t A, int32_t nc,
+               float center_scaler, float duration, int64_t B, float* preds, yad_stream_t stream) {
+  YAD_CHECK_ARG(anchors != nullptr, "yad_decode: null anchors");
+  return decode_impl(heads, G, ld, stride, n_scales, dtype, anchors, nullptr, A, nc, center_scaler, duration, B, preds, stream);
+}
+
+int yad_decode_dev(const void* const* heads, const int32_t* G, const int32_t* ld, const int32_t* stride,
+                   int32_t n_scales, int32_t dtype, const float* anchors_dev, int32_t A, int32_t nc,
+                   float center_scaler, float duration, int64_t B, float* preds, yad_stream_t stream) {
+  YAD_CHECK_ARG(anchors_dev != nullptr, "yad_decode_dev: null anchors");
+  return decode_impl(heads, G, ld, stride, n_scales, dtype, nullptr, anchors_dev, A, nc, center_scaler, duration, B, preds, stream);
 }
 
 int yad_nms(const float* preds, int64_t B, int32_t P, int32_t nc, double iou_thr, float conf_thr,

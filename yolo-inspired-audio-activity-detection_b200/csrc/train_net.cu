@@ -223,7 +223,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 __global__ void __launch_bounds__(TN_THREADS)
-dropout_kernel(const float* __restrict__ x, int64_t n, float p, uint64_t seed, int accumulate, float* __restrict__ y) {
+dropout_kernel(const float* __restrict__ x, int64_t n, float p, uint64_t seed, const uint64_t* __restrict__ seed_dev, int accumulate,
+               float* __restrict__ y) {
+  if (seed_dev != nullptr) seed += *seed_dev;      // CUDA-graph replays: the step counter lives on the device
   const float scale = 1.0f / (1.0f - p);
   const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -477,7 +479,17 @@ int yad_dropout(const float* x, int64_t n, float p, uint64_t seed, int32_t accum
   using namespace yad;
   YAD_CHECK_ARG(x && y && n >= 0 && p >= 0.0f && p < 1.0f, "yad_dropout: bad arguments");
   if (n == 0) return YAD_OK;
-  dropout_kernel<<<ew_blocks(n), TN_THREADS, 0, (cudaStream_t)stream>>>(x, n, p, seed, accumulate, y);
+  dropout_kernel<<<ew_blocks(n), TN_THREADS, 0, (cudaStream_t)stream>>>(x, n, p, seed, nullptr, accumulate, y);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_dropout_dev(const float* x, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, int32_t accumulate, float* y,
+                    yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x && y && seed_dev && n >= 0 && p >= 0.0f && p < 1.0f, "yad_dropout_dev: bad arguments");
+  if (n == 0) return YAD_OK;
+  dropout_kernel<<<ew_blocks(n), TN_THREADS, 0, (cudaStream_t)stream>>>(x, n, p, seed, seed_dev, accumulate, y);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

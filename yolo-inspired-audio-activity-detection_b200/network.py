@@ -182,6 +182,7 @@ class AudioDetectionNetwork(nn.Module):
     def __init__(self, num_classes: int, config: Union[str, Dict[str, Any]] = DEFAULT_CONFIG_PATH,
                  compute_dtype: str = "bf16", train_dtype: str = "tf32"):
         super().__init__()
+        self.train_graphs = False           # replay the train step from CUDA graphs (needs stable .grad buffers, e.g. FusedAdamEMA)
         self.train_dtype = train_dtype      # convolutions of train() mode: "tf32" (tcgen05, cuDNN's default for fp32 training) | "f32"
         if isinstance(config, str):
             with open(config, "r") as f:
@@ -285,9 +286,14 @@ class AudioDetectionNetwork(nn.Module):
     def _forward_train(self, x: torch.Tensor):
         """train() mode (pipeline/_trainer.py:98-104): batch-statistics BatchNorm, dropout, differentiable w.r.t. every
         parameter.  fp32 throughout, like the reference's training."""
-        from .train_engine import run_train_forward
+        from .train_engine import run_train_forward, run_train_forward_graphed
         fe = self._engine(frontend_only=True)
         B, _, L = x.shape
+        if self.train_graphs and torch.is_grad_enabled():
+            with torch.cuda.device(fe.dev):
+                out = run_train_forward_graphed(self, self._train_engine(), fe, x.contiguous().float())
+            if out is not None:
+                return out
         with torch.no_grad(), torch.cuda.device(fe.dev):
             xs = fe.run_frontend(x, {})
         L_res = -(-fe.rs_P * L // fe.rs_O)

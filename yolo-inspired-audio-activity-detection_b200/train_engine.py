@@ -11,6 +11,7 @@ stream and the autograd hook (`_TrainFn`), nothing else.  No CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -78,6 +79,12 @@ class TrainEngine:
         self._wcache: Dict[object, tuple] = {}
         self._plans: Dict[tuple, dict] = {}
         self._step = 0
+        self._seed_dev = torch.zeros(1, device=device, dtype=torch.int64)     # train-step counter (dropout seed offset)
+        self._graphs: Dict[tuple, dict] = {}
+        self._force_repack = False
+        # split-K (fp32 red.add of partial sums) for small forward grids: faster, but the summation order then varies from run
+        # to run and TF32 operand truncation amplifies that 1e-7 noise to ~1e-3 after 20 layers; off = reproducible forward
+        self.fwd_split_k = os.environ.get("YAD_TRAIN_FWD_SPLITK", "0") == "1"
         for m in model.modules():
             if hasattr(m, "conv_reparam"):
                 raise NotImplementedError("yad_b200: train-mode forward of the deploy (re-parameterised) form is not built")
@@ -181,7 +188,7 @@ class TrainEngine:
         key = ("tf32", id(w))
         ver = (w._version, _lib.param_epoch, w.data_ptr(), cin_pad, coutk)
         ent = self._wcache.get(key)
-        if ent is not None and ent[0] == ver:
+        if ent is not None and ent[0] == ver and not self._force_repack:
             return ent[1], ent[2]
         O, I, kh, kw = w.shape
         wd = w.detach()
@@ -222,7 +229,7 @@ class TrainEngine:
         wf, wt = self._packed_tf32(w, cin_pad, coutk)
         d = CorrDesc(B=x.B, H=x.H, W=x.W, Cin=cin_pad, ld_in=x.ld, Ho=Ho, Wo=Wo, Cout=O, ld_out=out.ld, sh=sh, sw=sw, out_sw=0,
                      out_sh=0, out_sb=0, n_taps=kh * kw, act=ACT_NONE, accumulate=0,
-                     whole_rows=1 if (out.off == 0 and out.ld in (O, _c32(O))) else 0)
+                     whole_rows=1 if (self.fwd_split_k and out.off == 0 and out.ld in (O, _c32(O))) else 0)
         fdh, fdw, fk = plan["fwd"]
         _lib.check(self.lib.yad_corr_tf32(C.byref(d), fdh, fdw, fk, x.ptr, wf.data_ptr(), wf.shape[0], kh * kw * cin_pad, _lib.ptr(b),
                                           out.ptr, self._s()), "conv fwd (tf32)")
@@ -261,7 +268,7 @@ class TrainEngine:
         key = ("stem", id(w))
         ver = (w._version, _lib.param_epoch, w.data_ptr())
         ent = self._wcache.get(key)
-        if ent is None or ent[0] != ver:
+        if ent is None or ent[0] != ver or self._force_repack:
             wf = ent[1] if ent is not None else torch.zeros((_c16(O), K), device=self.dev, dtype=torch.float32)
             wf[:O, :kh * kw * I].copy_(w.detach().permute(0, 2, 3, 1).reshape(O, -1))
             self._wcache[key] = ent = (ver, wf)
@@ -323,16 +330,19 @@ class TrainEngine:
         return out
 
     def dropout(self, x: _T, p: float) -> _T:
+        """nn.Dropout (modules/_backbone.py:133,147) with a counter-based mask; the step counter lives on the device so that
+        a captured CUDA graph draws a fresh mask on every replay."""
         if p <= 0.0:
             return x
         assert x.off == 0 and x.C == x.ld
         out = self._new(x.B, x.H, x.W, x.C)
-        seed = (int(torch.initial_seed()) * 1000003 + self._step) & ((1 << 63) - 1)
+        seed = (int(torch.initial_seed()) * 1000003) & ((1 << 62) - 1)
         n = x.buf.numel()
-        _lib.check(self.lib.yad_dropout(x.ptr, n, p, seed, 0, out.ptr, self._s()), "dropout")
+        sd = self._seed_dev
+        _lib.check(self.lib.yad_dropout_dev(x.ptr, n, p, seed, sd.data_ptr(), 0, out.ptr, self._s()), "dropout")
         if self._tape is not None:
             def bwd():
-                _lib.check(self.lib.yad_dropout(self._grad(out).ptr, n, p, seed, 1, self._grad(x).ptr, self._s()), "dropout bwd")
+                _lib.check(self.lib.yad_dropout_dev(self._grad(out).ptr, n, p, seed, sd.data_ptr(), 1, self._grad(x).ptr, self._s()), "dropout bwd")
             self._tape.append(bwd)
         return out
 
@@ -402,6 +412,7 @@ class TrainEngine:
         self._grads: Dict[int, torch.Tensor] = {}
         self._bn_counters: List[torch.Tensor] = []
         self._step += 1
+        self._seed_dev.add_(1)
         B, Cin, H0, _ = xs.shape
         if self.conv_mode == "tf32":
             x = self.stem_tf32(xs, fe.conv1)
@@ -459,8 +470,7 @@ class TrainEngine:
         # anchor decode (modules/_architecture.py:132-156), one call per scale
         dur = float(self.cfg["sample_duration"])
         anchors = [model.sm_anchors, model.md_anchors, model.lg_anchors]
-        anc_s = torch.stack([a.detach() for a in anchors]).float() * dur          # [3, A] seconds, device
-        anc_h = anc_s.cpu()
+        anc_s = torch.stack([a.detach() for a in anchors]).float() * dur          # [3, A] seconds, stays on the device
         center_scaler = T / (L_res / self.cfg["new_sample_rate"])
         preds, heads = [], (n2, n3, n4)
         for s, h in enumerate(heads):
@@ -468,9 +478,8 @@ class TrainEngine:
             assert h.C == nh
             p = torch.empty((B, G, self.A, self.E), device=self.dev, dtype=torch.float32)
             hp = (C.c_void_p * 1)(h.ptr)
-            anc = (C.c_float * self.A)(*anc_h[s].tolist())
-            _lib.check(self.lib.yad_decode(hp, (C.c_int32 * 1)(G), (C.c_int32 * 1)(h.ld), (C.c_int32 * 1)(T // G), 1, F32, anc, self.A,
-                                           self.nc, center_scaler, dur, B, p.data_ptr(), self._s()), "decode")
+            _lib.check(self.lib.yad_decode_dev(hp, (C.c_int32 * 1)(G), (C.c_int32 * 1)(h.ld), (C.c_int32 * 1)(T // G), 1, F32,
+                                               anc_s[s].data_ptr(), self.A, self.nc, center_scaler, dur, B, p.data_ptr(), self._s()), "decode")
             preds.append(p)
         state = None
         if record:
@@ -523,9 +532,88 @@ class _TrainFn(torch.autograd.Function):
         return (None,) * len(ctx.needs_input_grad)
 
 
+class _GraphFn(torch.autograd.Function):
+    """Replays the captured forward / backward CUDA graphs of one (batch, length) shape."""
+
+    @staticmethod
+    def forward(ctx, g: dict, x: torch.Tensor, *params):
+        g["x"].copy_(x)
+        g["fwd"].replay()
+        _lib.launch_count += g["fwd_launches"]
+        ctx.g = g
+        return tuple(p.detach() for p in g["preds"])
+
+    @staticmethod
+    def backward(ctx, *dpreds):
+        g = ctx.g
+        with torch.no_grad():
+            for dst, dp in zip(g["dpreds"], dpreds):
+                if dp is None:
+                    dst.zero_()
+                else:
+                    dst.copy_(dp)
+            g["bwd"].replay()
+        _lib.launch_count += g["bwd_launches"]
+        _lib.param_epoch += 1
+        return (None,) * len(ctx.needs_input_grad)
+
+
+def _capture_train_graphs(model, eng: TrainEngine, fe, x: torch.Tensor) -> dict:
+    """Captures frontend + train-mode forward and the backward of one input shape into two CUDA graphs (one memory pool).
+    The ~900 launches of a train step are CPU-bound when issued one by one; replayed they are GPU-bound."""
+    B, _, L = x.shape
+    L_res = -(-fe.rs_P * L // fe.rs_O)
+    for p in eng._params:                      # the graphs write through these pointers: they must exist and stay put
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    g = {"x": torch.empty_like(x), "plan": {}, "fe": fe}      # `fe` owns the packed frontend constants the graph points into
+    g["x"].copy_(x)
+    torch.cuda.synchronize(eng.dev)
+    pool = torch.cuda.graph_pool_handle()
+    fwd, bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    eng._force_repack = True                   # weight packing must be part of the graph (the parameters change every step)
+    try:
+        n0 = _lib.launch_count
+        with torch.cuda.graph(fwd, pool=pool):
+            xs = fe.run_frontend(g["x"], g["plan"])
+            preds, state = eng.forward(xs, xs.shape[-1], L_res, True)
+        n1 = _lib.launch_count
+        g["dpreds"] = [torch.zeros_like(p) for p in preds]
+        torch.cuda.synchronize(eng.dev)
+        with torch.cuda.graph(bwd, pool=pool):
+            eng.backward(state, g["dpreds"])
+        n2 = _lib.launch_count
+    finally:
+        eng._force_repack = False
+    _lib.launch_count = n0
+    g.update(fwd=fwd, bwd=bwd, preds=preds, state=state, fwd_launches=n1 - n0, bwd_launches=n2 - n1,
+             grad_ptrs=[p.grad.data_ptr() for p in eng._params])
+    return g
+
+
 def run_train_forward(model, eng: TrainEngine, xs: torch.Tensor, T: int, L_res: int):
     eng._params = [p for p in model.parameters() if p.requires_grad]
     if torch.is_grad_enabled() and eng._params:
         return _TrainFn.apply(eng, xs, T, L_res, *eng._params)
     preds, _ = eng.forward(xs, T, L_res, False)
     return tuple(preds)
+
+
+def run_train_forward_graphed(model, eng: TrainEngine, fe, x: torch.Tensor):
+    """PCM -> predictions through CUDA graphs (``model.train_graphs = True``).  The first two calls of a shape run eagerly
+    (lazy initialisation, allocator warm-up), the third captures, later ones replay.  Falls back to the eager path when a
+    parameter's ``.grad`` buffer was replaced (``zero_grad(set_to_none=True)``) - graphs need stable pointers."""
+    eng._params = [p for p in model.parameters() if p.requires_grad]
+    key = (tuple(x.shape), tuple(p.data_ptr() for p in eng._params[:8]))
+    ent = eng._graphs.get(key)
+    if ent is None:
+        ent = eng._graphs[key] = {"warm": 0, "g": None}
+    if ent["g"] is None:
+        if ent["warm"] < 2:
+            ent["warm"] += 1
+            return None
+        ent["g"] = _capture_train_graphs(model, eng, fe, x)
+    g = ent["g"]
+    if any(p.grad is None or p.grad.data_ptr() != q for p, q in zip(eng._params, g["grad_ptrs"])):
+        return None
+    return _GraphFn.apply(g, x, *eng._params)
