@@ -17,6 +17,13 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
 
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    """Other test modules switch autograd off globally; these tests compare against PyTorch autograd."""
+    with torch.enable_grad():
+        yield
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
