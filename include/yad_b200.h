@@ -264,6 +264,11 @@ int yad_conv_wgrad(const yad_conv_desc* d, const float* x, const float* dy, floa
 int yad_bn_train_fwd(const float* x, int32_t ld_x, int64_t N, int32_t C, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, int32_t act, float* y, int32_t ld_y,
                      float* save_mean, float* save_invstd, double* ws, yad_stream_t stream);
+/* The same from pre-computed moments: sums [2*C] f64 = (sum x, sum x^2) over the N rows (yad_corr_tf32's `stats`): one launch
+ * that finalises mean / invstd, updates the running statistics and applies. */
+int yad_bn_train_apply(const float* x, int32_t ld_x, int64_t N, int32_t C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, int32_t act, float* y, int32_t ld_y,
+                       float* save_mean, float* save_invstd, const double* sums, yad_stream_t stream);
 /* Its backward, the activation's included: g = dy * act'(y); dx (overwritten, or += when accumulate) = gamma * invstd * (g - mean(g) - xhat * mean(g xhat));
  * dgamma += sum g xhat; dbeta += sum g. */
 int yad_bn_train_bwd(const float* x, int32_t ld_x, const float* y, int32_t ld_y, const float* dy, int32_t ld_dy, int64_t N, int32_t C,
@@ -326,8 +331,11 @@ typedef struct {
   int32_t whole_rows;         /* out is a dense buffer of which this call owns every channel of the pitch: lets a small
                                  problem zero-fill it and split the K loop over CTAs (fp32 red.add of partial sums) */
 } yad_corr_desc;
+/* stats (may be NULL): [2*Cout] f64, += per-channel sum and sum of squares of the values written (the batch moments of the
+ * BatchNorm that follows the conv, fused into the epilogue; feed them to yad_bn_train_apply). */
 int yad_corr_tf32(const yad_corr_desc* d, const int32_t* tap_dh, const int32_t* tap_dw, const int32_t* tap_k, const float* in,
-                  const float* weight, int32_t cout_pad, int64_t k_total, const float* bias, float* out, yad_stream_t stream);
+                  const float* weight, int32_t cout_pad, int64_t k_total, const float* bias, float* out, double* stats,
+                  yad_stream_t stream);
 int yad_wgrad_tf32(const yad_corr_desc* d, const int32_t* tap_dh, const int32_t* tap_dw, const int32_t* tap_dst, const float* x,
                    const float* dy, float* dw, yad_stream_t stream);
 /* im2col of the stem conv1 (C -> 64, 7x7, stride 2, pad 3): x NCHW f32 [B,C,H,W] -> patches [B,(H-1)/2+1,(W-1)/2+1,K] with

@@ -68,8 +68,9 @@ SIGNATURES = {
     "yad_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "yad_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "yad_bn_train_fwd": [_p, _i32, _i64, _i32, _p, _p, _f32, _f32, _p, _p, _i32, _p, _i32, _p, _p, _p, _p],
+    "yad_bn_train_apply": [_p, _i32, _i64, _i32, _p, _p, _f32, _f32, _p, _p, _i32, _p, _i32, _p, _p, _p, _p],
     "yad_bn_train_bwd": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p, _p, _p, _i32, _p, _i32, _i32, _p, _p, _p, _p],
-    "yad_corr_tf32": [C.POINTER(CorrDesc), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _p, _p, _i32, _i64, _p, _p, _p],
+    "yad_corr_tf32": [C.POINTER(CorrDesc), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _p, _p, _i32, _i64, _p, _p, _p, _p],
     "yad_wgrad_tf32": [C.POINTER(CorrDesc), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _p, _p, _p, _p],
     "yad_stem_im2col": [_p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "yad_colsum_f64": [_p, _i32, _i64, _i32, _p, _p],

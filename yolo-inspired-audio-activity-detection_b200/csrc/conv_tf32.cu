@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1)
 corr_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                  const __grid_constant__ CUtensorMap map_w, const TfParams p, const float* __restrict__ bias,
-                 float* __restrict__ out) {
+                 float* __restrict__ out, double* __restrict__ stats) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = p.BN * 128;
@@ -178,6 +178,35 @@ corr_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
+      if (stats != nullptr) {
+        // per-channel sum / sum of squares of the conv output (the BatchNorm batch moments, modules/_common.py:43-48): lane l
+        // ends up with column c0 + l of this warp's 32 rows (32-step transpose-reduce with shuffles), then one fp64 atomic
+        float a[32], b2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = row_ok ? __uint_as_float(v[j]) + (bias != nullptr && n0 + c0 + j < p.Cout ? __ldg(bias + n0 + c0 + j) : 0.0f) : 0.0f;
+          a[j] = x;
+          b2[j] = x * x;
+        }
+        // butterfly transpose-reduce: after the steps 16, 8, 4, 2, 1 element 0 of lane l is the sum over the warp of column l
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int j = 0; j < off; ++j) {
+            const float sa = up ? a[j] : a[j + off], ka = up ? a[j + off] : a[j];
+            const float sb = up ? b2[j] : b2[j + off], kb = up ? b2[j + off] : b2[j];
+            a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+            b2[j] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+          }
+        }
+        const float s1 = a[0], s2 = b2[0];
+        const int n = n0 + c0 + lane;
+        if (n < p.Cout) {
+          atomicAdd(stats + n, (double)s1);
+          atomicAdd(stats + p.Cout + n, (double)s2);
+        }
+      }
       if (!row_ok) continue;
       const int nbase = n0 + c0;
       if (nbase >= p.Cout) continue;
@@ -445,7 +474,8 @@ static int build_parity_maps(const float* in, int B, int H, int W, int C, int ld
 extern "C" {
 
 int yad_corr_tf32(const yad_corr_desc* d, const int32_t* tap_dh, const int32_t* tap_dw, const int32_t* tap_k, const float* in,
-                  const float* weight, int32_t cout_pad, int64_t k_total, const float* bias, float* out, yad_stream_t stream) {
+                  const float* weight, int32_t cout_pad, int64_t k_total, const float* bias, float* out, double* stats,
+                  yad_stream_t stream) {
   using namespace yad;
   YAD_CHECK_ARG(d && tap_dh && tap_dw && tap_k && in && weight && out, "yad_corr_tf32: null pointer");
   YAD_CHECK_ARG(d->Cin % 32 == 0 && d->Cin >= 32 && d->ld_in >= d->Cin && d->ld_in % 4 == 0,
@@ -504,7 +534,7 @@ int yad_corr_tf32(const yad_corr_desc* d, const int32_t* tap_dh, const int32_t* 
   const int n_iters = n_taps * p.cin_chunks, tiles = p.n_wt * p.n_ht * p.n_bt * (cout_pad / BN);
   const int sms = sm_count() > 0 ? sm_count() : 148;
   int ksplit = 1;
-  if ((d->accumulate || d->whole_rows) && d->act == YAD_ACT_NONE && tiles < sms) {
+  if ((d->accumulate || d->whole_rows) && d->act == YAD_ACT_NONE && tiles < sms && stats == nullptr) {
     ksplit = sms / tiles;
     if (ksplit > n_iters / 2) ksplit = n_iters / 2;
     if (ksplit > 32) ksplit = 32;
@@ -538,7 +568,7 @@ int yad_corr_tf32(const yad_corr_desc* d, const int32_t* tap_dh, const int32_t* 
     if (rc) return rc;
   }
   dim3 grid((unsigned)(p.n_wt * p.n_ht * p.n_bt), (unsigned)(cout_pad / BN), (unsigned)ksplit);
-  corr_tf32_kernel<<<grid, TF_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], map_w, p, bias, out);
+  corr_tf32_kernel<<<grid, TF_THREADS, smem, st>>>(maps[0], maps[1], maps[2], maps[3], map_w, p, bias, out, stats);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

@@ -164,6 +164,42 @@ bn_apply_kernel(const float* __restrict__ x, int ld_x, int64_t N, int C, const f
   }
 }
 
+// finalize + apply in one launch: every block derives mean / invstd of all C channels from the fp64 sums into shared memory
+// (C <= 1024), block 0 also stores them and updates the running statistics
+__global__ void __launch_bounds__(TN_THREADS)
+bn_apply_fused_kernel(const float* __restrict__ x, int ld_x, int64_t N, int C, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const double* __restrict__ sums, float eps, float momentum,
+                      float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
+                      float* __restrict__ save_invstd, int act, float* __restrict__ y, int ld_y) {
+  __shared__ float s_scale[1024], s_shift[1024];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mu = sums[c] / (double)N;
+    double var = sums[C + c] / (double)N - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)mu, invstd = (float)(1.0 / sqrt(var + (double)eps));
+    // y = (x - mean) * invstd * gamma + beta, evaluated in the reference's order below
+    s_scale[c] = invstd;
+    s_shift[c] = mean;
+    if (blockIdx.x == 0) {
+      save_mean[c] = mean;
+      save_invstd[c] = invstd;
+      if (running_mean != nullptr) {
+        const double unb = N > 1 ? var * (double)N / (double)(N - 1) : var;
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unb;
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t n = N * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const float v = (x[r * ld_x + c] - s_shift[c]) * s_scale[c] * gamma[c] + beta[c];
+    y[r * ld_y + c] = apply_act(v, act);
+  }
+}
+
 // dx = gamma * invstd * (g - sum_g / N - xhat * sum_gx / N), g = dy * act'(y)
 __global__ void __launch_bounds__(TN_THREADS)
 bn_bwd_apply_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ y, int ld_y, const float* __restrict__ dy,
@@ -368,20 +404,27 @@ __global__ void add_f64_to_f32_kernel(const double* __restrict__ a, int n, float
 // for k < 49*C, zero above (K padded to a multiple of 32 so that the TF32 tensor-core kernels can treat conv1 as a 1x1 conv)
 __global__ void __launch_bounds__(TN_THREADS)
 stem_im2col_kernel(const float* __restrict__ x, int64_t B, int C, int H, int W, int Ho, int Wo, int K, float* __restrict__ out) {
-  const int64_t n = B * Ho * Wo * K;
+  const int K4 = K >> 2;                       // one thread = 4 consecutive k (one 16-byte store)
+  const int64_t n = B * Ho * Wo * K4;
+  const int kmax = 49 * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % K);
-    const int64_t p = i / K;
-    float v = 0.0f;
-    if (k < 49 * C) {
-      const int c = k % C, t = k / C;
-      const int kh = t / 7, kw = t % 7;
-      const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho);
-      const int64_t b = p / ((int64_t)Wo * Ho);
-      const int hi = 2 * ho + kh - 3, wi = 2 * wo + kw - 3;
-      if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[((b * C + c) * H + hi) * W + wi];
+    const int k0 = (int)(i % K4) * 4;
+    const int64_t p = i / K4;
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho);
+    const int64_t b = p / ((int64_t)Wo * Ho);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + e;
+      v[e] = 0.0f;
+      if (k < kmax) {
+        const int c = k % C, t = k / C;
+        const int kh = t / 7, kw = t - kh * 7;
+        const int hi = 2 * ho + kh - 3, wi = 2 * wo + kw - 3;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v[e] = __ldg(x + ((b * C + c) * H + hi) * W + wi);
+      }
     }
-    out[i] = v;
+    reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -433,6 +476,19 @@ int yad_bn_train_fwd(const float* x, int32_t ld_x, int64_t N, int32_t C, const f
                                                                  save_invstd);
   YAD_LAUNCH_CHECK();
   bn_apply_kernel<<<ew_blocks(N * C), TN_THREADS, 0, st>>>(x, ld_x, N, C, gamma, beta, save_mean, save_invstd, act, y, ld_y);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_bn_train_apply(const float* x, int32_t ld_x, int64_t N, int32_t C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, int32_t act, float* y, int32_t ld_y,
+                       float* save_mean, float* save_invstd, const double* sums, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x && gamma && beta && y && save_mean && save_invstd && sums && N >= 1 && C >= 1 && C <= 1024,
+                "yad_bn_train_apply: bad arguments (C <= 1024)");
+  bn_apply_fused_kernel<<<ew_blocks(N * C), TN_THREADS, 0, (cudaStream_t)stream>>>(x, ld_x, N, C, gamma, beta, sums, eps, momentum,
+                                                                                  running_mean, running_var, save_mean, save_invstd, act,
+                                                                                  y, ld_y);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }
@@ -564,10 +620,10 @@ int yad_permute4(const float* in, const int64_t* in_strides, float* out, const i
 
 int yad_stem_im2col(const float* x_nchw, int64_t B, int32_t C, int32_t H, int32_t W, int32_t K, float* patches, yad_stream_t stream) {
   using namespace yad;
-  YAD_CHECK_ARG(x_nchw && patches && C >= 1 && H >= 1 && W >= 1 && K >= 49 * C, "yad_stem_im2col: bad arguments");
+  YAD_CHECK_ARG(x_nchw && patches && C >= 1 && H >= 1 && W >= 1 && K >= 49 * C && K % 4 == 0, "yad_stem_im2col: bad arguments");
   if (B == 0) return YAD_OK;
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  stem_im2col_kernel<<<ew_blocks(B * Ho * Wo * K), TN_THREADS, 0, (cudaStream_t)stream>>>(x_nchw, B, C, H, W, Ho, Wo, K, patches);
+  stem_im2col_kernel<<<ew_blocks(B * Ho * Wo * (K / 4)), TN_THREADS, 0, (cudaStream_t)stream>>>(x_nchw, B, C, H, W, Ho, Wo, K, patches);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

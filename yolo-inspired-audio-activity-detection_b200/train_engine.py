@@ -82,6 +82,9 @@ class TrainEngine:
         self._seed_dev = torch.zeros(1, device=device, dtype=torch.int64)     # train-step counter (dropout seed offset)
         self._graphs: Dict[tuple, dict] = {}
         self._force_repack = False
+        self._bwd_arena, self._bwd_used, self._stats_arena, self._stats_used, self._act_numel = None, 0, None, 0, 0
+        self._n_weights = sum(p.numel() for p in model.parameters())
+        self._n_bn = sum(m.num_features for m in model.modules() if isinstance(m, nn.BatchNorm2d))
         # split-K (fp32 red.add of partial sums) for small forward grids: faster, but the summation order then varies from run
         # to run and TF32 operand truncation amplifies that 1e-7 noise to ~1e-3 after 20 layers; off = reproducible forward
         self.fwd_split_k = os.environ.get("YAD_TRAIN_FWD_SPLITK", "0") == "1"
@@ -93,11 +96,31 @@ class TrainEngine:
     def _s(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
+    def _zeros(self, numel: int) -> torch.Tensor:
+        """fp32 zeros carved from the backward arena (one memset per step instead of one per gradient buffer)."""
+        n = (numel + 63) // 64 * 64
+        ar = self._bwd_arena
+        if ar is None or self._bwd_used + n > ar.numel():
+            return torch.zeros(numel, device=self.dev, dtype=torch.float32)
+        t = ar[self._bwd_used:self._bwd_used + numel]
+        self._bwd_used += n
+        return t
+
+    def _stats(self, Cc: int) -> torch.Tensor:
+        """[2*C] fp64 zeros for the BatchNorm moments, carved from the forward's statistics arena."""
+        ar = self._stats_arena
+        if ar is None or self._stats_used + 2 * Cc > ar.numel():
+            return torch.zeros(2 * Cc, device=self.dev, dtype=torch.float64)
+        t = ar[self._stats_used:self._stats_used + 2 * Cc]
+        self._stats_used += 2 * Cc
+        return t
+
     def _new(self, B, H, W, Cc, zero=False) -> _T:
         """Fresh activation buffer.  Channel counts that are not a multiple of 32 (the 15-channel head tensors) get a
         zero-filled pitch of 32 so that the TF32 kernels can read whole 128-byte rows."""
         ld = Cc if Cc % 32 == 0 or Cc < 8 else (Cc + 31) // 32 * 32
         f = torch.zeros if (zero or ld != Cc) else torch.empty
+        self._act_numel += (B * H * W * ld + 63) // 64 * 64
         return _T(f((B, H, W, ld), device=self.dev, dtype=torch.float32), 0, Cc)
 
     def _grad(self, t: _T) -> _T:
@@ -105,7 +128,7 @@ class TrainEngine:
         key = t.buf.data_ptr()
         g = self._grads.get(key)
         if g is None:
-            g = self._grads[key] = torch.zeros_like(t.buf)
+            g = self._grads[key] = self._zeros(t.buf.numel()).view(t.buf.shape)
         return _T(g, t.off, t.C)
 
     @staticmethod
@@ -202,7 +225,7 @@ class TrainEngine:
         self._wcache[key] = (ver, wf, wt)
         return wf, wt
 
-    def _conv_tf32(self, x: _T, conv: nn.Conv2d, out: Optional[_T], need_dx: bool) -> _T:
+    def _conv_tf32(self, x: _T, conv: nn.Conv2d, out: Optional[_T], need_dx: bool, stats: Optional[torch.Tensor] = None) -> _T:
         """tcgen05 kind::tf32 path: forward, data gradient (one correlation per output stride-parity class) and weight
         gradient (MN-major operands) - see csrc/conv_tf32.cu."""
         w, b = conv.weight, conv.bias
@@ -232,12 +255,12 @@ class TrainEngine:
                      whole_rows=1 if (self.fwd_split_k and out.off == 0 and out.ld in (O, _c32(O))) else 0)
         fdh, fdw, fk = plan["fwd"]
         _lib.check(self.lib.yad_corr_tf32(C.byref(d), fdh, fdw, fk, x.ptr, wf.data_ptr(), wf.shape[0], kh * kw * cin_pad, _lib.ptr(b),
-                                          out.ptr, self._s()), "conv fwd (tf32)")
+                                          out.ptr, _lib.ptr(stats), self._s()), "conv fwd (tf32)")
         if self._tape is not None:
             def bwd():
                 dy = self._grad(out)
                 assert dy.off == 0 and dy.ld == coutk, "conv outputs are whole buffers with a 32-channel pitch"
-                dwk = torch.zeros((kh, kw, I, O), device=self.dev, dtype=torch.float32)
+                dwk = self._zeros(kh * kw * I * O)
                 dg = CorrDesc(B=x.B, H=x.H, W=x.W, Cin=I, ld_in=x.ld, Ho=Ho, Wo=Wo, Cout=O, ld_out=dy.ld, sh=sh, sw=sw, out_sw=0,
                               out_sh=0, out_sb=0, n_taps=kh * kw, act=ACT_NONE, accumulate=0)
                 _lib.check(self.lib.yad_wgrad_tf32(C.byref(dg), fdh, fdw, plan["dst"], x.ptr, dy.ptr, dwk.data_ptr(), self._s()), "conv wgrad (tf32)")
@@ -250,7 +273,7 @@ class TrainEngine:
                         dd = CorrDesc(B=x.B, H=Ho, W=Wo, Cin=coutk, ld_in=dy.ld, Ho=Hc, Wo=Wc, Cout=I, ld_out=dx.ld, sh=1, sw=1,
                                       out_sw=sw, out_sh=sh * x.W, out_sb=x.H * x.W, n_taps=nt, act=ACT_NONE, accumulate=1)
                         _lib.check(self.lib.yad_corr_tf32(C.byref(dd), tdh, tdw, tk, dy.ptr, wt.data_ptr(), wt.shape[0], kh * kw * coutk,
-                                                          0, dx.ptr + 4 * (rh * x.W + rw) * dx.ld, self._s()), "conv dgrad (tf32)")
+                                                          0, dx.ptr + 4 * (rh * x.W + rw) * dx.ld, 0, self._s()), "conv dgrad (tf32)")
             self._tape.append(bwd)
         return out
 
@@ -277,27 +300,33 @@ class TrainEngine:
         z = (C.c_int32 * 1)(0)
         d = CorrDesc(B=B, H=Ho, W=Wo, Cin=K, ld_in=K, Ho=Ho, Wo=Wo, Cout=O, ld_out=out.ld, sh=1, sw=1, out_sw=0, out_sh=0, out_sb=0,
                      n_taps=1, act=ACT_NONE, accumulate=0, whole_rows=0)
-        _lib.check(self.lib.yad_corr_tf32(C.byref(d), z, z, z, patches.ptr, wf.data_ptr(), wf.shape[0], K, 0, out.ptr, self._s()), "stem conv1 (tf32)")
+        _lib.check(self.lib.yad_corr_tf32(C.byref(d), z, z, z, patches.ptr, wf.data_ptr(), wf.shape[0], K, 0, out.ptr, 0, self._s()), "stem conv1 (tf32)")
         if self._tape is not None:
             def bwd():
                 dy = self._grad(out)
-                dwk = torch.zeros((K, O), device=self.dev, dtype=torch.float32)
+                dwk = self._zeros(K * O)
                 _lib.check(self.lib.yad_wgrad_tf32(C.byref(d), z, z, z, patches.ptr, dy.ptr, dwk.data_ptr(), self._s()), "stem wgrad (tf32)")
                 self._wgrad_finish(w, None, dwk, dy, O, I, kh, kw)       # rows 0..97 of dwk are [kh][kw][Cin][Cout]
             self._tape.append(bwd)
         return out
 
-    def bn(self, x: _T, bn: nn.BatchNorm2d, act: int, out: Optional[_T] = None) -> _T:
+    def bn(self, x: _T, bn: nn.BatchNorm2d, act: int, out: Optional[_T] = None, sums: Optional[torch.Tensor] = None) -> _T:
         Cc, N = x.C, x.rows
         if out is None:
             out = self._new(x.B, x.H, x.W, Cc)
         sm = torch.empty(2 * Cc, device=self.dev, dtype=torch.float32)
         mean, invstd = sm[:Cc], sm[Cc:]
-        ws = torch.empty(2 * Cc, device=self.dev, dtype=torch.float64)
         mom = 0.1 if bn.momentum is None else float(bn.momentum)
-        _lib.check(self.lib.yad_bn_train_fwd(x.ptr, x.ld, N, Cc, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), mom,
-                                             bn.running_mean.data_ptr(), bn.running_var.data_ptr(), act, out.ptr, out.ld,
-                                             mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), self._s()), "bn fwd")
+        if sums is not None:
+            ws = sums            # the backward reuses it as scratch
+            _lib.check(self.lib.yad_bn_train_apply(x.ptr, x.ld, N, Cc, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), mom,
+                                                   bn.running_mean.data_ptr(), bn.running_var.data_ptr(), act, out.ptr, out.ld,
+                                                   mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(), self._s()), "bn apply")
+        else:
+            ws = torch.empty(2 * Cc, device=self.dev, dtype=torch.float64)
+            _lib.check(self.lib.yad_bn_train_fwd(x.ptr, x.ld, N, Cc, bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), mom,
+                                                 bn.running_mean.data_ptr(), bn.running_var.data_ptr(), act, out.ptr, out.ld,
+                                                 mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), self._s()), "bn fwd")
         self._bn_counters.append(bn.num_batches_tracked)
         if self._tape is not None:
             def bwd():
@@ -309,9 +338,19 @@ class TrainEngine:
             self._tape.append(bwd)
         return out
 
+    def conv_bn(self, x: _T, conv: nn.Conv2d, bn: nn.BatchNorm2d, act: int, out: Optional[_T] = None) -> _T:
+        """conv -> BatchNorm(batch statistics) -> activation.  On the TF32 path the moments come out of the conv epilogue, so
+        the BatchNorm forward is one launch (finalise + running statistics + apply)."""
+        I = conv.weight.shape[1]
+        if not (self.conv_mode == "tf32" and I >= 8 and x.off == 0 and x.ld % 32 == 0 and (I % 32 == 0 or x.ld == _c32(I))):
+            return self.bn(self.conv(x, conv), bn, act, out)
+        sums = self._stats(conv.weight.shape[0])
+        y = self._conv_tf32(x, conv, None, True, stats=sums)
+        return self.bn(y, bn, act, out, sums=sums)
+
     def cbl(self, x: _T, m, out: Optional[_T] = None) -> _T:
         """ConvBorINorm (modules/_common.py:43-48): conv(+bias) -> BatchNorm (batch statistics) -> LeakyReLU(0.2)."""
-        return self.bn(self.conv(x, m.conv), m.norm, ACT_LRELU if m.has_activation else ACT_NONE, out)
+        return self.conv_bn(x, m.conv, m.norm, ACT_LRELU if m.has_activation else ACT_NONE, out)
 
     def add_act(self, a: _T, b: _T, c: Optional[_T], act: int, out: Optional[_T] = None) -> _T:
         if out is None:
@@ -397,9 +436,9 @@ class TrainEngine:
         return x
 
     def basic_block(self, x: _T, blk) -> _T:
-        t = self.bn(self.conv(x, blk.conv1), blk.bn1, ACT_RELU)
-        u = self.bn(self.conv(t, blk.conv2), blk.bn2, ACT_NONE)
-        idt = x if blk.downsample is None else self.bn(self.conv(x, blk.downsample[0]), blk.downsample[1], ACT_NONE)
+        t = self.conv_bn(x, blk.conv1, blk.bn1, ACT_RELU)
+        u = self.conv_bn(t, blk.conv2, blk.bn2, ACT_NONE)
+        idt = x if blk.downsample is None else self.conv_bn(x, blk.downsample[0], blk.downsample[1], ACT_NONE)
         return self.add_act(u, idt, None, ACT_RELU)
 
     # ------------------------------------------------------------------ the graph
@@ -413,6 +452,8 @@ class TrainEngine:
         self._bn_counters: List[torch.Tensor] = []
         self._step += 1
         self._seed_dev.add_(1)
+        self._act_numel = 0
+        self._stats_arena, self._stats_used = torch.zeros(2 * self._n_bn, device=self.dev, dtype=torch.float64), 0
         B, Cin, H0, _ = xs.shape
         if self.conv_mode == "tf32":
             x = self.stem_tf32(xs, fe.conv1)
@@ -420,8 +461,7 @@ class TrainEngine:
             x0 = self._new(B, H0, T, Cin)
             self._permute(xs.data_ptr(), (Cin * H0 * T, T, 1, H0 * T), x0.buf, (B, H0, T, Cin), False)     # NCHW -> NHWC
             x = self.conv(x0, fe.conv1, need_dx=False)
-        x = self.conv(x, fe.conv2)
-        x = self.bn(x, fe.bn1, ACT_RELU)
+        x = self.conv_bn(x, fe.conv2, fe.bn1, ACT_RELU)
         x = self.dropout(x, float(fe.dropout_p))
         fmaps = []
         for li in range(1, 5):
@@ -484,7 +524,8 @@ class TrainEngine:
         state = None
         if record:
             state = {"tape": self._tape, "grads": self._grads, "heads": heads, "anc_s": anc_s, "anchors": anchors,
-                     "strides": [T // h.W for h in heads], "center_scaler": center_scaler, "dur": dur, "B": B}
+                     "strides": [T // h.W for h in heads], "center_scaler": center_scaler, "dur": dur, "B": B,
+                     "arena_numel": self._act_numel + self._n_weights + 4096 * 64}
         self._tape, self._grads = None, {}
         return preds, state
 
@@ -492,6 +533,7 @@ class TrainEngine:
         """Accumulates d loss / d parameter into every ``p.grad`` (allocated when missing)."""
         self._grads = state["grads"]
         self._tape = None
+        self._bwd_arena, self._bwd_used = torch.zeros(state["arena_numel"], device=self.dev, dtype=torch.float32), 0
         dur, B = state["dur"], state["B"]
         danc = torch.zeros_like(state["anc_s"])
         for s, (h, dp) in enumerate(zip(state["heads"], dpreds)):
@@ -509,7 +551,7 @@ class TrainEngine:
             fn()
         state["tape"].clear()
         state["grads"].clear()
-        self._grads = {}
+        self._grads, self._bwd_arena = {}, None
 
 
 class _TrainFn(torch.autograd.Function):
