@@ -76,6 +76,15 @@ int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, in
                            const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
                            int64_t T, yad_stream_t stream);
 
+/* The same from 16-bit PCM [B, L] (the sample format of audio files): x = pcm / 32768 exactly as torchaudio.load(normalize=True)
+ * hands it to the reference (inference.py:137-149), so the result is bit-identical to the fp32 entry point on those values;
+ * half the bytes over PCIe and out of HBM. */
+int yad_frontend_mel_power_i16(const int16_t* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
+                               const float* taps, const int32_t* tap_base, int32_t window_len,
+                               const float* window, const float* twiddle, const float* fb_val,
+                               const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
+                               int64_t T, yad_stream_t stream);
+
 /* Stage B: mel power [B,32,T] -> x_spectral [B,2,32,T] f32 (channel 0 = standardised
  * dB-mel, channel 1 = standardised dB-of-MFCC).  One CTA per clip; T <= 1024.
  * Optional taps (may be NULL): meldb, mfcc, mfdb, each [B,32,T] f32 (pre-standardise). */

@@ -473,3 +473,24 @@ def test_host_pipeline_equals_direct_call(models, cuda_dev):
     seg_h, bidx_h = yad_b200.run_host_batch(m, x.pin_memory(), 0.1, 0.2, chunk=2)
     np.testing.assert_array_equal(bidx_h.numpy(), bidx_d.cpu().numpy())
     np.testing.assert_array_equal(seg_h.numpy(), seg_d.cpu().numpy())
+
+
+def test_int16_pcm_ingest_is_bit_identical(models, cuda_dev):
+    """16-bit PCM (the sample format of audio files): x / 32768 happens inside the frontend kernel, so mel
+    power, x_spectral and the predictions are BIT-identical to feeding the reference's float tensor (torchaudio.load with
+    normalize=True yields exactly int16 / 32768).  Covers the 16-byte cp.async path (L % 8 == 0) and the ragged fallback."""
+    m = models[("deploy", "bf16")]
+    for L in (22050 * 6, 22050 * 6 + 4, 22050 * 6 + 3):
+        xi = (synth.synth_clips(3, L, seed=77, silence_tail_every=3).clamp(-1, 1) * 32767).round().to(torch.int16)
+        xf = xi.float() / 32768.0
+        ta, tb = {}, {}
+        with torch.no_grad():
+            pa = m(xi.to(cuda_dev), combine_scales=True, taps=ta)
+            pb = m(xf.to(cuda_dev), combine_scales=True, taps=tb)
+        assert torch.equal(ta["mel"], tb["mel"]), L
+        assert torch.equal(ta["x_spectral"], tb["x_spectral"]), L
+        assert torch.equal(pa, pb), L
+    xi = (synth.synth_clips(5, 22050 * 6, seed=78).clamp(-1, 1) * 32767).round().to(torch.int16)
+    sa = yad_b200.run_host_batch(m, xi.pin_memory(), 0.1, 0.05, chunk=2)
+    sb = yad_b200.run_host_batch(m, (xi.float() / 32768.0).pin_memory(), 0.1, 0.05, chunk=2)
+    assert sa[0] is not None and torch.equal(sa[0], sb[0]) and torch.equal(sa[1], sb[1])

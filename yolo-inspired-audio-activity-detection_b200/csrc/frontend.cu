@@ -83,15 +83,40 @@ __device__ __forceinline__ int fe_stage_async(float* s_x, const float* __restric
   return 0;
 }
 
+// The same for 16-bit PCM (what audio files hold; torchaudio.load(normalize=True) turns it into x / 32768): 16-byte chunks of 8
+// samples, destination shifted by (x0 mod 8).  Fast path: clip base 16 B aligned and L % 8 == 0.
+__device__ __forceinline__ int fe_stage_async_i16(int16_t* s_raw, const int16_t* __restrict__ xb, int64_t x0, int SX, int64_t L,
+                                                  bool fast, int rt) {
+  if (fast) {
+    const int shift = (int)(((x0 % 8) + 8) % 8);
+    const int nchunk = (shift + SX + 7) >> 3;
+    const int64_t g0 = x0 - shift;                      // multiple of 8
+    for (int c = rt; c < nchunk; c += FE_ROLE) {
+      const int64_t gi = g0 + 8 * (int64_t)c;
+      const bool ok = gi >= 0 && gi + 8 <= L;
+      cp_async16(s_raw + 8 * c, xb + (ok ? gi : 0), ok ? 16 : 0);
+    }
+    cp_async_commit();
+    return shift;
+  }
+  for (int i = rt; i < SX; i += FE_ROLE) {
+    const int64_t src = x0 + i;
+    s_raw[i] = (src >= 0 && src < L) ? xb[src] : (int16_t)0;
+  }
+  return 0;
+}
+
+template <bool I16>
 __global__ void __launch_bounds__(FE_THREADS, 1)
-frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float* __restrict__ taps,
+frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float* __restrict__ taps,
                     const int32_t* __restrict__ tap_base, const float* __restrict__ window,
                     const float* __restrict__ twiddle, const float* __restrict__ fb_val,
                     const int32_t* __restrict__ fb_bin, const int32_t* __restrict__ fb_start,
                     float* __restrict__ mel) {
   extern __shared__ __align__(16) float fe_smem[];
-  const int sxp = (p.SX + 8 + 3) & ~3;
-  float* s_x = fe_smem;                                      // [2][sxp] staged PCM spans
+  const int sxp = (p.SX + 16 + 7) & ~7;
+  float* s_x = fe_smem;                                      // [2][sxp] staged PCM spans (16-bit input: two raw
+                                                             // int16 spans in the first half, the converted span in the second)
   float* s_fr = s_x + 2 * sxp;                               // [2][FE_FR_WORDS] frames / FFT exchange
   float* s_Y = s_fr + 2 * FE_FR_WORDS;                       // [FE_FR][25][21] complex: pass-A output in pass-B order
   float* s_P = s_Y + FE_Y_WORDS;                             // [FE_FR][FE_P_STRIDE] power spectrum (bins 0..500)
@@ -105,14 +130,23 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
   const int role = tid >> 8;          // 0: resample, 1: FFT / mel
   const int rt = tid & (FE_ROLE - 1);
   const int64_t b = blockIdx.y;
-  const float* xb = pcm + b * p.L;
-  const bool fast = ((p.L & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
+  const float* xb = reinterpret_cast<const float*>(pcm) + b * p.L;
+  const int16_t* xb16 = reinterpret_cast<const int16_t*>(pcm) + b * p.L;
+  int16_t* s_raw = reinterpret_cast<int16_t*>(s_x);          // [2][sxp] int16 (= sxp floats in total)
+  float* s_xf = s_x + sxp;
+  const bool fast = I16 ? (((p.L & 7) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0))
+                        : (((p.L & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0));
   const int g_first = blockIdx.x * p.groups_per_cta;
   if (g_first >= p.n_groups) return;
   const int n_my = min(p.groups_per_cta, p.n_groups - g_first);
 
   int shift = 0;
-  if (role == 0) shift = fe_stage_async(s_x, xb, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt);
+  if (role == 0) {
+    if (I16)
+      shift = fe_stage_async_i16(s_raw, xb16, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt);
+    else
+      shift = fe_stage_async(s_x, xb, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt);
+  }
 
   for (int i = tid; i < FE_NFFT; i += FE_THREADS) {
     s_tw[i] = make_float2(twiddle[2 * i], twiddle[2 * i + 1]);
@@ -150,13 +184,22 @@ frontend_mel_kernel(const float* __restrict__ pcm, const FeParams p, const float
       const int buf = gi & 1;
       cp_async_wait_all();
       bar_sync(BAR_RS, FE_ROLE);   // span of this group landed for every thread; nobody still reads the other buffer
+      if (I16) {                   // int16 -> float (x / 32768, exact), once per sample; the previous group's reads of s_xf are done
+        const int16_t* raw = s_raw + buf * sxp;
+        for (int i = rt; i < shift + p.SX; i += FE_ROLE) s_xf[i] = (float)raw[i] * (1.0f / 32768.0f);
+        bar_sync(BAR_RS, FE_ROLE);
+      }
       int shift_next = 0;
-      if (gi + 1 < n_my)
-        shift_next = fe_stage_async(s_x + (buf ^ 1) * sxp, xb, (int64_t)(g_first + gi + 1) * p.HG * p.O - p.width, p.SX,
-                                    p.L, fast, rt);
+      if (gi + 1 < n_my) {
+        const int64_t x0n = (int64_t)(g_first + gi + 1) * p.HG * p.O - p.width;
+        if (I16)
+          shift_next = fe_stage_async_i16(s_raw + (buf ^ 1) * sxp, xb16, x0n, p.SX, p.L, fast, rt);
+        else
+          shift_next = fe_stage_async(s_x + (buf ^ 1) * sxp, xb, x0n, p.SX, p.L, fast, rt);
+      }
       if (gi >= 2) bar_sync(BAR_EMPTY0 + buf, FE_THREADS);   // FFT role released this frame buffer
       if (active) {
-        const float* sx = s_x + buf * sxp + shift + base;
+        const float* sx = (I16 ? s_xf : s_x + buf * sxp) + shift + base;
         float* fr = s_fr + buf * FE_FR_WORDS;
         for (int h = sl; h < p.HG; h += p.nslice) {
           const float* xs = sx + h * p.O;
@@ -385,13 +428,14 @@ frontend_finish_kernel(const float* __restrict__ mel, int64_t T, const float* __
 }
 
 static size_t fe_smem_bytes(int SX, int nnz_pad) {
-  const int sxp = (SX + 8 + 3) & ~3;
+  const int sxp = (SX + 16 + 7) & ~7;
   return (size_t)(2 * sxp + 2 * FE_FR_WORDS + FE_Y_WORDS + ((FE_FR * FE_P_STRIDE + 3) & ~3) + 2 * FE_NFFT + 1000 + FE_NFFT + nnz_pad +
                   2 * FE_NMEL + 4) * sizeof(float);
 }
 
 int init_frontend_attrs() {
-  cudaError_t e = cudaFuncSetAttribute(frontend_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(frontend_mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(frontend_mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(frontend_mel_kernel) failed: %s", cudaGetErrorString(e));
     return YAD_ERR_CUDA;
@@ -403,10 +447,10 @@ int init_frontend_attrs() {
 
 extern "C" {
 
-int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
-                           const float* taps, const int32_t* tap_base, int32_t window_len, const float* window,
-                           const float* twiddle, const float* fb_val, const int32_t* fb_bin,
-                           const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
+static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
+                             const float* taps, const int32_t* tap_base, int32_t window_len, const float* window,
+                             const float* twiddle, const float* fb_val, const int32_t* fb_bin,
+                             const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
   using namespace yad;
   YAD_CHECK_ARG(pcm && taps && tap_base && window && twiddle && fb_val && fb_bin && fb_start && mel,
                 "yad_frontend_mel_power: null pointer");
@@ -445,10 +489,30 @@ int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, in
   const size_t smem = fe_smem_bytes(p.SX, p.fb_nnz_pad);
   YAD_CHECK_ARG(smem <= 226 * 1024, "yad_frontend_mel_power: staging span too large (%zu B of shared memory)", smem);
   dim3 grid((unsigned)((p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta), (unsigned)B);
-  frontend_mel_kernel<<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, window, twiddle, fb_val,
-                                                                        fb_bin, fb_start, mel);
+  if (i16)
+    frontend_mel_kernel<true><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, window, twiddle, fb_val,
+                                                                                fb_bin, fb_start, mel);
+  else
+    frontend_mel_kernel<false><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, window, twiddle, fb_val,
+                                                                                 fb_bin, fb_start, mel);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
+}
+
+int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
+                           const float* taps, const int32_t* tap_base, int32_t window_len, const float* window,
+                           const float* twiddle, const float* fb_val, const int32_t* fb_bin,
+                           const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
+  return frontend_mel_impl(pcm, false, B, L, P, O, width, taps, tap_base, window_len, window, twiddle, fb_val, fb_bin, fb_start,
+                           fb_nnz, mel, T, stream);
+}
+
+int yad_frontend_mel_power_i16(const int16_t* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
+                               const float* taps, const int32_t* tap_base, int32_t window_len, const float* window,
+                               const float* twiddle, const float* fb_val, const int32_t* fb_bin,
+                               const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
+  return frontend_mel_impl(pcm, true, B, L, P, O, width, taps, tap_base, window_len, window, twiddle, fb_val, fb_bin, fb_start,
+                           fb_nnz, mel, T, stream);
 }
 
 int yad_frontend_finish(const float* mel, int64_t B, int64_t T, const float* dct, float top_db, int32_t standardise,

@@ -306,13 +306,15 @@ class InferenceEngine:
         T = self.frames(L)
         if T < 32:
             raise ValueError(f"input too short: {L} samples give {T} frames (need >= 32)")
-        x = x.contiguous().float()
+        i16 = x.dtype == torch.int16          # 16-bit PCM (file sample format): converted (x / 32768) inside the kernel
+        x = x.contiguous() if i16 else x.contiguous().float()
         mel = plan.get("mel")
         if mel is None:
             mel = plan["mel"] = torch.empty((B, 32, T), device=self.dev, dtype=torch.float32)
             plan["xs"] = torch.empty((B, 2, 32, T), device=self.dev, dtype=torch.float32)
         xs = plan["xs"]
-        rc = self.lib.yad_frontend_mel_power(x.data_ptr(), B, L, self.rs_P, self.rs_O, self.rs_width, self.rs_taps.data_ptr(),
+        fn = self.lib.yad_frontend_mel_power_i16 if i16 else self.lib.yad_frontend_mel_power
+        rc = fn(x.data_ptr(), B, L, self.rs_P, self.rs_O, self.rs_width, self.rs_taps.data_ptr(),
                                              self.rs_base.data_ptr(), self.rs_window_len, self.win.data_ptr(), self.tw.data_ptr(),
                                              self.fb_val.data_ptr(), self.fb_bin.data_ptr(), self.fb_start.data_ptr(),
                                              self.fb_val.numel(), mel.data_ptr(), T, self._stream())

@@ -17,7 +17,7 @@ from .postprocess import process_model_outputs
 def run_host_batch(model, x_host: torch.Tensor, iou_threshold: float = 0.05, conf_threshold: float = 0.5, chunk: int = 64,
                    sample_duration: float = 60, return_start_end: bool = True,
                    ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """x_host [N,1,L] f32 on the host (pinned for an asynchronous copy) -> (segments [K,5], batch_idxs [K]) on the host, as
+    """x_host [N,1,L] f32 (or int16 PCM, half the bytes over PCIe) on the host (pinned for an asynchronous copy) -> (segments [K,5], batch_idxs [K]) on the host, as
     ``process_model_outputs`` returns them (``(None, None)`` when nothing passes the confidence threshold).
     ``model`` is a ``yad_b200.AudioDetectionNetwork`` on a CUDA device."""
     if x_host.is_cuda:
@@ -27,7 +27,9 @@ def run_host_batch(model, x_host: torch.Tensor, iou_threshold: float = 0.05, con
     chunk = max(1, min(int(chunk), N))
     compute = torch.cuda.current_stream(dev)
     copy = _copy_stream(dev)
-    bufs = [torch.empty((chunk, 1, L), device=dev, dtype=torch.float32) for _ in range(2)]
+    if x_host.dtype not in (torch.float32, torch.int16):
+        raise ValueError("run_host_batch takes fp32 PCM or 16-bit PCM (int16; x / 32768 is applied on the GPU)")
+    bufs = [torch.empty((chunk, 1, L), device=dev, dtype=x_host.dtype) for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
     preds = []
