@@ -242,6 +242,12 @@ int yad_build_targets(const float* targets, int32_t T, const float* anchors, int
                       float anchor_t, float duration, float edge_t, int64_t* batch_idx, int64_t* grid_idx,
                       int64_t* anchor_idx, int64_t* classes, float* cw, int32_t* n_out, yad_stream_t stream);
 
+/* Batch builder: the device half of AudioDataset.__getitem__ / collate_fn (dataset.py:132-155,276-283).
+ * packed: B ragged clips back to back, clip b = n_channels[b] x n_samples[b] elements (channel-major) starting at element
+ * offset[b]; fp32 or 16-bit PCM (dtype_i16 = 1: x / 32768).  out [B, 1, L] f32 = channel mean, zero padded to L samples. */
+int yad_collate_clips(const void* packed, int32_t dtype_i16, const int64_t* offset, const int32_t* n_samples,
+                      const int32_t* n_channels, int64_t B, int64_t L, float* out, yad_stream_t stream);
+
 /* Detection loss of ONE scale: modules/_loss.py:115-228 (AudioDetectionLoss.loss_fn + compute_ciou) for the default
  * train_config (multi_label BCE class loss with label smoothing, BCEWithLogits objectness, no focal loss).
  *   pred [B, G, A, 3+nc] f32 (decoded predictions: obj, cls.., centre_s, width_s); matches (bi, gi, ai, cl i64, cw [M,2] f32)

@@ -557,6 +557,40 @@ def build_target_by_scale(targets: Tensor, fmap_shape: int, anchors: Sequence[fl
     return (torch.from_numpy(bi), torch.from_numpy(gi), torch.from_numpy(ai)), torch.from_numpy(cl), torch.from_numpy(cw)
 
 
+def getitem_collate(clips: Sequence[Tensor], seg_lists: Sequence[np.ndarray], sample_rate: int, sample_duration: float,
+                    ignore_index: int = -100, gmins: Optional[Sequence[float]] = None) -> Tuple[Tensor, Tensor]:
+    """AudioDataset.__getitem__ from the loaded waveform on + collate_fn (ref: dataset.py:123-164,276-283).  ``clips[i]`` is what
+    torchaudio.load returned ([C, n] f32), ``seg_lists[i]`` the clip's (start_s, end_s, class_idx) rows."""
+    audios, targets = [], []
+    for i, (audio, seg) in enumerate(zip(clips, seg_lists)):
+        gmin = 0.0 if gmins is None else gmins[i]
+        seg = np.asarray(seg, dtype=np.float64)
+        times = seg[:, :2].astype(float)
+        a_start, a_end = times[0][0], times[-1][1]
+        a_start, a_end = a_start - gmin, a_end - gmin
+        times = times - gmin
+        if audio.ndim == 1:
+            audio = audio.unsqueeze(0)
+        if audio.shape[0] != 1:
+            audio = audio.mean(dim=0).unsqueeze(0)
+        classes = torch.from_numpy(seg[:, 2].astype(np.int64))
+        times[:, 1] = times[:, 1] - times[:, 0]
+        times[:, 0] = times[:, 0] + (times[:, 1] / 2)
+        labels = torch.cat((classes[:, None], torch.from_numpy(times).to(dtype=torch.float32)), dim=-1)
+        max_n = int(sample_duration * sample_rate)
+        if audio.shape[-1] < max_n:
+            audio = torch.cat((audio, torch.zeros((audio.shape[0], max_n - audio.shape[-1]), dtype=audio.dtype)), dim=-1)
+            pad_dur = (a_start + sample_duration) - a_end
+            pad_c = a_end + (pad_dur / 2)
+            labels = torch.cat((labels, torch.tensor([float(ignore_index), pad_c, pad_dur], dtype=labels.dtype).unsqueeze(0)), dim=0)
+        t = torch.zeros((labels.shape[0], labels.shape[1] + 1), dtype=labels.dtype)
+        t[:, 1:] = labels
+        t[:, 0] = i
+        audios.append(audio)
+        targets.append(t)
+    return torch.stack(audios, dim=0), torch.cat(targets, dim=0)
+
+
 def compute_ciou(p_cw: Tensor, t_cw: Tensor, e: float = 1e-8, _h: float = 10.0) -> Tensor:
     """ref: modules/_loss.py:193-228 (1-D segments dressed as boxes of height 10)."""
     pc, pw = p_cw[..., :1], p_cw[..., -1:]

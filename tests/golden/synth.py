@@ -102,3 +102,22 @@ def synth_targets(B: int, seed: int = 11, duration: float = 60.0) -> torch.Tenso
                 cls = -100
             rows.append([b, cls, 0.5 * (s + e), e - s])
     return torch.tensor(rows, dtype=torch.float32)
+
+
+# ---- batch-builder cases (tests/golden/make_golden_collate.py)
+COLLATE_SR, COLLATE_DUR = 2000, 6          # a small sample rate keeps the fixture tiny; the code path does not depend on it
+
+
+def collate_cases():
+    """(filename, channels, segments [(start, end, label)], group_minmax or None)"""
+    return [
+        ("a", 1, [(0.0, 1.25, "speech"), (1.25, 3.5, "music"), (3.5, 6.0, "speech")], None),            # full length
+        ("b", 2, [(0.0, 2.0, "music"), (2.0, 4.1, "speech")], None),                                    # stereo, short -> pad label
+        ("c", 1, [(12.0, 13.5, "speech"), (13.5, 15.75, "music"), (15.75, 17.0, "speech")], (12.0, 18.0)),  # grouped, short
+        ("d", 3, [(6.0, 9.0, "music"), (9.0, 12.0, "speech")], (6.0, 12.0)),                            # 3 channels, grouped, full
+    ]
+
+
+def collate_waveform(name: str, channels: int, frame_offset: int, num_frames: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(sum(map(ord, name)) * 7919 + frame_offset)
+    return (torch.randn(channels, num_frames, generator=g) * 0.25).clamp(-1, 1)

@@ -468,3 +468,22 @@ def test_train_step_cuda_graphs_equal_eager(ref_state_dict, cuda_dev):
         assert _rel_l2(gg.cpu(), ge.cpu()) < 1e-2
         np.testing.assert_allclose(rg.cpu().numpy(), re_.cpu().numpy(), atol=1e-5)
     assert out["graph"][4][3] == 1                          # load_state_dict reset the counter, the replay incremented it
+
+
+def test_collate_batch_vs_live_reference(gold, cuda_dev):
+    """GPU batch builder (SURVEY 8(f) N2) == the live reference's __getitem__ + collate_fn (fixture collate.npz), bit exact;
+    the int16 entry equals the oracle fed the de-quantised waveforms."""
+    from test_oracle_golden import _collate_inputs
+    g = gold("collate")
+    clips, segs, gmins, sr, dur = _collate_inputs()
+    tg = [yad_b200.clip_targets(s, s[0][0], s[-1][1], c.shape[-1], sr, dur, -100, gm) for c, s, gm in zip(clips, segs, gmins)]
+    audio, targets = yad_b200.collate_batch(clips, tg, sr, dur, cuda_dev)
+    np.testing.assert_array_equal(audio.cpu().numpy(), g["audio"])
+    np.testing.assert_array_equal(targets.cpu().numpy(), g["targets"])
+    ci = [(c * 32767).round().to(torch.int16) for c in clips]
+    a16, t16 = yad_b200.collate_batch(ci, tg, sr, dur, cuda_dev)
+    ref, _ = O.getitem_collate([c.float() / 32768.0 for c in ci], segs, sr, dur, -100, gmins)
+    np.testing.assert_allclose(a16.cpu().numpy(), ref.numpy(), atol=1e-7, rtol=0)      # 3-channel mean: one rounding apart at most
+    np.testing.assert_array_equal(t16.cpu().numpy(), g["targets"])
+    with pytest.raises(ValueError):
+        yad_b200.collate_batch([torch.zeros(1, sr * dur + 1)], [tg[0]], sr, dur, cuda_dev)

@@ -171,3 +171,25 @@ def test_train_mode_forward_backward_vs_live_reference(gold, ref_state_dict):
     for k in [k[3:] for k in g if k.startswith("rm:")]:
         np.testing.assert_allclose(sd[k + ".running_mean"].numpy(), g["rm:" + k], atol=1e-6)
         np.testing.assert_allclose(sd[k + ".running_var"].numpy(), g["rv:" + k], rtol=1e-5)
+
+
+def _collate_inputs():
+    idx = {"speech": 0, "music": 1}
+    clips, segs, gmins = [], [], []
+    sr, dur = synth.COLLATE_SR, synth.COLLATE_DUR
+    for name, ch, sg, gmm in synth.collate_cases():
+        a0, a1 = sg[0][0], sg[-1][1]
+        clips.append(synth.collate_waveform(name, ch, int(a0 * sr), int((a1 - a0) * sr)))
+        segs.append(np.array([[a, b, idx[lab]] for a, b, lab in sg], dtype=np.float64))
+        gmins.append(0.0 if gmm is None else gmm[0])
+    return clips, segs, gmins, sr, dur
+
+
+def test_getitem_collate_vs_live_reference(gold):
+    """Oracle restatement of AudioDataset.__getitem__ (from the loaded waveform on) + collate_fn == the live reference
+    (fixture collate.npz): zero padding, channel mean, ignore-label pad target, group shift, batch index.  Bit exact."""
+    g = gold("collate")
+    clips, segs, gmins, sr, dur = _collate_inputs()
+    audio, targets = O.getitem_collate(clips, segs, sr, dur, -100, gmins)
+    np.testing.assert_array_equal(audio.numpy(), g["audio"])
+    np.testing.assert_array_equal(targets.numpy(), g["targets"])

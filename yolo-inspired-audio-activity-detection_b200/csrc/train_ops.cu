@@ -107,6 +107,35 @@ __global__ void adam_ema_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------ batch builder
+// AudioDataset.__getitem__ tail + collate_fn (dataset.py:132-155,276-283) on the device: ragged clips (C_b channels x n_b
+// samples each, packed back to back, fp32 or 16-bit PCM) -> [B, 1, L] fp32, channel mean (audio_tensor.mean(dim=0)) and zero
+// padding up to L.  One grid row per clip.
+template <typename T>
+__global__ void __launch_bounds__(256)
+collate_clips_kernel(const T* __restrict__ packed, const int64_t* __restrict__ offset, const int32_t* __restrict__ n_samples,
+                     const int32_t* __restrict__ n_channels, int64_t L, float scale, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int64_t n = n_samples[b];
+  const int c = n_channels[b];
+  const T* src = packed + offset[b];
+  float* dst = out + (int64_t)b * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.0f;
+    if (i < n) {
+      if (c == 1) {
+        v = (float)src[i] * scale;
+      } else {                       // torch's mean: sum in channel order, then divide
+        float acc = 0.0f;
+        for (int k = 0; k < c; ++k) acc += (float)src[(int64_t)k * n + i] * scale;
+        v = acc / (float)c;
+      }
+    }
+    dst[i] = v;
+  }
+}
+
 }  // namespace yad
 
 extern "C" {
@@ -138,6 +167,24 @@ int yad_adam_ema_step(float* param, const float* grad, float* exp_avg, float* ex
   if (blocks > cap) blocks = cap;
   yad::adam_ema_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
       param, grad, exp_avg, exp_avg_sq, ema, n, step_size, beta1, beta2, eps, weight_decay, inv_bc2_sqrt, ema_momentum);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_collate_clips(const void* packed, int32_t dtype_i16, const int64_t* offset, const int32_t* n_samples,
+                      const int32_t* n_channels, int64_t B, int64_t L, float* out, yad_stream_t stream) {
+  YAD_CHECK_ARG(packed && offset && n_samples && n_channels && out && B >= 0 && B <= 65535 && L >= 1, "yad_collate_clips: bad arguments");
+  if (B == 0) return YAD_OK;
+  const int threads = 256;
+  int64_t bx = (L + threads - 1) / threads;
+  if (bx > 512) bx = 512;
+  dim3 grid((unsigned)bx, (unsigned)B);
+  if (dtype_i16)
+    yad::collate_clips_kernel<int16_t><<<grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int16_t*>(packed), offset,
+                                                                                 n_samples, n_channels, L, 1.0f / 32768.0f, out);
+  else
+    yad::collate_clips_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(packed), offset,
+                                                                               n_samples, n_channels, L, 1.0f, out);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

@@ -50,6 +50,71 @@ def build_target_by_scale(targets: torch.Tensor, fmap_shape: Union[int, torch.Si
     return [bi[:M], gi[:M], ai[:M]], cl[:M], cw[:M]
 
 
+def clip_targets(segments, audio_start: float, audio_end: float, n_samples: int, sample_rate: int, sample_duration: float,
+                 ignore_index: int = -100, gmin: float = 0.0) -> torch.Tensor:
+    """Labels of ONE clip as ``AudioDataset.__getitem__`` builds them (reference: dataset.py:123-160): rows
+    (0, class, centre_s, dur_s) from (start_s, end_s, class_idx) segments, shifted by the group minimum, plus the
+    ignore-label row that covers the zero padding of a clip shorter than ``sample_duration``."""
+    import numpy as np
+    seg = np.asarray(segments, dtype=np.float64).reshape(-1, 3)
+    times = seg[:, :2].copy() - gmin
+    a_start, a_end = audio_start - gmin, audio_end - gmin
+    times[:, 1] = times[:, 1] - times[:, 0]
+    times[:, 0] = times[:, 0] + times[:, 1] / 2
+    labels = torch.cat((torch.from_numpy(seg[:, 2].astype(np.int64))[:, None], torch.from_numpy(times).to(torch.float32)), dim=-1)
+    if n_samples < sample_duration * sample_rate:
+        pad_dur = (a_start + sample_duration) - a_end
+        pad_c = a_end + pad_dur / 2
+        labels = torch.cat((labels, torch.tensor([[float(ignore_index), pad_c, pad_dur]], dtype=labels.dtype)), dim=0)
+    out = torch.zeros((labels.shape[0], 4), dtype=labels.dtype)
+    out[:, 1:] = labels
+    return out
+
+
+def collate_batch(clips, targets, sample_rate: int, sample_duration: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GPU-side ``AudioDataset.collate_fn`` (reference: dataset.py:132-155,276-283) for clips that are still ragged: ``clips`` is
+    a list of host tensors [C_i, n_i] (fp32, or int16 PCM straight from the decoder), ``targets`` the matching list of
+    ``clip_targets`` results.  ONE packed host->device copy, one kernel (channel mean, zero padding to
+    ``sample_duration * sample_rate``), targets concatenated with their batch index.  Returns (audio [B,1,L] f32, targets [T,4] f32)
+    on ``device``."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("yad_b200.collate_batch builds the batch on a CUDA device (no CPU fallback)")
+    lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+    B = len(clips)
+    L = int(sample_duration * sample_rate)
+    dt = clips[0].dtype
+    if dt not in (torch.float32, torch.int16) or any(c.dtype != dt for c in clips):
+        raise ValueError("collate_batch: clips must all be float32 or all be int16")
+    shapes = [(1, c.shape[0]) if c.ndim == 1 else tuple(c.shape) for c in clips]
+    for ch, n in shapes:
+        if n > L:
+            raise ValueError(f"audio sample is more than {sample_duration}, ensure that the specified sample rate value "
+                             f"({sample_rate}) is correct")        # dataset.py:133-137
+    sizes = [ch * n for ch, n in shapes]
+    offs = [0]
+    for sz in sizes[:-1]:
+        offs.append(offs[-1] + sz)
+    packed = torch.empty(sum(sizes), dtype=dt).pin_memory()
+    for c, o, sz in zip(clips, offs, sizes):
+        packed[o:o + sz] = c.reshape(-1)
+    meta = torch.tensor(offs, dtype=torch.int64), torch.tensor([n for _, n in shapes], dtype=torch.int32), \
+        torch.tensor([ch for ch, _ in shapes], dtype=torch.int32)
+    pd = packed.to(device, non_blocking=True)
+    od, nd, cd = (m.to(device, non_blocking=True) for m in meta)
+    audio = torch.empty((B, 1, L), device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        rc = lib.yad_collate_clips(pd.data_ptr(), 1 if dt == torch.int16 else 0, od.data_ptr(), nd.data_ptr(), cd.data_ptr(), B, L,
+                                   audio.data_ptr(), _stream(device))
+    _lib.check(rc, "collate_clips")
+    tg = []
+    for i, t in enumerate(targets):
+        t = t.clone()
+        t[:, 0] = i
+        tg.append(t)
+    return audio, torch.cat(tg, dim=0).to(device, non_blocking=True)
+
+
 class _DetectionLossFn(torch.autograd.Function):
     """loss = f(preds); the kernels return d loss / d preds, so backward is a scale by the upstream gradient."""
 
