@@ -514,6 +514,46 @@ def process_model_outputs(outputs: Tensor, iou_threshold: float = 0.05, conf_thr
     return seg, bidx
 
 
+def evaluate_waveform(wav: Tensor, sd: Dict[str, Tensor], num_classes: int, sample_rate: int, sample_duration: float,
+                      batch_size: int, idx2class_map: Dict[int, str], iou_threshold: float = 0.1, conf_threshold: float = 0.65,
+                      config: Dict = DEFAULT_CONFIG):
+    """inference.evaluate_audio from the decoded mono waveform [n] on (ref: inference.py:126-198), incl. its clip-index quirk
+    (``batch_idxs += batch_idxs_list[-1][-1]``).  Returns (segments in file time, batch_idxs, rle rows)."""
+    from datetime import timedelta
+    sample_size = int(sample_duration * sample_rate)
+    batch_start, batch_end = 0, batch_size * sample_duration
+    seg_l, idx_l = [], []
+    while True:
+        lo, num = int(batch_start * sample_rate), int((batch_end - batch_start) * sample_rate)
+        x = wav[lo:lo + num]
+        if x.shape[-1] == 0:
+            break
+        if x.shape[0] % sample_size != 0:
+            nb = int(np.ceil(x.shape[0] / sample_size))
+            x = torch.cat([x, torch.zeros((nb * sample_size - x.shape[0],), dtype=x.dtype)], dim=0)
+        out = forward(x.reshape(-1, 1, sample_size), sd, num_classes, config, combine_scales=True)
+        seg, bidx = process_model_outputs(out, iou_threshold, conf_threshold, sample_duration, True)
+        if idx_l:
+            bidx = bidx + idx_l[-1][-1]
+        seg_l.append(seg)
+        idx_l.append(bidx)
+        batch_start = batch_end
+        batch_end += batch_size * sample_duration
+    seg = torch.cat(seg_l, dim=0)
+    bidx = torch.cat(idx_l, dim=0)
+    seg[..., -2:] = seg[..., -2:] + (bidx.unsqueeze(-1) * sample_duration)
+    rows = []
+    for i in range(seg.shape[0]):
+        s = seg[i]
+        start, end = timedelta(seconds=round(s[-2].item(), 2)), timedelta(seconds=round(s[-1].item(), 2))
+        cls = idx2class_map[int(s[2].item())]
+        if not rows or rows[-1]["class"] != cls:
+            rows.append({"start": start, "end": end, "class": cls})
+            continue
+        rows[-1]["end"] = end
+    return seg, bidx, rows
+
+
 # --------------------------------------------------------------------------
 # training-side integer work: anchor matching (ref: dataset.py:286-365)
 # --------------------------------------------------------------------------

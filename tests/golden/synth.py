@@ -121,3 +121,13 @@ def collate_cases():
 def collate_waveform(name: str, channels: int, frame_offset: int, num_frames: int) -> torch.Tensor:
     g = torch.Generator().manual_seed(sum(map(ord, name)) * 7919 + frame_offset)
     return (torch.randn(channels, num_frames, generator=g) * 0.25).clamp(-1, 1)
+
+
+# ---- file-level chunker case (tests/golden/make_golden_eval.py)
+EVAL_SR, EVAL_IOU, EVAL_CONF = 22050, 0.1, 0.2
+
+
+def eval_waveform() -> torch.Tensor:
+    """270 s mono waveform (4.5 clips of 60 s: three batches of 2, 2 and 1 zero-padded clip)."""
+    x = synth_clips(5, 22050 * 60, seed=4000, silence_tail_every=0)
+    return x.reshape(-1)[: int(270 * 22050)].contiguous()

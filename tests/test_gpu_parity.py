@@ -494,3 +494,22 @@ def test_int16_pcm_ingest_is_bit_identical(models, cuda_dev):
     sa = yad_b200.run_host_batch(m, xi.pin_memory(), 0.1, 0.05, chunk=2)
     sb = yad_b200.run_host_batch(m, (xi.float() / 32768.0).pin_memory(), 0.1, 0.05, chunk=2)
     assert sa[0] is not None and torch.equal(sa[0], sb[0]) and torch.equal(sa[1], sb[1])
+
+
+def test_evaluate_waveform_vs_live_reference(models, gold, cuda_dev):
+    """File-level chunker through the host-buffer pipeline == the live reference's evaluate_audio: same clips
+    kept, same labels, times within 2e-3 s (f32 parity model), the same CSV rows; the int16 entry keeps the same segments."""
+    from test_oracle_golden import _eval_expected, _rows_as_csv
+    seg_e, bidx_e, rows_e = _eval_expected(gold)
+    m = models[("train", "f32")]
+    wav = synth.eval_waveform()
+    seg, bidx, rows = yad_b200.evaluate_waveform(m, wav, synth.EVAL_SR, 60, 2, {0: "speech", 1: "music"}, synth.EVAL_IOU, synth.EVAL_CONF)
+    np.testing.assert_array_equal(bidx.numpy(), bidx_e.numpy())
+    np.testing.assert_array_equal(seg[:, 2].numpy(), seg_e[:, 2].numpy())
+    np.testing.assert_allclose(seg.numpy(), seg_e.numpy(), atol=2e-3, rtol=1e-4)
+    assert _rows_as_csv(rows) == rows_e
+    wi = (wav.clamp(-1, 1) * 32767).round().to(torch.int16)
+    seg16, bidx16, _ = yad_b200.evaluate_waveform(m, wi, synth.EVAL_SR, 60, 2, {0: "speech", 1: "music"}, synth.EVAL_IOU, synth.EVAL_CONF)
+    assert seg16.shape == seg.shape and torch.equal(bidx16, bidx)        # 16-bit quantisation does not move a keep decision here
+    with pytest.raises(NotImplementedError):
+        yad_b200.evaluate_waveform(m, wav, 16000, 60, 2, {0: "speech", 1: "music"})

@@ -193,3 +193,36 @@ def test_getitem_collate_vs_live_reference(gold):
     audio, targets = O.getitem_collate(clips, segs, sr, dur, -100, gmins)
     np.testing.assert_array_equal(audio.numpy(), g["audio"])
     np.testing.assert_array_equal(targets.numpy(), g["targets"])
+
+
+def _eval_expected(gold):
+    g = gold("eval_long")
+    segs, idxs = [], []
+    for i in range(int(g["n_batches"])):
+        b = torch.from_numpy(g[f"bidx{i}"]).clone()
+        if idxs:
+            b = b + idxs[-1][-1]                      # the reference's clip-index offset (inference.py:176-177)
+        segs.append(torch.from_numpy(g[f"seg{i}"]).clone())
+        idxs.append(b)
+    seg, bidx = torch.cat(segs), torch.cat(idxs)
+    seg[..., -2:] += bidx.unsqueeze(-1) * 60
+    import os
+    from conftest import GOLD
+    rows = [ln.strip() for ln in open(os.path.join(GOLD, "eval_long_results.csv")).read().strip().splitlines()[1:]]
+    return seg, bidx, rows
+
+
+def _rows_as_csv(rows):
+    import pandas as pd
+    return [ln.strip() for ln in pd.DataFrame(rows).to_csv(index=False).strip().splitlines()[1:]]
+
+
+def test_evaluate_waveform_vs_live_reference(gold, ref_state_dict):
+    """Oracle restatement of inference.evaluate_audio (chunker, padding, clip-index offset, file-time shift, RLE) == the live
+    reference on a 270 s waveform: per-batch segments as its process_model_outputs returned them and the CSV it wrote."""
+    seg_e, bidx_e, rows_e = _eval_expected(gold)
+    seg, bidx, rows = O.evaluate_waveform(synth.eval_waveform(), ref_state_dict, 2, synth.EVAL_SR, 60, 2, {0: "speech", 1: "music"},
+                                          synth.EVAL_IOU, synth.EVAL_CONF)
+    np.testing.assert_array_equal(bidx.numpy(), bidx_e.numpy())
+    np.testing.assert_allclose(seg.numpy(), seg_e.numpy(), atol=1e-4, rtol=1e-5)
+    assert _rows_as_csv(rows) == rows_e
