@@ -149,7 +149,7 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
   }
 
   for (int i = tid; i < FE_NFFT; i += FE_THREADS) {
-    s_tw[i] = make_float2(twiddle[2 * i], twiddle[2 * i + 1]);
+    s_tw[i] = make_float2(twiddle[2 * i + 1], -twiddle[2 * i]);   // -i W_1000^k: the untangle pass multiplies by it directly
     s_win[i] = window[i];
   }
   for (int i = tid; i < 500; i += FE_THREADS) {
@@ -157,10 +157,33 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
     const int e = (2 * n2 * passA_k1_of_reg(r)) % 1000;
     s_twA[i] = make_float2(twiddle[2 * e], twiddle[2 * e + 1]);
   }
-  const int nnz = fb_start[FE_NMEL];
-  for (int i = tid; i < nnz; i += FE_THREADS) s_fbv[i] = fb_val[i];
-  if (tid <= FE_NMEL) s_fbs[tid] = fb_start[tid];
-  if (tid < FE_NMEL) s_fbs[FE_NMEL + 1 + tid] = fb_bin[fb_start[tid]];   // bins of a band are contiguous
+  // Mel filterbank, re-packed for 8-byte shared-memory loads: band m covers the contiguous bins [bin0, bin0 + len); its
+  // padded row starts at the even bin (bin0 & ~1) (a leading zero weight when bin0 is odd), at an even offset, and is
+  // zero-padded to a multiple of 4 weights.  The weights carry the 1/4 of the untangle pass (power spectrum kept as 4 |X|^2).
+  for (int i = tid; i < p.fb_nnz_pad; i += FE_THREADS) s_fbv[i] = 0.0f;
+  for (int i = tid; i < FE_FR * (FE_P_STRIDE - 501); i += FE_THREADS)      // bins past 500: read (times zero) by the padded rows
+    s_P[(i / (FE_P_STRIDE - 501)) * FE_P_STRIDE + 501 + i % (FE_P_STRIDE - 501)] = 0.0f;
+  if (tid < FE_NMEL) {        // warp 0: one band per lane, exclusive prefix sum of the padded lengths
+    const int fb_s0 = fb_start[tid], fb_len = fb_start[tid + 1] - fb_s0;
+    const int bin0 = fb_len > 0 ? fb_bin[fb_s0] : 0;
+    const int fb_lead = bin0 & 1;
+    const int tot = (fb_lead + fb_len + 3) & ~3;
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += v;
+    }
+    s_fbs[tid] = incl - tot;
+    if (tid == FE_NMEL - 1) s_fbs[FE_NMEL] = incl;
+    s_fbs[FE_NMEL + 1 + tid] = bin0 - fb_lead;
+  }
+  __syncthreads();
+  for (int m = tid >> 5; m < FE_NMEL; m += FE_THREADS / 32) {   // one warp per band
+    const int s0 = fb_start[m], len = fb_start[m + 1] - s0;
+    const int lead = len > 0 ? (fb_bin[s0] & 1) : 0;
+    for (int i = tid & 31; i < len; i += 32) s_fbv[s_fbs[m] + lead + i] = 0.25f * fb_val[s0 + i];
+  }
   __syncthreads();
 
   if (role == 0) {
@@ -171,14 +194,18 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
     const int qi = rt % p.nquad, sl = rt / p.nquad;
     const int quad = qi < half ? 2 * qi : 2 * (qi - half) + 1;
     const bool active = sl < p.nslice;
-    float tq[4][FE_QW];
+    // taps of the phase pairs (4u, 4u+1) and (4u+2, 4u+3) as packed register pairs: one FFMA2 (fma.rn.f32x2 with the staged
+    // sample broadcast to both lanes) advances two phases, so a quad costs 21 LDS + 42 FFMA2 instead of 21 LDS + 84 FFMA.
+    // Each lane is an ordinary fmaf chain: results are bit-identical to the scalar form.
+    float2 tq01[FE_QW], tq23[FE_QW];
     int base = 0;
     if (active) {
       base = tap_base[quad];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < FE_QW; ++j) tq[i][j] = __ldg(taps + (quad * 4 + i) * FE_QW + j);
+      for (int j = 0; j < FE_QW; ++j) {
+        tq01[j] = make_float2(__ldg(taps + (quad * 4 + 0) * FE_QW + j), __ldg(taps + (quad * 4 + 1) * FE_QW + j));
+        tq23[j] = make_float2(__ldg(taps + (quad * 4 + 2) * FE_QW + j), __ldg(taps + (quad * 4 + 3) * FE_QW + j));
+      }
     }
     for (int gi = 0; gi < n_my; ++gi) {
       const int buf = gi & 1;
@@ -203,19 +230,20 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
         float* fr = s_fr + buf * FE_FR_WORDS;
         for (int h = sl; h < p.HG; h += p.nslice) {
           const float* xs = sx + h * p.O;
-          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+          float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);
 #pragma unroll
           for (int j = 0; j < FE_QW; ++j) {
             const float xv = xs[j];
-            a0 = fmaf(tq[0][j], xv, a0);
-            a1 = fmaf(tq[1][j], xv, a1);
-            a2 = fmaf(tq[2][j], xv, a2);
-            a3 = fmaf(tq[3][j], xv, a3);
+            const float2 xx = make_float2(xv, xv);
+            a01 = __ffma2_rn(tq01[j], xx, a01);
+            a23 = __ffma2_rn(tq23[j], xx, a23);
           }
           const int o = h * p.P + 4 * quad;
           const int f = o / FE_NFFT, pos = o - f * FE_NFFT;
           const float4 w = *reinterpret_cast<const float4*>(s_win + pos);
-          *reinterpret_cast<float4*>(fr + f * (2 * FFT_Z_STRIDE) + pos) = make_float4(a0 * w.x, a1 * w.y, a2 * w.z, a3 * w.w);
+          a01 = __fmul2_rn(a01, make_float2(w.x, w.y));
+          a23 = __fmul2_rn(a23, make_float2(w.z, w.w));
+          *reinterpret_cast<float4*>(fr + f * (2 * FFT_Z_STRIDE) + pos) = make_float4(a01.x, a01.y, a23.x, a23.y);
         }
       }
       __threadfence_block();
@@ -270,16 +298,16 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
         const cf32* zb = zf + f * FFT_Z_STRIDE;
         const cf32 zk = zb[k];
         const cf32 zq = zb[k == 0 ? 0 : 500 - k];
-        const cf32 zn = cmake(zq.x, -zq.y);
-        const cf32 E = cmake(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
-        const cf32 D = cmake(zk.x - zn.x, zk.y - zn.y);
-        const cf32 Od = cmake(0.5f * D.y, -0.5f * D.x);   // -i/2 * D
+        // with zn = conj(zq):  2 E = zk + zn,  D = zk - zn,  2 T = D * (-i W^k)  (s_tw holds -i W^k)
+        const cf32 E2 = cadd(zk, cmake(zq.x, -zq.y));
+        const cf32 D = cadd(zk, cmake(-zq.x, zq.y));
         const float2 w = s_tw[k];
-        const cf32 Tt = cmulc(Od, w.x, w.y);
-        const float pr = E.x + Tt.x, pi = E.y + Tt.y, qr = E.x - Tt.x, qi = E.y - Tt.y;
+        const cf32 T2 = __ffma2_rn(cmake(-D.y, D.x), cmake(w.y, w.y), __fmul2_rn(D, cmake(w.x, w.x)));   // D * w
+        const cf32 Pv = cadd(E2, T2), Qv = csub(E2, T2);            // 2 X[k], 2 conj(X[500-k])
+        const cf32 Ps = __fmul2_rn(Pv, Pv), Qs = __fmul2_rn(Qv, Qv);
         float* pp = s_P + f * FE_P_STRIDE;
-        pp[k] = pr * pr + pi * pi;
-        pp[500 - k] = qr * qr + qi * qi;
+        pp[k] = Ps.x + Ps.y;                                        // 4 |X[k]|^2 (the 1/4 lives in the mel weights: exact)
+        pp[500 - k] = Qs.x + Qs.y;
       }
       bar_sync(BAR_FT, FE_ROLE);      // power spectrum complete; the frame buffer is no longer read
       if (gi + 2 < n_my) {
@@ -293,21 +321,18 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
       {
         const int f = rt & (FE_FR - 1), m = rt >> 3;
         const int64_t t = (int64_t)g * FE_FR + f;
-        const float* pp = s_P + f * FE_P_STRIDE + s_fbs[FE_NMEL + 1 + m];
-        const int s0 = s_fbs[m], e0 = s_fbs[m + 1];
-        const float* fv = s_fbv + s0;
-        const int len = e0 - s0;
-        float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-        int i = 0;
-        for (; i + 3 < len; i += 4) {
-          const float p0 = pp[i], p1 = pp[i + 1], p2 = pp[i + 2], p3 = pp[i + 3];
-          const float w0 = fv[i], w1 = fv[i + 1], w2 = fv[i + 2], w3 = fv[i + 3];
-          acc0 = fmaf(p0, w0, acc0);
-          acc1 = fmaf(p1, w1, acc1);
-          acc2 = fmaf(p2, w2, acc2);
-          acc3 = fmaf(p3, w3, acc3);
+        const float2* pp = reinterpret_cast<const float2*>(s_P + f * FE_P_STRIDE + s_fbs[FE_NMEL + 1 + m]);
+        const int s0 = s_fbs[m], n4 = (s_fbs[m + 1] - s0) >> 2;
+        const float2* fv = reinterpret_cast<const float2*>(s_fbv + s0);
+        float2 acc01 = make_float2(0.0f, 0.0f), acc23 = make_float2(0.0f, 0.0f);
+#pragma unroll 2
+        for (int i = 0; i < n4; ++i) {
+          const float2 p01 = pp[2 * i], p23 = pp[2 * i + 1];
+          const float2 w01 = fv[2 * i], w23 = fv[2 * i + 1];
+          acc01 = __ffma2_rn(p01, w01, acc01);
+          acc23 = __ffma2_rn(p23, w23, acc23);
         }
-        for (; i < len; ++i) acc0 = fmaf(pp[i], fv[i], acc0);
+        const float acc0 = acc01.x, acc1 = acc01.y, acc2 = acc23.x, acc3 = acc23.y;
         if (t < p.T) mel[(b * FE_NMEL + m) * p.T + t] = (acc0 + acc1) + (acc2 + acc3);
       }
     }
@@ -485,7 +510,7 @@ static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, in
   if (gpc > 40) gpc = 40;
   if (gpc > p.n_groups) gpc = p.n_groups;
   p.groups_per_cta = (int)gpc;
-  p.fb_nnz_pad = (fb_nnz + 3) & ~3;
+  p.fb_nnz_pad = (fb_nnz + 4 * FE_NMEL + 3) & ~3;   // every band: <= 1 leading + <= 3 trailing zero weights
   const size_t smem = fe_smem_bytes(p.SX, p.fb_nnz_pad);
   YAD_CHECK_ARG(smem <= 226 * 1024, "yad_frontend_mel_power: staging span too large (%zu B of shared memory)", smem);
   dim3 grid((unsigned)((p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta), (unsigned)B);
