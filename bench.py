@@ -141,7 +141,7 @@ def time_stages(model, x, reps=3):
 
     def fe_a():
         _lib.check(eng.lib.yad_frontend_mel_power(xc.data_ptr(), B, L, eng.rs_P, eng.rs_O, eng.rs_width, eng.rs_taps.data_ptr(),
-                                                  eng.rs_base.data_ptr(), eng.rs_window_len, eng.win.data_ptr(), eng.tw.data_ptr(),
+                                                  eng.rs_base.data_ptr(), _lib.ptr(eng.rs_lane_map), eng.rs_window_len, eng.win.data_ptr(), eng.tw.data_ptr(),
                                                   eng.fb_val.data_ptr(), eng.fb_bin.data_ptr(), eng.fb_start.data_ptr(),
                                                   eng.fb_val.numel(), mel.data_ptr(), T, eng._stream()), "fe_a")
     out["frontend_mel_ms"], _ = timed(fe_a)

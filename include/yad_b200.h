@@ -62,6 +62,11 @@ int yad_init(int device);
  *                                          cut to the quad's common window [tap_base[u], +YAD_FE_QW)
  *                                          of the 2*width+O wide tap axis, zero padded
  *   tap_base   [P/4]                  i32
+ *   lane_map   [256] or NULL          i32  resample-role thread -> work item: quad | (hop slice << 16), -1 = idle lane.
+ *                                          Built by the host so that the 32 lanes of a warp read 32 distinct
+ *                                          shared-memory banks ((tap_base[quad] + slice * O) mod 32 distinct per
+ *                                          warp); every (quad, slice), slice < min(256 / (P/4), hops per group),
+ *                                          must occur exactly once.  NULL: built-in (conflicting) order.
  *   window_len                        max(tap_base) + YAD_FE_QW (span of the padded signal one hop reads)
  *   window     [1000]                 f32  analysis window
  *   twiddle    [1000][2]              f32  exp(-2*pi*i*k/1000), built in fp64 by the host
@@ -71,8 +76,8 @@ int yad_init(int device);
  */
 #define YAD_FE_QW 21
 int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
-                           const float* taps, const int32_t* tap_base, int32_t window_len,
-                           const float* window, const float* twiddle, const float* fb_val,
+                           const float* taps, const int32_t* tap_base, const int32_t* lane_map,
+                           int32_t window_len, const float* window, const float* twiddle, const float* fb_val,
                            const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
                            int64_t T, yad_stream_t stream);
 
@@ -80,8 +85,8 @@ int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, in
  * hands it to the reference (inference.py:137-149), so the result is bit-identical to the fp32 entry point on those values;
  * half the bytes over PCIe and out of HBM. */
 int yad_frontend_mel_power_i16(const int16_t* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
-                               const float* taps, const int32_t* tap_base, int32_t window_len,
-                               const float* window, const float* twiddle, const float* fb_val,
+                               const float* taps, const int32_t* tap_base, const int32_t* lane_map,
+                               int32_t window_len, const float* window, const float* twiddle, const float* fb_val,
                                const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
                                int64_t T, yad_stream_t stream);
 

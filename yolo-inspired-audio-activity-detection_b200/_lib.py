@@ -44,8 +44,8 @@ _p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_do
 # name -> argument types (all return int)
 SIGNATURES = {
     "yad_init": [C.c_int],
-    "yad_frontend_mel_power": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
-    "yad_frontend_mel_power_i16": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
+    "yad_frontend_mel_power": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
+    "yad_frontend_mel_power_i16": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
     "yad_frontend_finish": [_p, _i64, _i64, _p, _f32, _i32, _p, _p, _p, _p, _p],
     "yad_conv_stem": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],
     "yad_conv_stem_tc": [_p, _i64, _i32, _i32, _p, _p, _i32, _i32, _p],

@@ -20,6 +20,7 @@
 // (modules/_architecture.py:182-189).
 #include "common.cuh"
 #include "fft500.cuh"
+#include "tc_ptx.cuh"
 
 namespace yad {
 
@@ -58,50 +59,48 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Stage the zero-padded PCM span of one group: element i of the span is xpad[x0 + i] = x[x0 + i] (zero outside [0, L)).
-// Fast path (clip base 16 B aligned, L % 4 == 0): 16-byte cp.async with zero fill, destination shifted by
-// (x0 mod 4) floats so that global and shared addresses are congruent mod 16.  Returns that shift.
-// Called by the FE_ROLE resample threads only (rt = thread index inside the role).
-__device__ __forceinline__ int fe_stage_async(float* s_x, const float* __restrict__ xb, int64_t x0, int SX, int64_t L,
-                                              bool fast, int rt) {
-  if (fast) {
-    const int shift = (int)(((x0 % 4) + 4) % 4);
-    const int nchunk = (shift + SX + 3) >> 2;
-    const int64_t g0 = x0 - shift;                      // multiple of 4
-    for (int c = rt; c < nchunk; c += FE_ROLE) {
-      const int64_t gi = g0 + 4 * (int64_t)c;
-      const bool ok = gi >= 0 && gi + 4 <= L;
-      cp_async16(s_x + 4 * c, xb + (ok ? gi : 0), ok ? 16 : 0);
-    }
-    cp_async_commit();
-    return shift;
-  }
-  for (int i = rt; i < SX; i += FE_ROLE) {
-    const int64_t src = x0 + i;
-    s_x[i] = (src >= 0 && src < L) ? __ldg(xb + src) : 0.0f;
-  }
-  return 0;
+// 1-D bulk copy global -> shared through the TMA unit (cp.async.bulk): one instruction for the whole span, completion
+// (byte count) signalled on an mbarrier.  Addresses and size are multiples of 16 bytes.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-// The same for 16-bit PCM (what audio files hold; torchaudio.load(normalize=True) turns it into x / 32768): 16-byte chunks of 8
-// samples, destination shifted by (x0 mod 8).  Fast path: clip base 16 B aligned and L % 8 == 0.
-__device__ __forceinline__ int fe_stage_async_i16(int16_t* s_raw, const int16_t* __restrict__ xb, int64_t x0, int SX, int64_t L,
-                                                  bool fast, int rt) {
+// Stage the zero-padded PCM span of one group: element i of the span is xpad[x0 + i] = x[x0 + i] (zero outside [0, L)).
+// Tp = float (EPC = 4 elements per 16-byte chunk) or int16_t (EPC = 8; what audio files hold: torchaudio.load(normalize=True)
+// turns it into x / 32768).  Fast path (clip base 16 B aligned, L % EPC == 0): the destination is shifted by (x0 mod EPC)
+// elements so that global and shared addresses are congruent mod 16 (returns that shift);
+//   * span entirely inside the clip: ONE bulk copy issued by thread 0 of the role (bulk = true; wait on the mbarrier);
+//   * span touching either end of the clip: 16-byte cp.async per thread with zero fill.
+// Called by the FE_ROLE resample threads only (rt = thread index inside the role).
+template <typename Tp, int EPC>
+__device__ __forceinline__ int fe_stage_async(Tp* s_dst, const Tp* __restrict__ xb, int64_t x0, int SX, int64_t L, bool fast,
+                                              int rt, uint64_t* bar, bool& bulk) {
+  bulk = false;
   if (fast) {
-    const int shift = (int)(((x0 % 8) + 8) % 8);
-    const int nchunk = (shift + SX + 7) >> 3;
-    const int64_t g0 = x0 - shift;                      // multiple of 8
+    const int shift = (int)(((x0 % EPC) + EPC) % EPC);
+    const int nchunk = (shift + SX + EPC - 1) / EPC;
+    const int64_t g0 = x0 - shift;                      // multiple of EPC
+    if (g0 >= 0 && g0 + (int64_t)EPC * nchunk <= L) {
+      bulk = true;
+      if (rt == 0) {
+        mbar_expect_tx(bar, (uint32_t)nchunk * 16u);
+        bulk_g2s(s_dst, xb + g0, (uint32_t)nchunk * 16u, bar);
+      }
+      return shift;
+    }
     for (int c = rt; c < nchunk; c += FE_ROLE) {
-      const int64_t gi = g0 + 8 * (int64_t)c;
-      const bool ok = gi >= 0 && gi + 8 <= L;
-      cp_async16(s_raw + 8 * c, xb + (ok ? gi : 0), ok ? 16 : 0);
+      const int64_t gi = g0 + EPC * (int64_t)c;
+      const bool ok = gi >= 0 && gi + EPC <= L;
+      cp_async16(s_dst + EPC * c, xb + (ok ? gi : 0), ok ? 16 : 0);
     }
     cp_async_commit();
     return shift;
   }
   for (int i = rt; i < SX; i += FE_ROLE) {
     const int64_t src = x0 + i;
-    s_raw[i] = (src >= 0 && src < L) ? xb[src] : (int16_t)0;
+    s_dst[i] = (src >= 0 && src < L) ? xb[src] : (Tp)0;
   }
   return 0;
 }
@@ -109,7 +108,8 @@ __device__ __forceinline__ int fe_stage_async_i16(int16_t* s_raw, const int16_t*
 template <bool I16>
 __global__ void __launch_bounds__(FE_THREADS, 1)
 frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float* __restrict__ taps,
-                    const int32_t* __restrict__ tap_base, const float* __restrict__ window,
+                    const int32_t* __restrict__ tap_base, const int32_t* __restrict__ lane_map,
+                    const float* __restrict__ window,
                     const float* __restrict__ twiddle, const float* __restrict__ fb_val,
                     const int32_t* __restrict__ fb_bin, const int32_t* __restrict__ fb_start,
                     float* __restrict__ mel) {
@@ -140,12 +140,19 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
   if (g_first >= p.n_groups) return;
   const int n_my = min(p.groups_per_cta, p.n_groups - g_first);
 
+  __shared__ __align__(8) uint64_t s_bar[2];    // completion of the bulk copy into staging buffer 0 / 1
   int shift = 0;
+  bool bulk = false;
   if (role == 0) {
+    if (rt == 0) {                              // the only thread that ever arrives on them; the others wait after __syncthreads
+      mbar_init(&s_bar[0], 1);
+      mbar_init(&s_bar[1], 1);
+      fence_barrier_init();
+    }
     if (I16)
-      shift = fe_stage_async_i16(s_raw, xb16, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt);
+      shift = fe_stage_async<int16_t, 8>(s_raw, xb16, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt, &s_bar[0], bulk);
     else
-      shift = fe_stage_async(s_x, xb, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt);
+      shift = fe_stage_async<float, 4>(s_x, xb, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt, &s_bar[0], bulk);
   }
 
   for (int i = tid; i < FE_NFFT; i += FE_THREADS) {
@@ -190,10 +197,23 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
     // ===================================================================== resample role
     // One quad of adjacent phases per thread; consecutive lanes take every second quad so that their x windows are
     // ~11 words apart (an odd stride: conflict-free shared-memory reads).
-    const int half = (p.nquad + 1) >> 1;
-    const int qi = rt % p.nquad, sl = rt / p.nquad;
-    const int quad = qi < half ? 2 * qi : 2 * (qi - half) + 1;
-    const bool active = sl < p.nslice;
+    // With a host-built lane map (frontend_consts.pack_resample_taps) the (quad, hop slice) items are spread over the warps so
+    // that the 32 lanes of every load hit 32 distinct banks; without one, consecutive lanes take every second quad (x windows
+    // ~11 words apart) which leaves ~1.9 wavefronts per load.
+    int quad, sl;
+    bool active;
+    if (lane_map != nullptr) {
+      const int mp = __ldg(lane_map + rt);
+      active = mp >= 0;
+      quad = mp & 0xffff;
+      sl = mp >> 16;
+    } else {
+      const int half = (p.nquad + 1) >> 1;
+      const int qi = rt % p.nquad;
+      sl = rt / p.nquad;
+      quad = qi < half ? 2 * qi : 2 * (qi - half) + 1;
+      active = sl < p.nslice;
+    }
     // taps of the phase pairs (4u, 4u+1) and (4u+2, 4u+3) as packed register pairs: one FFMA2 (fma.rn.f32x2 with the staged
     // sample broadcast to both lanes) advances two phases, so a quad costs 21 LDS + 42 FFMA2 instead of 21 LDS + 84 FFMA.
     // Each lane is an ordinary fmaf chain: results are bit-identical to the scalar form.
@@ -207,9 +227,14 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
         tq23[j] = make_float2(__ldg(taps + (quad * 4 + 2) * FE_QW + j), __ldg(taps + (quad * 4 + 3) * FE_QW + j));
       }
     }
+    uint32_t bar_phase = 0u;     // bit b: parity of the next completion on s_bar[b]
     for (int gi = 0; gi < n_my; ++gi) {
       const int buf = gi & 1;
       cp_async_wait_all();
+      if (bulk) {
+        mbar_wait(&s_bar[buf], (bar_phase >> buf) & 1u);
+        bar_phase ^= 1u << buf;
+      }
       bar_sync(BAR_RS, FE_ROLE);   // span of this group landed for every thread; nobody still reads the other buffer
       if (I16) {                   // int16 -> float (x / 32768, exact), once per sample; the previous group's reads of s_xf are done
         const int16_t* raw = s_raw + buf * sxp;
@@ -217,12 +242,13 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
         bar_sync(BAR_RS, FE_ROLE);
       }
       int shift_next = 0;
+      bool bulk_next = false;
       if (gi + 1 < n_my) {
         const int64_t x0n = (int64_t)(g_first + gi + 1) * p.HG * p.O - p.width;
         if (I16)
-          shift_next = fe_stage_async_i16(s_raw + (buf ^ 1) * sxp, xb16, x0n, p.SX, p.L, fast, rt);
+          shift_next = fe_stage_async<int16_t, 8>(s_raw + (buf ^ 1) * sxp, xb16, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1], bulk_next);
         else
-          shift_next = fe_stage_async(s_x + (buf ^ 1) * sxp, xb, x0n, p.SX, p.L, fast, rt);
+          shift_next = fe_stage_async<float, 4>(s_x + (buf ^ 1) * sxp, xb, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1], bulk_next);
       }
       if (gi >= 2) bar_sync(BAR_EMPTY0 + buf, FE_THREADS);   // FFT role released this frame buffer
       if (active) {
@@ -249,6 +275,7 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
       __threadfence_block();
       bar_arrive(BAR_FULL0 + buf, FE_THREADS);
       shift = shift_next;
+      bulk = bulk_next;
     }
   } else {
     // ===================================================================== FFT / mel role
@@ -473,7 +500,8 @@ int init_frontend_attrs() {
 extern "C" {
 
 static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
-                             const float* taps, const int32_t* tap_base, int32_t window_len, const float* window,
+                             const float* taps, const int32_t* tap_base, const int32_t* lane_map, int32_t window_len,
+                             const float* window,
                              const float* twiddle, const float* fb_val, const int32_t* fb_bin,
                              const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
   using namespace yad;
@@ -515,28 +543,28 @@ static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, in
   YAD_CHECK_ARG(smem <= 226 * 1024, "yad_frontend_mel_power: staging span too large (%zu B of shared memory)", smem);
   dim3 grid((unsigned)((p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta), (unsigned)B);
   if (i16)
-    frontend_mel_kernel<true><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, window, twiddle, fb_val,
+    frontend_mel_kernel<true><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, lane_map, window, twiddle, fb_val,
                                                                                 fb_bin, fb_start, mel);
   else
-    frontend_mel_kernel<false><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, window, twiddle, fb_val,
+    frontend_mel_kernel<false><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, lane_map, window, twiddle, fb_val,
                                                                                  fb_bin, fb_start, mel);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }
 
 int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
-                           const float* taps, const int32_t* tap_base, int32_t window_len, const float* window,
+                           const float* taps, const int32_t* tap_base, const int32_t* lane_map, int32_t window_len, const float* window,
                            const float* twiddle, const float* fb_val, const int32_t* fb_bin,
                            const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
-  return frontend_mel_impl(pcm, false, B, L, P, O, width, taps, tap_base, window_len, window, twiddle, fb_val, fb_bin, fb_start,
+  return frontend_mel_impl(pcm, false, B, L, P, O, width, taps, tap_base, lane_map, window_len, window, twiddle, fb_val, fb_bin, fb_start,
                            fb_nnz, mel, T, stream);
 }
 
 int yad_frontend_mel_power_i16(const int16_t* pcm, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
-                               const float* taps, const int32_t* tap_base, int32_t window_len, const float* window,
+                               const float* taps, const int32_t* tap_base, const int32_t* lane_map, int32_t window_len, const float* window,
                                const float* twiddle, const float* fb_val, const int32_t* fb_bin,
                                const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
-  return frontend_mel_impl(pcm, true, B, L, P, O, width, taps, tap_base, window_len, window, twiddle, fb_val, fb_bin, fb_start,
+  return frontend_mel_impl(pcm, true, B, L, P, O, width, taps, tap_base, lane_map, window_len, window, twiddle, fb_val, fb_bin, fb_start,
                            fb_nnz, mel, T, stream);
 }
 

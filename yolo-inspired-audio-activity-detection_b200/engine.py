@@ -97,15 +97,17 @@ class InferenceEngine:
     def _pack_frontend(self, model):
         dev = self.dev
         k = model.resampler.kernel
-        pk = fc.pack_resample_taps(k)
-        self.rs_P, self.rs_KW = pk["P"], pk["KW"]
         g = math.gcd(int(self.cfg["sample_rate"]), int(self.cfg["new_sample_rate"]))
         self.rs_O = int(self.cfg["sample_rate"]) // g
+        P = int(self.cfg["new_sample_rate"]) // g
+        pk = fc.pack_resample_taps(k, orig_step=self.rs_O, hops_per_group=(8 * 1000) // P if (8 * 1000) % P == 0 else 0)
+        self.rs_P, self.rs_KW = pk["P"], pk["KW"]
         if int(self.cfg["new_sample_rate"]) // g != self.rs_P:
             raise ValueError("resampler.kernel does not match sample_rate/new_sample_rate")
         self.rs_width = (self.rs_KW - self.rs_O) // 2
         self.rs_taps = pk["taps"].to(dev)
         self.rs_base = pk["base"].to(dev)
+        self.rs_lane_map = None if pk["lane_map"] is None else pk["lane_map"].to(dev)
         self.rs_window_len = pk["window_len"]
         self.win = model.melspectogram_tfmr.spectrogram.window.detach().to(dev, torch.float32).contiguous()
         csr = fc.pack_mel_csr(model.melspectogram_tfmr.mel_scale.fb)
@@ -315,7 +317,7 @@ class InferenceEngine:
         xs = plan["xs"]
         fn = self.lib.yad_frontend_mel_power_i16 if i16 else self.lib.yad_frontend_mel_power
         rc = fn(x.data_ptr(), B, L, self.rs_P, self.rs_O, self.rs_width, self.rs_taps.data_ptr(),
-                                             self.rs_base.data_ptr(), self.rs_window_len, self.win.data_ptr(), self.tw.data_ptr(),
+                                             self.rs_base.data_ptr(), _lib.ptr(self.rs_lane_map), self.rs_window_len, self.win.data_ptr(), self.tw.data_ptr(),
                                              self.fb_val.data_ptr(), self.fb_bin.data_ptr(), self.fb_start.data_ptr(),
                                              self.fb_val.numel(), mel.data_ptr(), T, self._stream())
         _lib.check(rc, "frontend_mel_power")
