@@ -43,7 +43,8 @@ struct FeParams {
   int32_t P, O, width;
   int32_t HG;        // hops per group = FE_FR * FE_NFFT / P
   int32_t SX;        // staged PCM floats per group
-  int32_t n_groups;  // ceil(T / FE_FR)
+  int32_t n_groups;  // ceil(T / FE_FR), per clip
+  int64_t total_groups;   // B * n_groups
   int32_t groups_per_cta;
   int32_t fb_nnz_pad;  // mel CSR values, rounded up to a multiple of 4
   int32_t nquad, nslice;
@@ -129,17 +130,23 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
   const int tid = threadIdx.x;
   const int role = tid >> 8;          // 0: resample, 1: FFT / mel
   const int rt = tid & (FE_ROLE - 1);
-  const int64_t b = blockIdx.y;
-  const float* xb = reinterpret_cast<const float*>(pcm) + b * p.L;
-  const int16_t* xb16 = reinterpret_cast<const int16_t*>(pcm) + b * p.L;
+  // Persistent CTAs: the B * n_groups frame groups of the batch are one flat sequence (clip-major) that is cut into gridDim.x
+  // contiguous runs; group gl belongs to clip gl / n_groups.  The tables above are loaded once per CTA and the double-buffered
+  // staging pipeline runs straight across clip boundaries.
+  const float* xf = reinterpret_cast<const float*>(pcm);
+  const int16_t* x16 = reinterpret_cast<const int16_t*>(pcm);
   int16_t* s_raw = reinterpret_cast<int16_t*>(s_x);          // [2][sxp] int16 (= sxp floats in total)
   float* s_xf = s_x + sxp;
   const bool fast = I16 ? (((p.L & 7) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0))
                         : (((p.L & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0));
-  const int g_first = blockIdx.x * p.groups_per_cta;
-  if (g_first >= p.n_groups) return;
-  const int n_my = min(p.groups_per_cta, p.n_groups - g_first);
-
+  const int64_t g_first = (int64_t)blockIdx.x * p.groups_per_cta;
+  if (g_first >= p.total_groups) return;
+  const int n_my = (int)min((int64_t)p.groups_per_cta, p.total_groups - g_first);
+  // start sample (in the zero-padded clip) of group gl and its clip
+  auto group_x0 = [&](int64_t gl, int64_t& clip) {
+    clip = gl / p.n_groups;
+    return (gl - clip * p.n_groups) * p.HG * p.O - p.width;
+  };
   __shared__ __align__(8) uint64_t s_bar[2];    // completion of the bulk copy into staging buffer 0 / 1
   int shift = 0;
   bool bulk = false;
@@ -149,10 +156,12 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
       mbar_init(&s_bar[1], 1);
       fence_barrier_init();
     }
+    int64_t clip;
+    const int64_t x0 = group_x0(g_first, clip);
     if (I16)
-      shift = fe_stage_async<int16_t, 8>(s_raw, xb16, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt, &s_bar[0], bulk);
+      shift = fe_stage_async<int16_t, 8>(s_raw, x16 + clip * p.L, x0, p.SX, p.L, fast, rt, &s_bar[0], bulk);
     else
-      shift = fe_stage_async<float, 4>(s_x, xb, (int64_t)g_first * p.HG * p.O - p.width, p.SX, p.L, fast, rt, &s_bar[0], bulk);
+      shift = fe_stage_async<float, 4>(s_x, xf + clip * p.L, x0, p.SX, p.L, fast, rt, &s_bar[0], bulk);
   }
 
   for (int i = tid; i < FE_NFFT; i += FE_THREADS) {
@@ -244,11 +253,14 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
       int shift_next = 0;
       bool bulk_next = false;
       if (gi + 1 < n_my) {
-        const int64_t x0n = (int64_t)(g_first + gi + 1) * p.HG * p.O - p.width;
+        int64_t clip;
+        const int64_t x0n = group_x0(g_first + gi + 1, clip);
         if (I16)
-          shift_next = fe_stage_async<int16_t, 8>(s_raw + (buf ^ 1) * sxp, xb16, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1], bulk_next);
+          shift_next = fe_stage_async<int16_t, 8>(s_raw + (buf ^ 1) * sxp, x16 + clip * p.L, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1],
+                                                  bulk_next);
         else
-          shift_next = fe_stage_async<float, 4>(s_x + (buf ^ 1) * sxp, xb, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1], bulk_next);
+          shift_next = fe_stage_async<float, 4>(s_x + (buf ^ 1) * sxp, xf + clip * p.L, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1],
+                                                bulk_next);
       }
       if (gi >= 2) bar_sync(BAR_EMPTY0 + buf, FE_THREADS);   // FFT role released this frame buffer
       if (active) {
@@ -284,7 +296,8 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
     const int fB = rt / 25, k1 = rt - fB * 25;
     for (int gi = 0; gi < n_my; ++gi) {
       const int buf = gi & 1;
-      const int g = g_first + gi;
+      const int64_t b = (g_first + gi) / p.n_groups;
+      const int g = (int)((g_first + gi) - b * p.n_groups);
       cf32* zf = reinterpret_cast<cf32*>(s_fr + buf * FE_FR_WORDS);
       cf32* yf = reinterpret_cast<cf32*>(s_Y);
       bar_sync(BAR_FULL0 + buf, FE_THREADS);
@@ -512,7 +525,7 @@ static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, in
   YAD_CHECK_ARG((FE_FR * FE_NFFT) % P == 0, "yad_frontend_mel_power: %d-sample frame groups must be whole hops of P=%d",
                 FE_FR * FE_NFFT, P);
   YAD_CHECK_ARG(O >= 1 && width >= 0 && window_len >= FE_QW, "yad_frontend_mel_power: bad O/width/window_len");
-  YAD_CHECK_ARG(B >= 0 && B <= 65535 && L >= 1 && T >= 1, "yad_frontend_mel_power: bad B/L/T");
+  YAD_CHECK_ARG(B >= 0 && B <= (1 << 24) && L >= 1 && T >= 1, "yad_frontend_mel_power: bad B/L/T");
   YAD_CHECK_ARG(fb_nnz >= 1 && fb_nnz <= 16384, "yad_frontend_mel_power: bad fb_nnz=%d", fb_nnz);
   // frames must exist in the resampled signal: T*1000 <= ceil(P*L/O)
   YAD_CHECK_ARG((int64_t)T * FE_NFFT <= (P * L + O - 1) / O, "yad_frontend_mel_power: T=%lld frames exceed the resampled length",
@@ -531,17 +544,16 @@ static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, in
   p.nquad = P / 4;
   p.nslice = FE_ROLE / p.nquad;
   if (p.nslice > p.HG) p.nslice = p.HG;
-  // runs of groups per CTA: long enough to amortise the table / tap loads, short enough for >= ~8 CTAs per SM overall
+  // persistent CTAs (one per SM: the kernel's shared memory allows no more): equal contiguous runs of the flat group sequence
   const int nsm = sm_count() > 0 ? sm_count() : 148;
-  int64_t gpc = (B * (int64_t)p.n_groups) / ((int64_t)nsm * 8);
-  if (gpc < 1) gpc = 1;
-  if (gpc > 40) gpc = 40;
-  if (gpc > p.n_groups) gpc = p.n_groups;
+  p.total_groups = B * (int64_t)p.n_groups;
+  const int64_t gpc = (p.total_groups + nsm - 1) / nsm;
+  YAD_CHECK_ARG(gpc < (1ll << 30), "yad_frontend_mel_power: batch too large");
   p.groups_per_cta = (int)gpc;
   p.fb_nnz_pad = (fb_nnz + 4 * FE_NMEL + 3) & ~3;   // every band: <= 1 leading + <= 3 trailing zero weights
   const size_t smem = fe_smem_bytes(p.SX, p.fb_nnz_pad);
   YAD_CHECK_ARG(smem <= 226 * 1024, "yad_frontend_mel_power: staging span too large (%zu B of shared memory)", smem);
-  dim3 grid((unsigned)((p.n_groups + p.groups_per_cta - 1) / p.groups_per_cta), (unsigned)B);
+  dim3 grid((unsigned)((p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta));
   if (i16)
     frontend_mel_kernel<true><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, lane_map, window, twiddle, fb_val,
                                                                                 fb_bin, fb_start, mel);
