@@ -125,7 +125,10 @@ YAD_HD void dft20(cf32 (&v)[NV]) {
 // barriers; their frame strides are chosen so that consecutive work items (which straddle frames inside a warp) keep
 // walking through distinct banks (see frontend.cu).
 constexpr int FFT_NZ = 500;           // complex points per frame
-constexpr int FFT_Z_STRIDE = 500;     // natural-order frames (input z and output spectrum): 1000 words = 8 (mod 32)
+constexpr int FFT_Z_STRIDE = 500;     // natural-order input frames z
+constexpr int FFT_X_STRIDE = 505;     // output spectrum (aliases the frame buffer after pass A): pass-B work item i = 25 f + k1
+                                      // writes slot 480 f + i + 25 k2, and 480 slots = 0 (mod 32 banks): 16 consecutive
+                                      // items always hit 16 distinct bank pairs, also across a frame boundary
 constexpr int FFT_Y_PITCH = 21;       // Y[k1][n2] row pitch
 constexpr int FFT_Y_STRIDE = 525;     // 25 rows x 21: 1050 words = 26 (mod 32)
 

@@ -30,7 +30,7 @@ constexpr int FE_NMEL = 32;
 constexpr int FE_QW = YAD_FE_QW;    // taps per phase over the quad's common window (zero padded)
 constexpr int FE_ROLE = 256;        // threads per role
 constexpr int FE_THREADS = 2 * FE_ROLE;
-constexpr int FE_FR_WORDS = FE_FR * 2 * FFT_Z_STRIDE;   // frame buffer (floats): frames in, spectrum out (natural order)
+constexpr int FE_FR_WORDS = FE_FR * 2 * FFT_X_STRIDE;   // frame buffer (floats): frames in (stride FFT_Z_STRIDE), spectrum out (FFT_X_STRIDE)
 constexpr int FE_Y_WORDS = FE_FR * 2 * FFT_Y_STRIDE;    // pass-A -> pass-B exchange buffer
 constexpr int FE_P_STRIDE = 516;    // power-spectrum row pitch (= 4 mod 32: 8 frames x 4 adjacent bins hit 32 distinct banks)
 constexpr int FE_NPAIR = FE_FR * 251;
@@ -291,8 +291,12 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
     }
   } else {
     // ===================================================================== FFT / mel role
+    // pass-A work items (frame fA, column n2): half-warp h of warps 0..3 takes frame h, n2 = 0..15 (16 consecutive slots for
+    // every load / store; both halves read the same twiddles: broadcast); warp 4 takes n2 = 16..19 of all 8 frames.
+    // (The plain item = 20 f + n2 order cost 3.2 shared-memory wavefronts per 64-bit access instead of 2.)
     const bool actA = rt < FE_FR * 20, actB = rt < FE_FR * 25;
-    const int fA = rt / 20, n2 = rt - fA * 20;
+    const int fA = rt < 128 ? (rt >> 4) : ((rt - 128) >> 2);
+    const int n2 = rt < 128 ? (rt & 15) : 16 + (rt & 3);
     const int fB = rt / 25, k1 = rt - fB * 25;
     for (int gi = 0; gi < n_my; ++gi) {
       const int buf = gi & 1;
@@ -327,7 +331,7 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
 #pragma unroll
         for (int j = 0; j < 20; ++j) v[j] = src[j];
         dft20(v);
-        cf32* dst = zf + fB * FFT_Z_STRIDE + k1;
+        cf32* dst = zf + fB * FFT_X_STRIDE + k1;
 #pragma unroll
         for (int r = 0; r < 20; ++r) dst[25 * passB_k2_of_reg(r)] = v[r];
       }
@@ -335,7 +339,7 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
       // ---- real-FFT untangle + power: X[k] = E + W^k O ; X[500-k] = conj(E - W^k O); one thread owns the pair
       for (int item = rt; item < FE_NPAIR; item += FE_ROLE) {
         const int f = item / 251, k = item - f * 251;
-        const cf32* zb = zf + f * FFT_Z_STRIDE;
+        const cf32* zb = zf + f * FFT_X_STRIDE;
         const cf32 zk = zb[k];
         const cf32 zq = zb[k == 0 ? 0 : 500 - k];
         // with zn = conj(zq):  2 E = zk + zn,  D = zk - zn,  2 T = D * (-i W^k)  (s_tw holds -i W^k)
