@@ -268,9 +268,55 @@ def _basic_block(sd, p, x, stride):
     return F.relu(out + idt)
 
 
-def backbone(sd: Dict[str, Tensor], x: Tensor, block_layers: Sequence[int] = (2, 2, 2, 2)) -> List[Tensor]:
-    """ResNetBackBone.forward (eval: dropout = identity).  ref: modules/_backbone.py:142-152."""
+def _bottleneck(sd, p, x, stride):
+    """[tv] models/resnet.py:143-163 (resnet_config.block = Bottleneck, ref: modules/_backbone.py:128-138): 1x1 - 3x3 (stride) -
+    1x1 (x4), residual add, ReLU."""
+    idt = x
+    out = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"], None, 1, 0)))
+    out = F.relu(_bn(sd, p + ".bn2", F.conv2d(out, sd[p + ".conv2.weight"], None, stride, 1)))
+    out = _bn(sd, p + ".bn3", F.conv2d(out, sd[p + ".conv3.weight"], None, 1, 0))
+    if (p + ".downsample.0.weight") in sd:
+        idt = _bn(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride, 0))
+    return F.relu(out + idt)
+
+
+def _extractor_block(sd, p, x):
+    """ExtractorBlock.forward.  ref: modules/_backbone.py:49-79: only the LAST layer of a block halves the width."""
+    n = 0
+    while (f"{p}.module_dict.layer{n}._res_layer.weight") in sd:
+        n += 1
+    for i in range(n):
+        q = f"{p}.module_dict.layer{i}"
+        sw = 2 if i + 1 == n else 1
+        x1 = F.conv2d(x, sd[q + "._layer.0.weight"], sd[q + "._layer.0.bias"], stride=(1, sw), padding=(1, 3))
+        x1 = F.leaky_relu(_bn(sd, q + "._layer.1", x1), 0.2)
+        x1 = F.conv2d(x1, sd[q + "._layer.3.weight"], sd[q + "._layer.3.bias"], stride=(1, 1), padding=(1, 3))
+        x1 = _bn(sd, q + "._layer.4", x1)
+        x2 = F.conv2d(x, sd[q + "._res_layer.weight"], sd[q + "._res_layer.bias"], stride=(1, sw))
+        x = torch.cat((x1, x2), dim=1)
+    return x
+
+
+def custom_backbone(sd: Dict[str, Tensor], x: Tensor) -> List[Tensor]:
+    """CustomBackBone.forward (eval).  ref: modules/_backbone.py:108-116."""
     p = "feature_extractor"
+    x = F.conv2d(x, sd[p + ".first_conv.0.weight"], sd[p + ".first_conv.0.bias"], 1, 3)
+    x = F.leaky_relu(_bn(sd, p + ".first_conv.1", x), 0.2)
+    x = _extractor_block(sd, p + ".entry_block", x)
+    fmaps = []
+    for i in range(1, 5):
+        x = _extractor_block(sd, f"{p}.block{i}", x)
+        fmaps.append(x)
+    return fmaps
+
+
+def backbone(sd: Dict[str, Tensor], x: Tensor, block_layers: Sequence[int] = (2, 2, 2, 2)) -> List[Tensor]:
+    """ResNetBackBone.forward (eval: dropout = identity).  ref: modules/_backbone.py:142-152.  The backbone family is read off
+    the state dict: ``first_conv`` keys = CustomBackBone, ``conv3`` keys = torchvision Bottleneck, else BasicBlock."""
+    p = "feature_extractor"
+    if (p + ".first_conv.0.weight") in sd:
+        return custom_backbone(sd, x)
+    block = _bottleneck if (p + ".layer1.0.conv3.weight") in sd else _basic_block
     x = F.conv2d(x, sd[p + ".conv1.weight"], None, 2, 3)
     x = F.conv2d(x, sd[p + ".conv2.weight"], None, 2, 3)
     x = F.relu(_bn(sd, p + ".bn1", x))
@@ -278,7 +324,7 @@ def backbone(sd: Dict[str, Tensor], x: Tensor, block_layers: Sequence[int] = (2,
     for li, n in enumerate(block_layers):
         for bi in range(n):
             stride = 2 if (li > 0 and bi == 0) else 1
-            x = _basic_block(sd, f"{p}.layer{li + 1}.{bi}", x, stride)
+            x = block(sd, f"{p}.layer{li + 1}.{bi}", x, stride)
         fmaps.append(x)
     return fmaps
 

@@ -54,3 +54,32 @@ def cuda_dev():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+VARIANTS = {"bottleneck": {"resnet_config": {"block": "Bottleneck"}}, "custom": {"backbone": "custom"}}
+
+
+@pytest.fixture(scope="session")
+def variant_state_dict(meta):
+    """(state dict, config) of the other config-selectable backbones with the synthetic weights of
+    tests/golden/make_golden_backbones.py; the key layout is the live reference's (backbones_layout.json)."""
+    import copy
+    import synth
+    from oracle import ref_port as O
+    with open(os.path.join(GOLD, "backbones_layout.json")) as f:
+        layouts = json.load(f)
+    cache = {}
+
+    def make(name):
+        if name not in cache:
+            cfg = copy.deepcopy(O.DEFAULT_CONFIG)
+            cfg.update(copy.deepcopy(VARIANTS[name]))
+            layout = {k: v for k, v in layouts[name].items() if k not in SKIP_KEYS}
+            sd = synth.synth_state_dict(layout, seed=42)
+            sd.update(O.frontend_constants())
+            for k in ("sm_anchors", "md_anchors", "lg_anchors"):
+                sd[k] = torch.tensor(meta["anchors"][k], dtype=torch.float32)
+            sd["taper_window"] = torch.empty(0)
+            cache[name] = (sd, cfg)
+        return cache[name]
+    return make

@@ -36,6 +36,8 @@ def synth_state_dict(layout: Dict[str, Sequence[int]], seed: int = 42) -> Dict[s
         elif ".norm.weight" in k or ".bn" in k and k.endswith(".weight") or k.endswith("identity.weight") \
                 or ".downsample.1.weight" in k:
             out[k] = torch.rand(shp, generator=g) + 0.5
+        elif k.endswith(".weight") and len(shp) == 1:   # any other BatchNorm weight (custom backbone: first_conv.1, _layer.1/.4)
+            out[k] = torch.rand(shp, generator=g) + 0.5
         elif k.endswith(".bias"):
             out[k] = torch.randn(shp, generator=g) * 0.2
         else:

@@ -226,3 +226,24 @@ def test_evaluate_waveform_vs_live_reference(gold, ref_state_dict):
     np.testing.assert_array_equal(bidx.numpy(), bidx_e.numpy())
     np.testing.assert_allclose(seg.numpy(), seg_e.numpy(), atol=1e-4, rtol=1e-5)
     assert _rows_as_csv(rows) == rows_e
+
+
+# ---------------------------------------------------------------- other config-selectable backbones
+@pytest.mark.parametrize("variant", ["bottleneck", "custom"])
+@pytest.mark.parametrize("form", ["train", "deploy"])
+def test_other_backbones_short_clips(gold, variant_state_dict, variant, form):
+    """Bottleneck ResNet and the 3x7 CustomBackBone (2-D neck) vs the live reference's eval() outputs."""
+    g = gold("backbones")
+    sd, cfg = variant_state_dict(variant)
+    if form == "deploy":
+        sd = O.fold_repvgg(sd)
+    x = synth.synth_clips(2, 22050 * 6, seed=3000, silence_tail_every=0)
+    taps = {}
+    out = O.forward(x, sd, 2, config=cfg, taps=taps)
+    assert out.shape == (2, 63, 5)
+    np.testing.assert_allclose(out.numpy(), g[f"{variant}.preds_{form}"], atol=5e-3)
+    if form == "train":
+        np.testing.assert_allclose(taps["fmaps"][0][:, ::8, ::4, ::2].numpy(), g[f"{variant}.fmap1_s"], atol=2e-3)
+        np.testing.assert_allclose(taps["fmaps"][3][:, ::8, ::4, :].numpy(), g[f"{variant}.fmap4_s"], atol=2e-3)
+        for i, h in enumerate(taps["heads"]):
+            np.testing.assert_allclose(h.numpy(), g[f"{variant}.head{i}"], atol=5e-3)

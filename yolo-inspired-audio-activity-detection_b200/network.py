@@ -143,26 +143,112 @@ class BasicBlock(_NoForward):
             self.downsample = None
 
 
+class Bottleneck(_NoForward):
+    """torchvision Bottleneck parameter layout (conv1 1x1, conv2 3x3 carrying the stride, conv3 1x1 to 4 x planes,
+    downsample.{0,1}).  ref: [tv] models/resnet.py:108-163; selected by ``resnet_config.block: Bottleneck``
+    (modules/_backbone.py:128-138)."""
+    expansion = 4
+
+    def __init__(self, cin: int, planes: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, planes, 1, 1, 0, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, 1, 0, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.stride = stride
+        if stride != 1 or cin != planes * 4:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+        else:
+            self.downsample = None
+
+
 class ResNetBackBone(_NoForward):
     def __init__(self, in_channels: int, dropout: float = 0.0, block: str = "BasicBlock",
                  block_layers: Optional[Iterable[int]] = None):
         super().__init__()
-        if block not in ("BasicBlock",) and getattr(block, "__name__", None) != "BasicBlock":
-            _unsupported(f"resnet_config.block={block!r} (only BasicBlock, the reference default)")
+        name = block if isinstance(block, str) else getattr(block, "__name__", None)
+        if name not in ("BasicBlock", "Bottleneck"):
+            _unsupported(f"resnet_config.block={block!r} (BasicBlock and Bottleneck are the torchvision blocks)")
+        self.block_name = name
+        exp = 1 if name == "BasicBlock" else 4
         layers = list(block_layers or [3, 4, 6, 3])
         self.in_channels = in_channels
         self.dropout_p = dropout
         self.conv1 = nn.Conv2d(in_channels, 64, (7, 7), (2, 2), (3, 3), bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         cin = 64
-        for li, (n, cout) in enumerate(zip(layers, (64, 128, 256, 512))):
+        for li, (n, planes) in enumerate(zip(layers, (64, 128, 256, 512))):
             blocks = []
             for bi in range(n):
-                blocks.append(BasicBlock(cin, cout, 2 if (li > 0 and bi == 0) else 1))
-                cin = cout
+                stride = 2 if (li > 0 and bi == 0) else 1
+                blocks.append(BasicBlock(cin, planes, stride) if exp == 1 else Bottleneck(cin, planes, stride))
+                cin = planes * exp
             setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
         self.conv2 = nn.Conv2d(64, 64, (7, 7), (2, 2), (3, 3), bias=False)
-        self.fmap1_ch, self.fmap2_ch, self.fmap3_ch, self.fmap4_ch = 64, 128, 256, 512
+        self.fmap1_ch, self.fmap2_ch, self.fmap3_ch, self.fmap4_ch = 64 * exp, 128 * exp, 256 * exp, 512 * exp
+
+
+class ExtractorLayer(_NoForward):
+    """ref: modules/_backbone.py:8-46.  ``_layer`` = conv(3x7, stride (1, sw)) - BN - LeakyReLU(0.2) - conv(3x7, stride (sh, 1)) -
+    BN - Dropout (no activation after the second BatchNorm); ``_res_layer`` = biased 1x1 conv with stride (sh, sw) (the
+    reference's ``if not (h_stride or w_stride)`` is never true, so it is never an Identity); output = cat(_layer, _res_layer)."""
+
+    def __init__(self, cin: int, cout: int, dropout: float = 0.0, halve_w: bool = False, halve_h: bool = False):
+        super().__init__()
+        if cout % 2 == 0:
+            out = res_out = cout // 2
+        else:
+            res_out = cout // 2
+            out = cout - res_out
+        sw, sh = (2 if halve_w else 1), (2 if halve_h else 1)
+        self._layer = nn.Sequential(
+            nn.Conv2d(cin, 32, kernel_size=(3, 7), stride=(1, sw), padding=(1, 3)),
+            nn.BatchNorm2d(32),
+            nn.LeakyReLU(0.2),
+            nn.Conv2d(32, out, kernel_size=(3, 7), stride=(sh, 1), padding=(1, 3)),
+            nn.BatchNorm2d(out),
+            nn.Dropout(dropout),
+        )
+        self._res_layer = nn.Conv2d(cin, res_out, kernel_size=(1, 1), stride=(sh, sw))
+
+
+class ExtractorBlock(_NoForward):
+    """ref: modules/_backbone.py:49-79: ``num_layers`` ExtractorLayers, widths 64, 128, ... and the last one = out_channels with
+    the width halved."""
+
+    def __init__(self, cin: int, cout: int, num_layers: int, dropout: float = 0.0):
+        super().__init__()
+        width, md = 64, {}
+        for i in range(num_layers):
+            last = i + 1 == num_layers
+            if last:
+                width = cout
+            md[f"layer{i}"] = ExtractorLayer(cin, width, dropout=dropout, halve_h=False, halve_w=last)
+            cin = width
+            width *= 2
+        self.module_dict = nn.ModuleDict(md)
+
+
+class CustomBackBone(_NoForward):
+    """ref: modules/_backbone.py:82-116 (``backbone: custom``): the height stays 32 through the whole backbone, so the neck runs
+    in 2-D and the heads are averaged over H at the very end (modules/_common.py:248,259-261)."""
+
+    def __init__(self, in_channels: int, dropout: float = 0.0, block_layers: Optional[Iterable[int]] = None):
+        super().__init__()
+        bl = list(block_layers or [3, 4, 6, 3])
+        if len(bl) != 4:
+            raise ValueError("block config must be a list of length = 4")
+        self.in_channels = in_channels
+        self.first_conv = nn.Sequential(nn.Conv2d(in_channels, 64, kernel_size=(7, 7), stride=1, padding=3),
+                                        nn.BatchNorm2d(64), nn.LeakyReLU(0.2))
+        self.entry_block = ExtractorBlock(64, 64, 2, dropout=dropout)
+        self.block1 = ExtractorBlock(64, 128, bl[0], dropout=dropout)
+        self.block2 = ExtractorBlock(128, 256, bl[1], dropout=dropout)
+        self.block3 = ExtractorBlock(256, 512, bl[2], dropout=dropout)
+        self.block4 = ExtractorBlock(512, 1024, bl[3], dropout=dropout)
+        self.fmap1_ch, self.fmap2_ch, self.fmap3_ch, self.fmap4_ch = 128, 256, 512, 1024
 
 
 class _Buf(nn.Module):
@@ -222,10 +308,13 @@ class AudioDetectionNetwork(nn.Module):
         self.md_anchors = nn.Parameter(torch.FloatTensor(cfg["anchors"]["md"]) / dur, requires_grad=ta)
         self.lg_anchors = nn.Parameter(torch.FloatTensor(cfg["anchors"]["lg"]) / dur, requires_grad=ta)
 
-        if cfg["backbone"] != "resnet":
-            _unsupported(f"backbone={cfg['backbone']!r} (SURVEY section 8(f) N3; only the default 'resnet' path is built)")
-        self.feature_extractor = ResNetBackBone(2, dropout=cfg["dropout"], block_layers=cfg["block_layers"],
-                                                **cfg["resnet_config"])
+        if cfg["backbone"] == "custom":         # modules/_architecture.py:46-58
+            self.feature_extractor = CustomBackBone(2, dropout=cfg["dropout"], block_layers=cfg["block_layers"])
+        elif cfg["backbone"] == "resnet":
+            self.feature_extractor = ResNetBackBone(2, dropout=cfg["dropout"], block_layers=cfg["block_layers"],
+                                                    **cfg["resnet_config"])
+        else:
+            raise ValueError(f"invalid backbone {cfg['backbone']}")
         fe = self.feature_extractor
         self.multiscale_module = MultiScaleFmapModule(fe.fmap1_ch, fe.fmap2_ch, fe.fmap3_ch, fe.fmap4_ch,
                                                       out_channels=self.out_channels)
