@@ -194,6 +194,17 @@ int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C,
 int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
                    void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
 
+/* Height half of the 2-D SPPF pools (modules/_common.py:197,207-209 when the neck keeps its height, i.e. backbone: custom):
+ * out[b,h,w,c] = max over rows h-radius..h+radius (clipped) of the channel slice [ci_off, ci_off+C) of in [B,H,W,ld_in].
+ * k cascaded 5x5 stride-1 max pools = a (4k+1)^2 box max = yad_maxpool_h(radius 2k) of the k-fold W cascade that
+ * yad_sppf_pools (called with B*H rows) writes.  Out of place. */
+int yad_maxpool_h(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
+                  int32_t radius, void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream);
+/* x_spectral [B,C,H,W] f32 -> NHWC [B,H,W,ld_out] (out_dtype): input layout of CustomBackBone.first_conv
+ * (modules/_backbone.py:97-101,109). */
+int yad_nchw_to_nhwc(const float* in, int64_t B, int32_t C, int32_t H, int32_t W, void* out, int32_t out_dtype, int32_t ld_out,
+                     yad_stream_t stream);
+
 /* RepVGG train-form merge (modules/_common.py:90-95): out = act(a + b [+ scale*x + shift]); a, b are the
  * activated 3x3 / 1x1 branches [npix, ld_ab]; (scale, shift) the eval-mode identity BatchNorm (x may be NULL). */
 int yad_repvgg_merge(const void* a, const void* b, const void* x, const float* scale, const float* shift,
@@ -371,6 +382,18 @@ int yad_colsum_f64(const float* x, int32_t ld, int64_t N, int32_t C, double* ws,
 int yad_adam_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
                       int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                       int32_t step, float ema_momentum, yad_stream_t stream);
+
+/* ------------------------------------------------------------------ anchor clustering
+ * Replaces the iterations of sklearn.cluster.KMeans(algorithm="lloyd") in compute_anchors.py:72-86 for 1-D data (the segment
+ * durations), fp64, one CTA iterating to convergence on the device.
+ *   x        [n]  f64   centred data (device)
+ *   centers  [k]  f64   in: initial centres (k-means++ / random seeding is done by the host), out: final centres; k <= 16
+ *   tol_abs             tol * var(x): stop when sum_j |c_j' - c_j|^2 <= tol_abs, or when no label changes
+ *   labels   [n]  i32   out: label of every point for the final centres
+ *   n_iter   [1]  i32,  inertia [1] f64   out (device)
+ * E-step: argmin_j (c_j^2 - 2 x c_j), first minimum on ties; empty clusters are re-seeded with the farthest points. */
+int yad_kmeans1d_lloyd(const double* x, int64_t n, double* centers, int32_t k, int32_t max_iter, double tol_abs,
+                       int32_t* labels, int32_t* n_iter, double* inertia, yad_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -769,3 +769,105 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step: int, lr=1e-3, betas=(0.9
         bc2 = 1 - b2 ** step
         denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
         p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+# =====================================================================================================================
+# Anchor clustering.  ref: compute_anchors.py:63-87 -> sklearn.cluster.KMeans (sklearn 1.9.0, the image's
+# version; not vendored under /root/reference), algorithm "lloyd" on the 1-D segment durations, 9 clusters, sorted centres cut
+# into sm / md / lg triples.  Restated from sklearn/cluster/_kmeans.py (_kmeans_plusplus, _kmeans_single_lloyd, _tolerance,
+# KMeans.fit) and _k_means_lloyd.pyx / _k_means_common.pyx (E-step argmin of |c|^2 - 2 x.c, empty-cluster relocation, averaging).
+# Pinned by tests/golden/anchors.npz (the live sklearn run the way compute_anchors.py runs it: global numpy RNG seeded with 42).
+def _sq_dists_1d(xc: np.ndarray, x: np.ndarray, xsq: np.ndarray) -> np.ndarray:
+    """sklearn.metrics.pairwise._euclidean_distances(X[cand], X, squared=True) for one feature: -2 x.y + |x|^2 + |y|^2, clipped."""
+    d = -2.0 * (xc[:, None] * x[None, :])
+    d += (xc * xc)[:, None]
+    d += xsq[None, :]
+    np.maximum(d, 0, out=d)
+    return d
+
+
+def kmeans_plusplus_init(x: np.ndarray, k: int, rng: np.random.RandomState) -> np.ndarray:
+    """sklearn _kmeans_plusplus (unit sample weights) on centred 1-D data x [n]; returns the k initial centres."""
+    n = x.shape[0]
+    xsq = x * x
+    w = np.ones(n)
+    n_local_trials = 2 + int(np.log(k))
+    centers = np.empty(k)
+    cid = rng.choice(n, p=w / w.sum())
+    centers[0] = x[cid]
+    closest = _sq_dists_1d(centers[:1], x, xsq)
+    pot = closest @ w
+    for c in range(1, k):
+        rand_vals = rng.uniform(size=n_local_trials) * pot
+        cand = np.searchsorted(np.cumsum(w * closest), rand_vals)
+        np.clip(cand, None, closest.size - 1, out=cand)
+        d = _sq_dists_1d(x[cand], x, xsq)
+        np.minimum(closest, d, out=d)
+        cpot = d @ w.reshape(-1, 1)
+        best = int(np.argmin(cpot))
+        pot = cpot[best]
+        closest = d[best]
+        centers[c] = x[cand[best]]
+    return centers
+
+
+def kmeans_lloyd_1d(x: np.ndarray, centers_init: np.ndarray, max_iter: int, tol_abs: float):
+    """sklearn _kmeans_single_lloyd on centred 1-D data: returns (labels, inertia, centres, n_iter)."""
+    k = centers_init.shape[0]
+    centers = centers_init.astype(np.float64).copy()
+    labels_old = np.full(x.shape[0], -1, np.int64)
+    strict = False
+    it = 0
+
+    def e_step(c):
+        return np.argmin((c * c)[None, :] - 2.0 * (x[:, None] * c[None, :]), axis=1)     # first minimum wins ties
+
+    for it in range(max_iter):
+        labels = e_step(centers)
+        sums = np.bincount(labels, weights=x, minlength=k)
+        cnt = np.bincount(labels, minlength=k).astype(np.float64)
+        empty = np.where(cnt == 0)[0]
+        if empty.size:                               # _relocate_empty_clusters_dense: farthest points become the new centres
+            dist = (x - centers[labels]) ** 2
+            far = np.argpartition(dist, -empty.size)[:-empty.size - 1:-1]
+            for e, f in zip(empty, far):
+                sums[labels[f]] -= x[f]
+                cnt[labels[f]] -= 1
+                sums[e] = x[f]
+                cnt[e] = 1
+        new = sums / cnt
+        shift_tot = float(((new - centers) ** 2).sum())
+        centers = new
+        if np.array_equal(labels, labels_old):
+            strict = True
+            break
+        if shift_tot <= tol_abs:
+            break
+        labels_old = labels
+    if not strict:
+        labels = e_step(centers)
+    inertia = float(((x - centers[labels]) ** 2).sum())
+    return labels, inertia, centers, it + 1
+
+
+def compute_anchors(durations: Sequence[float], n_clusters: int = 9, init: str = "k-means++", n_init="auto", max_iter: int = 500,
+                    tol: float = 1e-10, rng: Optional[np.random.RandomState] = None):
+    """compute_anchors.py:72-86: KMeans(9, init, n_init, tol, max_iter).fit(durations) -> sorted centres -> (sm, md, lg)."""
+    rng = rng if rng is not None else np.random.mtrand._rand
+    X = np.asarray(durations, np.float64).reshape(-1)
+    tol_abs = float(np.var(X)) * tol
+    mean = X.mean()
+    x = X - mean
+    if n_init == "auto":
+        n_init = 1 if init == "k-means++" else 10
+    best = None
+    for _ in range(int(n_init)):
+        if init == "k-means++":
+            c0 = kmeans_plusplus_init(x, n_clusters, rng)
+        else:
+            c0 = x[rng.choice(x.shape[0], size=n_clusters, replace=False, p=np.ones(x.shape[0]) / x.shape[0])]
+        labels, inertia, centers, n_iter = kmeans_lloyd_1d(x, c0, max_iter, tol_abs)
+        if best is None or inertia < best[1]:
+            best = (labels, inertia, centers, n_iter)
+    a = np.sort(best[2] + mean)
+    return a[:3], a[3:6], a[6:], best

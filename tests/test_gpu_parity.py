@@ -513,3 +513,69 @@ def test_evaluate_waveform_vs_live_reference(models, gold, cuda_dev):
     assert seg16.shape == seg.shape and torch.equal(bidx16, bidx)        # 16-bit quantisation does not move a keep decision here
     with pytest.raises(NotImplementedError):
         yad_b200.evaluate_waveform(m, wav, 16000, 60, 2, {0: "speech", 1: "music"})
+
+
+# ------------------------------------------------------------------ other config-selectable backbones
+@pytest.mark.parametrize("variant", ["bottleneck", "custom"])
+@pytest.mark.parametrize("form", ["train", "deploy"])
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_other_backbones_vs_golden(variant_state_dict, gold, variant, form, dt, cuda_dev):
+    """``resnet_config.block: Bottleneck`` and ``backbone: custom`` (3x7 ExtractorLayers, 2-D neck with H = 32) against the
+    LIVE reference's eval() outputs (tests/golden/backbones.npz).  fp32 mode: the tolerance of the default net (5e-3);
+    bf16 mode: the default net's stated bf16 tolerance."""
+    g = gold("backbones")
+    sd, cfg = variant_state_dict(variant)
+    m = yad_b200.AudioDetectionNetwork(2, config=cfg, compute_dtype=dt)
+    m.load_state_dict(sd)
+    if form == "deploy":
+        m.inference()
+    m = m.eval().to(cuda_dev)
+    x = synth.synth_clips(2, 22050 * 6, seed=3000, silence_tail_every=0).to(cuda_dev)
+    taps = {}
+    out = m(x, combine_scales=True, taps=taps).cpu().numpy()
+    ref = g[f"{variant}.preds_{form}"]
+    assert out.shape == ref.shape == (2, 63, 5)
+    if dt == "f32":
+        np.testing.assert_allclose(out, ref, atol=5e-3)
+        if form == "train":
+            np.testing.assert_allclose(taps["fmaps"][0][:, ::8, ::4, ::2].cpu().numpy(), g[f"{variant}.fmap1_s"], atol=2e-3)
+            np.testing.assert_allclose(taps["fmaps"][3][:, ::8, ::4, :].cpu().numpy(), g[f"{variant}.fmap4_s"], atol=2e-3)
+            for i, h in enumerate(taps["heads"]):
+                np.testing.assert_allclose(h.cpu().numpy(), g[f"{variant}.head{i}"], atol=5e-3)
+    else:
+        d = np.abs(out - ref)
+        assert d[..., :3].max() < 0.15 and d[..., :3].mean() < 0.02, (d[..., :3].max(), d[..., :3].mean())
+        assert d[..., 3].max() < 0.1, d[..., 3].max()
+        assert d[..., 4].max() < 1.5 and d[..., 4].mean() < 0.15, (d[..., 4].max(), d[..., 4].mean())
+    sm, md, lg = m(x)
+    assert sm.shape == (2, 12, 3, 5) and md.shape == (2, 6, 3, 5) and lg.shape == (2, 3, 3, 5)
+
+
+# ------------------------------------------------------------------ anchor clustering (SURVEY 8(f) N4)
+@pytest.mark.parametrize("name,init", [("a", "k-means++"), ("b", "k-means++"), ("c", "random")])
+def test_kmeans_anchors_gpu(gold, name, init, cuda_dev):
+    """yad_kmeans1d_lloyd vs the live sklearn run of compute_anchors.py (fixture) and the oracle: identical labels and
+    iteration counts, centres to 1e-11 relative (fp64, different summation order)."""
+    g = gold("anchors")
+    d = g[f"{name}.durations"]
+    sm, md, lg = yad_b200.compute_anchors(d, init=init, random_state=np.random.RandomState(42), device=cuda_dev)
+    np.testing.assert_allclose(np.concatenate([sm, md, lg]), g[f"{name}.anchors"], rtol=1e-11)
+    x = torch.from_numpy(d - d.mean()).to(cuda_dev)
+    r = yad_b200.kmeans_lloyd(x, g[f"{name}.lloyd_init"] - d.mean(), 500, float(np.var(d)) * 1e-10)
+    np.testing.assert_allclose(r["centers"] + d.mean(), g[f"{name}.lloyd_centers"], rtol=1e-11)
+    np.testing.assert_array_equal(r["labels"].cpu().numpy(), g[f"{name}.lloyd_labels"])
+    assert r["n_iter"] == int(g[f"{name}.lloyd_n_iter"])
+    ol, oi, oc, on = O.kmeans_lloyd_1d(d - d.mean(), g[f"{name}.lloyd_init"] - d.mean(), 500, float(np.var(d)) * 1e-10)
+    np.testing.assert_allclose(r["inertia"], oi, rtol=1e-11)
+
+
+def test_kmeans_empty_cluster_gpu(cuda_dev):
+    x = np.concatenate([np.linspace(-5, -4, 20), np.linspace(4, 5, 20), [30.0]])
+    x = x - x.mean()
+    c0 = np.array([x.min(), x.min() + 0.5, 1e3])
+    r = yad_b200.kmeans_lloyd(torch.from_numpy(x).to(cuda_dev), c0, 100, 0.0)
+    ol, oi, oc, on = O.kmeans_lloyd_1d(x, c0, 100, 0.0)
+    np.testing.assert_allclose(np.sort(r["centers"]), np.sort(oc), rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(r["labels"].cpu().numpy(), ol)
+    with pytest.raises(yad_b200.YadError):
+        yad_b200.kmeans_lloyd(torch.zeros(4, dtype=torch.float64, device=cuda_dev), np.zeros(17), 10, 0.0)

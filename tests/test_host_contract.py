@@ -78,7 +78,9 @@ def test_config_surface(model):
     assert m2.out_channels == 3 * 6
     with pytest.raises(ValueError):
         yad_b200.AudioDetectionNetwork(2, config=7)
-    bad = copy.deepcopy(cfg); bad["backbone"] = "custom"
+    other = copy.deepcopy(cfg); other["backbone"] = "custom"
+    assert yad_b200.AudioDetectionNetwork(2, config=other).feature_extractor.fmap4_ch == 1024
+    bad = copy.deepcopy(cfg); bad["mfcc_config"]["n_mfcc"] = 20
     with pytest.raises(NotImplementedError):
         yad_b200.AudioDetectionNetwork(2, config=bad)      # unsupported options fail loudly
 

@@ -247,3 +247,31 @@ def test_other_backbones_short_clips(gold, variant_state_dict, variant, form):
         np.testing.assert_allclose(taps["fmaps"][3][:, ::8, ::4, :].numpy(), g[f"{variant}.fmap4_s"], atol=2e-3)
         for i, h in enumerate(taps["heads"]):
             np.testing.assert_allclose(h.numpy(), g[f"{variant}.head{i}"], atol=5e-3)
+
+
+# ---------------------------------------------------------------- anchor clustering
+@pytest.mark.parametrize("name,init", [("a", "k-means++"), ("b", "k-means++"), ("c", "random")])
+def test_kmeans_anchors_vs_live_sklearn(gold, name, init):
+    """compute_anchors.py's KMeans run (numpy RNG seeded with 42): same seeding, same number of Lloyd iterations, centres to
+    1e-12 relative (sklearn sums chunk-wise in parallel, the restatement in one pass)."""
+    g = gold("anchors")
+    d = g[f"{name}.durations"]
+    sm, md, lg, best = O.compute_anchors(d, init=init, rng=np.random.RandomState(42))
+    np.testing.assert_allclose(np.concatenate([sm, md, lg]), g[f"{name}.anchors"], rtol=1e-12)
+    assert best[3] == int(g[f"{name}.n_iter"])
+    np.testing.assert_allclose(best[1], float(g[f"{name}.inertia"]), rtol=1e-12)
+    labels, _, c, n_iter = O.kmeans_lloyd_1d(d - d.mean(), g[f"{name}.lloyd_init"] - d.mean(), 500, float(np.var(d)) * 1e-10)
+    np.testing.assert_allclose(c + d.mean(), g[f"{name}.lloyd_centers"], rtol=1e-12)
+    np.testing.assert_array_equal(labels, g[f"{name}.lloyd_labels"])
+    assert n_iter == int(g[f"{name}.lloyd_n_iter"])
+
+
+def test_kmeans_empty_cluster_relocation():
+    """A start with a centre nobody is closest to: the cluster is re-seeded with the farthest point (sklearn semantics)."""
+    x = np.concatenate([np.linspace(-5, -4, 20), np.linspace(4, 5, 20), [30.0]])
+    x = x - x.mean()
+    labels, inertia, c, n_iter = O.kmeans_lloyd_1d(x, np.array([x.min(), x.min() + 0.5, 1e3]), 100, 0.0)
+    assert len(set(labels.tolist())) == 3 and np.isfinite(c).all()
+    from sklearn.cluster import KMeans
+    km = KMeans(3, init=np.array([[x.min()], [x.min() + 0.5], [1e3]]), n_init=1, tol=0.0, max_iter=100).fit(x.reshape(-1, 1))
+    np.testing.assert_allclose(np.sort(c), np.sort(km.cluster_centers_.reshape(-1) ), rtol=1e-12, atol=1e-12)

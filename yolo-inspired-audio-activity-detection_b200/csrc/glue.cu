@@ -127,6 +127,35 @@ __global__ void repvgg_merge_kernel(const T* __restrict__ a, const T* __restrict
   st_from_float(out + px * ld_out + co_off + c, apply_act(v, act));
 }
 
+// max over the rows h - r .. h + r of one column (clipped to the image: max_pool2d pads with -inf).  Second half of the 2-D
+// SPPF pools when the neck keeps its height (backbone: custom): k cascaded 5x5 / stride-1 max pools = a (4k+1) x (4k+1) box
+// max = this (r = 2k) applied to the k-fold W cascade that yad_sppf_pools writes (max is separable and the cascades commute).
+template <typename T>
+__global__ void maxpool_h_kernel(const T* __restrict__ in, int64_t B, int H, int W, int C, int ld_in, int ci_off, int r,
+                                 T* __restrict__ out, int ld_out, int co_off) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * H * W * C) return;
+  const int c = (int)(gid % C);
+  int64_t px = gid / C;
+  const int w = (int)(px % W);
+  px /= W;
+  const int h = (int)(px % H);
+  const int64_t b = px / H;
+  float m = -INFINITY;
+  for (int y = max(h - r, 0); y <= min(h + r, H - 1); ++y)
+    m = fmaxf(m, ld_as_float(in + ((b * H + y) * W + w) * (int64_t)ld_in + ci_off + c));
+  st_from_float(out + ((b * H + h) * W + w) * (int64_t)ld_out + co_off + c, m);
+}
+
+// x_spectral NCHW f32 -> NHWC (dtype) with channel pitch ld_out: input layout of the custom backbone's first conv
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int64_t B, int C, int64_t HW, T* __restrict__ out, int ld_out) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * HW) return;
+  const int64_t b = gid / HW, px = gid - b * HW;
+  for (int c = 0; c < C; ++c) st_from_float(out + gid * ld_out + c, in[(b * C + c) * HW + px]);
+}
+
 }  // namespace yad
 
 #define YAD_DISPATCH_DTYPE(dtype, KERNEL, ...)                                              \
@@ -190,6 +219,33 @@ int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t 
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   YAD_DISPATCH_DTYPE(dtype, yad::sppf_kernel, (const T*)in, B, W, C, ld_in, ci_off, (T*)out, ld_out, co_off);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_maxpool_h(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, int32_t C, int32_t ld_in, int32_t ci_off,
+                  int32_t radius, void* out, int32_t ld_out, int32_t co_off, yad_stream_t stream) {
+  YAD_CHECK_ARG(in && out && in != out && H >= 1 && W >= 1 && C >= 1 && radius >= 0 && ld_in >= ci_off + C && ld_out >= co_off + C,
+                "yad_maxpool_h: bad arguments (out of place only)");
+  YAD_CHECK_ARG(dtype == YAD_F32 || dtype == YAD_BF16, "yad_maxpool_h: bad dtype %d", dtype);
+  const int64_t n = B * H * W * C;
+  if (n == 0) return YAD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  YAD_DISPATCH_DTYPE(dtype, yad::maxpool_h_kernel, (const T*)in, B, H, W, C, ld_in, ci_off, radius, (T*)out, ld_out, co_off);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+int yad_nchw_to_nhwc(const float* in, int64_t B, int32_t C, int32_t H, int32_t W, void* out, int32_t out_dtype, int32_t ld_out,
+                     yad_stream_t stream) {
+  YAD_CHECK_ARG(in && out && C >= 1 && H >= 1 && W >= 1 && ld_out >= C, "yad_nchw_to_nhwc: bad arguments");
+  YAD_CHECK_ARG(out_dtype == YAD_F32 || out_dtype == YAD_BF16, "yad_nchw_to_nhwc: bad dtype %d", out_dtype);
+  const int64_t n = B * (int64_t)H * W;
+  if (n == 0) return YAD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  YAD_DISPATCH_DTYPE(out_dtype, yad::nchw_to_nhwc_kernel, in, B, C, (int64_t)H * W, (T*)out, ld_out);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }

@@ -44,15 +44,17 @@ def _fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: nn.BatchNorm2d) -> 
 class _Conv:
     """One packed convolution (weights folded, both kernel layouts prepared lazily for the engine dtype)."""
 
-    def __init__(self, name, w, b, stride, pad, act, dev, dtype):
+    def __init__(self, name, w, b, stride, pad, act, dev, dtype, simt: bool = False):
         self.name = name
+        self.simt = simt or dtype != BF16   # CUDA-core kernel ([kh][kw][Cin][Cout] weights): fp32 mode, or a bf16 conv whose
+                                            # Cin is tiny (the 2-channel first conv of the custom backbone)
         self.cout, self.cin, self.kh, self.kw = w.shape
         self.sh, self.sw = (stride, stride) if isinstance(stride, int) else tuple(stride)
         self.ph, self.pw = (pad, pad) if isinstance(pad, int) else tuple(pad)
         self.act = act
         w = w.detach().to(dev, torch.float32)
         self.bias = b.detach().to(dev, torch.float32).contiguous()
-        if dtype == BF16:
+        if dtype == BF16 and not simt:
             self.cin_pad = _ceil(self.cin, 64)
             self.cout_pad = _ceil(self.cout, 16)
             wt = torch.zeros(self.cout_pad, self.kh, self.kw, self.cin_pad, device=dev, dtype=torch.float32)
@@ -67,6 +69,8 @@ class _Conv:
             self.cin_pad = self.cin
             self.cout_pad = self.cout
             self.w = w.permute(2, 3, 1, 0).contiguous()     # [kh, kw, Cin, Cout]
+            if dtype == BF16:
+                self.w = self.w.to(torch.bfloat16)
 
 
 class InferenceEngine:
@@ -132,8 +136,37 @@ class InferenceEngine:
             out["id_shift"] = (bn.bias - bn.running_mean * s).detach().to(self.dev, torch.float32).contiguous()
         return out
 
+    def _pack_custom(self, fe):
+        """CustomBackBone (modules/_backbone.py:82-116): first_conv + 5 ExtractorBlocks of ExtractorLayers (:8-46)."""
+        dev = self.dev
+        w, b = _fold_bn(fe.first_conv[0].weight, fe.first_conv[0].bias, fe.first_conv[1])
+        self.first_conv = _Conv("fe.first_conv", w, b, 1, 3, ACT_LRELU, dev, self.dtype, simt=True)
+        self.cblocks = []
+        for bn_ in ("entry_block", "block1", "block2", "block3", "block4"):
+            layers = []
+            for ln, lay in getattr(fe, bn_).module_dict.items():
+                ca, bna, cb, bnb = lay._layer[0], lay._layer[1], lay._layer[3], lay._layer[4]
+                wa, ba = _fold_bn(ca.weight, ca.bias, bna)
+                wb, bb = _fold_bn(cb.weight, cb.bias, bnb)
+                r = lay._res_layer
+                layers.append({
+                    "a": _Conv(f"{bn_}.{ln}.a", wa, ba, ca.stride, ca.padding, ACT_LRELU, dev, self.dtype),
+                    "b": _Conv(f"{bn_}.{ln}.b", wb, bb, cb.stride, cb.padding, ACT_NONE, dev, self.dtype),
+                    "r": _Conv(f"{bn_}.{ln}.res", r.weight, r.bias, r.stride, r.padding, ACT_NONE, dev, self.dtype),
+                })
+            self.cblocks.append(layers)
+
     def _pack_cnn(self, model):
         fe, ms = model.feature_extractor, model.multiscale_module
+        dev = self.dev
+        self.bb_kind = "custom" if hasattr(fe, "first_conv") else ("bottleneck" if fe.block_name == "Bottleneck" else "basic")
+        if self.bb_kind == "custom":
+            self._pack_custom(fe)
+        else:
+            self._pack_resnet(fe)
+        self._pack_neck(ms)
+
+    def _pack_resnet(self, fe):
         dev = self.dev
         # stem conv1: raw (no BN / bias / activation before conv2, modules/_backbone.py:143-144); [7][7][2][64] f32
         self.stem_w = fe.conv1.weight.detach().to(dev, torch.float32).permute(2, 3, 1, 0).contiguous()
@@ -144,7 +177,7 @@ class InferenceEngine:
             self.stem_w_tc = wk.reshape(8, 8, 14, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
         w2, b2 = _fold_bn(fe.conv2.weight, None, fe.bn1)
         self.conv2 = _Conv("fe.conv2", w2, b2, 2, 3, ACT_RELU, dev, self.dtype)
-        if self.dtype == BF16:
+        if self.dtype == BF16 and self.bb_kind == "basic":
             # conv2 over the space-to-depth stem output: tap (kh, kw) reads parity plane ((kh-3)&1, (kw-3)&1) shifted by
             # (floor((kh-3)/2), floor((kw-3)/2)); steps grouped by plane
             steps = []
@@ -159,6 +192,20 @@ class InferenceEngine:
         for li in range(1, 5):
             blocks = []
             for bi, blk in enumerate(getattr(fe, f"layer{li}")):
+                if hasattr(blk, "conv3"):      # torchvision Bottleneck ([tv] models/resnet.py:143-163): the 3x3 carries the stride
+                    w1, b1 = _fold_bn(blk.conv1.weight, None, blk.bn1)
+                    w2, b2_ = _fold_bn(blk.conv2.weight, None, blk.bn2)
+                    w3, b3 = _fold_bn(blk.conv3.weight, None, blk.bn3)
+                    ent = {
+                        "c1": _Conv(f"l{li}.{bi}.conv1", w1, b1, 1, 0, ACT_RELU, dev, self.dtype),
+                        "c2": _Conv(f"l{li}.{bi}.conv2", w2, b2_, blk.stride, 1, ACT_RELU, dev, self.dtype),
+                        "c3": _Conv(f"l{li}.{bi}.conv3", w3, b3, 1, 0, ACT_RELU, dev, self.dtype),   # relu after the residual add
+                    }
+                    if blk.downsample is not None:
+                        wd, bd = _fold_bn(blk.downsample[0].weight, None, blk.downsample[1])
+                        ent["ds"] = _Conv(f"l{li}.{bi}.ds", wd, bd, blk.stride, 0, ACT_NONE, dev, self.dtype)
+                    blocks.append(ent)
+                    continue
                 w1, b1 = _fold_bn(blk.conv1.weight, None, blk.bn1)
                 wB, bB = _fold_bn(blk.conv2.weight, None, blk.bn2)
                 ent = {
@@ -170,6 +217,8 @@ class InferenceEngine:
                     ent["ds"] = _Conv(f"l{li}.{bi}.ds", wd, bd, blk.stride, 0, ACT_NONE, dev, self.dtype)
                 blocks.append(ent)
             self.stages.append(blocks)
+
+    def _pack_neck(self, ms):
         sp = ms.cspsppf
         self.n = {
             "sp1": self._cbl("sp.c1", sp.conv_1_3_4[0]), "sp3": self._cbl("sp.c3", sp.conv_1_3_4[1]),
@@ -229,15 +278,16 @@ class InferenceEngine:
         Wo = (W + 2 * cv.pw - cv.kw) // cv.sw + 1
         assert out.shape[0] == B and out.shape[1] == Ho and out.shape[2] == Wo, (cv.name, tuple(out.shape), (B, Ho, Wo))
         in_ptr = x.data_ptr() + cin_off * es
-        if self.dtype == BF16:
+        if self.dtype == BF16 and not cv.simt:
             assert cin_off + cv.cin_pad <= ld_in, (cv.name, cin_off, cv.cin_pad, ld_in)
             rc = self.lib.yad_conv_tc(C.byref(d), in_ptr, cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), _lib.ptr(res),
                                       out.data_ptr(), BF16, _lib.ptr(out2), 0 if out2 is None else out2.shape[3], self._stream())
         else:
-            rc = self.lib.yad_conv_simt(C.byref(d), F32, in_ptr, cv.w.data_ptr(), cv.cout, cv.bias.data_ptr(), _lib.ptr(res),
+            d.Cin = cv.cin
+            rc = self.lib.yad_conv_simt(C.byref(d), self.dtype, in_ptr, cv.w.data_ptr(), cv.cout, cv.bias.data_ptr(), _lib.ptr(res),
                                         out.data_ptr(), self._stream())
             if out2 is not None:
-                raise AssertionError("out2 is only used on the bf16 path")
+                raise AssertionError("out2 is only used on the tensor-core path")
         _lib.check(rc, f"conv {cv.name}")
 
     # ---- flat (halo-padded, h-fastest) layout of the bf16 backbone: tensor [B, Wp, Hp, ld], see include/yad_b200.h
@@ -343,7 +393,12 @@ class InferenceEngine:
         H1, W1 = (H0 - 1) // 2 + 1, (T - 1) // 2 + 1          # conv1 output
         H, W = (H1 + 6 - 7) // 2 + 1, (W1 + 6 - 7) // 2 + 1     # conv2 output
         fmaps, geoms = [], []
-        if bf:
+        fast = bf and self.bb_kind == "basic"      # flat-layout tcgen05 path of the default net
+        if self.bb_kind == "custom":
+            fmaps, geoms = self._run_custom_backbone(xs, plan)
+            if taps is not None:
+                taps["fmaps"] = [f.float().permute(0, 3, 1, 2).contiguous() for f in fmaps]
+        elif fast:
             # conv1 writes the space-to-depth flat layout [B, W2+2, H2+2, 4 parity planes x 64]; conv2 (7x7 stride 2) then is a
             # stride-1 flat conv with 49 (plane, shift) steps; backbone activations stay in the flat layout (conv_flat.cu)
             H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
@@ -385,12 +440,34 @@ class InferenceEngine:
             if taps is not None:
                 taps["fmaps"] = [f[:, :w_, :h_, :].float().permute(0, 3, 2, 1).contiguous() for f, (h_, w_) in zip(fmaps, geoms)]
         else:
+            # dense NHWC path: fp32 parity mode, and the Bottleneck ResNet in bf16 (generic tap-by-tap tcgen05 convs)
             c1 = self._buf(plan, "c1", B, H1, W1, 64)
-            _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()), "conv_stem")
+            if bf:
+                _lib.check(self.lib.yad_conv_stem_tc(xs.data_ptr(), B, H0, T, self.stem_w_tc.data_ptr(), c1.data_ptr(), 0, 0, s()),
+                           "conv_stem_tc (dense)")
+            else:
+                _lib.check(self.lib.yad_conv_stem(xs.data_ptr(), B, H0, T, self.stem_w.data_ptr(), c1.data_ptr(), self.dtype, s()),
+                           "conv_stem")
             cur = self._buf(plan, "c2", B, H, W, 64)
             self._conv(self.conv2, c1, 0, cur, 0)
             for li, blocks in enumerate(self.stages):
                 for bi, blk in enumerate(blocks):
+                    if "c3" in blk:       # Bottleneck: 1x1 - 3x3 (stride) - 1x1 (+ identity / downsample) - ReLU
+                        st = blk["c2"].sh
+                        Ho, Wo = (H + 2 - 3) // st + 1, (W + 2 - 3) // st + 1
+                        t1 = self._buf(plan, f"s{li}.{bi}.t1", B, H, W, blk["c1"].cout)
+                        t2 = self._buf(plan, f"s{li}.{bi}.t2", B, Ho, Wo, blk["c2"].cout)
+                        y = self._buf(plan, f"s{li}.{bi}.y", B, Ho, Wo, blk["c3"].cout)
+                        self._conv(blk["c1"], cur, 0, t1, 0)
+                        self._conv(blk["c2"], t1, 0, t2, 0)
+                        if "ds" in blk:
+                            idt = self._buf(plan, f"s{li}.{bi}.d", B, Ho, Wo, blk["c3"].cout)
+                            self._conv(blk["ds"], cur, 0, idt, 0)
+                        else:
+                            idt = cur
+                        self._conv(blk["c3"], t2, 0, y, 0, res=idt)
+                        cur, H, W = y, Ho, Wo
+                        continue
                     c1v, c2v = blk["c1"], blk["c2"]
                     Ho, Wo = (H + 2 - 3) // c1v.sh + 1, (W + 2 - 3) // c1v.sw + 1
                     ld = c1v.cout
@@ -411,16 +488,20 @@ class InferenceEngine:
 
         # ---- neck (H = 1 after the H-mean; modules/_common.py:241-265)
         hs = [g_[0] for g_ in geoms]
-        if not (hs[0] != hs[1] != hs[2] != hs[3]):
-            raise NotImplementedError("neck with equal feature-map heights (2-D neck) is not built")
+        # the reference's chained comparison (modules/_common.py:248): the H-mean runs only when it is true; otherwise (equal
+        # heights, i.e. the custom backbone) the neck stays 2-D and the heads are averaged over H at the very end (:259-261)
+        pool_first = hs[0] != hs[1] != hs[2] != hs[3]
+        if not pool_first and len(set(hs)) != 1:
+            raise NotImplementedError(f"feature-map heights {hs}: the reference's neck would fail on these shapes as well")
+        Hn = 1 if pool_first else hs[0]
         pooled = []
         for i, (f, (Hf, Wf)) in enumerate(zip(fmaps, geoms)):
             ldf = f.shape[3]
-            if Hf == 1 and not bf:
+            if not pool_first or (Hf == 1 and not fast):
                 pooled.append(f)
                 continue
             pm = self._buf(plan, f"fm{i}", B, 1, Wf, ldf)
-            if bf:
+            if fast:
                 Hpf, Wpf = self._flat_geom(Hf, Wf)
                 isw, ish, isb = Hpf, 1, Wpf * Hpf
             else:
@@ -431,49 +512,57 @@ class InferenceEngine:
         W1, W2, W3, W4 = f1m.shape[2], f2m.shape[2], f3m.shape[2], f4m.shape[2]
         n = self.n
         # CSPSPPF -> p4, written straight into cat_n4[:, 0:128]
-        a1 = self._buf(plan, "sp.a1", B, 1, W4, 64)
-        a2 = self._buf(plan, "sp.a2", B, 1, W4, 64)
-        cat5 = self._buf(plan, "sp.cat5", B, 1, W4, 256)
-        cat7 = self._buf(plan, "sp.cat7", B, 1, W4, 128)
-        c5 = self._buf(plan, "sp.c5", B, 1, W4, 64)
-        cat_n4 = self._buf(plan, "cat_n4", B, 1, W4, 256)
+        a1 = self._buf(plan, "sp.a1", B, Hn, W4, 64)
+        a2 = self._buf(plan, "sp.a2", B, Hn, W4, 64)
+        cat5 = self._buf(plan, "sp.cat5", B, Hn, W4, 256)
+        cat7 = self._buf(plan, "sp.cat7", B, Hn, W4, 128)
+        c5 = self._buf(plan, "sp.c5", B, Hn, W4, 64)
+        cat_n4 = self._buf(plan, "cat_n4", B, Hn, W4, 256)
         self._conv(n["sp1"], f4m, 0, a1, 0)
         self._conv(n["sp3"], a1, 0, a2, 0)
         self._conv(n["sp4"], a2, 0, cat5, 0)
         self._conv(n["sp2"], f4m, 0, cat7, 64)
-        _lib.check(self.lib.yad_sppf_pools(cat5.data_ptr(), self.dtype, B, W4, 64, 256, 0, cat5.data_ptr(), 256, 64, s()), "sppf")
+        if Hn == 1:
+            _lib.check(self.lib.yad_sppf_pools(cat5.data_ptr(), self.dtype, B, W4, 64, 256, 0, cat5.data_ptr(), 256, 64, s()), "sppf")
+        else:
+            # 2-D 5x5 cascades = W cascades (into a scratch tensor) followed by box maxima over 5 / 9 / 13 rows
+            wp = self._buf(plan, "sp.wpool", B, Hn, W4, 192)
+            _lib.check(self.lib.yad_sppf_pools(cat5.data_ptr(), self.dtype, B * Hn, W4, 64, 256, 0, wp.data_ptr(), 192, 0, s()), "sppf(W)")
+            for k_ in range(3):
+                _lib.check(self.lib.yad_maxpool_h(wp.data_ptr(), self.dtype, B, Hn, W4, 64, 192, 64 * k_, 2 * (k_ + 1),
+                                                  cat5.data_ptr(), 256, 64 * (k_ + 1), s()), "sppf(H)")
         self._conv(n["sp5"], cat5, 0, c5, 0)
         self._conv(n["sp6"], c5, 0, cat7, 0)
         self._conv(n["sp7"], cat7, 0, cat_n4, 0)                       # p4
         # BiC3 -> RepBlock3_1 -> p3, written into cat_n3[:, 0:128]
-        cat_b3 = self._buf(plan, "cat_b3", B, 1, W3, 256)
-        c0_3 = self._buf(plan, "b3.c0", B, 1, W2, 64)
-        b3 = self._buf(plan, "b3", B, 1, W3, 128)
-        cat_n3 = self._buf(plan, "cat_n3", B, 1, W3, 256)
+        cat_b3 = self._buf(plan, "cat_b3", B, Hn, W3, 256)
+        c0_3 = self._buf(plan, "b3.c0", B, Hn, W2, 64)
+        b3 = self._buf(plan, "b3", B, Hn, W3, 128)
+        cat_n3 = self._buf(plan, "cat_n3", B, Hn, W3, 256)
         self._conv(n["b3c1"], f3m, 0, cat_b3, 0)
         self._conv(n["b3c0"], f2m, 0, c0_3, 0)
-        _lib.check(self.lib.yad_resize_w(c0_3.data_ptr(), self.dtype, B, W2, 64, 64, 0, 0, cat_b3.data_ptr(), 256, 64, s()), "pairavg")
-        _lib.check(self.lib.yad_resize_w(cat_n4.data_ptr(), self.dtype, B, W4, 128, 256, 0, 1, cat_b3.data_ptr(), 256, 128, s()), "up2")
+        _lib.check(self.lib.yad_resize_w(c0_3.data_ptr(), self.dtype, B * Hn, W2, 64, 64, 0, 0, cat_b3.data_ptr(), 256, 64, s()), "pairavg")
+        _lib.check(self.lib.yad_resize_w(cat_n4.data_ptr(), self.dtype, B * Hn, W4, 128, 256, 0, 1, cat_b3.data_ptr(), 256, 128, s()), "up2")
         self._conv(n["b3o"], cat_b3, 0, b3, 0)
         self._repblock(plan, "rb31", self.rep["rep_block3_1"], b3, 0, cat_n3, 0)   # p3
         # BiC2 -> RepBlock2_1 -> n2 (sm head)
-        cat_b2 = self._buf(plan, "cat_b2", B, 1, W2, 256)
-        c0_2 = self._buf(plan, "b2.c0", B, 1, W1, 64)
-        b2 = self._buf(plan, "b2", B, 1, W2, 128)
+        cat_b2 = self._buf(plan, "cat_b2", B, Hn, W2, 256)
+        c0_2 = self._buf(plan, "b2.c0", B, Hn, W1, 64)
+        b2 = self._buf(plan, "b2", B, Hn, W2, 128)
         self._conv(n["b2c1"], f2m, 0, cat_b2, 0)
         self._conv(n["b2c0"], f1m, 0, c0_2, 0)
-        _lib.check(self.lib.yad_resize_w(c0_2.data_ptr(), self.dtype, B, W1, 64, 64, 0, 0, cat_b2.data_ptr(), 256, 64, s()), "pairavg")
-        _lib.check(self.lib.yad_resize_w(cat_n3.data_ptr(), self.dtype, B, W3, 128, 256, 0, 1, cat_b2.data_ptr(), 256, 128, s()), "up2")
+        _lib.check(self.lib.yad_resize_w(c0_2.data_ptr(), self.dtype, B * Hn, W1, 64, 64, 0, 0, cat_b2.data_ptr(), 256, 64, s()), "pairavg")
+        _lib.check(self.lib.yad_resize_w(cat_n3.data_ptr(), self.dtype, B * Hn, W3, 128, 256, 0, 1, cat_b2.data_ptr(), 256, 128, s()), "up2")
         self._conv(n["b2o"], cat_b2, 0, b2, 0)
         hl = _ceil(self.n_head, 64) if bf else self.n_head     # head channel pitch
         h32 = _ceil(self.n_head, 4)                            # fp32 head copies fed to the decoder
-        n2 = self._buf(plan, "n2", B, 1, W2, hl, zero=True)
-        n3 = self._buf(plan, "n3", B, 1, W3, hl, zero=True)
-        n4 = self._buf(plan, "n4", B, 1, W4, hl, zero=True)
+        n2 = self._buf(plan, "n2", B, Hn, W2, hl, zero=True)
+        n3 = self._buf(plan, "n3", B, Hn, W3, hl, zero=True)
+        n4 = self._buf(plan, "n4", B, Hn, W4, hl, zero=True)
         if bf:
-            n2f = self._buf(plan, "n2f", B, 1, W2, h32, zero=True, dtype=torch.float32)
-            n3f = self._buf(plan, "n3f", B, 1, W3, h32, zero=True, dtype=torch.float32)
-            n4f = self._buf(plan, "n4f", B, 1, W4, h32, zero=True, dtype=torch.float32)
+            n2f = self._buf(plan, "n2f", B, Hn, W2, h32, zero=True, dtype=torch.float32)
+            n3f = self._buf(plan, "n3f", B, Hn, W3, h32, zero=True, dtype=torch.float32)
+            n4f = self._buf(plan, "n4f", B, Hn, W4, h32, zero=True, dtype=torch.float32)
         else:
             n2f, n3f, n4f = None, None, None
         self._repblock(plan, "rb21", self.rep["rep_block2_1"], b2, 0, n2, 0, out2=n2f)
@@ -482,9 +571,45 @@ class InferenceEngine:
         self._conv(n["ds3"], n3, 0, cat_n4, 128)
         self._repblock(plan, "rb41", self.rep["rep_block4_1"], cat_n4, 0, n4, 0, out2=n4f)
         heads = [n2f, n3f, n4f] if bf else [n2, n3, n4]
+        if Hn > 1:     # adaptive_avg_pool2d of the three heads over H (modules/_common.py:259-261), fp32
+            pooled_heads = []
+            for i, h in enumerate(heads):
+                Wh, ldh = h.shape[2], h.shape[3]
+                ph = self._buf(plan, f"head_mean{i}", B, 1, Wh, ldh, dtype=torch.float32)
+                _lib.check(self.lib.yad_hmean(h.data_ptr(), F32, B, Hn, Wh, ldh, ldh, 1, Wh, Hn * Wh, ph.data_ptr(), ldh, 0, s()),
+                           "hmean(heads)")
+                pooled_heads.append(ph)
+            heads = pooled_heads
         if taps is not None:
             taps["heads"] = [h.reshape(B, h.shape[2], h.shape[3])[..., : self.n_head].float().clone() for h in heads]
         return heads
+
+    def _run_custom_backbone(self, xs: torch.Tensor, plan: dict):
+        """CustomBackBone.forward in eval mode (modules/_backbone.py:108-116), dense NHWC; every ExtractorLayer writes its two
+        branches into the channel slices of one buffer (the reference's torch.cat, :45)."""
+        B, Cx, H, W = xs.shape
+        s = self._stream
+        x0 = self._buf(plan, "cb.x", B, H, W, Cx)
+        _lib.check(self.lib.yad_nchw_to_nhwc(xs.data_ptr(), B, Cx, H, W, x0.data_ptr(), self.dtype, Cx, s()), "nchw_to_nhwc")
+        pitch = (lambda c: _ceil(c, 64)) if self.dtype == BF16 else (lambda c: c)
+        cur = self._buf(plan, "cb.first", B, H, W, pitch(64))
+        self._conv(self.first_conv, x0, 0, cur, 0)
+        fmaps, geoms = [], []
+        for bi, layers in enumerate(self.cblocks):
+            for li, lay in enumerate(layers):
+                ca, cb, cr = lay["a"], lay["b"], lay["r"]
+                Wo = (W + 2 * ca.pw - ca.kw) // ca.sw + 1
+                Ho = (H + 2 * cb.ph - cb.kh) // cb.sh + 1
+                t = self._buf(plan, f"cb{bi}.{li}.t", B, H, Wo, pitch(ca.cout), zero=True)
+                y = self._buf(plan, f"cb{bi}.{li}.y", B, Ho, Wo, pitch(cb.cout + cr.cout), zero=True)
+                self._conv(ca, cur, 0, t, 0)
+                self._conv(cb, t, 0, y, 0)
+                self._conv(cr, cur, 0, y, cb.cout)
+                cur, H, W = y, Ho, Wo
+            if bi >= 1:
+                fmaps.append(cur)
+                geoms.append((H, W))
+        return fmaps, geoms
 
     def run_decode(self, heads: List[torch.Tensor], B: int, T: int, L_res: int) -> torch.Tensor:
         G = [h.shape[2] for h in heads]
