@@ -579,3 +579,64 @@ def test_kmeans_empty_cluster_gpu(cuda_dev):
     np.testing.assert_array_equal(r["labels"].cpu().numpy(), ol)
     with pytest.raises(yad_b200.YadError):
         yad_b200.kmeans_lloyd(torch.zeros(4, dtype=torch.float64, device=cuda_dev), np.zeros(17), 10, 0.0)
+
+
+# ------------------------------------------------------------------ checkpoint plumbing (pipeline/_trainer.py:38-53)
+def test_checkpoint_roundtrip_with_torch_adam(tmp_path, cuda_dev):
+    """A checkpoint in the reference's layout ({"network_params", "optimizer_params"} with torch.optim.Adam's state dict) resumes
+    into FusedAdamEMA: the next fused step equals torch.optim.Adam's next step; and the other way round."""
+    g = torch.Generator().manual_seed(5)
+    w0 = [torch.randn(7, 5, generator=g), torch.randn(11, generator=g)]
+    grads = [[torch.randn(7, 5, generator=g), torch.randn(11, generator=g)] for _ in range(4)]
+    kw = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.002)
+    ref_p = [torch.nn.Parameter(w.clone()) for w in w0]
+    ref = torch.optim.Adam(ref_p, **kw)
+    for s in range(2):
+        for p, gr in zip(ref_p, grads[s]):
+            p.grad = gr.clone()
+        ref.step()
+    mid = {"network_params": {f"p{i}": p.data.clone() for i, p in enumerate(ref_p)}, "optimizer_params": ref.state_dict()}
+    torch.save(mid, tmp_path / "ck.pth.tar")
+    saved = torch.load(tmp_path / "ck.pth.tar", map_location=cuda_dev)
+    ps = [torch.nn.Parameter(saved["network_params"][f"p{i}"].clone()) for i in range(2)]
+    opt = yad_b200.FusedAdamEMA(ps, lr=9.0)            # hyper-parameters come from the checkpoint
+    opt.load_state_dict(saved["optimizer_params"])
+    assert opt.step_count == 2 and opt.lr == 1e-3 and opt.wd == 0.002
+    for s in (2, 3):
+        for p, q, gr in zip(ref_p, ps, grads[s]):
+            p.grad = gr.clone()
+            q.grad.copy_(gr.to(cuda_dev))
+        ref.step()
+        opt.step()
+    for p, q in zip(ref_p, ps):
+        np.testing.assert_allclose(q.data.cpu().numpy(), p.data.numpy(), atol=2e-6)
+    # and back: our state dict loads into torch.optim.Adam with the same moments
+    sd = opt.state_dict()
+    assert set(sd) == set(ref.state_dict()) and set(sd["param_groups"][0]) == set(ref.state_dict()["param_groups"][0])
+    back = torch.optim.Adam([torch.nn.Parameter(q.data.cpu().clone()) for q in ps], **kw)
+    back.load_state_dict({"state": {k: {kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} for k, v in sd["state"].items()},
+                          "param_groups": sd["param_groups"]})
+    for i in range(2):
+        np.testing.assert_allclose(back.state_dict()["state"][i]["exp_avg"].numpy(), ref.state_dict()["state"][i]["exp_avg"].numpy(), atol=1e-7)
+        assert float(back.state_dict()["state"][i]["step"]) == 4.0
+
+
+def test_save_load_checkpoint_model(tmp_path, models, cuda_dev):
+    m = models[("train", "f32")]
+    ps = [p for p in m.parameters()]
+    x = synth.synth_clips(1, 22050 * 6, seed=77, silence_tail_every=0).to(cuda_dev)
+    want = m(x, combine_scales=True).clone()
+
+    class _Opt:
+        def state_dict(self):
+            return {"state": {}, "param_groups": []}
+    path = str(tmp_path / "saved_model" / "AudioDetectionNetwork.pth.tar")
+    yad_b200.save_checkpoint(path, m, _Opt())
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"network_params", "optimizer_params"} and len(ck["network_params"]) == 357
+    m2 = yad_b200.AudioDetectionNetwork(2, compute_dtype="f32").eval().to(cuda_dev)
+    yad_b200.load_checkpoint(path, m2, device=cuda_dev)
+    np.testing.assert_array_equal(m2(x, combine_scales=True).cpu().numpy(), want.cpu().numpy())
+    with pytest.raises(OSError):
+        yad_b200.load_checkpoint(str(tmp_path / "nope.pth.tar"), m2)
+    assert len(ps) == 182

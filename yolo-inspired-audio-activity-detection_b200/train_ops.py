@@ -284,6 +284,71 @@ class FusedAdamEMA:
         _lib.param_epoch += 1        # the packed-weight caches of the engines key on this
 
 
+    # ---- checkpoint plumbing (pipeline/_trainer.py:38-53 stores optimizer.state_dict() under "optimizer_params")
+    def state_dict(self) -> dict:
+        """The layout of ``torch.optim.Adam.state_dict()`` (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``, one param group),
+        so checkpoints written here load into the reference's Adam and vice versa."""
+        state, o = {}, 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            if self.step_count > 0:
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[o:o + k].view_as(p.data).clone(),
+                            "exp_avg_sq": self.v[o:o + k].view_as(p.data).clone()}
+            o += k
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("FusedAdamEMA.load_state_dict: expected one param group covering every parameter")
+        g = groups[0]
+        if g.get("amsgrad") or g.get("maximize") or g.get("decoupled_weight_decay"):
+            raise NotImplementedError("FusedAdamEMA: amsgrad / maximize / decoupled weight decay are not built")
+        self.lr, self.betas, self.eps, self.wd = float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])
+        steps, o = set(), 0
+        self.m.zero_()
+        self.v.zero_()
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is not None:
+                self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+            o += k
+        if len(steps) > 1:
+            raise NotImplementedError("FusedAdamEMA: per-parameter step counts differ (one fused bias correction per step)")
+        self.step_count = steps.pop() if steps else 0
+
+
+def save_checkpoint(path: str, model, optimizer, ema_smoothener=None) -> None:
+    """TrainerPipeline.save_model (pipeline/_trainer.py:38-47): {"network_params", "optimizer_params"}; the EMA weights replace
+    the live ones when a smoothener is in use."""
+    import os
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    net = model.state_dict() if not ema_smoothener else ema_smoothener.get_ema_state_dict()
+    torch.save({"network_params": net, "optimizer_params": optimizer.state_dict()}, path)
+
+
+def load_checkpoint(path: str, model, device=None, optimizer=None):
+    """TrainerPipeline.load_model (pipeline/_trainer.py:49-53) / inference.py:29-31; optionally resumes the optimizer too."""
+    import os
+    if not os.path.exists(path):
+        raise OSError(f"model is yet to be saved in path: {path}")
+    saved = torch.load(path, map_location=device)
+    out = model.load_state_dict(saved["network_params"])
+    _lib.param_epoch += 1
+    if optimizer is not None and "optimizer_params" in saved:
+        optimizer.load_state_dict(saved["optimizer_params"])
+    return out
+
+
 class EMAParamsSmoothener:
     """Drop-in for smoothener/_ema.py:7-32 (parameters only; warm-up momentum) using one fused launch per
     update over flattened parameter arenas."""
