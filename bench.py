@@ -148,6 +148,14 @@ def time_stages(model, x, reps=3):
     out["frontend_ms"], xs = timed(lambda: eng.run_frontend(x, plan))
 
     def stem():
+        if getattr(eng, "fused_stem", False):      # conv1 o conv2 as one convolution (+ border-column fix-up)
+            cur = plan["c2"]
+            fx = plan["fstem_cols"]
+            _lib.check(eng.lib.yad_conv_stem_fused(xs.data_ptr(), B, 32, T, eng.fstem_w.data_ptr(), eng.fstem_bias.data_ptr(), cur.data_ptr(),
+                                                   cur.shape[2], cur.shape[1], int(os.environ.get("YAD_STEM_NINT", "0")), eng._stream()), "stem_fused")
+            _lib.check(eng.lib.yad_conv_stem_fused_fixup(xs.data_ptr(), B, 32, T, eng.fstem_wvar.data_ptr(), eng.fstem_bias.data_ptr(), fx[0],
+                                                         fx[1], fx[2], cur.data_ptr(), cur.shape[2], cur.shape[1], eng._stream()), "stem_fixup")
+            return
         c1 = plan["c1"]
         if eng.dtype == _lib.BF16:
             _lib.check(eng.lib.yad_conv_stem_tc(xs.data_ptr(), B, 32, T, eng.stem_w_tc.data_ptr(), c1.data_ptr(), c1.shape[2], c1.shape[1],

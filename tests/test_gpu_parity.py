@@ -640,3 +640,42 @@ def test_save_load_checkpoint_model(tmp_path, models, cuda_dev):
     with pytest.raises(OSError):
         yad_b200.load_checkpoint(str(tmp_path / "nope.pth.tar"), m2)
     assert len(ps) == 182
+
+
+# ------------------------------------------------------------------ fused stem: conv1 o conv2 as one 19x19 stride-4 convolution
+@pytest.mark.parametrize("B,T", [(2, 96), (1, 960), (3, 61), (2, 130)])
+def test_fused_stem_vs_two_convs(B, T, cuda_dev):
+    """yad_conv_stem_fused + fix-up against F.conv2d(F.conv2d(x, W1), W2 * bn) in fp32 on the bf16-rounded input (the kernel
+    rounds x and the composite weights to bf16, accumulates in fp32): every output pixel incl. the border rows / columns whose
+    conv2 taps leave conv1's output (zero padding of the intermediate tensor)."""
+    from yad_b200.engine import InferenceEngine
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    w1 = (torch.rand(64, 2, 7, 7, generator=g) * 2 - 1) * 0.17
+    w2 = (torch.rand(64, 64, 7, 7, generator=g) * 2 - 1) * 0.03
+    b2 = torch.randn(64, generator=g) * 0.2
+    x = torch.randn(B, 2, 32, T, generator=g)
+    eng = InferenceEngine.__new__(InferenceEngine)
+    eng.dev = cuda_dev
+    eng._pack_fused_stem(w1, w2, b2)
+    lib = _lib.init(0)
+    H1, W1 = 16, (T - 1) // 2 + 1
+    Ho, Wo = 8, (W1 - 1) // 2 + 1
+    Hp, Wp = Ho + 1, Wo + 1
+    out = torch.zeros(B, Wp, Hp, 64, device=cuda_dev, dtype=torch.bfloat16)
+    xd = x.to(cuda_dev)
+    _lib.check(lib.yad_conv_stem_fused(xd.data_ptr(), B, 32, T, eng.fstem_w.data_ptr(), eng.fstem_bias.data_ptr(), out.data_ptr(), Hp, Wp, 0,
+                                       _stream()), "fused")
+    cols, var = InferenceEngine._fused_stem_border_cols(T)
+    _lib.check(lib.yad_conv_stem_fused_fixup(xd.data_ptr(), B, 32, T, eng.fstem_wvar.data_ptr(), eng.fstem_bias.data_ptr(),
+                                             (C.c_int32 * len(cols))(*cols), (C.c_int32 * len(var))(*var), len(cols), out.data_ptr(), Hp, Wp,
+                                             _stream()), "fixup")
+    got = out[:, :Wo, :Ho, :].float().permute(0, 3, 2, 1).cpu()            # [B, 64, Ho, Wo]
+    xb = x.bfloat16().float()
+    ref = F.relu(F.conv2d(F.conv2d(xb.double(), w1.double(), None, 2, 3), w2.double(), b2.double(), 2, 3)).float()
+    assert got.shape == ref.shape
+    scale = ref.abs().max().item()
+    err = (got - ref).abs()
+    assert err.max().item() < 2e-2 * scale, (err.max().item(), scale)      # bf16 weights / output rounding
+    assert err.mean().item() < 2e-3 * scale
+    # the halo cells stay zero
+    assert out[:, Wo:, :, :].abs().max().item() == 0 and out[:, :, Ho:, :].abs().max().item() == 0

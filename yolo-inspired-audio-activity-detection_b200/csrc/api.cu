@@ -25,6 +25,7 @@ int init_conv_tc_attrs();   // conv_tc.cu
 int init_conv_flat_attrs(); // conv_flat.cu
 int init_frontend_attrs();  // frontend.cu
 int init_conv_stem_tc_attrs();  // conv_stem_tc.cu
+int init_conv_stem_fused_attrs();  // conv_stem_fused.cu
 int init_conv_tf32_attrs();  // conv_tf32.cu
 
 }  // namespace yad
@@ -63,6 +64,8 @@ int yad_init(int device) {
   rc = yad::init_conv_flat_attrs();
   if (rc) return rc;
   rc = yad::init_conv_stem_tc_attrs();
+  if (rc) return rc;
+  rc = yad::init_conv_stem_fused_attrs();
   if (rc) return rc;
   rc = yad::init_frontend_attrs();
   if (rc) return rc;

@@ -1,0 +1,291 @@
+// Stem conv1 o conv2 as ONE convolution on the tcgen05 tensor cores.
+//
+// The reference runs conv1 (2 -> 64, 7x7, stride 2, pad 3, no bias) and conv2 (64 -> 64, 7x7, stride 2, pad 3) back to back with
+// nothing in between (modules/_backbone.py:143-146: BatchNorm + ReLU come after conv2), i.e. two LINEAR maps.  Their composition
+// is a single 19x19 / stride-4 / pad-9 convolution 2 -> 64 with W12 = conv_transpose(W2, W1) (built in fp64 by the host): 722
+// taps per output pixel instead of 98 x 4 + 3136, and the 503 MB intermediate tensor (B = 512) is never written or read.
+// The only subtlety is the zero padding of the INTERMEDIATE tensor: conv2 taps that fall outside conv1's output are dropped by
+// the reference, so output rows 0, 1 and Ho-1 (and columns 0, 1 and the last one or two) need composite weights built from the
+// valid conv2 taps only.  Rows: the CTAs are split into four classes (interior rows 2..6 | row 0 | row 1 | row 7), each keeping
+// its own weight variant resident in shared memory.  Columns: this kernel uses the interior-column weights everywhere and
+// stem_fixup_kernel below recomputes the handful of border columns exactly (CUDA cores, < 2 % of the pixels).
+//
+// GEMM view per output row ho and 128 consecutive output pixels: D[128, 64] = sum over the kernel rows dh whose input row
+// hi = 4 ho - 9 + dh is inside the image of  A_dh[128, 48] * W_dh[64, 48]^T,  K index = dw * 2 + c (38 real + 10 zero-weight).
+// As in conv_stem_tc.cu the A operand is NOT an im2col copy: the patch lives in shared memory as channel-interleaved bf16 rows
+// (one 4-byte word per input pixel) and the no-swizzle K-major UMMA descriptor (LBO = 16 B, SBO = 128 B) reads operand row r
+// at byte 16 r of the patch row - exactly the stride-4 window of output pixel r.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace yad {
+
+constexpr int SF_THREADS = 256;
+constexpr int SF_SEG = 128;                    // output pixels (columns) per tile = MMA M
+constexpr int SF_KD = 19;                      // composite kernel size
+constexpr int SF_KROW = 48;                    // K per kernel row: 19 taps x 2 channels = 38, padded to 3 MMA steps of 16
+constexpr int SF_K = SF_KD * SF_KROW;          // 912
+constexpr int SF_PW = 4 * (SF_SEG - 1) + SF_KROW / 2 + 4;   // 536 words per patch row (last window ends at word 4*127 + 24)
+constexpr int SF_ROWB = SF_PW * 4;             // 2144 B, multiple of 16
+constexpr int SF_MAXROWS = 35;                 // input rows of the interior class: 4*2-9 .. 4*6-9+18 -> -1 .. 33
+constexpr int SF_SBO_W = (SF_K / 8) * 128;     // weights: bytes between 8-row (cout) groups
+constexpr int SF_B_BYTES = 8 * SF_SBO_W;       // 116736
+constexpr int SF_TMEM_COLS = 512;              // up to 5 accumulators of 64 columns
+
+__device__ __forceinline__ uint64_t sf_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+struct StemFusedParams {
+  int32_t B, H, W, Ho, Wo, n_seg;
+  int32_t Hp, Wp;                // flat output pitches: pixel (b, h, w) at ((b * Wp + w) * Hp + h) * 64
+  int32_t cta_first[5];          // CTA ranges of the 4 row classes: class c owns blocks [cta_first[c], cta_first[c+1])
+  int32_t row_first[4], row_cnt[4];
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(SF_THREADS, 1)
+conv_stem_fused_kernel(const float* __restrict__ x, const StemFusedParams p, const uint4* __restrict__ w_classes,
+                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t sf_smem[];
+  uint8_t* sB = sf_smem;                                   // this class's weights, core-matrix layout
+  uint8_t* sP = sB + SF_B_BYTES;                           // [rows][SF_ROWB] patch
+  float* s_bias = reinterpret_cast<float*>(sP + SF_MAXROWS * SF_ROWB + 256);   // +256: slack read by the last row's last windows
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int cls = 0;
+  while (cls < 3 && (int)blockIdx.x >= p.cta_first[cls + 1]) ++cls;
+  const int cta_in_cls = blockIdx.x - p.cta_first[cls], n_cta_cls = p.cta_first[cls + 1] - p.cta_first[cls];
+  const int ho0 = p.row_first[cls], nrow = p.row_cnt[cls];
+  // input rows this class touches: [hi_lo, hi_hi)
+  const int hi_lo = max(4 * ho0 - 9, 0), hi_hi = min(4 * (ho0 + nrow - 1) - 9 + SF_KD, p.H);
+  const int prow = hi_hi - hi_lo;
+
+  const uint4* wsrc = w_classes + (size_t)cls * (SF_B_BYTES / 16);
+  for (int i = tid; i < SF_B_BYTES / 16; i += SF_THREADS) reinterpret_cast<uint4*>(sB)[i] = __ldg(wsrc + i);
+  if (tid < 64) s_bias[tid] = bias[tid];
+  if (tid == 0) {
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, SF_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t p_addr = smem_u32(sP), b_addr = smem_u32(sB);
+  const int q = warp & 3, half = warp >> 2;     // epilogue: TMEM lane quadrant, channel half
+  const int r = q * 32 + lane;                  // pixel inside the segment
+  uint32_t phase = 0;
+  const int n_tiles = p.B * p.n_seg;
+
+  for (int tile = cta_in_cls; tile < n_tiles; tile += n_cta_cls) {
+    const int seg = tile % p.n_seg, b = tile / p.n_seg;
+    const int wo0 = seg * SF_SEG, wi0 = 4 * wo0 - 9;
+    // (1) patch: fp32 NCHW -> bf16x2 words, zero outside the image (rows outside the image are simply not stored: their MMAs
+    //     are skipped)
+    const float* x0 = x + (int64_t)b * 2 * p.H * p.W;
+    uint32_t* P = reinterpret_cast<uint32_t*>(sP);
+    for (int col = tid; col < SF_PW; col += SF_THREADS) {
+      const int wi = wi0 + col;
+      const bool wok = wi >= 0 && wi < p.W;
+#pragma unroll 1
+      for (int row0 = 0; row0 < prow; row0 += 7) {
+        float a[7], c[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const int hi = hi_lo + row0 + j;
+          const bool ok = wok && row0 + j < prow;
+          a[j] = ok ? __ldg(x0 + (int64_t)hi * p.W + wi) : 0.0f;
+          c[j] = ok ? __ldg(x0 + ((int64_t)p.H + hi) * p.W + wi) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          if (row0 + j < prow) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a[j], c[j]);
+            P[(row0 + j) * SF_PW + col] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+      }
+    }
+    fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();
+    // (2) MMAs: one accumulator per output row of the class; kernel rows whose input row is outside the image are skipped
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        for (int j = 0; j < nrow; ++j) {
+          const int hi_base = 4 * (ho0 + j) - 9;
+          uint32_t acc = 0u;
+          for (int dh = 0; dh < SF_KD; ++dh) {
+            const int hi = hi_base + dh;
+            if (hi < 0 || hi >= p.H) continue;
+            const uint32_t a0 = p_addr + (uint32_t)(hi - hi_lo) * SF_ROWB;
+            const uint32_t b0 = b_addr + (uint32_t)(dh * 3) * 256u;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              umma_bf16(tmem_base + (uint32_t)(j * 64), sf_nosw_desc(a0 + s * 32, 16, 128), sf_nosw_desc(b0 + s * 256, 128, SF_SBO_W),
+                        p.idesc, acc);
+              acc = 1u;
+            }
+          }
+        }
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(mma_bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // (3) epilogue: bias + ReLU, bf16, flat halo layout; thread = (pixel r, 32-channel half); the rows of a class are adjacent
+    //     in memory (h fastest), so a thread's stores of consecutive rows are contiguous
+    const int wo = wo0 + r;
+    const bool ok = wo < p.Wo;
+    for (int j = 0; j < nrow; ++j) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + half * 32), v);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* op = reinterpret_cast<uint4*>(out + (((int64_t)b * p.Wp + wo) * p.Hp + (ho0 + j)) * 64 + half * 32);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = half * 32 + j4 * 8 + e * 2;
+            const float f0 = fmaxf(__uint_as_float(v[j4 * 8 + e * 2]) + s_bias[c], 0.0f);
+            const float f1 = fmaxf(__uint_as_float(v[j4 * 8 + e * 2 + 1]) + s_bias[c + 1], 0.0f);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+            w[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          op[j4] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();       // accumulators drained before the next tile overwrites them / the patch is refilled
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, SF_TMEM_COLS);
+}
+
+// Exact recomputation of the border COLUMNS (conv2 taps outside conv1's output dropped along W): one CTA per (clip, column),
+// thread = (output row, output channel); fp32 on the CUDA cores.  w_var [n_var][4 row classes][19][19][2][64] f32.
+struct StemFixupParams {
+  int32_t B, H, W, Ho, Hp, Wp, n_cols;
+  int32_t col[8], var[8];
+  int32_t row_class[8];          // row class of output rows 0..7
+};
+
+__global__ void __launch_bounds__(512, 1)
+stem_fixup_kernel(const float* __restrict__ x, const StemFixupParams p, const float* __restrict__ w_var,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_x[2][32][SF_KD + 1];
+  const int ci = blockIdx.x, b = blockIdx.y;
+  const int wo = p.col[ci], var = p.var[ci];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * p.H * SF_KD; i += blockDim.x) {
+    const int dw = i % SF_KD, hi = (i / SF_KD) % p.H, c = i / (SF_KD * p.H);
+    const int wi = 4 * wo - 9 + dw;
+    s_x[c][hi][dw] = (wi >= 0 && wi < p.W) ? x[(((int64_t)b * 2 + c) * p.H + hi) * p.W + wi] : 0.0f;
+  }
+  __syncthreads();
+  const int co = tid & 63, ho = tid >> 6;
+  if (ho >= p.Ho) return;
+  const float* wv = w_var + ((size_t)(var * 4 + p.row_class[ho]) * SF_KD * SF_KD * 2) * 64 + co;
+  float acc = bias[co];
+  for (int dh = 0; dh < SF_KD; ++dh) {
+    const int hi = 4 * ho - 9 + dh;
+    if (hi < 0 || hi >= p.H) continue;
+#pragma unroll
+    for (int dw = 0; dw < SF_KD; ++dw) {
+      acc = fmaf(s_x[0][hi][dw], __ldg(wv + ((dh * SF_KD + dw) * 2 + 0) * 64), acc);
+      acc = fmaf(s_x[1][hi][dw], __ldg(wv + ((dh * SF_KD + dw) * 2 + 1) * 64), acc);
+    }
+  }
+  out[(((int64_t)b * p.Wp + wo) * p.Hp + ho) * 64 + co] = __float2bfloat16_rn(fmaxf(acc, 0.0f));
+}
+
+static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + 64; }
+
+int init_conv_stem_fused_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(conv_stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem_fused_smem_bytes());
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(conv_stem_fused_kernel) failed: %s", cudaGetErrorString(e));
+    return YAD_ERR_CUDA;
+  }
+  return YAD_OK;
+}
+
+}  // namespace yad
+
+extern "C" int yad_conv_stem_fused(const float* x_nchw, int64_t B, int32_t H, int32_t W, const void* w_classes, const float* bias,
+                                   void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x_nchw && w_classes && bias && out_flat_bf16, "yad_conv_stem_fused: null pointer");
+  YAD_CHECK_ARG(H == 32 && W >= 8 && B >= 0 && B < (1 << 22), "yad_conv_stem_fused: built for H = 32 (n_mels), W >= 8 (got H=%d W=%d)", H, W);
+  YAD_CHECK_ARG((reinterpret_cast<uintptr_t>(w_classes) % 16 == 0) && (reinterpret_cast<uintptr_t>(out_flat_bf16) % 16 == 0),
+                "yad_conv_stem_fused: weights / out must be 16-byte aligned");
+  if (B == 0) return YAD_OK;
+  StemFusedParams p;
+  p.B = (int)B;
+  p.H = H;
+  p.W = W;
+  p.Ho = 8;
+  p.Wo = (((W - 1) / 2 + 1) - 1) / 2 + 1;
+  YAD_CHECK_ARG(Hp >= p.Ho && Wp >= p.Wo, "yad_conv_stem_fused: output pitches (%d,%d) smaller than the image (%d,%d)", Hp, Wp, p.Ho, p.Wo);
+  p.n_seg = (p.Wo + SF_SEG - 1) / SF_SEG;
+  p.Hp = Hp;
+  p.Wp = Wp;
+  const int rf[4] = {2, 0, 1, 7}, rc[4] = {5, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) p.row_first[i] = rf[i], p.row_cnt[i] = rc[i];
+  const int nsm = sm_count() > 0 ? sm_count() : 148;
+  const int64_t n_tiles = B * p.n_seg;
+  int n_int = n_cta_interior > 0 ? n_cta_interior : (nsm * 46) / 100;      // measured balance point of the four classes
+  if (n_int > nsm - 3) n_int = nsm - 3;
+  if (n_int < 1) n_int = 1;
+  int rest = nsm - n_int;
+  int n1 = rest / 3, n2 = rest / 3, n3 = rest - 2 * (rest / 3);
+  auto cap = [&](int v) { return (int)(v > n_tiles ? n_tiles : (v < 1 ? 1 : v)); };
+  n_int = cap(n_int), n1 = cap(n1), n2 = cap(n2), n3 = cap(n3);
+  p.cta_first[0] = 0;
+  p.cta_first[1] = n_int;
+  p.cta_first[2] = n_int + n1;
+  p.cta_first[3] = n_int + n1 + n2;
+  p.cta_first[4] = n_int + n1 + n2 + n3;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  conv_stem_fused_kernel<<<p.cta_first[4], SF_THREADS, stem_fused_smem_bytes(), (cudaStream_t)stream>>>(
+      x_nchw, p, reinterpret_cast<const uint4*>(w_classes), bias, reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}
+
+extern "C" int yad_conv_stem_fused_fixup(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* w_var, const float* bias,
+                                         const int32_t* cols, const int32_t* col_var, int32_t n_cols, void* out_flat_bf16,
+                                         int32_t Hp, int32_t Wp, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x_nchw && w_var && bias && out_flat_bf16 && (n_cols == 0 || (cols && col_var)), "yad_conv_stem_fused_fixup: null pointer");
+  YAD_CHECK_ARG(H == 32 && W >= 8 && B >= 0 && B <= 65535 && n_cols >= 0 && n_cols <= 8, "yad_conv_stem_fused_fixup: bad arguments");
+  if (B == 0 || n_cols == 0) return YAD_OK;
+  StemFixupParams p;
+  p.B = (int)B;
+  p.H = H;
+  p.W = W;
+  p.Ho = 8;
+  p.Hp = Hp;
+  p.Wp = Wp;
+  p.n_cols = n_cols;
+  for (int i = 0; i < 8; ++i) p.col[i] = i < n_cols ? cols[i] : 0, p.var[i] = i < n_cols ? col_var[i] : 0;
+  const int rcls[8] = {1, 2, 0, 0, 0, 0, 0, 3};
+  for (int i = 0; i < 8; ++i) p.row_class[i] = rcls[i];
+  stem_fixup_kernel<<<dim3((unsigned)n_cols, (unsigned)B), 512, 0, (cudaStream_t)stream>>>(x_nchw, p, w_var, bias,
+                                                                                         reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import threading
 from typing import Dict, List, Optional, Tuple
 
@@ -188,6 +189,9 @@ class InferenceEngine:
             steps.sort(key=lambda t: t[0])
             arr = lambda i: (C.c_int32 * len(steps))(*[t[i] for t in steps])   # noqa: E731
             self.conv2_steps = (arr(0), arr(1), arr(2), arr(3))
+        self.fused_stem = (self.dtype == BF16 and self.bb_kind == "basic" and os.environ.get("YAD_FUSED_STEM", "1") != "0")
+        if self.fused_stem:
+            self._pack_fused_stem(fe.conv1.weight, w2, b2)
         self.stages = []
         for li in range(1, 5):
             blocks = []
@@ -217,6 +221,48 @@ class InferenceEngine:
                     ent["ds"] = _Conv(f"l{li}.{bi}.ds", wd, bd, blk.stride, 0, ACT_NONE, dev, self.dtype)
                 blocks.append(ent)
             self.stages.append(blocks)
+
+    # column tap sets of conv2 that stay inside conv1's output: (lo, hi) = valid kw2 range; index = variant of the fix-up weights
+    _COL_VARIANTS = [(3, 6), (1, 6), (0, 3), (0, 4), (0, 5)]
+    _ROW_CLASSES = [(0, 6), (3, 6), (1, 6), (0, 4)]        # rows 2..6 | row 0 | row 1 | row 7 (H = 32 -> 16 -> 8)
+
+    def _pack_fused_stem(self, w1, w2f, b2):
+        """conv1 o (conv2 * bn1) as one 19x19 stride-4 convolution (csrc/conv_stem_fused.cu): composite weights
+        W12[co, c, dh, dw] = sum_{c1, kh2, kw2 valid} W2[co, c1, kh2, kw2] W1[c1, c, dh - 2 kh2, dw - 2 kw2], built in fp64 as a
+        transposed convolution; one variant per set of conv2 taps that fall inside conv1's output (zero padding of the
+        INTERMEDIATE tensor, modules/_backbone.py:143-144)."""
+        dev = self.dev
+        w1d = w1.detach().to(dev, torch.float64)
+        w2d = w2f.detach().to(dev, torch.float64)
+
+        def compose(rows, cols):
+            m = torch.zeros_like(w2d)
+            m[:, :, rows[0]:rows[1] + 1, cols[0]:cols[1] + 1] = w2d[:, :, rows[0]:rows[1] + 1, cols[0]:cols[1] + 1]
+            return torch.nn.functional.conv_transpose2d(m, w1d, stride=2)            # [64, 2, 19, 19]
+        cls = []
+        for rows in self._ROW_CLASSES:
+            w12 = compose(rows, (0, 6)).permute(0, 2, 3, 1).reshape(64, 19, 38)      # K order (dh, dw, c)
+            wk = torch.zeros(64, 19, 48, device=dev, dtype=torch.float64)
+            wk[:, :, :38] = w12
+            cls.append(wk.reshape(8, 8, 114, 8).permute(0, 2, 1, 3).contiguous())    # [n/8][k/8][n%8][k%8]
+        self.fstem_w = torch.stack(cls).to(torch.bfloat16).contiguous()
+        var = [torch.stack([compose(rows, cols).permute(2, 3, 1, 0) for rows in self._ROW_CLASSES]) for cols in self._COL_VARIANTS]
+        self.fstem_wvar = torch.stack(var).to(torch.float32).contiguous()            # [5][4][19][19][2][64]
+        self.fstem_bias = b2.detach().to(dev, torch.float32).contiguous()
+
+    @classmethod
+    def _fused_stem_border_cols(cls, W: int):
+        """Output columns whose conv2 taps partly fall outside conv1's output, with their fix-up weight variant."""
+        W1 = (W - 1) // 2 + 1
+        Wo = (W1 - 1) // 2 + 1
+        cols, var = [], []
+        for wo in list(range(0, min(2, Wo))) + list(range(max(Wo - 3, 2), Wo)):
+            v = [k for k in range(7) if 0 <= 2 * wo - 3 + k < W1]
+            if len(v) == 7:
+                continue
+            cols.append(wo)
+            var.append(cls._COL_VARIANTS.index((v[0], v[-1])))
+        return cols, var
 
     def _pack_neck(self, ms):
         sp = ms.cspsppf
@@ -403,20 +449,20 @@ class InferenceEngine:
             # stride-1 flat conv with 49 (plane, shift) steps; backbone activations stay in the flat layout (conv_flat.cu)
             H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
             assert (H2, W2) == (H, W)
-            c1 = plan.get("c1")
-            if c1 is None:
-                c1 = plan["c1"] = torch.zeros((B, W2 + 2, H2 + 2, 256), device=self.dev, dtype=torch.bfloat16)
-            _lib.check(self.lib.yad_conv_stem_tc(xs.data_ptr(), B, H0, T, self.stem_w_tc.data_ptr(), c1.data_ptr(), H2 + 2, W2 + 2, s()),
-                       "conv_stem_tc")
-            cur = self._flat_buf(plan, "c2", B, H, W, 64)
-            Hp, Wp = self._flat_geom(H, W)
-            cv = self.conv2
-            d = FlatDesc(B=B, H=H2, W=W2, Hp=H2 + 2, Wp=W2 + 2, Cin=256, ld_in=256, Cout=cv.cout, ld_out=64, co_off=0, kh=1, kw=1,
-                         ph=0, pw=0, act=cv.act, ld_res=0, Hp_out=Hp, Wp_out=Wp)
-            ch, dh, dw, wk = self.conv2_steps
-            _lib.check(self.lib.yad_conv_flat_taps(C.byref(d), len(ch), ch, dh, dw, wk, cv.kh * cv.kw * cv.cin_pad, c1.data_ptr(),
-                                                   cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), 0, cur.data_ptr(), s()),
-                       "conv fe.conv2 (flat, space-to-depth)")
+            if self.fused_stem and H0 == 32 and T >= 32:
+                cur = self._flat_buf(plan, "c2", B, H, W, 64)
+                Hp, Wp = self._flat_geom(H, W)
+                _lib.check(self.lib.yad_conv_stem_fused(xs.data_ptr(), B, H0, T, self.fstem_w.data_ptr(), self.fstem_bias.data_ptr(),
+                                                        cur.data_ptr(), Hp, Wp, int(os.environ.get("YAD_STEM_NINT", "0")), s()),
+                           "conv_stem_fused")
+                fx = plan.get("fstem_cols")
+                if fx is None:
+                    cols, var = self._fused_stem_border_cols(T)
+                    fx = plan["fstem_cols"] = ((C.c_int32 * len(cols))(*cols), (C.c_int32 * len(var))(*var), len(cols))
+                _lib.check(self.lib.yad_conv_stem_fused_fixup(xs.data_ptr(), B, H0, T, self.fstem_wvar.data_ptr(), self.fstem_bias.data_ptr(),
+                                                              fx[0], fx[1], fx[2], cur.data_ptr(), Hp, Wp, s()), "conv_stem_fused_fixup")
+            else:
+                cur = self._run_stem_two_convs(xs, plan, B, H0, T, H, W, H2, W2)
             for li, blocks in enumerate(self.stages):
                 for bi, blk in enumerate(blocks):
                     c1v, c2v = blk["c1"], blk["c2"]
@@ -583,6 +629,26 @@ class InferenceEngine:
         if taps is not None:
             taps["heads"] = [h.reshape(B, h.shape[2], h.shape[3])[..., : self.n_head].float().clone() for h in heads]
         return heads
+
+    def _run_stem_two_convs(self, xs, plan, B, H0, T, H, W, H2, W2):
+        """conv1 -> space-to-depth flat tensor -> conv2 as a stride-1 flat conv (the path the fused stem replaces; kept for input
+        heights other than 32 and as the A/B reference: YAD_FUSED_STEM=0)."""
+        s = self._stream
+        c1 = plan.get("c1")
+        if c1 is None:
+            c1 = plan["c1"] = torch.zeros((B, W2 + 2, H2 + 2, 256), device=self.dev, dtype=torch.bfloat16)
+        _lib.check(self.lib.yad_conv_stem_tc(xs.data_ptr(), B, H0, T, self.stem_w_tc.data_ptr(), c1.data_ptr(), H2 + 2, W2 + 2, s()),
+                   "conv_stem_tc")
+        cur = self._flat_buf(plan, "c2", B, H, W, 64)
+        Hp, Wp = self._flat_geom(H, W)
+        cv = self.conv2
+        d = FlatDesc(B=B, H=H2, W=W2, Hp=H2 + 2, Wp=W2 + 2, Cin=256, ld_in=256, Cout=cv.cout, ld_out=64, co_off=0, kh=1, kw=1,
+                     ph=0, pw=0, act=cv.act, ld_res=0, Hp_out=Hp, Wp_out=Wp)
+        ch, dh, dw, wk = self.conv2_steps
+        _lib.check(self.lib.yad_conv_flat_taps(C.byref(d), len(ch), ch, dh, dw, wk, cv.kh * cv.kw * cv.cin_pad, c1.data_ptr(),
+                                               cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), 0, cur.data_ptr(), s()),
+                   "conv fe.conv2 (flat, space-to-depth)")
+        return cur
 
     def _run_custom_backbone(self, xs: torch.Tensor, plan: dict):
         """CustomBackBone.forward in eval mode (modules/_backbone.py:108-116), dense NHWC; every ExtractorLayer writes its two
