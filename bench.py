@@ -151,7 +151,8 @@ def time_stages(model, x, reps=3):
         if getattr(eng, "fused_stem", False):      # conv1 o conv2 as one convolution (+ border-column fix-up)
             cur = plan["c2"]
             fx = plan["fstem_cols"]
-            _lib.check(eng.lib.yad_conv_stem_fused(xs.data_ptr(), B, 32, T, eng.fstem_w.data_ptr(), eng.fstem_bias.data_ptr(), cur.data_ptr(),
+            xb = plan["xs_bf16"]
+            _lib.check(eng.lib.yad_conv_stem_fused(xb.data_ptr(), xb.shape[2], B, 32, T, eng.fstem_w.data_ptr(), eng.fstem_bias.data_ptr(), cur.data_ptr(),
                                                    cur.shape[2], cur.shape[1], int(os.environ.get("YAD_STEM_NINT", "0")), eng._stream()), "stem_fused")
             _lib.check(eng.lib.yad_conv_stem_fused_fixup(xs.data_ptr(), B, 32, T, eng.fstem_wvar.data_ptr(), eng.fstem_bias.data_ptr(), fx[0],
                                                          fx[1], fx[2], cur.data_ptr(), cur.shape[2], cur.shape[1], eng._stream()), "stem_fixup")

@@ -97,6 +97,13 @@ int yad_frontend_finish(const float* mel, int64_t B, int64_t T, const float* dct
                         float top_db, int32_t standardise, float* x_spectral, float* tap_meldb,
                         float* tap_mfcc, float* tap_mfdb, yad_stream_t stream);
 
+/* Stage B that additionally writes x_spectral as channel-interleaved bf16 words (ch0 in the low half) into
+ * xs_bf16 [B][32][bf_pitch] at word offset bf_margin + t: the input form of yad_conv_stem_fused (bf_margin = 9 = its left
+ * padding; the caller zero-fills the tensor once, the margins are never written).  T <= 1024. */
+int yad_frontend_finish_bf16(const float* mel, int64_t B, int64_t T, const float* dct, float top_db, int32_t standardise,
+                             float* x_spectral, float* tap_meldb, float* tap_mfcc, float* tap_mfdb, void* xs_bf16,
+                             int64_t bf_pitch, int32_t bf_margin, yad_stream_t stream);
+
 /* ------------------------------------------------------------------ convolutions
  * Replace F.conv2d + batch_norm(eval) + activation (+ residual add) call sites:
  * modules/_backbone.py:143-151, [tv] models/resnet.py:89-105, modules/_common.py:43-48,86-95.
@@ -136,17 +143,20 @@ int yad_conv_stem_tc(const float* x_nchw, int64_t B, int32_t H, int32_t W, const
 
 /* conv1 o conv2 of the stem as ONE 19x19 / stride-4 / pad-9 convolution 2 -> 64 (+ bias, ReLU) on the tensor cores: the two
  * reference convolutions (modules/_backbone.py:143-146) have nothing between them, so W12 = conv_transpose(W2 * bn1, W1) and
- * the intermediate [B,64,16,480] tensor never exists.  Reads x_spectral NCHW f32 (H = 32), writes the FLAT halo-padded bf16
- * layout of yad_conv_flat ([B, Wp, Hp, 64], pixel (b,h,w) at (b*Wp + w)*Hp + h).
+ * the intermediate [B,64,16,480] tensor never exists.  Reads x_spectral in the padded channel-interleaved bf16 form of
+ * yad_frontend_finish_bf16 ([B][32][x_pitch] words, 9-word zero margin on the left, zeros up to x_pitch on the right,
+ * x_pitch % 4 == 0 and >= 512*(n_seg-1) + 536: every patch row is one 16-byte aligned bulk copy), H = 32; writes the FLAT
+ * halo-padded bf16 layout of yad_conv_flat ([B, Wp, Hp, 64], pixel (b,h,w) at (b*Wp + w)*Hp + h).
  * w_classes: bf16 [4 row classes][64][912] (K = dh*48 + dw*2 + c, zero for dw >= 19) in the 8x8 core-matrix layout of
  * yad_conv_stem_tc (element (n,k) of a class at byte (n/8)*14592 + (k/8)*128 + (n%8)*16 + (k%8)*2); the classes hold the
  * composite built from the conv2 row taps that stay inside conv1's output: 0 = rows 2..6 (all), 1 = row 0 (kh2 >= 3),
  * 2 = row 1 (kh2 >= 1), 3 = row 7 (kh2 <= 4).  n_cta_interior: CTAs given to class 0 (0 = built-in split).
  * Border COLUMNS (0, 1 and the last one or two) are computed with the interior-column weights here; yad_conv_stem_fused_fixup
- * must follow on the same stream: it recomputes them exactly in fp32.  cols / col_var are HOST arrays (n_cols <= 8);
+ * must follow on the same stream: it recomputes them exactly in fp32 from x_spectral NCHW f32.  cols / col_var are HOST arrays (n_cols <= 8);
  * w_var f32 [n_var][4 row classes][19][19][2][64]. */
-int yad_conv_stem_fused(const float* x_nchw, int64_t B, int32_t H, int32_t W, const void* w_classes, const float* bias,
-                        void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior, yad_stream_t stream);
+int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W, const void* w_classes,
+                        const float* bias, void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior,
+                        yad_stream_t stream);
 int yad_conv_stem_fused_fixup(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* w_var, const float* bias,
                               const int32_t* cols, const int32_t* col_var, int32_t n_cols, void* out_flat_bf16,
                               int32_t Hp, int32_t Wp, yad_stream_t stream);

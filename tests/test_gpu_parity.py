@@ -663,8 +663,13 @@ def test_fused_stem_vs_two_convs(B, T, cuda_dev):
     Hp, Wp = Ho + 1, Wo + 1
     out = torch.zeros(B, Wp, Hp, 64, device=cuda_dev, dtype=torch.bfloat16)
     xd = x.to(cuda_dev)
-    _lib.check(lib.yad_conv_stem_fused(xd.data_ptr(), B, 32, T, eng.fstem_w.data_ptr(), eng.fstem_bias.data_ptr(), out.data_ptr(), Hp, Wp, 0,
-                                       _stream()), "fused")
+    # padded channel-interleaved bf16 words (what yad_frontend_finish_bf16 writes): 9-word zero margin, zero tail
+    n_seg = (Wo + 127) // 128
+    pitch = (max(512 * (n_seg - 1) + 536, 9 + T) + 3) // 4 * 4
+    xb16 = torch.zeros(B, 32, pitch, 2, device=cuda_dev, dtype=torch.bfloat16)
+    xb16[:, :, 9:9 + T, :] = xd.permute(0, 2, 3, 1).to(torch.bfloat16)
+    _lib.check(lib.yad_conv_stem_fused(xb16.data_ptr(), pitch, B, 32, T, eng.fstem_w.data_ptr(), eng.fstem_bias.data_ptr(), out.data_ptr(), Hp,
+                                       Wp, 0, _stream()), "fused")
     cols, var = InferenceEngine._fused_stem_border_cols(T)
     _lib.check(lib.yad_conv_stem_fused_fixup(xd.data_ptr(), B, 32, T, eng.fstem_wvar.data_ptr(), eng.fstem_bias.data_ptr(),
                                              (C.c_int32 * len(cols))(*cols), (C.c_int32 * len(var))(*var), len(cols), out.data_ptr(), Hp, Wp,

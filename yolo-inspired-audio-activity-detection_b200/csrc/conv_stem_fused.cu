@@ -13,7 +13,8 @@
 // GEMM view per output row ho and 128 consecutive output pixels: D[128, 64] = sum over the kernel rows dh whose input row
 // hi = 4 ho - 9 + dh is inside the image of  A_dh[128, 48] * W_dh[64, 48]^T,  K index = dw * 2 + c (38 real + 10 zero-weight).
 // As in conv_stem_tc.cu the A operand is NOT an im2col copy: the patch lives in shared memory as channel-interleaved bf16 rows
-// (one 4-byte word per input pixel) and the no-swizzle K-major UMMA descriptor (LBO = 16 B, SBO = 128 B) reads operand row r
+// (one 4-byte word per input pixel; frontend stage B writes x_spectral a second time in exactly this form, with zero margins, so
+// a patch row is ONE 2144-byte bulk copy) and the no-swizzle K-major UMMA descriptor (LBO = 16 B, SBO = 128 B) reads operand row r
 // at byte 16 r of the patch row - exactly the stride-4 window of output pixel r.
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -44,20 +45,29 @@ __device__ __forceinline__ uint64_t sf_nosw_desc(uint32_t smem_addr, uint32_t lb
 struct StemFusedParams {
   int32_t B, H, W, Ho, Wo, n_seg;
   int32_t Hp, Wp;                // flat output pitches: pixel (b, h, w) at ((b * Wp + w) * Hp + h) * 64
+  int64_t xpitch;                // words per row of the padded bf16 input
   int32_t cta_first[5];          // CTA ranges of the 4 row classes: class c owns blocks [cta_first[c], cta_first[c+1])
   int32_t row_first[4], row_cnt[4];
   uint32_t idesc;
 };
 
+// 1-D bulk copy global -> shared (TMA unit), completion counted on an mbarrier
+__device__ __forceinline__ void sf_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __global__ void __launch_bounds__(SF_THREADS, 1)
-conv_stem_fused_kernel(const float* __restrict__ x, const StemFusedParams p, const uint4* __restrict__ w_classes,
+conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p, const uint4* __restrict__ w_classes,
                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(128) uint8_t sf_smem[];
   uint8_t* sB = sf_smem;                                   // this class's weights, core-matrix layout
   uint8_t* sP = sB + SF_B_BYTES;                           // [rows][SF_ROWB] patch
   float* s_bias = reinterpret_cast<float*>(sP + SF_MAXROWS * SF_ROWB + 256);   // +256: slack read by the last row's last windows
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint64_t* fill_bar = mma_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(fill_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int cls = 0;
@@ -73,9 +83,11 @@ conv_stem_fused_kernel(const float* __restrict__ x, const StemFusedParams p, con
   if (tid < 64) s_bias[tid] = bias[tid];
   if (tid == 0) {
     mbar_init(mma_bar, 1);
+    mbar_init(fill_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, SF_TMEM_COLS);
+  fence_proxy_async();     // the weights were written through the generic proxy; the tensor core reads them through the async one
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -88,35 +100,16 @@ conv_stem_fused_kernel(const float* __restrict__ x, const StemFusedParams p, con
 
   for (int tile = cta_in_cls; tile < n_tiles; tile += n_cta_cls) {
     const int seg = tile % p.n_seg, b = tile / p.n_seg;
-    const int wo0 = seg * SF_SEG, wi0 = 4 * wo0 - 9;
-    // (1) patch: fp32 NCHW -> bf16x2 words, zero outside the image (rows outside the image are simply not stored: their MMAs
-    //     are skipped)
-    const float* x0 = x + (int64_t)b * 2 * p.H * p.W;
-    uint32_t* P = reinterpret_cast<uint32_t*>(sP);
-    for (int col = tid; col < SF_PW; col += SF_THREADS) {
-      const int wi = wi0 + col;
-      const bool wok = wi >= 0 && wi < p.W;
-#pragma unroll 1
-      for (int row0 = 0; row0 < prow; row0 += 7) {
-        float a[7], c[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          const int hi = hi_lo + row0 + j;
-          const bool ok = wok && row0 + j < prow;
-          a[j] = ok ? __ldg(x0 + (int64_t)hi * p.W + wi) : 0.0f;
-          c[j] = ok ? __ldg(x0 + ((int64_t)p.H + hi) * p.W + wi) : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          if (row0 + j < prow) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(a[j], c[j]);
-            P[(row0 + j) * SF_PW + col] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-        }
-      }
+    const int wo0 = seg * SF_SEG;
+    // (1) patch rows: the input lives as channel-interleaved bf16 words with a 9-word zero margin on the left (and zeros on the
+    //     right), so the window row of this segment is the 16-byte aligned span [4 wo0, 4 wo0 + SF_PW) of the padded row: one
+    //     bulk copy per input row, no bounds logic.  Rows outside the image are not loaded (their MMAs are skipped).
+    if (tid == 0) {
+      mbar_expect_tx(fill_bar, (uint32_t)prow * SF_ROWB);
+      const uint32_t* src = xb + ((int64_t)b * p.H + hi_lo) * p.xpitch + 4 * wo0;
+      for (int rr = 0; rr < prow; ++rr) sf_bulk_g2s(sP + rr * SF_ROWB, src + (int64_t)rr * p.xpitch, SF_ROWB, fill_bar);
     }
-    fence_proxy_async();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    __syncthreads();
+    mbar_wait(fill_bar, phase);
     // (2) MMAs: one accumulator per output row of the class; kernel rows whose input row is outside the image are skipped
     if (warp == 0) {
       if (elect_one()) {
@@ -183,38 +176,45 @@ struct StemFixupParams {
   int32_t row_class[8];          // row class of output rows 0..7
 };
 
+constexpr int FX_CLIPS = 8;      // clips per CTA: every composite weight is fetched once per 8 clips (the kernel is bound by them)
+
 __global__ void __launch_bounds__(512, 1)
 stem_fixup_kernel(const float* __restrict__ x, const StemFixupParams p, const float* __restrict__ w_var,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
-  __shared__ float s_x[2][32][SF_KD + 1];
-  const int ci = blockIdx.x, b = blockIdx.y;
+  __shared__ float s_x[FX_CLIPS][2][32][SF_KD + 1];
+  const int ci = blockIdx.x, b0 = blockIdx.y * FX_CLIPS;
+  const int nb = min(FX_CLIPS, p.B - b0);
   const int wo = p.col[ci], var = p.var[ci];
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * p.H * SF_KD; i += blockDim.x) {
-    const int dw = i % SF_KD, hi = (i / SF_KD) % p.H, c = i / (SF_KD * p.H);
+  for (int i = tid; i < FX_CLIPS * 2 * 32 * SF_KD; i += blockDim.x) {
+    const int dw = i % SF_KD, hi = (i / SF_KD) % 32, c = (i / (SF_KD * 32)) % 2, bb = i / (SF_KD * 32 * 2);
     const int wi = 4 * wo - 9 + dw;
-    s_x[c][hi][dw] = (wi >= 0 && wi < p.W) ? x[(((int64_t)b * 2 + c) * p.H + hi) * p.W + wi] : 0.0f;
+    s_x[bb][c][hi][dw] = (bb < nb && hi < p.H && wi >= 0 && wi < p.W) ? x[(((int64_t)(b0 + bb) * 2 + c) * p.H + hi) * p.W + wi] : 0.0f;
   }
   __syncthreads();
   const int co = tid & 63, ho = tid >> 6;
   if (ho >= p.Ho) return;
   const float* wv = w_var + ((size_t)(var * 4 + p.row_class[ho]) * SF_KD * SF_KD * 2) * 64 + co;
-  float acc = bias[co];
+  float acc[FX_CLIPS];
+#pragma unroll
+  for (int bb = 0; bb < FX_CLIPS; ++bb) acc[bb] = bias[co];
   for (int dh = 0; dh < SF_KD; ++dh) {
     const int hi = 4 * ho - 9 + dh;
     if (hi < 0 || hi >= p.H) continue;
-#pragma unroll
     for (int dw = 0; dw < SF_KD; ++dw) {
-      acc = fmaf(s_x[0][hi][dw], __ldg(wv + ((dh * SF_KD + dw) * 2 + 0) * 64), acc);
-      acc = fmaf(s_x[1][hi][dw], __ldg(wv + ((dh * SF_KD + dw) * 2 + 1) * 64), acc);
+      const float w0 = __ldg(wv + ((dh * SF_KD + dw) * 2 + 0) * 64), w1 = __ldg(wv + ((dh * SF_KD + dw) * 2 + 1) * 64);
+#pragma unroll
+      for (int bb = 0; bb < FX_CLIPS; ++bb) acc[bb] = fmaf(s_x[bb][1][hi][dw], w1, fmaf(s_x[bb][0][hi][dw], w0, acc[bb]));
     }
   }
-  out[(((int64_t)b * p.Wp + wo) * p.Hp + ho) * 64 + co] = __float2bfloat16_rn(fmaxf(acc, 0.0f));
+  for (int bb = 0; bb < nb; ++bb)
+    out[(((int64_t)(b0 + bb) * p.Wp + wo) * p.Hp + ho) * 64 + co] = __float2bfloat16_rn(fmaxf(acc[bb], 0.0f));
 }
 
 static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + 64; }
 
 int init_conv_stem_fused_attrs() {
+  static_assert(SF_ROWB % 16 == 0, "bulk copies move multiples of 16 bytes");
   cudaError_t e = cudaFuncSetAttribute(conv_stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem_fused_smem_bytes());
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_stem_fused_kernel) failed: %s", cudaGetErrorString(e));
@@ -225,10 +225,12 @@ int init_conv_stem_fused_attrs() {
 
 }  // namespace yad
 
-extern "C" int yad_conv_stem_fused(const float* x_nchw, int64_t B, int32_t H, int32_t W, const void* w_classes, const float* bias,
-                                   void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior, yad_stream_t stream) {
+extern "C" int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W, const void* w_classes,
+                                   const float* bias, void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior,
+                                   yad_stream_t stream) {
   using namespace yad;
-  YAD_CHECK_ARG(x_nchw && w_classes && bias && out_flat_bf16, "yad_conv_stem_fused: null pointer");
+  YAD_CHECK_ARG(x_bf16_padded && w_classes && bias && out_flat_bf16, "yad_conv_stem_fused: null pointer");
+  YAD_CHECK_ARG(reinterpret_cast<uintptr_t>(x_bf16_padded) % 16 == 0 && x_pitch % 4 == 0, "yad_conv_stem_fused: input rows must be 16-byte aligned");
   YAD_CHECK_ARG(H == 32 && W >= 8 && B >= 0 && B < (1 << 22), "yad_conv_stem_fused: built for H = 32 (n_mels), W >= 8 (got H=%d W=%d)", H, W);
   YAD_CHECK_ARG((reinterpret_cast<uintptr_t>(w_classes) % 16 == 0) && (reinterpret_cast<uintptr_t>(out_flat_bf16) % 16 == 0),
                 "yad_conv_stem_fused: weights / out must be 16-byte aligned");
@@ -241,13 +243,17 @@ extern "C" int yad_conv_stem_fused(const float* x_nchw, int64_t B, int32_t H, in
   p.Wo = (((W - 1) / 2 + 1) - 1) / 2 + 1;
   YAD_CHECK_ARG(Hp >= p.Ho && Wp >= p.Wo, "yad_conv_stem_fused: output pitches (%d,%d) smaller than the image (%d,%d)", Hp, Wp, p.Ho, p.Wo);
   p.n_seg = (p.Wo + SF_SEG - 1) / SF_SEG;
+  YAD_CHECK_ARG(x_pitch >= 4 * SF_SEG * (p.n_seg - 1) + SF_PW && x_pitch >= 9 + W,
+                "yad_conv_stem_fused: x_pitch %lld too small (need >= %d words: 9-word left margin + W + zero tail)", (long long)x_pitch,
+                4 * SF_SEG * (p.n_seg - 1) + SF_PW);
+  p.xpitch = x_pitch;
   p.Hp = Hp;
   p.Wp = Wp;
   const int rf[4] = {2, 0, 1, 7}, rc[4] = {5, 1, 1, 1};
   for (int i = 0; i < 4; ++i) p.row_first[i] = rf[i], p.row_cnt[i] = rc[i];
   const int nsm = sm_count() > 0 ? sm_count() : 148;
   const int64_t n_tiles = B * p.n_seg;
-  int n_int = n_cta_interior > 0 ? n_cta_interior : (nsm * 46) / 100;      // measured balance point of the four classes
+  int n_int = n_cta_interior > 0 ? n_cta_interior : (nsm * 57) / 100;      // measured balance point of the four classes
   if (n_int > nsm - 3) n_int = nsm - 3;
   if (n_int < 1) n_int = 1;
   int rest = nsm - n_int;
@@ -261,7 +267,8 @@ extern "C" int yad_conv_stem_fused(const float* x_nchw, int64_t B, int32_t H, in
   p.cta_first[4] = n_int + n1 + n2 + n3;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   conv_stem_fused_kernel<<<p.cta_first[4], SF_THREADS, stem_fused_smem_bytes(), (cudaStream_t)stream>>>(
-      x_nchw, p, reinterpret_cast<const uint4*>(w_classes), bias, reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
+      reinterpret_cast<const uint32_t*>(x_bf16_padded), p, reinterpret_cast<const uint4*>(w_classes), bias,
+      reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }
@@ -284,7 +291,7 @@ extern "C" int yad_conv_stem_fused_fixup(const float* x_nchw, int64_t B, int32_t
   for (int i = 0; i < 8; ++i) p.col[i] = i < n_cols ? cols[i] : 0, p.var[i] = i < n_cols ? col_var[i] : 0;
   const int rcls[8] = {1, 2, 0, 0, 0, 0, 0, 3};
   for (int i = 0; i < 8; ++i) p.row_class[i] = rcls[i];
-  stem_fixup_kernel<<<dim3((unsigned)n_cols, (unsigned)B), 512, 0, (cudaStream_t)stream>>>(x_nchw, p, w_var, bias,
+  stem_fixup_kernel<<<dim3((unsigned)n_cols, (unsigned)((B + FX_CLIPS - 1) / FX_CLIPS)), 512, 0, (cudaStream_t)stream>>>(x_nchw, p, w_var, bias,
                                                                                          reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
   YAD_LAUNCH_CHECK();
   return YAD_OK;

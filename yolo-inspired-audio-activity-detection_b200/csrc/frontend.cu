@@ -519,7 +519,7 @@ __device__ __forceinline__ Tv block_reduce_n(Tv v, Tv* scratch, Op op, Tv ident)
 __global__ void __launch_bounds__(FB2_MAXT, 1)
 frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, const float* __restrict__ dct, float top_db,
                           int standardise, float* __restrict__ xs, float* __restrict__ tap_meldb, float* __restrict__ tap_mfcc,
-                          float* __restrict__ tap_mfdb) {
+                          float* __restrict__ tap_mfdb, uint32_t* __restrict__ xs_bf16, int64_t bf_pitch, int bf_margin) {
   extern __shared__ __align__(16) float fb2_smem[];
   float* s_dct = fb2_smem;                       // [32][32]
   float* s_x = fb2_smem + FE_NMEL * FE_NMEL;     // [32][T]
@@ -600,16 +600,19 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
     // 4: standardise and write both planes once
     const float den0 = sd0 + 1e-5f, den1 = sd1 + 1e-5f;
     if (act) {
-#pragma unroll 8
+#pragma unroll
       for (int m = 0; m < FE_NMEL; ++m) {
         const float x = s_x[m * T + t];
         if (tap_meldb) tap_meldb[(b * FE_NMEL + m) * T + t] = x;
-        o0[m * T + t] = standardise ? __fdiv_rn(x - mu0, den0) : x;
-      }
-#pragma unroll
-      for (int k = 0; k < FE_NMEL; ++k) {
-        if (tap_mfdb) tap_mfdb[(b * FE_NMEL + k) * T + t] = mf[k];
-        o1[k * T + t] = standardise ? __fdiv_rn(mf[k] - mu1, den1) : mf[k];
+        if (tap_mfdb) tap_mfdb[(b * FE_NMEL + m) * T + t] = mf[m];
+        const float v0 = standardise ? __fdiv_rn(x - mu0, den0) : x;
+        const float v1 = standardise ? __fdiv_rn(mf[m] - mu1, den1) : mf[m];
+        o0[m * T + t] = v0;
+        o1[m * T + t] = v1;
+        if (xs_bf16 != nullptr) {      // channel-interleaved bf16 copy with zero margins: the fused stem's patch rows (bulk-copied)
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          xs_bf16[(b * FE_NMEL + m) * bf_pitch + bf_margin + t] = *reinterpret_cast<uint32_t*>(&h2);
+        }
       }
     }
     __syncthreads();     // s_x is reused by the next clip
@@ -707,9 +710,12 @@ int yad_frontend_mel_power_i16(const int16_t* pcm, int64_t B, int64_t L, int32_t
                            fb_nnz, mel, T, stream);
 }
 
-int yad_frontend_finish(const float* mel, int64_t B, int64_t T, const float* dct, float top_db, int32_t standardise,
-                        float* x_spectral, float* tap_meldb, float* tap_mfcc, float* tap_mfdb, yad_stream_t stream) {
+static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const float* dct, float top_db, int32_t standardise,
+                                float* x_spectral, float* tap_meldb, float* tap_mfcc, float* tap_mfdb, void* xs_bf16, int64_t bf_pitch,
+                                int32_t bf_margin, yad_stream_t stream) {
   YAD_CHECK_ARG(mel && dct && x_spectral && T >= 2 && B >= 0, "yad_frontend_finish: bad arguments");
+  YAD_CHECK_ARG(xs_bf16 == nullptr || (T <= yad::FB2_MAXT && bf_margin >= 0 && bf_pitch >= bf_margin + T),
+                "yad_frontend_finish_bf16: needs T <= %d and pitch >= margin + T", yad::FB2_MAXT);
   if (B == 0) return YAD_OK;
   if (T <= yad::FB2_MAXT) {     // one-pass form: thread = frame, dB-mel column in shared memory, MFCC column in registers
     const int nsm = yad::sm_count() > 0 ? yad::sm_count() : 148;
@@ -717,7 +723,8 @@ int yad_frontend_finish(const float* mel, int64_t B, int64_t T, const float* dct
     const unsigned threads = (unsigned)((T + 31) / 32 * 32);
     const size_t smem = (size_t)(yad::FE_NMEL * yad::FE_NMEL + yad::FE_NMEL * T) * sizeof(float);
     yad::frontend_finish_v2_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(mel, B, T, dct, top_db, standardise, x_spectral,
-                                                                                tap_meldb, tap_mfcc, tap_mfdb);
+                                                                                tap_meldb, tap_mfcc, tap_mfdb,
+                                                                                reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, bf_margin);
     YAD_LAUNCH_CHECK();
     return YAD_OK;
   }
@@ -725,6 +732,19 @@ int yad_frontend_finish(const float* mel, int64_t B, int64_t T, const float* dct
       mel, T, dct, top_db, standardise, x_spectral, tap_meldb, tap_mfcc, tap_mfdb);
   YAD_LAUNCH_CHECK();
   return YAD_OK;
+}
+
+int yad_frontend_finish(const float* mel, int64_t B, int64_t T, const float* dct, float top_db, int32_t standardise,
+                        float* x_spectral, float* tap_meldb, float* tap_mfcc, float* tap_mfdb, yad_stream_t stream) {
+  return frontend_finish_impl(mel, B, T, dct, top_db, standardise, x_spectral, tap_meldb, tap_mfcc, tap_mfdb, nullptr, 0, 0, stream);
+}
+
+int yad_frontend_finish_bf16(const float* mel, int64_t B, int64_t T, const float* dct, float top_db, int32_t standardise,
+                             float* x_spectral, float* tap_meldb, float* tap_mfcc, float* tap_mfdb, void* xs_bf16, int64_t bf_pitch,
+                             int32_t bf_margin, yad_stream_t stream) {
+  YAD_CHECK_ARG(xs_bf16 != nullptr, "yad_frontend_finish_bf16: null pointer");
+  return frontend_finish_impl(mel, B, T, dct, top_db, standardise, x_spectral, tap_meldb, tap_mfcc, tap_mfdb, xs_bf16, bf_pitch, bf_margin,
+                              stream);
 }
 
 }  // extern "C"

@@ -421,9 +421,21 @@ class InferenceEngine:
         if taps is not None:
             for k in ("meldb", "mfcc", "mfdb"):
                 tm[k] = torch.empty((B, 1, 32, T), device=self.dev, dtype=torch.float32)
-        rc = self.lib.yad_frontend_finish(mel.data_ptr(), B, T, self.dct.data_ptr(), 80.0, 1 if self.cfg["scale_input"] else 0,
-                                          xs.data_ptr(), _lib.ptr(tm.get("meldb")), _lib.ptr(tm.get("mfcc")),
-                                          _lib.ptr(tm.get("mfdb")), self._stream())
+        if getattr(self, "fused_stem", False) and T <= 1024:
+            # x_spectral a second time as padded channel-interleaved bf16 words: the patch rows of the fused stem (bulk copies)
+            xb = plan.get("xs_bf16")
+            if xb is None:
+                W1 = (T - 1) // 2 + 1
+                n_seg = (((W1 - 1) // 2 + 1) + 127) // 128
+                pitch = _ceil(max(512 * (n_seg - 1) + 536, 9 + T), 4)
+                xb = plan["xs_bf16"] = torch.zeros((B, 32, pitch), device=self.dev, dtype=torch.int32)
+            rc = self.lib.yad_frontend_finish_bf16(mel.data_ptr(), B, T, self.dct.data_ptr(), 80.0, 1 if self.cfg["scale_input"] else 0,
+                                                   xs.data_ptr(), _lib.ptr(tm.get("meldb")), _lib.ptr(tm.get("mfcc")),
+                                                   _lib.ptr(tm.get("mfdb")), xb.data_ptr(), xb.shape[2], 9, self._stream())
+        else:
+            rc = self.lib.yad_frontend_finish(mel.data_ptr(), B, T, self.dct.data_ptr(), 80.0, 1 if self.cfg["scale_input"] else 0,
+                                              xs.data_ptr(), _lib.ptr(tm.get("meldb")), _lib.ptr(tm.get("mfcc")),
+                                              _lib.ptr(tm.get("mfdb")), self._stream())
         _lib.check(rc, "frontend_finish")
         if taps is not None:
             taps.update(tm)
@@ -449,10 +461,11 @@ class InferenceEngine:
             # stride-1 flat conv with 49 (plane, shift) steps; backbone activations stay in the flat layout (conv_flat.cu)
             H2, W2 = (H1 + 1) // 2, (W1 + 1) // 2
             assert (H2, W2) == (H, W)
-            if self.fused_stem and H0 == 32 and T >= 32:
+            if self.fused_stem and H0 == 32 and 32 <= T <= 1024 and "xs_bf16" in plan:
                 cur = self._flat_buf(plan, "c2", B, H, W, 64)
                 Hp, Wp = self._flat_geom(H, W)
-                _lib.check(self.lib.yad_conv_stem_fused(xs.data_ptr(), B, H0, T, self.fstem_w.data_ptr(), self.fstem_bias.data_ptr(),
+                xb = plan["xs_bf16"]
+                _lib.check(self.lib.yad_conv_stem_fused(xb.data_ptr(), xb.shape[2], B, H0, T, self.fstem_w.data_ptr(), self.fstem_bias.data_ptr(),
                                                         cur.data_ptr(), Hp, Wp, int(os.environ.get("YAD_STEM_NINT", "0")), s()),
                            "conv_stem_fused")
                 fx = plan.get("fstem_cols")
