@@ -31,8 +31,8 @@ CLIP_SAMPLES = 1323000
 FRONTEND_BYTES_PER_CLIP = 4 * CLIP_SAMPLES + 2 * 32 * 960 * 4          # PCM read + feature write (whole frontend)
 MEL_KERNEL_BYTES_PER_CLIP = 4 * CLIP_SAMPLES + 32 * 960 * 4            # frontend_mel_kernel alone: PCM read + mel-power write
 # dram__bytes_read.sum + dram__bytes_write.sum of frontend_mel_kernel per clip, from the ncu --set full capture
-# profiles/r01_ncu_full_frontend_mel_b64_v3.txt (338.81 MB + 9.05 MB over 64 clips)
-MEL_KERNEL_TRAFFIC_PER_CLIP = (338812672 + 9049088) / 64
+# profiles/r01_ncu_full_frontend_mel_b512_v7.txt (2.709669 GB + 65.228 MB over 512 clips)
+MEL_KERNEL_TRAFFIC_PER_CLIP = (2709669000 + 65228288) / 512
 CNN_FLOP_PER_CLIP = 2 * 1150923632                                     # useful MACs, deploy form
 METRIC = "audio-seconds/sec (mel+RepVGG fwd+decode/NMS)"
 
@@ -501,8 +501,9 @@ def main():
         roof = {"kernel": "frontend_mel_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": MEL_KERNEL_TRAFFIC_PER_CLIP * B, "peak_source": peaks["source"],
                 "algorithmic_bytes_per_launch": MEL_KERNEL_BYTES_PER_CLIP * B, "launch_ms": fe_ms,
-                "note": "achieved = (PCM read + mel write) / CUDA-event time of the launch; the kernel is FP32-issue bound "
-                        "(~24.8 k warp instructions per 8-frame group), not HBM bound - see DESIGN.md"}
+                "note": "achieved = (PCM read + mel write) / CUDA-event time of the launch; DRAM traffic = algorithmic bytes; the kernel "
+                        "is bound by shared-memory wavefronts / latency (l1tex 73 %, issue 48 %, fma pipe 48 %; 13.8 k warp "
+                        "instructions per 8-frame group after packing the arithmetic into FFMA2 / FADD2), not by HBM - see DESIGN.md"}
         roof["frontend_hbm"] = {"achieved_gbs": FRONTEND_BYTES_PER_CLIP * B / (fe_ms / 1e3) / 1e9,
                                 "frac": FRONTEND_BYTES_PER_CLIP * B / (fe_ms / 1e3) / 1e9 / peaks["hbm_gbs"]}
         roof["cnn_tensor"] = {"achieved_tflops": CNN_FLOP_PER_CLIP * B / (conv_ms / 1e3) / 1e12,
@@ -511,10 +512,10 @@ def main():
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic",
                 "config": {"workload": f"full pipeline, deploy-form (reparameterised) net, {B} clips x 60 s per GPU per step: PCM f32 -> "
-                                       "fused resample/log-mel/MFCC frontend -> stem + ResNet-18 + RepBi-PAN (tcgen05 implicit GEMM) -> "
+                                       "fused resample/log-mel/MFCC frontend -> fused stem (conv1 o conv2) + ResNet-18 + RepBi-PAN (tcgen05 implicit GEMM) -> "
                                        "anchor decode -> per-clip segment NMS (BASELINE configs[1]+[2] chained)",
                            "clips_per_gpu": B, "clip_seconds": CLIP_SECONDS, "num_classes": 2,
-                           "l2_policy": "inputs (2.7 GB PCM + 1.3 GB activations per step) are larger than the 126 MB L2",
+                           "l2_policy": "inputs (2.7 GB PCM + 0.8 GB activations per step) are larger than the 126 MB L2",
                            "parallelism": f"clip-sharded x{world}, no data-path collective"},
                 "e2e": e2e, "e2e_int16": e2e_i16, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
                 "clocks": sampler.summary(), "roofline": roof, "stages_ms": st}

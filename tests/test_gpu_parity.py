@@ -684,3 +684,28 @@ def test_fused_stem_vs_two_convs(B, T, cuda_dev):
     assert err.mean().item() < 2e-3 * scale
     # the halo cells stay zero
     assert out[:, Wo:, :, :].abs().max().item() == 0 and out[:, :, Ho:, :].abs().max().item() == 0
+
+
+def test_recorded_call_list_replay(models, cuda_dev):
+    """The first forward of a (batch, length) plan records its C-ABI calls; later forwards replay them with the input pointer,
+    the output and the stream patched in.  Replays must equal a fresh engine's first run bit for bit, also on another tensor
+    and on another stream."""
+    m = models[("deploy", "bf16")]
+    xa = synth.synth_clips(2, 22050 * 6, seed=501, silence_tail_every=0).to(cuda_dev)
+    xb = synth.synth_clips(2, 22050 * 6, seed=502, silence_tail_every=0).to(cuda_dev)
+    m._engine_cache.clear()
+    first_a = m(xa, combine_scales=True).clone()            # recorded run
+    eng = m._engine()
+    assert any(isinstance(k, tuple) and k[0] == "prog" for k in eng._plan((2, 22050 * 6)))
+    rep_a = m(xa, combine_scales=True).clone()              # replay, same tensor
+    rep_b = m(xb, combine_scales=True).clone()              # replay, other tensor
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        rep_a2 = m(xa, combine_scales=True).clone()         # replay on another stream
+    side.synchronize()
+    m._engine_cache.clear()
+    first_b = m(xb, combine_scales=True).clone()            # fresh engine, recorded run on the other tensor
+    torch.cuda.synchronize()
+    assert torch.equal(first_a, rep_a) and torch.equal(first_a, rep_a2) and torch.equal(first_b, rep_b)
+    assert not torch.equal(first_a, first_b)

@@ -98,17 +98,20 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
   uint32_t phase = 0;
   const int n_tiles = p.B * p.n_seg;
 
+  auto issue_fill = [&](int tl) {
+    const int sg = tl % p.n_seg, bb = tl / p.n_seg;
+    mbar_expect_tx(fill_bar, (uint32_t)prow * SF_ROWB);
+    const uint32_t* src = xb + ((int64_t)bb * p.H + hi_lo) * p.xpitch + 4 * sg * SF_SEG;
+    for (int rr = 0; rr < prow; ++rr) sf_bulk_g2s(sP + rr * SF_ROWB, src + (int64_t)rr * p.xpitch, SF_ROWB, fill_bar);
+  };
   for (int tile = cta_in_cls; tile < n_tiles; tile += n_cta_cls) {
     const int seg = tile % p.n_seg, b = tile / p.n_seg;
     const int wo0 = seg * SF_SEG;
     // (1) patch rows: the input lives as channel-interleaved bf16 words with a 9-word zero margin on the left (and zeros on the
     //     right), so the window row of this segment is the 16-byte aligned span [4 wo0, 4 wo0 + SF_PW) of the padded row: one
     //     bulk copy per input row, no bounds logic.  Rows outside the image are not loaded (their MMAs are skipped).
-    if (tid == 0) {
-      mbar_expect_tx(fill_bar, (uint32_t)prow * SF_ROWB);
-      const uint32_t* src = xb + ((int64_t)b * p.H + hi_lo) * p.xpitch + 4 * wo0;
-      for (int rr = 0; rr < prow; ++rr) sf_bulk_g2s(sP + rr * SF_ROWB, src + (int64_t)rr * p.xpitch, SF_ROWB, fill_bar);
-    }
+    //     The copies of the NEXT tile are issued as soon as this tile's MMAs have finished (they overlap the epilogue).
+    if (tid == 0 && tile == cta_in_cls) issue_fill(tile);
     mbar_wait(fill_bar, phase);
     // (2) MMAs: one accumulator per output row of the class; kernel rows whose input row is outside the image are skipped
     if (warp == 0) {
@@ -137,6 +140,7 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
     mbar_wait(mma_bar, phase);
     phase ^= 1;
     tc_fence_after();
+    if (tid == 0 && tile + n_cta_cls < n_tiles) issue_fill(tile + n_cta_cls);   // the patch is free: the MMAs that read it are done
     // (3) epilogue: bias + ReLU, bf16, flat halo layout; thread = (pixel r, 32-channel half); the rows of a class are adjacent
     //     in memory (h fastest), so a thread's stores of consecutive rows are contiguous
     const int wo = wo0 + r;
@@ -176,12 +180,13 @@ struct StemFixupParams {
   int32_t row_class[8];          // row class of output rows 0..7
 };
 
-constexpr int FX_CLIPS = 8;      // clips per CTA: every composite weight is fetched once per 8 clips (the kernel is bound by them)
+constexpr int FX_CLIPS = 8;      // clips per CTA: every composite weight is fetched once per 8 clips
+constexpr int FX_THREADS = 256;  // thread = (output row 0..7, channel quad 0..15, clip half 0..1): 4 channels x 4 clips of accumulators
 
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(FX_THREADS, 2)
 stem_fixup_kernel(const float* __restrict__ x, const StemFixupParams p, const float* __restrict__ w_var,
                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
-  __shared__ float s_x[FX_CLIPS][2][32][SF_KD + 1];
+  __shared__ float s_x[2][32][SF_KD + 1][FX_CLIPS];        // clip fastest: the 4 clips of a thread are one 16-byte load
   const int ci = blockIdx.x, b0 = blockIdx.y * FX_CLIPS;
   const int nb = min(FX_CLIPS, p.B - b0);
   const int wo = p.col[ci], var = p.var[ci];
@@ -189,26 +194,45 @@ stem_fixup_kernel(const float* __restrict__ x, const StemFixupParams p, const fl
   for (int i = tid; i < FX_CLIPS * 2 * 32 * SF_KD; i += blockDim.x) {
     const int dw = i % SF_KD, hi = (i / SF_KD) % 32, c = (i / (SF_KD * 32)) % 2, bb = i / (SF_KD * 32 * 2);
     const int wi = 4 * wo - 9 + dw;
-    s_x[bb][c][hi][dw] = (bb < nb && hi < p.H && wi >= 0 && wi < p.W) ? x[(((int64_t)(b0 + bb) * 2 + c) * p.H + hi) * p.W + wi] : 0.0f;
+    s_x[c][hi][dw][bb] = (bb < nb && hi < p.H && wi >= 0 && wi < p.W) ? x[(((int64_t)(b0 + bb) * 2 + c) * p.H + hi) * p.W + wi] : 0.0f;
   }
   __syncthreads();
-  const int co = tid & 63, ho = tid >> 6;
+  const int q4 = (tid & 15) * 4, half = (tid >> 4) & 1, ho = tid >> 5;
   if (ho >= p.Ho) return;
-  const float* wv = w_var + ((size_t)(var * 4 + p.row_class[ho]) * SF_KD * SF_KD * 2) * 64 + co;
-  float acc[FX_CLIPS];
+  const float* wv = w_var + ((size_t)(var * 4 + p.row_class[ho]) * SF_KD * SF_KD * 2) * 64 + q4;
+  float acc[4][4];     // [clip][channel]
 #pragma unroll
-  for (int bb = 0; bb < FX_CLIPS; ++bb) acc[bb] = bias[co];
+  for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[bb][e] = bias[q4 + e];
   for (int dh = 0; dh < SF_KD; ++dh) {
     const int hi = 4 * ho - 9 + dh;
     if (hi < 0 || hi >= p.H) continue;
     for (int dw = 0; dw < SF_KD; ++dw) {
-      const float w0 = __ldg(wv + ((dh * SF_KD + dw) * 2 + 0) * 64), w1 = __ldg(wv + ((dh * SF_KD + dw) * 2 + 1) * 64);
 #pragma unroll
-      for (int bb = 0; bb < FX_CLIPS; ++bb) acc[bb] = fmaf(s_x[bb][1][hi][dw], w1, fmaf(s_x[bb][0][hi][dw], w0, acc[bb]));
+      for (int c = 0; c < 2; ++c) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wv + ((dh * SF_KD + dw) * 2 + c) * 64));
+        const float4 xv = *reinterpret_cast<const float4*>(&s_x[c][hi][dw][half * 4]);
+        const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          acc[bb][0] = fmaf(xs4[bb], w.x, acc[bb][0]);
+          acc[bb][1] = fmaf(xs4[bb], w.y, acc[bb][1]);
+          acc[bb][2] = fmaf(xs4[bb], w.z, acc[bb][2]);
+          acc[bb][3] = fmaf(xs4[bb], w.w, acc[bb][3]);
+        }
+      }
     }
   }
-  for (int bb = 0; bb < nb; ++bb)
-    out[(((int64_t)(b0 + bb) * p.Wp + wo) * p.Hp + ho) * 64 + co] = __float2bfloat16_rn(fmaxf(acc[bb], 0.0f));
+#pragma unroll
+  for (int bb = 0; bb < 4; ++bb) {
+    const int bl = half * 4 + bb;
+    if (bl >= nb) continue;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(acc[bb][0], 0.0f), fmaxf(acc[bb][1], 0.0f));
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(acc[bb][2], 0.0f), fmaxf(acc[bb][3], 0.0f));
+    uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(out + (((int64_t)(b0 + bl) * p.Wp + wo) * p.Hp + ho) * 64 + q4) = o;
+  }
 }
 
 static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + 64; }
@@ -253,7 +277,7 @@ extern "C" int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, i
   for (int i = 0; i < 4; ++i) p.row_first[i] = rf[i], p.row_cnt[i] = rc[i];
   const int nsm = sm_count() > 0 ? sm_count() : 148;
   const int64_t n_tiles = B * p.n_seg;
-  int n_int = n_cta_interior > 0 ? n_cta_interior : (nsm * 57) / 100;      // measured balance point of the four classes
+  int n_int = n_cta_interior > 0 ? n_cta_interior : (nsm * 62) / 100;      // measured balance point of the four classes (tools/stem_sweep.py)
   if (n_int > nsm - 3) n_int = nsm - 3;
   if (n_int < 1) n_int = 1;
   int rest = nsm - n_int;
@@ -291,7 +315,7 @@ extern "C" int yad_conv_stem_fused_fixup(const float* x_nchw, int64_t B, int32_t
   for (int i = 0; i < 8; ++i) p.col[i] = i < n_cols ? cols[i] : 0, p.var[i] = i < n_cols ? col_var[i] : 0;
   const int rcls[8] = {1, 2, 0, 0, 0, 0, 0, 3};
   for (int i = 0; i < 8; ++i) p.row_class[i] = rcls[i];
-  stem_fixup_kernel<<<dim3((unsigned)n_cols, (unsigned)((B + FX_CLIPS - 1) / FX_CLIPS)), 512, 0, (cudaStream_t)stream>>>(x_nchw, p, w_var, bias,
+  stem_fixup_kernel<<<dim3((unsigned)n_cols, (unsigned)((B + FX_CLIPS - 1) / FX_CLIPS)), FX_THREADS, 0, (cudaStream_t)stream>>>(x_nchw, p, w_var, bias,
                                                                                          reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
   YAD_LAUNCH_CHECK();
   return YAD_OK;

@@ -36,13 +36,19 @@ __global__ void hmean_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
   const __nv_bfloat16* p0 = in + (b * isb + w * isw) * (int64_t)ld_in + c;
-  for (int h = 0; h < H; ++h) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p0 + h * ish * (int64_t)ld_in));
-    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+  for (int h0 = 0; h0 < H; h0 += 8) {          // up to 8 independent 16-byte loads in flight per thread (H = 8, 4, 2)
+    uint4 u[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      acc[2 * e] += __uint_as_float(ww[e] << 16);
-      acc[2 * e + 1] += __uint_as_float(ww[e] & 0xffff0000u);
+    for (int j = 0; j < 8; ++j)
+      u[j] = h0 + j < H ? __ldg(reinterpret_cast<const uint4*>(p0 + (h0 + j) * ish * (int64_t)ld_in)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t ww[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] += __uint_as_float(ww[e] << 16);
+        acc[2 * e + 1] += __uint_as_float(ww[e] & 0xffff0000u);
+      }
     }
   }
   const float inv = 1.0f / (float)H;
