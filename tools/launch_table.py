@@ -8,7 +8,7 @@ for row in csv.DictReader(lines):
     d.setdefault(int(row['ID']), {'name': row['Kernel Name'].split('(')[0].replace('void ', '')[:24], 'grid': row['Grid Size']})[row['Metric Name']] = float(row['Metric Value'].replace(',', ''))
 ids = sorted(d)
 starts = [i for i in ids if d[i]['name'].startswith('frontend_mel')]
-lo = starts[-2] if len(starts) > 1 and max(ids) - starts[-1] < 50 else starts[-1]
+lo = starts[-2] if len(starts) > 1 and max(ids) - starts[-1] < 40 else starts[-1]
 hi = starts[starts.index(lo) + 1] if starts.index(lo) + 1 < len(starts) else max(ids) + 1
 tot = 0
 for i in ids:
