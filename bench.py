@@ -33,7 +33,10 @@ MEL_KERNEL_BYTES_PER_CLIP = 4 * CLIP_SAMPLES + 32 * 960 * 4            # fronten
 # dram__bytes_read.sum + dram__bytes_write.sum of frontend_mel_kernel per clip, from the ncu --set full capture
 # profiles/r01_ncu_full_frontend_mel_b512_v7.txt (2.709669 GB + 65.228 MB over 512 clips)
 MEL_KERNEL_TRAFFIC_PER_CLIP = (2709669000 + 65228288) / 512
-CNN_FLOP_PER_CLIP = 2 * 1150923632                                     # useful MACs, deploy form
+CNN_FLOP_PER_CLIP = 2 * 1150923632                                     # useful MACs of the reference graph, deploy form
+# executed by this implementation: conv1 (45.5 MMAC) and conv2 (342.8 MMAC) run as ONE composite 19x19 stride-4 convolution
+# (8 x 240 pixels x 722 taps x 64 channels = 88.7 MMAC)
+CNN_FLOP_EXECUTED_PER_CLIP = 2 * (1150923632 - 45500000 - 342800000 + 8 * 240 * 722 * 64)
 METRIC = "audio-seconds/sec (mel+RepVGG fwd+decode/NMS)"
 
 
@@ -510,8 +513,13 @@ def main():
                         "instructions per 8-frame group after packing the arithmetic into FFMA2 / FADD2), not by HBM - see DESIGN.md"}
         roof["frontend_hbm"] = {"achieved_gbs": FRONTEND_BYTES_PER_CLIP * B / (fe_ms / 1e3) / 1e9,
                                 "frac": FRONTEND_BYTES_PER_CLIP * B / (fe_ms / 1e3) / 1e9 / peaks["hbm_gbs"]}
-        roof["cnn_tensor"] = {"achieved_tflops": CNN_FLOP_PER_CLIP * B / (conv_ms / 1e3) / 1e12,
-                              "frac": CNN_FLOP_PER_CLIP * B / (conv_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]}
+        fused = getattr(model._engine(), "fused_stem", False)
+        flop = CNN_FLOP_EXECUTED_PER_CLIP if fused else CNN_FLOP_PER_CLIP
+        roof["cnn_tensor"] = {"achieved_tflops": flop * B / (conv_ms / 1e3) / 1e12,
+                              "frac": flop * B / (conv_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
+                              "reference_graph_tflops": CNN_FLOP_PER_CLIP * B / (conv_ms / 1e3) / 1e12,
+                              "note": "achieved = FLOPs this implementation executes (stem conv1 o conv2 composed: 1.70 instead of "
+                                      "2.30 GFLOP per clip) / CNN stage time; reference_graph_tflops credits the reference's FLOPs"}
         line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic",
