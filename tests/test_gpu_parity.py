@@ -709,3 +709,26 @@ def test_recorded_call_list_replay(models, cuda_dev):
     torch.cuda.synchronize()
     assert torch.equal(first_a, rep_a) and torch.equal(first_a, rep_a2) and torch.equal(first_b, rep_b)
     assert not torch.equal(first_a, first_b)
+
+
+@pytest.mark.parametrize("seconds", [2.0, 10.0, 22.0])
+def test_fused_stem_network_equals_two_conv_path(models, seconds, cuda_dev, monkeypatch):
+    """Whole bf16 network with the composed stem against the same network with conv1 and conv2 as separate tensor-core
+    convolutions (YAD_FUSED_STEM=0) at other clip lengths (T = 32, 160, 352 frames: one and two column segments, the shortest
+    input the net takes; the odd-width border variants are covered by test_fused_stem_vs_two_convs).  The two differ only by
+    bf16 rounding of the intermediate tensor / of the composite weights."""
+    m = models[("deploy", "bf16")]
+    L = int(22050 * seconds) // 4 * 4
+    x = synth.synth_clips(3, L, seed=900 + int(seconds), silence_tail_every=0).to(cuda_dev)
+    m._engine_cache.clear()
+    fused = m(x, combine_scales=True).clone()
+    assert m._engine().fused_stem
+    monkeypatch.setenv("YAD_FUSED_STEM", "0")
+    m._engine_cache.clear()
+    plain = m(x, combine_scales=True).clone()
+    assert not m._engine().fused_stem
+    monkeypatch.delenv("YAD_FUSED_STEM")
+    m._engine_cache.clear()
+    d = (fused - plain).abs()
+    assert d[..., :3].max().item() < 0.1 and d[..., :3].mean().item() < 0.01, (d[..., :3].max().item(), d[..., :3].mean().item())
+    assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
