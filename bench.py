@@ -50,25 +50,52 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled from the MAIN thread at the one
+    moment that does not disturb the measurement: right after the timed steps have been enqueued, while the GPU is still
+    executing them (the host runs many steps ahead of the device).  A background poller is the obvious alternative and was
+    measured to be harmful: every NVML / nvidia-smi query takes a driver lock that stalls kernel LAUNCHES for milliseconds -
+    with nvidia-smi every 0.2 s the 40 ms timed region read 3.99 or 4.6 ms per step depending on whether a query landed in it,
+    with NVML every 25 ms it read 6.4-9.2 ms.  Work that is already queued is not affected.  Uses NVML in-process
+    (nvidia_ml_py: the data source of `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`), falls back to
+    the nvidia-smi subprocess."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
-
-    def run(self):
-        while not self.stop_flag.is_set():
+        self.index, self.samples = index, []
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
             try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def sample(self):
+        """One sample; call it while the device is busy with already-enqueued work."""
+        try:
+            if self.nvml is not None:
+                n, h = self.nvml, self.handle
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+                get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(get(h))
+                act = lambda bit: "Active" if r & bit else "Not Active"   # noqa: E731
+                # nvml.h: HwSlowdown 0x8, HwThermalSlowdown 0x40, SwThermalSlowdown 0x20, SwPowerCap 0x4
+                self.samples.append([str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)])
+            else:
                 o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                    capture_output=True, text=True, timeout=5).stdout.strip()
                 if o:
                     self.samples.append([s.strip() for s in o.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            self.stop_flag.wait(0.2)
+        except Exception:  # noqa: BLE001
+            pass
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
@@ -76,7 +103,8 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi",
+                "when": "after the warm-up / timed / end-to-end steps were enqueued, while the device was executing them"}
 
 
 def synth_clips_device(B: int, dev, seed: int):
@@ -322,9 +350,13 @@ def run_train(args):
         return met
 
     sampler = ClockSampler(local)
-    sampler.start()
+    t_ramp = time.perf_counter()           # untimed clock ramp, see the inference workload
+    while time.perf_counter() - t_ramp < float(os.environ.get("YAD_BENCH_RAMP_S", "1.5")):
+        step(x, tg)
+        torch.cuda.synchronize()
     for _ in range(W):
         step(x, tg)
+    sampler.sample()            # warm-up steps still executing
     torch.cuda.synchronize()
     n0 = _lib.launch_count
     met = step(x, tg)
@@ -340,6 +372,7 @@ def run_train(args):
         met = step(x, tg)
     torch.cuda.nvtx.range_pop()
     e1.record()
+    sampler.sample()            # the timed steps are enqueued and still executing: a query now cannot stall a launch
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -359,7 +392,7 @@ def run_train(args):
     e1.record()
     torch.cuda.synchronize()
     ms_e = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
-    sampler.stop_flag.set(); sampler.join(timeout=3)
+    sampler.sample()
     if rank == 0:
         peaks = load_peaks()
         value = CLIP_SECONDS * B * world * K / (ms / 1e3)
@@ -430,10 +463,17 @@ def main():
         preds = model(inp, combine_scales=True)
         return yad_b200.nms_raw(preds, 0.1, 0.2)
 
-    sampler = ClockSampler(local)      # samples from the warm-up to the end of the end-to-end loop (all under load)
-    sampler.start()
+    sampler = ClockSampler(local)      # main-thread samples while enqueued work executes (warm-up, timed region, end-to-end loop)
+    # Untimed ramp before the W warm-up steps: a GPU that has been idle (fresh box, first process) needs on the order of a
+    # second of load to reach its full SM / memory clocks; with only W = 3 steps (12 ms) of warm-up the first bench on a fresh
+    # box read 5.2 ms per step and every later one 3.9 ms.
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < float(os.environ.get("YAD_BENCH_RAMP_S", "1.5")):
+        step(x)
+        torch.cuda.synchronize()
     for _ in range(W):
         step(x)
+    sampler.sample()
     torch.cuda.synchronize()
     n0 = _lib.launch_count
     step(x)
@@ -450,6 +490,7 @@ def main():
         r = step(x)
     torch.cuda.nvtx.range_pop()
     e1.record()
+    sampler.sample()            # the timed steps are enqueued and still executing: a query now cannot stall a launch
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -474,10 +515,9 @@ def main():
         if seg is not None:
             d2h = seg.numel() * 4 + bidx.numel() * 8 + 8
     e1.record()
+    sampler.sample()
     torch.cuda.synchronize()
     ms_e = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
-    sampler.stop_flag.set()
-    sampler.join(timeout=3)
     e2e = {"value": CLIP_SECONDS * B * world * Ke / (ms_e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": B * CLIP_SAMPLES * 4,
            "d2h_bytes_per_step": d2h, "steps": Ke}
     # the same call with 16-bit PCM host buffers (the sample format of audio files; x / 32768 inside the frontend kernel): half

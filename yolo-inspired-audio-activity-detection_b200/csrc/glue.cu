@@ -90,6 +90,84 @@ __global__ void resize_w_kernel(const T* __restrict__ in, int64_t B, int W, int 
   st_from_float(out + (b * Wo + wo) * (int64_t)ld_out + co_off + c, v);
 }
 
+// bf16 fast paths of the two kernels above and below: 8 channels (16 bytes) per thread, same arithmetic per element
+__device__ __forceinline__ void bf8_unpack(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float (&f)[8]) {
+  uint32_t o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    o[e] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void resize_w_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_t B, int W, int C8, int ld_in, int ci_off, int up,
+                                       __nv_bfloat16* __restrict__ out, int ld_out, int co_off) {
+  const int Wo = up ? 2 * W : W / 2;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * Wo * C8) return;
+  const int c = (int)(gid % C8) * 8;
+  const int64_t bw = gid / C8;
+  const int wo = (int)(bw % Wo);
+  const int64_t b = bw / Wo;
+  const __nv_bfloat16* row = in + b * W * (int64_t)ld_in + ci_off + c;
+  float a[8], nb[8], v[8];
+  if (up) {
+    const int k = wo >> 1;
+    const int k2 = (wo & 1) ? min(k + 1, W - 1) : max(k - 1, 0);
+    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)k * ld_in)), a);
+    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)k2 * ld_in)), nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (wo & 1) ? (0.75f * a[j] + 0.25f * nb[j]) : (0.25f * nb[j] + 0.75f * a[j]);
+  } else {
+    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(2 * wo) * ld_in)), a);
+    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)(2 * wo + 1) * ld_in)), nb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.5f * a[j] + 0.5f * nb[j];
+  }
+  *reinterpret_cast<uint4*>(out + (b * Wo + wo) * (int64_t)ld_out + co_off + c) = bf8_pack(v);
+}
+
+__global__ void sppf_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_t B, int W, int C8, int C, int ld_in, int ci_off,
+                                   __nv_bfloat16* __restrict__ out, int ld_out, int co_off) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= B * W * C8) return;
+  const int c = (int)(gid % C8) * 8;
+  const int64_t bw = gid / C8;
+  const int w = (int)(bw % W);
+  const int64_t b = bw / W;
+  const __nv_bfloat16* row = in + b * W * (int64_t)ld_in + ci_off + c;
+  float m1[8], m2[8], m3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m1[j] = m2[j] = m3[j] = -INFINITY;
+#pragma unroll
+  for (int d = -6; d <= 6; ++d) {
+    const int x = w + d;
+    if (x < 0 || x >= W) continue;
+    float v[8];
+    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(row + (int64_t)x * ld_in)), v);
+    const int ad = d < 0 ? -d : d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (ad <= 2) m1[j] = fmaxf(m1[j], v[j]);
+      if (ad <= 4) m2[j] = fmaxf(m2[j], v[j]);
+      m3[j] = fmaxf(m3[j], v[j]);
+    }
+  }
+  __nv_bfloat16* o = out + (b * W + w) * (int64_t)ld_out + co_off + c;
+  *reinterpret_cast<uint4*>(o) = bf8_pack(m1);
+  *reinterpret_cast<uint4*>(o + C) = bf8_pack(m2);
+  *reinterpret_cast<uint4*>(o + 2 * C) = bf8_pack(m3);
+}
+
 // three cascaded MaxPool2d(k=5, s=1, p=2) at H=1 == running max over windows of 5 / 9 / 13 (-inf padding)
 template <typename T>
 __global__ void sppf_kernel(const T* __restrict__ in, int64_t B, int W, int C, int ld_in, int ci_off,
@@ -209,6 +287,14 @@ int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C,
   const int64_t n = B * Wo * C;
   if (n == 0) return YAD_OK;
   const int threads = 256;
+  if (dtype == YAD_BF16 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ci_off % 8 == 0 && co_off % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    const int64_t n8 = B * Wo * (C / 8);
+    yad::resize_w_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)in, B, W, C / 8, ld_in, ci_off, up, (__nv_bfloat16*)out, ld_out, co_off);
+    YAD_LAUNCH_CHECK();
+    return YAD_OK;
+  }
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   YAD_DISPATCH_DTYPE(dtype, yad::resize_w_kernel, (const T*)in, B, W, C, ld_in, ci_off, up, (T*)out, ld_out, co_off);
   YAD_LAUNCH_CHECK();
@@ -223,6 +309,14 @@ int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t 
   const int64_t n = B * W * C;
   if (n == 0) return YAD_OK;
   const int threads = 256;
+  if (dtype == YAD_BF16 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ci_off % 8 == 0 && co_off % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    const int64_t n8 = B * W * (C / 8);
+    yad::sppf_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)in, B, W, C / 8, C, ld_in, ci_off, (__nv_bfloat16*)out, ld_out, co_off);
+    YAD_LAUNCH_CHECK();
+    return YAD_OK;
+  }
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   YAD_DISPATCH_DTYPE(dtype, yad::sppf_kernel, (const T*)in, B, W, C, ld_in, ci_off, (T*)out, ld_out, co_off);
   YAD_LAUNCH_CHECK();
