@@ -28,10 +28,11 @@ __global__ void hmean_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = B * W * C8;
   if (gid >= n) return;
-  const int c = (int)(gid % C8) * 8;
-  const int64_t bw = gid / C8;
-  const int w = (int)(bw % W);
-  const int64_t b = bw / W;
+  const uint32_t g32 = (uint32_t)gid;            // the host guarantees n < 2^32: 32-bit index arithmetic (64-bit div / mod
+  const int c = (int)(g32 % (uint32_t)C8) * 8;   // cost more than the loads of the small stages)
+  const uint32_t bw = g32 / (uint32_t)C8;
+  const int w = (int)(bw % (uint32_t)W);
+  const int64_t b = bw / (uint32_t)W;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
@@ -114,10 +115,11 @@ __global__ void resize_w_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int
   const int Wo = up ? 2 * W : W / 2;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * Wo * C8) return;
-  const int c = (int)(gid % C8) * 8;
-  const int64_t bw = gid / C8;
-  const int wo = (int)(bw % Wo);
-  const int64_t b = bw / Wo;
+  const uint32_t g32 = (uint32_t)gid;            // 32-bit index arithmetic (the host checks the element count)
+  const int c = (int)(g32 % (uint32_t)C8) * 8;
+  const uint32_t bw = g32 / (uint32_t)C8;
+  const int wo = (int)(bw % (uint32_t)Wo);
+  const int64_t b = bw / (uint32_t)Wo;
   const __nv_bfloat16* row = in + b * W * (int64_t)ld_in + ci_off + c;
   float a[8], nb[8], v[8];
   if (up) {
@@ -140,10 +142,11 @@ __global__ void sppf_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_t
                                    __nv_bfloat16* __restrict__ out, int ld_out, int co_off) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * W * C8) return;
-  const int c = (int)(gid % C8) * 8;
-  const int64_t bw = gid / C8;
-  const int w = (int)(bw % W);
-  const int64_t b = bw / W;
+  const uint32_t g32 = (uint32_t)gid;            // 32-bit index arithmetic (the host checks the element count)
+  const int c = (int)(g32 % (uint32_t)C8) * 8;
+  const uint32_t bw = g32 / (uint32_t)C8;
+  const int w = (int)(bw % (uint32_t)W);
+  const int64_t b = bw / (uint32_t)W;
   const __nv_bfloat16* row = in + b * W * (int64_t)ld_in + ci_off + c;
   float m1[8], m2[8], m3[8];
 #pragma unroll
@@ -264,6 +267,7 @@ int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, in
   if (dtype == YAD_BF16 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && co_off % 8 == 0 &&
       reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
     const int64_t n8 = B * W * (C / 8);
+    YAD_CHECK_ARG(n8 < (1ll << 32), "yad_hmean: tensor too large for the 32-bit index path");
     yad::hmean_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)in, B, H, W, C / 8, ld_in, (int64_t)in_sw, (int64_t)in_sh, (int64_t)in_sb, (__nv_bfloat16*)out,
         ld_out, co_off);
@@ -288,7 +292,7 @@ int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C,
   if (n == 0) return YAD_OK;
   const int threads = 256;
   if (dtype == YAD_BF16 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ci_off % 8 == 0 && co_off % 8 == 0 &&
-      reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+      reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && B * Wo * (int64_t)(C / 8) < (1ll << 32)) {
     const int64_t n8 = B * Wo * (C / 8);
     yad::resize_w_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)in, B, W, C / 8, ld_in, ci_off, up, (__nv_bfloat16*)out, ld_out, co_off);
@@ -310,7 +314,7 @@ int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t 
   if (n == 0) return YAD_OK;
   const int threads = 256;
   if (dtype == YAD_BF16 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ci_off % 8 == 0 && co_off % 8 == 0 &&
-      reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+      reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && B * W * (int64_t)(C / 8) < (1ll << 32)) {
     const int64_t n8 = B * W * (C / 8);
     yad::sppf_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)in, B, W, C / 8, C, ld_in, ci_off, (__nv_bfloat16*)out, ld_out, co_off);

@@ -348,6 +348,10 @@ class InferenceEngine:
         Wo = (W + 2 * cv.pw - cv.kw) // cv.sw + 1
         assert out.shape[0] == B and out.shape[1] == Ho and out.shape[2] == Wo, (cv.name, tuple(out.shape), (B, Ho, Wo))
         in_ptr = x.data_ptr() + cin_off * es
+        if not x.is_contiguous():      # strided pixel view (e.g. the H = 1 stage read straight out of its flat layout)
+            assert x.stride(3) == 1 and all(st % ld_in == 0 for st in x.stride()[:3]), (cv.name, x.stride())
+            d.in_sw, d.in_sh, d.in_sb = x.stride(2) // ld_in, x.stride(1) // ld_in, x.stride(0) // ld_in
+            assert self.dtype == BF16 and not cv.simt, "strided inputs are a tensor-core path feature"
         if self.dtype == BF16 and not cv.simt:
             assert cin_off + cv.cin_pad <= ld_in, (cv.name, cin_off, cv.cin_pad, ld_in)
             rc = self.lib.yad_conv_tc(C.byref(d), in_ptr, cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), _lib.ptr(res),
@@ -583,6 +587,12 @@ class InferenceEngine:
             ldf = f.shape[3]
             if not pool_first or (Hf == 1 and not fast):
                 pooled.append(f)
+                continue
+            if Hf == 1 and fast:
+                # the flat layout of an H = 1 stage is already [B, Wp, 1, ld]: the mean is the identity, the neck's 1x1 convs read
+                # it in place through a strided view (batch pitch Wp pixels) instead of a copy kernel
+                Hpf, Wpf = self._flat_geom(Hf, Wf)
+                pooled.append(f.as_strided((B, 1, Wf, ldf), (Wpf * Hpf * ldf, Wpf * Hpf * ldf, Hpf * ldf, 1)))
                 continue
             pm = self._buf(plan, f"fm{i}", B, 1, Wf, ldf)
             if fast:
