@@ -546,9 +546,9 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
     }
     const float floor1 = to_db(block_reduce_n<float>(mx, s_redf, fmax_op, 0.0f)) - top_db;
     // 2: clamped dB-mel (parked in smem), MFCC column in registers, moments of the dB-mel plane
-    float mf[FE_NMEL];
+    float2 mf2[FE_NMEL / 2];       // MFCC column as register pairs: the DCT advances two coefficients per FFMA2
 #pragma unroll
-    for (int k = 0; k < FE_NMEL; ++k) mf[k] = 0.0f;
+    for (int k = 0; k < FE_NMEL / 2; ++k) mf2[k] = make_float2(0.0f, 0.0f);
     double s0 = 0.0, q0 = 0.0;
     float mxf = -INFINITY;
     if (act) {
@@ -561,12 +561,14 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
 #pragma unroll
         for (int k4 = 0; k4 < FE_NMEL / 4; ++k4) {
           const float4 d4 = dr[k4];
-          mf[k4 * 4 + 0] = fmaf(x, d4.x, mf[k4 * 4 + 0]);
-          mf[k4 * 4 + 1] = fmaf(x, d4.y, mf[k4 * 4 + 1]);
-          mf[k4 * 4 + 2] = fmaf(x, d4.z, mf[k4 * 4 + 2]);
-          mf[k4 * 4 + 3] = fmaf(x, d4.w, mf[k4 * 4 + 3]);
+          const float2 xx = make_float2(x, x);
+          mf2[k4 * 2 + 0] = __ffma2_rn(xx, make_float2(d4.x, d4.y), mf2[k4 * 2 + 0]);
+          mf2[k4 * 2 + 1] = __ffma2_rn(xx, make_float2(d4.z, d4.w), mf2[k4 * 2 + 1]);
         }
       }
+    }
+    float* mf = reinterpret_cast<float*>(mf2);      // the same registers, scalar view (all indices below are compile-time)
+    if (act) {
 #pragma unroll
       for (int k = 0; k < FE_NMEL; ++k) {
         if (tap_mfcc) tap_mfcc[(b * FE_NMEL + k) * T + t] = mf[k];
