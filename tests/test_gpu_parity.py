@@ -732,3 +732,47 @@ def test_fused_stem_network_equals_two_conv_path(models, seconds, cuda_dev, monk
     d = (fused - plain).abs()
     assert d[..., :3].max().item() < 0.1 and d[..., :3].mean().item() < 0.01, (d[..., :3].max().item(), d[..., :3].mean().item())
     assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
+
+
+# ------------------------------------------------------------------ small kernels added for the 2-D neck / fused stem
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_maxpool_h_and_2d_sppf_vs_torch(dt, cuda_dev):
+    """yad_sppf_pools (W cascades, B*H rows) followed by yad_maxpool_h (box maxima over 5 / 9 / 13 rows) = three cascaded
+    F.max_pool2d(k=5, s=1, p=2) of the reference's CSPSPPFModule when the neck keeps its height (modules/_common.py:197,207-209)."""
+    lib = _lib.init(0)
+    tdt, code = (torch.float32, F32) if dt == "f32" else (torch.bfloat16, BF16)
+    B, H, W, Cc = 2, 32, 7, 64
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, H, W, Cc, generator=g).to(tdt).to(cuda_dev)
+    wp = torch.zeros(B, H, W, 192, device=cuda_dev, dtype=tdt)
+    out = torch.zeros(B, H, W, 256, device=cuda_dev, dtype=tdt)
+    out[..., :64] = x
+    _lib.check(lib.yad_sppf_pools(out.data_ptr(), code, B * H, W, 64, 256, 0, wp.data_ptr(), 192, 0, _stream()), "sppf")
+    for k in range(3):
+        _lib.check(lib.yad_maxpool_h(wp.data_ptr(), code, B, H, W, 64, 192, 64 * k, 2 * (k + 1), out.data_ptr(), 256, 64 * (k + 1), _stream()), "mph")
+    xn = x.float().permute(0, 3, 1, 2)
+    p1 = F.max_pool2d(xn, 5, 1, 2); p2 = F.max_pool2d(p1, 5, 1, 2); p3 = F.max_pool2d(p2, 5, 1, 2)
+    ref = torch.cat([xn, p1, p2, p3], 1).permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), ref)             # maxima of the same values: exact in both dtypes
+
+
+def test_nchw_to_nhwc_and_bf16_stage_b_copy(models, cuda_dev):
+    lib = _lib.init(0)
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(3, 2, 32, 50, generator=g).to(cuda_dev)
+    for tdt, code in ((torch.float32, F32), (torch.bfloat16, BF16)):
+        o = torch.zeros(3, 32, 50, 2, device=cuda_dev, dtype=tdt)
+        _lib.check(lib.yad_nchw_to_nhwc(x.data_ptr(), 3, 2, 32, 50, o.data_ptr(), code, 2, _stream()), "nchw_to_nhwc")
+        assert torch.equal(o, x.permute(0, 2, 3, 1).to(tdt))
+    # stage B's padded channel-interleaved bf16 copy = x_spectral rounded to bf16, margins untouched (zero)
+    m = models[("deploy", "bf16")]
+    clips = synth.synth_clips(2, 22050 * 6, seed=77, silence_tail_every=0).to(cuda_dev)
+    m._engine_cache.clear()
+    m(clips, combine_scales=True)
+    eng = m._engine()
+    plan = eng._plan((2, 22050 * 6))
+    xs, xb = plan["xs"], plan["xs_bf16"]
+    T = xs.shape[-1]
+    words = xb.view(torch.bfloat16).reshape(2, 32, xb.shape[2], 2)
+    assert torch.equal(words[:, :, 9:9 + T, :], xs.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert words[:, :, :9].abs().max().item() == 0 and words[:, :, 9 + T:].abs().max().item() == 0
