@@ -410,6 +410,13 @@ int yad_adam_ema_step(float* param, const float* grad, float* exp_avg, float* ex
                       int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                       int32_t step, float ema_momentum, yad_stream_t stream);
 
+/* Train step: every OIHW master weight -> the two K-major fp32 operands of the TF32 convolutions (forward / weight gradient
+ * [ceil16(O)][kh*kw][cin_pad] and data gradient [ceil16(I)][kh*kw][coutk]) in ONE launch (the parameters change every step:
+ * pipeline/_trainer.py:105).  table: DEVICE array of n_entries 56-byte records
+ *   { const float* src; float* wf; float* wt; int32 O, I, KK, cin_pad, coutk, pad; int64 start }   (start = prefix sum of O*I*KK),
+ * total_elems = sum of O*I*KK.  Pad rows / columns of wf, wt are not written (the caller zero-fills them once). */
+int yad_pack_weights_tf32(const void* table, int32_t n_entries, int64_t total_elems, yad_stream_t stream);
+
 /* ------------------------------------------------------------------ anchor clustering
  * Replaces the iterations of sklearn.cluster.KMeans(algorithm="lloyd") in compute_anchors.py:72-86 for 1-D data (the segment
  * durations), fp64, one CTA iterating to convergence on the device.

@@ -82,6 +82,7 @@ SIGNATURES = {
     "yad_wgrad_tf32": [C.POINTER(CorrDesc), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _p, _p, _p, _p],
     "yad_stem_im2col": [_p, _i64, _i32, _i32, _i32, _i32, _p, _p],
     "yad_colsum_f64": [_p, _i32, _i64, _i32, _p, _p],
+    "yad_pack_weights_tf32": [_p, _i32, _i64, _p],
     "yad_permute4": [_p, C.POINTER(_i64), _p, C.POINTER(_i32), _i32, _p],
     "yad_add_f64_to_f32": [_p, _i32, _p, _p],
     "yad_add_act": [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _i32, _p, _i32, _p],

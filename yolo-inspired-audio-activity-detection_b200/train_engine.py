@@ -82,6 +82,9 @@ class TrainEngine:
         self._seed_dev = torch.zeros(1, device=device, dtype=torch.int64)     # train-step counter (dropout seed offset)
         self._graphs: Dict[tuple, dict] = {}
         self._force_repack = False
+        self._bulk_packed = False          # the packed TF32 weights were refreshed by _bulk_pack() for the forward in progress
+        self._pack_entries: Dict = {}
+        self._pack_table = None
         self._bwd_arena, self._bwd_used, self._stats_arena, self._stats_used, self._act_numel = None, 0, None, 0, 0
         self._n_weights = sum(p.numel() for p in model.parameters())
         self._n_bn = sum(m.num_features for m in model.modules() if isinstance(m, nn.BatchNorm2d))
@@ -211,8 +214,8 @@ class TrainEngine:
         key = ("tf32", id(w))
         ver = (w._version, _lib.param_epoch, w.data_ptr(), cin_pad, coutk)
         ent = self._wcache.get(key)
-        if ent is not None and ent[0] == ver and not self._force_repack:
-            return ent[1], ent[2]
+        if ent is not None and (self._bulk_packed or (ent[0] == ver and not self._force_repack)):
+            return ent[1], ent[2]          # up to date (or refreshed by the one-launch bulk pack at the start of this forward)
         O, I, kh, kw = w.shape
         wd = w.detach()
         if ent is not None and ent[1].shape == (_c16(O), kh, kw, cin_pad) and ent[2].shape == (_c16(I), kh, kw, coutk):
@@ -223,7 +226,43 @@ class TrainEngine:
         wf[:O, :, :, :I].copy_(wd.permute(0, 2, 3, 1))
         wt[:I, :, :, :O].copy_(wd.permute(1, 2, 3, 0))
         self._wcache[key] = (ver, wf, wt)
+        self._pack_entries[key] = (w, wf, wt, cin_pad, coutk)
+        self._pack_table = None
         return wf, wt
+
+    def _ensure_pack_table(self):
+        """Device table of yad_pack_weights_tf32 (pointers + geometry of every convolution weight); call outside graph capture."""
+        import numpy as np
+        if not self._pack_entries:
+            return
+        ptrs = [w.data_ptr() for w, *_ in self._pack_entries.values()]
+        if self._pack_table is not None and self._pack_table[3] == ptrs:
+            return
+        dt = np.dtype([("src", "<u8"), ("wf", "<u8"), ("wt", "<u8"), ("O", "<i4"), ("I", "<i4"), ("KK", "<i4"), ("cin_pad", "<i4"),
+                       ("coutk", "<i4"), ("pad", "<i4"), ("start", "<i8")])
+        assert dt.itemsize == 56
+        tab = np.zeros(len(self._pack_entries), dt)
+        start = 0
+        for j, (w, wf, wt, cin_pad, coutk) in enumerate(self._pack_entries.values()):
+            O, I, kh, kw = w.shape
+            if not w.is_contiguous() or wf.shape[3] != cin_pad or wt.shape[3] != coutk:
+                self._pack_table = None
+                return
+            tab[j] = (w.data_ptr(), wf.data_ptr(), wt.data_ptr(), O, I, kh * kw, cin_pad, coutk, 0, start)
+            start += O * I * kh * kw
+        self._pack_table = (torch.from_numpy(tab.view(np.uint8).copy()).to(self.dev), len(tab), start, ptrs)
+
+    def _bulk_pack(self):
+        """Refresh every packed TF32 weight operand with ONE launch (yad_pack_weights_tf32) instead of two strided copies per
+        convolution; used when the step is captured into CUDA graphs (the parameters change every step, so the packing is part
+        of the graph).  The table holds device pointers: parameters and packed buffers must stay put, which the graphs need anyway."""
+        if self._pack_table is None:       # built outside graph capture (it needs a host -> device copy): _ensure_pack_table
+            return False
+        t, n, total, ptrs = self._pack_table
+        if ptrs != [w.data_ptr() for w, *_ in self._pack_entries.values()]:
+            return False
+        _lib.check(self.lib.yad_pack_weights_tf32(t.data_ptr(), n, total, self._s()), "pack_weights_tf32")
+        return True
 
     def _conv_tf32(self, x: _T, conv: nn.Conv2d, out: Optional[_T], need_dx: bool, stats: Optional[torch.Tensor] = None) -> _T:
         """tcgen05 kind::tf32 path: forward, data gradient (one correlation per output stride-parity class) and weight
@@ -447,6 +486,9 @@ class TrainEngine:
         [B,G,A,E], tape)."""
         model = self.model
         fe, ms = model.feature_extractor, model.multiscale_module
+        # graph capture: refresh all packed TF32 weights with one launch; the per-convolution copies are then skipped
+        self._bulk_packed = bool(self._force_repack and self.conv_mode == "tf32" and self._pack_entries
+                                 and os.environ.get("YAD_BULK_PACK", "1") != "0" and self._bulk_pack())
         self._tape: Optional[List[Callable[[], None]]] = [] if record else None
         self._grads: Dict[int, torch.Tensor] = {}
         self._bn_counters: List[torch.Tensor] = []
@@ -527,6 +569,7 @@ class TrainEngine:
                      "strides": [T // h.W for h in heads], "center_scaler": center_scaler, "dur": dur, "B": B,
                      "arena_numel": self._act_numel + self._n_weights + 4096 * 64}
         self._tape, self._grads = None, {}
+        self._bulk_packed = False
         return preds, state
 
     def backward(self, state, dpreds: List[Optional[torch.Tensor]]):
@@ -610,6 +653,7 @@ def _capture_train_graphs(model, eng: TrainEngine, fe, x: torch.Tensor) -> dict:
             p.grad = torch.zeros_like(p)
     g = {"x": torch.empty_like(x), "plan": {}, "fe": fe}      # `fe` owns the packed frontend constants the graph points into
     g["x"].copy_(x)
+    eng._ensure_pack_table()                   # host -> device copy: must happen before the capture starts
     torch.cuda.synchronize(eng.dev)
     pool = torch.cuda.graph_pool_handle()
     fwd, bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -628,6 +672,7 @@ def _capture_train_graphs(model, eng: TrainEngine, fe, x: torch.Tensor) -> dict:
     finally:
         eng._force_repack = False
     _lib.launch_count = n0
+    g["pack_table"] = eng._pack_table           # the captured pack kernel reads this device table: keep it alive with the graph
     g.update(fwd=fwd, bwd=bwd, preds=preds, state=state, fwd_launches=n1 - n0, bwd_launches=n2 - n1,
              grad_ptrs=[p.grad.data_ptr() for p in eng._params])
     return g
