@@ -199,7 +199,7 @@ def time_stages(model, x, reps=3):
     L_res = -(-eng.rs_P * L // eng.rs_O)
     out["decode_ms"], preds = timed(lambda: eng.run_decode(heads, B, T, L_res))
     import yad_b200
-    out["nms_ms"], _ = timed(lambda: yad_b200.nms_raw(preds, 0.1, 0.2))
+    out["nms_ms"], _ = timed(lambda: yad_b200.nms_raw(preds, 0.1, 0.2, want_keep=False))
     return out
 
 
@@ -461,7 +461,7 @@ def main():
 
     def step(inp):
         preds = model(inp, combine_scales=True)
-        return yad_b200.nms_raw(preds, 0.1, 0.2)
+        return yad_b200.nms_raw(preds, 0.1, 0.2, want_keep=False)   # what process_model_outputs runs (segments only)
 
     sampler = ClockSampler(local)      # main-thread samples while enqueued work executes (warm-up, timed region, end-to-end loop)
     # Untimed ramp before the W warm-up steps: a GPU that has been idle (fresh box, first process) needs on the order of a

@@ -260,8 +260,9 @@ int yad_decode_dev(const void* const* heads, const int32_t* G, const int32_t* ld
  * segments dressed as boxes of height _h; fp32 IoU; suppress iff iou > (double)thr; stable
  * descending score order; NaN never suppresses.
  *   preds      [B, P, 3+nc] f32 (P <= 1024)
- *   keep       [B, P] i32   kept local indices in descending score order (first n_keep[b] valid)
- *   n_keep     [B]    i32
+ *   keep       [B, P] i32   kept local indices in descending score order (first n_keep[b] valid); keep and n_keep may both
+ *   n_keep     [B]    i32   be NULL when only seg_rows is wanted: the greedy scan then stops at the first surviving box
+ *                           with conf <= conf_thr (lower-scored boxes cannot change the segments)
  *   conf/boxes [B, P] / [B, P, 2] f32  optional taps (may be NULL): confidence, clipped (x1,x2)
  *   seg_rows   [B, P, 5] f32  per clip: rows passing conf > conf_thr, sorted by centre ascending,
  *                             = [conf, obj_logit, label, start, end] (or centre,width if !start_end)

@@ -776,3 +776,18 @@ def test_nchw_to_nhwc_and_bf16_stage_b_copy(models, cuda_dev):
     words = xb.view(torch.bfloat16).reshape(2, 32, xb.shape[2], 2)
     assert torch.equal(words[:, :, 9:9 + T, :], xs.permute(0, 2, 3, 1).to(torch.bfloat16))
     assert words[:, :, :9].abs().max().item() == 0 and words[:, :, 9 + T:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("iou,cthr", [(0.1, 0.2), (0.05, 0.5), (0.1, 0.9999)])
+def test_nms_segments_only_equals_full_scan(gold, iou, cthr, cuda_dev):
+    """want_keep=False lets the greedy scan stop at the confidence threshold: the segments must be identical to the full scan's
+    (a box can only be suppressed by a higher-scored one, and the reference filters after the NMS: inference.py:75-88)."""
+    for seed, B in ((5, 4), (9, 2)):
+        o = synth.synth_heads(B, 630, 2, seed=seed).to(cuda_dev)
+        full = yad_b200.nms_raw(o, iou, cthr)
+        fast = yad_b200.nms_raw(o, iou, cthr, want_keep=False)
+        assert "keep" not in fast
+        assert torch.equal(full["n_seg"], fast["n_seg"])
+        for b in range(B):
+            n = int(full["n_seg"][b])
+            assert torch.equal(full["seg_rows"][b, :n], fast["seg_rows"][b, :n])

@@ -168,6 +168,10 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
     const int fw = __ffs(nz) - 1;
     const uint32_t fword = __shfl_sync(0xffffffffu, wrd, fw);
     const int i = (fw << 5) + (__ffs(fword) - 1);
+    // Without a keep list to report, the scan may stop at the first surviving box that fails the confidence filter: boxes
+    // are visited in descending score order and a box can only be suppressed by a higher-scored one, so nothing after this
+    // point can change which boxes with conf > conf_thr survive (inference.py:75-88 filters after the NMS).
+    if (keep_out == nullptr && !(s_conf[s_order[i]] > conf_thr)) break;
     if (threadIdx.x == 0) s_keep[nk] = i;
     ++nk;
     const float x1i = sx1[i], x2i = sx2[i], ai = sarea[i];
@@ -187,9 +191,11 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
     __syncthreads();
     cur = i + 1;
   }
-  for (int i = threadIdx.x; i < P; i += blockDim.x)
-    keep_out[(int64_t)b * P + i] = (i < nk) ? s_order[s_keep[i]] : -1;
-  if (threadIdx.x == 0) n_keep_out[b] = nk;
+  if (keep_out != nullptr) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+      keep_out[(int64_t)b * P + i] = (i < nk) ? s_order[s_keep[i]] : -1;
+    if (threadIdx.x == 0) n_keep_out[b] = nk;
+  }
   if (seg_rows == nullptr) return;
 
   // 4. confidence filter + per-clip sort by centre (inference.py:85-99)
@@ -340,7 +346,8 @@ int yad_decode_dev(const void* const* heads, const int32_t* G, const int32_t* ld
 int yad_nms(const float* preds, int64_t B, int32_t P, int32_t nc, double iou_thr, float conf_thr,
             float duration, float box_h, int32_t return_start_end, int32_t* keep, int32_t* n_keep,
             float* conf, float* boxes, float* seg_rows, int32_t* n_seg, yad_stream_t stream) {
-  YAD_CHECK_ARG(preds && keep && n_keep, "yad_nms: null preds/keep/n_keep");
+  YAD_CHECK_ARG(preds && ((keep == nullptr) == (n_keep == nullptr)) && (keep != nullptr || seg_rows != nullptr),
+                "yad_nms: null preds, or keep / n_keep not both given, or nothing to compute");
   YAD_CHECK_ARG(P >= 1 && P <= yad::NMS_MAXP, "yad_nms: P=%d not in [1,%d]", P, yad::NMS_MAXP);
   YAD_CHECK_ARG(nc >= 1 && nc <= 64, "yad_nms: nc=%d not in [1,64]", nc);
   YAD_CHECK_ARG((seg_rows == nullptr) == (n_seg == nullptr), "yad_nms: seg_rows and n_seg go together");

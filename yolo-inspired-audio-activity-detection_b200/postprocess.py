@@ -10,9 +10,11 @@ from . import _lib
 
 
 def nms_raw(outputs: torch.Tensor, iou_threshold: float, conf_threshold: float, sample_duration: float = 60,
-            return_start_end: bool = True, _h: float = 10, want_taps: bool = False) -> Dict[str, torch.Tensor]:
+            return_start_end: bool = True, _h: float = 10, want_taps: bool = False, want_keep: bool = True) -> Dict[str, torch.Tensor]:
     """Runs the per-clip NMS kernel and returns its raw device outputs:
-    keep [B,P] i32 (descending score, -1 padded), n_keep [B], seg_rows [B,P,5], n_seg [B] (+ conf/boxes taps)."""
+    keep [B,P] i32 (descending score, -1 padded), n_keep [B], seg_rows [B,P,5], n_seg [B] (+ conf/boxes taps).
+    ``want_keep=False`` (what ``process_model_outputs`` needs: the reference never returns the keep list) lets the kernel stop
+    its greedy scan at the confidence threshold."""
     if not outputs.is_cuda:
         raise RuntimeError("yad_b200.process_model_outputs needs a CUDA tensor (no CPU fallback)")
     if outputs.ndim != 3:
@@ -24,18 +26,19 @@ def nms_raw(outputs: torch.Tensor, iou_threshold: float, conf_threshold: float, 
     B, P, E = x.shape
     nc = E - 3
     r = {
-        "keep": torch.empty((B, P), device=dev, dtype=torch.int32),
-        "n_keep": torch.empty((B,), device=dev, dtype=torch.int32),
         "seg_rows": torch.empty((B, P, 5), device=dev, dtype=torch.float32),
         "n_seg": torch.empty((B,), device=dev, dtype=torch.int32),
     }
+    if want_keep:
+        r["keep"] = torch.empty((B, P), device=dev, dtype=torch.int32)
+        r["n_keep"] = torch.empty((B,), device=dev, dtype=torch.int32)
     if want_taps:
         r["conf"] = torch.empty((B, P), device=dev, dtype=torch.float32)
         r["boxes"] = torch.empty((B, P, 2), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         rc = lib.yad_nms(x.data_ptr(), B, P, nc, float(iou_threshold), float(conf_threshold), float(sample_duration), float(_h),
-                         1 if return_start_end else 0, r["keep"].data_ptr(), r["n_keep"].data_ptr(), _lib.ptr(r.get("conf")),
+                         1 if return_start_end else 0, _lib.ptr(r.get("keep")), _lib.ptr(r.get("n_keep")), _lib.ptr(r.get("conf")),
                          _lib.ptr(r.get("boxes")), r["seg_rows"].data_ptr(), r["n_seg"].data_ptr(), stream)
     _lib.check(rc, "nms")
     return r
@@ -50,9 +53,9 @@ def process_model_outputs(outputs: torch.Tensor, iou_threshold: float = 0.05, co
     Class-agnostic per-clip NMS on un-offset coordinates (== torchvision.batched_nms whenever it takes its
     per-index loop, and at B = 1).  Raises ValueError when nothing passes ``conf_threshold`` - the
     reference fails the same way (torch.cat of an empty list, inference.py:100)."""
-    r = nms_raw(outputs, iou_threshold, conf_threshold, sample_duration, return_start_end, _h)
-    dev = r["keep"].device
-    B, P = r["keep"].shape
+    r = nms_raw(outputs, iou_threshold, conf_threshold, sample_duration, return_start_end, _h, want_keep=False)
+    dev = r["seg_rows"].device
+    B, P = r["seg_rows"].shape[:2]
     lib = _lib.load()
     segments = torch.empty((B * P, 5), device=dev, dtype=torch.float32)
     batch_idxs = torch.empty((B * P,), device=dev, dtype=torch.int64)
