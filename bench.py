@@ -51,12 +51,12 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled from the MAIN thread at the one
-    moment that does not disturb the measurement: right after the timed steps have been enqueued, while the GPU is still
-    executing them (the host runs many steps ahead of the device).  A background poller is the obvious alternative and was
-    measured to be harmful: every NVML / nvidia-smi query takes a driver lock that stalls kernel LAUNCHES for milliseconds -
-    with nvidia-smi every 0.2 s the 40 ms timed region read 3.99 or 4.6 ms per step depending on whether a query landed in it,
-    with NVML every 25 ms it read 6.4-9.2 ms.  Work that is already queued is not affected.  Uses NVML in-process
+    """SM clock + throttle reasons under the benchmark's load (B200_PROFILING.md recipe), sampled from the MAIN thread while
+    enqueued steps execute: the warm-up steps right before the timed region, an untimed repeat of the K timed steps right after
+    it, and the end-to-end loop.  Queries INSIDE the timed region were measured to corrupt it, whichever way they are made:
+    a background nvidia-smi every 0.2 s -> 3.99 or 4.6 ms per step depending on whether a query landed in the 40 ms region;
+    NVML in a thread every 25 ms -> 6.4-9.2 ms per step; one NVML query from the main thread after the K steps were enqueued ->
+    3.9 ms in most runs but 13.4 ms in two of twelve (a ~95 ms device stall).  Uses NVML in-process
     (nvidia_ml_py: the data source of `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`), falls back to
     the nvidia-smi subprocess."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -65,20 +65,27 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.samples = index, []
         self.nvml = self.handle = None
+        self._init_done = False
+
+    def _init(self):
+        # lazily, at the first sample: not even nvmlInit() runs before the timed regions are over
+        self._init_done = True
         try:
             import pynvml
             pynvml.nvmlInit()
             try:
-                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
                 self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
             except Exception:  # noqa: BLE001
-                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.nvml = pynvml
         except Exception:  # noqa: BLE001
             self.nvml = None
 
     def sample(self):
         """One sample; call it while the device is busy with already-enqueued work."""
+        if not self._init_done:
+            self._init()
         try:
             if self.nvml is not None:
                 n, h = self.nvml, self.handle
@@ -104,7 +111,9 @@ class ClockSampler:
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi",
-                "when": "after the warm-up / timed / end-to-end steps were enqueued, while the device was executing them"}
+                "when": "after every timed measurement: while the device executed untimed repeats of the K timed steps (and of one "
+                        "end-to-end step); no monitoring query runs before or inside a timed region - NVML / nvidia-smi queries "
+                        "stall the device (see ClockSampler)"}
 
 
 def synth_clips_device(B: int, dev, seed: int):
@@ -356,7 +365,6 @@ def run_train(args):
         torch.cuda.synchronize()
     for _ in range(W):
         step(x, tg)
-    sampler.sample()            # warm-up steps still executing
     torch.cuda.synchronize()
     n0 = _lib.launch_count
     met = step(x, tg)
@@ -372,7 +380,6 @@ def run_train(args):
         met = step(x, tg)
     torch.cuda.nvtx.range_pop()
     e1.record()
-    sampler.sample()            # the timed steps are enqueued and still executing: a query now cannot stall a launch
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -392,7 +399,11 @@ def run_train(args):
     e1.record()
     torch.cuda.synchronize()
     ms_e = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
-    sampler.sample()
+    for _ in range(3):              # clocks under the same load, after every timed measurement (see the inference workload)
+        for _ in range(min(K, 5)):
+            step(x, tg)
+        sampler.sample()
+        torch.cuda.synchronize()
     if rank == 0:
         peaks = load_peaks()
         value = CLIP_SECONDS * B * world * K / (ms / 1e3)
@@ -473,7 +484,6 @@ def main():
         torch.cuda.synchronize()
     for _ in range(W):
         step(x)
-    sampler.sample()
     torch.cuda.synchronize()
     n0 = _lib.launch_count
     step(x)
@@ -490,7 +500,6 @@ def main():
         r = step(x)
     torch.cuda.nvtx.range_pop()
     e1.record()
-    sampler.sample()            # the timed steps are enqueued and still executing: a query now cannot stall a launch
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -515,7 +524,6 @@ def main():
         if seg is not None:
             d2h = seg.numel() * 4 + bidx.numel() * 8 + 8
     e1.record()
-    sampler.sample()
     torch.cuda.synchronize()
     ms_e = parallel.max_over_ranks(e0.elapsed_time(e1), device=dev)
     e2e = {"value": CLIP_SECONDS * B * world * Ke / (ms_e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": B * CLIP_SAMPLES * 4,
@@ -537,6 +545,17 @@ def main():
     e2e_i16 = {"value": CLIP_SECONDS * B * world * Ke / (ms_i / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": B * CLIP_SAMPLES * 2,
                "steps": Ke, "input": "int16 PCM (same clips quantised to 16 bit)"}
     del xi
+    # Clocks / throttle reasons under exactly the benchmark's load: every timed measurement above is finished; the K steps and one
+    # end-to-end step are run once more, untimed, and sampled while they execute.  No monitoring query (not even nvmlInit) runs
+    # before this point: queries before or inside a timed region were measured to corrupt it (see ClockSampler).
+    for _ in range(3):
+        for _ in range(K):
+            step(x)
+        sampler.sample()
+        torch.cuda.synchronize()
+    e2e_step()
+    sampler.sample()
+    torch.cuda.synchronize()
 
     if rank == 0:
         peaks = load_peaks()

@@ -90,6 +90,16 @@ int yad_frontend_mel_power_i16(const int16_t* pcm, int64_t B, int64_t L, int32_t
                                const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
                                int64_t T, yad_stream_t stream);
 
+/* Stage A with `taper_input: true` (modules/_architecture.py:87-94): the resampled 16 kHz signal is multiplied by a clip-long
+ * window (taper [taper_len] f32, taper_len >= T*1000; the reference's registered buffer `taper_window`, a non-periodic
+ * hann / hamming / ... window of the resampled length) before the Hann analysis window, in the reference's order
+ * (x * taper) * hann.  pcm is fp32 (pcm_is_i16 = 0) or 16-bit PCM. */
+int yad_frontend_mel_power_taper(const void* pcm, int32_t pcm_is_i16, const float* taper, int64_t taper_len, int64_t B, int64_t L,
+                                 int32_t P, int32_t O, int32_t width, const float* taps, const int32_t* tap_base,
+                                 const int32_t* lane_map, int32_t window_len, const float* window, const float* twiddle,
+                                 const float* fb_val, const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
+                                 int64_t T, yad_stream_t stream);
+
 /* Stage B: mel power [B,32,T] -> x_spectral [B,2,32,T] f32 (channel 0 = standardised
  * dB-mel, channel 1 = standardised dB-of-MFCC).  One CTA per clip; T <= 1024.
  * Optional taps (may be NULL): meldb, mfcc, mfdb, each [B,32,T] f32 (pre-standardise). */

@@ -56,7 +56,8 @@ def cuda_dev():
     return torch.device("cuda", 0)
 
 
-VARIANTS = {"bottleneck": {"resnet_config": {"block": "Bottleneck"}}, "custom": {"backbone": "custom"}}
+VARIANTS = {"bottleneck": {"resnet_config": {"block": "Bottleneck"}}, "custom": {"backbone": "custom"},
+            "taper": {"taper_input": True}}
 
 
 @pytest.fixture(scope="session")

@@ -34,7 +34,8 @@ import synth  # noqa: E402
 from make_golden import SKIP  # noqa: E402
 
 torch.set_grad_enabled(False)
-VARIANTS = {"bottleneck": {"resnet_config": {"block": "Bottleneck"}}, "custom": {"backbone": "custom"}}
+VARIANTS = {"bottleneck": {"resnet_config": {"block": "Bottleneck"}}, "custom": {"backbone": "custom"},
+            "taper": {"taper_input": True}}       # default ResNet with the clip-long taper window (modules/_architecture.py:87-94)
 
 
 def variant_config(name):
@@ -49,7 +50,7 @@ def main():
     for name in VARIANTS:
         m = AudioDetectionNetwork(2, config=variant_config(name))
         layout = {k: list(v.shape) for k, v in m.state_dict().items() if k not in SKIP}
-        layouts[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+        layouts[name] = {k: list(v.shape) for k, v in m.state_dict().items()}       # (taper_window is still empty here)
         full = dict(m.state_dict()); full.update(synth.synth_state_dict(layout, seed=42))
         m.load_state_dict(full)
         m.eval()

@@ -516,7 +516,7 @@ def test_evaluate_waveform_vs_live_reference(models, gold, cuda_dev):
 
 
 # ------------------------------------------------------------------ other config-selectable backbones
-@pytest.mark.parametrize("variant", ["bottleneck", "custom"])
+@pytest.mark.parametrize("variant", ["bottleneck", "custom", "taper"])
 @pytest.mark.parametrize("form", ["train", "deploy"])
 @pytest.mark.parametrize("dt", ["f32", "bf16"])
 def test_other_backbones_vs_golden(variant_state_dict, gold, variant, form, dt, cuda_dev):
@@ -791,3 +791,22 @@ def test_nms_segments_only_equals_full_scan(gold, iou, cthr, cuda_dev):
         for b in range(B):
             n = int(full["n_seg"][b])
             assert torch.equal(full["seg_rows"][b, :n], fast["seg_rows"][b, :n])
+
+
+def test_graph_replay_of_repeated_input(models, cuda_dev):
+    """The same input TENSOR coming back turns the recorded plan into one CUDA-graph launch: identical results, it reads the
+    tensor's current contents, returns fresh output tensors, and a different tensor falls back to the plain replay."""
+    m = models[("deploy", "bf16")]
+    xa = synth.synth_clips(2, 22050 * 6, seed=611, silence_tail_every=0).to(cuda_dev)
+    xb = synth.synth_clips(2, 22050 * 6, seed=612, silence_tail_every=0).to(cuda_dev)
+    m._engine_cache.clear()
+    outs = [m(xa, combine_scales=True) for _ in range(5)]             # record, replay, capture + graph, graph, graph
+    eng = m._engine()
+    progs = [v for k, v in eng._plan((2, 22050 * 6)).items() if isinstance(k, tuple) and k[0] == "prog"]
+    assert progs and "graph" in progs[0]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0]) and o.data_ptr() != outs[0].data_ptr()
+    ref_b = m(xb, combine_scales=True).clone()                        # other tensor: plain replay
+    assert not torch.equal(ref_b, outs[0])
+    xa.copy_(xb)                                                      # same tensor, new contents: the graph reads them
+    assert torch.equal(m(xa, combine_scales=True), ref_b)

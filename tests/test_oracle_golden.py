@@ -229,7 +229,7 @@ def test_evaluate_waveform_vs_live_reference(gold, ref_state_dict):
 
 
 # ---------------------------------------------------------------- other config-selectable backbones
-@pytest.mark.parametrize("variant", ["bottleneck", "custom"])
+@pytest.mark.parametrize("variant", ["bottleneck", "custom", "taper"])
 @pytest.mark.parametrize("form", ["train", "deploy"])
 def test_other_backbones_short_clips(gold, variant_state_dict, variant, form):
     """Bottleneck ResNet and the 3x7 CustomBackBone (2-D neck) vs the live reference's eval() outputs."""

@@ -45,6 +45,7 @@ _p, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_do
 SIGNATURES = {
     "yad_init": [C.c_int],
     "yad_frontend_mel_power": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
+    "yad_frontend_mel_power_taper": [_p, _i32, _p, _i64, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
     "yad_frontend_mel_power_i16": [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _p],
     "yad_frontend_finish": [_p, _i64, _i64, _p, _f32, _i32, _p, _p, _p, _p, _p],
     "yad_conv_stem": [_p, _i64, _i32, _i32, _p, _p, _i32, _p],

@@ -45,6 +45,7 @@ struct FeParams {
   int32_t SX;        // staged PCM floats per group
   int32_t n_groups;  // ceil(T / FE_FR), per clip
   int64_t total_groups;   // B * n_groups
+  int64_t taper_len;      // elements of the taper window (0 = none)
   int32_t groups_per_cta;
   int32_t fb_nnz_pad;  // mel CSR values, rounded up to a multiple of 4
   int32_t nquad, nslice;
@@ -106,9 +107,9 @@ __device__ __forceinline__ int fe_stage_async(Tp* s_dst, const Tp* __restrict__ 
   return 0;
 }
 
-template <bool I16>
+template <bool I16, bool TAPER>
 __global__ void __launch_bounds__(FE_THREADS, 1)
-frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float* __restrict__ taps,
+frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ taper, const FeParams p, const float* __restrict__ taps,
                     const int32_t* __restrict__ tap_base, const int32_t* __restrict__ lane_map,
                     const float* __restrict__ window,
                     const float* __restrict__ twiddle, const float* __restrict__ fb_val,
@@ -266,6 +267,9 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
       if (active) {
         const float* sx = (I16 ? s_xf : s_x + buf * sxp) + shift + base;
         float* fr = s_fr + buf * FE_FR_WORDS;
+        // taper_input (modules/_architecture.py:87-94): the resampled signal times a clip-long window, before framing
+        const int64_t gcl = (g_first + gi) % p.n_groups;           // group inside its clip
+        const float* tpg = TAPER ? taper + gcl * (FE_FR * FE_NFFT) : nullptr;
         for (int h = sl; h < p.HG; h += p.nslice) {
           const float* xs = sx + h * p.O;
           float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);
@@ -279,6 +283,12 @@ frontend_mel_kernel(const void* __restrict__ pcm, const FeParams p, const float*
           const int o = h * p.P + 4 * quad;
           const int f = o / FE_NFFT, pos = o - f * FE_NFFT;
           const float4 w = *reinterpret_cast<const float4*>(s_win + pos);
+          if (TAPER) {       // (x * taper) * hann, in the reference's order; samples past the window (unused tail frames) get 0
+            const int64_t n = gcl * (FE_FR * FE_NFFT) + o;
+            const float4 tp = n + 4 <= p.taper_len ? __ldg(reinterpret_cast<const float4*>(tpg + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a01 = __fmul2_rn(a01, make_float2(tp.x, tp.y));
+            a23 = __fmul2_rn(a23, make_float2(tp.z, tp.w));
+          }
           a01 = __fmul2_rn(a01, make_float2(w.x, w.y));
           a23 = __fmul2_rn(a23, make_float2(w.z, w.w));
           *reinterpret_cast<float4*>(fr + f * (2 * FFT_Z_STRIDE) + pos) = make_float4(a01.x, a01.y, a23.x, a23.y);
@@ -628,11 +638,20 @@ static size_t fe_smem_bytes(int SX, int nnz_pad) {
 }
 
 int init_frontend_attrs() {
-  cudaError_t e = cudaFuncSetAttribute(frontend_mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(&frontend_mel_kernel<false, false>),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(&frontend_mel_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             226 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(&frontend_mel_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             226 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(&frontend_mel_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             226 * 1024);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(frontend_finish_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((FE_NMEL * FE_NMEL + FE_NMEL * FB2_MAXT) * sizeof(float)));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(frontend_mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(frontend_mel_kernel) failed: %s", cudaGetErrorString(e));
     return YAD_ERR_CUDA;
@@ -644,7 +663,8 @@ int init_frontend_attrs() {
 
 extern "C" {
 
-static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, int32_t P, int32_t O, int32_t width,
+static int frontend_mel_impl(const void* pcm, bool i16, const float* taper, int64_t taper_len, int64_t B, int64_t L, int32_t P, int32_t O,
+                             int32_t width,
                              const float* taps, const int32_t* tap_base, const int32_t* lane_map, int32_t window_len,
                              const float* window,
                              const float* twiddle, const float* fb_val, const int32_t* fb_bin,
@@ -686,12 +706,18 @@ static int frontend_mel_impl(const void* pcm, bool i16, int64_t B, int64_t L, in
   const size_t smem = fe_smem_bytes(p.SX, p.fb_nnz_pad);
   YAD_CHECK_ARG(smem <= 226 * 1024, "yad_frontend_mel_power: staging span too large (%zu B of shared memory)", smem);
   dim3 grid((unsigned)((p.total_groups + p.groups_per_cta - 1) / p.groups_per_cta));
-  if (i16)
-    frontend_mel_kernel<true><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, lane_map, window, twiddle, fb_val,
-                                                                                fb_bin, fb_start, mel);
-  else
-    frontend_mel_kernel<false><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, p, taps, tap_base, lane_map, window, twiddle, fb_val,
-                                                                                 fb_bin, fb_start, mel);
+  YAD_CHECK_ARG(taper == nullptr || (taper_len >= T * FE_NFFT && reinterpret_cast<uintptr_t>(taper) % 16 == 0),
+                "yad_frontend_mel_power: taper window shorter than T*1000 samples or not 16-byte aligned");
+  p.taper_len = taper ? taper_len : 0;
+#define YAD_FE_LAUNCH(I16_, TAPER_)                                                                                          \
+  frontend_mel_kernel<I16_, TAPER_><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, taper, p, taps, tap_base, lane_map, window, \
+                                                                                      twiddle, fb_val, fb_bin, fb_start, mel)
+  if (i16) {
+    if (taper) YAD_FE_LAUNCH(true, true); else YAD_FE_LAUNCH(true, false);
+  } else {
+    if (taper) YAD_FE_LAUNCH(false, true); else YAD_FE_LAUNCH(false, false);
+  }
+#undef YAD_FE_LAUNCH
   YAD_LAUNCH_CHECK();
   return YAD_OK;
 }
@@ -700,7 +726,7 @@ int yad_frontend_mel_power(const float* pcm, int64_t B, int64_t L, int32_t P, in
                            const float* taps, const int32_t* tap_base, const int32_t* lane_map, int32_t window_len, const float* window,
                            const float* twiddle, const float* fb_val, const int32_t* fb_bin,
                            const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
-  return frontend_mel_impl(pcm, false, B, L, P, O, width, taps, tap_base, lane_map, window_len, window, twiddle, fb_val, fb_bin, fb_start,
+  return frontend_mel_impl(pcm, false, nullptr, 0, B, L, P, O, width, taps, tap_base, lane_map, window_len, window, twiddle, fb_val, fb_bin, fb_start,
                            fb_nnz, mel, T, stream);
 }
 
@@ -708,8 +734,18 @@ int yad_frontend_mel_power_i16(const int16_t* pcm, int64_t B, int64_t L, int32_t
                                const float* taps, const int32_t* tap_base, const int32_t* lane_map, int32_t window_len, const float* window,
                                const float* twiddle, const float* fb_val, const int32_t* fb_bin,
                                const int32_t* fb_start, int32_t fb_nnz, float* mel, int64_t T, yad_stream_t stream) {
-  return frontend_mel_impl(pcm, true, B, L, P, O, width, taps, tap_base, lane_map, window_len, window, twiddle, fb_val, fb_bin, fb_start,
+  return frontend_mel_impl(pcm, true, nullptr, 0, B, L, P, O, width, taps, tap_base, lane_map, window_len, window, twiddle, fb_val, fb_bin, fb_start,
                            fb_nnz, mel, T, stream);
+}
+
+int yad_frontend_mel_power_taper(const void* pcm, int32_t pcm_is_i16, const float* taper, int64_t taper_len, int64_t B, int64_t L,
+                                 int32_t P, int32_t O, int32_t width, const float* taps, const int32_t* tap_base,
+                                 const int32_t* lane_map, int32_t window_len, const float* window, const float* twiddle,
+                                 const float* fb_val, const int32_t* fb_bin, const int32_t* fb_start, int32_t fb_nnz, float* mel,
+                                 int64_t T, yad_stream_t stream) {
+  YAD_CHECK_ARG(taper != nullptr, "yad_frontend_mel_power_taper: null taper window");
+  return frontend_mel_impl(pcm, pcm_is_i16 != 0, taper, taper_len, B, L, P, O, width, taps, tap_base, lane_map, window_len, window,
+                           twiddle, fb_val, fb_bin, fb_start, fb_nnz, mel, T, stream);
 }
 
 static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const float* dct, float top_db, int32_t standardise,

@@ -375,6 +375,19 @@ class AudioDetectionNetwork(nn.Module):
             eng = self._engine_cache[key] = TrainEngine(self, dev, self.train_dtype)
         return eng
 
+    def _taper(self, x: torch.Tensor) -> Optional[torch.Tensor]:
+        """``taper_input: true`` (modules/_architecture.py:87-94): the clip-long window over the RESAMPLED signal, created on first
+        use with the resampled length of that input and kept as the registered buffer ``taper_window`` (it is in the state dict)."""
+        if not self.config["taper_input"]:
+            return None
+        L_res = -(-self._rs_new * x.shape[-1] // self._rs_orig)
+        if self.taper_window.numel() == 0:
+            self.taper_window = getattr(torch, f"{self.config['taper_window']}_window")(L_res, periodic=False, device=x.device)
+        if self.taper_window.numel() != L_res:
+            raise RuntimeError(f"The size of tensor a ({L_res}) must match the size of tensor b ({self.taper_window.numel()}) at "
+                               "non-singleton dimension 2 (taper_window was built for another clip length, as in the reference)")
+        return self.taper_window.to(x.device, torch.float32).contiguous()
+
     def _forward_train(self, x: torch.Tensor):
         """train() mode (pipeline/_trainer.py:98-104): batch-statistics BatchNorm, dropout, differentiable w.r.t. every
         parameter.  fp32 throughout, like the reference's training."""
@@ -387,7 +400,7 @@ class AudioDetectionNetwork(nn.Module):
             if out is not None:
                 return out
         with torch.no_grad(), torch.cuda.device(fe.dev):
-            xs = fe.run_frontend(x, {})
+            xs = fe.run_frontend(x, {}, None, self._taper(x))
         L_res = -(-fe.rs_P * L // fe.rs_O)
         with torch.cuda.device(fe.dev):
             return run_train_forward(self, self._train_engine(), xs, xs.shape[-1], L_res)
@@ -396,8 +409,6 @@ class AudioDetectionNetwork(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("yad_b200.AudioDetectionNetwork runs on sm_100a only; move the input and the model to "
                                "a CUDA device (there is no CPU fallback)")
-        if self.config["taper_input"]:
-            _unsupported("taper_input=true")
         if x.ndim != 3 or x.shape[1] != 1:
             raise ValueError(f"expected input of shape [N, 1, n_time], got {tuple(x.shape)}")
         B, E = x.shape[0], self.num_classes + 3
@@ -406,7 +417,7 @@ class AudioDetectionNetwork(nn.Module):
             if combine_scales:
                 return torch.cat([p.reshape(B, -1, E) for p in (sm, md, lg)], dim=1)
             return sm, md, lg
-        preds = self._engine().run(x, taps=taps)
+        preds = self._engine().run(x, taps=taps, taper=self._taper(x))
         if combine_scales:
             return preds
         A = self.config["num_anchors"]

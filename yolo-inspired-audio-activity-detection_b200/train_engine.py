@@ -661,7 +661,7 @@ def _capture_train_graphs(model, eng: TrainEngine, fe, x: torch.Tensor) -> dict:
     try:
         n0 = _lib.launch_count
         with torch.cuda.graph(fwd, pool=pool):
-            xs = fe.run_frontend(g["x"], g["plan"])
+            xs = fe.run_frontend(g["x"], g["plan"], None, model._taper(g["x"]))
             preds, state = eng.forward(xs, xs.shape[-1], L_res, True)
         n1 = _lib.launch_count
         g["dpreds"] = [torch.zeros_like(p) for p in preds]
