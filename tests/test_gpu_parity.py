@@ -810,3 +810,34 @@ def test_graph_replay_of_repeated_input(models, cuda_dev):
     assert not torch.equal(ref_b, outs[0])
     xa.copy_(xb)                                                      # same tensor, new contents: the graph reads them
     assert torch.equal(m(xa, combine_scales=True), ref_b)
+
+
+def test_shared_model_across_threads_with_graph_replay(models, cuda_dev):
+    """inference.py:212-236 hands ONE model to 10 worker threads.  Each thread has its own plans (workspaces, recorded call lists,
+    CUDA graphs): four threads calling the model repeatedly with their own tensors, while graphs are being captured, must each
+    get the single-threaded result."""
+    import threading
+    m = models[("deploy", "bf16")]
+    m._engine_cache.clear()
+    xs_ = [synth.synth_clips(2, 22050 * 6, seed=700 + i, silence_tail_every=0).to(cuda_dev) for i in range(4)]
+    want = [m(x, combine_scales=True).clone() for x in xs_]
+    torch.cuda.synchronize()
+    got, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(cuda_dev)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(5):
+                    o = m(xs_[i], combine_scales=True)
+                st.synchronize()
+            got[i] = o.clone()
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in range(4):
+        assert torch.equal(got[i], want[i]), i

@@ -110,6 +110,7 @@ class InferenceEngine:
         self.lib = _RecLib(_lib.init(device.index if device.index is not None else torch.cuda.current_device()), self._tls)
         self.dtype = BF16 if compute_dtype == "bf16" else F32
         self.use_graphs = os.environ.get("YAD_INFER_GRAPHS", "1") != "0"
+        self._threads_seen = set()
         self.tdtype = torch.bfloat16 if self.dtype == BF16 else torch.float32
         self.cfg = model.config
         self.nc = model.num_classes
@@ -807,7 +808,10 @@ class InferenceEngine:
         captured into a CUDA graph once and the whole forward becomes one graph launch.  The host then needs microseconds per
         step: on a busy machine the Python thread is descheduled for tens of milliseconds now and then, and with 57 launches to
         issue per 3.9 ms step that showed up as 6-15 ms steps in a third of the benchmark runs."""
-        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+        # graphs only while ONE thread uses this engine: a capture forbids device-wide operations (allocation, synchronize) that
+        # other worker threads of the reference's 10-thread fan-out (inference.py:212-236) issue at any time
+        self._threads_seen.add(threading.get_ident())
+        if not self.use_graphs or len(self._threads_seen) > 1 or torch.cuda.is_current_stream_capturing():
             return self._replay(prog, x)
         g = prog.get("graph")
         if g is not None:
@@ -818,11 +822,18 @@ class InferenceEngine:
             if g["x"]() is None:
                 prog.pop("graph")               # the captured input tensor is gone: its memory may be anybody's now
         seen = prog.get("last")
-        if seen is not None and seen[0]() is x and seen[1] == x.data_ptr() and "graph" not in prog:
+        if seen is not None and seen[0]() is x and seen[1] == x.data_ptr() and "graph" not in prog and not prog.get("no_graph"):
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(self.dev)
-            with torch.cuda.device(self.dev), torch.cuda.graph(graph):
-                preds = self._replay(prog, x)
+            try:
+                # thread_local: the reference shares one model across 10 worker threads (inference.py:212-236); their CUDA
+                # calls must not be poisoned by this thread's capture
+                with torch.cuda.device(self.dev), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    preds = self._replay(prog, x)
+            except Exception:  # noqa: BLE001  - capture is an optimisation: fall back to the plain replay for this plan
+                prog["no_graph"] = True
+                torch.cuda.synchronize(self.dev)
+                return self._replay(prog, x)
             prog["graph"] = {"graph": graph, "preds": preds, "x": weakref.ref(x), "ptr": x.data_ptr()}
             graph.replay()
             return preds.clone()
