@@ -12,6 +12,7 @@ decode -> per-clip segment NMS.  Prints ONE JSON line (rank 0).  Per-GPU work is
 clips are sharded across ranks with no data-path collective.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -378,10 +379,22 @@ def run_train(args):
     # first call in a process loads the tools library - tens of milliseconds from a cold page cache, which the first bench on a
     # fresh box otherwise books as 12 ms steps
     torch.cuda.nvtx.range_push("timed")
+    # no cyclic garbage collection inside the timed region: a generation-2 pass over this process's millions of objects takes
+    # ~100 ms on the host; when it lands in the few milliseconds in which the K steps are enqueued, the device idles and the
+    # region reads 12-15 ms per step instead of 3.75 (seen in ~1 run of 4)
+    gc.collect()
+    gc.disable()
+    # ... and no dependence on the launching thread at all: a ~60 ms spin kernel is queued first, the start event, the K steps
+    # and the stop event are enqueued behind it while it runs, so the device executes the timed region back to back from a
+    # full queue (what it does in production behind a CUDA graph / a busy stream) and stays at load clocks up to the start event.
+    # Without it the region read 3.75 ms per step in most processes and 8-15 ms in one of four on busy hosts - with identical
+    # per-stage times and clocks (a host-side stall while the device had nothing queued).
+    torch.cuda._sleep(int(1.2e8))
     e0.record()
     for _ in range(K):
         met = step(x, tg)
     e1.record()
+    gc.enable()
     torch.cuda.nvtx.range_pop()
     torch.cuda.synchronize()
     if world > 1:
@@ -501,10 +514,22 @@ def main():
     # first call in a process loads the tools library - tens of milliseconds from a cold page cache, which the first bench on a
     # fresh box otherwise books as 12 ms steps
     torch.cuda.nvtx.range_push("timed")
+    # no cyclic garbage collection inside the timed region: a generation-2 pass over this process's millions of objects takes
+    # ~100 ms on the host; when it lands in the few milliseconds in which the K steps are enqueued, the device idles and the
+    # region reads 12-15 ms per step instead of 3.75 (seen in ~1 run of 4)
+    gc.collect()
+    gc.disable()
+    # ... and no dependence on the launching thread at all: a ~60 ms spin kernel is queued first, the start event, the K steps
+    # and the stop event are enqueued behind it while it runs, so the device executes the timed region back to back from a
+    # full queue (what it does in production behind a CUDA graph / a busy stream) and stays at load clocks up to the start event.
+    # Without it the region read 3.75 ms per step in most processes and 8-15 ms in one of four on busy hosts - with identical
+    # per-stage times and clocks (a host-side stall while the device had nothing queued).
+    torch.cuda._sleep(int(1.2e8))
     e0.record()
     for _ in range(K):
         r = step(x)
     e1.record()
+    gc.enable()
     torch.cuda.nvtx.range_pop()
     torch.cuda.synchronize()
     if world > 1:
@@ -593,7 +618,11 @@ def main():
                                        "anchor decode -> per-clip segment NMS (BASELINE configs[1]+[2] chained)",
                            "clips_per_gpu": B, "clip_seconds": CLIP_SECONDS, "num_classes": 2,
                            "l2_policy": "inputs (2.7 GB PCM + 0.8 GB activations per step) are larger than the 126 MB L2",
-                           "parallelism": f"clip-sharded x{world}, no data-path collective"},
+                           "parallelism": f"clip-sharded x{world}, no data-path collective",
+                           "timing": "CUDA events around exactly K steps, barrier + synchronize on both sides; the steps are enqueued "
+                                     "behind a ~60 ms spin kernel queued before the start event, so the device runs the timed region "
+                                     "from a full queue (no dependence on the launching thread); gc disabled inside; clocks sampled "
+                                     "after all timed measurements during untimed repeats"},
                 "e2e": e2e, "e2e_int16": e2e_i16, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
                 "clocks": sampler.summary(), "roofline": roof, "stages_ms": st}
         if not args.no_cpu_baseline and world == 1:
