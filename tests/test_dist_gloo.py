@@ -90,3 +90,44 @@ def test_two_rank_gradient_allreduce():
     for _, got in res:
         assert got == want
     assert parallel.allreduce_mean_(torch.ones(4)).tolist() == [1.0] * 4     # not initialised: no-op
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    # buckets in the order a backward completes them: tail of the arena first (neck + layer4), then layer3, then the head
+    bar = parallel.BucketedAllReduce(g, [[(600, 800), (900, 1000)], (250, 600), None, [(0, 250), (800, 900)]])
+    mid = []
+    for i in range(4):
+        bar.ready(i)
+        mid.append(len(bar._works))
+    bar.wait()
+    q.put((rank, g.tolist(), mid))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_allreduce_overlap_api():
+    """The overlapped form of the train step's collective: each bucket is reduced as it becomes ready, wait() joins them;
+    the result equals the one-shot mean over the whole arena."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (torch.arange(1000, dtype=torch.float32) * 1.5).tolist()
+    for _, got, mid in res:
+        assert got == want
+        assert mid == [2, 3, 3, 5]           # one collective per contiguous run; an empty bucket launches nothing
+    bar = parallel.BucketedAllReduce(torch.ones(8), [(0, 8)])
+    bar.ready(0); bar.wait()                 # not initialised: no-op
+    assert bar.flat.tolist() == [1.0] * 8
+    with pytest.raises(ValueError):
+        parallel.BucketedAllReduce(torch.ones(8), [(4, 12)])

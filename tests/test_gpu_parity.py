@@ -74,6 +74,43 @@ def test_frontend_full_clip_and_ragged_lengths(models, gold, ref_state_dict, cud
     _check_frontend(taps, O.frontend(xr, ref_state_dict))
 
 
+# ---- the benchmarked code path: persistent CTAs running MANY groups each (the bench has ~415 groups per CTA; every test above
+#      has at most one).  9 full-length clips = 1080 groups -> 8 per CTA on 148 SMs: double-buffered staging, the BAR_EMPTY
+#      handshake (gi >= 2), mbarrier phase flips and clip-boundary crossings all run.  modules/_architecture.py:84-108.
+@pytest.fixture(scope="module")
+def long_batch():
+    return synth.synth_clips(9, 1323000, seed=5000, silence_tail_every=3)
+
+
+@pytest.mark.parametrize("kind", ["f32", "int16", "taper"])
+def test_frontend_multigroup_persistent_path(models, variant_state_dict, ref_state_dict, long_batch, kind, cuda_dev):
+    x = long_batch
+    cfg = O.DEFAULT_CONFIG
+    if kind == "taper":
+        sd, cfg = variant_state_dict("taper")
+        m = yad_b200.AudioDetectionNetwork(2, config=cfg, compute_dtype="f32")
+        m.load_state_dict(sd)
+        m = m.eval().to(cuda_dev)
+    else:
+        m = models[("train", "f32")]
+    if kind == "int16":
+        xi = (x.clamp(-1, 1) * 32767).round().to(torch.int16)
+        x, xin = xi.float() / 32768.0, xi
+    else:
+        xin = x
+    taps = {}
+    m(xin.to(cuda_dev), combine_scales=True, taps=taps)
+    assert taps["mel"].shape == (9, 1, 32, 960)
+    _check_frontend(taps, O.frontend(x, ref_state_dict, cfg))
+    # size-independent property of the persistent schedule: a clip's planes do not depend on where in the flat group sequence
+    # (which CTA, which staging buffer, before / after a clip boundary) its groups ran - bitwise
+    for idx in ([0], [4, 2], [8, 7, 6]):
+        t2 = {}
+        m(xin[idx].to(cuda_dev), combine_scales=True, taps=t2)
+        assert torch.equal(t2["mel"], taps["mel"][idx]), (kind, idx)
+        assert torch.equal(t2["x_spectral"], taps["x_spectral"][idx]), (kind, idx)
+
+
 # ------------------------------------------------------------------ convolutions
 CONV_CASES = [
     # B, H, W, Cin, Cout, k, stride, pad, act, residual
@@ -286,6 +323,50 @@ def test_full_clip_config1_end_to_end(models, gold, cuda_dev):
     np.testing.assert_allclose(out.cpu().numpy(), g["preds_train"], atol=5e-3)
     outd = models[("deploy", "f32")](x, combine_scales=True)
     np.testing.assert_allclose(outd.cpu().numpy(), g["preds_deploy"], atol=5e-3)
+
+
+def _bf16_close(out, ref, what=""):
+    """The stated bf16 tolerance of the tcgen05 path (see test_network_bf16_vs_golden)."""
+    d = np.abs(out - ref)
+    assert d[..., :3].max() < 0.15 and d[..., :3].mean() < 0.02, (what, d[..., :3].max(), d[..., :3].mean())
+    assert d[..., 3].max() < 0.1, (what, d[..., 3].max())
+    assert d[..., 4].max() < 1.5 and d[..., 4].mean() < 0.15, (what, d[..., 4].max(), d[..., 4].mean())
+
+
+def test_bf16_deploy_full_clip_vs_live_reference(models, gold, cuda_dev):
+    """BASELINE configs[2] shape per clip (T = 960, W = 240 -> multi-super-tile flat convs) on the bf16 tcgen05 path against the
+    LIVE reference's deploy-form prediction of the 60 s fixture (tests/golden/full_clip.npz)."""
+    g = gold("full_clip")
+    x = synth.synth_clips(1, 1323000, seed=2000, silence_tail_every=0).to(cuda_dev)
+    out = models[("deploy", "bf16")](x, combine_scales=True).cpu().numpy()
+    assert out.shape == g["preds_deploy"].shape == (1, 630, 5)
+    _bf16_close(out, g["preds_deploy"], "deploy bf16 T=960")
+    outt = models[("train", "bf16")](x, combine_scales=True).cpu().numpy()
+    _bf16_close(outt, g["preds_train"], "train-form bf16 T=960")
+
+
+def test_bf16_deploy_batch160_vs_oracle(models, ref_state_dict, cuda_dev):
+    """More clips than SMs (B = 160 > 148: every per-clip kernel and every persistent tile loop wraps) at full length: 4 sampled
+    clips against the oracle at the bf16 tolerance, and every replica of a clip bitwise equal to its first occurrence (batch
+    position must not change a result), and equal to the same clip run in a batch of 4."""
+    m = models[("deploy", "bf16")]
+    base = synth.synth_clips(16, 1323000, seed=6000, silence_tail_every=8)
+    idx = torch.arange(160) % 16
+    x = base[idx].to(cuda_dev)
+    out = m(x, combine_scales=True)
+    assert out.shape == (160, 630, 5)
+    for i in range(16, 160):
+        assert torch.equal(out[i], out[i % 16]), i
+    pick = [0, 37, 148, 159]
+    small = m(x[pick].contiguous(), combine_scales=True)
+    assert torch.equal(small, out[pick])
+    sd = O.fold_repvgg({k: v.cpu() for k, v in ref_state_dict.items()})
+    ref = O.forward(base[[p % 16 for p in pick]], sd, 2)
+    _bf16_close(out[pick].cpu().numpy(), ref.numpy(), "B=160")
+    # the post-processing of the whole batch: clip ids of replicas repeat with period 16
+    seg, bidx = yad_b200.process_model_outputs(out, 0.1, 0.2)
+    cnt = torch.bincount(bidx.cpu(), minlength=160)
+    assert torch.equal(cnt[:16].repeat(10), cnt)
 
 
 def test_decode_vs_oracle(cuda_dev, ref_state_dict):
@@ -803,11 +884,15 @@ def test_graph_replay_of_repeated_input(models, cuda_dev):
     outs = [m(xa, combine_scales=True) for _ in range(5)]             # record, replay, capture + graph, graph, graph
     eng = m._engine()
     progs = [v for k, v in eng._plan((2, 22050 * 6)).items() if isinstance(k, tuple) and k[0] == "prog"]
-    assert progs and "graph" in progs[0]
+    assert progs and len(progs[0].get("graphs", {})) == 1
     for o in outs[1:]:
         assert torch.equal(o, outs[0]) and o.data_ptr() != outs[0].data_ptr()
-    ref_b = m(xb, combine_scales=True).clone()                        # other tensor: plain replay
+    ref_b = m(xb, combine_scales=True).clone()                        # other tensor, first sighting: plain replay
     assert not torch.equal(ref_b, outs[0])
+    assert len(progs[0]["graphs"]) == 1
+    for _ in range(2):                                                # it comes back: its own graph (a ring of staging buffers)
+        assert torch.equal(m(xb, combine_scales=True), ref_b)
+    assert len(progs[0]["graphs"]) == 2
     xa.copy_(xb)                                                      # same tensor, new contents: the graph reads them
     assert torch.equal(m(xa, combine_scales=True), ref_b)
 

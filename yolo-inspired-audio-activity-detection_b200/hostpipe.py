@@ -54,6 +54,71 @@ def run_host_batch(model, x_host: torch.Tensor, iou_threshold: float = 0.05, con
         return seg.cpu(), bidx.cpu()
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs: the PCI device's ``numa_node`` and that
+    node's ``cpulist``), so that staging buffers allocated afterwards (``pin_memory`` first-touches its pages in the calling
+    thread) are node-local and the H2D DMA does not cross the inter-socket link.  One process per GPU (torchrun): call it before
+    allocating pinned memory.  Returns what it did; never raises (containers may forbid it) - the copy path works unbound."""
+    import os
+    info = {"bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        info["pci"] = bdf
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            info["why"] = "the platform reports no NUMA node for this device"
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["node_cpus"], info["allowed_cpus"] = len(cpus), len(allowed)
+        if not use:
+            info["why"] = "none of the node's CPUs is in this process's cpuset"
+            return info
+        os.sched_setaffinity(0, use)
+        info["bound"], info["cpus"] = True, len(use)
+    except Exception as e:  # noqa: BLE001
+        info["why"] = f"{type(e).__name__}: {e}"
+    return info
+
+
+def h2d_ceiling_gbs(nbytes_per_copy: int, copies: int, device, reps: int = 3) -> float:
+    """Raw pinned-host -> device copy rate (GB/s) for the same transfer pattern ``run_host_batch`` issues: ``copies`` back-to-back
+    ``cudaMemcpyAsync`` of ``nbytes_per_copy`` each on one stream, timed with CUDA events (best of ``reps``).  The ceiling the
+    end-to-end number is quoted against."""
+    src = torch.empty(nbytes_per_copy, dtype=torch.uint8, pin_memory=True)
+    src.zero_()
+    dst = [torch.empty(nbytes_per_copy, dtype=torch.uint8, device=device) for _ in range(2)]
+    st = _copy_stream(device)
+    best = 0.0
+    with torch.cuda.stream(st):
+        dst[0].copy_(src, non_blocking=True)
+        st.synchronize()
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            for i in range(copies):
+                dst[i & 1].copy_(src, non_blocking=True)
+            b.record(st)
+            st.synchronize()
+            best = max(best, nbytes_per_copy * copies / (a.elapsed_time(b) / 1e3) / 1e9)
+    return best
+
+
 _COPY_STREAMS = {}
 
 

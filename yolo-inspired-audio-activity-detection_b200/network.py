@@ -346,6 +346,21 @@ class AudioDetectionNetwork(nn.Module):
         std = x.std(dim=(-2, -1))[:, :, None, None]
         return (x - mu) / (std + e)
 
+    def invalidate_engines(self):
+        """Drop the packed-weight engines (and their CUDA-graph plans) so the next eval() forward re-packs the live parameters.
+        Staleness is detected through ``tensor._version`` and ``_lib.param_epoch`` (bumped by FusedAdamEMA.step,
+        EMAParamsSmoothener.update, load_state_dict, load_checkpoint); writes through ``.data`` (``p.data.mul_()``,
+        ``conv.weight.data = w``) bypass both - call this after such a write."""
+        from . import _lib
+        _lib.param_epoch += 1
+        self._engine_cache.clear()
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        from . import _lib
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        _lib.param_epoch += 1
+        return out
+
     # ---- forward -------------------------------------------------------------------------------
     def _engine(self, frontend_only: bool = False):
         from .engine import InferenceEngine

@@ -59,3 +59,44 @@ def allreduce_mean_(flat: torch.Tensor, bucket_bytes: int = 32 << 20) -> torch.T
         w.wait()
     flat.div_(world)
     return flat
+
+
+class BucketedAllReduce:
+    """Gradient averaging overlapped with the backward: contiguous ranges of one flat gradient arena, each all-reduced
+    asynchronously the moment its producer reports it complete (``ready(i)``), joined by ``wait()`` before the optimizer step.
+    NCCL (CUDA tensors) averages inside the collective; gloo (CPU tensors, the world_size-2 tests) sums and divides in ``wait``.
+    No-op when torch.distributed is not initialised or the world has one rank."""
+
+    def __init__(self, flat: torch.Tensor, ranges):
+        """``ranges[i]``: the (lo, hi) element range of bucket i, a list of such ranges (a bucket whose parameters are not adjacent
+        in the arena: one collective per range), or None (empty bucket)."""
+        n = flat.numel()
+        norm = []
+        for r in ranges:
+            rs = [] if r is None else ([tuple(r)] if isinstance(r[0], int) else [tuple(q) for q in r])
+            for lo, hi in rs:
+                if not (0 <= lo < hi <= n):
+                    raise ValueError(f"bucket {(lo, hi)} outside the arena of {n} elements")
+            norm.append(rs)
+        self.flat, self.ranges, self._works = flat, norm, []
+
+    @staticmethod
+    def _active() -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def ready(self, i: int) -> None:
+        if not self._active():
+            return
+        for lo, hi in self.ranges[i]:
+            seg = self.flat[lo:hi]
+            if seg.is_cuda:
+                self._works.append((dist.all_reduce(seg, op=dist.ReduceOp.AVG, async_op=True), None))
+            else:
+                self._works.append((dist.all_reduce(seg, op=dist.ReduceOp.SUM, async_op=True), seg))
+
+    def wait(self) -> None:
+        for w, seg in self._works:
+            w.wait()
+            if seg is not None:
+                seg.div_(dist.get_world_size())
+        self._works = []

@@ -44,15 +44,10 @@ def nms_raw(outputs: torch.Tensor, iou_threshold: float, conf_threshold: float, 
     return r
 
 
-def process_model_outputs(outputs: torch.Tensor, iou_threshold: float = 0.05, conf_threshold: float = 0.5,
-                          sample_duration: float = 60, return_start_end: bool = True, _h: int = 10,
-                          ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Same signature and return as the reference: (segments [K,5] f32 = [conf, obj_logit, label, start, end],
-    batch_idxs [K] i64), clips in order, segments sorted by centre inside a clip.
-
-    Class-agnostic per-clip NMS on un-offset coordinates (== torchvision.batched_nms whenever it takes its
-    per-index loop, and at B = 1; SURVEY Q9).  Raises ValueError when nothing passes ``conf_threshold`` - the
-    reference fails the same way (torch.cat of an empty list, inference.py:100)."""
+def segments_device(outputs: torch.Tensor, iou_threshold: float = 0.05, conf_threshold: float = 0.5, sample_duration: float = 60,
+                    return_start_end: bool = True, _h: int = 10) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The device side of ``process_model_outputs`` without its host synchronisation: per-clip NMS + compaction.  Returns
+    (segments [B*P,5], batch_idxs [B*P], total [1] i64) on the device; rows [0, total) are valid."""
     r = nms_raw(outputs, iou_threshold, conf_threshold, sample_duration, return_start_end, _h, want_keep=False)
     dev = r["seg_rows"].device
     B, P = r["seg_rows"].shape[:2]
@@ -65,6 +60,19 @@ def process_model_outputs(outputs: torch.Tensor, iou_threshold: float = 0.05, co
         rc = lib.yad_compact_segments(r["seg_rows"].data_ptr(), r["n_seg"].data_ptr(), B, P, segments.data_ptr(),
                                       batch_idxs.data_ptr(), total.data_ptr(), stream)
     _lib.check(rc, "compact_segments")
+    return segments, batch_idxs, total
+
+
+def process_model_outputs(outputs: torch.Tensor, iou_threshold: float = 0.05, conf_threshold: float = 0.5,
+                          sample_duration: float = 60, return_start_end: bool = True, _h: int = 10,
+                          ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Same signature and return as the reference: (segments [K,5] f32 = [conf, obj_logit, label, start, end],
+    batch_idxs [K] i64), clips in order, segments sorted by centre inside a clip.
+
+    Class-agnostic per-clip NMS on un-offset coordinates (== torchvision.batched_nms whenever it takes its
+    per-index loop, and at B = 1; SURVEY Q9).  Raises ValueError when nothing passes ``conf_threshold`` - the
+    reference fails the same way (torch.cat of an empty list, inference.py:100)."""
+    segments, batch_idxs, total = segments_device(outputs, iou_threshold, conf_threshold, sample_duration, return_start_end, _h)
     K = int(total.item())            # the output shape is data dependent: one host sync, like the reference
     if K == 0:
         raise ValueError("no segment passed conf_threshold (the reference raises here too: torch.cat of an empty list)")

@@ -416,7 +416,7 @@ class TrainEngine:
         out = self._new(x.B, x.H, x.W, x.C)
         seed = (int(torch.initial_seed()) * 1000003) & ((1 << 62) - 1)
         n = x.buf.numel()
-        sd = self._seed_dev
+        sd = self._seed_snap
         _lib.check(self.lib.yad_dropout_dev(x.ptr, n, p, seed, sd.data_ptr(), 0, out.ptr, self._s()), "dropout")
         if self._tape is not None:
             def bwd():
@@ -494,6 +494,10 @@ class TrainEngine:
         self._bn_counters: List[torch.Tensor] = []
         self._step += 1
         self._seed_dev.add_(1)
+        # per-forward snapshot of the counter: the backward of THIS tape must redraw the mask its forward used, even when another
+        # train-mode forward (gradient accumulation, a no_grad train-mode pass) advances the counter in between.  Inside a graph
+        # capture the clone is a copy node into a pool tensor, replayed with the graph.
+        self._seed_snap = self._seed_dev.clone()
         self._act_numel = 0
         self._stats_arena, self._stats_used = torch.zeros(2 * self._n_bn, device=self.dev, dtype=torch.float64), 0
         B, Cin, H0, _ = xs.shape
@@ -505,11 +509,12 @@ class TrainEngine:
             x = self.conv(x0, fe.conv1, need_dx=False)
         x = self.conv_bn(x, fe.conv2, fe.bn1, ACT_RELU)
         x = self.dropout(x, float(fe.dropout_p))
-        fmaps = []
+        fmaps, marks = [], []
         for li in range(1, 5):
             for blk in getattr(fe, f"layer{li}"):
                 x = self.basic_block(x, blk)
             fmaps.append(x)
+            marks.append(len(self._tape) if self._tape is not None else 0)      # tape length after layer li (gradient buckets)
         hs = [f.H for f in fmaps]
         if not (hs[0] != hs[1] != hs[2] != hs[3]):
             raise NotImplementedError("neck with equal feature-map heights (2-D neck) is not built")
@@ -567,34 +572,72 @@ class TrainEngine:
         if record:
             state = {"tape": self._tape, "grads": self._grads, "heads": heads, "anc_s": anc_s, "anchors": anchors,
                      "strides": [T // h.W for h in heads], "center_scaler": center_scaler, "dur": dur, "B": B,
-                     "arena_numel": self._act_numel + self._n_weights + 4096 * 64}
+                     "arena_numel": self._act_numel + self._n_weights + 4096 * 64, "marks": marks}
         self._tape, self._grads = None, {}
         self._bulk_packed = False
         return preds, state
 
+    # Gradient buckets, in the order the backward completes them (reverse of the forward): 0 = neck + layer4 (36.6 MB of the
+    # 48.5 MB fp32 gradient, finished after ~15 % of the backward's time), 1 = layer3 (8.4 MB), 2 = layer2, layer1, stem and the
+    # anchors.  ``on_bucket(i)`` (set by FusedAdamEMA.overlap_allreduce) is called right after bucket i's last kernel was
+    # enqueued, so its NCCL all-reduce runs under the rest of the backward ("bucketed behind backward").
+    N_BUCKETS = 3
+    on_bucket: Optional[Callable[[int], None]] = None
+
+    def bucket_params(self) -> List[List[torch.nn.Parameter]]:
+        fe, ms = self.model.feature_extractor, self.model.multiscale_module
+        b0 = list(fe.layer4.parameters()) + list(ms.parameters())
+        b1 = list(fe.layer3.parameters())
+        seen = {id(p) for p in b0 + b1}
+        b2 = [p for p in self.model.parameters() if id(p) not in seen]
+        return [b0, b1, b2]
+
+    def backward_segments(self, state, dpreds: List[Optional[torch.Tensor]]) -> List[Callable[[], None]]:
+        """The backward as N_BUCKETS callables to run in order; after the i-th, the gradients of bucket i are final."""
+        tape, marks = state["tape"], state["marks"]
+
+        def prologue():
+            self._grads = state["grads"]
+            self._tape = None
+            self._bwd_arena, self._bwd_used = torch.zeros(state["arena_numel"], device=self.dev, dtype=torch.float32), 0
+            dur, B = state["dur"], state["B"]
+            danc = torch.zeros_like(state["anc_s"])
+            for s, (h, dp) in enumerate(zip(state["heads"], dpreds)):
+                if dp is None:
+                    continue
+                dp = dp.contiguous().float()
+                dh = self._grad(h)
+                _lib.check(self.lib.yad_decode_bwd(h.ptr, h.ld, dp.data_ptr(), B, h.W, self.A, self.nc, state["anc_s"][s].data_ptr(),
+                                                   float(state["strides"][s]) / float(state["center_scaler"]), dur, dh.ptr, dh.ld,
+                                                   danc[s].data_ptr(), self._s()), "decode bwd")
+            for s, a in enumerate(state["anchors"]):
+                if a.requires_grad:
+                    self._pgrad(a).add_(danc[s], alpha=dur)
+
+        def run(lo, hi):
+            for fn in reversed(tape[lo:hi]):
+                fn()
+
+        def seg0():
+            prologue()
+            run(marks[2], len(tape))          # neck, H-means, layer4
+
+        def seg1():
+            run(marks[1], marks[2])           # layer3
+
+        def seg2():
+            run(0, marks[1])                  # layer2, layer1, stem
+            tape.clear()
+            state["grads"].clear()
+            self._grads, self._bwd_arena = {}, None
+        return [seg0, seg1, seg2]
+
     def backward(self, state, dpreds: List[Optional[torch.Tensor]]):
         """Accumulates d loss / d parameter into every ``p.grad`` (allocated when missing)."""
-        self._grads = state["grads"]
-        self._tape = None
-        self._bwd_arena, self._bwd_used = torch.zeros(state["arena_numel"], device=self.dev, dtype=torch.float32), 0
-        dur, B = state["dur"], state["B"]
-        danc = torch.zeros_like(state["anc_s"])
-        for s, (h, dp) in enumerate(zip(state["heads"], dpreds)):
-            if dp is None:
-                continue
-            dp = dp.contiguous().float()
-            dh = self._grad(h)
-            _lib.check(self.lib.yad_decode_bwd(h.ptr, h.ld, dp.data_ptr(), B, h.W, self.A, self.nc, state["anc_s"][s].data_ptr(),
-                                               float(state["strides"][s]) / float(state["center_scaler"]), dur, dh.ptr, dh.ld,
-                                               danc[s].data_ptr(), self._s()), "decode bwd")
-        for s, a in enumerate(state["anchors"]):
-            if a.requires_grad:
-                self._pgrad(a).add_(danc[s], alpha=dur)
-        for fn in reversed(state["tape"]):
-            fn()
-        state["tape"].clear()
-        state["grads"].clear()
-        self._grads, self._bwd_arena = {}, None
+        for i, seg in enumerate(self.backward_segments(state, dpreds)):
+            seg()
+            if self.on_bucket is not None:
+                self.on_bucket(i)
 
 
 class _TrainFn(torch.autograd.Function):
@@ -637,7 +680,11 @@ class _GraphFn(torch.autograd.Function):
                     dst.zero_()
                 else:
                     dst.copy_(dp)
-            g["bwd"].replay()
+            hook = g["eng"].on_bucket
+            for i, gb in enumerate(g["bwd"]):
+                gb.replay()
+                if hook is not None:
+                    hook(i)
         _lib.launch_count += g["bwd_launches"]
         _lib.param_epoch += 1
         return (None,) * len(ctx.needs_input_grad)
@@ -656,7 +703,7 @@ def _capture_train_graphs(model, eng: TrainEngine, fe, x: torch.Tensor) -> dict:
     eng._ensure_pack_table()                   # host -> device copy: must happen before the capture starts
     torch.cuda.synchronize(eng.dev)
     pool = torch.cuda.graph_pool_handle()
-    fwd, bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    fwd, bwd = torch.cuda.CUDAGraph(), [torch.cuda.CUDAGraph() for _ in range(TrainEngine.N_BUCKETS)]
     eng._force_repack = True                   # weight packing must be part of the graph (the parameters change every step)
     try:
         n0 = _lib.launch_count
@@ -666,14 +713,17 @@ def _capture_train_graphs(model, eng: TrainEngine, fe, x: torch.Tensor) -> dict:
         n1 = _lib.launch_count
         g["dpreds"] = [torch.zeros_like(p) for p in preds]
         torch.cuda.synchronize(eng.dev)
-        with torch.cuda.graph(bwd, pool=pool):
-            eng.backward(state, g["dpreds"])
+        # one graph per gradient bucket (same pool, replayed in capture order): the all-reduce of bucket i is launched between
+        # replays and overlaps the later segments
+        for gb, seg in zip(bwd, eng.backward_segments(state, g["dpreds"])):
+            with torch.cuda.graph(gb, pool=pool):
+                seg()
         n2 = _lib.launch_count
     finally:
         eng._force_repack = False
     _lib.launch_count = n0
     g["pack_table"] = eng._pack_table           # the captured pack kernel reads this device table: keep it alive with the graph
-    g.update(fwd=fwd, bwd=bwd, preds=preds, state=state, fwd_launches=n1 - n0, bwd_launches=n2 - n1,
+    g.update(eng=eng, fwd=fwd, bwd=bwd, preds=preds, state=state, fwd_launches=n1 - n0, bwd_launches=n2 - n1,
              grad_ptrs=[p.grad.data_ptr() for p in eng._params])
     return g
 

@@ -186,7 +186,7 @@ class AudioDetectionLoss(torch.nn.Module):
         cm = confs.cpu().numpy()
         nan = float("nan")
         lbox = lconf = lcls = 0.0
-        met = {k: 0.0 for k in ("mean_ciou", "conf_loss", "avg_pos_conf", "avg_neg_conf", "class_loss", "accuracy", "f1", "precision", "recall")}
+        per = {k: [] for k in ("mean_ciou", "conf_loss", "avg_pos_conf", "avg_neg_conf", "class_loss", "accuracy", "f1", "precision", "recall")}
         for s in range(3):
             M, N, nvalid = Ms[s], Ns[s], a[s, 7]
             box = a[s, 0] / M if M else nan
@@ -195,16 +195,22 @@ class AudioDetectionLoss(torch.nn.Module):
             lbox += 0.0 if box != box else box          # handle_nan (modules/_loss.py:178)
             lconf += self.SCALE_W[s] * conf
             lcls += 0.0 if cls != cls else cls
-            met["mean_ciou"] += (a[s, 1] / M if M else nan) / 3
-            met["conf_loss"] += conf / 3
-            met["avg_pos_conf"] += (a[s, 4] / M if M else nan) / 3
-            met["avg_neg_conf"] += (a[s, 5] / a[s, 6] if a[s, 6] else nan) / 3
-            met["class_loss"] += cls / 3
+            per["mean_ciou"].append(a[s, 1] / M if M else nan)
+            per["conf_loss"].append(conf)
+            per["avg_pos_conf"].append(a[s, 4] / M if M else nan)
+            per["avg_neg_conf"].append(a[s, 5] / a[s, 6] if a[s, 6] else nan)
+            per["class_loss"].append(cls)
             acc_, f1_, pr_, rc_ = _macro_metrics(cm[s]) if nvalid else (nan, nan, nan, nan)
-            met["accuracy"] += acc_ / 3
-            met["f1"] += f1_ / 3
-            met["precision"] += pr_ / 3
-            met["recall"] += rc_ / 3
+            per["accuracy"].append(acc_)
+            per["f1"].append(f1_)
+            per["precision"].append(pr_)
+            per["recall"].append(rc_)
+        # the reference averages the three scales with pandas DataFrame.mean(), which SKIPS NaN (modules/_loss.py:101-110): a
+        # scale without matches does not poison the metric; NaN only when all three are NaN
+        met = {}
+        for k, vals in per.items():
+            ok = [float(v) for v in vals if v == v]
+            met[k] = sum(ok) / len(ok) if ok else nan
         loss_v = (self.box_w * lbox + self.conf_w * lconf + self.class_w * lcls) * bscale
         met = {"aggregate_loss": float(loss_v), **{k: float(v) for k, v in met.items()}}
         return torch.tensor(loss_v, device=dev, dtype=torch.float32), grads, met
@@ -239,22 +245,31 @@ class FusedAdamEMA:
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_momentum: float = 0.0,
                  ema_N: int = 2000, use_ema: bool = False):
         self.params = [p for p in params]
-        dev = self.params[0].device
+        # like torch.optim.Adam (train.py:83-90), parameters that never receive a gradient are left alone: only tensors with
+        # requires_grad live in the arena (a frozen tensor - e.g. the anchors when train_anchors is false - would otherwise be
+        # stepped with g = weight_decay * p and drift).  state_dict() still indexes ALL parameters, as Adam's does.
+        self.active = [i for i, p in enumerate(self.params) if p.requires_grad]
+        if not self.active:
+            raise ValueError("FusedAdamEMA: no parameter requires a gradient")
+        dev = self.params[self.active[0]].device
         if dev.type != "cuda":
             raise RuntimeError("FusedAdamEMA needs CUDA parameters (no CPU fallback)")
         self.dev = dev
         self.lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.step_count = 0
-        n = sum(p.numel() for p in self.params)
+        n = sum(self.params[i].numel() for i in self.active)
         self.flat = torch.empty(n, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.offsets = {}
         o = 0
-        for p in self.params:
+        for i in self.active:
+            p = self.params[i]
             k = p.numel()
             self.flat[o:o + k].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + k].view_as(p.data)
             p.grad = self.grad[o:o + k].view_as(p.data)
+            self.offsets[i] = (o, k)
             o += k
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
@@ -269,9 +284,42 @@ class FusedAdamEMA:
         self.grad.zero_()
 
     def allreduce_grads(self):
-        """Average the flat gradient arena across the data-parallel ranks (one bucketed NCCL all-reduce)."""
+        """Average the flat gradient arena across the data-parallel ranks (one bucketed NCCL all-reduce).
+        Serial form: call it after ``loss.backward()``.  See ``overlap_allreduce`` for the overlapped form."""
         from .parallel import allreduce_mean_
         allreduce_mean_(self.grad)
+
+    def overlap_allreduce(self, model) -> None:
+        """Bucket the gradient all-reduce behind the backward (pipeline/_trainer.py:94-108 under data parallelism):
+        the train engine reports each gradient bucket as soon as its last kernel is enqueued (neck + layer4 = 75 % of the bytes
+        after ~15 % of the backward) and this optimizer launches that bucket's asynchronous all-reduce on NCCL's stream; call
+        ``wait_allreduce()`` between ``loss.backward()`` and ``step()``.  The buckets are contiguous ranges of the flat arena."""
+        eng = model._train_engine()
+        pos = {id(self.params[i]): oc for i, oc in self.offsets.items()}
+        self._buckets = []
+        for plist in eng.bucket_params():
+            rng = [pos[id(p)] for p in plist if id(p) in pos]
+            if not rng:
+                self._buckets.append(None)
+                continue
+            # contiguous runs of the bucket's parameters in the arena (module order puts the stem's conv2 after layer4, so two of
+            # the three buckets are two runs each)
+            runs = []
+            for o, k in sorted(rng):
+                if runs and runs[-1][1] == o:
+                    runs[-1][1] = o + k
+                else:
+                    runs.append([o, o + k])
+            self._buckets.append([tuple(r) for r in runs])
+        from .parallel import BucketedAllReduce
+        self._bar = BucketedAllReduce(self.grad, self._buckets)
+        eng.on_bucket = self._bar.ready
+
+    def wait_allreduce(self) -> None:
+        """Make the current stream wait for the bucket all-reduces launched during the backward."""
+        bar = getattr(self, "_bar", None)
+        if bar is not None:
+            bar.wait()
 
     def step(self):
         self.step_count += 1
@@ -288,14 +336,13 @@ class FusedAdamEMA:
     def state_dict(self) -> dict:
         """The layout of ``torch.optim.Adam.state_dict()`` (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``, one param group),
         so checkpoints written here load into the reference's Adam and vice versa."""
-        state, o = {}, 0
-        for i, p in enumerate(self.params):
-            k = p.numel()
+        state = {}
+        for i, (o, k) in self.offsets.items():
+            p = self.params[i]
             if self.step_count > 0:
                 state[i] = {"step": torch.tensor(float(self.step_count)),
                             "exp_avg": self.m[o:o + k].view_as(p.data).clone(),
                             "exp_avg_sq": self.v[o:o + k].view_as(p.data).clone()}
-            o += k
         group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
@@ -309,17 +356,15 @@ class FusedAdamEMA:
         if g.get("amsgrad") or g.get("maximize") or g.get("decoupled_weight_decay"):
             raise NotImplementedError("FusedAdamEMA: amsgrad / maximize / decoupled weight decay are not built")
         self.lr, self.betas, self.eps, self.wd = float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])
-        steps, o = set(), 0
+        steps = set()
         self.m.zero_()
         self.v.zero_()
-        for i, p in enumerate(self.params):
-            k = p.numel()
+        for i, (o, k) in self.offsets.items():
             st = sd["state"].get(i, sd["state"].get(str(i)))
             if st is not None:
                 self.m[o:o + k].copy_(st["exp_avg"].reshape(-1))
                 self.v[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
                 steps.add(int(float(st["step"])))
-            o += k
         if len(steps) > 1:
             raise NotImplementedError("FusedAdamEMA: per-parameter step counts differ (one fused bias correction per step)")
         self.step_count = steps.pop() if steps else 0
@@ -350,8 +395,10 @@ def load_checkpoint(path: str, model, device=None, optimizer=None):
 
 
 class EMAParamsSmoothener:
-    """Drop-in for smoothener/_ema.py:7-32 (parameters only; warm-up momentum) using one fused launch per
-    update over flattened parameter arenas."""
+    """Drop-in for smoothener/_ema.py:7-32 (parameters only; warm-up momentum).  The update is two ``torch._foreach`` calls over
+    the parameter lists (ATen multi-tensor kernels, not a kernel of this library); the train step's own EMA is fused into
+    ``FusedAdamEMA`` (``yad_adam_ema_step``).  Every update bumps ``_lib.param_epoch`` so an ``ema_model`` in eval mode re-packs
+    its weights instead of running stale ones (in-place ``.data`` writes do not change ``tensor._version``)."""
 
     def __init__(self, model, momentum: float = 0.002, num_updates: int = 0, N: int = 2_000):
         self.model = model
@@ -370,9 +417,11 @@ class EMAParamsSmoothener:
             src = [p.data for e, p in zip(self.ema_model.parameters(), self.model.parameters()) if e.dtype.is_floating_point]
             torch._foreach_mul_(ema, 1 - m)
             torch._foreach_add_(ema, src, alpha=m)
+        _lib.param_epoch += 1
 
     def get_ema_state_dict(self):
         return self.ema_model.state_dict()
 
     def load_state_dict(self, state_dict):
         self.ema_model.load_state_dict(state_dict)
+        _lib.param_epoch += 1
