@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace yad {
 
@@ -20,6 +21,13 @@ void set_error(const char* fmt, ...) {
 }
 void* tensor_map_encode_fn() { return g_encode; }
 int sm_count() { return g_sm_count; }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("YAD_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 int init_conv_tc_attrs();   // conv_tc.cu
 int init_conv_flat_attrs(); // conv_flat.cu

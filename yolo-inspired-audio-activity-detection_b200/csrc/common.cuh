@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include "../../include/yad_b200.h"
 
 namespace yad {
@@ -74,5 +75,35 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // driver entry point resolved by yad_init (no link-time libcuda dependency)
 void* tensor_map_encode_fn();
 int sm_count();
+
+// ---- programmatic dependent launch (PDL).  The inference step is a chain of ~60 short kernels on one stream; with the
+// cudaLaunchAttributeProgrammaticStreamSerialization attribute kernel N+1 is launched while kernel N still runs, executes its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, constant tables) and blocks in pdl_wait() until kernel N has
+// completed and flushed its memory.  Rules every kernel launched through launch_pdl follows:
+//   * pdl_wait() before the first access to any buffer another kernel writes or reads (only launch-constant tables before it);
+//   * pdl_trigger() only AFTER the CTA holds every resource it will ever need (TMEM columns in particular): a dependent CTA that
+//     became resident earlier could otherwise hold the columns this CTA is waiting for while itself waiting for this grid.
+// YAD_PDL=0 in the environment launches everything fully serialised.
+bool pdl_enabled();
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace yad

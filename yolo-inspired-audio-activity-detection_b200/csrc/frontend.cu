@@ -143,11 +143,12 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
   const int64_t g_first = (int64_t)blockIdx.x * p.groups_per_cta;
   if (g_first >= p.total_groups) return;
   const int n_my = (int)min((int64_t)p.groups_per_cta, p.total_groups - g_first);
-  // start sample (in the zero-padded clip) of group gl and its clip
-  auto group_x0 = [&](int64_t gl, int64_t& clip) {
-    clip = gl / p.n_groups;
-    return (gl - clip * p.n_groups) * p.HG * p.O - p.width;
-  };
+  // (clip, group inside the clip) of this CTA's first group: the only division of the kernel; every thread then walks its own
+  // counters (the int64 divisions per group were 6 % of all executed instructions)
+  const int64_t clip_first = g_first / p.n_groups;
+  const int g_in_first = (int)(g_first - clip_first * p.n_groups);
+  // start sample (in the zero-padded clip) of group g of a clip
+  auto group_x0 = [&](int g) { return (int64_t)g * (p.HG * p.O) - p.width; };
   __shared__ __align__(8) uint64_t s_bar[2];    // completion of the bulk copy into staging buffer 0 / 1
   int shift = 0;
   bool bulk = false;
@@ -157,12 +158,11 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
       mbar_init(&s_bar[1], 1);
       fence_barrier_init();
     }
-    int64_t clip;
-    const int64_t x0 = group_x0(g_first, clip);
+    const int64_t x0 = group_x0(g_in_first);
     if (I16)
-      shift = fe_stage_async<int16_t, 8>(s_raw, x16 + clip * p.L, x0, p.SX, p.L, fast, rt, &s_bar[0], bulk);
+      shift = fe_stage_async<int16_t, 8>(s_raw, x16 + clip_first * p.L, x0, p.SX, p.L, fast, rt, &s_bar[0], bulk);
     else
-      shift = fe_stage_async<float, 4>(s_x, xf + clip * p.L, x0, p.SX, p.L, fast, rt, &s_bar[0], bulk);
+      shift = fe_stage_async<float, 4>(s_x, xf + clip_first * p.L, x0, p.SX, p.L, fast, rt, &s_bar[0], bulk);
   }
 
   for (int i = tid; i < FE_NFFT; i += FE_THREADS) {
@@ -238,6 +238,11 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
       }
     }
     uint32_t bar_phase = 0u;     // bit b: parity of the next completion on s_bar[b]
+    int64_t clip_n = clip_first;   // (clip, group in clip) of the group being STAGED (one ahead of the one being resampled)
+    int g_n = g_in_first, gcl = g_in_first;
+    // output position of this thread's first quad-hop inside the group: frame f0, sample pos0; it advances by nslice * P
+    const int o0 = sl * p.P + 4 * quad, o_step = p.nslice * p.P;
+    const int f0 = o0 / FE_NFFT, pos0 = o0 - f0 * FE_NFFT;
     for (int gi = 0; gi < n_my; ++gi) {
       const int buf = gi & 1;
       cp_async_wait_all();
@@ -253,14 +258,15 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
       }
       int shift_next = 0;
       bool bulk_next = false;
+      gcl = g_n;                                             // group inside its clip of the group resampled now
+      if (++g_n == p.n_groups) { g_n = 0; ++clip_n; }
       if (gi + 1 < n_my) {
-        int64_t clip;
-        const int64_t x0n = group_x0(g_first + gi + 1, clip);
+        const int64_t x0n = group_x0(g_n);
         if (I16)
-          shift_next = fe_stage_async<int16_t, 8>(s_raw + (buf ^ 1) * sxp, x16 + clip * p.L, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1],
+          shift_next = fe_stage_async<int16_t, 8>(s_raw + (buf ^ 1) * sxp, x16 + clip_n * p.L, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1],
                                                   bulk_next);
         else
-          shift_next = fe_stage_async<float, 4>(s_x + (buf ^ 1) * sxp, xf + clip * p.L, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1],
+          shift_next = fe_stage_async<float, 4>(s_x + (buf ^ 1) * sxp, xf + clip_n * p.L, x0n, p.SX, p.L, fast, rt, &s_bar[buf ^ 1],
                                                 bulk_next);
       }
       if (gi >= 2) bar_sync(BAR_EMPTY0 + buf, FE_THREADS);   // FFT role released this frame buffer
@@ -268,8 +274,8 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
         const float* sx = (I16 ? s_xf : s_x + buf * sxp) + shift + base;
         float* fr = s_fr + buf * FE_FR_WORDS;
         // taper_input (modules/_architecture.py:87-94): the resampled signal times a clip-long window, before framing
-        const int64_t gcl = (g_first + gi) % p.n_groups;           // group inside its clip
-        const float* tpg = TAPER ? taper + gcl * (FE_FR * FE_NFFT) : nullptr;
+        const float* tpg = TAPER ? taper + (int64_t)gcl * (FE_FR * FE_NFFT) : nullptr;
+        int f = f0, pos = pos0;
         for (int h = sl; h < p.HG; h += p.nslice) {
           const float* xs = sx + h * p.O;
           float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);
@@ -280,11 +286,10 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
             a01 = __ffma2_rn(tq01[j], xx, a01);
             a23 = __ffma2_rn(tq23[j], xx, a23);
           }
-          const int o = h * p.P + 4 * quad;
-          const int f = o / FE_NFFT, pos = o - f * FE_NFFT;
           const float4 w = *reinterpret_cast<const float4*>(s_win + pos);
           if (TAPER) {       // (x * taper) * hann, in the reference's order; samples past the window (unused tail frames) get 0
-            const int64_t n = gcl * (FE_FR * FE_NFFT) + o;
+            const int o = h * p.P + 4 * quad;
+            const int64_t n = (int64_t)gcl * (FE_FR * FE_NFFT) + o;
             const float4 tp = n + 4 <= p.taper_len ? __ldg(reinterpret_cast<const float4*>(tpg + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
             a01 = __fmul2_rn(a01, make_float2(tp.x, tp.y));
             a23 = __fmul2_rn(a23, make_float2(tp.z, tp.w));
@@ -292,6 +297,8 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
           a01 = __fmul2_rn(a01, make_float2(w.x, w.y));
           a23 = __fmul2_rn(a23, make_float2(w.z, w.w));
           *reinterpret_cast<float4*>(fr + f * (2 * FFT_Z_STRIDE) + pos) = make_float4(a01.x, a01.y, a23.x, a23.y);
+          pos += o_step;
+          while (pos >= FE_NFFT) { pos -= FE_NFFT; ++f; }
         }
       }
       __threadfence_block();
@@ -304,14 +311,20 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
     // pass-A work items (frame fA, column n2): half-warp h of warps 0..3 takes frame h, n2 = 0..15 (16 consecutive slots for
     // every load / store; both halves read the same twiddles: broadcast); warp 4 takes n2 = 16..19 of all 8 frames.
     // (The plain item = 20 f + n2 order cost 3.2 shared-memory wavefronts per 64-bit access instead of 2.)
-    const bool actA = rt < FE_FR * 20, actB = rt < FE_FR * 25;
-    const int fA = rt < 128 ? (rt >> 4) : ((rt - 128) >> 2);
-    const int n2 = rt < 128 ? (rt & 15) : 16 + (rt & 3);
+    // Warp placement: a role's warp w sits on SM sub-partition w % 4.  Pass A (160 items = 5 warps) runs on warps 3..7 and pass B
+    // (200 items = 6.25 warps) on warps 0..6, so that every sub-partition carries 3 of the 12 pass-warps (with both passes on
+    // warps 0.. the first sub-partition had 4 and the last 2); the mel pass pairs a short with a long band group per
+    // sub-partition (see below).
+    constexpr int A_FIRST = FE_ROLE - FE_FR * 20;
+    const bool actA = rt >= A_FIRST, actB = rt < FE_FR * 25;
+    const int ia = rt - A_FIRST;
+    const int fA = ia < 128 ? (ia >> 4) : ((ia - 128) >> 2);
+    const int n2 = ia < 128 ? (ia & 15) : 16 + (ia & 3);
     const int fB = rt / 25, k1 = rt - fB * 25;
+    int64_t b = clip_first;
+    int g = g_in_first;
     for (int gi = 0; gi < n_my; ++gi) {
       const int buf = gi & 1;
-      const int64_t b = (g_first + gi) / p.n_groups;
-      const int g = (int)((g_first + gi) - b * p.n_groups);
       cf32* zf = reinterpret_cast<cf32*>(s_fr + buf * FE_FR_WORDS);
       cf32* yf = reinterpret_cast<cf32*>(s_Y);
       bar_sync(BAR_FULL0 + buf, FE_THREADS);
@@ -347,8 +360,13 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
       }
       bar_sync(BAR_FT, FE_ROLE);
       // ---- real-FFT untangle + power: X[k] = E + W^k O ; X[500-k] = conj(E - W^k O); one thread owns the pair
-      for (int item = rt; item < FE_NPAIR; item += FE_ROLE) {
-        const int f = item / 251, k = item - f * 251;
+      //      (warp = frame, lane walks k: no division, consecutive 8-byte accesses; fully unrolled so that the loads of all 8
+      //      pairs are in flight together - the pass is a chain of dependent packed operations behind a shared-memory load)
+      const int f_u = rt >> 5;
+#pragma unroll
+      for (int ku = 0; ku < 8; ++ku) {
+        const int f = f_u, k_raw = (rt & 31) + 32 * ku;
+        const int k = k_raw > 250 ? 250 : k_raw;                    // lanes past the last pair recompute it; only the store is predicated
         const cf32* zb = zf + f * FFT_X_STRIDE;
         const cf32 zk = zb[k];
         const cf32 zq = zb[k == 0 ? 0 : 500 - k];
@@ -360,8 +378,10 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
         const cf32 Pv = cadd(E2, T2), Qv = csub(E2, T2);            // 2 X[k], 2 conj(X[500-k])
         const cf32 Ps = __fmul2_rn(Pv, Pv), Qs = __fmul2_rn(Qv, Qv);
         float* pp = s_P + f * FE_P_STRIDE;
-        pp[k] = Ps.x + Ps.y;                                        // 4 |X[k]|^2 (the 1/4 lives in the mel weights: exact)
-        pp[500 - k] = Qs.x + Qs.y;
+        if (k_raw <= 250) {
+          pp[k] = Ps.x + Ps.y;                                      // 4 |X[k]|^2 (the 1/4 lives in the mel weights: exact)
+          pp[500 - k] = Qs.x + Qs.y;
+        }
       }
       bar_sync(BAR_FT, FE_ROLE);      // power spectrum complete; the frame buffer is no longer read
       if (gi + 2 < n_my) {
@@ -373,13 +393,16 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
       //      (Tried and measured slower: a 4-way split of every band across lanes with shuffle reduction - 2.3x the
       //      instructions; deferring the pass to the warps that idle during the next group's pass A - 18 % slower.)
       {
-        const int f = rt & (FE_FR - 1), m = rt >> 3;
+        // band group (4 adjacent bands) of a warp: warps w and w + 4 share a sub-partition and take groups w and 7 - w (the
+        // bands widen with frequency: 7 .. 77 bins)
+        const int wr = rt >> 5, mg = wr < 4 ? wr : 11 - wr;
+        const int f = rt & (FE_FR - 1), m = 4 * mg + ((rt & 31) >> 3);
         const int64_t t = (int64_t)g * FE_FR + f;
         const float2* pp = reinterpret_cast<const float2*>(s_P + f * FE_P_STRIDE + s_fbs[FE_NMEL + 1 + m]);
         const int s0 = s_fbs[m], n4 = (s_fbs[m + 1] - s0) >> 2;
         const float2* fv = reinterpret_cast<const float2*>(s_fbv + s0);
         float2 acc01 = make_float2(0.0f, 0.0f), acc23 = make_float2(0.0f, 0.0f);
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < n4; ++i) {
           const float2 p01 = pp[2 * i], p23 = pp[2 * i + 1];
           const float2 w01 = fv[2 * i], w23 = fv[2 * i + 1];
@@ -389,6 +412,7 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
         const float acc0 = acc01.x, acc1 = acc01.y, acc2 = acc23.x, acc3 = acc23.y;
         if (t < p.T) mel[(b * FE_NMEL + m) * p.T + t] = (acc0 + acc1) + (acc2 + acc3);
       }
+      if (++g == p.n_groups) { g = 0; ++b; }
     }
   }
 }
