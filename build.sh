@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        --expt-relaxed-constexpr -I"$ROOT/include")
 mkdir -p "$SRC/build"
 pids=()
-for f in api frontend conv_simt conv_tc conv_flat conv_stem_tc conv_stem_fused conv_tf32 glue decode_nms train_ops loss train_net anchors; do
+for f in api frontend conv_simt conv_tc conv_flat conv_stem_tc conv_stem_fused neck_fused conv_tf32 glue decode_nms train_ops loss train_net anchors; do
   [ -f "$SRC/$f.cu" ] || continue
   if [ ! -f "$SRC/build/$f.o" ] || [ "$SRC/$f.cu" -nt "$SRC/build/$f.o" ] || [ "$SRC/common.cuh" -nt "$SRC/build/$f.o" ] || [ "$SRC/tc_ptx.cuh" -nt "$SRC/build/$f.o" ] || [ "$SRC/fft500.cuh" -nt "$SRC/build/$f.o" ] \
      || [ "$ROOT/include/yad_b200.h" -nt "$SRC/build/$f.o" ]; then

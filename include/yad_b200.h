@@ -216,6 +216,24 @@ int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* c
                        const int32_t* wk, int64_t k_total, const void* in, const void* weight, int32_t cout_pad,
                        const float* bias, const void* residual, void* out, yad_stream_t stream);
 
+/* ------------------------------------------------------------------ the whole neck as one kernel (bf16, H = 1, deploy form)
+ * Replaces MultiScaleFmapModule.forward, modules/_common.py:241-265, for the default ResNet backbone: H-means (:248-252),
+ * CSPSPPF (:204-215), both BiC blocks (:179-185), the four RepBlocks (:148-158, re-parameterised), the two stride-(1,2)
+ * downsample convs (:238-239) and the [B, G, 15] permute (:259-264).  One persistent CTA per SM runs a host-compiled program
+ * (yad_b200/neck_fused.py) clip by clip with every intermediate activation in shared memory (csrc/neck_fused.cu).
+ *   fmaps[4]            the backbone maps layer1..layer4 in the flat layout of yad_conv_flat ([B, Wp, Hp, C] bf16)
+ *   fmap_k[i]           Hp * C of map i (channels of one (b, w) column incl. the zero halo row: the H-mean is folded into K)
+ *   fmap_rows_per_clip  Wp of map i
+ *   wblob [wrows, 64]   bf16 weight blocks ([N x 64] per K block, stacked), bias [n_bias] f32
+ *   ops / kbs           the program (n_ops x 16 int32, n_kb x 2 int32; layouts in csrc/neck_fused.cu), device memory
+ *   pool_bytes, n_slots shared-memory plan: activation pool size and ring depth (16 KB slots)
+ *   heads[3]            fp32 outputs [B, head_W[i], head_ld] (sm, md, lg), first 3 * (3 + nc) channels valid
+ *   dbg                 optional bf16 buffer for the program's DUMP ops (NULL in production) */
+int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_t* fmap_rows_per_clip, int64_t B,
+                   const void* wblob, int64_t wrows, const float* bias, int32_t n_bias, const void* ops, int32_t n_ops,
+                   const void* kbs, int32_t n_kb, int32_t pool_bytes, int32_t n_slots, float* const* heads,
+                   const int32_t* head_W, int32_t head_ld, void* dbg, yad_stream_t stream);
+
 /* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
  * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5
  * :173-174,181-182; cascaded max_pool2d k5 s1 p2 :207-209.  All write into a channel slice

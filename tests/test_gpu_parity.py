@@ -815,6 +815,31 @@ def test_fused_stem_network_equals_two_conv_path(models, seconds, cuda_dev, monk
     assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
 
 
+@pytest.mark.parametrize("seconds,B", [(2.0, 3), (10.0, 2), (22.0, 5), (60.0, 3)])
+def test_fused_neck_equals_layer_by_layer_neck(models, seconds, B, cuda_dev, monkeypatch):
+    """The one-kernel neck (yad_neck_fused: H-means folded into K, every intermediate in shared memory; reference
+    modules/_common.py:241-265) against the layer-by-layer neck (YAD_FUSED_NECK=0: yad_hmean + 21 convolutions + glue kernels)
+    on the same bf16 deploy-form network, at clip lengths giving 1..2 M tiles per level (W1 = 8, 40, 88, 240).  They differ by
+    the bf16 rounding of the pooled maps only (the fused kernel accumulates the H-mean in fp32 inside the GEMM)."""
+    m = models[("deploy", "bf16")]
+    L = int(22050 * seconds) // 4 * 4
+    x = synth.synth_clips(B, L, seed=1300 + int(seconds), silence_tail_every=2).to(cuda_dev)
+    m._engine_cache.clear()
+    fused = m(x, combine_scales=True).clone()
+    eng = m._engine()
+    assert eng.fused_neck and any(v is not None for v in eng.__dict__.get("_fused_necks", {}).values())
+    monkeypatch.setenv("YAD_FUSED_NECK", "0")
+    m._engine_cache.clear()
+    plain = m(x, combine_scales=True).clone()
+    assert not m._engine().fused_neck
+    monkeypatch.delenv("YAD_FUSED_NECK")
+    m._engine_cache.clear()
+    assert torch.isfinite(fused).all()
+    d = (fused - plain).abs()
+    assert d[..., :3].max().item() < 0.1 and d[..., :3].mean().item() < 0.01, (d[..., :3].max().item(), d[..., :3].mean().item())
+    assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
+
+
 # ------------------------------------------------------------------ small kernels added for the 2-D neck / fused stem
 @pytest.mark.parametrize("dt", ["f32", "bf16"])
 def test_maxpool_h_and_2d_sppf_vs_torch(dt, cuda_dev):

@@ -21,12 +21,12 @@ void set_error(const char* fmt, ...) {
 }
 void* tensor_map_encode_fn() { return g_encode; }
 int sm_count() { return g_sm_count; }
-bool pdl_enabled() {
-  static const bool on = [] {
+int pdl_mode() {
+  static const int mode = [] {
     const char* e = getenv("YAD_PDL");
-    return !(e && e[0] == '0');
+    return e ? atoi(e) : 1;
   }();
-  return on;
+  return mode;
 }
 
 int init_conv_tc_attrs();   // conv_tc.cu
@@ -35,6 +35,7 @@ int init_frontend_attrs();  // frontend.cu
 int init_conv_stem_tc_attrs();  // conv_stem_tc.cu
 int init_conv_stem_fused_attrs();  // conv_stem_fused.cu
 int init_conv_tf32_attrs();  // conv_tf32.cu
+int init_neck_fused_attrs(); // neck_fused.cu
 
 }  // namespace yad
 
@@ -78,6 +79,8 @@ int yad_init(int device) {
   rc = yad::init_frontend_attrs();
   if (rc) return rc;
   rc = yad::init_conv_tf32_attrs();
+  if (rc) return rc;
+  rc = yad::init_neck_fused_attrs();
   if (rc) return rc;
   yad::g_inited_device = device;
   return YAD_OK;

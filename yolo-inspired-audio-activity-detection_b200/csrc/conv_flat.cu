@@ -156,6 +156,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();          // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_trigger();
   const int rows_per_super = 128 * p.MT;
   const int n_boxes = p.patch_rows / FL_BOX_ROWS;
 
@@ -359,10 +361,8 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   }
   const int nsm = sm_count() > 0 ? sm_count() : 148;
   const int grid = p.n_super < nsm ? p.n_super : nsm;
-  conv_flat_kernel<<<grid, FL_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, p, bias,
-                                                                   reinterpret_cast<const __nv_bfloat16*>(residual),
-                                                                   reinterpret_cast<__nv_bfloat16*>(out));
-  YAD_LAUNCH_CHECK();
+  YAD_CUDA(launch_pdl(conv_flat_kernel, dim3((unsigned)grid), dim3(FL_THREADS), smem, (cudaStream_t)stream, map_a, map_w, p, bias,
+                      reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<__nv_bfloat16*>(out)));
   return YAD_OK;
 }
 

@@ -92,6 +92,8 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();          // programmatic dependent launch: the 117 KB weight load above overlapped the frontend's tail
+  pdl_trigger();
   const uint32_t p_addr = smem_u32(sP), b_addr = smem_u32(sB);
   const int q = warp & 3, half = warp >> 2;     // epilogue: TMEM lane quadrant, channel half
   const int r = q * 32 + lane;                  // pixel inside the segment
@@ -191,6 +193,8 @@ stem_fixup_kernel(const float* __restrict__ x, const StemFixupParams p, const fl
   const int nb = min(FX_CLIPS, p.B - b0);
   const int wo = p.col[ci], var = p.var[ci];
   const int tid = threadIdx.x;
+  pdl_wait();          // the fused stem kernel wrote approximate border columns: this kernel must overwrite them afterwards
+  pdl_trigger();
   for (int i = tid; i < FX_CLIPS * 2 * 32 * SF_KD; i += blockDim.x) {
     const int dw = i % SF_KD, hi = (i / SF_KD) % 32, c = (i / (SF_KD * 32)) % 2, bb = i / (SF_KD * 32 * 2);
     const int wi = 4 * wo - 9 + dw;
@@ -290,10 +294,9 @@ extern "C" int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, i
   p.cta_first[3] = n_int + n1 + n2;
   p.cta_first[4] = n_int + n1 + n2 + n3;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  conv_stem_fused_kernel<<<p.cta_first[4], SF_THREADS, stem_fused_smem_bytes(), (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint32_t*>(x_bf16_padded), p, reinterpret_cast<const uint4*>(w_classes), bias,
-      reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
-  YAD_LAUNCH_CHECK();
+  YAD_CUDA(launch_pdl(conv_stem_fused_kernel, dim3((unsigned)p.cta_first[4]), dim3(SF_THREADS), stem_fused_smem_bytes(), (cudaStream_t)stream,
+                      reinterpret_cast<const uint32_t*>(x_bf16_padded), p, reinterpret_cast<const uint4*>(w_classes), bias,
+                      reinterpret_cast<__nv_bfloat16*>(out_flat_bf16)));
   return YAD_OK;
 }
 
@@ -315,8 +318,7 @@ extern "C" int yad_conv_stem_fused_fixup(const float* x_nchw, int64_t B, int32_t
   for (int i = 0; i < 8; ++i) p.col[i] = i < n_cols ? cols[i] : 0, p.var[i] = i < n_cols ? col_var[i] : 0;
   const int rcls[8] = {1, 2, 0, 0, 0, 0, 0, 3};
   for (int i = 0; i < 8; ++i) p.row_class[i] = rcls[i];
-  stem_fixup_kernel<<<dim3((unsigned)n_cols, (unsigned)((B + FX_CLIPS - 1) / FX_CLIPS)), FX_THREADS, 0, (cudaStream_t)stream>>>(x_nchw, p, w_var, bias,
-                                                                                         reinterpret_cast<__nv_bfloat16*>(out_flat_bf16));
-  YAD_LAUNCH_CHECK();
+  YAD_CUDA(launch_pdl(stem_fixup_kernel, dim3((unsigned)n_cols, (unsigned)((B + FX_CLIPS - 1) / FX_CLIPS)), dim3(FX_THREADS), 0,
+                      (cudaStream_t)stream, x_nchw, p, w_var, bias, reinterpret_cast<__nv_bfloat16*>(out_flat_bf16)));
   return YAD_OK;
 }

@@ -109,6 +109,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; its results are visible from here
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -422,8 +425,7 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
     if (rc) return rc;
   }
   dim3 grid((unsigned)(p.n_wt * p.n_ht * p.n_bt), (unsigned)p.n_ntiles);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], map_w, p, bias,
-                                                                  reinterpret_cast<const __nv_bfloat16*>(residual), out, out2_f32);
-  YAD_LAUNCH_CHECK();
+  YAD_CUDA(launch_pdl(conv_tc_kernel, grid, dim3(TC_THREADS), smem, (cudaStream_t)stream, maps[0], maps[1], maps[2], maps[3], map_w, p, bias,
+                      reinterpret_cast<const __nv_bfloat16*>(residual), out, out2_f32));
   return YAD_OK;
 }

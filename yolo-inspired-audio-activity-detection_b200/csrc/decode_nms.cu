@@ -22,6 +22,8 @@ struct DecodeParams {
 
 template <typename T>
 __global__ void decode_kernel(DecodeParams p, int64_t B, float* __restrict__ preds) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * p.rows_total) return;
   const int64_t b = gid / p.rows_total;
@@ -84,6 +86,8 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
            float* __restrict__ conf_out, float* __restrict__ boxes_out, float* __restrict__ seg_rows,
            int32_t* __restrict__ n_seg_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   const int E = 3 + nc;
   const int W = (P + 31) >> 5;  // alive-mask words
@@ -250,6 +254,8 @@ __global__ void compact_kernel(const float* __restrict__ seg_rows, const int32_t
                                int64_t* __restrict__ total) {
   __shared__ long long s_base;
   __shared__ int s_part[32];
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -322,10 +328,9 @@ static int decode_impl(const void* const* heads, const int32_t* G, const int32_t
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   if (dtype == YAD_F32)
-    yad::decode_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(p, B, preds);
+    YAD_CUDA(yad::launch_pdl(yad::decode_kernel<float>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, p, B, preds));
   else
-    yad::decode_kernel<__nv_bfloat16><<<blocks, threads, 0, (cudaStream_t)stream>>>(p, B, preds);
-  YAD_LAUNCH_CHECK();
+    YAD_CUDA(yad::launch_pdl(yad::decode_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, p, B, preds));
   return YAD_OK;
 }
 
@@ -359,18 +364,16 @@ int yad_nms(const float* preds, int64_t B, int32_t P, int32_t nc, double iou_thr
   (void)W;
   if (smem > 48 * 1024)
     YAD_CUDA(cudaFuncSetAttribute(yad::nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  yad::nms_kernel<<<(unsigned)B, yad::NMS_THREADS, smem, (cudaStream_t)stream>>>(
-      preds, P, nc, iou_thr, conf_thr, duration, box_h, return_start_end, keep, n_keep, conf, boxes, seg_rows,
-      n_seg);
-  YAD_LAUNCH_CHECK();
+  YAD_CUDA(yad::launch_pdl(yad::nms_kernel, dim3((unsigned)B), dim3(yad::NMS_THREADS), smem, (cudaStream_t)stream, preds, (int)P, (int)nc,
+                           iou_thr, conf_thr, duration, box_h, (int)return_start_end, keep, n_keep, conf, boxes, seg_rows, n_seg));
   return YAD_OK;
 }
 
 int yad_compact_segments(const float* seg_rows, const int32_t* n_seg, int64_t B, int32_t P, float* segments,
                          int64_t* batch_idxs, int64_t* total, yad_stream_t stream) {
   YAD_CHECK_ARG(seg_rows && n_seg && segments && batch_idxs && total, "yad_compact_segments: null pointer");
-  yad::compact_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(seg_rows, n_seg, B, P, segments, batch_idxs, total);
-  YAD_LAUNCH_CHECK();
+  YAD_CUDA(yad::launch_pdl(yad::compact_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, seg_rows, n_seg, B, (int)P, segments,
+                           batch_idxs, total));
   return YAD_OK;
 }
 

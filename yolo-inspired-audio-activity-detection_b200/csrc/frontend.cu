@@ -33,7 +33,6 @@ constexpr int FE_THREADS = 2 * FE_ROLE;
 constexpr int FE_FR_WORDS = FE_FR * 2 * FFT_X_STRIDE;   // frame buffer (floats): frames in (stride FFT_Z_STRIDE), spectrum out (FFT_X_STRIDE)
 constexpr int FE_Y_WORDS = FE_FR * 2 * FFT_Y_STRIDE;    // pass-A -> pass-B exchange buffer
 constexpr int FE_P_STRIDE = 516;    // power-spectrum row pitch (= 4 mod 32: 8 frames x 4 adjacent bins hit 32 distinct banks)
-constexpr int FE_NPAIR = FE_FR * 251;
 
 // named barriers (0 is __syncthreads)
 constexpr int BAR_RS = 1, BAR_FT = 2, BAR_FULL0 = 3, BAR_EMPTY0 = 5;
@@ -130,6 +129,8 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
 
   const int tid = threadIdx.x;
   const int role = tid >> 8;          // 0: resample, 1: FFT / mel
+  pdl_wait();                         // programmatic dependent launch (the PCM may come from a kernel, e.g. the batch builder)
+  pdl_trigger();
   const int rt = tid & (FE_ROLE - 1);
   // Persistent CTAs: the B * n_groups frame groups of the batch are one flat sequence (clip-major) that is cut into gridDim.x
   // contiguous runs; group gl belongs to clip gl / n_groups.  The tables above are loaded once per CTA and the double-buffered
@@ -562,6 +563,8 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
   const int t = threadIdx.x;
   const bool act = t < T;
   for (int i = threadIdx.x; i < FE_NMEL * FE_NMEL; i += blockDim.x) s_dct[i] = dct[i];
+  pdl_wait();          // programmatic dependent launch: stage A's mel plane is complete and visible from here
+  pdl_trigger();
   auto fmax_op = [](float a, float c) { return fmaxf(a, c); };
   auto dadd_op = [](double a, double c) { return a + c; };
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
@@ -734,8 +737,8 @@ static int frontend_mel_impl(const void* pcm, bool i16, const float* taper, int6
                 "yad_frontend_mel_power: taper window shorter than T*1000 samples or not 16-byte aligned");
   p.taper_len = taper ? taper_len : 0;
 #define YAD_FE_LAUNCH(I16_, TAPER_)                                                                                          \
-  frontend_mel_kernel<I16_, TAPER_><<<grid, FE_THREADS, smem, (cudaStream_t)stream>>>(pcm, taper, p, taps, tap_base, lane_map, window, \
-                                                                                      twiddle, fb_val, fb_bin, fb_start, mel)
+  YAD_CUDA(launch_pdl(frontend_mel_kernel<I16_, TAPER_>, grid, dim3(FE_THREADS), smem, (cudaStream_t)stream, pcm, taper, p, taps,  \
+                      tap_base, lane_map, window, twiddle, fb_val, fb_bin, fb_start, mel))
   if (i16) {
     if (taper) YAD_FE_LAUNCH(true, true); else YAD_FE_LAUNCH(true, false);
   } else {
@@ -784,10 +787,9 @@ static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const fl
     const unsigned grid = (unsigned)(B < nsm ? B : nsm);
     const unsigned threads = (unsigned)((T + 31) / 32 * 32);
     const size_t smem = (size_t)(yad::FE_NMEL * yad::FE_NMEL + yad::FE_NMEL * T) * sizeof(float);
-    yad::frontend_finish_v2_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(mel, B, T, dct, top_db, standardise, x_spectral,
-                                                                                tap_meldb, tap_mfcc, tap_mfdb,
-                                                                                reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, bf_margin);
-    YAD_LAUNCH_CHECK();
+    YAD_CUDA(yad::launch_pdl(yad::frontend_finish_v2_kernel, dim3(grid), dim3(threads), smem, (cudaStream_t)stream, mel, B, T, dct, top_db,
+                             (int)standardise, x_spectral, tap_meldb, tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch,
+                             (int)bf_margin));
     return YAD_OK;
   }
   yad::frontend_finish_kernel<<<(unsigned)B, yad::FB_THREADS, 0, (cudaStream_t)stream>>>(

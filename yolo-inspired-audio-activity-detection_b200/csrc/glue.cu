@@ -25,6 +25,8 @@ __global__ void hmean_kernel(const T* __restrict__ in, int64_t B, int H, int W, 
 __global__ void hmean_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_t B, int H, int W, int C8, int ld_in,
                                     int64_t isw, int64_t ish, int64_t isb, __nv_bfloat16* __restrict__ out, int ld_out,
                                     int co_off) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t n = B * W * C8;
   if (gid >= n) return;
@@ -112,6 +114,8 @@ __device__ __forceinline__ uint4 bf8_pack(const float (&f)[8]) {
 
 __global__ void resize_w_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_t B, int W, int C8, int ld_in, int ci_off, int up,
                                        __nv_bfloat16* __restrict__ out, int ld_out, int co_off) {
+  pdl_wait();
+  pdl_trigger();
   const int Wo = up ? 2 * W : W / 2;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * Wo * C8) return;
@@ -140,6 +144,8 @@ __global__ void resize_w_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int
 
 __global__ void sppf_bf16x8_kernel(const __nv_bfloat16* __restrict__ in, int64_t B, int W, int C8, int C, int ld_in, int ci_off,
                                    __nv_bfloat16* __restrict__ out, int ld_out, int co_off) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= B * W * C8) return;
   const uint32_t g32 = (uint32_t)gid;            // 32-bit index arithmetic (the host checks the element count)
@@ -268,10 +274,9 @@ int yad_hmean(const void* in, int32_t dtype, int64_t B, int32_t H, int32_t W, in
       reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
     const int64_t n8 = B * W * (C / 8);
     YAD_CHECK_ARG(n8 < (1ll << 32), "yad_hmean: tensor too large for the 32-bit index path");
-    yad::hmean_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)in, B, H, W, C / 8, ld_in, (int64_t)in_sw, (int64_t)in_sh, (int64_t)in_sb, (__nv_bfloat16*)out,
-        ld_out, co_off);
-    YAD_LAUNCH_CHECK();
+    YAD_CUDA(yad::launch_pdl(yad::hmean_bf16x8_kernel, dim3((unsigned)((n8 + threads - 1) / threads)), dim3(threads), 0, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)in, B, H, W, C / 8, ld_in, (int64_t)in_sw, (int64_t)in_sh, (int64_t)in_sb,
+                             (__nv_bfloat16*)out, ld_out, co_off));
     return YAD_OK;
   }
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
@@ -294,9 +299,9 @@ int yad_resize_w(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t C,
   if (dtype == YAD_BF16 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ci_off % 8 == 0 && co_off % 8 == 0 &&
       reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && B * Wo * (int64_t)(C / 8) < (1ll << 32)) {
     const int64_t n8 = B * Wo * (C / 8);
-    yad::resize_w_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)in, B, W, C / 8, ld_in, ci_off, up, (__nv_bfloat16*)out, ld_out, co_off);
-    YAD_LAUNCH_CHECK();
+    YAD_CUDA(yad::launch_pdl(yad::resize_w_bf16x8_kernel, dim3((unsigned)((n8 + threads - 1) / threads)), dim3(threads), 0,
+                             (cudaStream_t)stream, (const __nv_bfloat16*)in, B, W, C / 8, ld_in, ci_off, up, (__nv_bfloat16*)out, ld_out,
+                             co_off));
     return YAD_OK;
   }
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
@@ -316,9 +321,9 @@ int yad_sppf_pools(const void* in, int32_t dtype, int64_t B, int32_t W, int32_t 
   if (dtype == YAD_BF16 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ci_off % 8 == 0 && co_off % 8 == 0 &&
       reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 && B * W * (int64_t)(C / 8) < (1ll << 32)) {
     const int64_t n8 = B * W * (C / 8);
-    yad::sppf_bf16x8_kernel<<<(unsigned)((n8 + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)in, B, W, C / 8, C, ld_in, ci_off, (__nv_bfloat16*)out, ld_out, co_off);
-    YAD_LAUNCH_CHECK();
+    YAD_CUDA(yad::launch_pdl(yad::sppf_bf16x8_kernel, dim3((unsigned)((n8 + threads - 1) / threads)), dim3(threads), 0,
+                             (cudaStream_t)stream, (const __nv_bfloat16*)in, B, W, C / 8, C, ld_in, ci_off, (__nv_bfloat16*)out, ld_out,
+                             co_off));
     return YAD_OK;
   }
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);

@@ -110,6 +110,7 @@ class InferenceEngine:
         self.lib = _RecLib(_lib.init(device.index if device.index is not None else torch.cuda.current_device()), self._tls)
         self.dtype = BF16 if compute_dtype == "bf16" else F32
         self.use_graphs = os.environ.get("YAD_INFER_GRAPHS", "1") != "0"
+        self.fused_neck = os.environ.get("YAD_FUSED_NECK", "1") != "0"
         self._threads_seen = set()
         self.tdtype = torch.bfloat16 if self.dtype == BF16 else torch.float32
         self.cfg = model.config
@@ -308,6 +309,19 @@ class InferenceEngine:
             rb = getattr(ms, nm)
             blocks = [rb.conv1] + (list(rb.blocks) if isinstance(rb.blocks, nn.Sequential) else [])
             self.rep[nm] = [self._rep(f"{nm}.{i}", b) for i, b in enumerate(blocks)]
+
+    def _fused_neck_for(self, geoms, fmaps):
+        """The compiled fused-neck program of this feature-map geometry (None when the geometry / model form is not covered:
+        the layer-by-layer path runs instead)."""
+        key = tuple(geoms)
+        cache = self.__dict__.setdefault("_fused_necks", {})
+        if key not in cache:
+            from .neck_fused import FusedNeck
+            try:
+                cache[key] = FusedNeck(self, [g_[0] for g_ in geoms], [g_[1] for g_ in geoms], [f.shape[3] for f in fmaps])
+            except (NotImplementedError, ValueError):
+                cache[key] = None
+        return cache[key]
 
     # ------------------------------------------------------------------ shapes
     def frames(self, L: int) -> int:
@@ -584,6 +598,14 @@ class InferenceEngine:
 
         # ---- neck (H = 1 after the H-mean; modules/_common.py:241-265)
         hs = [g_[0] for g_ in geoms]
+        if fast and self.fused_neck and taps is None and hs[0] != hs[1] != hs[2] != hs[3]:
+            fn = self._fused_neck_for(geoms, fmaps)
+            if fn is not None:
+                # the whole neck (H-means included) as ONE persistent kernel reading the flat backbone maps (neck_fused.cu)
+                h32 = _ceil(self.n_head, 4)
+                heads = [self._buf(plan, f"n{i + 2}f", B, 1, geoms[i + 1][1], h32, zero=True, dtype=torch.float32) for i in range(3)]
+                fn.run(self.lib, fmaps, heads, s())
+                return heads
         # the reference's chained comparison (modules/_common.py:248): the H-mean runs only when it is true; otherwise (equal
         # heights, i.e. the custom backbone) the neck stays 2-D and the heads are averaged over H at the very end (:259-261)
         pool_first = hs[0] != hs[1] != hs[2] != hs[3]

@@ -1,0 +1,288 @@
+"""Host-side compiler of the fused neck kernel (csrc/neck_fused.cu, C ABI ``yad_neck_fused``).
+
+``MultiScaleFmapModule.forward`` (reference: modules/_common.py:241-265) at H = 1, deploy form, becomes a PROGRAM: a list of
+ops (convolutions as lists of K blocks over shared-memory activation planes or over the backbone maps in global memory; the
+max-pool cascade; bilinear x2 / x0.5; the even / odd split in front of the stride-2 convs) plus a shared-memory plan (plane
+offsets from a first-fit allocator with explicit lifetimes) plus one weight blob in the order the kernel consumes it.  The
+kernel interprets the program once per clip; this module only decides WHAT runs and WHERE it lives.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+CONV, POOLS, PAIRAVG, UP2, DEINT, DUMP = 0, 1, 2, 3, 4, 5
+SLOT = 16384
+SMEM_MAX = 227 * 1024
+ACT_LRELU = _lib.ACT_LRELU
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class _Pool:
+    """First-fit allocator over 1024-byte units (planes must start on a swizzle-atom boundary)."""
+
+    def __init__(self):
+        self.live: Dict[int, int] = {}     # offset -> size (units)
+        self.high = 0
+
+    def alloc(self, nbytes: int) -> int:
+        n = _ceil(nbytes, 1024) // 1024
+        spans = sorted(self.live.items())
+        pos = 0
+        for off, sz in spans:
+            if off - pos >= n:
+                break
+            pos = max(pos, off + sz)
+        self.live[pos] = n
+        self.high = max(self.high, pos + n)
+        return pos * 1024
+
+    def free(self, off: int) -> None:
+        del self.live[off // 1024]
+
+
+class FusedNeck:
+    """Compiled neck for one input geometry.  ``eng`` is the InferenceEngine (packed convolutions ``eng.n`` / ``eng.rep``)."""
+
+    def __init__(self, eng, Hs: Sequence[int], Ws: Sequence[int], Cs: Sequence[int], debug: bool = False):
+        self.eng, self.dev = eng, eng.dev
+        self.Hs, self.Ws, self.Cs = list(Hs), list(Ws), list(Cs)
+        W1, W2, W3, W4 = Ws
+        if not (W1 == 2 * W2 and W2 == 2 * W3 and W3 == 2 * W4):
+            raise ValueError("feature-map widths do not nest")
+        for h in Hs:
+            if h & (h - 1):
+                raise NotImplementedError("fused neck: feature-map heights must be powers of two (exact 1/H in bf16)")
+        for nm, blocks in eng.rep.items():
+            if any("deploy" not in b for b in blocks) or len(blocks) != 2:
+                raise NotImplementedError("fused neck: re-parameterised (deploy) RepBlocks of two blocks only")
+        self.G = 1                                              # clips per CTA pass
+        self.lv = {}                                            # level -> geometry
+        for i, W in enumerate(Ws):
+            Wp = W + 1
+            R = self.G * Wp
+            self.lv[i + 1] = {"W": W, "Wp": Wp, "R": R, "n_mt": (R + 127) // 128, "bytes": _ceil(R + 2, 8) * 128}
+            if self.lv[i + 1]["n_mt"] > 4:
+                raise NotImplementedError("fused neck: clip too long (more than 4 M tiles per level)")
+        self.pool = _Pool()
+        self.ops: List[List[int]] = []
+        self.kbs: List[Tuple[int, int]] = []
+        self.wblocks: List[torch.Tensor] = []
+        self.wrows = 0
+        self.biases: List[torch.Tensor] = []
+        self.nbias = 0
+        self.debug = debug
+        self.dumps: Dict[str, Tuple[int, int, int]] = {}        # name -> (element offset, rows, level)
+        self.dump_elems = 0
+        self._build()
+        self._finish()
+
+    # ------------------------------------------------------------------ weights
+    @staticmethod
+    def _w4(cv) -> torch.Tensor:
+        return cv.w.view(cv.cout_pad, cv.kh, cv.kw, cv.cin_pad).float()
+
+    def _blk(self, cvs, kh: int, kw: int, chunk: int, scale: float = 1.0) -> torch.Tensor:
+        """[N, 64] weight block of K chunk ``chunk`` at tap (kh, kw); several convs are stacked along N (merged convolutions)."""
+        return torch.cat([self._w4(cv)[:, kh, kw, 64 * chunk:64 * chunk + 64] * scale for cv in cvs], 0)
+
+    # ------------------------------------------------------------------ program emission
+    def _plane(self, level: int) -> int:
+        return self.pool.alloc(self.lv[level]["bytes"])
+
+    def _conv(self, cvs, level: int, kblocks, outs: List[int], head: int = -1, src_global: int = -1):
+        """kblocks: list of (src, shift, weight block [N, 64])."""
+        g = self.lv[level]
+        N = sum(cv.cout_pad for cv in cvs)
+        assert N in (16, 64, 128), N
+        assert g["n_mt"] * N <= 256, "accumulator does not fit the TMEM allocation"
+        assert len(outs) == (N + 63) // 64
+        kb_first = len(self.kbs)
+        for src, shift, wb in kblocks:
+            assert wb.shape == (N, 64), (wb.shape, N)
+            self.kbs.append((int(src), int(shift)))
+            self.wblocks.append(wb)
+        bias = torch.cat([cv.bias.float() for cv in cvs])
+        assert bias.numel() == N
+        op = [CONV, g["n_mt"], N, kb_first, len(kblocks), g["R"], g["Wp"], g["W"], self.nbias, outs[0], outs[1] if len(outs) > 1 else -1,
+              head, {16: 0, 64: 1, 128: 2}[N], self.wrows, src_global, ACT_LRELU]
+        for cv in cvs:
+            assert cv.act == ACT_LRELU
+        self.ops.append(op)
+        self.biases.append(bias)
+        self.nbias += N
+        self.wrows += N * len(kblocks)
+
+    def _taps3(self, cv, planes: List[int]):
+        """3-tap (1 x 3 at H = 1: the middle row of the 3 x 3 filter) stride-1 convolution over the given planes (= torch.cat)."""
+        assert cv.kh == 3 and cv.kw == 3 and cv.sh == 1 and cv.sw == 1 and cv.cin_pad == 64 * len(planes), (cv.name, cv.cin_pad, len(planes))
+        return [(pl, kw - 1, self._blk([cv], 1, kw, c)) for c, pl in enumerate(planes) for kw in range(3)]
+
+    def _taps1(self, cvs, planes: List[int]):
+        for cv in cvs:
+            assert cv.kh == 1 and cv.kw == 1 and cv.cin_pad == 64 * len(planes), (cv.name, cv.cin_pad, len(planes))
+        return [(pl, 0, self._blk(cvs, 0, 0, c)) for c, pl in enumerate(planes)]
+
+    def _taps_global(self, cvs, fi: int):
+        """1 x 1 convolution(s) of the H-mean of backbone map ``fi``: K runs over the Hp * C channels of a flat column."""
+        H, Cc = self.Hs[fi], self.Cs[fi]
+        Hp = H + 1 if H > 1 else 1
+        for cv in cvs:
+            assert cv.kh == 1 and cv.kw == 1 and cv.cin_pad == Cc, (cv.name, cv.cin_pad, Cc)
+        out = []
+        for h in range(Hp):
+            for c in range(Cc // 64):
+                wb = self._blk(cvs, 0, 0, c, 1.0 / H) if h < H else torch.zeros(sum(cv.cout_pad for cv in cvs), 64)
+                out.append((h * (Cc // 64) + c, 0, wb.to(self._w4(cvs[0]).device)))
+        return out
+
+    def _ew(self, typ: int, level_out: int, a: int, b: int, c: int = 0, d: int = 0, wp_in: int = 0):
+        g = self.lv[level_out]
+        self.ops.append([typ, a, b, c, d, g["R"], g["Wp"], g["W"], wp_in, 0, 0, 0, 0, 0, 0, 0])
+
+    def _dump(self, name: str, plane: int, level: int):
+        if not self.debug:
+            return
+        rows = self.lv[level]["bytes"] // 128
+        self.dumps[name] = (self.dump_elems, rows, level)
+        self.ops.append([DUMP, plane, rows, self.dump_elems, 0] + [0] * 11)
+        self.dump_elems += rows * 64
+
+    def _build(self):
+        n, rep, P, F = self.eng.n, self.eng.rep, self._plane, self.pool.free
+        lv = self.lv
+        # ---- CSPSPPF (modules/_common.py:204-215) at level 4; conv1 and conv2 read the same map: one N = 128 convolution
+        a1, y = P(4), P(4)
+        self._conv([n["sp1"], n["sp2"]], 4, self._taps_global([n["sp1"], n["sp2"]], 3), [a1, y], src_global=3)
+        self._dump("a1", a1, 4); self._dump("y", y, 4)
+        a2 = P(4)
+        self._conv([n["sp3"]], 4, self._taps3(n["sp3"], [a1]), [a2]); F(a1)
+        self._dump("a2", a2, 4)
+        a3 = P(4)
+        self._conv([n["sp4"]], 4, self._taps1([n["sp4"]], [a2]), [a3]); F(a2)
+        m1, m2, m3 = P(4), P(4), P(4)
+        self._ew(POOLS, 4, a3, m1, m2, m3)
+        self._dump("a3", a3, 4); self._dump("m1", m1, 4); self._dump("m3", m3, 4)
+        b1 = P(4)
+        self._conv([n["sp5"]], 4, self._taps1([n["sp5"]], [a3, m1, m2, m3]), [b1])
+        self._dump("b1", b1, 4)
+        for x in (a3, m1, m2, m3):
+            F(x)
+        b2 = P(4)
+        self._conv([n["sp6"]], 4, self._taps3(n["sp6"], [b1]), [b2]); F(b1)
+        p4 = [P(4), P(4)]
+        self._conv([n["sp7"]], 4, self._taps1([n["sp7"]], [b2, y]), p4); F(b2); F(y)
+        self._dump("p4_0", p4[0], 4); self._dump("p4_1", p4[1], 4)
+        # ---- BiC3 (:179-185): cat[conv_c1(f3'), pairavg(conv_c0(f2')), up2(p4)] -> conv_out; f2' also feeds BiC2's conv_c1
+        c1_3 = P(3)
+        self._conv([n["b3c1"]], 3, self._taps_global([n["b3c1"]], 2), [c1_3], src_global=2)
+        t, c1_2 = P(2), P(2)
+        self._conv([n["b3c0"], n["b2c1"]], 2, self._taps_global([n["b3c0"], n["b2c1"]], 1), [t, c1_2], src_global=1)
+        c0_3 = P(3)
+        self._ew(PAIRAVG, 3, t, c0_3, wp_in=lv[2]["Wp"]); F(t)
+        u3 = [P(3), P(3)]
+        for i in range(2):
+            self._ew(UP2, 3, p4[i], u3[i], wp_in=lv[4]["Wp"])
+        bic3 = [P(3), P(3)]
+        self._conv([n["b3o"]], 3, self._taps1([n["b3o"]], [c1_3, c0_3, u3[0], u3[1]]), bic3)
+        for x in (c1_3, c0_3, u3[0], u3[1]):
+            F(x)
+        self._dump("b3_0", bic3[0], 3)
+        r1 = [P(3), P(3)]
+        self._conv([rep["rep_block3_1"][0]["deploy"]], 3, self._taps3(rep["rep_block3_1"][0]["deploy"], bic3), r1); F(bic3[0]); F(bic3[1])
+        p3 = [P(3), P(3)]
+        self._conv([rep["rep_block3_1"][1]["deploy"]], 3, self._taps3(rep["rep_block3_1"][1]["deploy"], r1), p3); F(r1[0]); F(r1[1])
+        self._dump("p3_0", p3[0], 3); self._dump("p3_1", p3[1], 3)
+        # ---- BiC2
+        t1 = P(1)
+        self._conv([n["b2c0"]], 1, self._taps_global([n["b2c0"]], 0), [t1], src_global=0)
+        c0_2 = P(2)
+        self._ew(PAIRAVG, 2, t1, c0_2, wp_in=lv[1]["Wp"]); F(t1)
+        u2 = [P(2), P(2)]
+        for i in range(2):
+            self._ew(UP2, 2, p3[i], u2[i], wp_in=lv[3]["Wp"])
+        # the output of a convolution may overwrite its own inputs (the epilogue starts after the last MMA has retired)
+        bic2 = u2
+        self._conv([n["b2o"]], 2, self._taps1([n["b2o"]], [c1_2, c0_2, u2[0], u2[1]]), bic2); F(c1_2); F(c0_2)
+        self._dump("b2_0", bic2[0], 2); self._dump("b2_1", bic2[1], 2)
+        # ---- RepBlock2_1 -> n2 (sm head)
+        q1 = P(2)
+        self._conv([rep["rep_block2_1"][0]["deploy"]], 2, self._taps3(rep["rep_block2_1"][0]["deploy"], bic2), [q1]); F(bic2[0]); F(bic2[1])
+        n2 = P(2)
+        self._conv([rep["rep_block2_1"][1]["deploy"]], 2, self._taps3(rep["rep_block2_1"][1]["deploy"], [q1]), [n2], head=0); F(q1)
+        # ---- conv2_downsample (3 x 3, stride (1, 2), pad 1) on even / odd planes: out[k] = W0 odd[k-1] + W1 even[k] + W2 odd[k]
+        e2, o2 = P(3), P(3)
+        self._ew(DEINT, 3, n2, e2, o2, wp_in=lv[2]["Wp"]); F(n2)
+        d2 = [P(3), P(3)]
+        self._conv([n["ds2"]], 3, self._taps_s2(n["ds2"], e2, o2), d2); F(e2); F(o2)
+        q2 = P(3)
+        self._conv([rep["rep_block3_2"][0]["deploy"]], 3, self._taps3(rep["rep_block3_2"][0]["deploy"], p3 + d2), [q2])
+        for x in p3 + d2:
+            F(x)
+        n3 = P(3)
+        self._conv([rep["rep_block3_2"][1]["deploy"]], 3, self._taps3(rep["rep_block3_2"][1]["deploy"], [q2]), [n3], head=1); F(q2)
+        e3, o3 = P(4), P(4)
+        self._ew(DEINT, 4, n3, e3, o3, wp_in=lv[3]["Wp"]); F(n3)
+        d3 = [P(4), P(4)]
+        self._conv([n["ds3"]], 4, self._taps_s2(n["ds3"], e3, o3), d3); F(e3); F(o3)
+        q3 = P(4)
+        self._conv([rep["rep_block4_1"][0]["deploy"]], 4, self._taps3(rep["rep_block4_1"][0]["deploy"], p4 + d3), [q3])
+        for x in p4 + d3:
+            F(x)
+        n4 = P(4)
+        self._conv([rep["rep_block4_1"][1]["deploy"]], 4, self._taps3(rep["rep_block4_1"][1]["deploy"], [q3]), [n4], head=2); F(q3); F(n4)
+        assert not self.pool.live, self.pool.live
+
+    def _taps_s2(self, cv, even: int, odd: int):
+        assert cv.kh == 3 and cv.kw == 3 and (cv.sh, cv.sw) == (1, 2) and (cv.ph, cv.pw) == (1, 1) and cv.cin_pad == 64, cv.name
+        return [(odd, -1, self._blk([cv], 1, 0, 0)), (even, 0, self._blk([cv], 1, 1, 0)), (odd, 0, self._blk([cv], 1, 2, 0))]
+
+    def _finish(self):
+        dev = self.dev
+        self.pool_bytes = _ceil(self.pool.high * 1024, 1024)
+        tables = len(self.ops) * 64 + len(self.kbs) * 8 + self.nbias * 4 + 8 + 18 * 8 + 16
+        self.n_slots = min(8, (SMEM_MAX - 1024 - self.pool_bytes - tables) // SLOT)
+        need = 1 + max(op[1] for op in self.ops if op[0] == CONV and op[14] >= 0)     # A tiles of one K block + its weight block
+        if self.n_slots < need + 1:
+            raise NotImplementedError(f"fused neck: shared-memory plan does not fit (pool {self.pool_bytes} B, {self.n_slots} ring slots)")
+        self.wblob = torch.cat(self.wblocks, 0).to(dev, torch.bfloat16).contiguous()
+        # the last block of the blob may be read with a larger box than its N: pad so that every box stays inside the array
+        self.wblob = torch.cat([self.wblob, torch.zeros(128, 64, device=dev, dtype=torch.bfloat16)], 0).contiguous()
+        assert self.wblob.shape[0] == self.wrows + 128
+        self.bias = torch.cat(self.biases).to(dev, torch.float32).contiguous()
+        self.kbs_t = torch.tensor(self.kbs, dtype=torch.int32, device=dev).contiguous()
+        for op in self.ops:
+            if op[0] == DUMP:
+                op[4] = self.dump_elems          # per-clip stride of the debug buffer
+        self.ops_t = torch.tensor(self.ops, dtype=torch.int32, device=dev).contiguous()
+        assert self.ops_t.shape[1] == 16
+        self.dbg = torch.zeros(0, dtype=torch.bfloat16, device=dev)
+
+    # ------------------------------------------------------------------ launch
+    def run(self, lib, fmaps: Sequence[torch.Tensor], heads: Sequence[torch.Tensor], stream, dbg: Optional[torch.Tensor] = None):
+        """fmaps: the four flat backbone maps [B, Wp, Hp, C] bf16; heads: three fp32 tensors [B, 1, W, ld]."""
+        B = fmaps[0].shape[0]
+        fk, fr = [], []
+        for i, f in enumerate(fmaps):
+            _, Wp, Hp, Cc = f.shape
+            assert f.is_contiguous() and f.dtype == torch.bfloat16 and Wp == self.Ws[i] + 1 and Cc == self.Cs[i], (i, tuple(f.shape))
+            assert Hp == (self.Hs[i] + 1 if self.Hs[i] > 1 else 1)
+            fk.append(Hp * Cc)
+            fr.append(Wp)
+        ld = heads[0].shape[-1]
+        for i, h in enumerate(heads):
+            assert h.dtype == torch.float32 and h.is_contiguous() and h.shape[-1] == ld and h.shape[-2] == self.Ws[i + 1] and h.shape[0] == B
+        fm = (C.c_void_p * 4)(*[f.data_ptr() for f in fmaps])
+        hd = (C.c_void_p * 3)(*[h.data_ptr() for h in heads])
+        rc = lib.yad_neck_fused(fm, (C.c_int32 * 4)(*fk), (C.c_int32 * 4)(*fr), B, self.wblob.data_ptr(), self.wblob.shape[0],
+                                self.bias.data_ptr(), self.nbias, self.ops_t.data_ptr(), len(self.ops), self.kbs_t.data_ptr(), len(self.kbs),
+                                self.pool_bytes, self.n_slots, hd, (C.c_int32 * 3)(*self.Ws[1:]), ld,
+                                0 if dbg is None else dbg.data_ptr(), stream)
+        _lib.check(rc, "neck_fused")
