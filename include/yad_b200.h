@@ -186,6 +186,16 @@ int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int3
                 float* out2_f32 /* optional fp32 copy of the output, pitch ld_out2, may be NULL */,
                 int32_t ld_out2, yad_stream_t stream);
 
+/* yad_conv_tc plus the BasicBlock's downsample branch in the same launch (torchvision resnet.py:92-100 via
+ * modules/_backbone.py:148: `identity = self.downsample(x)` next to `out = relu(bn1(conv1(x)))`, both strided convolutions of
+ * the same x): the 1x1 stride-(sh, sw) pad-0 convolution reads exactly the input pixels of the main convolution's centre tap,
+ * so it runs as Cin / 64 extra K-blocks into a second TMEM accumulator and is written by the same epilogue.
+ *   weight_ds [cout_pad][Cin] bf16, bias_ds [cout_pad], act_ds its activation (YAD_ACT_NONE for the reference's downsample),
+ *   out_ds: bf16, same pixel strides / channel pitch (d->ld_out) as `out`.  Requires Cout == cout_pad, a multiple of 32, co_off 0.
+ * Both outputs are bitwise what two yad_conv_tc calls produce. */
+int yad_conv_tc_dual(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias, void* out,
+                     const void* weight_ds, const float* bias_ds, int32_t act_ds, void* out_ds, yad_stream_t stream);
+
 /* Patch-resident tcgen05 implicit GEMM for stride-1 'same' convolutions on the FLAT halo-padded layout:
  * pixel (b,h,w) of an activation lives at flat index f = (b*Wp + w)*Hp + h (h fastest), channel pitch ld; cells with
  * h >= H or w >= W are the (shared) zero halo: they are read as padding and never written, so the caller zero-fills
@@ -206,6 +216,14 @@ typedef struct {
 } yad_flat_desc;
 int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
                   const void* residual, void* out, int32_t flags, yad_stream_t stream);
+/* yad_conv_flat that also writes a SPACE-TO-DEPTH copy of its output for the stride-2 block that follows (torchvision
+ * resnet.py:92-100: the first BasicBlock of layer2..4 reads its input with stride 2 twice, conv1 and downsample):
+ *   out_s2d [B, Wp2, Hp2, 4 * Cout] bf16, pixel (b, h, w) -> cell (b, w / 2, h / 2), channel plane (h & 1) * 2 + (w & 1).
+ * On that copy a stride-2 convolution is a stride-1 flat convolution over (plane, shift) steps (yad_conv_flat_taps), i.e. it
+ * runs in the patch-resident kernel and reads every input element once.  Zero-filled by the caller once (halo cells). */
+int yad_conv_flat_s2d(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
+                      const void* residual, void* out, void* out_s2d, int32_t Hp2, int32_t Wp2, yad_stream_t stream);
+
 /* The same kernel with an explicit step list (kh/kw/ph/pw of d are ignored): step i reads the input channels
  * [64*chunk[i], 64*chunk[i]+64) at the flat shift dw[i]*Hp + dh[i] and multiplies them with the [cout_pad x 64] block
  * at K offset wk[i] of weight [cout_pad][k_total].  Steps must be grouped by ascending chunk; at most 64 steps.

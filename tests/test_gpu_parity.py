@@ -840,6 +840,50 @@ def test_fused_neck_equals_layer_by_layer_neck(models, seconds, B, cuda_dev, mon
     assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
 
 
+def _run_with_env(m, x, monkeypatch, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m._engine_cache.clear()
+    taps = {}
+    out = m(x, combine_scales=True, taps=taps).clone()
+    eng = m._engine()
+    for k in env:
+        monkeypatch.delenv(k)
+    m._engine_cache.clear()
+    return out, taps["fmaps"], eng
+
+
+@pytest.mark.parametrize("seconds,B", [(2.0, 3), (22.0, 2), (60.0, 2)])
+def test_stride2_block_routes_agree(models, seconds, B, cuda_dev, monkeypatch):
+    """First BasicBlock of layer2..4 (torchvision resnet.py:92-100 via modules/_backbone.py:148): conv1 (3x3 stride 2) and the
+    1x1 stride-2 downsample of the same input, three ways:
+      a) two tap-by-tap launches (yad_conv_tc; YAD_S2D=0 YAD_DUAL_DS=0),
+      b) one tap-by-tap launch with two TMEM accumulators (yad_conv_tc_dual; YAD_S2D=0): same tiles and K order -> bitwise a),
+      c) default: the previous layer also writes a space-to-depth copy (yad_conv_flat_s2d) and both convolutions run in the
+         patch-resident kernel over (plane, shift) steps (yad_conv_flat_taps): other K order -> equal up to fp32 summation order
+         and the bf16 rounding that follows (checked on the backbone maps and on the predictions)."""
+    m = models[("deploy", "bf16")]
+    L = int(22050 * seconds) // 4 * 4
+    x = synth.synth_clips(B, L, seed=1500 + int(seconds), silence_tail_every=0).to(cuda_dev)
+    out_a, fm_a, eng_a = _run_with_env(m, x, monkeypatch, {"YAD_S2D": "0", "YAD_DUAL_DS": "0"})
+    assert not eng_a.dual_ds and not eng_a.s2d_route
+    out_b, fm_b, eng_b = _run_with_env(m, x, monkeypatch, {"YAD_S2D": "0"})
+    assert eng_b.dual_ds and not eng_b.s2d_route
+    for a, b in zip(fm_a, fm_b):
+        assert torch.equal(a, b)
+    assert torch.equal(out_a, out_b)
+    out_c, fm_c, eng_c = _run_with_env(m, x, monkeypatch, {})
+    assert eng_c.s2d_route
+    for i, (a, c) in enumerate(zip(fm_a, fm_c)):
+        assert a.shape == c.shape and torch.isfinite(c).all()
+        d = (a - c).abs()
+        scale = a.abs().max().item()
+        assert d.max().item() <= 0.02 * scale + 1e-3 and d.mean().item() <= 5e-4 * scale, (i, d.max().item(), d.mean().item(), scale)
+    assert torch.equal(fm_a[0], fm_c[0])          # layer1 is untouched by the route
+    d = (out_a - out_c).abs()
+    assert d[..., :3].max().item() < 0.05 and d[..., 3].max().item() < 0.05 and d[..., 4].max().item() < 0.5
+
+
 # ------------------------------------------------------------------ small kernels added for the 2-D neck / fused stem
 @pytest.mark.parametrize("dt", ["f32", "bf16"])
 def test_maxpool_h_and_2d_sppf_vs_torch(dt, cuda_dev):

@@ -52,7 +52,9 @@ SIGNATURES = {
     "yad_conv_stem_tc": [_p, _i64, _i32, _i32, _p, _p, _i32, _i32, _p],
     "yad_conv_simt": [C.POINTER(ConvDesc), _i32, _p, _p, _i32, _p, _p, _p, _p],
     "yad_conv_tc": [C.POINTER(ConvDesc), _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p],
+    "yad_conv_tc_dual": [C.POINTER(ConvDesc), _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p],
     "yad_conv_flat": [C.POINTER(FlatDesc), _p, _p, _i32, _p, _p, _p, _i32, _p],
+    "yad_conv_flat_s2d": [C.POINTER(FlatDesc), _p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _p],
     "yad_conv_flat_taps": [C.POINTER(FlatDesc), _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i64, _p, _p,
                            _i32, _p, _p, _p, _p],
     "yad_hmean": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],

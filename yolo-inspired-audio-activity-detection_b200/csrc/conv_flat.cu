@@ -47,6 +47,8 @@ struct FlatParams {
   int32_t Cout, ld_out, co_off, ld_res, act;
   uint32_t idesc;
   int32_t flags;                // reserved (0)
+  int32_t s2d_Hp, s2d_Wp;       // second, space-to-depth copy of the output (0: none): pixel (b, h, w) goes to flat cell
+                                // (b * s2d_Wp + w / 2) * s2d_Hp + h / 2, channel plane (h & 1) * 2 + (w & 1) of 4 * Cout channels
   uint32_t step_mma[FL_MAX_STEPS];    // MMA warp: bits 0..15 = first patch row of the tap in 16-byte units, bit 30 = first
                                       // step of its chunk, bit 31 = last step of its chunk
   int16_t step_off[FL_MAX_STEPS];     // flat pixel shift of the tap
@@ -118,7 +120,8 @@ __device__ __forceinline__ void flat_mma_loop(const FlatParams& p, uint8_t* sm_a
 __global__ void __launch_bounds__(FL_THREADS, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ FlatParams p, const float* __restrict__ bias,
-                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out) {
+                 const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+                 __nv_bfloat16* __restrict__ out_s2d) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sm_a = smem;                                       // [NA][patch_bytes]
@@ -215,6 +218,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // residual prefetch for item 0 (independent of the accumulator): hides the HBM latency behind the barrier wait
       uint4 rq[4];
       // item j -> (output flat index, first channel, valid); the output may use other pitches than the input
+      uint32_t f2_cur = 0;          // element offset of the item's 32 channels in the space-to-depth copy
       auto item_geom = [&](int j, uint32_t& f, int& nbase, bool& ok) {
         const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
         f = fbase + 128u * (uint32_t)mt;
@@ -222,6 +226,9 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         nbase = n0 + 32 * (2 * cj + half);
         ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W && nbase < p.Cout;
         if (p.remap) f = (bb * (uint32_t)p.Wpo + w) * (uint32_t)p.Hpo + h;
+        if (p.s2d_Hp)
+          f2_cur = (((bb * (uint32_t)p.s2d_Wp + (w >> 1)) * (uint32_t)p.s2d_Hp + (h >> 1)) * 4u + ((h & 1u) << 1 | (w & 1u))) * (uint32_t)p.Cout +
+                   (uint32_t)nbase;
       };
       auto load_res = [&](uint32_t f, int nbase, bool ok) {
         if (residual != nullptr && ok) {
@@ -266,7 +273,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
         }
-        const uint32_t f_st = f_cur;
+        const uint32_t f_st = f_cur, f2_st = f2_cur;
         const int nb_st = nb_cur;
         const bool ok_st = ok_cur;
         if (j + 1 < n_items) {       // prefetch the next item's residual before the stores of this one
@@ -277,6 +284,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) x[jj] = apply_act(x[jj], p.act);
           uint4* op = reinterpret_cast<uint4*>(out + (int64_t)f_st * p.ld_out + p.co_off + nb_st);
+          uint4* op2 = reinterpret_cast<uint4*>(out_s2d + f2_st);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             uint32_t ww[4];
@@ -286,6 +294,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               ww[e] = *reinterpret_cast<uint32_t*>(&h2);
             }
             op[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+            if (p.s2d_Hp) op2[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
           }
         }
       }
@@ -318,7 +327,7 @@ namespace yad {
 // common launcher: the caller has filled the geometry / epilogue fields and the step lists (grouped by chunk)
 static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const void* in, int cin_total, int ld_in,
                        const void* weight, int64_t k_total, int cout_pad, const float* bias, const void* residual, void* out,
-                       yad_stream_t stream) {
+                       yad_stream_t stream, void* out_s2d = nullptr) {
   for (int i = 0; i < p.n_steps; ++i)
     p.step_mma[i] = (uint32_t)((p.step_off[i] - p.min_off) * 8) | (p.step_first[i] ? 1u << 30 : 0u) | (p.step_last[i] ? 1u << 31 : 0u);
   YAD_CHECK_ARG((max_off - p.min_off) * 8 < 65536, "yad_conv_flat: filter reach too large");
@@ -362,7 +371,8 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   const int nsm = sm_count() > 0 ? sm_count() : 148;
   const int grid = p.n_super < nsm ? p.n_super : nsm;
   YAD_CUDA(launch_pdl(conv_flat_kernel, dim3((unsigned)grid), dim3(FL_THREADS), smem, (cudaStream_t)stream, map_a, map_w, p, bias,
-                      reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<__nv_bfloat16*>(out)));
+                      reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<__nv_bfloat16*>(out),
+                      reinterpret_cast<__nv_bfloat16*>(out_s2d)));
   return YAD_OK;
 }
 
@@ -401,13 +411,19 @@ static int check_flat_common(const yad_flat_desc* d, const void* in, const void*
 
 }  // namespace yad
 
-extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad,
-                             const float* bias, const void* residual, void* out, int32_t flags, yad_stream_t stream) {
+static int conv_flat_impl(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
+                          const void* residual, void* out, void* out_s2d, int32_t Hp2, int32_t Wp2, yad_stream_t stream) {
   using namespace yad;
-  YAD_CHECK_ARG(flags == 0, "yad_conv_flat: flags must be 0");
   FlatParams p;
   int rc = check_flat_common(d, in, weight, cout_pad, bias, residual, out, p);
   if (rc) return rc;
+  if (out_s2d != nullptr) {
+    YAD_CHECK_ARG(Hp2 >= (d->H + 1) / 2 && Wp2 >= (d->W + 1) / 2 && reinterpret_cast<uintptr_t>(out_s2d) % 16 == 0 && d->Cout % 32 == 0 &&
+                      (int64_t)d->B * Wp2 * Hp2 * 4 * d->Cout < ((int64_t)1 << 32),
+                  "yad_conv_flat_s2d: space-to-depth pitches (%d,%d) too small for a %dx%d image, or tensor too large", Hp2, Wp2, d->H, d->W);
+    p.s2d_Hp = Hp2;
+    p.s2d_Wp = Wp2;
+  }
   YAD_CHECK_ARG(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 49 && d->ph >= 0 && d->pw >= 0 && d->ph < d->kh && d->pw < d->kw,
                 "yad_conv_flat: bad kernel/padding");
   YAD_CHECK_ARG(d->kh - 1 - d->ph == d->ph && d->kw - 1 - d->pw == d->pw, "yad_conv_flat: only 'same' (output size = input size) convs");
@@ -447,7 +463,21 @@ extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void*
   p.n_steps = ns;
   p.min_off = min_off;
   return launch_flat(p, n_chunks, max_off, in, d->Cin, d->ld_in, weight, (int64_t)d->kh * d->kw * d->Cin, cout_pad, bias, residual,
-                     out, stream);
+                     out, stream, out_s2d);
+}
+
+extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad,
+                             const float* bias, const void* residual, void* out, int32_t flags, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(flags == 0, "yad_conv_flat: flags must be 0");
+  return conv_flat_impl(d, in, weight, cout_pad, bias, residual, out, nullptr, 0, 0, stream);
+}
+
+extern "C" int yad_conv_flat_s2d(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
+                                 const void* residual, void* out, void* out_s2d, int32_t Hp2, int32_t Wp2, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(out_s2d != nullptr, "yad_conv_flat_s2d: null pointer");
+  return conv_flat_impl(d, in, weight, cout_pad, bias, residual, out, out_s2d, Hp2, Wp2, stream);
 }
 
 extern "C" int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* chunk, const int32_t* dh,

@@ -46,6 +46,10 @@ struct TcParams {
   int8_t tap_widx[TC_MAX_TAPS];
   int32_t cin;                   // K elements per tap in the packed weight
   int32_t osw, osh, osb;         // output pixel strides
+  // fused 1x1 downsample branch (torchvision BasicBlock.downsample, resnet.py:99-100): the strided 1x1 convolution of the same
+  // input reads exactly the pixels of the main convolution's centre tap, so it runs as ds_chunks extra K-blocks (tap entry
+  // n_taps, weights map_w2) into a second accumulator at TMEM column BN; 0 = no second branch
+  int32_t ds_chunks, ds_cin, act2;
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
@@ -65,8 +69,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
-               const __grid_constant__ CUtensorMap map_w, const TcParams p, const float* __restrict__ bias,
-               const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, float* __restrict__ out2) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w2, const TcParams p,
+               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual, void* __restrict__ out,
+               float* __restrict__ out2, const float* __restrict__ bias_ds, __nv_bfloat16* __restrict__ out_ds) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A 16 KB][B BN*128] | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -79,7 +84,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const int n_iters = p.n_taps * p.cin_chunks;
+  const int n_main = p.n_taps * p.cin_chunks;
+  const int n_iters = n_main + p.ds_chunks;
 
   // tile coordinates
   int t = blockIdx.x;
@@ -92,11 +98,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int n0 = blockIdx.y * p.BN;
 
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+  while ((int)tmem_cols < (p.ds_chunks ? 2 * p.BN : p.BN)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
     prefetch_tmap(&map_w);
+    if (p.ds_chunks) prefetch_tmap(&map_w2);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -118,9 +125,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (lane == 0) {
       const uint32_t tx_bytes = (uint32_t)(p.tb * p.th * p.tw * 128 + b_stage_bytes);
       uint32_t s = 0, phase = 0;     // ring (slot, phase): no integer division on the single-thread path
-      for (int tap = 0; tap < p.n_taps; ++tap) {
+      for (int tap = 0; tap < p.n_taps + (p.ds_chunks ? 1 : 0); ++tap) {
         const int mi = p.tap_map[tap];
         const CUtensorMap* ma = mi == 0 ? &map_a0 : (mi == 1 ? &map_a1 : (mi == 2 ? &map_a2 : &map_a3));
+        const CUtensorMap* mw = tap < p.n_taps ? &map_w : &map_w2;
         const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap];
         const int kbase = p.tap_widx[tap] * p.cin;
         for (int cc = 0; cc < p.cin_chunks; ++cc) {
@@ -129,7 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           uint8_t* sb = sa + TC_A_STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], tx_bytes);
           tma_load_4d(ma, &full_bar[s], sa, cc * TC_BK, cw, ch, b0);
-          tma_load_2d(&map_w, &full_bar[s], sb, kbase + cc * TC_BK, n0);
+          tma_load_2d(mw, &full_bar[s], sb, kbase + cc * TC_BK, n0);
           if (++s == (uint32_t)S) { s = 0; phase ^= 1; }
         }
       }
@@ -144,10 +152,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sb = sa + TC_A_STAGE_BYTES;
         const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sb);
+        const bool is_ds = it >= n_main;                     // K-blocks of the fused downsample branch: second accumulator
+        const uint32_t acc = tmem_base + (is_ds ? (uint32_t)p.BN : 0u);
+        const bool first = it == 0 || it == n_main;
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           // advance 16 bf16 = 32 B along K inside the swizzled 128 B row: +2 in the 16-byte address field
-          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (!first || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);                       // frees the smem stage when these MMAs retire
         if (it == n_iters - 1) umma_commit(tmem_full_bar);  // accumulator complete
@@ -233,6 +244,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
+    if (p.ds_chunks) {        // downsample branch: bias, activation act2, bf16, same pixel strides and row pitch as the main output
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.BN + c0), v);
+        tmem_ld_wait();
+        const int nbase = n0 + c0;
+        if (row_ok && nbase + 32 <= p.Cout) {
+          uint4* op = reinterpret_cast<uint4*>(out_ds + pix * p.ld_out + nbase);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 8 + e * 2;
+              const float x0 = apply_act(__uint_as_float(v[j]) + __ldg(bias_ds + nbase + j), p.act2);
+              const float x1 = apply_act(__uint_as_float(v[j + 1]) + __ldg(bias_ds + nbase + j + 1), p.act2);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+              w[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            op[j4] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -308,9 +343,10 @@ static void choose_tile(int B, int Ho, int Wo, int* tb, int* th, int* tw) {
 
 }  // namespace yad
 
-extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad,
-                           const float* bias, const void* residual, void* out, int32_t out_dtype,
-                           float* out2_f32, int32_t ld_out2, yad_stream_t stream) {
+static int conv_tc_impl(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad,
+                        const float* bias, const void* residual, void* out, int32_t out_dtype,
+                        float* out2_f32, int32_t ld_out2, const void* weight_ds, const float* bias_ds, int32_t act_ds, void* out_ds,
+                        yad_stream_t stream) {
   using namespace yad;
   YAD_CHECK_ARG(d && in && weight && bias && out, "yad_conv_tc: null pointer");
   YAD_CHECK_ARG(d->Cin % 64 == 0 && d->Cin >= 64, "yad_conv_tc: Cin=%d must be a multiple of 64 (zero-pad channels)", d->Cin);
@@ -383,6 +419,24 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
   }
   YAD_CHECK_ARG(n_taps >= 1, "yad_conv_tc: no tap touches the input");
   p.n_taps = n_taps;
+  if (weight_ds != nullptr) {
+    // the 1x1 stride-(sh, sw) pad-0 convolution of the same input = the centre tap (kh, kw) = (ph, pw) of the main convolution
+    YAD_CHECK_ARG(bias_ds && out_ds && d->ph < d->kh && d->pw < d->kw && n_taps < TC_MAX_TAPS && cout_pad % 32 == 0 && d->Cout == cout_pad &&
+                      out_dtype == YAD_BF16 && d->co_off == 0 && reinterpret_cast<uintptr_t>(weight_ds) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(out_ds) % 16 == 0,
+                  "yad_conv_tc_dual: needs a centre tap, Cout == cout_pad (a multiple of 32), bf16 output at co_off 0, aligned pointers");
+    int centre = -1;
+    for (int t = 0; t < n_taps; ++t)
+      if (p.tap_widx[t] == d->ph * d->kw + d->pw) centre = t;
+    YAD_CHECK_ARG(centre >= 0, "yad_conv_tc_dual: the centre tap is not part of the convolution");
+    p.tap_map[n_taps] = p.tap_map[centre];
+    p.tap_dh[n_taps] = p.tap_dh[centre];
+    p.tap_dw[n_taps] = p.tap_dw[centre];
+    p.tap_widx[n_taps] = 0;
+    p.ds_chunks = p.cin_chunks;
+    p.ds_cin = d->Cin;
+    p.act2 = act_ds;
+  }
 
   // pipeline depth: aim for two resident CTAs per SM (<= ~100 KB each) but at least 3 stages
   const int stage_bytes = TC_A_STAGE_BYTES + BN * 128;
@@ -424,8 +478,31 @@ extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* w
     int rc = encode_map_bf16(&map_w, weight, 2, dims, strides, bx);
     if (rc) return rc;
   }
+  CUtensorMap map_w2 = map_w;
+  if (weight_ds != nullptr) {
+    const uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)cout_pad};
+    const uint64_t strides[1] = {(uint64_t)d->Cin * 2};
+    const uint32_t bx[2] = {64u, (uint32_t)BN};
+    int rc = encode_map_bf16(&map_w2, weight_ds, 2, dims, strides, bx);
+    if (rc) return rc;
+  }
   dim3 grid((unsigned)(p.n_wt * p.n_ht * p.n_bt), (unsigned)p.n_ntiles);
-  YAD_CUDA(launch_pdl(conv_tc_kernel, grid, dim3(TC_THREADS), smem, (cudaStream_t)stream, maps[0], maps[1], maps[2], maps[3], map_w, p, bias,
-                      reinterpret_cast<const __nv_bfloat16*>(residual), out, out2_f32));
+  YAD_CUDA(launch_pdl(conv_tc_kernel, grid, dim3(TC_THREADS), smem, (cudaStream_t)stream, maps[0], maps[1], maps[2], maps[3], map_w, map_w2, p,
+                      bias, reinterpret_cast<const __nv_bfloat16*>(residual), out, out2_f32, bias_ds,
+                      reinterpret_cast<__nv_bfloat16*>(out_ds)));
   return YAD_OK;
+}
+
+extern "C" int yad_conv_tc(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad,
+                           const float* bias, const void* residual, void* out, int32_t out_dtype,
+                           float* out2_f32, int32_t ld_out2, yad_stream_t stream) {
+  return conv_tc_impl(d, in, weight, cout_pad, bias, residual, out, out_dtype, out2_f32, ld_out2, nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int yad_conv_tc_dual(const yad_conv_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
+                                void* out, const void* weight_ds, const float* bias_ds, int32_t act_ds, void* out_ds,
+                                yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(weight_ds && bias_ds && out_ds, "yad_conv_tc_dual: null pointer");
+  return conv_tc_impl(d, in, weight, cout_pad, bias, nullptr, out, YAD_BF16, nullptr, 0, weight_ds, bias_ds, act_ds, out_ds, stream);
 }

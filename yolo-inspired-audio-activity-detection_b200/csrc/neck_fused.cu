@@ -39,7 +39,9 @@ enum { NK_CONV = 0, NK_POOLS = 1, NK_PAIRAVG = 2, NK_UP2 = 3, NK_DEINT = 4, NK_D
 
 // One op = 16 int32 (the meaning of v[1..] depends on the type; byte offsets are relative to the 1024-aligned smem base).
 //   CONV   : 1 n_mt, 2 N, 3 kb_first, 4 kb_count, 5 R, 6 Wp, 7 W, 8 bias_off, 9 out_plane0, 10 out_plane1, 11 head (-1: none),
-//            12 wmap (0: N = 16, 1: N = 64, 2: N = 128), 13 wrow, 14 src_global (-1: planes in smem, else input map 0..3), 15 act
+//            12 flags (bit j: output plane j is written PAIR-AVERAGED, out[k] = (y[2k] + y[2k+1]) / 2 of the bf16-rounded rows,
+//            at the next level's geometry W / 2 - the bilinear x0.5 of BiC's conv_c0 branch folded into the epilogue),
+//            13 wrow, 14 src_global (-1: planes in smem, else input map 0..3), 15 act
 //   POOLS  : 1 in, 2 out1, 3 out2, 4 out3, 5 R, 6 Wp, 7 W
 //   PAIRAVG: 1 in, 2 out, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in            (out[k] = (in[2k] + in[2k+1]) / 2)
 //   UP2    : 1 in, 2 out, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in            (bilinear x2, align_corners = False)
@@ -150,7 +152,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           const NkOp& op = s_ops[oi];
           if (op.v[0] != NK_CONV) continue;
           const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], R = op.v[5], srcg = op.v[14];
-          const CUtensorMap* mw = op.v[12] == 0 ? &map_w16 : (op.v[12] == 1 ? &map_w64 : &map_w128);
+          const CUtensorMap* mw = N == 16 ? &map_w16 : (N == 64 ? &map_w64 : &map_w128);
           const CUtensorMap* ma = srcg == 0 ? &map_in0 : (srcg == 1 ? &map_in1 : (srcg == 2 ? &map_in2 : &map_in3));
           for (int k = 0; k < nkb; ++k) {
             if (srcg >= 0) {
@@ -288,9 +290,30 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
                   if (4 * i4 < p.head_ld) reinterpret_cast<float4*>(hp)[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
               }
               const int pj = op.v[9 + (b >> 1)];
-              if (pj >= 0 && in_plane) {
+              const int hb = 4 * (b & 1);
+              if ((op.v[12] >> (b >> 1)) & 1) {
+                // pair-averaged output (one clip per pass: r = w): rows (2k, 2k + 1) sit in adjacent lanes; both are rounded to
+                // bf16 first (what the separate x0.5 pass read), averaged in fp32, and lane 2k writes row k of the half-width plane
                 uint8_t* plane = base + pj;
-                const int hb = 4 * (b & 1);
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const uint4 mine = nk_pack(x + 8 * i4);
+                  uint4 oth;
+                  oth.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+                  oth.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+                  oth.z = __shfl_xor_sync(0xffffffffu, mine.z, 1);
+                  oth.w = __shfl_xor_sync(0xffffffffu, mine.w, 1);
+                  float fa[8], fb[8], av[8];
+                  nk_unpack(mine, fa);
+                  nk_unpack(oth, fb);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) av[e] = 0.5f * fa[e] + 0.5f * fb[e];
+                  uint4 pk = nk_pack(av);
+                  if (!valid) pk = make_uint4(0u, 0u, 0u, 0u);          // w = W (even): the halo cell of the half-width plane
+                  if (in_plane && !(r & 1)) *nk_chunk(plane, (r >> 1) + 1, hb + i4) = pk;
+                }
+              } else if (pj >= 0 && in_plane) {
+                uint8_t* plane = base + pj;
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
                   uint4 pk = nk_pack(x + 8 * i4);

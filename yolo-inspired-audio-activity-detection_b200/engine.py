@@ -111,6 +111,8 @@ class InferenceEngine:
         self.dtype = BF16 if compute_dtype == "bf16" else F32
         self.use_graphs = os.environ.get("YAD_INFER_GRAPHS", "1") != "0"
         self.fused_neck = os.environ.get("YAD_FUSED_NECK", "1") != "0"
+        self.dual_ds = os.environ.get("YAD_DUAL_DS", "1") != "0"
+        self.s2d_route = os.environ.get("YAD_S2D", "1") != "0"
         self._threads_seen = set()
         self.tdtype = torch.bfloat16 if self.dtype == BF16 else torch.float32
         self.cfg = model.config
@@ -403,15 +405,74 @@ class InferenceEngine:
                                     out.data_ptr(), 0, self._stream())
         _lib.check(rc, f"conv_flat {cv.name}")
 
-    def _conv_flat_s2(self, cv: _Conv, x: torch.Tensor, H: int, W: int, out: torch.Tensor, Ho: int, Wo: int):
+    def _conv_flat_with_s2d(self, cv: _Conv, x: torch.Tensor, H: int, W: int, out: torch.Tensor, res: Optional[torch.Tensor],
+                            s2d: torch.Tensor):
+        """_conv_flat that also writes the space-to-depth copy the next layer's stride-2 block reads (yad_conv_flat_s2d)."""
+        B, Wp, Hp, ld_in = x.shape
+        _, Wp2, Hp2, ld2 = s2d.shape
+        assert out.shape[:3] == x.shape[:3] and cv.sh == 1 and cv.sw == 1 and ld2 == 4 * cv.cout
+        d = FlatDesc(B=B, H=H, W=W, Hp=Hp, Wp=Wp, Cin=cv.cin_pad, ld_in=ld_in, Cout=cv.cout, ld_out=out.shape[3], co_off=0,
+                     kh=cv.kh, kw=cv.kw, ph=cv.ph, pw=cv.pw, act=cv.act, ld_res=0 if res is None else res.shape[3])
+        rc = self.lib.yad_conv_flat_s2d(C.byref(d), x.data_ptr(), cv.w.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), _lib.ptr(res),
+                                        out.data_ptr(), s2d.data_ptr(), Hp2, Wp2, self._stream())
+        _lib.check(rc, f"conv_flat (+ space-to-depth copy) {cv.name}")
+
+    def _s2d_steps(self, cv: _Conv, H: int, W: int, Ho: int, Wo: int):
+        """(chunk, dh, dw, wk) step lists of a stride-2 convolution read from the space-to-depth copy of its input: tap (kh, kw)
+        reads parity plane ((kh - ph) & 1, (kw - pw) & 1) shifted by (floor((kh - ph) / 2), floor((kw - pw) / 2)); taps that only
+        ever see padding are dropped; steps grouped by ascending 64-channel chunk (one patch load per plane chunk)."""
+        key = (cv.name, H, W)
+        cache = self.__dict__.setdefault("_s2d_step_cache", {})
+        if key not in cache:
+            nch = cv.cin_pad // 64
+            steps = []
+            for kh in range(cv.kh):
+                rh = kh - cv.ph
+                if not any(0 <= 2 * h2 + rh < H for h2 in range(Ho)):
+                    continue
+                for kw in range(cv.kw):
+                    rw = kw - cv.pw
+                    if not any(0 <= 2 * w2 + rw < W for w2 in range(Wo)):
+                        continue
+                    a, b_ = rh // 2, rw // 2
+                    plane = (rh - 2 * a) * 2 + (rw - 2 * b_)
+                    for c in range(nch):
+                        steps.append((plane * nch + c, a, b_, (kh * cv.kw + kw) * cv.cin_pad + c * 64))
+            steps.sort(key=lambda t: t[0])
+            arr = lambda i: (C.c_int32 * len(steps))(*[t[i] for t in steps])   # noqa: E731
+            cache[key] = (arr(0), arr(1), arr(2), arr(3), len(steps))
+        return cache[key]
+
+    def _conv_s2d(self, cv: _Conv, s2d: torch.Tensor, H: int, W: int, out: torch.Tensor, Ho: int, Wo: int):
+        """Stride-2 convolution (3x3 pad 1, or the 1x1 pad 0 downsample) of the layer whose output was also written in
+        space-to-depth form: a stride-1 flat convolution over (plane, shift) steps in the patch-resident kernel."""
+        B, Wp2, Hp2, ld_in = s2d.shape
+        assert out.shape[1:3] == (Wp2, Hp2) and ld_in == 4 * cv.cin_pad and (cv.sh, cv.sw) == (2, 2)
+        ch, dh, dw, wk, n = self._s2d_steps(cv, H, W, Ho, Wo)
+        d = FlatDesc(B=B, H=Ho, W=Wo, Hp=Hp2, Wp=Wp2, Cin=ld_in, ld_in=ld_in, Cout=cv.cout, ld_out=out.shape[3], co_off=0, kh=1, kw=1,
+                     ph=0, pw=0, act=cv.act, ld_res=0, Hp_out=Hp2, Wp_out=Wp2)
+        rc = self.lib.yad_conv_flat_taps(C.byref(d), n, ch, dh, dw, wk, cv.kh * cv.kw * cv.cin_pad, s2d.data_ptr(), cv.w.data_ptr(),
+                                         cv.cout_pad, cv.bias.data_ptr(), 0, out.data_ptr(), self._stream())
+        _lib.check(rc, f"conv (stride 2, space-to-depth) {cv.name}")
+
+    def _conv_flat_s2(self, cv: _Conv, x: torch.Tensor, H: int, W: int, out: torch.Tensor, Ho: int, Wo: int,
+                      ds: Optional[_Conv] = None, out_ds: Optional[torch.Tensor] = None):
         """Strided conv, flat in -> flat out: the tap-by-tap kernel run with the roles of H and W swapped (so that the
-        input pixel strides are ascending for its 4-D tensor map), transposed filter taps."""
+        input pixel strides are ascending for its 4-D tensor map), transposed filter taps.  With ``ds`` the BasicBlock's 1x1
+        downsample branch of the same input is computed in the same launch (yad_conv_tc_dual) into ``out_ds``."""
         B, Wp, Hp, ld_in = x.shape
         _, Wpo, Hpo, ld_out = out.shape
         d = ConvDesc(B=B, H=W, W=H, Cin=cv.cin_pad, ld_in=ld_in, Cout=cv.cout, ld_out=ld_out, co_off=0, kh=cv.kw, kw=cv.kh,
                      sh=cv.sw, sw=cv.sh, ph=cv.pw, pw=cv.ph, act=cv.act, ld_res=0,
                      in_sw=1, in_sh=Hp, in_sb=Wp * Hp, out_sw=1, out_sh=Hpo, out_sb=Wpo * Hpo)
         assert (W + 2 * cv.pw - cv.kw) // cv.sw + 1 == Wo and (H + 2 * cv.ph - cv.kh) // cv.sh + 1 == Ho
+        if ds is not None:
+            assert (ds.kh, ds.kw, ds.ph, ds.pw) == (1, 1, 0, 0) and (ds.sh, ds.sw) == (cv.sh, cv.sw) and ds.cin_pad == cv.cin_pad
+            assert ds.cout_pad == cv.cout_pad == cv.cout and out_ds.shape == out.shape
+            rc = self.lib.yad_conv_tc_dual(C.byref(d), x.data_ptr(), cv.w_t.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), out.data_ptr(),
+                                           ds.w_t.data_ptr(), ds.bias.data_ptr(), ds.act, out_ds.data_ptr(), self._stream())
+            _lib.check(rc, f"conv(s2, flat, + downsample) {cv.name}")
+            return
         rc = self.lib.yad_conv_tc(C.byref(d), x.data_ptr(), cv.w_t.data_ptr(), cv.cout_pad, cv.bias.data_ptr(), 0, out.data_ptr(),
                                   BF16, 0, 0, self._stream())
         _lib.check(rc, f"conv(s2, flat) {cv.name}")
@@ -527,6 +588,7 @@ class InferenceEngine:
                                                               fx[0], fx[1], fx[2], cur.data_ptr(), Hp, Wp, s()), "conv_stem_fused_fixup")
             else:
                 cur = self._run_stem_two_convs(xs, plan, B, H0, T, H, W, H2, W2)
+            s2d_in = None      # space-to-depth copy of `cur` (written by the previous layer's last convolution)
             for li, blocks in enumerate(self.stages):
                 for bi, blk in enumerate(blocks):
                     c1v, c2v = blk["c1"], blk["c2"]
@@ -534,16 +596,37 @@ class InferenceEngine:
                     ld = _ceil(c1v.cout, 64)
                     t = self._flat_buf(plan, f"s{li}.{bi}.t", B, Ho, Wo, ld)
                     y = self._flat_buf(plan, f"s{li}.{bi}.y", B, Ho, Wo, ld)
+                    idt = self._flat_buf(plan, f"s{li}.{bi}.d", B, Ho, Wo, ld) if "ds" in blk else cur
                     if c1v.sh == 1 and c1v.sw == 1:
                         self._conv_flat(c1v, cur, H, W, t)
+                        if "ds" in blk:
+                            self._conv_flat_s2(blk["ds"], cur, H, W, idt, Ho, Wo)
+                    elif s2d_in is not None:      # stride-2 block on the space-to-depth copy: both convs in the patch-resident kernel
+                        self._conv_s2d(c1v, s2d_in, H, W, t, Ho, Wo)
+                        if "ds" in blk:
+                            self._conv_s2d(blk["ds"], s2d_in, H, W, idt, Ho, Wo)
                     else:
-                        self._conv_flat_s2(c1v, cur, H, W, t, Ho, Wo)
-                    if "ds" in blk:
-                        idt = self._flat_buf(plan, f"s{li}.{bi}.d", B, Ho, Wo, ld)
-                        self._conv_flat_s2(blk["ds"], cur, H, W, idt, Ho, Wo)
+                        dual = ("ds" in blk and self.dual_ds and blk["ds"].cout_pad == c1v.cout_pad == c1v.cout and c1v.cout % 32 == 0
+                                and (blk["ds"].sh, blk["ds"].sw) == (c1v.sh, c1v.sw))
+                        if dual:       # conv1 and the downsample branch of the same input in one tap-by-tap launch
+                            self._conv_flat_s2(c1v, cur, H, W, t, Ho, Wo, ds=blk["ds"], out_ds=idt)
+                        else:
+                            self._conv_flat_s2(c1v, cur, H, W, t, Ho, Wo)
+                            if "ds" in blk:
+                                self._conv_flat_s2(blk["ds"], cur, H, W, idt, Ho, Wo)
+                    s2d_in = None
+                    nxt = self.stages[li + 1][0] if (bi == len(blocks) - 1 and li + 1 < len(self.stages)) else None
+                    if (nxt is not None and self.s2d_route and (nxt["c1"].sh, nxt["c1"].sw) == (2, 2) and nxt["c1"].kh == 3 and
+                            nxt["c1"].ph == 1 and c2v.cout == c2v.cout_pad == nxt["c1"].cin_pad and c2v.cout % 64 == 0 and
+                            ("ds" not in nxt or ((nxt["ds"].sh, nxt["ds"].sw) == (2, 2) and nxt["ds"].kh == 1 and nxt["ds"].ph == 0))):
+                        H2n, W2n = (Ho + 2 - 3) // 2 + 1, (Wo + 2 - 3) // 2 + 1
+                        s2d_in = plan.get(f"s{li}.s2d")
+                        if s2d_in is None:
+                            Hp2, Wp2 = self._flat_geom(H2n, W2n)
+                            s2d_in = plan[f"s{li}.s2d"] = torch.zeros((B, Wp2, Hp2, 4 * c2v.cout), device=self.dev, dtype=torch.bfloat16)
+                        self._conv_flat_with_s2d(c2v, t, Ho, Wo, y, idt, s2d_in)
                     else:
-                        idt = cur
-                    self._conv_flat(c2v, t, Ho, Wo, y, res=idt)
+                        self._conv_flat(c2v, t, Ho, Wo, y, res=idt)
                     cur, H, W = y, Ho, Wo
                 fmaps.append(cur)
                 geoms.append((H, W))

@@ -25,27 +25,43 @@ def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+TOKEN = 1 << 24      # plane handles are TOKEN + id until _finish() has placed them
+
+
 class _Pool:
-    """First-fit allocator over 1024-byte units (planes must start on a swizzle-atom boundary)."""
+    """Shared-memory planner over 1024-byte units (planes start on a swizzle-atom boundary).  While the program is emitted a
+    plane is only a handle with a lifetime [born, died) in op indices; place() then packs all planes offline: largest first, each
+    at the lowest offset that is free during its whole lifetime (an online first-fit allocator needed 123 KB for a 90 KB peak)."""
 
     def __init__(self):
-        self.live: Dict[int, int] = {}     # offset -> size (units)
-        self.high = 0
+        self.planes: List[List[int]] = []      # [units, born, died]
+        self.live: set = set()
 
-    def alloc(self, nbytes: int) -> int:
-        n = _ceil(nbytes, 1024) // 1024
-        spans = sorted(self.live.items())
-        pos = 0
-        for off, sz in spans:
-            if off - pos >= n:
-                break
-            pos = max(pos, off + sz)
-        self.live[pos] = n
-        self.high = max(self.high, pos + n)
-        return pos * 1024
+    def alloc(self, nbytes: int, now: int) -> int:
+        self.planes.append([_ceil(nbytes, 1024) // 1024, now, -1])
+        self.live.add(len(self.planes) - 1)
+        return TOKEN + len(self.planes) - 1
 
-    def free(self, off: int) -> None:
-        del self.live[off // 1024]
+    def free(self, tok: int, now: int) -> None:
+        i = tok - TOKEN
+        self.live.remove(i)
+        self.planes[i][2] = now
+
+    def place(self) -> Tuple[List[int], int]:
+        order = sorted(range(len(self.planes)), key=lambda i: (-self.planes[i][0], self.planes[i][1]))
+        off = [-1] * len(self.planes)
+        for i in order:
+            n, b, d = self.planes[i]
+            busy = sorted((off[j], off[j] + self.planes[j][0]) for j in range(len(self.planes))
+                          if off[j] >= 0 and self.planes[j][1] < d and b < self.planes[j][2])
+            pos = 0
+            for lo, hi in busy:
+                if lo - pos >= n:
+                    break
+                pos = max(pos, hi)
+            off[i] = pos
+        high = max(off[i] + self.planes[i][0] for i in range(len(self.planes)))
+        return [o * 1024 for o in off], high * 1024
 
 
 class FusedNeck:
@@ -95,10 +111,14 @@ class FusedNeck:
 
     # ------------------------------------------------------------------ program emission
     def _plane(self, level: int) -> int:
-        return self.pool.alloc(self.lv[level]["bytes"])
+        return self.pool.alloc(self.lv[level]["bytes"], len(self.ops))
 
-    def _conv(self, cvs, level: int, kblocks, outs: List[int], head: int = -1, src_global: int = -1):
-        """kblocks: list of (src, shift, weight block [N, 64])."""
+    def _free(self, tok: int) -> None:
+        self.pool.free(tok, len(self.ops))
+
+    def _conv(self, cvs, level: int, kblocks, outs: List[int], head: int = -1, src_global: int = -1, pair: Sequence[bool] = ()):
+        """kblocks: list of (src, shift, weight block [N, 64]).  pair[j]: output plane j is written pair-averaged (bilinear x0.5,
+        F.interpolate in BiC's conv_c0 branch, modules/_common.py:181-182) at the NEXT level's geometry."""
         g = self.lv[level]
         N = sum(cv.cout_pad for cv in cvs)
         assert N in (16, 64, 128), N
@@ -111,8 +131,11 @@ class FusedNeck:
             self.wblocks.append(wb)
         bias = torch.cat([cv.bias.float() for cv in cvs])
         assert bias.numel() == N
+        flags = sum(1 << j for j, pr in enumerate(pair) if pr)
+        if flags:
+            assert self.G == 1 and g["W"] % 2 == 0 and N >= 64, "pair-averaged outputs: one clip per pass, even width"
         op = [CONV, g["n_mt"], N, kb_first, len(kblocks), g["R"], g["Wp"], g["W"], self.nbias, outs[0], outs[1] if len(outs) > 1 else -1,
-              head, {16: 0, 64: 1, 128: 2}[N], self.wrows, src_global, ACT_LRELU]
+              head, flags, self.wrows, src_global, ACT_LRELU]
         for cv in cvs:
             assert cv.act == ACT_LRELU
         self.ops.append(op)
@@ -156,7 +179,7 @@ class FusedNeck:
         self.dump_elems += rows * 64
 
     def _build(self):
-        n, rep, P, F = self.eng.n, self.eng.rep, self._plane, self.pool.free
+        n, rep, P, F = self.eng.n, self.eng.rep, self._plane, self._free
         lv = self.lv
         # ---- CSPSPPF (modules/_common.py:204-215) at level 4; conv1 and conv2 read the same map: one N = 128 convolution
         a1, y = P(4), P(4)
@@ -183,10 +206,9 @@ class FusedNeck:
         # ---- BiC3 (:179-185): cat[conv_c1(f3'), pairavg(conv_c0(f2')), up2(p4)] -> conv_out; f2' also feeds BiC2's conv_c1
         c1_3 = P(3)
         self._conv([n["b3c1"]], 3, self._taps_global([n["b3c1"]], 2), [c1_3], src_global=2)
-        t, c1_2 = P(2), P(2)
-        self._conv([n["b3c0"], n["b2c1"]], 2, self._taps_global([n["b3c0"], n["b2c1"]], 1), [t, c1_2], src_global=1)
-        c0_3 = P(3)
-        self._ew(PAIRAVG, 3, t, c0_3, wp_in=lv[2]["Wp"]); F(t)
+        # conv_c0 of BiC3 (-> x0.5, written pair-averaged straight into the level-3 plane) and conv_c1 of BiC2 read the same map
+        c0_3, c1_2 = P(3), P(2)
+        self._conv([n["b3c0"], n["b2c1"]], 2, self._taps_global([n["b3c0"], n["b2c1"]], 1), [c0_3, c1_2], src_global=1, pair=(True, False))
         u3 = [P(3), P(3)]
         for i in range(2):
             self._ew(UP2, 3, p4[i], u3[i], wp_in=lv[4]["Wp"])
@@ -201,10 +223,8 @@ class FusedNeck:
         self._conv([rep["rep_block3_1"][1]["deploy"]], 3, self._taps3(rep["rep_block3_1"][1]["deploy"], r1), p3); F(r1[0]); F(r1[1])
         self._dump("p3_0", p3[0], 3); self._dump("p3_1", p3[1], 3)
         # ---- BiC2
-        t1 = P(1)
-        self._conv([n["b2c0"]], 1, self._taps_global([n["b2c0"]], 0), [t1], src_global=0)
         c0_2 = P(2)
-        self._ew(PAIRAVG, 2, t1, c0_2, wp_in=lv[1]["Wp"]); F(t1)
+        self._conv([n["b2c0"]], 1, self._taps_global([n["b2c0"]], 0), [c0_2], src_global=0, pair=(True,))
         u2 = [P(2), P(2)]
         for i in range(2):
             self._ew(UP2, 2, p3[i], u2[i], wp_in=lv[3]["Wp"])
@@ -246,7 +266,14 @@ class FusedNeck:
 
     def _finish(self):
         dev = self.dev
-        self.pool_bytes = _ceil(self.pool.high * 1024, 1024)
+        offs, high = self.pool.place()
+        res = lambda v: offs[v - TOKEN] if v >= TOKEN else v      # noqa: E731
+        plane_fields = {CONV: (9, 10), POOLS: (1, 2, 3, 4), PAIRAVG: (1, 2), UP2: (1, 2), DEINT: (1, 2, 3), DUMP: (1,)}
+        for op in self.ops:
+            for f in plane_fields[op[0]]:
+                op[f] = res(op[f])
+        self.kbs = [(res(src), sh) for src, sh in self.kbs]
+        self.pool_bytes = _ceil(high, 1024)
         tables = len(self.ops) * 64 + len(self.kbs) * 8 + self.nbias * 4 + 8 + 18 * 8 + 16
         self.n_slots = min(8, (SMEM_MAX - 1024 - self.pool_bytes - tables) // SLOT)
         need = 1 + max(op[1] for op in self.ops if op[0] == CONV and op[14] >= 0)     # A tiles of one K block + its weight block
