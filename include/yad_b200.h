@@ -198,8 +198,8 @@ int yad_conv_tc_dual(const yad_conv_desc* d, const void* in, const void* weight,
 
 /* Patch-resident tcgen05 implicit GEMM for stride-1 'same' convolutions on the FLAT halo-padded layout:
  * pixel (b,h,w) of an activation lives at flat index f = (b*Wp + w)*Hp + h (h fastest), channel pitch ld; cells with
- * h >= H or w >= W are the (shared) zero halo: they are read as padding and never written, so the caller zero-fills
- * the buffer once.  Hp - H / Wp - W must cover the filter reach (taps that can only see padding, e.g. the top and
+ * h >= H or w >= W are the (shared) zero halo: they are read as padding and only ever written with zeros, so the caller
+ * zero-fills the buffer once.  Hp - H / Wp - W must cover the filter reach (taps that can only see padding, e.g. the top and
  * bottom rows of a 3x3 at H = 1, are skipped and need no halo).  Every tap is then a constant shift in f, so a CTA
  * loads each input pixel once per tile instead of once per tap.  in / out / residual share the geometry.
  * Requirements: Cin % 64 == 0, Cout % 32 == 0, cout_pad % 64 == 0 (weight rows / bias zero padded), bf16 in and out.
@@ -216,6 +216,16 @@ typedef struct {
 } yad_flat_desc;
 int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad, const float* bias,
                   const void* residual, void* out, int32_t flags, yad_stream_t stream);
+/* yad_conv_flat_taps over TWO input tensors of the same flat geometry: step i reads 64-channel chunk chunk[i] of input src[i]
+ * (0: `in`, Cin / ld_in of the descriptor; 1: `in2`, cin2 / ld_in2).  Used to fold the BasicBlock's downsample branch into the
+ * block's second convolution (torchvision resnet.py:96-103 via modules/_backbone.py:148: out = relu(bn2(conv2(t)) + downsample(x))):
+ * both are linear in their inputs and meet before the activation, so downsample(x) is Cin(x) / 64 more K steps of the same GEMM
+ * (weights concatenated along K, biases added by the caller) - no separate launch, no identity tensor written and re-read. */
+int yad_conv_flat_taps2(const yad_flat_desc* d, int32_t n_steps, const int32_t* src, const int32_t* chunk, const int32_t* dh,
+                        const int32_t* dw, const int32_t* wk, int64_t k_total, const void* in, const void* in2, int32_t cin2,
+                        int32_t ld_in2, const void* weight, int32_t cout_pad, const float* bias, const void* residual, void* out,
+                        yad_stream_t stream);
+
 /* yad_conv_flat that also writes a SPACE-TO-DEPTH copy of its output for the stride-2 block that follows (torchvision
  * resnet.py:92-100: the first BasicBlock of layer2..4 reads its input with stride 2 twice, conv1 and downsample):
  *   out_s2d [B, Wp2, Hp2, 4 * Cout] bf16, pixel (b, h, w) -> cell (b, w / 2, h / 2), channel plane (h & 1) * 2 + (w & 1).

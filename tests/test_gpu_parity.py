@@ -276,9 +276,11 @@ def test_conv_flat(case, cuda_dev):
     torch.cuda.synchronize()
     got = out[:, :W, :H, co_off:co_off + Cout].float().permute(0, 3, 2, 1).cpu()
     np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-2, rtol=1e-2)
-    # halo cells and channels outside the slice are never written
-    assert torch.all(out[:, W:].float() == 7.0) and torch.all(out[:, :, H:].float() == 7.0)
-    assert torch.all(out[..., :co_off].float() == 7.0)
+    # channels outside the slice are never written; halo cells of the slice are either left alone (register-sourced epilogue)
+    # or written as the zeros they have to be (whole tiles stored by the TMA unit)
+    halo = torch.cat([out[:, W:, :, co_off:co_off + Cout].reshape(-1), out[:, :, H:, co_off:co_off + Cout].reshape(-1)]).float()
+    assert torch.all((halo == 7.0) | (halo == 0.0))
+    assert torch.all(out[..., :co_off].float() == 7.0) and torch.all(out[..., co_off + Cout:].float() == 7.0)
 
 
 # ------------------------------------------------------------------ whole network (S2/S3)
@@ -859,9 +861,10 @@ def test_stride2_block_routes_agree(models, seconds, B, cuda_dev, monkeypatch):
     1x1 stride-2 downsample of the same input, three ways:
       a) two tap-by-tap launches (yad_conv_tc; YAD_S2D=0 YAD_DUAL_DS=0),
       b) one tap-by-tap launch with two TMEM accumulators (yad_conv_tc_dual; YAD_S2D=0): same tiles and K order -> bitwise a),
-      c) default: the previous layer also writes a space-to-depth copy (yad_conv_flat_s2d) and both convolutions run in the
-         patch-resident kernel over (plane, shift) steps (yad_conv_flat_taps): other K order -> equal up to fp32 summation order
-         and the bf16 rounding that follows (checked on the backbone maps and on the predictions)."""
+      c) default: the previous layer also writes a space-to-depth copy (yad_conv_flat_s2d); conv1 runs in the patch-resident
+         kernel over (plane, shift) steps (yad_conv_flat_taps) and the downsample rides in conv2's GEMM as extra K steps
+         (yad_conv_flat_taps2): other K order, identity not rounded to bf16 -> equal up to fp32 summation order and bf16 rounding
+         (checked on the backbone maps and on the predictions)."""
     m = models[("deploy", "bf16")]
     L = int(22050 * seconds) // 4 * 4
     x = synth.synth_clips(B, L, seed=1500 + int(seconds), silence_tail_every=0).to(cuda_dev)
@@ -881,7 +884,9 @@ def test_stride2_block_routes_agree(models, seconds, B, cuda_dev, monkeypatch):
         assert d.max().item() <= 0.02 * scale + 1e-3 and d.mean().item() <= 5e-4 * scale, (i, d.max().item(), d.mean().item(), scale)
     assert torch.equal(fm_a[0], fm_c[0])          # layer1 is untouched by the route
     d = (out_a - out_c).abs()
-    assert d[..., :3].max().item() < 0.05 and d[..., 3].max().item() < 0.05 and d[..., 4].max().item() < 0.5
+    # same tolerance as the other bf16 route comparisons (test_fused_stem_network_equals_two_conv_path)
+    assert d[..., :3].max().item() < 0.1 and d[..., :3].mean().item() < 0.01, (d[..., :3].max().item(), d[..., :3].mean().item())
+    assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
 
 
 # ------------------------------------------------------------------ small kernels added for the 2-D neck / fused stem

@@ -54,6 +54,8 @@ SIGNATURES = {
     "yad_conv_tc": [C.POINTER(ConvDesc), _p, _p, _i32, _p, _p, _p, _i32, _p, _i32, _p],
     "yad_conv_tc_dual": [C.POINTER(ConvDesc), _p, _p, _i32, _p, _p, _p, _p, _i32, _p, _p],
     "yad_conv_flat": [C.POINTER(FlatDesc), _p, _p, _i32, _p, _p, _p, _i32, _p],
+    "yad_conv_flat_taps2": [C.POINTER(FlatDesc), _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
+                            _i64, _p, _p, _i32, _i32, _p, _i32, _p, _p, _p, _p],
     "yad_conv_flat_s2d": [C.POINTER(FlatDesc), _p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _p],
     "yad_conv_flat_taps": [C.POINTER(FlatDesc), _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i64, _p, _p,
                            _i32, _p, _p, _p, _p],

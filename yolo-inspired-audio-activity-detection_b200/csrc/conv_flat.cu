@@ -19,16 +19,28 @@
 // Weights stream through their own ring, one [BN x 64] block per (tap, chunk), shared by the MT accumulators.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..9 = epilogue (tcgen05.ld -> bias / residual / activation -> global; two warps per TMEM lane quadrant, each
-// taking every second 32-column chunk; the residual of the next chunk is prefetched), TMEM accumulators double-buffered
+// warps 2..9 = epilogue (tcgen05.ld -> bias / residual / activation; two warps per TMEM lane quadrant, each taking every
+// second 32-column chunk), warp 10 = epilogue TMA (residual tiles in, output tiles out), TMEM accumulators double-buffered
 // so the epilogue of super-tile i overlaps the MMAs of super-tile i + 1.
+//
+// Epilogue memory traffic goes through the TMA unit: a thread owns one pixel row of the accumulator, so register-sourced
+// stores / residual loads are 16 bytes per lane at a 128- or 256-byte lane stride - one LSU wavefront per 16 bytes.  ncu on
+// the layer1 shape (profiles/r02_ncu_conv_flat_l1_*): l1tex__data_pipe_lsu_wavefronts at 71 % of peak, 135 k global
+// wavefronts per SM, tensor pipe 34 %: the kernel was bound by its own epilogue.  Now each [128 pixel x 64 channel] tile of
+// the residual is bulk-loaded into a swizzled 16 KB staging buffer, the epilogue warps add / activate / round IN PLACE
+// (conflict-free 16-byte shared-memory accesses) and the tile is bulk-stored from the same buffer; halo pixels are written
+// as the zeros they have to stay.  Three staging buffers: the residual tile of item g + 2 lands while item g is computed.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace yad {
 
-constexpr int FL_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int FL_THREADS = 352;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 epilogue TMA (stores / residual loads)
+constexpr int FL_SRC2 = 0x4000;
+constexpr int FL_NSTAGE = 3;        // epilogue staging buffers of [128 rows x 128 B]
+constexpr int FL_STAGE_BYTES = 128 * 128;
 constexpr int FL_EPI_THREADS = 256;
 constexpr int FL_MAX_STEPS = 64;
 constexpr int FL_MAX_RING = 8;
@@ -47,12 +59,14 @@ struct FlatParams {
   int32_t Cout, ld_out, co_off, ld_res, act;
   uint32_t idesc;
   int32_t flags;                // reserved (0)
+  int32_t tma_epi;              // 1: residual / output tiles move through the TMA unit and the staging buffers (needs Cout % 64 == 0,
+                                // same pitches in and out); 0: register-sourced global accesses
   int32_t s2d_Hp, s2d_Wp;       // second, space-to-depth copy of the output (0: none): pixel (b, h, w) goes to flat cell
                                 // (b * s2d_Wp + w / 2) * s2d_Hp + h / 2, channel plane (h & 1) * 2 + (w & 1) of 4 * Cout channels
   uint32_t step_mma[FL_MAX_STEPS];    // MMA warp: bits 0..15 = first patch row of the tap in 16-byte units, bit 30 = first
                                       // step of its chunk, bit 31 = last step of its chunk
   int16_t step_off[FL_MAX_STEPS];     // flat pixel shift of the tap
-  int16_t step_chunk[FL_MAX_STEPS];   // 64-channel chunk
+  int16_t step_chunk[FL_MAX_STEPS];   // 64-channel chunk; bit 14 (FL_SRC2): of the SECOND input tensor (same flat geometry)
   int8_t step_first[FL_MAX_STEPS];    // first step of its chunk (load a new patch)
   int8_t step_last[FL_MAX_STEPS];     // last step of its chunk (release the patch)
   int32_t step_wk[FL_MAX_STEPS];      // K offset of the [BN x 64] weight block
@@ -118,7 +132,9 @@ __device__ __forceinline__ void flat_mma_loop(const FlatParams& p, uint8_t* sm_a
 }
 
 __global__ void __launch_bounds__(FL_THREADS, 1)
-conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                  const __grid_constant__ FlatParams p, const float* __restrict__ bias,
                  const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ out_s2d) {
@@ -126,13 +142,17 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sm_a = smem;                                       // [NA][patch_bytes]
   uint8_t* sm_w = sm_a + (size_t)p.NA * p.patch_bytes;        // [NW][w_bytes]
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(sm_w + (size_t)p.NW * p.w_bytes);
+  uint8_t* sm_o = sm_w + (size_t)p.NW * p.w_bytes;            // [FL_NSTAGE][16 KB] epilogue staging (1024-byte aligned: patch and
+                                                              // weight slots are multiples of 1 KB)
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sm_o + (p.tma_epi ? FL_NSTAGE * FL_STAGE_BYTES : 0));
   uint64_t* empty_a = full_a + FL_MAX_RING;
   uint64_t* full_w = empty_a + FL_MAX_RING;
   uint64_t* empty_w = full_w + FL_MAX_RING;
   uint64_t* tmem_full = empty_w + FL_MAX_RING;                // [2]
   uint64_t* tmem_empty = tmem_full + 2;                       // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* buf_ready = tmem_empty + 2;                       // [FL_NSTAGE] staging buffer free (and its residual tile landed)
+  uint64_t* out_full = buf_ready + FL_NSTAGE;                 // [FL_NSTAGE] staging buffer holds a finished output tile
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(out_full + FL_NSTAGE);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [n_ntiles * BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,6 +171,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], FL_EPI_THREADS);
+    }
+    for (int s = 0; s < FL_NSTAGE; ++s) {
+      mbar_init(&buf_ready[s], 1);
+      mbar_init(&out_full[s], FL_EPI_THREADS);
+    }
+    if (p.tma_epi) {
+      prefetch_tmap(&map_out);
+      if (residual != nullptr) prefetch_tmap(&map_res);
     }
     fence_barrier_init();
   }
@@ -179,10 +207,11 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(&empty_a[a_slot], a_phase ^ 1);
             uint8_t* dst = sm_a + (size_t)a_slot * p.patch_bytes;
             mbar_expect_tx(&full_a[a_slot], (uint32_t)p.patch_bytes);
-            const int c0 = p.step_chunk[s] * 64;
+            const int c0 = (p.step_chunk[s] & (FL_SRC2 - 1)) * 64;
+            const CUtensorMap* ma = (p.step_chunk[s] & FL_SRC2) ? &map_a2 : &map_a;
             const int r0 = (int)(f0 + p.min_off);
             for (int i = 0; i < n_boxes; ++i)
-              tma_load_2d(&map_a, &full_a[a_slot], dst + i * (FL_BOX_ROWS * 128), c0, r0 + i * FL_BOX_ROWS);
+              tma_load_2d(ma, &full_a[a_slot], dst + i * (FL_BOX_ROWS * 128), c0, r0 + i * FL_BOX_ROWS);
             if (++a_slot == (uint32_t)p.NA) { a_slot = 0; a_phase ^= 1; }
           }
           mbar_wait(&empty_w[w_slot], w_phase ^ 1);
@@ -202,6 +231,47 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       flat_mma_loop<4, 64>(p, sm_a, sm_w, full_a, empty_a, full_w, empty_w, tmem_full, tmem_empty);
     else
       flat_mma_loop<2, 128>(p, sm_a, sm_w, full_a, empty_a, full_w, empty_w, tmem_full, tmem_empty);
+  } else if (warp == 10) {
+    // ===================== epilogue TMA: stores the finished tiles, loads the residual tiles two items ahead =====================
+    if (p.tma_epi && lane == 0) {
+      const int cpa = p.BN >> 6, n_items = p.MT * cpa;
+      const int n_my = (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = n_my * n_items;
+      // item g of this CTA -> (channel, row) coordinate of its [128 x 64] tile
+      auto coords = [&](int g, int& ch, int& row) {
+        const int sti = g / n_items, j = g - sti * n_items;
+        const int st = (int)blockIdx.x + sti * (int)gridDim.x;
+        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
+        const int mt = j / cpa, cj = j - mt * cpa;
+        ch = nt * p.BN + 64 * cj;
+        row = mtile * rows_per_super + 128 * mt;
+      };
+      auto make_ready = [&](int g) {          // buffer g % FL_NSTAGE is free: fetch the residual tile of item g, or just say so
+        uint64_t* bar = &buf_ready[g % FL_NSTAGE];
+        if (residual != nullptr) {
+          int ch, row;
+          coords(g, ch, row);
+          mbar_expect_tx(bar, FL_STAGE_BYTES);
+          tma_load_2d(&map_res, bar, sm_o + (g % FL_NSTAGE) * FL_STAGE_BYTES, ch, row);
+        } else {
+          mbar_arrive(bar);
+        }
+      };
+      for (int g = 0; g < total && g < FL_NSTAGE - 1; ++g) make_ready(g);
+      for (int g = 0; g < total; ++g) {
+        const int b = g % FL_NSTAGE;
+        mbar_wait(&out_full[b], (uint32_t)(g / FL_NSTAGE) & 1u);
+        int ch, row;
+        coords(g, ch, row);
+        tma_store_2d(&map_out, sm_o + b * FL_STAGE_BYTES, p.co_off + ch, row);
+        bulk_commit_group();
+        if (g + FL_NSTAGE - 1 < total) {
+          bulk_wait_group_read<1>();          // the store of item g - 1 has read its buffer: it is the one item g + 2 uses
+          make_ready(g + FL_NSTAGE - 1);
+        }
+      }
+      bulk_wait_group<0>();                   // all tiles written before the CTA (and its shared memory) goes away
+    }
   } else {
     // ===================== epilogue: 8 warps; TMEM lane quadrant = warp % 4, column-chunk parity = (warp - 2) / 4 =====
     const int q = warp & 3;
@@ -211,97 +281,179 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int n_items = p.MT * chunks_per_acc;       // work items per super-tile: (mt, chunk)
     const uint32_t Hp = (uint32_t)p.Hp, Wp = (uint32_t)p.Wp;
     uint32_t as = 0, acc_phase = 0;
-    for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-      const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
-      const int n0 = nt * p.BN;
-      const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
-      // residual prefetch for item 0 (independent of the accumulator): hides the HBM latency behind the barrier wait
-      uint4 rq[4];
-      // item j -> (output flat index, first channel, valid); the output may use other pitches than the input
-      uint32_t f2_cur = 0;          // element offset of the item's 32 channels in the space-to-depth copy
-      auto item_geom = [&](int j, uint32_t& f, int& nbase, bool& ok) {
-        const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
-        f = fbase + 128u * (uint32_t)mt;
-        const uint32_t col = f / Hp, h = f - col * Hp, bb = col / Wp, w = col - bb * Wp;
-        nbase = n0 + 32 * (2 * cj + half);
-        ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W && nbase < p.Cout;
-        if (p.remap) f = (bb * (uint32_t)p.Wpo + w) * (uint32_t)p.Hpo + h;
-        if (p.s2d_Hp)
-          f2_cur = (((bb * (uint32_t)p.s2d_Wp + (w >> 1)) * (uint32_t)p.s2d_Hp + (h >> 1)) * 4u + ((h & 1u) << 1 | (w & 1u))) * (uint32_t)p.Cout +
-                   (uint32_t)nbase;
-      };
-      auto load_res = [&](uint32_t f, int nbase, bool ok) {
-        if (residual != nullptr && ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(residual + (int64_t)f * p.ld_res + nbase);
+    if (p.tma_epi) {
+      // ---- tiles through the staging buffers (see the header): item = (mt, 64-channel block) = one [128 x 64] tile that the 8
+      //      warps fill together; thread = (pixel row r, channel half): four 16-byte chunks of its row, swizzled like the TMA image
+      uint32_t sb = 0, sb_phase = 0;
+      const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)r & 7u;
+      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
+        const int n0 = nt * p.BN;
+        const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
+        mbar_wait(&tmem_full[as], acc_phase);
+        tc_fence_after();
+        for (int j = 0; j < n_items; ++j) {
+          const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
+          const int c0 = 32 * (2 * cj + half);
+          const uint32_t f = fbase + 128u * (uint32_t)mt;
+          const uint32_t col = f / Hp, h = f - col * Hp, bb = col / Wp, w = col - bb * Wp;
+          const bool ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W;
+          const int nbase = n0 + c0;
+          uint32_t v[32];
+          tmem_ld32(((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
+          tmem_ld_wait();
+          uint8_t* S = sm_o + sb * FL_STAGE_BYTES + row_off;
+          mbar_wait(&buf_ready[sb], sb_phase);       // the buffer is free and (if any) the residual tile has landed in it
+          uint4 pk[4];
+          if (ok) {
+            float x[32];
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + nbase);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) rq[j4] = __ldg(rp + j4);
-        }
-      };
-      uint32_t f_cur;
-      int nb_cur;
-      bool ok_cur;
-      item_geom(0, f_cur, nb_cur, ok_cur);
-      load_res(f_cur, nb_cur, ok_cur);
-      mbar_wait(&tmem_full[as], acc_phase);
-      tc_fence_after();
-      for (int j = 0; j < n_items; ++j) {
-        const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
-        const int c0 = 32 * (2 * cj + half);
-        uint32_t v[32];
-        tmem_ld32(((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
-        tmem_ld_wait();
-        float x[32];
-        if (ok_cur) {
-          const float4* bp = reinterpret_cast<const float4*>(s_bias + nb_cur);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = bp[j4];
+              x[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
+              x[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+              x[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
+              x[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+            }
+            if (residual != nullptr) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = bp[j4];
-            x[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
-            x[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
-            x[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
-            x[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
-          }
-          if (residual != nullptr) {
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 rq = *reinterpret_cast<const uint4*>(S + ((((uint32_t)(4 * half + j4)) ^ rx) << 4));
+                const uint32_t ww[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  x[j4 * 8 + e * 2 + 0] += __uint_as_float(ww[e] << 16);
+                  x[j4 * 8 + e * 2 + 1] += __uint_as_float(ww[e] & 0xffff0000u);
+                }
+              }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) x[jj] = apply_act(x[jj], p.act);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const uint32_t ww[4] = {rq[j4].x, rq[j4].y, rq[j4].z, rq[j4].w};
+              uint32_t ww[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                x[j4 * 8 + e * 2 + 0] += __uint_as_float(ww[e] << 16);
-                x[j4 * 8 + e * 2 + 1] += __uint_as_float(ww[e] & 0xffff0000u);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+                ww[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              pk[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+            }
+            if (p.s2d_Hp) {
+              uint4* op2 = reinterpret_cast<uint4*>(
+                  out_s2d + (((bb * (uint32_t)p.s2d_Wp + (w >> 1)) * (uint32_t)p.s2d_Hp + (h >> 1)) * 4u + ((h & 1u) << 1 | (w & 1u))) *
+                                (uint32_t)p.Cout + (uint32_t)nbase);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) op2[j4] = pk[j4];
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) pk[j4] = make_uint4(0u, 0u, 0u, 0u);      // halo cell: stays zero in global memory
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(S + ((((uint32_t)(4 * half + j4)) ^ rx) << 4)) = pk[j4];
+          fence_proxy_async();               // generic-proxy writes -> visible to the bulk store
+          mbar_arrive(&out_full[sb]);
+          if (++sb == FL_NSTAGE) { sb = 0; sb_phase ^= 1; }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);
+        if ((as ^= 1) == 0) acc_phase ^= 1;
+      }
+    } else {
+      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
+        const int n0 = nt * p.BN;
+        const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
+        // residual prefetch for item 0 (independent of the accumulator): hides the HBM latency behind the barrier wait
+        uint4 rq[4];
+        // item j -> (output flat index, first channel, valid); the output may use other pitches than the input
+        uint32_t f2_cur = 0;          // element offset of the item's 32 channels in the space-to-depth copy
+        auto item_geom = [&](int j, uint32_t& f, int& nbase, bool& ok) {
+          const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
+          f = fbase + 128u * (uint32_t)mt;
+          const uint32_t col = f / Hp, h = f - col * Hp, bb = col / Wp, w = col - bb * Wp;
+          nbase = n0 + 32 * (2 * cj + half);
+          ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W && nbase < p.Cout;
+          if (p.remap) f = (bb * (uint32_t)p.Wpo + w) * (uint32_t)p.Hpo + h;
+          if (p.s2d_Hp)
+            f2_cur = (((bb * (uint32_t)p.s2d_Wp + (w >> 1)) * (uint32_t)p.s2d_Hp + (h >> 1)) * 4u + ((h & 1u) << 1 | (w & 1u))) * (uint32_t)p.Cout +
+                     (uint32_t)nbase;
+        };
+        auto load_res = [&](uint32_t f, int nbase, bool ok) {
+          if (residual != nullptr && ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(residual + (int64_t)f * p.ld_res + nbase);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) rq[j4] = __ldg(rp + j4);
+          }
+        };
+        uint32_t f_cur;
+        int nb_cur;
+        bool ok_cur;
+        item_geom(0, f_cur, nb_cur, ok_cur);
+        load_res(f_cur, nb_cur, ok_cur);
+        mbar_wait(&tmem_full[as], acc_phase);
+        tc_fence_after();
+        for (int j = 0; j < n_items; ++j) {
+          const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
+          const int c0 = 32 * (2 * cj + half);
+          uint32_t v[32];
+          tmem_ld32(((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
+          tmem_ld_wait();
+          float x[32];
+          if (ok_cur) {
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + nb_cur);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = bp[j4];
+              x[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
+              x[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
+              x[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
+              x[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + b4.w;
+            }
+            if (residual != nullptr) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint32_t ww[4] = {rq[j4].x, rq[j4].y, rq[j4].z, rq[j4].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  x[j4 * 8 + e * 2 + 0] += __uint_as_float(ww[e] << 16);
+                  x[j4 * 8 + e * 2 + 1] += __uint_as_float(ww[e] & 0xffff0000u);
+                }
               }
             }
           }
-        }
-        const uint32_t f_st = f_cur, f2_st = f2_cur;
-        const int nb_st = nb_cur;
-        const bool ok_st = ok_cur;
-        if (j + 1 < n_items) {       // prefetch the next item's residual before the stores of this one
-          item_geom(j + 1, f_cur, nb_cur, ok_cur);
-          load_res(f_cur, nb_cur, ok_cur);
-        }
-        if (ok_st) {
+          const uint32_t f_st = f_cur, f2_st = f2_cur;
+          const int nb_st = nb_cur;
+          const bool ok_st = ok_cur;
+          if (j + 1 < n_items) {       // prefetch the next item's residual before the stores of this one
+            item_geom(j + 1, f_cur, nb_cur, ok_cur);
+            load_res(f_cur, nb_cur, ok_cur);
+          }
+          if (ok_st) {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) x[jj] = apply_act(x[jj], p.act);
-          uint4* op = reinterpret_cast<uint4*>(out + (int64_t)f_st * p.ld_out + p.co_off + nb_st);
-          uint4* op2 = reinterpret_cast<uint4*>(out_s2d + f2_st);
+            for (int jj = 0; jj < 32; ++jj) x[jj] = apply_act(x[jj], p.act);
+            uint4* op = reinterpret_cast<uint4*>(out + (int64_t)f_st * p.ld_out + p.co_off + nb_st);
+            uint4* op2 = reinterpret_cast<uint4*>(out_s2d + f2_st);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint32_t ww[4];
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint32_t ww[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
-              ww[e] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(x[j4 * 8 + e * 2], x[j4 * 8 + e * 2 + 1]);
+                ww[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              op[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+              if (p.s2d_Hp) op2[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
             }
-            op[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
-            if (p.s2d_Hp) op2[j4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
           }
         }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);
+        if ((as ^= 1) == 0) acc_phase ^= 1;
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[as]);
-      if ((as ^= 1) == 0) acc_phase ^= 1;
-    }
+      }
   }
   tc_fence_before();
   __syncthreads();
@@ -327,7 +479,7 @@ namespace yad {
 // common launcher: the caller has filled the geometry / epilogue fields and the step lists (grouped by chunk)
 static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const void* in, int cin_total, int ld_in,
                        const void* weight, int64_t k_total, int cout_pad, const float* bias, const void* residual, void* out,
-                       yad_stream_t stream, void* out_s2d = nullptr) {
+                       yad_stream_t stream, void* out_s2d = nullptr, const void* in2 = nullptr, int cin2_total = 0, int ld_in2 = 0) {
   for (int i = 0; i < p.n_steps; ++i)
     p.step_mma[i] = (uint32_t)((p.step_off[i] - p.min_off) * 8) | (p.step_first[i] ? 1u << 30 : 0u) | (p.step_last[i] ? 1u << 31 : 0u);
   YAD_CHECK_ARG((max_off - p.min_off) * 8 < 65536, "yad_conv_flat: filter reach too large");
@@ -343,14 +495,30 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   p.n_super = (int)(n_mtiles * p.n_ntiles);
   p.flags = 0;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  // shared-memory budget: barriers + bias + alignment slack, then the two rings
-  const size_t fixed = 1024 + (4 * FL_MAX_RING + 4) * 8 + 16 + (size_t)cout_pad * 4 + 64;
-  const size_t budget = 227 * 1024 - fixed;
-  p.NA = n_chunks_distinct > 1 ? 3 : 2;
-  while (p.NA > 1 && (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes > budget) --p.NA;
-  YAD_CHECK_ARG((size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes <= budget, "yad_conv_flat: patch of %d rows does not fit", p.patch_rows);
-  p.NW = (int)((budget - (size_t)p.NA * p.patch_bytes) / p.w_bytes);
-  if (p.NW > FL_MAX_RING) p.NW = FL_MAX_RING;
+  // epilogue through the TMA unit: whole 64-channel blocks, one geometry for input, output and residual
+  static const bool tma_epi_enabled = [] {
+    const char* e = getenv("YAD_FLAT_TMA_EPI");
+    return !(e && e[0] == '0');
+  }();
+  p.tma_epi = (tma_epi_enabled && !p.remap && p.Cout == cout_pad && cout_pad % 64 == 0 && p.co_off % 8 == 0) ? 1 : 0;
+  // shared-memory budget: barriers + bias + alignment slack, the epilogue staging buffers, then the two rings
+  size_t fixed = 0;
+  for (;;) {
+    fixed = 1024 + (4 * FL_MAX_RING + 4 + 2 * FL_NSTAGE) * 8 + 16 + (size_t)cout_pad * 4 + 64 +
+            (p.tma_epi ? (size_t)FL_NSTAGE * FL_STAGE_BYTES : 0);
+    const size_t budget = 227 * 1024 - fixed;
+    p.NA = n_chunks_distinct > 1 ? 3 : 2;
+    while (p.NA > 1 && (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes > budget) --p.NA;
+    const bool fits = (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes <= budget;
+    if ((!fits || p.NA < 2) && p.tma_epi) {     // the staging buffers cost the patch double-buffering: keep the register-sourced epilogue
+      p.tma_epi = 0;
+      continue;
+    }
+    YAD_CHECK_ARG(fits, "yad_conv_flat: patch of %d rows does not fit", p.patch_rows);
+    p.NW = (int)((budget - (size_t)p.NA * p.patch_bytes) / p.w_bytes);
+    if (p.NW > FL_MAX_RING) p.NW = FL_MAX_RING;
+    break;
+  }
   const size_t smem = fixed + (size_t)p.NA * p.patch_bytes + (size_t)p.NW * p.w_bytes;
 
   CUtensorMap map_a, map_w;
@@ -368,9 +536,34 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
     int rc = encode_map_bf16(&map_w, weight, 2, dims, strides, box);
     if (rc) return rc;
   }
+  CUtensorMap map_a2 = map_a;
+  if (in2 != nullptr) {
+    const uint64_t dims[2] = {(uint64_t)cin2_total, (uint64_t)p.F};
+    const uint64_t strides[1] = {(uint64_t)ld_in2 * 2};
+    const uint32_t box[2] = {64u, (uint32_t)FL_BOX_ROWS};
+    int rc = encode_map_bf16(&map_a2, in2, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  CUtensorMap map_out = map_a, map_res = map_a;
+  if (p.tma_epi) {
+    const uint64_t rows_out = (uint64_t)p.F;       // same geometry as the input (no remap)
+    const uint32_t box[2] = {64u, 128u};
+    {
+      const uint64_t dims[2] = {(uint64_t)p.ld_out, rows_out};
+      const uint64_t strides[1] = {(uint64_t)p.ld_out * 2};
+      int rc = encode_map_bf16(&map_out, out, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    if (residual != nullptr) {
+      const uint64_t dims[2] = {(uint64_t)p.ld_res, rows_out};
+      const uint64_t strides[1] = {(uint64_t)p.ld_res * 2};
+      int rc = encode_map_bf16(&map_res, residual, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+  }
   const int nsm = sm_count() > 0 ? sm_count() : 148;
   const int grid = p.n_super < nsm ? p.n_super : nsm;
-  YAD_CUDA(launch_pdl(conv_flat_kernel, dim3((unsigned)grid), dim3(FL_THREADS), smem, (cudaStream_t)stream, map_a, map_w, p, bias,
+  YAD_CUDA(launch_pdl(conv_flat_kernel, dim3((unsigned)grid), dim3(FL_THREADS), smem, (cudaStream_t)stream, map_a, map_a2, map_w, map_out, map_res, p, bias,
                       reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<__nv_bfloat16*>(out),
                       reinterpret_cast<__nv_bfloat16*>(out_s2d)));
   return YAD_OK;
@@ -480,19 +673,27 @@ extern "C" int yad_conv_flat_s2d(const yad_flat_desc* d, const void* in, const v
   return conv_flat_impl(d, in, weight, cout_pad, bias, residual, out, out_s2d, Hp2, Wp2, stream);
 }
 
-extern "C" int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* chunk, const int32_t* dh,
-                                  const int32_t* dw, const int32_t* wk, int64_t k_total, const void* in, const void* weight,
-                                  int32_t cout_pad, const float* bias, const void* residual, void* out, yad_stream_t stream) {
+static int conv_flat_taps_impl(const yad_flat_desc* d, int32_t n_steps, const int32_t* src, const int32_t* chunk, const int32_t* dh,
+                               const int32_t* dw, const int32_t* wk, int64_t k_total, const void* in, const void* in2, int32_t cin2,
+                               int32_t ld_in2, const void* weight, int32_t cout_pad, const float* bias, const void* residual, void* out,
+                               yad_stream_t stream) {
   using namespace yad;
   FlatParams p;
   int rc = check_flat_common(d, in, weight, cout_pad, bias, residual, out, p);
   if (rc) return rc;
+  YAD_CHECK_ARG(in2 == nullptr || (src != nullptr && cin2 % 64 == 0 && cin2 >= 64 && ld_in2 % 8 == 0 && ld_in2 >= cin2 &&
+                                   reinterpret_cast<uintptr_t>(in2) % 16 == 0),
+                "yad_conv_flat_taps2: bad second input (Cin2=%d, ld_in2=%d)", cin2, ld_in2);
   YAD_CHECK_ARG(chunk && dh && dw && wk && n_steps >= 1 && n_steps <= FL_MAX_STEPS, "yad_conv_flat_taps: bad step list (1..%d steps)",
                 FL_MAX_STEPS);
   int min_off = 0, max_off = 0, n_distinct = 0;
   for (int i = 0; i < n_steps; ++i) {
-    YAD_CHECK_ARG(chunk[i] >= 0 && chunk[i] * 64 + 64 <= d->Cin, "yad_conv_flat_taps: step %d reads chunk %d outside Cin=%d", i, chunk[i], d->Cin);
-    YAD_CHECK_ARG(i == 0 || chunk[i] >= chunk[i - 1], "yad_conv_flat_taps: steps must be grouped by ascending chunk");
+    const int sr = (src != nullptr && in2 != nullptr) ? src[i] : 0;
+    YAD_CHECK_ARG(sr == 0 || sr == 1, "yad_conv_flat_taps2: step %d: source must be 0 or 1", i);
+    YAD_CHECK_ARG(chunk[i] >= 0 && chunk[i] * 64 + 64 <= (sr ? cin2 : d->Cin), "yad_conv_flat_taps: step %d reads chunk %d outside Cin=%d", i,
+                  chunk[i], sr ? cin2 : d->Cin);
+    YAD_CHECK_ARG(i == 0 || (sr ? FL_SRC2 : 0) + chunk[i] >= p.step_chunk[i - 1],
+                  "yad_conv_flat_taps: steps must be grouped by (source, ascending chunk)");
     YAD_CHECK_ARG(wk[i] >= 0 && wk[i] % 8 == 0 && (int64_t)wk[i] + 64 <= k_total, "yad_conv_flat_taps: bad weight offset in step %d", i);
     const int adh = dh[i] < 0 ? -dh[i] : dh[i], adw = dw[i] < 0 ? -dw[i] : dw[i];
     YAD_CHECK_ARG(adh <= d->Hp - d->H && adw <= d->Wp - d->W, "yad_conv_flat_taps: step %d reaches (%d,%d) beyond the halo (%d,%d)", i,
@@ -501,13 +702,31 @@ extern "C" int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const
     min_off = off < min_off ? off : min_off;
     max_off = off > max_off ? off : max_off;
     p.step_off[i] = (int16_t)off;
-    p.step_chunk[i] = (int16_t)chunk[i];
-    p.step_first[i] = (i == 0 || chunk[i] != chunk[i - 1]);
-    p.step_last[i] = (i == n_steps - 1 || chunk[i + 1] != chunk[i]);
+    p.step_chunk[i] = (int16_t)((sr ? FL_SRC2 : 0) + chunk[i]);
     p.step_wk[i] = wk[i];
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    p.step_first[i] = (i == 0 || p.step_chunk[i] != p.step_chunk[i - 1]);
+    p.step_last[i] = (i == n_steps - 1 || p.step_chunk[i + 1] != p.step_chunk[i]);
     if (p.step_first[i]) ++n_distinct;
   }
   p.n_steps = n_steps;
   p.min_off = min_off;
-  return launch_flat(p, n_distinct, max_off, in, d->Cin, d->ld_in, weight, k_total, cout_pad, bias, residual, out, stream);
+  return launch_flat(p, n_distinct, max_off, in, d->Cin, d->ld_in, weight, k_total, cout_pad, bias, residual, out, stream, nullptr, in2, cin2,
+                     ld_in2);
+}
+
+extern "C" int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* chunk, const int32_t* dh,
+                                  const int32_t* dw, const int32_t* wk, int64_t k_total, const void* in, const void* weight,
+                                  int32_t cout_pad, const float* bias, const void* residual, void* out, yad_stream_t stream) {
+  return conv_flat_taps_impl(d, n_steps, nullptr, chunk, dh, dw, wk, k_total, in, nullptr, 0, 0, weight, cout_pad, bias, residual, out, stream);
+}
+
+extern "C" int yad_conv_flat_taps2(const yad_flat_desc* d, int32_t n_steps, const int32_t* src, const int32_t* chunk, const int32_t* dh,
+                                   const int32_t* dw, const int32_t* wk, int64_t k_total, const void* in, const void* in2, int32_t cin2,
+                                   int32_t ld_in2, const void* weight, int32_t cout_pad, const float* bias, const void* residual, void* out,
+                                   yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(in2 != nullptr && src != nullptr, "yad_conv_flat_taps2: null pointer");
+  return conv_flat_taps_impl(d, n_steps, src, chunk, dh, dw, wk, k_total, in, in2, cin2, ld_in2, weight, cout_pad, bias, residual, out, stream);
 }

@@ -113,6 +113,7 @@ class InferenceEngine:
         self.fused_neck = os.environ.get("YAD_FUSED_NECK", "1") != "0"
         self.dual_ds = os.environ.get("YAD_DUAL_DS", "1") != "0"
         self.s2d_route = os.environ.get("YAD_S2D", "1") != "0"
+        self.fold_ds = os.environ.get("YAD_FOLD_DS", "1") != "0"
         self._threads_seen = set()
         self.tdtype = torch.bfloat16 if self.dtype == BF16 else torch.float32
         self.cfg = model.config
@@ -455,6 +456,35 @@ class InferenceEngine:
                                          cv.cout_pad, cv.bias.data_ptr(), 0, out.data_ptr(), self._stream())
         _lib.check(rc, f"conv (stride 2, space-to-depth) {cv.name}")
 
+    def _conv_flat_plus_ds(self, blk: dict, t: torch.Tensor, s2d: torch.Tensor, H: int, W: int, out: torch.Tensor):
+        """out = relu(conv2(t) + downsample(x)) as ONE flat convolution (yad_conv_flat_taps2): the 1x1 stride-2 downsample of x is
+        read from plane 0 of x's space-to-depth copy as Cin(x) / 64 extra K steps; weights concatenated along K and biases summed
+        once per engine (torchvision BasicBlock, resnet.py:96-103)."""
+        cv, ds = blk["c2"], blk["ds"]
+        B, Wp, Hp, ld_in = t.shape
+        assert s2d.shape[:3] == t.shape[:3] and out.shape[:3] == t.shape[:3] and ds.cout_pad == cv.cout_pad and cv.kh == 3 and cv.ph == 1
+        fz = blk.get("c2ds")
+        if fz is None:
+            fz = blk["c2ds"] = {"w": torch.cat([cv.w, ds.w], 1).contiguous(), "bias": (cv.bias + ds.bias).contiguous(), "steps": {}}
+        st = fz["steps"].get((H, W))
+        if st is None:
+            steps = []
+            for c in range(cv.cin_pad // 64):
+                for kh in range(3):
+                    for kw in range(3):
+                        if abs(kh - 1) < H and abs(kw - 1) < W:
+                            steps.append((0, c, kh - 1, kw - 1, (kh * 3 + kw) * cv.cin_pad + c * 64))
+            for c in range(ds.cin_pad // 64):
+                steps.append((1, c, 0, 0, 9 * cv.cin_pad + c * 64))
+            arr = lambda i: (C.c_int32 * len(steps))(*[s_[i] for s_ in steps])   # noqa: E731
+            st = fz["steps"][(H, W)] = (arr(0), arr(1), arr(2), arr(3), arr(4), len(steps))
+        d = FlatDesc(B=B, H=H, W=W, Hp=Hp, Wp=Wp, Cin=cv.cin_pad, ld_in=ld_in, Cout=cv.cout, ld_out=out.shape[3], co_off=0, kh=1, kw=1,
+                     ph=0, pw=0, act=cv.act, ld_res=0)
+        rc = self.lib.yad_conv_flat_taps2(C.byref(d), st[5], st[0], st[1], st[2], st[3], st[4], 9 * cv.cin_pad + ds.cin_pad, t.data_ptr(),
+                                          s2d.data_ptr(), ds.cin_pad, s2d.shape[3], fz["w"].data_ptr(), cv.cout_pad, fz["bias"].data_ptr(), 0,
+                                          out.data_ptr(), self._stream())
+        _lib.check(rc, f"conv_flat (+ downsample as K steps) {cv.name}")
+
     def _conv_flat_s2(self, cv: _Conv, x: torch.Tensor, H: int, W: int, out: torch.Tensor, Ho: int, Wo: int,
                       ds: Optional[_Conv] = None, out_ds: Optional[torch.Tensor] = None):
         """Strided conv, flat in -> flat out: the tap-by-tap kernel run with the roles of H and W swapped (so that the
@@ -603,8 +633,13 @@ class InferenceEngine:
                             self._conv_flat_s2(blk["ds"], cur, H, W, idt, Ho, Wo)
                     elif s2d_in is not None:      # stride-2 block on the space-to-depth copy: both convs in the patch-resident kernel
                         self._conv_s2d(c1v, s2d_in, H, W, t, Ho, Wo)
-                        if "ds" in blk:
+                        fold_ds = "ds" in blk and self.fold_ds and bi < len(blocks) - 1 and blk["ds"].cout_pad == c2v.cout_pad
+                        if "ds" in blk and not fold_ds:
                             self._conv_s2d(blk["ds"], s2d_in, H, W, idt, Ho, Wo)
+                        if fold_ds:               # ... and the downsample branch rides in conv2's GEMM
+                            self._conv_flat_plus_ds(blk, t, s2d_in, Ho, Wo, y)
+                            cur, H, W, s2d_in = y, Ho, Wo, None
+                            continue
                     else:
                         dual = ("ds" in blk and self.dual_ds and blk["ds"].cout_pad == c1v.cout_pad == c1v.cout and c1v.cout % 32 == 0
                                 and (blk["ds"].sh, blk["ds"].sw) == (c1v.sh, c1v.sw))
