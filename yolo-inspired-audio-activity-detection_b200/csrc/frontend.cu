@@ -277,16 +277,9 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
         // taper_input (modules/_architecture.py:87-94): the resampled signal times a clip-long window, before framing
         const float* tpg = TAPER ? taper + (int64_t)gcl * (FE_FR * FE_NFFT) : nullptr;
         int f = f0, pos = pos0;
-        for (int h = sl; h < p.HG; h += p.nslice) {
-          const float* xs = sx + h * p.O;
-          float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);
-#pragma unroll
-          for (int j = 0; j < FE_QW; ++j) {
-            const float xv = xs[j];
-            const float2 xx = make_float2(xv, xv);
-            a01 = __ffma2_rn(tq01[j], xx, a01);
-            a23 = __ffma2_rn(tq23[j], xx, a23);
-          }
+        // two hops per iteration: four independent FFMA2 chains per thread instead of two (the role has two warps per SM
+        // sub-partition; with two chains each the FMA pipe idled on the 4-cycle dependency)
+        auto finish = [&](float2 a01, float2 a23, int h) {
           const float4 w = *reinterpret_cast<const float4*>(s_win + pos);
           if (TAPER) {       // (x * taper) * hann, in the reference's order; samples past the window (unused tail frames) get 0
             const int o = h * p.P + 4 * quad;
@@ -300,6 +293,35 @@ frontend_mel_kernel(const void* __restrict__ pcm, const float* __restrict__ tape
           *reinterpret_cast<float4*>(fr + f * (2 * FFT_Z_STRIDE) + pos) = make_float4(a01.x, a01.y, a23.x, a23.y);
           pos += o_step;
           while (pos >= FE_NFFT) { pos -= FE_NFFT; ++f; }
+        };
+        int h = sl;
+        for (; h + p.nslice < p.HG; h += 2 * p.nslice) {
+          const float* xs0 = sx + h * p.O;
+          const float* xs1 = xs0 + p.nslice * p.O;
+          float2 a01 = make_float2(0.0f, 0.0f), a23 = a01, b01 = a01, b23 = a01;
+#pragma unroll
+          for (int j = 0; j < FE_QW; ++j) {
+            const float xv = xs0[j], yv = xs1[j];
+            const float2 xx = make_float2(xv, xv), yy = make_float2(yv, yv);
+            a01 = __ffma2_rn(tq01[j], xx, a01);
+            a23 = __ffma2_rn(tq23[j], xx, a23);
+            b01 = __ffma2_rn(tq01[j], yy, b01);
+            b23 = __ffma2_rn(tq23[j], yy, b23);
+          }
+          finish(a01, a23, h);
+          finish(b01, b23, h + p.nslice);
+        }
+        if (h < p.HG) {      // odd hop count of this slice
+          const float* xs = sx + h * p.O;
+          float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int j = 0; j < FE_QW; ++j) {
+            const float xv = xs[j];
+            const float2 xx = make_float2(xv, xv);
+            a01 = __ffma2_rn(tq01[j], xx, a01);
+            a23 = __ffma2_rn(tq23[j], xx, a23);
+          }
+          finish(a01, a23, h);
         }
       }
       __threadfence_block();
@@ -559,7 +581,7 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
   float* s_dct = fb2_smem;                       // [32][32]
   float* s_x = fb2_smem + FE_NMEL * FE_NMEL;     // [32][T]
   __shared__ float s_redf[32];
-  __shared__ double s_redd[32];
+  __shared__ double s_red4[32 * 4];
   const int t = threadIdx.x;
   const bool act = t < T;
   for (int i = threadIdx.x; i < FE_NMEL * FE_NMEL; i += blockDim.x) s_dct[i] = dct[i];
@@ -627,10 +649,27 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
     const double n_el = (double)FE_NMEL * (double)T;
     float mu0 = 0.0f, mu1 = 0.0f, sd0 = 1.0f, sd1 = 1.0f;
     if (standardise) {
-      const double S0 = block_reduce_n<double>(s0, s_redd, dadd_op, 0.0);
-      const double Q0 = block_reduce_n<double>(q0, s_redd, dadd_op, 0.0);
-      const double S1 = block_reduce_n<double>(s1, s_redd, dadd_op, 0.0);
-      const double Q1 = block_reduce_n<double>(q1, s_redd, dadd_op, 0.0);
+      // the four moments in ONE block reduction (two barriers instead of eight): per-warp shuffle sums, lane 0 parks the four
+      // partial sums, every thread then adds the warps' partials in the same order (bit-identical to four separate reductions)
+      double m4[4] = {s0, q0, s1, q1};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m4[i] += __shfl_xor_sync(0xffffffffu, m4[i], o);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_red4[(threadIdx.x >> 5) * 4 + i] = m4[i];
+      }
+      __syncthreads();
+      double S0 = 0.0, Q0 = 0.0, S1 = 0.0, Q1 = 0.0;
+      const int nw = (blockDim.x + 31) >> 5;
+      for (int w = 0; w < nw; ++w) {
+        S0 += s_red4[w * 4 + 0];
+        Q0 += s_red4[w * 4 + 1];
+        S1 += s_red4[w * 4 + 2];
+        Q1 += s_red4[w * 4 + 3];
+      }
       mu0 = (float)(S0 / n_el);
       mu1 = (float)(S1 / n_el);
       sd0 = (float)sqrt(fmax(Q0 - S0 * S0 / n_el, 0.0) / (n_el - 1.0));
