@@ -262,6 +262,14 @@ int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_
                    const void* kbs, int32_t n_kb, int32_t pool_bytes, int32_t n_slots, float* const* heads,
                    const int32_t* head_W, int32_t head_ld, void* dbg, yad_stream_t stream);
 
+/* ------------------------------------------------------------------ file-rate resampling in front of the network
+ * Replaces the torchaudio.transforms.Resample(orig_freq = file rate, new_freq = model sample_rate) of inference.py:152-159
+ * (default Hann-windowed sinc bank, [ta] functional.py:1305-1431).  x [B, L] f32 or int16 PCM (x / 32768), kernel [P][2 * width + O]
+ * f32 (P / O = new / orig rate over their gcd; built by yad_b200.frontend_consts.sinc_resample_kernel), out [B, Lout] f32 with
+ * Lout <= ceil(P * L / O). */
+int yad_resample_sinc(const void* x, int32_t x_is_i16, int64_t B, int64_t L, int32_t O, int32_t P, int32_t width,
+                      const float* kernel, float* out, int64_t Lout, yad_stream_t stream);
+
 /* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
  * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5
  * :173-174,181-182; cascaded max_pool2d k5 s1 p2 :207-209.  All write into a channel slice
@@ -353,15 +361,26 @@ int yad_collate_clips(const void* packed, int32_t dtype_i16, const int64_t* offs
  *   pred [B, G, A, 3+nc] f32 (decoded predictions: obj, cls.., centre_s, width_s); matches (bi, gi, ai, cl i64, cw [M,2] f32)
  *   as produced by yad_build_targets, M known to the host.
  * Outputs: grad [B, G, A, 3+nc] f32 (overwritten) = d(box_w * box + conf_scale * conf + class_w * cls) / d pred, where
- * conf_scale = conf_w * the scale's weight (4 / 2 / 1); acc [8] f64 sums: {sum(1-ciou), sum ciou, sum BCE objectness over all
+ * conf_scale = conf_w * the scale's weight (4 / 2 / 1); acc [16] f64 (9 used) sums: {sum(1-ciou), sum ciou, sum BCE objectness over all
  * cells, sum BCE class, sum sigmoid(obj) over matches, sum sigmoid(obj) over cells with t_conf == 0, count of those cells,
- * count of matches whose class != ignore_index}; confusion [nc][nc] i32 (target class x argmax class) for the
+ * count of matches whose class != ignore_index, sum of class_weights[target] over those matches}; confusion [nc][nc] i32 (target class x argmax class) for the
  * accuracy / precision / recall / f1 metrics.  Duplicate (b,g,a) matches: the last one owns t_conf (index_put_ order, Q12),
  * all of them receive box / class gradients.  Workspaces: owner_ws [B*G*A] i32, ciou_ws [M] f32. */
 int yad_loss_scale(const float* pred, int64_t B, int32_t G, int32_t A, int32_t nc, const int64_t* bi, const int64_t* gi,
                    const int64_t* ai, const int64_t* cl, const float* cw, int32_t M, float box_w, float conf_scale,
                    float class_w, float label_smoothing, int64_t ignore_index, int32_t* owner_ws, float* ciou_ws,
                    int32_t* confusion, double* acc, float* grad, yad_stream_t stream);
+
+/* The other two branches of the reference constructor (modules/_loss.py:74-81):
+ *   cls_mode 1: class loss = nn.CrossEntropyLoss(weight=class_weights, ignore_index) over the class-valid matches (multi_label:
+ *               false, :157-158); class_weights [nc] f32 on the device or NULL; acc[3] then holds sum_m w[c_m] (logsumexp - x_c)
+ *               and acc[8] the divisor sum_m w[c_m];
+ *   focal_gamma > 0: objectness = FocalLoss(alpha, gamma, with_logits=True) = mean(alpha (1 - exp(-bce))^gamma bce) (:9-37). */
+int yad_loss_scale_ex(const float* pred, int64_t B, int32_t G, int32_t A, int32_t nc, const int64_t* bi, const int64_t* gi,
+                      const int64_t* ai, const int64_t* cl, const float* cw, int32_t M, float box_w, float conf_scale,
+                      float class_w, float label_smoothing, int64_t ignore_index, int32_t cls_mode, const float* class_weights,
+                      float focal_alpha, float focal_gamma, int32_t* owner_ws, float* ciou_ws, int32_t* confusion, double* acc,
+                      float* grad, yad_stream_t stream);
 
 /* ------------------------------------------------------------------ train-mode network (fp32, NHWC rows x channels)
  * What autograd does for TrainerPipeline.__feed (pipeline/_trainer.py:94-108): the backward of F.conv2d, BatchNorm2d in

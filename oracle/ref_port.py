@@ -564,8 +564,12 @@ def evaluate_waveform(wav: Tensor, sd: Dict[str, Tensor], num_classes: int, samp
                       batch_size: int, idx2class_map: Dict[int, str], iou_threshold: float = 0.1, conf_threshold: float = 0.65,
                       config: Dict = DEFAULT_CONFIG):
     """inference.evaluate_audio from the decoded mono waveform [n] on (ref: inference.py:126-198), incl. its clip-index quirk
-    (``batch_idxs += batch_idxs_list[-1][-1]``).  Returns (segments in file time, batch_idxs, rle rows)."""
+    (``batch_idxs += batch_idxs_list[-1][-1]``).  ``sample_rate`` is the FILE's rate: when it differs from the model's
+    ``config['sample_rate']`` every batch goes through an extra torchaudio Resample first (:152-159).
+    Returns (segments in file time, batch_idxs, rle rows)."""
     from datetime import timedelta
+    model_rate = int(config["sample_rate"])
+    rs_kernel = resample_kernel(int(sample_rate), model_rate)[0] if int(sample_rate) != model_rate else None
     sample_size = int(sample_duration * sample_rate)
     batch_start, batch_end = 0, batch_size * sample_duration
     seg_l, idx_l = [], []
@@ -577,7 +581,10 @@ def evaluate_waveform(wav: Tensor, sd: Dict[str, Tensor], num_classes: int, samp
         if x.shape[0] % sample_size != 0:
             nb = int(np.ceil(x.shape[0] / sample_size))
             x = torch.cat([x, torch.zeros((nb * sample_size - x.shape[0],), dtype=x.dtype)], dim=0)
-        out = forward(x.reshape(-1, 1, sample_size), sd, num_classes, config, combine_scales=True)
+        xb = x.reshape(-1, 1, sample_size)
+        if rs_kernel is not None:
+            xb = resample(xb, rs_kernel, int(sample_rate), model_rate)
+        out = forward(xb, sd, num_classes, config, combine_scales=True)
         seg, bidx = process_model_outputs(out, iou_threshold, conf_threshold, sample_duration, True)
         if idx_l:
             bidx = bidx + idx_l[-1][-1]
@@ -702,9 +709,12 @@ def compute_ciou(p_cw: Tensor, t_cw: Tensor, e: float = 1e-8, _h: float = 10.0) 
 def detection_loss(preds: Sequence[Tensor], targets: Tensor, anchors_dict: Dict[str, List[float]], num_classes: int,
                    anchor_t: float = 5, edge_t: float = 0.5, sample_duration: float = 60, box_w: float = 0.1,
                    conf_w: float = 1.0, class_w: float = 0.3, label_smoothing: float = 0.08,
-                   ignore_index: int = -100) -> Tuple[Tensor, Dict[str, float]]:
-    """AudioDetectionLoss.forward with multi_label=True, no focal loss (the default
-    train_config).  ref: modules/_loss.py:83-190.  Metrics: the device-computable subset."""
+                   ignore_index: int = -100, multi_label: bool = True, class_weights: Optional[Tensor] = None,
+                   alpha: Optional[float] = None, gamma: Optional[float] = None) -> Tuple[Tensor, Dict[str, float]]:
+    """AudioDetectionLoss.forward.  ref: modules/_loss.py:83-190; defaults = the reference train_config (multi_label BCE class
+    loss, BCEWithLogits objectness).  multi_label=False: CrossEntropyLoss(weight=class_weights) over the class-valid matches
+    (:79-81,157-158); alpha and gamma: FocalLoss(with_logits=True) objectness = mean(alpha (1 - exp(-bce))^gamma bce) (:9-37,
+    74-75).  Metrics: the device-computable subset."""
     lbox = lconf = lcls = 0.0
     ws = (4.0, 2.0, 1.0)
     met = {"mean_ciou": 0.0, "conf_loss": 0.0, "class_loss": 0.0, "avg_pos_conf": 0.0, "avg_neg_conf": 0.0}
@@ -722,13 +732,20 @@ def detection_loss(preds: Sequence[Tensor], targets: Tensor, anchors_dict: Dict[
         _, first_rev = np.unique(keys[::-1], return_index=True)
         last = torch.from_numpy(np.sort(len(keys) - 1 - first_rev).astype(np.int64))
         t_conf[bi[last], gi[last], ai[last]] = ciou.detach()[last]
-        conf = F.binary_cross_entropy_with_logits(p[..., 0], t_conf)
+        if alpha and gamma:
+            bce = F.binary_cross_entropy_with_logits(p[..., 0], t_conf, reduction="none")
+            conf = ((alpha * (1 - torch.exp(-bce)) ** gamma) * bce).mean()
+        else:
+            conf = F.binary_cross_entropy_with_logits(p[..., 0], t_conf)
         m = cl != ignore_index
         pcls = mp[:, 1:1 + num_classes][m]
-        cn = 0.5 * label_smoothing
-        tcls = torch.full_like(pcls, cn)
-        tcls[range(int(m.sum())), cl[m]] = 1.0 - cn
-        cls = F.binary_cross_entropy_with_logits(pcls, tcls)
+        if multi_label:
+            cn = 0.5 * label_smoothing
+            tcls = torch.full_like(pcls, cn)
+            tcls[range(int(m.sum())), cl[m]] = 1.0 - cn
+            cls = F.binary_cross_entropy_with_logits(pcls, tcls)
+        else:
+            cls = F.cross_entropy(pcls, cl[m], weight=class_weights, ignore_index=ignore_index)
         hn = lambda v: v if bool(v == v) else torch.tensor(0.0)
         lbox = lbox + hn(box)
         lconf = lconf + w * hn(conf)

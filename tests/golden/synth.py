@@ -133,3 +133,13 @@ def eval_waveform() -> torch.Tensor:
     """270 s mono waveform (4.5 clips of 60 s: three batches of 2, 2 and 1 zero-padded clip)."""
     x = synth_clips(5, 22050 * 60, seed=4000, silence_tail_every=0)
     return x.reshape(-1)[: int(270 * 22050)].contiguous()
+
+
+EVAL_RATE2 = 16000
+
+
+def eval_waveform_rate(rate: int = EVAL_RATE2) -> torch.Tensor:
+    """150 s mono waveform at another file rate (2.5 clips of 60 s: two batches of 2 and 1 zero-padded clip): the chunker's
+    file-rate branch (inference.py:152-159)."""
+    x = synth_clips(3, rate * 60, seed=4100, silence_tail_every=0)
+    return x.reshape(-1)[: int(150 * rate)].contiguous()

@@ -509,6 +509,61 @@ def test_detection_loss_vs_reference_golden(gold, cuda_dev):
                         "precision", "recall"}
 
 
+LOSS_VARIANTS = {
+    "ce": dict(multi_label=False),
+    "ce_weighted": dict(multi_label=False, class_weights=torch.tensor([0.3, 1.7])),
+    "focal": dict(multi_label=True, alpha=0.25, gamma=1.5),
+    "focal_ce": dict(multi_label=False, alpha=0.4, gamma=2.0, class_weights=torch.tensor([1.2, 0.6])),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LOSS_VARIANTS))
+def test_detection_loss_variants_vs_reference_golden(gold, name, cuda_dev):
+    """yad_loss_scale_ex: cross-entropy class loss (multi_label: false, with / without class weights) and the focal objectness
+    loss against loss value, gradients and metrics of the LIVE reference (modules/_loss.py:9-37,74-81,157-158; fixture
+    tests/golden/loss_variants.npz), plus a random case with ignore labels and duplicates against the oracle."""
+    g, tr = gold("loss_variants"), gold("train")
+    lc = dict(yad_b200.default_config()["train_config"]["loss_config"])
+    lc.update(LOSS_VARIANTS[name])
+    mod = yad_b200.AudioDetectionLoss(yad_b200.default_config()["anchors"], 2, **lc)
+    tg = torch.from_numpy(g["targets"]).to(cuda_dev)
+    preds = [torch.from_numpy(tr[f"pred{i}"]).to(cuda_dev).requires_grad_(True) for i in range(3)]
+    with torch.enable_grad():
+        loss, met = mod(preds, tg)
+        loss.backward()
+    np.testing.assert_allclose(float(loss), float(g[f"{name}_loss"]), rtol=5e-6)
+    for i in range(3):
+        np.testing.assert_allclose(preds[i].grad.cpu().numpy(), g[f"{name}_grad{i}"], atol=2e-7, rtol=2e-4)
+    for k in ("conf_loss", "class_loss", "mean_ciou", "accuracy", "f1"):
+        np.testing.assert_allclose(met[k], float(g[f"{name}_{k}"]), rtol=2e-5)
+    # random case vs the oracle
+    gen = torch.Generator().manual_seed(77)
+    B, T = 8, 150
+    rp = []
+    for G in (120, 60, 30):
+        p = torch.randn(B, G, 3, 5, generator=gen) * 2
+        p[..., 3] = torch.rand(B, G, 3, generator=gen) * 60
+        p[..., 4] = torch.rand(B, G, 3, generator=gen) * 20 + 0.05
+        rp.append(p)
+    t2 = torch.zeros(T, 4)
+    t2[:, 0] = torch.randint(0, B, (T,), generator=gen).float()
+    t2[:, 1] = torch.randint(0, 2, (T,), generator=gen).float()
+    t2[::9, 1] = -100.0
+    t2[:, 2] = torch.rand(T, generator=gen) * 60
+    t2[:, 3] = torch.rand(T, generator=gen) * 12 + 0.2
+    t2[7] = t2[6]
+    with torch.enable_grad():
+        ref_p = [p.clone().requires_grad_(True) for p in rp]
+        ref_loss, _ = O.detection_loss(ref_p, t2, O.DEFAULT_CONFIG["anchors"], 2, **LOSS_VARIANTS[name])
+        ref_loss.backward()
+        cu_p = [p.to(cuda_dev).requires_grad_(True) for p in rp]
+        loss2, _ = mod(cu_p, t2.to(cuda_dev))
+        loss2.backward()
+    np.testing.assert_allclose(float(loss2), float(ref_loss), rtol=5e-5)
+    for a, b in zip(cu_p, ref_p):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), atol=3e-7, rtol=5e-4)
+
+
 @pytest.mark.parametrize("seed,B,T", [(0, 4, 23), (1, 16, 200), (2, 3, 0), (3, 32, 900)])
 def test_detection_loss_vs_oracle(seed, B, T, cuda_dev):
     """Random predictions / targets (incl. duplicates, ignore labels, the no-target case) vs the CPU oracle."""
@@ -594,8 +649,30 @@ def test_evaluate_waveform_vs_live_reference(models, gold, cuda_dev):
     wi = (wav.clamp(-1, 1) * 32767).round().to(torch.int16)
     seg16, bidx16, _ = yad_b200.evaluate_waveform(m, wi, synth.EVAL_SR, 60, 2, {0: "speech", 1: "music"}, synth.EVAL_IOU, synth.EVAL_CONF)
     assert seg16.shape == seg.shape and torch.equal(bidx16, bidx)        # 16-bit quantisation does not move a keep decision here
-    with pytest.raises(NotImplementedError):
-        yad_b200.evaluate_waveform(m, wav, 16000, 60, 2, {0: "speech", 1: "music"})
+
+
+def test_evaluate_waveform_file_rate_vs_live_reference(models, gold, cuda_dev):
+    """The chunker's file-rate branch (inference.py:152-159): a 16 kHz file through yad_resample_sinc + the 22.05 kHz model ==
+    the live reference's evaluate_audio (same clips kept, same labels, times within 2e-3 s, same CSV rows); the resampling
+    kernel alone == torchaudio.transforms.Resample for three rate pairs (fp32) and its int16 entry == the fp32 one on x / 32768."""
+    from test_oracle_golden import _eval_expected, _rows_as_csv
+    from yad_b200.evaluate import resample_to_model_rate
+    g = gold("eval_rate16k")
+    x = torch.from_numpy(g["rs_x"]).to(cuda_dev)
+    for o, n in ((16000, 22050), (48000, 22050), (44100, 22050)):
+        got = resample_to_model_rate(x, o, n)
+        np.testing.assert_allclose(got.cpu().numpy(), g[f"rs_{o}_{n}"], atol=3e-6, rtol=1e-5)
+    xi = (x.clamp(-1, 1) * 32767).round().to(torch.int16)
+    np.testing.assert_array_equal(resample_to_model_rate(xi, 48000, 22050).cpu().numpy(),
+                                  resample_to_model_rate(xi.float() / 32768.0, 48000, 22050).cpu().numpy())
+    seg_e, bidx_e, rows_e = _eval_expected(gold, "eval_rate16k")
+    m = models[("train", "f32")]
+    seg, bidx, rows = yad_b200.evaluate_waveform(m, synth.eval_waveform_rate(), synth.EVAL_RATE2, 60, 2, {0: "speech", 1: "music"},
+                                                 synth.EVAL_IOU, synth.EVAL_CONF)
+    np.testing.assert_array_equal(bidx.numpy(), bidx_e.numpy())
+    np.testing.assert_array_equal(seg[:, 2].numpy(), seg_e[:, 2].numpy())
+    np.testing.assert_allclose(seg.numpy(), seg_e.numpy(), atol=2e-3, rtol=1e-4)
+    assert _rows_as_csv(rows) == rows_e
 
 
 # ------------------------------------------------------------------ other config-selectable backbones (SURVEY 8(f) N3)

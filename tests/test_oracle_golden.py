@@ -137,6 +137,31 @@ def test_loss_value_and_grads(gold):
         np.testing.assert_allclose(preds[i].grad.numpy(), g[f"grad{i}"], atol=1e-7, rtol=1e-4)
 
 
+LOSS_VARIANTS = {
+    "ce": dict(multi_label=False),
+    "ce_weighted": dict(multi_label=False, class_weights=torch.tensor([0.3, 1.7])),
+    "focal": dict(multi_label=True, alpha=0.25, gamma=1.5),
+    "focal_ce": dict(multi_label=False, alpha=0.4, gamma=2.0, class_weights=torch.tensor([1.2, 0.6])),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LOSS_VARIANTS))
+def test_loss_variants_vs_live_reference(gold, name):
+    """Cross-entropy class loss (with / without class weights) and focal objectness (modules/_loss.py:9-37,74-81,157-158): the
+    oracle against loss, gradients and metrics the LIVE reference produced (tests/golden/make_golden_loss_variants.py)."""
+    g, tr = gold("loss_variants"), gold("train")
+    tg = torch.from_numpy(g["targets"])
+    preds = [torch.from_numpy(tr[f"pred{i}"]).clone().requires_grad_(True) for i in range(3)]
+    with torch.enable_grad():
+        loss, met = O.detection_loss(preds, tg, O.DEFAULT_CONFIG["anchors"], 2, **LOSS_VARIANTS[name])
+        loss.backward()
+    np.testing.assert_allclose(float(loss), float(g[f"{name}_loss"]), rtol=2e-6)
+    for i in range(3):
+        np.testing.assert_allclose(preds[i].grad.numpy(), g[f"{name}_grad{i}"], atol=1e-8, rtol=1e-5)
+    for k in ("conf_loss", "class_loss", "mean_ciou"):
+        np.testing.assert_allclose(met[k], float(g[f"{name}_{k}"]), rtol=1e-5)
+
+
 def test_adam_and_ema(gold):
     g = gold("train")
     w = torch.from_numpy(g["adam_w0"]).clone()
@@ -195,8 +220,8 @@ def test_getitem_collate_vs_live_reference(gold):
     np.testing.assert_array_equal(targets.numpy(), g["targets"])
 
 
-def _eval_expected(gold):
-    g = gold("eval_long")
+def _eval_expected(gold, name="eval_long"):
+    g = gold(name)
     segs, idxs = [], []
     for i in range(int(g["n_batches"])):
         b = torch.from_numpy(g[f"bidx{i}"]).clone()
@@ -208,7 +233,7 @@ def _eval_expected(gold):
     seg[..., -2:] += bidx.unsqueeze(-1) * 60
     import os
     from conftest import GOLD
-    rows = [ln.strip() for ln in open(os.path.join(GOLD, "eval_long_results.csv")).read().strip().splitlines()[1:]]
+    rows = [ln.strip() for ln in open(os.path.join(GOLD, f"{name}_results.csv")).read().strip().splitlines()[1:]]
     return seg, bidx, rows
 
 
@@ -222,6 +247,23 @@ def test_evaluate_waveform_vs_live_reference(gold, ref_state_dict):
     reference on a 270 s waveform: per-batch segments as its process_model_outputs returned them and the CSV it wrote."""
     seg_e, bidx_e, rows_e = _eval_expected(gold)
     seg, bidx, rows = O.evaluate_waveform(synth.eval_waveform(), ref_state_dict, 2, synth.EVAL_SR, 60, 2, {0: "speech", 1: "music"},
+                                          synth.EVAL_IOU, synth.EVAL_CONF)
+    np.testing.assert_array_equal(bidx.numpy(), bidx_e.numpy())
+    np.testing.assert_allclose(seg.numpy(), seg_e.numpy(), atol=1e-4, rtol=1e-5)
+    assert _rows_as_csv(rows) == rows_e
+
+
+def test_evaluate_waveform_file_rate_vs_live_reference(gold, ref_state_dict):
+    """The chunker's file-rate branch (inference.py:152-159: a 16 kHz file, the model at 22.05 kHz, an extra torchaudio Resample
+    per batch): the oracle == the live reference on a 150 s waveform; and the oracle's sinc bank + polyphase resampling == what
+    torchaudio.transforms.Resample returned for three rate pairs (tests/golden/make_golden_eval_rate.py)."""
+    g = gold("eval_rate16k")
+    x = torch.from_numpy(g["rs_x"])
+    for o, n in ((16000, 22050), (48000, 22050), (44100, 22050)):
+        got = O.resample(x, O.resample_kernel(o, n)[0], o, n)
+        np.testing.assert_allclose(got.numpy(), g[f"rs_{o}_{n}"], atol=2e-6, rtol=1e-5)
+    seg_e, bidx_e, rows_e = _eval_expected(gold, "eval_rate16k")
+    seg, bidx, rows = O.evaluate_waveform(synth.eval_waveform_rate(), ref_state_dict, 2, synth.EVAL_RATE2, 60, 2, {0: "speech", 1: "music"},
                                           synth.EVAL_IOU, synth.EVAL_CONF)
     np.testing.assert_array_equal(bidx.numpy(), bidx_e.numpy())
     np.testing.assert_allclose(seg.numpy(), seg_e.numpy(), atol=1e-4, rtol=1e-5)

@@ -59,6 +59,7 @@ SIGNATURES = {
     "yad_conv_flat_s2d": [C.POINTER(FlatDesc), _p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _p],
     "yad_conv_flat_taps": [C.POINTER(FlatDesc), _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i64, _p, _p,
                            _i32, _p, _p, _p, _p],
+    "yad_resample_sinc": [_p, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p, _i64, _p],
     "yad_hmean": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_resize_w": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_neck_fused": [C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), _i64, _p, _i64, _p, _i32, _p, _i32, _p, _i32, _i32, _i32,
@@ -79,6 +80,8 @@ SIGNATURES = {
     "yad_compact_segments": [_p, _p, _i64, _i32, _p, _p, _p, _p],
     "yad_build_targets": [_p, _i32, _p, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p],
     "yad_collate_clips": [_p, _i32, _p, _p, _p, _i64, _i64, _p, _p],
+    "yad_loss_scale_ex": [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _f32, _f32, _f32, _f32, _i64, _i32, _p, _f32, _f32, _p, _p, _p,
+                          _p, _p, _p],
     "yad_loss_scale": [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, _f32, _f32, _f32, _f32, _i64, _p, _p, _p, _p, _p, _p],
     "yad_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "yad_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],

@@ -249,6 +249,38 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int64_t B, int
   for (int c = 0; c < C; ++c) st_from_float(out + gid * ld_out + c, in[(b * C + c) * HW + px]);
 }
 
+
+// File-rate resampling in front of the network (inference.py:152-159: torchaudio.transforms.Resample(orig_freq = the file's
+// rate, new_freq = the model's sample_rate) with its default Hann-windowed sinc bank, [ta] functional.py:1405-1431):
+//   out[b, i * P + p] = sum_k kernel[p][k] * xpad[b, i * O + k],  xpad = x zero-padded by (width, width + O),
+// P / O = new / orig rate over their gcd, first ceil(P * L / O) samples.  One thread per output sample; a cold path (runs once
+// per file batch, ~KW = 2 * width + O multiply-adds per sample), so no staging: taps and samples come through L1.
+template <typename Tin>
+__global__ void resample_sinc_kernel(const Tin* __restrict__ x, int64_t B, int64_t L, int O, int P, int width, int KW,
+                                     const float* __restrict__ kernel, float* __restrict__ out, int64_t Lout) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * Lout) return;
+  const int64_t b = idx / Lout, t = idx - b * Lout;
+  const int64_t i = t / P;
+  const int ph = (int)(t - i * P);
+  const int64_t base = i * O - width;
+  const Tin* xb = x + b * L;
+  const float* kp = kernel + (int64_t)ph * KW;
+  const int k_lo = base < 0 ? (int)(-base) : 0;
+  const int64_t hi = L - base;
+  const int k_hi = hi < KW ? (int)(hi > 0 ? hi : 0) : KW;
+  float acc = 0.0f;
+  for (int k = k_lo; k < k_hi; ++k) {
+    float v;
+    if (sizeof(Tin) == 2)
+      v = (float)xb[base + k] * (1.0f / 32768.0f);      // 16-bit PCM: what torchaudio.load(normalize=True) hands the reference
+    else
+      v = (float)xb[base + k];
+    acc = fmaf(__ldg(kp + k), v, acc);
+  }
+  out[idx] = acc;
+}
+
 }  // namespace yad
 
 #define YAD_DISPATCH_DTYPE(dtype, KERNEL, ...)                                              \
@@ -376,3 +408,25 @@ int yad_repvgg_merge(const void* a, const void* b, const void* x, const float* s
 }
 
 }  // extern "C"
+
+extern "C" int yad_resample_sinc(const void* x, int32_t x_is_i16, int64_t B, int64_t L, int32_t O, int32_t P, int32_t width,
+                                 const float* kernel, float* out, int64_t Lout, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x && kernel && out, "yad_resample_sinc: null pointer");
+  YAD_CHECK_ARG(B >= 0 && L >= 1 && O >= 1 && P >= 1 && width >= 0, "yad_resample_sinc: bad sizes");
+  YAD_CHECK_ARG(Lout >= 0 && Lout <= ((int64_t)P * L + O - 1) / O, "yad_resample_sinc: Lout=%lld exceeds ceil(P * L / O)", (long long)Lout);
+  if (B == 0 || Lout == 0) return YAD_OK;
+  const int KW = 2 * width + O;
+  const int threads = 256;
+  const int64_t n = B * Lout;
+  YAD_CHECK_ARG((n + threads - 1) / threads < ((int64_t)1 << 31), "yad_resample_sinc: too many samples");
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  if (x_is_i16)
+    resample_sinc_kernel<int16_t><<<blocks, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int16_t*>(x), B, L, O, P, width, KW,
+                                                                             kernel, out, Lout);
+  else
+    resample_sinc_kernel<float><<<blocks, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(x), B, L, O, P, width, KW,
+                                                                           kernel, out, Lout);
+  YAD_LAUNCH_CHECK();
+  return YAD_OK;
+}

@@ -1,6 +1,9 @@
 // YOLO-style detection loss of one scale: forward value, metrics sums and the gradient with respect to the decoded
-// predictions.  Replaces AudioDetectionLoss.loss_fn + compute_ciou (modules/_loss.py:115-228) for the default
-// train_config (multi_label BCE class loss with label smoothing, BCEWithLogits objectness, no focal loss):
+// predictions.  Replaces AudioDetectionLoss.loss_fn + compute_ciou (modules/_loss.py:115-228).  Default train_config
+// (multi_label BCE class loss with label smoothing, BCEWithLogits objectness); the other two branches of the constructor
+// (:74-81) are selected by yad_loss_scale_ex: cls_mode 1 = CrossEntropyLoss(weight=class_weights) over the class-valid
+// matches (sum_m w[c_m] (logsumexp(x_m) - x_m[c_m]) / sum_m w[c_m]), focal_gamma > 0 = FocalLoss(with_logits=True) objectness
+// (mean of alpha (1 - exp(-bce))^gamma bce, :9-37).
 //   ciou_m   = CIoU(pred[b,g,a, -2:], target cw_m)          1-D segments dressed as boxes of height 10 (:193-228)
 //   box      = mean_m (1 - ciou_m)
 //   t_conf   = zeros[B,G,A]; t_conf[b,g,a] = ciou_m          duplicates: the LAST match wins (index_put_ on CPU; Q12)
@@ -16,7 +19,7 @@ namespace yad {
 
 constexpr int LS_THREADS = 256;
 // accumulator slots (double)
-enum { ACC_BOX = 0, ACC_CIOU, ACC_CONF, ACC_CLS, ACC_POS, ACC_NEG, ACC_NNEG, ACC_NVALID, ACC_N };
+enum { ACC_BOX = 0, ACC_CIOU, ACC_CONF, ACC_CLS, ACC_POS, ACC_NEG, ACC_NNEG, ACC_NVALID, ACC_WSUM, ACC_N };
 
 struct CiouOut {
   float ciou;       // clipped at 0
@@ -89,11 +92,11 @@ __device__ __forceinline__ void block_add(double v, double* dst, double* scratch
 __global__ void __launch_bounds__(LS_THREADS)
 loss_match_kernel(const float* __restrict__ pred, int G, int A, int E, const int64_t* __restrict__ bi,
                   const int64_t* __restrict__ gi, const int64_t* __restrict__ ai, const int64_t* __restrict__ cl,
-                  const float* __restrict__ cw, int M, int64_t ignore_index, int32_t* __restrict__ owner,
-                  float* __restrict__ ciou_ws, double* __restrict__ acc) {
+                  const float* __restrict__ cw, int M, int64_t ignore_index, int nc, const float* __restrict__ class_weights,
+                  int32_t* __restrict__ owner, float* __restrict__ ciou_ws, double* __restrict__ acc) {
   __shared__ double scratch[LS_THREADS / 32];
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  double nvalid = 0.0;
+  double nvalid = 0.0, wsum = 0.0;
   if (m < M) {
     const int64_t cell = (bi[m] * G + gi[m]) * A + ai[m];
     const float* p = pred + cell * E;
@@ -101,15 +104,17 @@ loss_match_kernel(const float* __restrict__ pred, int G, int A, int E, const int
     ciou_ws[m] = o.ciou;
     atomicMax(owner + cell, m);
     nvalid = cl[m] != ignore_index ? 1.0 : 0.0;
+    if (cl[m] != ignore_index) wsum = (class_weights != nullptr && cl[m] >= 0 && cl[m] < nc) ? (double)class_weights[cl[m]] : 1.0;
   }
   block_add(nvalid, acc + ACC_NVALID, scratch);
+  block_add(wsum, acc + ACC_WSUM, scratch);       // CrossEntropyLoss(weight) divides by the sum of the targets' weights
 }
 
 // pass 2 over cells: objectness BCE vs t_conf, its gradient; zero the other gradient columns
 __global__ void __launch_bounds__(LS_THREADS)
 loss_cell_kernel(const float* __restrict__ pred, int64_t N, int E, const int32_t* __restrict__ owner,
-                 const float* __restrict__ ciou_ws, float conf_scale /* conf_w * scale weight */, float* __restrict__ grad,
-                 double* __restrict__ acc) {
+                 const float* __restrict__ ciou_ws, float conf_scale /* conf_w * scale weight */, float focal_alpha,
+                 float focal_gamma /* <= 0: plain BCE */, float* __restrict__ grad, double* __restrict__ acc) {
   __shared__ double scratch[LS_THREADS / 32];
   double s_conf = 0.0, s_neg = 0.0, n_neg = 0.0;
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x) {
@@ -117,13 +122,22 @@ loss_cell_kernel(const float* __restrict__ pred, int64_t N, int E, const int32_t
     const float t = o >= 0 ? ciou_ws[o] : 0.0f;
     const float x = pred[c * E];
     const float sg = sigmoidf_(x);
-    s_conf += (double)bce_logits(x, t);
+    const float bce = bce_logits(x, t);
+    float dl = 1.0f;                          // d loss_cell / d bce
+    if (focal_gamma > 0.0f) {                 // FocalLoss: f = alpha u^gamma bce with u = 1 - exp(-bce)
+      const float pt = expf(-bce), u = 1.0f - pt;
+      const float ug = u > 0.0f ? powf(u, focal_gamma) : 0.0f;
+      s_conf += (double)(focal_alpha * ug * bce);
+      dl = u > 0.0f ? focal_alpha * (focal_gamma * (ug / u) * pt * bce + ug) : 0.0f;
+    } else {
+      s_conf += (double)bce;
+    }
     if (t == 0.0f) {
       s_neg += (double)sg;
       n_neg += 1.0;
     }
     float* g = grad + c * E;
-    g[0] = conf_scale * (sg - t) / (float)N;
+    g[0] = conf_scale * dl * (sg - t) / (float)N;
     for (int j = 1; j < E; ++j) g[j] = 0.0f;
   }
   block_add(s_conf, acc + ACC_CONF, scratch);
@@ -136,9 +150,9 @@ loss_cell_kernel(const float* __restrict__ pred, int64_t N, int E, const int32_t
 __global__ void __launch_bounds__(LS_THREADS)
 loss_match_grad_kernel(const float* __restrict__ pred, int G, int A, int E, int nc, const int64_t* __restrict__ bi,
                        const int64_t* __restrict__ gi, const int64_t* __restrict__ ai, const int64_t* __restrict__ cl,
-                       const float* __restrict__ cw, int M, int64_t ignore_index, float box_w, float class_w, float cn,
-                       float* __restrict__ grad, int32_t* __restrict__ confusion /* [nc][nc] target x predicted */,
-                       double* __restrict__ acc) {
+                       const float* __restrict__ cw, int M, int64_t ignore_index, float box_w, float class_w, float cn, int cls_mode,
+                       const float* __restrict__ class_weights, float* __restrict__ grad,
+                       int32_t* __restrict__ confusion /* [nc][nc] target x predicted */, double* __restrict__ acc) {
   __shared__ double scratch[LS_THREADS / 32];
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   double s_box = 0.0, s_ciou = 0.0, s_cls = 0.0, s_pos = 0.0;
@@ -156,18 +170,30 @@ loss_match_grad_kernel(const float* __restrict__ pred, int G, int A, int E, int 
     const int64_t c = cl[m];
     if (c != ignore_index) {
       const double nvalid = acc[ACC_NVALID];          // complete: written by the first pass (previous launch)
-      const float gs = class_w / (float)(nvalid * nc);
       int best = 0;
       float bestv = p[1];
-      for (int j = 0; j < nc; ++j) {
-        const float x = p[1 + j];
-        const float t = (j == (int)c) ? 1.0f - cn : cn;
-        s_cls += (double)bce_logits(x, t);
-        atomicAdd(g + 1 + j, gs * (sigmoidf_(x) - t));
-        if (x > bestv) {
-          bestv = x;
+      for (int j = 1; j < nc; ++j) {
+        if (p[1 + j] > bestv) {
+          bestv = p[1 + j];
           best = j;
         }
+      }
+      if (cls_mode == 0) {                             // BCEWithLogits against the smoothed one-hot row, mean over valid x nc
+        const float gs = class_w / (float)(nvalid * nc);
+        for (int j = 0; j < nc; ++j) {
+          const float x = p[1 + j];
+          const float t = (j == (int)c) ? 1.0f - cn : cn;
+          s_cls += (double)bce_logits(x, t);
+          atomicAdd(g + 1 + j, gs * (sigmoidf_(x) - t));
+        }
+      } else if (c >= 0 && c < nc) {                   // CrossEntropyLoss: w_c (logsumexp(x) - x_c) / sum of the targets' weights
+        const float wc = class_weights != nullptr ? class_weights[c] : 1.0f;
+        float se = 0.0f;
+        for (int j = 0; j < nc; ++j) se += expf(p[1 + j] - bestv);
+        const float lse = bestv + logf(se);
+        s_cls += (double)(wc * (lse - p[1 + c]));
+        const float gs = class_w * wc / (float)acc[ACC_WSUM];
+        for (int j = 0; j < nc; ++j) atomicAdd(g + 1 + j, gs * (expf(p[1 + j] - lse) - (j == (int)c ? 1.0f : 0.0f)));
       }
       if (c >= 0 && c < nc) atomicAdd(confusion + (int)c * nc + best, 1);
     }
@@ -180,11 +206,14 @@ loss_match_grad_kernel(const float* __restrict__ pred, int G, int A, int E, int 
 
 }  // namespace yad
 
-extern "C" int yad_loss_scale(const float* pred, int64_t B, int32_t G, int32_t A, int32_t nc, const int64_t* bi, const int64_t* gi,
-                              const int64_t* ai, const int64_t* cl, const float* cw, int32_t M, float box_w, float conf_scale,
-                              float class_w, float label_smoothing, int64_t ignore_index, int32_t* owner_ws, float* ciou_ws,
-                              int32_t* confusion, double* acc, float* grad, yad_stream_t stream) {
+extern "C" int yad_loss_scale_ex(const float* pred, int64_t B, int32_t G, int32_t A, int32_t nc, const int64_t* bi, const int64_t* gi,
+                                 const int64_t* ai, const int64_t* cl, const float* cw, int32_t M, float box_w, float conf_scale,
+                                 float class_w, float label_smoothing, int64_t ignore_index, int32_t cls_mode,
+                                 const float* class_weights, float focal_alpha, float focal_gamma, int32_t* owner_ws, float* ciou_ws,
+                                 int32_t* confusion, double* acc, float* grad, yad_stream_t stream) {
   using namespace yad;
+  YAD_CHECK_ARG(cls_mode == 0 || cls_mode == 1, "yad_loss_scale_ex: cls_mode must be 0 (multi-label BCE) or 1 (cross entropy)");
+  YAD_CHECK_ARG(class_weights == nullptr || cls_mode == 1, "yad_loss_scale_ex: class weights belong to the cross-entropy mode");
   YAD_CHECK_ARG(pred && owner_ws && acc && grad && confusion, "yad_loss_scale: null pointer");
   YAD_CHECK_ARG(B >= 1 && G >= 1 && A >= 1 && nc >= 1 && M >= 0, "yad_loss_scale: bad shape");
   YAD_CHECK_ARG(M == 0 || (bi && gi && ai && cl && cw && ciou_ws), "yad_loss_scale: null match arrays");
@@ -197,18 +226,26 @@ extern "C" int yad_loss_scale(const float* pred, int64_t B, int32_t G, int32_t A
   YAD_CUDA(cudaMemsetAsync(confusion, 0, (size_t)nc * nc * sizeof(int32_t), st));
   const unsigned mb = (unsigned)((M + LS_THREADS - 1) / LS_THREADS);
   if (M > 0) {
-    loss_match_kernel<<<mb, LS_THREADS, 0, st>>>(pred, G, A, E, bi, gi, ai, cl, cw, M, ignore_index, owner_ws, ciou_ws, acc);
+    loss_match_kernel<<<mb, LS_THREADS, 0, st>>>(pred, G, A, E, bi, gi, ai, cl, cw, M, ignore_index, nc, class_weights, owner_ws, ciou_ws, acc);
     YAD_LAUNCH_CHECK();
   }
   int64_t cb = (N + LS_THREADS - 1) / LS_THREADS;
   const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 8;
   if (cb > cap) cb = cap;
-  loss_cell_kernel<<<(unsigned)cb, LS_THREADS, 0, st>>>(pred, N, E, owner_ws, ciou_ws, conf_scale, grad, acc);
+  loss_cell_kernel<<<(unsigned)cb, LS_THREADS, 0, st>>>(pred, N, E, owner_ws, ciou_ws, conf_scale, focal_alpha, focal_gamma, grad, acc);
   YAD_LAUNCH_CHECK();
   if (M > 0) {
     loss_match_grad_kernel<<<mb, LS_THREADS, 0, st>>>(pred, G, A, E, nc, bi, gi, ai, cl, cw, M, ignore_index, box_w, class_w,
-                                                     0.5f * label_smoothing, grad, confusion, acc);
+                                                     0.5f * label_smoothing, cls_mode, class_weights, grad, confusion, acc);
     YAD_LAUNCH_CHECK();
   }
   return YAD_OK;
+}
+
+extern "C" int yad_loss_scale(const float* pred, int64_t B, int32_t G, int32_t A, int32_t nc, const int64_t* bi, const int64_t* gi,
+                              const int64_t* ai, const int64_t* cl, const float* cw, int32_t M, float box_w, float conf_scale,
+                              float class_w, float label_smoothing, int64_t ignore_index, int32_t* owner_ws, float* ciou_ws,
+                              int32_t* confusion, double* acc, float* grad, yad_stream_t stream) {
+  return yad_loss_scale_ex(pred, B, G, A, nc, bi, gi, ai, cl, cw, M, box_w, conf_scale, class_w, label_smoothing, ignore_index, 0, nullptr,
+                           0.0f, 0.0f, owner_ws, ciou_ws, confusion, acc, grad, stream);
 }

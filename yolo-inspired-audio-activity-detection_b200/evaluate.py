@@ -7,10 +7,44 @@ from __future__ import annotations
 from datetime import timedelta
 from typing import Dict, List, Tuple
 
+import ctypes as C
+import math
+
 import numpy as np
 import torch
 
+from . import _lib
+from .frontend_consts import sinc_resample_kernel
 from .hostpipe import run_host_batch
+from .postprocess import process_model_outputs
+
+_RS_CACHE: Dict[Tuple[int, int, str], Tuple[torch.Tensor, int, int, int]] = {}
+
+
+def resample_to_model_rate(x: torch.Tensor, orig_rate: int, new_rate: int) -> torch.Tensor:
+    """``torchaudio.transforms.Resample(orig_freq, new_freq)`` (defaults: Hann-windowed sinc, lowpass_filter_width 6, rolloff
+    0.99) of a CUDA batch ``x [B, 1, L]`` (fp32 or int16 PCM) -> fp32 ``[B, 1, ceil(new * L / orig)]`` on the sm_100a kernel
+    ``yad_resample_sinc`` (reference call site: inference.py:152-159)."""
+    if not x.is_cuda:
+        raise RuntimeError("resample_to_model_rate needs a CUDA tensor (no CPU fallback)")
+    if x.dtype not in (torch.float32, torch.int16):
+        raise ValueError("resample_to_model_rate takes fp32 or int16 PCM")
+    dev = x.device
+    key = (int(orig_rate), int(new_rate), str(dev))
+    if key not in _RS_CACHE:
+        k, width, o, n = sinc_resample_kernel(int(orig_rate), int(new_rate))
+        _RS_CACHE[key] = (k[:, 0, :].contiguous().to(dev), width, o, n)
+    k, width, o, n = _RS_CACHE[key]
+    B, _, L = x.shape
+    Lout = int(math.ceil(n * L / o))
+    x = x.contiguous()
+    out = torch.empty((B, 1, Lout), device=dev, dtype=torch.float32)
+    lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        rc = lib.yad_resample_sinc(x.data_ptr(), 1 if x.dtype == torch.int16 else 0, B, L, o, n, width, k.data_ptr(), out.data_ptr(),
+                                   Lout, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc, "resample_sinc")
+    return out
 
 
 def evaluate_waveform(model, waveform: torch.Tensor, og_sample_rate: int, sample_duration: float, batch_size: int,
@@ -24,9 +58,7 @@ def evaluate_waveform(model, waveform: torch.Tensor, og_sample_rate: int, sample
     (``batch_idxs += batch_idxs_list[-1][-1]``, inference.py:176-177), not the clip count; a batch without any segment above
     ``conf_threshold`` raises ``ValueError`` (the reference's ``torch.cat`` of an empty list)."""
     in_rate = int(model.config["sample_rate"])
-    if int(og_sample_rate) != in_rate:
-        raise NotImplementedError(f"yad_b200.evaluate_waveform: the file is at {og_sample_rate} Hz, the model expects {in_rate} Hz; "
-                                  "the extra torchaudio Resample of inference.py:152-159 is not built")
+    file_rate = int(og_sample_rate) != in_rate      # the extra Resample of inference.py:152-159 (yad_resample_sinc)
     if waveform.is_cuda:
         raise ValueError("evaluate_waveform takes the decoded waveform on the host")
     wav = waveform if waveform.ndim == 2 else waveform.unsqueeze(0)
@@ -52,8 +84,16 @@ def evaluate_waveform(model, waveform: torch.Tensor, og_sample_rate: int, sample
         if len(idx2class_map) < model.num_classes:
             raise RuntimeError("model output does not match idx2class mapping")
         xp = x if x.is_pinned() else x.contiguous().pin_memory()
-        segments, batch_idxs = run_host_batch(model, xp, iou_threshold, conf_threshold, chunk=chunk, sample_duration=sample_duration,
-                                              return_start_end=True)
+        if file_rate:
+            dev = next(model.parameters()).device
+            with torch.no_grad():
+                xr = resample_to_model_rate(xp.to(dev, non_blocking=True), int(og_sample_rate), in_rate)
+                out = model(xr, combine_scales=True)
+            segments, batch_idxs = process_model_outputs(out, iou_threshold, conf_threshold, sample_duration, True)   # raises if empty
+            segments, batch_idxs = segments.cpu(), batch_idxs.cpu()
+        else:
+            segments, batch_idxs = run_host_batch(model, xp, iou_threshold, conf_threshold, chunk=chunk, sample_duration=sample_duration,
+                                                  return_start_end=True)
         if segments is None:
             raise ValueError("no segment passed conf_threshold in this batch (the reference raises here too: torch.cat of an empty list)")
         if len(batch_idxs_list) > 0:

@@ -133,8 +133,9 @@ class _DetectionLossFn(torch.autograd.Function):
 class AudioDetectionLoss(torch.nn.Module):
     """Drop-in for the reference ``AudioDetectionLoss`` (modules/_loss.py:39-191) on sm_100a kernels: same constructor,
     ``forward((sm, md, lg), targets) -> (loss, metrics dict)`` with the same 10 metric keys; ``loss`` is differentiable
-    with respect to the three prediction tensors (CUDA, fp32).  Built: the default train_config (``multi_label=True``,
-    no focal loss); the other branches raise NotImplementedError."""
+    with respect to the three prediction tensors (CUDA, fp32).  All branches of the reference constructor (:74-81):
+    ``multi_label`` BCE class loss with label smoothing (the train_config default) or ``CrossEntropyLoss(weight=class_weights)``,
+    BCEWithLogits objectness or ``FocalLoss(alpha, gamma)`` (yad_loss_scale_ex)."""
 
     SCALE_W = (4.0, 2.0, 1.0)
 
@@ -142,10 +143,9 @@ class AudioDetectionLoss(torch.nn.Module):
                  class_w=1.0, multi_label=False, class_weights=None, label_smoothing=0, batch_scale_loss=False, alpha=None,
                  gamma=None, ignore_index=-100):
         super().__init__()
-        if not multi_label:
-            raise NotImplementedError("yad_b200.AudioDetectionLoss: only multi_label=True (the reference train_config) is built")
-        if alpha and gamma:
-            raise NotImplementedError("yad_b200.AudioDetectionLoss: the focal-loss objectness variant is not built")
+        self.multi_label = bool(multi_label)
+        self.focal = (float(alpha), float(gamma)) if (alpha and gamma) else (0.0, 0.0)      # same truthiness test as the reference
+        self.class_weights = None if (class_weights is None or multi_label) else torch.as_tensor(class_weights, dtype=torch.float32)
         self.anchors_dict, self.num_classes = anchors_dict, int(num_classes)
         self.anchor_t, self.edge_t, self.sample_duration = anchor_t, edge_t, sample_duration
         self.box_w, self.conf_w, self.class_w = float(box_w), float(conf_w), float(class_w)
@@ -159,7 +159,10 @@ class AudioDetectionLoss(torch.nn.Module):
         lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
         nc = self.num_classes
         bscale = float(preds[-1].shape[0]) if self.batch_scale_loss else 1.0
-        accs = torch.zeros((3, 8), device=dev, dtype=torch.float64)
+        accs = torch.zeros((3, 16), device=dev, dtype=torch.float64)
+        cwt = None if self.class_weights is None else self.class_weights.to(dev).contiguous()
+        if cwt is not None and cwt.numel() != nc:
+            raise ValueError(f"class_weights has {cwt.numel()} entries, expected {nc}")
         confs = torch.zeros((3, nc, nc), device=dev, dtype=torch.int32)
         grads, Ms, Ns = [], [], []
         with torch.cuda.device(dev):
@@ -174,15 +177,16 @@ class AudioDetectionLoss(torch.nn.Module):
                 owner = torch.empty(B * G * A, device=dev, dtype=torch.int32)
                 ciou = torch.empty(max(M, 1), device=dev, dtype=torch.float32)
                 g = torch.empty_like(p)
-                rc = lib.yad_loss_scale(p.data_ptr(), B, G, A, nc, _lib.ptr(bi), _lib.ptr(gi), _lib.ptr(ai), _lib.ptr(cl), _lib.ptr(cw),
-                                        M, self.box_w * bscale, self.conf_w * self.SCALE_W[s] * bscale, self.class_w * bscale,
-                                        self.label_smoothing, self.ignore_index, owner.data_ptr(), ciou.data_ptr(),
-                                        confs[s].data_ptr(), accs[s].data_ptr(), g.data_ptr(), _stream(dev))
+                rc = lib.yad_loss_scale_ex(p.data_ptr(), B, G, A, nc, _lib.ptr(bi), _lib.ptr(gi), _lib.ptr(ai), _lib.ptr(cl), _lib.ptr(cw),
+                                           M, self.box_w * bscale, self.conf_w * self.SCALE_W[s] * bscale, self.class_w * bscale,
+                                           self.label_smoothing, self.ignore_index, 0 if self.multi_label else 1, _lib.ptr(cwt),
+                                           self.focal[0], self.focal[1], owner.data_ptr(), ciou.data_ptr(),
+                                           confs[s].data_ptr(), accs[s].data_ptr(), g.data_ptr(), _stream(dev))
                 _lib.check(rc, f"loss_scale {name}")
                 grads.append(g)
                 Ms.append(M)
                 Ns.append(B * G * A)
-        a = accs.cpu().numpy()            # one 192-byte read; the reference syncs on every .item() too
+        a = accs.cpu().numpy()            # one 384-byte read; the reference syncs on every .item() too
         cm = confs.cpu().numpy()
         nan = float("nan")
         lbox = lconf = lcls = 0.0
@@ -191,7 +195,10 @@ class AudioDetectionLoss(torch.nn.Module):
             M, N, nvalid = Ms[s], Ns[s], a[s, 7]
             box = a[s, 0] / M if M else nan
             conf = a[s, 2] / N
-            cls = a[s, 3] / (nvalid * nc) if nvalid else nan
+            if self.multi_label:
+                cls = a[s, 3] / (nvalid * nc) if nvalid else nan
+            else:            # CrossEntropyLoss: weighted mean; no class-valid match (or zero weight sum) -> nan, like torch
+                cls = a[s, 3] / a[s, 8] if (nvalid and a[s, 8]) else nan
             lbox += 0.0 if box != box else box          # handle_nan (modules/_loss.py:178)
             lconf += self.SCALE_W[s] * conf
             lcls += 0.0 if cls != cls else cls
