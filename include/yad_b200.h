@@ -170,6 +170,16 @@ int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, int64_t B, i
 int yad_conv_stem_fused_fixup(const float* x_nchw, int64_t B, int32_t H, int32_t W, const float* w_var, const float* bias,
                               const int32_t* cols, const int32_t* col_var, int32_t n_cols, void* out_flat_bf16,
                               int32_t Hp, int32_t Wp, yad_stream_t stream);
+/* The overlapped pair: yad_conv_stem_fused_skip leaves output columns [0, skip_lo) and [Wo - skip_hi, Wo) unwritten and
+ * yad_conv_stem_fused_fixup_bf16 computes exactly those columns (cols must be that set) from the SAME padded bf16 input the
+ * tensor-core kernel reads (20 KB of shared memory: its CTAs fit next to the resident stem CTA).  The two write disjoint cells
+ * and depend only on the frontend's output, so they may run on different streams at the same time. */
+int yad_conv_stem_fused_skip(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W, const void* w_classes,
+                             const float* bias, void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior,
+                             int32_t skip_lo, int32_t skip_hi, yad_stream_t stream);
+int yad_conv_stem_fused_fixup_bf16(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W, const float* w_var,
+                                   const float* bias, const int32_t* cols, const int32_t* col_var, int32_t n_cols,
+                                   void* out_flat_bf16, int32_t Hp, int32_t Wp, yad_stream_t stream);
 
 /* CUDA-core implicit GEMM (fp32 accumulate; in/out dtype f32 or bf16).
  * weight [kh][kw][Cin][Cout_pad] in `dtype`; bias [Cout] f32; residual/out NHWC. */

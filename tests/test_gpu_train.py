@@ -271,6 +271,47 @@ def test_train_network_forward_backward_vs_oracle_and_reference(gold, ref_state_
     print("worst relative gradient error:", worst)
 
 
+def test_train_bottleneck_backbone_vs_oracle(variant_state_dict, cuda_dev):
+    """``resnet_config.block: Bottleneck`` in train() mode (torchvision resnet.py:143-163 via modules/_backbone.py:128-138):
+    predictions, loss, every parameter gradient and the BatchNorm running statistics against the oracle's autograd in fp64
+    (same tolerances as the BasicBlock network: < 3e-2 relative L2 everywhere, tight on the neck)."""
+    import train_helpers as TH
+    from yad_b200.train_engine import run_train_forward
+    sd_v, cfg = variant_state_dict("bottleneck")
+    x, tg = TH.train_inputs()
+    preds_o, loss_o, grads_o, sd_o, xs = TH.oracle_train_step(sd_v, x, tg, dtype=torch.float64)
+    cfg = dict(cfg, dropout=0.0)
+    m = yad_b200.AudioDetectionNetwork(2, config=cfg, train_dtype="f32")
+    m.load_state_dict(sd_v)
+    m = m.to(cuda_dev).train()
+    L_res = -(-320 * x.shape[-1] // 441)
+    with torch.enable_grad():
+        preds = run_train_forward(m, m._train_engine(), xs.to(cuda_dev).contiguous(), xs.shape[-1], L_res)
+        loss, _ = _loss_fn()(preds, tg.to(cuda_dev))
+        loss.backward()
+    torch.cuda.synchronize()
+    for i in range(3):
+        np.testing.assert_allclose(preds[i].detach().cpu().numpy(), preds_o[i].numpy(), atol=2e-3, rtol=2e-4)
+    np.testing.assert_allclose(float(loss), float(loss_o), rtol=1e-4)
+    params = dict(m.named_parameters())
+    assert sorted(params) == sorted(grads_o)
+    worst = ("", 0.0)
+    for k, p in params.items():
+        assert p.grad is not None, k
+        go = grads_o[k]
+        if float(go.norm()) < 1e-9:
+            assert float(p.grad.double().norm()) < 1e-4, k
+            continue
+        r = _rel_l2(p.grad.cpu(), go)
+        worst = max(worst, (k, r), key=lambda t: t[1])
+        assert r < (2e-3 if k.startswith("multiscale_module.") else 3e-2), (k, r)
+    sd = m.state_dict()
+    for k in [k[:-13] for k in sd_o if k.endswith(".running_mean")]:
+        np.testing.assert_allclose(sd[k + ".running_mean"].cpu().numpy(), sd_o[k + ".running_mean"].float().numpy(), atol=5e-6, rtol=1e-4)
+        np.testing.assert_allclose(sd[k + ".running_var"].cpu().numpy(), sd_o[k + ".running_var"].float().numpy(), rtol=1e-4, atol=1e-7)
+    print("worst relative gradient error:", worst)
+
+
 def test_train_forward_end_to_end_and_eval_after(gold, ref_state_dict, cuda_dev):
     """model.train(); model(x) from PCM through the GPU frontend: loss within 2e-3 of the reference's; no_grad works;
     eval() afterwards uses the updated running statistics (engine re-packs)."""

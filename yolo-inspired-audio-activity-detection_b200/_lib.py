@@ -67,6 +67,8 @@ SIGNATURES = {
     "yad_sppf_pools": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_conv_stem_fused": [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _i32, _i32, _p],
     "yad_frontend_finish_bf16": [_p, _i64, _i64, _p, _f32, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p],
+    "yad_conv_stem_fused_skip": [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p],
+    "yad_conv_stem_fused_fixup_bf16": [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _i32, _p],
     "yad_conv_stem_fused_fixup": [_p, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _i32, _p],
     "yad_kmeans1d_lloyd": [_p, _i64, _p, _i32, _i32, _f64, _p, _p, _p, _p],
     "yad_maxpool_h": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],

@@ -49,6 +49,8 @@ struct StemFusedParams {
   int32_t cta_first[5];          // CTA ranges of the 4 row classes: class c owns blocks [cta_first[c], cta_first[c+1])
   int32_t row_first[4], row_cnt[4];
   uint32_t idesc;
+  int32_t skip_lo, skip_hi;      // output columns [0, skip_lo) and [Wo - skip_hi, Wo) are NOT written: the fix-up kernel owns them
+                                 // and may then run concurrently (another stream) instead of after this kernel
 };
 
 // 1-D bulk copy global -> shared (TMA unit), completion counted on an mbarrier
@@ -146,7 +148,7 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
     // (3) epilogue: bias + ReLU, bf16, flat halo layout; thread = (pixel r, 32-channel half); the rows of a class are adjacent
     //     in memory (h fastest), so a thread's stores of consecutive rows are contiguous
     const int wo = wo0 + r;
-    const bool ok = wo < p.Wo;
+    const bool ok = wo < p.Wo - p.skip_hi && wo >= p.skip_lo;
     for (int j = 0; j < nrow; ++j) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + half * 32), v);
@@ -239,6 +241,64 @@ stem_fixup_kernel(const float* __restrict__ x, const StemFixupParams p, const fl
   }
 }
 
+// The same fix-up reading the channel-interleaved bf16 copy of x_spectral that the tensor-core kernel reads (one 4-byte word per
+// pixel, 9-word zero left margin: window column 4 wo - 9 + dw is word 4 wo + dw, never out of range): 20 KB of shared memory
+// instead of 40, so that its CTAs fit next to the resident stem CTA (192 KB) and the two kernels overlap when launched on
+// different streams (the stem kernel then skips these columns: skip_lo / skip_hi).
+__global__ void __launch_bounds__(FX_THREADS, 2)
+stem_fixup_bf16_kernel(const uint32_t* __restrict__ xb, int64_t xpitch, const StemFixupParams p, const float* __restrict__ w_var,
+                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) uint32_t s_xw[32][SF_KD + 1][FX_CLIPS];        // clip fastest: the 4 clips of a thread are one 16-byte load
+  const int ci = blockIdx.x, b0 = blockIdx.y * FX_CLIPS;
+  const int nb = min(FX_CLIPS, p.B - b0);
+  const int wo = p.col[ci], var = p.var[ci];
+  const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  for (int i = tid; i < FX_CLIPS * 32 * SF_KD; i += blockDim.x) {
+    const int dw = i % SF_KD, hi = (i / SF_KD) % 32, bb = i / (SF_KD * 32);
+    s_xw[hi][dw][bb] = (bb < nb && hi < p.H) ? __ldg(xb + ((int64_t)(b0 + bb) * p.H + hi) * xpitch + 4 * wo + dw) : 0u;
+  }
+  __syncthreads();
+  const int q4 = (tid & 15) * 4, half = (tid >> 4) & 1, ho = tid >> 5;
+  if (ho >= p.Ho) return;
+  const float* wv = w_var + ((size_t)(var * 4 + p.row_class[ho]) * SF_KD * SF_KD * 2) * 64 + q4;
+  float acc[4][4];
+#pragma unroll
+  for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[bb][e] = bias[q4 + e];
+  for (int dh = 0; dh < SF_KD; ++dh) {
+    const int hi = 4 * ho - 9 + dh;
+    if (hi < 0 || hi >= p.H) continue;
+    for (int dw = 0; dw < SF_KD; ++dw) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(&s_xw[hi][dw][half * 4]);
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wv + ((dh * SF_KD + dw) * 2 + c) * 64));
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const float xs = __uint_as_float(c == 0 ? (xw[bb] << 16) : (xw[bb] & 0xffff0000u));
+          acc[bb][0] = fmaf(xs, w.x, acc[bb][0]);
+          acc[bb][1] = fmaf(xs, w.y, acc[bb][1]);
+          acc[bb][2] = fmaf(xs, w.z, acc[bb][2]);
+          acc[bb][3] = fmaf(xs, w.w, acc[bb][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int bb = 0; bb < 4; ++bb) {
+    const int bl = half * 4 + bb;
+    if (bl >= nb) continue;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(acc[bb][0], 0.0f), fmaxf(acc[bb][1], 0.0f));
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(acc[bb][2], 0.0f), fmaxf(acc[bb][3], 0.0f));
+    uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(out + (((int64_t)(b0 + bl) * p.Wp + wo) * p.Hp + ho) * 64 + q4) = o;
+  }
+}
+
 static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + 64; }
 
 int init_conv_stem_fused_attrs() {
@@ -253,9 +313,9 @@ int init_conv_stem_fused_attrs() {
 
 }  // namespace yad
 
-extern "C" int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W, const void* w_classes,
-                                   const float* bias, void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior,
-                                   yad_stream_t stream) {
+static int conv_stem_fused_impl(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W, const void* w_classes,
+                                const float* bias, void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior, int32_t skip_lo,
+                                int32_t skip_hi, yad_stream_t stream) {
   using namespace yad;
   YAD_CHECK_ARG(x_bf16_padded && w_classes && bias && out_flat_bf16, "yad_conv_stem_fused: null pointer");
   YAD_CHECK_ARG(reinterpret_cast<uintptr_t>(x_bf16_padded) % 16 == 0 && x_pitch % 4 == 0, "yad_conv_stem_fused: input rows must be 16-byte aligned");
@@ -294,8 +354,54 @@ extern "C" int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, i
   p.cta_first[3] = n_int + n1 + n2;
   p.cta_first[4] = n_int + n1 + n2 + n3;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  YAD_CHECK_ARG(skip_lo >= 0 && skip_hi >= 0 && skip_lo + skip_hi <= p.Wo, "yad_conv_stem_fused: bad skipped column counts");
+  p.skip_lo = skip_lo;
+  p.skip_hi = skip_hi;
   YAD_CUDA(launch_pdl(conv_stem_fused_kernel, dim3((unsigned)p.cta_first[4]), dim3(SF_THREADS), stem_fused_smem_bytes(), (cudaStream_t)stream,
                       reinterpret_cast<const uint32_t*>(x_bf16_padded), p, reinterpret_cast<const uint4*>(w_classes), bias,
+                      reinterpret_cast<__nv_bfloat16*>(out_flat_bf16)));
+  return YAD_OK;
+}
+
+extern "C" int yad_conv_stem_fused(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W, const void* w_classes,
+                                   const float* bias, void* out_flat_bf16, int32_t Hp, int32_t Wp, int32_t n_cta_interior,
+                                   yad_stream_t stream) {
+  return conv_stem_fused_impl(x_bf16_padded, x_pitch, B, H, W, w_classes, bias, out_flat_bf16, Hp, Wp, n_cta_interior, 0, 0, stream);
+}
+
+extern "C" int yad_conv_stem_fused_skip(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W,
+                                        const void* w_classes, const float* bias, void* out_flat_bf16, int32_t Hp, int32_t Wp,
+                                        int32_t n_cta_interior, int32_t skip_lo, int32_t skip_hi, yad_stream_t stream) {
+  return conv_stem_fused_impl(x_bf16_padded, x_pitch, B, H, W, w_classes, bias, out_flat_bf16, Hp, Wp, n_cta_interior, skip_lo, skip_hi,
+                              stream);
+}
+
+extern "C" int yad_conv_stem_fused_fixup_bf16(const void* x_bf16_padded, int64_t x_pitch, int64_t B, int32_t H, int32_t W,
+                                              const float* w_var, const float* bias, const int32_t* cols, const int32_t* col_var,
+                                              int32_t n_cols, void* out_flat_bf16, int32_t Hp, int32_t Wp, yad_stream_t stream) {
+  using namespace yad;
+  YAD_CHECK_ARG(x_bf16_padded && w_var && bias && out_flat_bf16 && (n_cols == 0 || (cols && col_var)), "yad_conv_stem_fused_fixup_bf16: null pointer");
+  YAD_CHECK_ARG(H == 32 && W >= 8 && B >= 0 && B <= 65535 * (int64_t)FX_CLIPS && n_cols >= 0 && n_cols <= 8,
+                "yad_conv_stem_fused_fixup_bf16: bad arguments");
+  if (B == 0 || n_cols == 0) return YAD_OK;
+  const int Wo = (((W - 1) / 2 + 1) - 1) / 2 + 1;
+  StemFixupParams p;
+  p.B = (int)B;
+  p.H = H;
+  p.W = W;
+  p.Ho = 8;
+  p.Hp = Hp;
+  p.Wp = Wp;
+  p.n_cols = n_cols;
+  for (int i = 0; i < 8; ++i) {
+    p.col[i] = i < n_cols ? cols[i] : 0, p.var[i] = i < n_cols ? col_var[i] : 0;
+    YAD_CHECK_ARG(i >= n_cols || (cols[i] >= 0 && cols[i] < Wo && 4 * (int64_t)cols[i] + SF_KD <= x_pitch),
+                  "yad_conv_stem_fused_fixup_bf16: column %d outside the image / the padded row", i < n_cols ? cols[i] : 0);
+  }
+  const int rcls[8] = {1, 2, 0, 0, 0, 0, 0, 3};
+  for (int i = 0; i < 8; ++i) p.row_class[i] = rcls[i];
+  YAD_CUDA(launch_pdl(stem_fixup_bf16_kernel, dim3((unsigned)n_cols, (unsigned)((B + FX_CLIPS - 1) / FX_CLIPS)), dim3(FX_THREADS), 0,
+                      (cudaStream_t)stream, reinterpret_cast<const uint32_t*>(x_bf16_padded), x_pitch, p, w_var, bias,
                       reinterpret_cast<__nv_bfloat16*>(out_flat_bf16)));
   return YAD_OK;
 }

@@ -75,6 +75,11 @@ class _Conv:
                 self.w = self.w.to(torch.bfloat16)
 
 
+class _SideHandle(C.c_void_p):
+    """Stream argument of a call that runs on the engine's side stream: left alone when a recorded plan is replayed (the
+    main-stream handles are patched to the caller's current stream)."""
+
+
 class _RecLib:
     """The ctypes library seen through a thread-local recorder: while ``tls.rec`` is a list, every C-ABI call is appended to
     it as (function, argument list, name).  ``InferenceEngine.run`` records the first forward of a (batch, length) plan and
@@ -114,6 +119,7 @@ class InferenceEngine:
         self.dual_ds = os.environ.get("YAD_DUAL_DS", "1") != "0"
         self.s2d_route = os.environ.get("YAD_S2D", "1") != "0"
         self.fold_ds = os.environ.get("YAD_FOLD_DS", "1") != "0"
+        self.stem_overlap = os.environ.get("YAD_STEM_OVERLAP", "1") != "0"
         self._threads_seen = set()
         self.tdtype = torch.bfloat16 if self.dtype == BF16 else torch.float32
         self.cfg = model.config
@@ -347,6 +353,32 @@ class InferenceEngine:
     # ------------------------------------------------------------------ execution helpers
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    # ---- a second stream for work that is independent of the main chain (the stem's border-column fix-up): fork / join are
+    #      recorded into the plan as pseudo-calls, so a replay - and a CUDA graph captured from it - keeps the two branches
+    def _side_stream(self) -> torch.cuda.Stream:
+        st = getattr(self._tls, "side", None)
+        if st is None:
+            st = self._tls.side = torch.cuda.Stream(self.dev)
+            self._tls.ev_fork, self._tls.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        return st
+
+    def _fork(self) -> int:
+        side = self._side_stream()
+        self._tls.ev_fork.record(torch.cuda.current_stream(self.dev))
+        side.wait_event(self._tls.ev_fork)
+        return 0
+
+    def _join(self) -> int:
+        self._tls.ev_join.record(self._side_stream())
+        torch.cuda.current_stream(self.dev).wait_event(self._tls.ev_join)
+        return 0
+
+    def _pseudo(self, fn, name: str) -> None:
+        fn()
+        rec = getattr(self._tls, "rec", None)
+        if rec is not None:
+            rec.append((fn, [], name))
 
     def _buf(self, plan, name, B, H, W, ld, zero=False, dtype=None):
         t = plan.get(name)
@@ -607,15 +639,30 @@ class InferenceEngine:
                 cur = self._flat_buf(plan, "c2", B, H, W, 64)
                 Hp, Wp = self._flat_geom(H, W)
                 xb = plan["xs_bf16"]
-                _lib.check(self.lib.yad_conv_stem_fused(xb.data_ptr(), xb.shape[2], B, H0, T, self.fstem_w.data_ptr(), self.fstem_bias.data_ptr(),
-                                                        cur.data_ptr(), Hp, Wp, int(os.environ.get("YAD_STEM_NINT", "0")), s()),
-                           "conv_stem_fused")
                 fx = plan.get("fstem_cols")
                 if fx is None:
                     cols, var = self._fused_stem_border_cols(T)
-                    fx = plan["fstem_cols"] = ((C.c_int32 * len(cols))(*cols), (C.c_int32 * len(var))(*var), len(cols))
-                _lib.check(self.lib.yad_conv_stem_fused_fixup(xs.data_ptr(), B, H0, T, self.fstem_wvar.data_ptr(), self.fstem_bias.data_ptr(),
-                                                              fx[0], fx[1], fx[2], cur.data_ptr(), Hp, Wp, s()), "conv_stem_fused_fixup")
+                    Wo_ = W
+                    lo_n = sum(1 for c_ in cols if c_ < 2)
+                    hi_n = len(cols) - lo_n
+                    contiguous = cols == list(range(lo_n)) + list(range(Wo_ - hi_n, Wo_))
+                    fx = plan["fstem_cols"] = ((C.c_int32 * len(cols))(*cols), (C.c_int32 * len(var))(*var), len(cols), lo_n, hi_n, contiguous)
+                nint = int(os.environ.get("YAD_STEM_NINT", "0"))
+                if self.stem_overlap and fx[5] and fx[2] > 0:
+                    # the border columns on a second stream, concurrently with the tensor-core kernel (which skips them)
+                    self._pseudo(self._fork, "fork")
+                    _lib.check(self.lib.yad_conv_stem_fused_fixup_bf16(xb.data_ptr(), xb.shape[2], B, H0, T, self.fstem_wvar.data_ptr(),
+                                                                       self.fstem_bias.data_ptr(), fx[0], fx[1], fx[2], cur.data_ptr(), Hp, Wp,
+                                                                       _SideHandle(self._side_stream().cuda_stream)), "conv_stem_fused_fixup_bf16")
+                    _lib.check(self.lib.yad_conv_stem_fused_skip(xb.data_ptr(), xb.shape[2], B, H0, T, self.fstem_w.data_ptr(),
+                                                                 self.fstem_bias.data_ptr(), cur.data_ptr(), Hp, Wp, nint, fx[3], fx[4], s()),
+                               "conv_stem_fused_skip")
+                    self._pseudo(self._join, "join")
+                else:
+                    _lib.check(self.lib.yad_conv_stem_fused(xb.data_ptr(), xb.shape[2], B, H0, T, self.fstem_w.data_ptr(), self.fstem_bias.data_ptr(),
+                                                            cur.data_ptr(), Hp, Wp, nint, s()), "conv_stem_fused")
+                    _lib.check(self.lib.yad_conv_stem_fused_fixup(xs.data_ptr(), B, H0, T, self.fstem_wvar.data_ptr(), self.fstem_bias.data_ptr(),
+                                                                  fx[0], fx[1], fx[2], cur.data_ptr(), Hp, Wp, s()), "conv_stem_fused_fixup")
             else:
                 cur = self._run_stem_two_convs(xs, plan, B, H0, T, H, W, H2, W2)
             s2d_in = None      # space-to-depth copy of `cur` (written by the previous layer's last convolution)
@@ -938,6 +985,8 @@ class InferenceEngine:
         pin, pout, pst = [], [], []
         for ci, (_, args, _) in enumerate(rec):
             for ai, a in enumerate(args):
+                if isinstance(a, _SideHandle):
+                    continue
                 if isinstance(a, C.c_void_p):
                     pst.append((ci, ai))
                 elif isinstance(a, int) and not isinstance(a, bool):
@@ -947,7 +996,8 @@ class InferenceEngine:
                         pout.append((ci, ai))
         if not pin or not pout:
             raise RuntimeError("engine: recorded call list does not reference the input / output tensors")
-        return {"calls": rec, "in": pin, "out": pout, "stream": pst, "shape": tuple(preds.shape)}
+        return {"calls": rec, "in": pin, "out": pout, "stream": pst, "shape": tuple(preds.shape),
+                "n_launch": sum(1 for _, args, _ in rec if args)}        # fork / join pseudo-calls launch nothing
 
     def _replay_or_graph(self, prog: dict, x: torch.Tensor) -> torch.Tensor:
         """Replay of a recorded plan; when the SAME input tensor comes back (a staging buffer, a benchmark loop) the call list is
@@ -965,7 +1015,7 @@ class InferenceEngine:
         if g is not None:
             if g["x"]() is x:
                 g["graph"].replay()
-                _lib.launch_count += len(prog["calls"])
+                _lib.launch_count += prog["n_launch"]
                 return g["preds"].clone()
             graphs.pop(x.data_ptr())            # the captured input tensor is gone: its memory is somebody else's now
         for k in [k for k, v in graphs.items() if v["x"]() is None]:
@@ -1008,5 +1058,5 @@ class InferenceEngine:
                 rc = fn(*args)
                 if rc:
                     _lib.check(rc, name)
-            _lib.launch_count += len(calls)
+            _lib.launch_count += prog["n_launch"]
         return preds

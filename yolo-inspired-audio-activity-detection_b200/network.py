@@ -381,8 +381,8 @@ class AudioDetectionNetwork(nn.Module):
     def _train_engine(self):
         from .train_engine import TrainEngine
         fe = self.feature_extractor
-        if not isinstance(fe, ResNetBackBone) or fe.block_name != "BasicBlock":
-            _unsupported("train() mode (autograd) of the custom / Bottleneck backbones (their eval() forward is built)")
+        if not isinstance(fe, ResNetBackBone):
+            _unsupported("train() mode (autograd) of the custom backbone (its eval() forward is built)")
         dev = self.sm_anchors.device
         key = (str(dev), "train", self.train_dtype)
         eng = self._engine_cache.get(key)

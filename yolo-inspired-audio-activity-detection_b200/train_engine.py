@@ -480,6 +480,16 @@ class TrainEngine:
         idt = x if blk.downsample is None else self.conv_bn(x, blk.downsample[0], blk.downsample[1], ACT_NONE)
         return self.add_act(u, idt, None, ACT_RELU)
 
+    def bottleneck(self, x: _T, blk) -> _T:
+        """torchvision Bottleneck in train mode (resnet.py:143-163 via modules/_backbone.py:128-138, ``resnet_config.block:
+        Bottleneck``): 1x1 - 3x3 (carries the stride) - 1x1 (x4 channels), each with batch-statistics BatchNorm; ReLU after the
+        residual add."""
+        t = self.conv_bn(x, blk.conv1, blk.bn1, ACT_RELU)
+        u = self.conv_bn(t, blk.conv2, blk.bn2, ACT_RELU)
+        v = self.conv_bn(u, blk.conv3, blk.bn3, ACT_NONE)
+        idt = x if blk.downsample is None else self.conv_bn(x, blk.downsample[0], blk.downsample[1], ACT_NONE)
+        return self.add_act(v, idt, None, ACT_RELU)
+
     # ------------------------------------------------------------------ the graph
     def forward(self, xs: torch.Tensor, T: int, L_res: int, record: bool):
         """x_spectral [B,2,32,T] f32 (frontend output, not differentiable: it has no parameters) -> (preds per scale
@@ -512,7 +522,7 @@ class TrainEngine:
         fmaps, marks = [], []
         for li in range(1, 5):
             for blk in getattr(fe, f"layer{li}"):
-                x = self.basic_block(x, blk)
+                x = self.bottleneck(x, blk) if hasattr(blk, "conv3") else self.basic_block(x, blk)
             fmaps.append(x)
             marks.append(len(self._tape) if self._tape is not None else 0)      # tape length after layer li (gradient buckets)
         hs = [f.H for f in fmaps]
