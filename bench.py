@@ -826,8 +826,9 @@ def main():
                 "peak_source": peaks["source"],
                 "algorithmic_bytes_per_launch": MEL_KERNEL_BYTES_PER_CLIP * B, "launch_ms": fe_ms,
                 "note": "achieved = (PCM read + mel write) / CUDA-event time of the launch; DRAM traffic = algorithmic bytes; the kernel "
-                        "is bound by shared-memory wavefronts / latency (l1tex 73 %, issue 48 %, fma pipe 48 %; 13.8 k warp "
-                        "instructions per 8-frame group after packing the arithmetic into FFMA2 / FADD2), not by HBM - see DESIGN.md"}
+                        "is bound by the shared-memory data pipe, not by HBM (ncu r02: l1tex__data_pipe_lsu_wavefronts 78 % of peak, 4.7 k "
+                        "wavefronts and 12.9 k warp instructions per 8-frame group, FMA pipe 52 %, barrier stalls 25 % of the warp "
+                        "samples) - see DESIGN.md and profiles/r02_ncu_frontend_mel_b512_v3_by_line.txt"}
         fe_all = st["frontend_ms"]             # stage A + stage B: the whole frontend's bytes over the whole frontend's time
         roof["frontend_hbm"] = {"achieved_gbs": FRONTEND_BYTES_PER_CLIP * B / (fe_all / 1e3) / 1e9,
                                 "frac": FRONTEND_BYTES_PER_CLIP * B / (fe_all / 1e3) / 1e9 / peaks["hbm_gbs"], "ms": fe_all}
