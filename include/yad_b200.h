@@ -280,6 +280,10 @@ int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_
 int yad_resample_sinc(const void* x, int32_t x_is_i16, int64_t B, int64_t L, int32_t O, int32_t P, int32_t width,
                       const float* kernel, float* out, int64_t Lout, yad_stream_t stream);
 
+/* Debug aid of yad_neck_fused: dev_buf (4 * n_ops int64, device) receives CTA 0's per-op clock64 stamps of its first clip on the
+ * following launches (tools/neck_timeline.py); NULL switches it off (the default). */
+int yad_neck_fused_set_timeline(void* dev_buf);
+
 /* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
  * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5
  * :173-174,181-182; cascaded max_pool2d k5 s1 p2 :207-209.  All write into a channel slice

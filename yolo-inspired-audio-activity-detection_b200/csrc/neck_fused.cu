@@ -56,6 +56,7 @@ struct NkKb {
 };
 
 struct NkParams {
+  long long* tlog;     // debug timeline (yad_neck_fused_set_timeline): CTA 0 records clock64 per op, 4 stamps each; NULL in production
   int32_t n_ops, n_kb, n_clips, n_slots;
   int32_t pool_bytes, n_bias;
   int32_t head_W[3];
@@ -132,7 +133,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(op_done, NK_EPI);
+    mbar_init(op_done, NK_EPI / 32);       // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, NK_TMEM_COLS);
@@ -191,6 +192,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             tc_fence_after();
           }
           first_conv = false;
+          if (p.tlog != nullptr && blockIdx.x == 0 && lane == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 0] = clock64();
           const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], srcg = op.v[14];
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
           for (int k = 0; k < nkb; ++k) {
@@ -234,6 +236,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             }
             __syncwarp();
           }
+          if (p.tlog != nullptr && blockIdx.x == 0 && lane == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 1] = clock64();
         }
       }
     }
@@ -256,6 +259,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
           tc_fence_after();
+          if (p.tlog != nullptr && blockIdx.x == 0 && te == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 2] = clock64();
           const int nb = (N + 31) >> 5;   // 32-column blocks (N = 16: one block, upper 16 columns unused)
           for (int mt = 0; mt < n_mt; ++mt) {
             const int r = 128 * mt + q * 32 + lane, s = r + 1;
@@ -417,9 +421,11 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             }
           }
         }
+        if (p.tlog != nullptr && blockIdx.x == 0 && te == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 3] = clock64();
         if (oi == p.n_ops - 1 || s_ops[oi + 1].v[0] == NK_CONV) {
           fence_proxy_async();   // this thread's plane writes (this op and the element-wise ops before it) become visible to the
-          nk_mbar_arrive(op_done);   // tensor core (async proxy); see the MMA warp
+          __syncwarp();          // tensor core (async proxy); one arrival per warp (256 arrivals on one mbarrier cost ~500 cycles)
+          if (lane == 0) nk_mbar_arrive(op_done);
         }
       }
     }
@@ -442,6 +448,14 @@ int init_neck_fused_attrs() {
 }
 
 }  // namespace yad
+
+static long long* g_nk_tlog = nullptr;
+/* debug: device buffer of 4 * n_ops int64 that the next launches fill with CTA 0's per-op clock64 stamps of its first clip
+ * (MMA warp: start of the op after its dependencies, last MMA issued; epilogue: accumulator complete, op done); NULL switches it off */
+extern "C" int yad_neck_fused_set_timeline(void* dev_buf) {
+  g_nk_tlog = reinterpret_cast<long long*>(dev_buf);
+  return YAD_OK;
+}
 
 extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_t* fmap_rows_per_clip, int64_t B,
                               const void* wblob, int64_t wrows, const float* bias, int32_t n_bias, const void* ops, int32_t n_ops,
@@ -477,6 +491,7 @@ extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, c
     if (rc) return rc;
   }
   NkParams p;
+  p.tlog = g_nk_tlog;
   p.n_ops = n_ops;
   p.n_kb = n_kb;
   p.n_clips = (int)B;
