@@ -457,7 +457,16 @@ def measure_train(args, world, rank, local, dev, K, W, batch=None, e2e=True, lea
 
     with torch.enable_grad():
         t_ramp = time.perf_counter()           # untimed clock ramp, see the inference workload
-        while time.perf_counter() - t_ramp < float(os.environ.get("YAD_BENCH_RAMP_S", "1.5")):
+        ramp_s = float(os.environ.get("YAD_BENCH_RAMP_S", "1.5"))
+        while True:
+            # every step holds collectives (the gradient buckets): all ranks must run the SAME number of ramp steps, so rank 0's
+            # clock decides and the decision is broadcast (a per-rank time test let one rank take one step more and deadlocked
+            # the others in the next barrier - seen at N = 2)
+            go = torch.tensor([1 if time.perf_counter() - t_ramp < ramp_s else 0], device=dev, dtype=torch.int32)
+            if world > 1:
+                dist.broadcast(go, 0)
+            if int(go.item()) == 0:
+                break
             step(x, tg)
             torch.cuda.synchronize()
         for _ in range(W):
