@@ -236,6 +236,13 @@ int yad_conv_flat_taps2(const yad_flat_desc* d, int32_t n_steps, const int32_t* 
                         int32_t ld_in2, const void* weight, int32_t cout_pad, const float* bias, const void* residual, void* out,
                         yad_stream_t stream);
 
+/* Debug aid of the yad_conv_flat* family: dev_buf (16 int64 per CTA, one CTA per SM; device) receives on the following
+ * launches the CTA's coarse timeline - [8] entry, [9] set-up done, [10] / [11] MMA loop begin / end, [12] epilogue done, [13] exit
+ * (clock64), [14] / [15] globaltimer at entry / exit - and, with YAD_FLAT_DBG bit 4, the MMA-issuing warp's cycle budget - [0] total,
+ * [1] waiting for an accumulator stage, [2] for a patch, [3] for a weight block, [4] inside the issue blocks
+ * (tools/bench_conv.py --timeline); NULL switches it off (the default). */
+int yad_conv_flat_set_timeline(void* dev_buf);
+
 /* yad_conv_flat that also writes a SPACE-TO-DEPTH copy of its output for the stride-2 block that follows (torchvision
  * resnet.py:92-100: the first BasicBlock of layer2..4 reads its input with stride 2 twice, conv1 and downsample):
  *   out_s2d [B, Wp2, Hp2, 4 * Cout] bf16, pixel (b, h, w) -> cell (b, w / 2, h / 2), channel plane (h & 1) * 2 + (w & 1).

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--shapes", default="layer1,layer2,layer3,layer4,l1_1x1,l2_1x1")
+    ap.add_argument("--timeline", type=int, default=0, help="print the MMA warp's cycle budget (yad_conv_flat_set_timeline)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = _lib.init(0)
@@ -51,6 +52,26 @@ def main():
             torch.cuda.synchronize()
             if i:
                 ts.append(e0.elapsed_time(e1) * 1e3)
+        if a.timeline:
+            tl = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+            _lib.check(lib.yad_conv_flat_set_timeline(tl.data_ptr()), "tl")
+            _lib.check(lib.yad_conv_flat(C.byref(d), x.data_ptr(), w.data_ptr(), Cout, bias.data_ptr(), _lib.ptr(res), out.data_ptr(),
+                                         a.flags, st), "conv_flat")
+            torch.cuda.synchronize()
+            _lib.check(lib.yad_conv_flat_set_timeline(None), "tl")
+            tv = tl.view(148, 16).double()
+            m = tv.mean(0).tolist()
+            print(f"   MMA warp cycles (mean over CTAs, max total {tv[:, 0].max().item():.0f}): total {m[0]:.0f}  wait acc {m[1]:.0f}  "
+                  f"wait patch {m[2]:.0f}  wait weights {m[3]:.0f}  issue block {m[4]:.0f}")
+            ent = tv[:, 8:9]
+            rel = (tv[:, 9:14] - ent)
+            i = int(torch.argmax(rel[:, 4]))
+            ns = (tv[:, 15] - tv[:, 14])
+            g0 = tv[:, 14].min()
+            print(f"   coarse (cycles from CTA entry; mean | slowest CTA {i}): setup {rel[:, 0].mean():.0f} | {rel[i, 0]:.0f}  mma begin {rel[:, 1].mean():.0f} | "
+                  f"{rel[i, 1]:.0f}  mma end {rel[:, 2].mean():.0f} | {rel[i, 2]:.0f}  epilogue end {rel[:, 3].mean():.0f} | {rel[i, 3]:.0f}  exit "
+                  f"{rel[:, 4].mean():.0f} | {rel[i, 4]:.0f};  CTA lifetime {ns.mean() / 1e3:.1f} us mean, {ns.max() / 1e3:.1f} max; first entry -> last exit "
+                  f"{(tv[:, 15].max() - g0) / 1e3:.1f} us; entry spread {(tv[:, 14].max() - g0) / 1e3:.1f} us; clock {rel[i, 4] / ns[i]:.3f} GHz")
         t = sorted(ts)[len(ts) // 2]
         useful = B * H * W * Cout * Cin * (k * k if H > 1 else k) / 1e6
         print(f"{name:8s} B={B} flags={a.flags} res={a.res}: {t:8.1f} us  useful {2 * useful / t / 1e6:7.1f} TFLOP/s")

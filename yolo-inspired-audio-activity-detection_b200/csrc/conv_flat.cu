@@ -37,28 +37,31 @@
 
 namespace yad {
 
-constexpr int FL_THREADS = 352;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 epilogue TMA (stores / residual loads)
+// Warps: 0 weight TMA, 1 MMA stream A, 2..9 epilogue, 10 epilogue TMA (stores / residual loads), 11 patch TMA, 12 MMA stream B
+constexpr int FL_THREADS = 416;
 constexpr int FL_SRC2 = 0x4000;
 constexpr int FL_NSTAGE = 3;        // epilogue staging buffers of [128 rows x 128 B]
 constexpr int FL_STAGE_BYTES = 128 * 128;
 constexpr int FL_EPI_THREADS = 256;
 constexpr int FL_MAX_STEPS = 64;
-constexpr int FL_MAX_RING = 8;
-constexpr int FL_BOX_ROWS = 64;    // pixel rows per TMA box of the patch (8 KB)
+constexpr int FL_MAX_RING = 8;      // weight ring slots
+constexpr int FL_MAX_NA = 4;        // patch slots per stream
+constexpr int FL_BOX_ROWS = 32;     // pixel rows per TMA box of the patch (4 KB)
+constexpr int FL_ACC_COLS = 128;    // TMEM columns of one accumulator stage of one stream (MT x BN)
 
 struct FlatParams {
   int64_t F;                    // flat pixels = B * Wp * Hp
   int32_t H, W, Hp, Wp;
   int32_t Hpo, Wpo;             // output / residual pitches (same image size)
   int32_t remap;                // 1 when (Hpo, Wpo) != (Hp, Wp)
-  int32_t MT, BN, n_ntiles, n_super;   // n_super = M super-tiles * n_ntiles
+  int32_t MT, BN, n_ntiles, n_super;   // tile = 128 * MT pixel rows x BN channels (MT * BN = 128); n_super = M tiles * n_ntiles
   int32_t n_steps;
-  int32_t NA, NW;               // ring depths
+  int32_t NA, NW;               // ring depths: patch slots per stream, weight slots
   int32_t patch_rows, patch_bytes, w_bytes;
   int32_t min_off;
   int32_t Cout, ld_out, co_off, ld_res, act;
   uint32_t idesc;
-  int32_t flags;                // reserved (0)
+  int32_t flags;                // bit 4: fine timeline of the MMA warps (with tlog)
   int32_t tma_epi;              // 1: residual / output tiles move through the TMA unit and the staging buffers (needs Cout % 64 == 0,
                                 // same pitches in and out); 0: register-sourced global accesses
   int32_t s2d_Hp, s2d_Wp;       // second, space-to-depth copy of the output (0: none): pixel (b, h, w) goes to flat cell
@@ -70,6 +73,7 @@ struct FlatParams {
   int8_t step_first[FL_MAX_STEPS];    // first step of its chunk (load a new patch)
   int8_t step_last[FL_MAX_STEPS];     // last step of its chunk (release the patch)
   int32_t step_wk[FL_MAX_STEPS];      // K offset of the [BN x 64] weight block
+  long long* tlog;                    // debug timeline (16 int64 per CTA), NULL in production
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -83,33 +87,50 @@ constexpr uint32_t FL_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)FL_DESC_HI << 32) | (uint64_t)lo; }
 
-// The MMA warp's loop, specialised on the tile shape so that all 4 * MT descriptors of a step are immediates off two
-// uniform registers.  A single warp runs this latency-bound scalar code for the whole CTA: every instruction saved here
-// is tensor-pipe time gained (B200: 48 / 64 cycles per M=128 MMA at N = 64 / 128).
-template <int MT, int BN>
-__device__ __forceinline__ void flat_mma_loop(const FlatParams& p, uint8_t* sm_a, uint8_t* sm_w, uint64_t* full_a,
-                                              uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty) {
+// One MMA-issuing warp = one STREAM.  Measured on B200 (tools/micro/mma_queue.cu, profiles/r02_mma_queue.txt): the tensor pipe
+// queues ONE tcgen05.mma behind the executing one (less after a tcgen05.commit), so whatever the issuing thread does between
+// two steps - step-table load, mbarrier polls, fence, elect, a dozen R2UR, commits: ~210 cycles - runs with an idle pipe:
+// a lone issuing warp reached 91 / 69 cycles per MMA at N = 128 / 64 against 64 / 48 back to back, with no memory traffic and
+// no epilogue at all (YAD_FLAT_DBG experiments of round 2).  Two warps issuing into DISJOINT accumulators hide each other's
+// gaps completely (same micro-benchmark: 2 x (4 MMAs + up to ~300 idle cycles) per 512 cycles).  So the CTA runs two streams:
+// stream A takes the even, stream B the odd tiles of the CTA's tile sequence, each with its own patch ring and its own
+// double-buffered accumulator (TMEM columns (2 * stream + stage) * 128); both consume the SAME weight blocks (the tiles of a
+// CTA share one N tile), whose ring slots are released by one commit of each stream.
+// The whole warp walks the (warp-uniform) loops so that descriptors stay in uniform registers; one elected lane issues.
+template <int MT, int BN, bool TL>
+__device__ __forceinline__ void flat_mma_loop(const FlatParams& p, const int stream, const int n_my, uint8_t* sm_a, uint8_t* sm_w,
+                                              uint64_t* full_a, uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
+                                              uint64_t* tmem_full, uint64_t* tmem_empty, long long* tl) {
   uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0, as = 0, acc_phase = 0, a_cur = 0, a_lo0 = 0;
   const uint32_t w_lo0 = desc_lo(smem_u32(sm_w));
   const uint32_t a_base_lo = desc_lo(smem_u32(sm_a));
   const uint32_t a_slot_units = (uint32_t)p.patch_bytes >> 4;
   constexpr uint32_t W_UNITS = BN * 128 / 16;
   const int n_steps = p.n_steps;
-  for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+  const uint32_t idesc = p.idesc;
+  long long t_begin = 0, t_acc = 0, t_a = 0, t_w = 0, t_issue = 0, t0 = 0, t1 = 0;
+  if (TL) t_begin = clock64();
+  for (int i = stream; i < n_my; i += 2) {
+    const bool lone = (i + 1 == n_my) && stream == 0;      // no partner tile: this stream releases the weight slots for both
+    if (TL) t0 = clock64();
     mbar_wait(&tmem_empty[as], acc_phase ^ 1);      // epilogue drained this accumulator stage (free on the first lap)
     tc_fence_after();
-    const uint32_t d0 = as * (MT * BN);
+    if (TL) { t1 = clock64(); t_acc += t1 - t0; }
+    const uint32_t d0 = (uint32_t)(2 * stream + as) * FL_ACC_COLS;
     for (int s = 0; s < n_steps; ++s) {
       const uint32_t sm = p.step_mma[s];
       if (sm & (1u << 30)) {
         a_cur = a_slot;
+        if (TL) t0 = clock64();
         mbar_wait(&full_a[a_cur], a_phase);
+        if (TL) { t1 = clock64(); t_a += t1 - t0; }
         a_lo0 = a_base_lo + a_cur * a_slot_units;
         if (++a_slot == (uint32_t)p.NA) { a_slot = 0; a_phase ^= 1; }
       }
+      if (TL) t0 = clock64();
       mbar_wait(&full_w[w_slot], w_phase);
       tc_fence_after();
+      if (TL) { t1 = clock64(); t_w += t1 - t0; }
       if (elect_one()) {
         const uint32_t a_lo = a_lo0 + (sm & 0xFFFFu);
         const uint32_t b_lo = w_lo0 + w_slot * W_UNITS;
@@ -118,16 +139,25 @@ __device__ __forceinline__ void flat_mma_loop(const FlatParams& p, uint8_t* sm_a
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d0 + mt * BN, desc64(a_lo + mt * 1024 + 2 * k), desc64(b_lo + 2 * k), p.idesc, k > 0 ? 1u : acc0);
+            umma_bf16(d0 + mt * BN, desc64(a_lo + mt * 1024 + 2 * k), desc64(b_lo + 2 * k), idesc, k > 0 ? 1u : acc0);
         }
         umma_commit(&empty_w[w_slot]);
+        if (lone) umma_commit(&empty_w[w_slot]);
         if (sm & (1u << 31)) umma_commit(&empty_a[a_cur]);
         if (s == n_steps - 1) umma_commit(&tmem_full[as]);
       }
       __syncwarp();
+      if (TL) t_issue += clock64() - t1;
       if (++w_slot == (uint32_t)p.NW) { w_slot = 0; w_phase ^= 1; }
     }
     if ((as ^= 1) == 0) acc_phase ^= 1;
+  }
+  if (TL && stream == 0 && (threadIdx.x & 31) == 0) {
+    tl[0] = clock64() - t_begin;
+    tl[1] = t_acc;
+    tl[2] = t_a;
+    tl[3] = t_w;
+    tl[4] = t_issue;
   }
 }
 
@@ -140,35 +170,46 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  __nv_bfloat16* __restrict__ out_s2d) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sm_a = smem;                                       // [NA][patch_bytes]
-  uint8_t* sm_w = sm_a + (size_t)p.NA * p.patch_bytes;        // [NW][w_bytes]
+  uint8_t* sm_a = smem;                                       // [2 streams][NA][patch_bytes]
+  uint8_t* sm_w = sm_a + (size_t)2 * p.NA * p.patch_bytes;    // [NW][w_bytes]
   uint8_t* sm_o = sm_w + (size_t)p.NW * p.w_bytes;            // [FL_NSTAGE][16 KB] epilogue staging (1024-byte aligned: patch and
                                                               // weight slots are multiples of 1 KB)
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(sm_o + (p.tma_epi ? FL_NSTAGE * FL_STAGE_BYTES : 0));
-  uint64_t* empty_a = full_a + FL_MAX_RING;
-  uint64_t* full_w = empty_a + FL_MAX_RING;
-  uint64_t* empty_w = full_w + FL_MAX_RING;
-  uint64_t* tmem_full = empty_w + FL_MAX_RING;                // [2]
-  uint64_t* tmem_empty = tmem_full + 2;                       // [2]
-  uint64_t* buf_ready = tmem_empty + 2;                       // [FL_NSTAGE] staging buffer free (and its residual tile landed)
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sm_o + (p.tma_epi ? FL_NSTAGE * FL_STAGE_BYTES : 0));   // [2][FL_MAX_NA]
+  uint64_t* empty_a = full_a + 2 * FL_MAX_NA;                 // [2][FL_MAX_NA]
+  uint64_t* full_w = empty_a + 2 * FL_MAX_NA;                 // [FL_MAX_RING]
+  uint64_t* empty_w = full_w + FL_MAX_RING;                   // [FL_MAX_RING]
+  uint64_t* tmem_full = empty_w + FL_MAX_RING;                // [2 streams][2 stages]
+  uint64_t* tmem_empty = tmem_full + 4;                       // [2 streams][2 stages]
+  uint64_t* buf_ready = tmem_empty + 4;                       // [FL_NSTAGE] staging buffer free (and its residual tile landed)
   uint64_t* out_full = buf_ready + FL_NSTAGE;                 // [FL_NSTAGE] staging buffer holds a finished output tile
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(out_full + FL_NSTAGE);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);   // [n_ntiles * BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncout_pad = p.n_ntiles * p.BN;
+  // coarse debug timeline (p.tlog, 16 int64 per CTA): [8] entry, [9] set-up done, [10] / [11] MMA loop of stream A, [12] epilogue
+  // done, [13] exit (clock64), [14] / [15] globaltimer at entry / exit; [0..4] see flat_mma_loop
+  long long* tl = p.tlog != nullptr ? p.tlog + (size_t)blockIdx.x * 16 : nullptr;
+  if (tl != nullptr && threadIdx.x == 32) {
+    tl[8] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tl[14] = (long long)gt;
+  }
   for (int i = threadIdx.x; i < ncout_pad; i += FL_THREADS) s_bias[i] = bias[i];
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_w);
-    for (int s = 0; s < FL_MAX_RING; ++s) {
+    for (int s = 0; s < 2 * FL_MAX_NA; ++s) {
       mbar_init(&full_a[s], 1);
       mbar_init(&empty_a[s], 1);
-      mbar_init(&full_w[s], 1);
-      mbar_init(&empty_w[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < FL_MAX_RING; ++s) {
+      mbar_init(&full_w[s], 1);
+      mbar_init(&empty_w[s], 2);             // one commit of each stream
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], FL_EPI_THREADS);
     }
@@ -189,31 +230,24 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();          // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
   pdl_trigger();
+  if (tl != nullptr && threadIdx.x == 32) tl[9] = clock64();
   const int rows_per_super = 128 * p.MT;
   const int n_boxes = p.patch_rows / FL_BOX_ROWS;
+  // this CTA's tile sequence: st = blockIdx.x + i * gridDim.x, i < n_my.  gridDim.x is a multiple of n_ntiles, so all of them have the
+  // same N tile (one weight stream per CTA); tile i belongs to stream i & 1, the pair (2 j, 2 j + 1) shares every weight block
+  const int n_my = (int)blockIdx.x < p.n_super ? (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n0 = ((int)blockIdx.x % p.n_ntiles) * p.BN;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== weight producer: one block per step of every tile PAIR =====================
+    // Patches and weights have their own producer threads (this warp and warp 11): a patch is requested the moment its slot is
+    // released, not after the NW weight blocks in front of it.
     if (lane == 0) {
       // ring state kept as (slot, phase) counters: no integer division on this latency-bound single-thread path.
       // Waiting on parity (phase ^ 1) of a fresh mbarrier returns at once, so the first lap needs no special case.
-      uint32_t a_slot = 0, a_phase = 0, w_slot = 0, w_phase = 0;
-      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
-        const int64_t f0 = (int64_t)mtile * rows_per_super;
-        const int n0 = nt * p.BN;
+      uint32_t w_slot = 0, w_phase = 0;
+      for (int j = 0; 2 * j < n_my; ++j) {
         for (int s = 0; s < p.n_steps; ++s) {
-          if (p.step_first[s]) {
-            mbar_wait(&empty_a[a_slot], a_phase ^ 1);
-            uint8_t* dst = sm_a + (size_t)a_slot * p.patch_bytes;
-            mbar_expect_tx(&full_a[a_slot], (uint32_t)p.patch_bytes);
-            const int c0 = (p.step_chunk[s] & (FL_SRC2 - 1)) * 64;
-            const CUtensorMap* ma = (p.step_chunk[s] & FL_SRC2) ? &map_a2 : &map_a;
-            const int r0 = (int)(f0 + p.min_off);
-            for (int i = 0; i < n_boxes; ++i)
-              tma_load_2d(ma, &full_a[a_slot], dst + i * (FL_BOX_ROWS * 128), c0, r0 + i * FL_BOX_ROWS);
-            if (++a_slot == (uint32_t)p.NA) { a_slot = 0; a_phase ^= 1; }
-          }
           mbar_wait(&empty_w[w_slot], w_phase ^ 1);
           mbar_expect_tx(&full_w[w_slot], (uint32_t)p.w_bytes);
           tma_load_2d(&map_w, &full_w[w_slot], sm_w + (size_t)w_slot * p.w_bytes, p.step_wk[s], n0);
@@ -221,29 +255,67 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the (warp-uniform) loops so that every descriptor / TMEM address stays in uniform
-    // registers; one elected lane issues the tcgen05.mma / commit instructions.  All 512 TMEM columns are ours, so the
-    // allocation starts at column 0 and accumulator addresses are plain constants.
+  } else if (warp == 11) {
+    // ===================== patch producer: per chunk of a tile pair, stream A's patch then stream B's =====================
+    // (the streams advance in lock step - they share the weight ring - so serving them in program order cannot starve one)
+    if (lane == 0) {
+      uint32_t a_slot[2] = {0, 0}, a_phase[2] = {0, 0};
+      for (int j = 0; 2 * j < n_my; ++j) {
+        for (int s = 0; s < p.n_steps; ++s) {
+          if (!p.step_first[s]) continue;
+          const int c0 = (p.step_chunk[s] & (FL_SRC2 - 1)) * 64;
+          const CUtensorMap* ma = (p.step_chunk[s] & FL_SRC2) ? &map_a2 : &map_a;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int i = 2 * j + q;
+            if (i >= n_my) break;
+            const int st = (int)blockIdx.x + i * (int)gridDim.x;
+            const int mtile = st / p.n_ntiles;
+            const int r0 = (int)((int64_t)mtile * rows_per_super + p.min_off);
+            uint64_t* fb = &full_a[q * FL_MAX_NA + a_slot[q]];
+            mbar_wait(&empty_a[q * FL_MAX_NA + a_slot[q]], a_phase[q] ^ 1);
+            uint8_t* dst = sm_a + (size_t)(q * p.NA + a_slot[q]) * p.patch_bytes;
+            mbar_expect_tx(fb, (uint32_t)p.patch_bytes);
+            for (int b = 0; b < n_boxes; ++b) tma_load_2d(ma, fb, dst + b * (FL_BOX_ROWS * 128), c0, r0 + b * FL_BOX_ROWS);
+            if (++a_slot[q] == (uint32_t)p.NA) { a_slot[q] = 0; a_phase[q] ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 12) {
+    // ===================== MMA issuers: stream A (warp 1), stream B (warp 12) =====================
+    // All 512 TMEM columns are ours, so the allocation starts at column 0 and accumulator addresses are plain constants.
     if (tmem_base != 0) __trap();
-    if (p.MT == 4)
-      flat_mma_loop<4, 64>(p, sm_a, sm_w, full_a, empty_a, full_w, empty_w, tmem_full, tmem_empty);
-    else
-      flat_mma_loop<2, 128>(p, sm_a, sm_w, full_a, empty_a, full_w, empty_w, tmem_full, tmem_empty);
+    const int stream = warp == 1 ? 0 : 1;
+    uint8_t* sa = sm_a + (size_t)stream * p.NA * p.patch_bytes;
+    uint64_t* fa = full_a + stream * FL_MAX_NA;
+    uint64_t* ea = empty_a + stream * FL_MAX_NA;
+    uint64_t* tf = tmem_full + 2 * stream;
+    uint64_t* te = tmem_empty + 2 * stream;
+    if (tl != nullptr && warp == 1 && lane == 0) tl[10] = clock64();
+    if (p.tlog != nullptr && (p.flags & 16)) {
+      if (p.MT == 2)
+        flat_mma_loop<2, 64, true>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+      else
+        flat_mma_loop<1, 128, true>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+    } else if (p.MT == 2) {
+      flat_mma_loop<2, 64, false>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+    } else {
+      flat_mma_loop<1, 128, false>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+    }
+    if (tl != nullptr && warp == 1 && lane == 0) tl[11] = clock64();
   } else if (warp == 10) {
     // ===================== epilogue TMA: stores the finished tiles, loads the residual tiles two items ahead =====================
     if (p.tma_epi && lane == 0) {
       const int cpa = p.BN >> 6, n_items = p.MT * cpa;
-      const int n_my = (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = n_my * n_items;
       // item g of this CTA -> (channel, row) coordinate of its [128 x 64] tile
       auto coords = [&](int g, int& ch, int& row) {
         const int sti = g / n_items, j = g - sti * n_items;
         const int st = (int)blockIdx.x + sti * (int)gridDim.x;
-        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
+        const int mtile = st / p.n_ntiles;
         const int mt = j / cpa, cj = j - mt * cpa;
-        ch = nt * p.BN + 64 * cj;
+        ch = n0 + 64 * cj;
         row = mtile * rows_per_super + 128 * mt;
       };
       auto make_ready = [&](int g) {          // buffer g % FL_NSTAGE is free: fetch the residual tile of item g, or just say so
@@ -274,23 +346,24 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ===================== epilogue: 8 warps; TMEM lane quadrant = warp % 4, column-chunk parity = (warp - 2) / 4 =====
+    // Tiles are drained in sequence order i = 0, 1, 2, ...: stream i & 1, accumulator stage (i >> 1) & 1, barrier phase (i >> 2) & 1
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int chunks_per_acc = p.BN >> 6;            // 32-column chunks handled by this warp per accumulator (1 or 2)
-    const int n_items = p.MT * chunks_per_acc;       // work items per super-tile: (mt, chunk)
+    const int n_items = p.MT * chunks_per_acc;       // work items per tile: (mt, chunk)
     const uint32_t Hp = (uint32_t)p.Hp, Wp = (uint32_t)p.Wp;
-    uint32_t as = 0, acc_phase = 0;
     if (p.tma_epi) {
       // ---- tiles through the staging buffers (see the header): item = (mt, 64-channel block) = one [128 x 64] tile that the 8
       //      warps fill together; thread = (pixel row r, channel half): four 16-byte chunks of its row, swizzled like the TMA image
       uint32_t sb = 0, sb_phase = 0;
       const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)r & 7u;
-      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
-        const int n0 = nt * p.BN;
+      for (int i = 0; i < n_my; ++i) {
+        const int st = (int)blockIdx.x + i * (int)gridDim.x;
+        const int mtile = st / p.n_ntiles;
+        const uint32_t acc = (uint32_t)(2 * (i & 1) + ((i >> 1) & 1));      // accumulator (stream, stage) = barrier index
         const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
-        mbar_wait(&tmem_full[as], acc_phase);
+        mbar_wait(&tmem_full[acc], (uint32_t)(i >> 2) & 1u);
         tc_fence_after();
         for (int j = 0; j < n_items; ++j) {
           const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
@@ -300,7 +373,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const bool ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W;
           const int nbase = n0 + c0;
           uint32_t v[32];
-          tmem_ld32(((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
+          tmem_ld32(((uint32_t)(q * 32) << 16) + acc * FL_ACC_COLS + (uint32_t)(mt * p.BN + c0), v);
           tmem_ld_wait();
           uint8_t* S = sm_o + sb * FL_STAGE_BYTES + row_off;
           mbar_wait(&buf_ready[sb], sb_phase);       // the buffer is free and (if any) the residual tile has landed in it
@@ -358,13 +431,13 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (++sb == FL_NSTAGE) { sb = 0; sb_phase ^= 1; }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[as]);
-        if ((as ^= 1) == 0) acc_phase ^= 1;
+        mbar_arrive(&tmem_empty[acc]);
       }
     } else {
-      for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
-        const int mtile = st / p.n_ntiles, nt = st - mtile * p.n_ntiles;
-        const int n0 = nt * p.BN;
+      for (int i = 0; i < n_my; ++i) {
+        const int st = (int)blockIdx.x + i * (int)gridDim.x;
+        const int mtile = st / p.n_ntiles;
+        const uint32_t acc = (uint32_t)(2 * (i & 1) + ((i >> 1) & 1));
         const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
         // residual prefetch for item 0 (independent of the accumulator): hides the HBM latency behind the barrier wait
         uint4 rq[4];
@@ -393,13 +466,13 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         bool ok_cur;
         item_geom(0, f_cur, nb_cur, ok_cur);
         load_res(f_cur, nb_cur, ok_cur);
-        mbar_wait(&tmem_full[as], acc_phase);
+        mbar_wait(&tmem_full[acc], (uint32_t)(i >> 2) & 1u);
         tc_fence_after();
         for (int j = 0; j < n_items; ++j) {
           const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
           const int c0 = 32 * (2 * cj + half);
           uint32_t v[32];
-          tmem_ld32(((uint32_t)(q * 32) << 16) + (uint32_t)((as * p.MT + mt) * p.BN + c0), v);
+          tmem_ld32(((uint32_t)(q * 32) << 16) + acc * FL_ACC_COLS + (uint32_t)(mt * p.BN + c0), v);
           tmem_ld_wait();
           float x[32];
           if (ok_cur) {
@@ -450,14 +523,20 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[as]);
-        if ((as ^= 1) == 0) acc_phase ^= 1;
+        mbar_arrive(&tmem_empty[acc]);
       }
-      }
+    }
+    if (tl != nullptr && threadIdx.x == 64) tl[12] = clock64();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (tl != nullptr && threadIdx.x == 32) {
+    tl[13] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tl[15] = (long long)gt;
+  }
 }
 
 int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -476,6 +555,8 @@ int init_conv_flat_attrs() {
 
 namespace yad {
 
+static long long* g_flat_tlog = nullptr;     // yad_conv_flat_set_timeline
+
 // common launcher: the caller has filled the geometry / epilogue fields and the step lists (grouped by chunk)
 static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const void* in, int cin_total, int ld_in,
                        const void* weight, int64_t k_total, int cout_pad, const float* bias, const void* residual, void* out,
@@ -485,7 +566,7 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   YAD_CHECK_ARG((max_off - p.min_off) * 8 < 65536, "yad_conv_flat: filter reach too large");
   p.BN = cout_pad % 128 == 0 ? 128 : 64;
   p.n_ntiles = cout_pad / p.BN;
-  p.MT = 256 / p.BN;                      // 2 accumulator stages x MT x BN = 512 TMEM columns
+  p.MT = FL_ACC_COLS / p.BN;              // 2 streams x 2 accumulator stages x MT x BN = 512 TMEM columns
   const int rows_per_super = 128 * p.MT;
   const int patch_rows_raw = rows_per_super + max_off - p.min_off;
   p.patch_rows = (patch_rows_raw + FL_BOX_ROWS - 1) / FL_BOX_ROWS * FL_BOX_ROWS;
@@ -493,7 +574,12 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   p.w_bytes = p.BN * 128;
   const int64_t n_mtiles = (p.F + rows_per_super - 1) / rows_per_super;
   p.n_super = (int)(n_mtiles * p.n_ntiles);
-  p.flags = 0;
+  static const int dbg_flags = [] {           // timing experiments only (results are wrong with any bit set)
+    const char* e = getenv("YAD_FLAT_DBG");
+    return e ? atoi(e) : 0;
+  }();
+  p.flags = dbg_flags;
+  p.tlog = g_flat_tlog;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // epilogue through the TMA unit: whole 64-channel blocks, one geometry for input, output and residual
   static const bool tma_epi_enabled = [] {
@@ -504,22 +590,32 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   // shared-memory budget: barriers + bias + alignment slack, the epilogue staging buffers, then the two rings
   size_t fixed = 0;
   for (;;) {
-    fixed = 1024 + (4 * FL_MAX_RING + 4 + 2 * FL_NSTAGE) * 8 + 16 + (size_t)cout_pad * 4 + 64 +
+    fixed = 1024 + (4 * FL_MAX_NA + 2 * FL_MAX_RING + 8 + 2 * FL_NSTAGE) * 8 + 16 + (size_t)cout_pad * 4 + 64 +
             (p.tma_epi ? (size_t)FL_NSTAGE * FL_STAGE_BYTES : 0);
     const size_t budget = 227 * 1024 - fixed;
-    p.NA = n_chunks_distinct > 1 ? 3 : 2;
-    while (p.NA > 1 && (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes > budget) --p.NA;
-    const bool fits = (size_t)p.NA * p.patch_bytes + 2 * (size_t)p.w_bytes <= budget;
+    // patch slots (per stream): the patch producer requests a patch the moment a slot is released, i.e. (NA - 1) chunk durations
+    // before its first MMA.  Two slots are enough when one chunk's MMAs (of both streams: they share the tensor pipe) outlast the
+    // load of the next patch (~4 k cycles for 20-36 KB); everything else goes to the weight ring, which has to cover the L2
+    // latency of its 8 / 16 KB blocks.
+    static const int na_forced = [] {
+      const char* e = getenv("YAD_FLAT_NA");
+      return e ? atoi(e) : 0;
+    }();
+    const int chunk_cycles = 2 * (p.n_steps / (n_chunks_distinct > 0 ? n_chunks_distinct : 1)) * p.MT * 4 * (p.BN == 128 ? 64 : 48);
+    p.NA = chunk_cycles >= 4000 ? 2 : 3;
+    if (na_forced >= 2 && na_forced <= FL_MAX_NA) p.NA = na_forced;
+    while (p.NA > 1 && 2 * (size_t)p.NA * p.patch_bytes + 3 * (size_t)p.w_bytes > budget) --p.NA;
+    const bool fits = 2 * (size_t)p.NA * p.patch_bytes + 3 * (size_t)p.w_bytes <= budget;
     if ((!fits || p.NA < 2) && p.tma_epi) {     // the staging buffers cost the patch double-buffering: keep the register-sourced epilogue
       p.tma_epi = 0;
       continue;
     }
     YAD_CHECK_ARG(fits, "yad_conv_flat: patch of %d rows does not fit", p.patch_rows);
-    p.NW = (int)((budget - (size_t)p.NA * p.patch_bytes) / p.w_bytes);
+    p.NW = (int)((budget - 2 * (size_t)p.NA * p.patch_bytes) / p.w_bytes);
     if (p.NW > FL_MAX_RING) p.NW = FL_MAX_RING;
     break;
   }
-  const size_t smem = fixed + (size_t)p.NA * p.patch_bytes + (size_t)p.NW * p.w_bytes;
+  const size_t smem = fixed + 2 * (size_t)p.NA * p.patch_bytes + (size_t)p.NW * p.w_bytes;
 
   CUtensorMap map_a, map_w;
   {
@@ -562,7 +658,9 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
     }
   }
   const int nsm = sm_count() > 0 ? sm_count() : 148;
-  const int grid = p.n_super < nsm ? p.n_super : nsm;
+  // a multiple of n_ntiles (the tiles of a CTA then share one N tile = one weight stream); n_super is one
+  int grid = (p.n_super < nsm ? p.n_super : nsm) / p.n_ntiles * p.n_ntiles;
+  if (grid < p.n_ntiles) grid = p.n_ntiles;
   YAD_CUDA(launch_pdl(conv_flat_kernel, dim3((unsigned)grid), dim3(FL_THREADS), smem, (cudaStream_t)stream, map_a, map_a2, map_w, map_out, map_res, p, bias,
                       reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<__nv_bfloat16*>(out),
                       reinterpret_cast<__nv_bfloat16*>(out_s2d)));
@@ -657,6 +755,13 @@ static int conv_flat_impl(const yad_flat_desc* d, const void* in, const void* we
   p.min_off = min_off;
   return launch_flat(p, n_chunks, max_off, in, d->Cin, d->ld_in, weight, (int64_t)d->kh * d->kw * d->Cin, cout_pad, bias, residual,
                      out, stream, out_s2d);
+}
+
+/* debug: device buffer of 8 int64 per CTA (148 CTAs) that the next conv_flat launches fill with the MMA warp's cycle budget
+ * [total, wait accumulator stage, wait patch, wait weights, issue block]; NULL switches it off */
+extern "C" int yad_conv_flat_set_timeline(void* dev_buf) {
+  yad::g_flat_tlog = reinterpret_cast<long long*>(dev_buf);
+  return YAD_OK;
 }
 
 extern "C" int yad_conv_flat(const yad_flat_desc* d, const void* in, const void* weight, int32_t cout_pad,

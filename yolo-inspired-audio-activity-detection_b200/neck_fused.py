@@ -159,12 +159,8 @@ class FusedNeck:
         Hp = H + 1 if H > 1 else 1
         for cv in cvs:
             assert cv.kh == 1 and cv.kw == 1 and cv.cin_pad == Cc, (cv.name, cv.cin_pad, Cc)
-        out = []
-        for h in range(Hp):
-            for c in range(Cc // 64):
-                wb = self._blk(cvs, 0, 0, c, 1.0 / H) if h < H else torch.zeros(sum(cv.cout_pad for cv in cvs), 64)
-                out.append((h * (Cc // 64) + c, 0, wb.to(self._w4(cvs[0]).device)))
-        return out
+        # the halo row h = H of a flat column is zero: its K blocks are left out (they were streamed against zero weights)
+        return [(h * (Cc // 64) + c, 0, self._blk(cvs, 0, 0, c, 1.0 / H)) for h in range(H) for c in range(Cc // 64)]
 
     def _ew(self, typ: int, level_out: int, a: int, b: int, c: int = 0, d: int = 0, wp_in: int = 0):
         g = self.lv[level_out]
