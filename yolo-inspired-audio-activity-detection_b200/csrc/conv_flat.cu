@@ -97,7 +97,7 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)FL_D
 // double-buffered accumulator (TMEM columns (2 * stream + stage) * 128); both consume the SAME weight blocks (the tiles of a
 // CTA share one N tile), whose ring slots are released by one commit of each stream.
 // The whole warp walks the (warp-uniform) loops so that descriptors stay in uniform registers; one elected lane issues.
-template <int MT, int BN, bool TL>
+template <int MT, int BN, bool TL, bool PAIR>
 __device__ __forceinline__ void flat_mma_loop(const FlatParams& p, const int stream, const int n_my, uint8_t* sm_a, uint8_t* sm_w,
                                               uint64_t* full_a, uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
                                               uint64_t* tmem_full, uint64_t* tmem_empty, long long* tl) {
@@ -105,13 +105,12 @@ __device__ __forceinline__ void flat_mma_loop(const FlatParams& p, const int str
   const uint32_t w_lo0 = desc_lo(smem_u32(sm_w));
   const uint32_t a_base_lo = desc_lo(smem_u32(sm_a));
   const uint32_t a_slot_units = (uint32_t)p.patch_bytes >> 4;
-  constexpr uint32_t W_UNITS = BN * 128 / 16;
+  constexpr uint32_t W_UNITS = (PAIR ? BN / 2 : BN) * 128 / 16;      // a CTA of a pair holds half of the weight block's rows
   const int n_steps = p.n_steps;
   const uint32_t idesc = p.idesc;
   long long t_begin = 0, t_acc = 0, t_a = 0, t_w = 0, t_issue = 0, t0 = 0, t1 = 0;
   if (TL) t_begin = clock64();
-  for (int i = stream; i < n_my; i += 2) {
-    const bool lone = (i + 1 == n_my) && stream == 0;      // no partner tile: this stream releases the weight slots for both
+  for (int j = 0; j < n_my; ++j) {                  // one tile of this stream per tile pair
     if (TL) t0 = clock64();
     mbar_wait(&tmem_empty[as], acc_phase ^ 1);      // epilogue drained this accumulator stage (free on the first lap)
     tc_fence_after();
@@ -138,13 +137,22 @@ __device__ __forceinline__ void flat_mma_loop(const FlatParams& p, const int str
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d0 + mt * BN, desc64(a_lo + mt * 1024 + 2 * k), desc64(b_lo + 2 * k), idesc, k > 0 ? 1u : acc0);
+          for (int k = 0; k < 4; ++k) {
+            if (PAIR)
+              umma_bf16_pair(d0 + mt * BN, desc64(a_lo + mt * 1024 + 2 * k), desc64(b_lo + 2 * k), idesc, k > 0 ? 1u : acc0);
+            else
+              umma_bf16(d0 + mt * BN, desc64(a_lo + mt * 1024 + 2 * k), desc64(b_lo + 2 * k), idesc, k > 0 ? 1u : acc0);
+          }
         }
-        umma_commit(&empty_w[w_slot]);
-        if (lone) umma_commit(&empty_w[w_slot]);
-        if (sm & (1u << 31)) umma_commit(&empty_a[a_cur]);
-        if (s == n_steps - 1) umma_commit(&tmem_full[as]);
+        if (PAIR) {                                   // the same barriers of both CTAs
+          umma_commit_pair(&empty_w[w_slot]);
+          if (sm & (1u << 31)) umma_commit_pair(&empty_a[a_cur]);
+          if (s == n_steps - 1) umma_commit_pair(&tmem_full[as]);
+        } else {
+          umma_commit(&empty_w[w_slot]);
+          if (sm & (1u << 31)) umma_commit(&empty_a[a_cur]);
+          if (s == n_steps - 1) umma_commit(&tmem_full[as]);
+        }
       }
       __syncwarp();
       if (TL) t_issue += clock64() - t1;
@@ -161,6 +169,7 @@ __device__ __forceinline__ void flat_mma_loop(const FlatParams& p, const int str
   }
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(FL_THREADS, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_w,
@@ -211,7 +220,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], FL_EPI_THREADS);
+      mbar_init(&tmem_empty[s], PAIR ? 2 * FL_EPI_THREADS : FL_EPI_THREADS);     // the leader's barrier counts both epilogues
     }
     for (int s = 0; s < FL_NSTAGE; ++s) {
       mbar_init(&buf_ready[s], 1);
@@ -223,9 +232,17 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  if (warp == 1) {
+    if (PAIR)
+      tmem_alloc_pair(tmem_ptr_smem, 512);
+    else
+      tmem_alloc(tmem_ptr_smem, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();        // the peer's barriers are initialised before any TMA completion / commit / arrive reaches them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();          // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
@@ -233,10 +250,21 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (tl != nullptr && threadIdx.x == 32) tl[9] = clock64();
   const int rows_per_super = 128 * p.MT;
   const int n_boxes = p.patch_rows / FL_BOX_ROWS;
-  // this CTA's tile sequence: st = blockIdx.x + i * gridDim.x, i < n_my.  gridDim.x is a multiple of n_ntiles, so all of them have the
-  // same N tile (one weight stream per CTA); tile i belongs to stream i & 1, the pair (2 j, 2 j + 1) shares every weight block
-  const int n_my = (int)blockIdx.x < p.n_super ? (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int n0 = ((int)blockIdx.x % p.n_ntiles) * p.BN;
+  // Work units: a CTA (a CTA pair with PAIR) walks the sequence of tile PAIRS P = unit + j * n_units, j < n_my; pair P = N tile
+  // P % n_ntiles, M-pair P / n_ntiles; its two tiles (stream 0 / 1) are adjacent M tiles and share every weight block.  With PAIR a
+  // tile is 2 x 128 * MT rows, one half per CTA (cluster rank).  Tiles past the end of the tensor are computed on zero-filled
+  // patches and dropped by the epilogue's masks / the TMA unit's clipping.
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int unit = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x;
+  const int n_units = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
+  const int n_my = unit < p.n_super ? (p.n_super - unit + n_units - 1) / n_units : 0;
+  auto pair_nt = [&](int j) { return (unit + j * n_units) % p.n_ntiles; };
+  auto tile_m = [&](int j, int q) {            // M tile (of 128 * MT rows) of stream q of this CTA in pair j
+    const int mp = (unit + j * n_units) / p.n_ntiles;
+    return PAIR ? (2 * mp + q) * 2 + rank : 2 * mp + q;
+  };
+  const uint32_t leader_full_a = PAIR ? mapa_u32(full_a, 0) : 0u, leader_full_w = PAIR ? mapa_u32(full_w, 0) : 0u;
+  const uint32_t leader_tmem_empty = PAIR ? mapa_u32(tmem_empty, 0) : 0u;
 
   if (warp == 0) {
     // ===================== weight producer: one block per step of every tile PAIR =====================
@@ -246,11 +274,19 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // ring state kept as (slot, phase) counters: no integer division on this latency-bound single-thread path.
       // Waiting on parity (phase ^ 1) of a fresh mbarrier returns at once, so the first lap needs no special case.
       uint32_t w_slot = 0, w_phase = 0;
-      for (int j = 0; 2 * j < n_my; ++j) {
+      const uint32_t wb = (uint32_t)p.w_bytes;          // this CTA's share of a weight block (half of its rows with PAIR)
+      for (int j = 0; j < n_my; ++j) {
+        const int n0 = pair_nt(j) * p.BN + (PAIR ? rank * (p.BN >> 1) : 0);
         for (int s = 0; s < p.n_steps; ++s) {
           mbar_wait(&empty_w[w_slot], w_phase ^ 1);
-          mbar_expect_tx(&full_w[w_slot], (uint32_t)p.w_bytes);
-          tma_load_2d(&map_w, &full_w[w_slot], sm_w + (size_t)w_slot * p.w_bytes, p.step_wk[s], n0);
+          if (PAIR) {
+            // both CTAs' halves complete on the LEADER's barrier (its MMA warps wait there); only the leader announces the bytes
+            if (rank == 0) mbar_expect_tx(&full_w[w_slot], 2u * wb);
+            tma_load_2d_pair(&map_w, leader_full_w + 8u * w_slot, sm_w + (size_t)w_slot * wb, p.step_wk[s], n0);
+          } else {
+            mbar_expect_tx(&full_w[w_slot], wb);
+            tma_load_2d(&map_w, &full_w[w_slot], sm_w + (size_t)w_slot * wb, p.step_wk[s], n0);
+          }
           if (++w_slot == (uint32_t)p.NW) { w_slot = 0; w_phase ^= 1; }
         }
       }
@@ -260,23 +296,25 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // (the streams advance in lock step - they share the weight ring - so serving them in program order cannot starve one)
     if (lane == 0) {
       uint32_t a_slot[2] = {0, 0}, a_phase[2] = {0, 0};
-      for (int j = 0; 2 * j < n_my; ++j) {
+      for (int j = 0; j < n_my; ++j) {
         for (int s = 0; s < p.n_steps; ++s) {
           if (!p.step_first[s]) continue;
           const int c0 = (p.step_chunk[s] & (FL_SRC2 - 1)) * 64;
           const CUtensorMap* ma = (p.step_chunk[s] & FL_SRC2) ? &map_a2 : &map_a;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const int i = 2 * j + q;
-            if (i >= n_my) break;
-            const int st = (int)blockIdx.x + i * (int)gridDim.x;
-            const int mtile = st / p.n_ntiles;
-            const int r0 = (int)((int64_t)mtile * rows_per_super + p.min_off);
-            uint64_t* fb = &full_a[q * FL_MAX_NA + a_slot[q]];
-            mbar_wait(&empty_a[q * FL_MAX_NA + a_slot[q]], a_phase[q] ^ 1);
+            const int r0 = (int)((int64_t)tile_m(j, q) * rows_per_super + p.min_off);
+            const int bi = q * FL_MAX_NA + (int)a_slot[q];
+            mbar_wait(&empty_a[bi], a_phase[q] ^ 1);
             uint8_t* dst = sm_a + (size_t)(q * p.NA + a_slot[q]) * p.patch_bytes;
-            mbar_expect_tx(fb, (uint32_t)p.patch_bytes);
-            for (int b = 0; b < n_boxes; ++b) tma_load_2d(ma, fb, dst + b * (FL_BOX_ROWS * 128), c0, r0 + b * FL_BOX_ROWS);
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(&full_a[bi], 2u * (uint32_t)p.patch_bytes);
+              for (int b = 0; b < n_boxes; ++b)
+                tma_load_2d_pair(ma, leader_full_a + 8u * bi, dst + b * (FL_BOX_ROWS * 128), c0, r0 + b * FL_BOX_ROWS);
+            } else {
+              mbar_expect_tx(&full_a[bi], (uint32_t)p.patch_bytes);
+              for (int b = 0; b < n_boxes; ++b) tma_load_2d(ma, &full_a[bi], dst + b * (FL_BOX_ROWS * 128), c0, r0 + b * FL_BOX_ROWS);
+            }
             if (++a_slot[q] == (uint32_t)p.NA) { a_slot[q] = 0; a_phase[q] ^= 1; }
           }
         }
@@ -293,30 +331,30 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tf = tmem_full + 2 * stream;
     uint64_t* te = tmem_empty + 2 * stream;
     if (tl != nullptr && warp == 1 && lane == 0) tl[10] = clock64();
-    if (p.tlog != nullptr && (p.flags & 16)) {
-      if (p.MT == 2)
-        flat_mma_loop<2, 64, true>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
-      else
-        flat_mma_loop<1, 128, true>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
-    } else if (p.MT == 2) {
-      flat_mma_loop<2, 64, false>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
-    } else {
-      flat_mma_loop<1, 128, false>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+    if (rank == 0) {           // with PAIR only the leader CTA issues (for both CTAs)
+      if (p.tlog != nullptr && (p.flags & 16)) {
+        if (p.MT == 2)
+          flat_mma_loop<2, 64, true, PAIR>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+        else
+          flat_mma_loop<1, 128, true, PAIR>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+      } else if (p.MT == 2) {
+        flat_mma_loop<2, 64, false, PAIR>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+      } else {
+        flat_mma_loop<1, 128, false, PAIR>(p, stream, n_my, sa, sm_w, fa, ea, full_w, empty_w, tf, te, tl);
+      }
     }
     if (tl != nullptr && warp == 1 && lane == 0) tl[11] = clock64();
   } else if (warp == 10) {
     // ===================== epilogue TMA: stores the finished tiles, loads the residual tiles two items ahead =====================
     if (p.tma_epi && lane == 0) {
       const int cpa = p.BN >> 6, n_items = p.MT * cpa;
-      const int total = n_my * n_items;
-      // item g of this CTA -> (channel, row) coordinate of its [128 x 64] tile
+      const int total = 2 * n_my * n_items;
+      // item g of this CTA -> (channel, row) coordinate of its [128 x 64] tile; tiles in sequence order i = 2 j + stream
       auto coords = [&](int g, int& ch, int& row) {
-        const int sti = g / n_items, j = g - sti * n_items;
-        const int st = (int)blockIdx.x + sti * (int)gridDim.x;
-        const int mtile = st / p.n_ntiles;
-        const int mt = j / cpa, cj = j - mt * cpa;
-        ch = n0 + 64 * cj;
-        row = mtile * rows_per_super + 128 * mt;
+        const int i = g / n_items, jj = g - i * n_items;
+        const int mt = jj / cpa, cj = jj - mt * cpa;
+        ch = pair_nt(i >> 1) * p.BN + 64 * cj;
+        row = tile_m(i >> 1, i & 1) * rows_per_super + 128 * mt;
       };
       auto make_ready = [&](int g) {          // buffer g % FL_NSTAGE is free: fetch the residual tile of item g, or just say so
         uint64_t* bar = &buf_ready[g % FL_NSTAGE];
@@ -358,9 +396,9 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       //      warps fill together; thread = (pixel row r, channel half): four 16-byte chunks of its row, swizzled like the TMA image
       uint32_t sb = 0, sb_phase = 0;
       const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)r & 7u;
-      for (int i = 0; i < n_my; ++i) {
-        const int st = (int)blockIdx.x + i * (int)gridDim.x;
-        const int mtile = st / p.n_ntiles;
+      for (int i = 0; i < 2 * n_my; ++i) {
+        const int mtile = tile_m(i >> 1, i & 1);
+        const int n0 = pair_nt(i >> 1) * p.BN;
         const uint32_t acc = (uint32_t)(2 * (i & 1) + ((i >> 1) & 1));      // accumulator (stream, stage) = barrier index
         const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
         mbar_wait(&tmem_full[acc], (uint32_t)(i >> 2) & 1u);
@@ -431,12 +469,15 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (++sb == FL_NSTAGE) { sb = 0; sb_phase ^= 1; }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        if (PAIR)
+          mbar_arrive_cluster(leader_tmem_empty + 8u * acc);
+        else
+          mbar_arrive(&tmem_empty[acc]);
       }
     } else {
-      for (int i = 0; i < n_my; ++i) {
-        const int st = (int)blockIdx.x + i * (int)gridDim.x;
-        const int mtile = st / p.n_ntiles;
+      for (int i = 0; i < 2 * n_my; ++i) {
+        const int mtile = tile_m(i >> 1, i & 1);
+        const int n0 = pair_nt(i >> 1) * p.BN;
         const uint32_t acc = (uint32_t)(2 * (i & 1) + ((i >> 1) & 1));
         const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
         // residual prefetch for item 0 (independent of the accumulator): hides the HBM latency behind the barrier wait
@@ -523,14 +564,25 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        if (PAIR)
+          mbar_arrive_cluster(leader_tmem_empty + 8u * acc);
+        else
+          mbar_arrive(&tmem_empty[acc]);
       }
     }
     if (tl != nullptr && threadIdx.x == 64) tl[12] = clock64();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (PAIR)
+    cluster_sync_all();        // the leader's MMAs read the peer's shared memory and both epilogues arrive on the leader's barriers
+  else
+    __syncthreads();
+  if (warp == 1) {
+    if (PAIR)
+      tmem_dealloc_pair(tmem_base, 512);
+    else
+      tmem_dealloc(tmem_base, 512);
+  }
   if (tl != nullptr && threadIdx.x == 32) {
     tl[13] = clock64();
     unsigned long long gt;
@@ -543,7 +595,8 @@ int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* 
                     const uint32_t* box);   // conv_tc.cu
 
 int init_conv_flat_attrs() {
-  cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_flat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_flat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(conv_flat_kernel) failed: %s", cudaGetErrorString(e));
     return YAD_ERR_CUDA;
@@ -567,20 +620,31 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   p.BN = cout_pad % 128 == 0 ? 128 : 64;
   p.n_ntiles = cout_pad / p.BN;
   p.MT = FL_ACC_COLS / p.BN;              // 2 streams x 2 accumulator stages x MT x BN = 512 TMEM columns
+  // CTA pairs (cluster of 2, tcgen05 cta_group::2): every MMA covers 128 rows of each CTA and takes half of the weight block's
+  // rows from each CTA's shared memory - half the B-operand reads and half the weight fill per SM (YAD_FLAT_PAIR=0: off)
+  static const bool pair_enabled = [] {
+    const char* e = getenv("YAD_FLAT_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  const int nsm = sm_count() > 0 ? sm_count() : 148;
+  // N = 64 stays single-CTA: measured (layer1 shape) 75 cycles per cta_group::2 MMA against 69 per cta_group::1 MMA - the A
+  // operand (4 KB per MMA either way) dominates there and the pair instruction costs more than the 1 KB of B it saves
+  const bool pair = pair_enabled && nsm >= 2 && p.BN == 128;
   const int rows_per_super = 128 * p.MT;
   const int patch_rows_raw = rows_per_super + max_off - p.min_off;
   p.patch_rows = (patch_rows_raw + FL_BOX_ROWS - 1) / FL_BOX_ROWS * FL_BOX_ROWS;
   p.patch_bytes = p.patch_rows * 128;
-  p.w_bytes = p.BN * 128;
+  p.w_bytes = (pair ? p.BN / 2 : p.BN) * 128;          // per CTA
   const int64_t n_mtiles = (p.F + rows_per_super - 1) / rows_per_super;
-  p.n_super = (int)(n_mtiles * p.n_ntiles);
+  const int tiles_per_pair = pair ? 4 : 2;             // two streams (x two CTAs)
+  p.n_super = (int)((n_mtiles + tiles_per_pair - 1) / tiles_per_pair * p.n_ntiles);     // tile pairs
   static const int dbg_flags = [] {           // timing experiments only (results are wrong with any bit set)
     const char* e = getenv("YAD_FLAT_DBG");
     return e ? atoi(e) : 0;
   }();
   p.flags = dbg_flags;
   p.tlog = g_flat_tlog;
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((pair ? 256 : 128) >> 4) << 24);
   // epilogue through the TMA unit: whole 64-channel blocks, one geometry for input, output and residual
   static const bool tma_epi_enabled = [] {
     const char* e = getenv("YAD_FLAT_TMA_EPI");
@@ -628,7 +692,7 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
   {
     const uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)cout_pad};
     const uint64_t strides[1] = {(uint64_t)k_total * 2};
-    const uint32_t box[2] = {64u, (uint32_t)p.BN};
+    const uint32_t box[2] = {64u, (uint32_t)(pair ? p.BN / 2 : p.BN)};
     int rc = encode_map_bf16(&map_w, weight, 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -657,13 +721,40 @@ static int launch_flat(FlatParams& p, int n_chunks_distinct, int max_off, const 
       if (rc) return rc;
     }
   }
-  const int nsm = sm_count() > 0 ? sm_count() : 148;
-  // a multiple of n_ntiles (the tiles of a CTA then share one N tile = one weight stream); n_super is one
-  int grid = (p.n_super < nsm ? p.n_super : nsm) / p.n_ntiles * p.n_ntiles;
-  if (grid < p.n_ntiles) grid = p.n_ntiles;
-  YAD_CUDA(launch_pdl(conv_flat_kernel, dim3((unsigned)grid), dim3(FL_THREADS), smem, (cudaStream_t)stream, map_a, map_a2, map_w, map_out, map_res, p, bias,
-                      reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<__nv_bfloat16*>(out),
-                      reinterpret_cast<__nv_bfloat16*>(out_s2d)));
+  const int units = pair ? nsm / 2 : nsm;
+  const int n_units = p.n_super < units ? p.n_super : units;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(pair ? 2 * n_units : n_units));
+  cfg.blockDim = dim3(FL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  {    // programmatic dependent launch: same policy as launch_pdl (common.cuh)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    int mode = pdl_mode();
+    if (mode == 1 && cudaStreamIsCapturing(cfg.stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) mode = 0;
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = mode ? 1 : 0;
+    ++na;
+  }
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  const __nv_bfloat16* res_p = reinterpret_cast<const __nv_bfloat16*>(residual);
+  __nv_bfloat16* out_p = reinterpret_cast<__nv_bfloat16*>(out);
+  __nv_bfloat16* s2d_p = reinterpret_cast<__nv_bfloat16*>(out_s2d);
+  if (pair)
+    YAD_CUDA(cudaLaunchKernelEx(&cfg, conv_flat_kernel<true>, map_a, map_a2, map_w, map_out, map_res, p, bias, res_p, out_p, s2d_p));
+  else
+    YAD_CUDA(cudaLaunchKernelEx(&cfg, conv_flat_kernel<false>, map_a, map_a2, map_w, map_out, map_res, p, bias, res_p, out_p, s2d_p));
   return YAD_OK;
 }
 
