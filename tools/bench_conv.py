@@ -63,6 +63,8 @@ def main():
             m = tv.mean(0).tolist()
             print(f"   MMA warp cycles (mean over CTAs, max total {tv[:, 0].max().item():.0f}): total {m[0]:.0f}  wait acc {m[1]:.0f}  "
                   f"wait patch {m[2]:.0f}  wait weights {m[3]:.0f}  issue block {m[4]:.0f}")
+            print(f"   epilogue thread cycles (mean over CTAs): wait accumulator {m[5]:.0f}  wait staging buffer {m[6]:.0f}  tcgen05.ld {m[7]:.0f}  "
+                  f"(epilogue lifetime {(tv[:, 12] - tv[:, 9]).mean():.0f})")
             ent = tv[:, 8:9]
             rel = (tv[:, 9:14] - ent)
             i = int(torch.argmax(rel[:, 4]))

@@ -43,6 +43,7 @@ constexpr int FL_SRC2 = 0x4000;
 constexpr int FL_NSTAGE = 3;        // epilogue staging buffers of [128 rows x 128 B]
 constexpr int FL_STAGE_BYTES = 128 * 128;
 constexpr int FL_EPI_THREADS = 256;
+constexpr int FL_EPI_WARPS = FL_EPI_THREADS / 32;
 constexpr int FL_MAX_STEPS = 64;
 constexpr int FL_MAX_RING = 8;      // weight ring slots
 constexpr int FL_MAX_NA = 4;        // patch slots per stream
@@ -64,6 +65,7 @@ struct FlatParams {
   int32_t flags;                // bit 4: fine timeline of the MMA warps (with tlog)
   int32_t tma_epi;              // 1: residual / output tiles move through the TMA unit and the staging buffers (needs Cout % 64 == 0,
                                 // same pitches in and out); 0: register-sourced global accesses
+  uint32_t hp_mul, hp_sh, wp_mul, wp_sh;   // f / Hp and col / Wp as multiply-high (exact for f < 2^31): (f * mul) >> sh
   int32_t s2d_Hp, s2d_Wp;       // second, space-to-depth copy of the output (0: none): pixel (b, h, w) goes to flat cell
                                 // (b * s2d_Wp + w / 2) * s2d_Hp + h / 2, channel plane (h & 1) * 2 + (w & 1) of 4 * Cout channels
   uint32_t step_mma[FL_MAX_STEPS];    // MMA warp: bits 0..15 = first patch row of the tap in 16-byte units, bit 30 = first
@@ -78,6 +80,13 @@ struct FlatParams {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// exact n / d for n < 2^31 with host-computed (mul, sh) = (ceil(2^(31 + s) / d), 31 + s), 2^s >= d
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t sh) { return (uint32_t)(((uint64_t)n * mul) >> sh); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
 // K-major SWIZZLE_128B shared-memory descriptor = (FL_DESC_HI << 32) | lo, lo = (address >> 4) | LBO field (1 << 16);
@@ -220,11 +229,11 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], PAIR ? 2 * FL_EPI_THREADS : FL_EPI_THREADS);     // the leader's barrier counts both epilogues
+      mbar_init(&tmem_empty[s], PAIR ? 2 * FL_EPI_WARPS : FL_EPI_WARPS);     // one arrival per epilogue warp (of both CTAs)
     }
     for (int s = 0; s < FL_NSTAGE; ++s) {
       mbar_init(&buf_ready[s], 1);
-      mbar_init(&out_full[s], FL_EPI_THREADS);
+      mbar_init(&out_full[s], FL_EPI_WARPS);     // one arrival per warp: 256 arrivals on one mbarrier serialise (~500 cycles)
     }
     if (p.tma_epi) {
       prefetch_tmap(&map_out);
@@ -391,37 +400,47 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int chunks_per_acc = p.BN >> 6;            // 32-column chunks handled by this warp per accumulator (1 or 2)
     const int n_items = p.MT * chunks_per_acc;       // work items per tile: (mt, chunk)
     const uint32_t Hp = (uint32_t)p.Hp, Wp = (uint32_t)p.Wp;
+    const int cpa_sh = chunks_per_acc >> 1;          // chunks_per_acc is 1 or 2
+    const uint32_t s_bias_addr = smem_u32(s_bias);
     if (p.tma_epi) {
       // ---- tiles through the staging buffers (see the header): item = (mt, 64-channel block) = one [128 x 64] tile that the 8
       //      warps fill together; thread = (pixel row r, channel half): four 16-byte chunks of its row, swizzled like the TMA image
       uint32_t sb = 0, sb_phase = 0;
       const uint32_t row_off = (uint32_t)r * 128u, rx = (uint32_t)r & 7u;
+      const bool etl = tl != nullptr && (p.flags & 16) && threadIdx.x == 64;     // fine timeline of one epilogue thread
+      long long e_full = 0, e_buf = 0, e_ld = 0, e0 = 0;
       for (int i = 0; i < 2 * n_my; ++i) {
         const int mtile = tile_m(i >> 1, i & 1);
         const int n0 = pair_nt(i >> 1) * p.BN;
         const uint32_t acc = (uint32_t)(2 * (i & 1) + ((i >> 1) & 1));      // accumulator (stream, stage) = barrier index
         const uint32_t fbase = (uint32_t)mtile * (uint32_t)rows_per_super + (uint32_t)r;
+        if (etl) e0 = clock64();
         mbar_wait(&tmem_full[acc], (uint32_t)(i >> 2) & 1u);
         tc_fence_after();
+        if (etl) e_full += clock64() - e0;
         for (int j = 0; j < n_items; ++j) {
-          const int mt = j / chunks_per_acc, cj = j - mt * chunks_per_acc;
+          const int mt = j >> cpa_sh, cj = j & (chunks_per_acc - 1);
           const int c0 = 32 * (2 * cj + half);
           const uint32_t f = fbase + 128u * (uint32_t)mt;
-          const uint32_t col = f / Hp, h = f - col * Hp, bb = col / Wp, w = col - bb * Wp;
+          const uint32_t col = fast_div(f, p.hp_mul, p.hp_sh), h = f - col * Hp, bb = fast_div(col, p.wp_mul, p.wp_sh), w = col - bb * Wp;
           const bool ok = (int64_t)f < p.F && h < (uint32_t)p.H && w < (uint32_t)p.W;
           const int nbase = n0 + c0;
           uint32_t v[32];
+          if (etl) e0 = clock64();
           tmem_ld32(((uint32_t)(q * 32) << 16) + acc * FL_ACC_COLS + (uint32_t)(mt * p.BN + c0), v);
           tmem_ld_wait();
+          if (etl) e_ld += clock64() - e0;
           uint8_t* S = sm_o + sb * FL_STAGE_BYTES + row_off;
+          if (etl) e0 = clock64();
           mbar_wait(&buf_ready[sb], sb_phase);       // the buffer is free and (if any) the residual tile has landed in it
+          if (etl) e_buf += clock64() - e0;
           uint4 pk[4];
           if (ok) {
             float x[32];
-            const float4* bp = reinterpret_cast<const float4*>(s_bias + nbase);
+            const uint32_t bp = s_bias_addr + (uint32_t)nbase * 4u;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b4 = bp[j4];
+              const float4 b4 = lds_f4(bp + 16u * j4);
               x[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + b4.x;
               x[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + b4.y;
               x[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + b4.z;
@@ -465,14 +484,23 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<uint4*>(S + ((((uint32_t)(4 * half + j4)) ^ rx) << 4)) = pk[j4];
           fence_proxy_async();               // generic-proxy writes -> visible to the bulk store
-          mbar_arrive(&out_full[sb]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_full[sb]);
           if (++sb == FL_NSTAGE) { sb = 0; sb_phase ^= 1; }
         }
         tc_fence_before();
-        if (PAIR)
-          mbar_arrive_cluster(leader_tmem_empty + 8u * acc);
-        else
-          mbar_arrive(&tmem_empty[acc]);
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR)
+            mbar_arrive_cluster(leader_tmem_empty + 8u * acc);
+          else
+            mbar_arrive(&tmem_empty[acc]);
+        }
+      }
+      if (etl) {
+        tl[5] = e_full;
+        tl[6] = e_buf;
+        tl[7] = e_ld;
       }
     } else {
       for (int i = 0; i < 2 * n_my; ++i) {
@@ -564,10 +592,13 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tc_fence_before();
-        if (PAIR)
-          mbar_arrive_cluster(leader_tmem_empty + 8u * acc);
-        else
-          mbar_arrive(&tmem_empty[acc]);
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR)
+            mbar_arrive_cluster(leader_tmem_empty + 8u * acc);
+          else
+            mbar_arrive(&tmem_empty[acc]);
+        }
       }
     }
     if (tl != nullptr && threadIdx.x == 64) tl[12] = clock64();
@@ -781,6 +812,16 @@ static int check_flat_common(const yad_flat_desc* d, const void* in, const void*
   p.Hpo = Hpo;
   p.Wpo = Wpo;
   p.remap = (Hpo != d->Hp || Wpo != d->Wp) ? 1 : 0;
+  {
+    auto magic = [](uint32_t dv, uint32_t& mul, uint32_t& sh) {
+      uint32_t sft = 0;
+      while ((1u << sft) < dv) ++sft;
+      sh = 31 + sft;
+      mul = (uint32_t)((((uint64_t)1 << sh) + dv - 1) / dv);
+    };
+    magic((uint32_t)d->Hp, p.hp_mul, p.hp_sh);
+    magic((uint32_t)d->Wp, p.wp_mul, p.wp_sh);
+  }
   p.F = (int64_t)d->B * d->Wp * d->Hp;
   YAD_CHECK_ARG(p.F < (int64_t)1 << 31 && (int64_t)d->B * Wpo * Hpo < (int64_t)1 << 31, "yad_conv_flat: tensor too large");
   p.Cout = d->Cout;
