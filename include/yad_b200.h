@@ -270,8 +270,8 @@ int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* c
  *   fmap_k[i]           Hp * C of map i (channels of one (b, w) column incl. the zero halo row: the H-mean is folded into K)
  *   fmap_rows_per_clip  Wp of map i
  *   wblob [wrows, 64]   bf16 weight blocks ([N x 64] per K block, stacked), bias [n_bias] f32
- *   ops / kbs           the program (n_ops x 16 int32, n_kb x 2 int32; layouts in csrc/neck_fused.cu), device memory
- *   pool_bytes, n_slots shared-memory plan: activation pool size and ring depth (16 KB slots)
+ *   ops / kbs           the program (n_ops x 20 int32, n_kb x 2 int32; layouts in csrc/neck_fused.cu), device memory
+ *   pool_bytes, n_slots shared-memory plan: activation pool size and ring depth (16 KB slots, 3..8)
  *   heads[3]            fp32 outputs [B, head_W[i], head_ld] (sm, md, lg), first 3 * (3 + nc) channels valid
  *   dbg                 optional bf16 buffer for the program's DUMP ops (NULL in production) */
 int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_t* fmap_rows_per_clip, int64_t B,
@@ -287,9 +287,11 @@ int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_
 int yad_resample_sinc(const void* x, int32_t x_is_i16, int64_t B, int64_t L, int32_t O, int32_t P, int32_t width,
                       const float* kernel, float* out, int64_t Lout, yad_stream_t stream);
 
-/* Debug aid of yad_neck_fused: dev_buf (4 * n_ops int64, device) receives CTA 0's per-op clock64 stamps of its first clip on the
- * following launches (tools/neck_timeline.py); NULL switches it off (the default). */
+/* Debug aid of yad_neck_fused: dev_buf (8 * n_ops int64, device, zeroed by the caller) receives CTA 0's per-op clock64 stamps of
+ * one of its clips on the following launches (tools/neck_timeline.py); NULL switches it off (the default).
+ * yad_neck_fused_set_timeline_iter: which clip of CTA 0 (0 = its first: cold; 1 = its second: steady state, maps prefetched). */
 int yad_neck_fused_set_timeline(void* dev_buf);
+int yad_neck_fused_set_timeline_iter(int32_t iter);
 
 /* ------------------------------------------------------------------ neck glue (NHWC, dtype f32|bf16)
  * adaptive_avg_pool2d(H->1) modules/_common.py:248-252; F.interpolate bilinear x2 / x0.5

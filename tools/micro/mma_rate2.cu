@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(320, 1) mma_rate2_kernel(int BN, int mode, int
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 96 * 1024);
-    const int MT = 256 / BN;                 // accumulators per group (as conv_flat: MT x BN = 256 columns)
+    const int MT = grp > 0 ? grp : 256 / BN; // accumulators per group (default as conv_flat: MT x BN = 256 columns)
     long long t0 = clock64();
     uint32_t slot = 0;
     for (int it = 0; it < iters; ++it) {
@@ -100,14 +100,17 @@ int main() {
   cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 4000;
   printf("   N  mode   cycles/MMA   ideal\n");
-  for (int BN : {64, 128})
+  for (int grp : {0, 1, 2})
+  for (int BN : {16, 64, 128})
     for (int mode : {0, 1, 2, 3, 4, 7, 12, 15, 31}) {
-      mma_rate2_kernel<<<148, 320, 180 * 1024>>>(BN, mode, 0, iters, d);
+      if (grp > 0 && mode > 3) continue;
+      if (grp == 0 && BN == 16) continue;
+      mma_rate2_kernel<<<148, 320, 180 * 1024>>>(BN, mode, grp, iters, d);
       cudaError_t e = cudaDeviceSynchronize();
       long long c = 0;
       cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
-      const int per_it = (256 / BN) * 4;
-      printf("%4d %5d   %10.1f   %5d   %s\n", BN, mode, (double)c / ((double)iters * per_it), BN == 64 ? 48 : 64,
+      const int per_it = (grp > 0 ? grp : 256 / BN) * 4;
+      printf("grp %d %4d %5d   %10.1f   %5d   %s\n", grp, BN, mode, (double)c / ((double)iters * per_it), BN == 64 ? 48 : 64,
              e == cudaSuccess ? "" : cudaGetErrorString(e));
     }
   return 0;

@@ -65,6 +65,7 @@ SIGNATURES = {
     "yad_neck_fused": [C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), _i64, _p, _i64, _p, _i32, _p, _i32, _p, _i32, _i32, _i32,
                        C.POINTER(_p), C.POINTER(_i32), _i32, _p, _p],
     "yad_neck_fused_set_timeline": [_p],
+    "yad_neck_fused_set_timeline_iter": [_i32],
     "yad_conv_flat_set_timeline": [_p],
     "yad_sppf_pools": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_conv_stem_fused": [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _i32, _i32, _i32, _p],

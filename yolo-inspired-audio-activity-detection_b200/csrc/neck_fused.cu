@@ -34,6 +34,8 @@ constexpr int NK_SLOT = 16384;    // ring slot: 128 rows x 128 B
 constexpr int NK_MAX_SLOTS = 8;
 constexpr int NK_MAX_MT = 4;
 constexpr int NK_TMEM_COLS = 256;
+constexpr int NK_TL = 8;          // timeline stamps per op (yad_neck_fused_set_timeline)
+constexpr int NK_MAX_KG = 8;      // K blocks per ring slot (N = 16: 8 x 2 KB)
 
 enum { NK_CONV = 0, NK_POOLS = 1, NK_PAIRAVG = 2, NK_UP2 = 3, NK_DEINT = 4, NK_DUMP = 5 };
 
@@ -41,26 +43,33 @@ enum { NK_CONV = 0, NK_POOLS = 1, NK_PAIRAVG = 2, NK_UP2 = 3, NK_DEINT = 4, NK_D
 //   CONV   : 1 n_mt, 2 N, 3 kb_first, 4 kb_count, 5 R, 6 Wp, 7 W, 8 bias_off, 9 out_plane0, 10 out_plane1, 11 head (-1: none),
 //            12 flags (bit j: output plane j is written PAIR-AVERAGED, out[k] = (y[2k] + y[2k+1]) / 2 of the bf16-rounded rows,
 //            at the next level's geometry W / 2 - the bilinear x0.5 of BiC's conv_c0 branch folded into the epilogue),
-//            13 wrow, 14 src_global (-1: planes in smem, else input map 0..3), 15 act
+//            (bit 8: DE-INTERLEAVED output for the stride-2 conv that follows: row w of clip c goes to row c * (W / 2 + 1) + w / 2
+//            of plane out_plane0 (w even) or out_plane1 (w odd) - the even / odd split folded into the epilogue),
+//            13 wrow, 14 src_global (-1: planes in smem, else input map 0..3), 15 act,
+//            16 kg = K blocks per weight-ring slot (kg * N <= 128 rows), 17..19 unused
 //   POOLS  : 1 in, 2 out1, 3 out2, 4 out3, 5 R, 6 Wp, 7 W
 //   PAIRAVG: 1 in, 2 out, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in            (out[k] = (in[2k] + in[2k+1]) / 2)
 //   UP2    : 1 in, 2 out, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in            (bilinear x2, align_corners = False)
 //   DEINT  : 1 in, 2 out_even, 3 out_odd, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in
 //   DUMP   : 1 plane, 2 rows, 3 destination offset (bf16 elements) in the debug buffer, 4 per-clip stride (elements)
+constexpr int NK_OP_WORDS = 20;
 struct NkOp {
-  int32_t v[16];
+  int32_t v[NK_OP_WORDS];
 };
 struct NkKb {
-  int32_t src;     // plane byte offset (smem-sourced conv) or 64-channel chunk index of the input map (global-sourced conv)
-  int32_t shift;   // row shift of the tap (-1, 0, +1)
+  int32_t src;     // smem-sourced conv: (plane byte offset + (1 + tap shift) * 128) >> 4 = what the tap adds to the low descriptor
+                   // word; global-sourced conv: 64-channel chunk index of the input map
+  int32_t pad;
 };
 
 struct NkParams {
-  long long* tlog;     // debug timeline (yad_neck_fused_set_timeline): CTA 0 records clock64 per op, 4 stamps each; NULL in production
+  long long* tlog;     // debug timeline (yad_neck_fused_set_timeline): CTA 0 records clock64 per op, NK_TL stamps each; NULL in production
   int32_t n_ops, n_kb, n_clips, n_slots;
   int32_t pool_bytes, n_bias;
   int32_t head_W[3];
   int32_t head_ld;
+  int32_t a_bytes[4];  // bytes of one A box of input map i (rows of one clip, rounded up to 8, at most 128, x 128 B)
+  int32_t tl_iter;     // timeline: which of CTA 0's clips is recorded (0 = first: cold, nothing prefetched; 1 = steady state)
 };
 
 __device__ __forceinline__ void nk_mbar_arrive(uint64_t* bar) {
@@ -73,6 +82,9 @@ constexpr uint32_t NK_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint64_t nk_desc(uint32_t smem_addr) {
   return ((uint64_t)NK_DESC_HI << 32) | (uint64_t)(((smem_addr & 0x3FFFFu) >> 4) | (1u << 16));
 }
+
+// the same from a precomputed low word ((address >> 4) | 1 << 16): adding 8 per row, 2 per 16 K elements needs no re-masking
+__device__ __forceinline__ uint64_t nk_desc64(uint32_t lo) { return ((uint64_t)NK_DESC_HI << 32) | (uint64_t)lo; }
 
 // 16-byte chunk j (8 channels) of row s of a plane
 __device__ __forceinline__ uint4* nk_chunk(uint8_t* plane, int s, int j) {
@@ -117,7 +129,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // the program, the K-block list and the biases are launch constants (written once at pack time): loaded before pdl_wait
-  for (int i = threadIdx.x; i < p.n_ops * 16; i += NK_THREADS) reinterpret_cast<int32_t*>(s_ops)[i] = reinterpret_cast<const int32_t*>(g_ops)[i];
+  for (int i = threadIdx.x; i < p.n_ops * NK_OP_WORDS; i += NK_THREADS) reinterpret_cast<int32_t*>(s_ops)[i] = reinterpret_cast<const int32_t*>(g_ops)[i];
   for (int i = threadIdx.x; i < p.n_kb * 2; i += NK_THREADS) reinterpret_cast<int32_t*>(s_kbs)[i] = reinterpret_cast<const int32_t*>(g_kbs)[i];
   for (int i = threadIdx.x; i < p.n_bias; i += NK_THREADS) s_bias[i] = g_bias[i];
   if (warp == 0 && lane == 0) {
@@ -152,37 +164,62 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         for (int oi = 0; oi < p.n_ops; ++oi) {
           const NkOp& op = s_ops[oi];
           if (op.v[0] != NK_CONV) continue;
-          const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], R = op.v[5], srcg = op.v[14];
+          const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], R = op.v[5], srcg = op.v[14], kg = op.v[16];
           const CUtensorMap* mw = N == 16 ? &map_w16 : (N == 64 ? &map_w64 : &map_w128);
-          const CUtensorMap* ma = srcg == 0 ? &map_in0 : (srcg == 1 ? &map_in1 : (srcg == 2 ? &map_in2 : &map_in3));
-          for (int k = 0; k < nkb; ++k) {
-            if (srcg >= 0) {
+          if (srcg >= 0) {
+            const CUtensorMap* ma = srcg == 0 ? &map_in0 : (srcg == 1 ? &map_in1 : (srcg == 2 ? &map_in2 : &map_in3));
+            const uint32_t a_bytes = (uint32_t)p.a_bytes[srcg];
+            for (int k = 0; k < nkb; ++k) {
               const int c0 = s_kbs[kb0 + k].src * 64;
               for (int mt = 0; mt < n_mt; ++mt) {
                 mbar_wait(&empty_bar[slot], phase ^ 1);
-                mbar_expect_tx(&full_bar[slot], NK_SLOT);
+                mbar_expect_tx(&full_bar[slot], a_bytes);
                 tma_load_2d(ma, &full_bar[slot], ring + (size_t)slot * NK_SLOT, c0, clip * R + 128 * mt);
                 if (++slot == (uint32_t)p.n_slots) { slot = 0; phase ^= 1; }
               }
+              mbar_wait(&empty_bar[slot], phase ^ 1);
+              mbar_expect_tx(&full_bar[slot], (uint32_t)N * 128u);
+              tma_load_2d(mw, &full_bar[slot], ring + (size_t)slot * NK_SLOT, 0, op.v[13] + k * N);
+              if (++slot == (uint32_t)p.n_slots) { slot = 0; phase ^= 1; }
             }
-            mbar_wait(&empty_bar[slot], phase ^ 1);
-            mbar_expect_tx(&full_bar[slot], (uint32_t)N * 128u);
-            tma_load_2d(mw, &full_bar[slot], ring + (size_t)slot * NK_SLOT, 0, op.v[13] + k * N);
-            if (++slot == (uint32_t)p.n_slots) { slot = 0; phase ^= 1; }
+          } else {
+            // smem-sourced conv: kg consecutive weight blocks share one ring slot (one barrier)
+            for (int k0 = 0; k0 < nkb; k0 += kg) {
+              const int cnt = nkb - k0 < kg ? nkb - k0 : kg;
+              mbar_wait(&empty_bar[slot], phase ^ 1);
+              mbar_expect_tx(&full_bar[slot], (uint32_t)(cnt * N) * 128u);
+              for (int j = 0; j < cnt; ++j)
+                tma_load_2d(mw, &full_bar[slot], ring + (size_t)slot * NK_SLOT + (size_t)(j * N) * 128, 0, op.v[13] + (k0 + j) * N);
+              if (++slot == (uint32_t)p.n_slots) { slot = 0; phase ^= 1; }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (whole warp walks, one lane issues)
+    // The tensor pipe queues only ONE MMA behind the executing one (conv_flat.cu) and a lone thread retires an instruction
+    // every 5 - 10 cycles, so whatever this warp does between two MMAs - barrier poll, fence, election, table load, descriptor
+    // moves, commit - is idle pipe time; the first version of this kernel (descriptors built with shift / mask / or per MMA,
+    // one visit per K block) paid ~580 cycles per K block for 160 - 256 cycles of MMA.  Now (a) descriptor low words are sums
+    // of precomputed terms (the host table carries the tap's share, see NkKb) and (b) kg K blocks share one ring slot = one
+    // visit (poll, fence, election, commit) per 4 * kg MMAs: 280 (N = 16) / 480 (N = 64) / 600 (N = 128) cycles per K block.
+    // Measured in round 2 and dropped (profiles/r02_neck_timeline_*.txt): a second issuing warp taking alternate slots into a
+    // second accumulator set (the per-MMA issue cost, not the visit, dominates; the epilogue pays for the extra TMEM loads);
+    // releasing the ring slots of a whole convolution in one burst of commits; visits of up to 4 slots / 8 K blocks, rolled
+    // or unrolled (more bookkeeping per MMA than they save per visit); one polling lane per waiting epilogue warp; L2
+    // prefetch of the next clip's maps by the producer (a prefetch occupies the TMA unit as long as the load it saves).
     uint32_t slot = 0, phase = 0, done_phase = 0;
     bool first_conv = true;
-    const uint32_t base_addr = smem_u32(base), ring_addr = smem_u32(ring);
-    for (int clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+    const uint32_t plane_lo = (smem_u32(base) >> 4) | (1u << 16);       // + NkKb.src + 1024 * mt + 2 * kk
+    const uint32_t ring_lo = (smem_u32(ring) >> 4) | (1u << 16);        // + 1024 * slot + 8 * N * j + 2 * kk
+    const uint32_t n_slots = (uint32_t)p.n_slots;
+    int iter = 0;
+    for (int clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x, ++iter) {
       for (int oi = 0; oi < p.n_ops; ++oi) {
         const NkOp& op = s_ops[oi];
         if (op.v[0] == NK_CONV) {
-          // Everything before this convolution is complete: the 128 epilogue threads arrive on op_done at the end of the op
+          // Everything before this convolution is complete: the epilogue warps arrive on op_done at the end of the op
           // that PRECEDES a convolution (and of the program's last op), i.e. once per convolution - planes written and fenced
           // for the async proxy, accumulator drained.  One phase per convolution: the epilogue cannot get a phase ahead,
           // because it next waits for this convolution's accumulator.
@@ -192,51 +229,75 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             tc_fence_after();
           }
           first_conv = false;
-          if (p.tlog != nullptr && blockIdx.x == 0 && lane == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 0] = clock64();
-          const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], srcg = op.v[14];
+          const bool tl = p.tlog != nullptr && blockIdx.x == 0 && lane == 0 && iter == p.tl_iter;
+          if (tl) p.tlog[oi * NK_TL + 0] = clock64();
+          const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], srcg = op.v[14], kg = op.v[16];
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-          for (int k = 0; k < nkb; ++k) {
-            uint32_t a_addr[NK_MAX_MT], a_slot[NK_MAX_MT];
-            if (srcg >= 0) {
+          uint32_t acc = 0u;
+          if (srcg >= 0) {
+            for (int k = 0; k < nkb; ++k) {
+              uint32_t a_slot[NK_MAX_MT];
 #pragma unroll
               for (int mt = 0; mt < NK_MAX_MT; ++mt) {
                 if (mt < n_mt) {
                   mbar_wait(&full_bar[slot], phase);
                   a_slot[mt] = slot;
-                  a_addr[mt] = ring_addr + slot * NK_SLOT;
-                  if (++slot == (uint32_t)p.n_slots) { slot = 0; phase ^= 1; }
+                  if (++slot == n_slots) { slot = 0; phase ^= 1; }
                 }
               }
-            } else {
-              const NkKb kb = s_kbs[kb0 + k];
+              mbar_wait(&full_bar[slot], phase);
+              const uint32_t w_slot = slot, b_lo = ring_lo + slot * (NK_SLOT >> 4);
+              if (++slot == n_slots) { slot = 0; phase ^= 1; }
+              tc_fence_after();
+              if (elect_one()) {
 #pragma unroll
-              for (int mt = 0; mt < NK_MAX_MT; ++mt) a_addr[mt] = base_addr + (uint32_t)kb.src + (uint32_t)((1 + kb.shift + 128 * mt) * 128);
-            }
-            mbar_wait(&full_bar[slot], phase);
-            const uint32_t w_slot = slot, b_addr = ring_addr + slot * NK_SLOT;
-            if (++slot == (uint32_t)p.n_slots) { slot = 0; phase ^= 1; }
-            tc_fence_after();
-            if (elect_one()) {
+                for (int mt = 0; mt < NK_MAX_MT; ++mt) {
+                  if (mt < n_mt) {
+                    const uint32_t a_lo = ring_lo + a_slot[mt] * (NK_SLOT >> 4);
 #pragma unroll
-              for (int mt = 0; mt < NK_MAX_MT; ++mt) {
-                if (mt < n_mt) {
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem_base + (uint32_t)(mt * N), nk_desc(a_addr[mt] + 32 * kk), nk_desc(b_addr + 32 * kk), idesc,
-                              (k > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk)
+                      umma_bf16(tmem_base + (uint32_t)(mt * N), nk_desc64(a_lo + 2 * kk), nk_desc64(b_lo + 2 * kk), idesc,
+                                kk > 0 ? 1u : acc);
+                  }
                 }
-              }
-              if (srcg >= 0) {
 #pragma unroll
                 for (int mt = 0; mt < NK_MAX_MT; ++mt)
                   if (mt < n_mt) umma_commit(&empty_bar[a_slot[mt]]);
+                umma_commit(&empty_bar[w_slot]);
+                if (k == nkb - 1) umma_commit(acc_full);
               }
-              umma_commit(&empty_bar[w_slot]);
-              if (k == nkb - 1) umma_commit(acc_full);
+              acc = 1u;
+              __syncwarp();
             }
-            __syncwarp();
+          } else {
+            const uint32_t n_units = (uint32_t)N * 8u;                  // one weight block = N rows x 128 B, in 16-byte units
+            for (int k0 = 0; k0 < nkb; k0 += kg) {
+              const int cnt = nkb - k0 < kg ? nkb - k0 : kg;
+              mbar_wait(&full_bar[slot], phase);
+              tc_fence_after();
+              if (elect_one()) {
+                uint32_t b_lo = ring_lo + slot * (NK_SLOT >> 4);
+                for (int j = 0; j < cnt; ++j) {
+                  uint32_t a_lo = plane_lo + (uint32_t)s_kbs[kb0 + k0 + j].src;
+                  for (int mt = 0; mt < n_mt; ++mt) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                      umma_bf16(tmem_base + (uint32_t)(mt * N), nk_desc64(a_lo + 2 * kk), nk_desc64(b_lo + 2 * kk), idesc,
+                                kk > 0 ? 1u : acc);
+                    a_lo += 1024u;                                      // next M tile: 128 rows x 128 B
+                  }
+                  acc = 1u;
+                  b_lo += n_units;
+                }
+                umma_commit(&empty_bar[slot]);
+                if (k0 + cnt == nkb) umma_commit(acc_full);
+              }
+              acc = 1u;
+              __syncwarp();
+              if (++slot == n_slots) { slot = 0; phase ^= 1; }
+            }
           }
-          if (p.tlog != nullptr && blockIdx.x == 0 && lane == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 1] = clock64();
+          if (tl) p.tlog[oi * NK_TL + 1] = clock64();
         }
       }
     }
@@ -246,7 +307,9 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     const int half = (warp - 2) >> 2;     // which 32-column blocks of an accumulator this warp converts (b & 1 == half)
     const int te = threadIdx.x - 64;      // 0..255
     uint32_t acc_phase = 0;
-    for (int clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+    int iter = 0;
+    for (int clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x, ++iter) {
+      const bool tle = p.tlog != nullptr && blockIdx.x == 0 && iter == p.tl_iter;
       for (int oi = 0; oi < p.n_ops; ++oi) {
         const NkOp& op = s_ops[oi];
         nk_bar_sync(1, NK_EPI);           // the previous op's planes are complete (and no thread still reads what this op overwrites)
@@ -259,7 +322,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           mbar_wait(acc_full, acc_phase);
           acc_phase ^= 1;
           tc_fence_after();
-          if (p.tlog != nullptr && blockIdx.x == 0 && te == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 2] = clock64();
+          if (tle && te == 0) p.tlog[oi * NK_TL + 2] = clock64();
           const int nb = (N + 31) >> 5;   // 32-column blocks (N = 16: one block, upper 16 columns unused)
           for (int mt = 0; mt < n_mt; ++mt) {
             const int r = 128 * mt + q * 32 + lane, s = r + 1;
@@ -315,6 +378,30 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
                   uint4 pk = nk_pack(av);
                   if (!valid) pk = make_uint4(0u, 0u, 0u, 0u);          // w = W (even): the halo cell of the half-width plane
                   if (in_plane && !(r & 1)) *nk_chunk(plane, (r >> 1) + 1, hb + i4) = pk;
+                }
+              } else if (op.v[12] & 256) {
+                // de-interleaved output (N <= 64: one 64-channel block) in front of a stride-2 conv: even columns to out_plane0,
+                // odd ones to out_plane1, both at the next level's geometry W / 2 (+ halo); the halo cell w = W (W even) lands
+                // on the halo cell of the even plane, the same thread zeroes the one of the odd plane
+                if (in_plane) {
+                  const int so = c * ((W >> 1) + 1) + (w >> 1) + 1;
+                  uint8_t* pe = base + op.v[9];
+                  uint8_t* po = base + op.v[10];
+                  uint8_t* plane = (w & 1) ? po : pe;
+#pragma unroll
+                  for (int i4 = 0; i4 < 4; ++i4) {
+                    uint4 pk = nk_pack(x + 8 * i4);
+                    if (!valid) pk = make_uint4(0u, 0u, 0u, 0u);
+                    *nk_chunk(plane, so, hb + i4) = pk;
+                    if (!valid) *nk_chunk(po, so, hb + i4) = pk;
+                  }
+                  if (N == 16) {
+#pragma unroll
+                    for (int i4 = 4; i4 < 8; ++i4) {
+                      *nk_chunk(plane, so, i4) = make_uint4(0u, 0u, 0u, 0u);
+                      if (!valid) *nk_chunk(po, so, i4) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                  }
                 }
               } else if (pj >= 0 && in_plane) {
                 uint8_t* plane = base + pj;
@@ -421,11 +508,15 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
             }
           }
         }
-        if (p.tlog != nullptr && blockIdx.x == 0 && te == 0 && clip == (int)blockIdx.x) p.tlog[oi * 4 + 3] = clock64();
+        if (tle && te == 0) p.tlog[oi * NK_TL + 3] = clock64();
         if (oi == p.n_ops - 1 || s_ops[oi + 1].v[0] == NK_CONV) {
           fence_proxy_async();   // this thread's plane writes (this op and the element-wise ops before it) become visible to the
           __syncwarp();          // tensor core (async proxy); one arrival per warp (256 arrivals on one mbarrier cost ~500 cycles)
           if (lane == 0) nk_mbar_arrive(op_done);
+          if (tle && lane == 0) {
+            if (te == 0) p.tlog[oi * NK_TL + 4] = clock64();                                                  // warp 2 arrived
+            atomicMax(reinterpret_cast<unsigned long long*>(p.tlog + oi * NK_TL + 5), (unsigned long long)clock64());   // last warp arrived
+          }
         }
       }
     }
@@ -450,10 +541,16 @@ int init_neck_fused_attrs() {
 }  // namespace yad
 
 static long long* g_nk_tlog = nullptr;
+static int g_nk_tl_iter = 0;
 /* debug: device buffer of 4 * n_ops int64 that the next launches fill with CTA 0's per-op clock64 stamps of its first clip
  * (MMA warp: start of the op after its dependencies, last MMA issued; epilogue: accumulator complete, op done); NULL switches it off */
 extern "C" int yad_neck_fused_set_timeline(void* dev_buf) {
   g_nk_tlog = reinterpret_cast<long long*>(dev_buf);
+  return YAD_OK;
+}
+/* which of CTA 0's clips the timeline records: 0 = its first (cold: nothing prefetched), 1 = its second (steady state), ... */
+extern "C" int yad_neck_fused_set_timeline_iter(int32_t iter) {
+  g_nk_tl_iter = iter;
   return YAD_OK;
 }
 
@@ -472,13 +569,17 @@ extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, c
                       (size_t)n_bias * 4 + 8 + (2 * NK_MAX_SLOTS + 2) * 8 + 16;
   YAD_CHECK_ARG(smem <= 227 * 1024, "yad_neck_fused: %zu bytes of shared memory needed", smem);
   CUtensorMap mi[4], mw[3];
+  uint32_t a_rows[4];
   for (int i = 0; i < 4; ++i) {
     YAD_CHECK_ARG(fmaps[i] && fmap_k[i] % 64 == 0 && fmap_k[i] >= 64 && fmap_rows_per_clip[i] >= 1 &&
                       reinterpret_cast<uintptr_t>(fmaps[i]) % 16 == 0,
                   "yad_neck_fused: bad feature map %d", i);
     const uint64_t dims[2] = {(uint64_t)fmap_k[i], (uint64_t)B * (uint64_t)fmap_rows_per_clip[i]};
     const uint64_t strides[1] = {(uint64_t)fmap_k[i] * 2};
-    const uint32_t box[2] = {64u, 128u};
+    // one clip's rows (rounded up to 8) when they fit one M tile: rows past the box keep stale shared-memory contents, which
+    // only reach accumulator rows >= R that no epilogue reads
+    a_rows[i] = fmap_rows_per_clip[i] <= 128 ? (uint32_t)((fmap_rows_per_clip[i] + 7) / 8 * 8) : 128u;
+    const uint32_t box[2] = {64u, a_rows[i]};
     int rc = encode_map_bf16(&mi[i], fmaps[i], 2, dims, strides, box);
     if (rc) return rc;
   }
@@ -500,6 +601,8 @@ extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, c
   p.n_bias = n_bias;
   for (int i = 0; i < 3; ++i) p.head_W[i] = head_W[i];
   p.head_ld = head_ld;
+  for (int i = 0; i < 4; ++i) p.a_bytes[i] = (int32_t)(a_rows[i] * 128u);
+  p.tl_iter = g_nk_tl_iter;
   const int nsm = sm_count() > 0 ? sm_count() : 148;
   const unsigned grid = (unsigned)(B < nsm ? B : nsm);
   YAD_CUDA(launch_pdl(neck_fused_kernel, dim3(grid), dim3(NK_THREADS), smem, (cudaStream_t)stream, mi[0], mi[1], mi[2], mi[3], mw[0], mw[1],

@@ -89,7 +89,7 @@ class FusedNeck:
                 raise NotImplementedError("fused neck: clip too long (more than 4 M tiles per level)")
         self.pool = _Pool()
         self.ops: List[List[int]] = []
-        self.kbs: List[Tuple[int, int]] = []
+        self.kbs: List[Tuple[int, int, bool]] = []             # (plane / chunk, tap shift, global-sourced)
         self.wblocks: List[torch.Tensor] = []
         self.wrows = 0
         self.biases: List[torch.Tensor] = []
@@ -116,26 +116,33 @@ class FusedNeck:
     def _free(self, tok: int) -> None:
         self.pool.free(tok, len(self.ops))
 
-    def _conv(self, cvs, level: int, kblocks, outs: List[int], head: int = -1, src_global: int = -1, pair: Sequence[bool] = ()):
+    def _conv(self, cvs, level: int, kblocks, outs: List[int], head: int = -1, src_global: int = -1, pair: Sequence[bool] = (),
+              deint: bool = False):
         """kblocks: list of (src, shift, weight block [N, 64]).  pair[j]: output plane j is written pair-averaged (bilinear x0.5,
-        F.interpolate in BiC's conv_c0 branch, modules/_common.py:181-182) at the NEXT level's geometry."""
+        F.interpolate in BiC's conv_c0 branch, modules/_common.py:181-182) at the NEXT level's geometry.  deint: outs = (even, odd)
+        planes at the next level's geometry - the column split that the stride-(1, 2) conv behind it reads (N <= 64)."""
         g = self.lv[level]
         N = sum(cv.cout_pad for cv in cvs)
         assert N in (16, 64, 128), N
         assert g["n_mt"] * N <= 256, "accumulator does not fit the TMEM allocation"
-        assert len(outs) == (N + 63) // 64
+        if deint:
+            assert N <= 64 and len(outs) == 2 and g["W"] % 2 == 0 and not pair
+        else:
+            assert len(outs) == (N + 63) // 64
         kb_first = len(self.kbs)
         for src, shift, wb in kblocks:
             assert wb.shape == (N, 64), (wb.shape, N)
-            self.kbs.append((int(src), int(shift)))
+            self.kbs.append((int(src), int(shift), src_global >= 0))
             self.wblocks.append(wb)
         bias = torch.cat([cv.bias.float() for cv in cvs])
         assert bias.numel() == N
-        flags = sum(1 << j for j, pr in enumerate(pair) if pr)
-        if flags:
+        flags = sum(1 << j for j, pr in enumerate(pair) if pr) | (256 if deint else 0)
+        if flags & 3:
             assert self.G == 1 and g["W"] % 2 == 0 and N >= 64, "pair-averaged outputs: one clip per pass, even width"
         op = [CONV, g["n_mt"], N, kb_first, len(kblocks), g["R"], g["Wp"], g["W"], self.nbias, outs[0], outs[1] if len(outs) > 1 else -1,
-              head, flags, self.wrows, src_global, ACT_LRELU]
+              head, flags, self.wrows, src_global, ACT_LRELU,
+              1 if src_global >= 0 else max(1, 128 // N), 0, 0, 0]
+        # op[16]: K blocks per ring slot of a smem-sourced conv (<= 16 KB per slot)
         for cv in cvs:
             assert cv.act == ACT_LRELU
         self.ops.append(op)
@@ -164,14 +171,14 @@ class FusedNeck:
 
     def _ew(self, typ: int, level_out: int, a: int, b: int, c: int = 0, d: int = 0, wp_in: int = 0):
         g = self.lv[level_out]
-        self.ops.append([typ, a, b, c, d, g["R"], g["Wp"], g["W"], wp_in, 0, 0, 0, 0, 0, 0, 0])
+        self.ops.append([typ, a, b, c, d, g["R"], g["Wp"], g["W"], wp_in] + [0] * 11)
 
     def _dump(self, name: str, plane: int, level: int):
         if not self.debug:
             return
         rows = self.lv[level]["bytes"] // 128
         self.dumps[name] = (self.dump_elems, rows, level)
-        self.ops.append([DUMP, plane, rows, self.dump_elems, 0] + [0] * 11)
+        self.ops.append([DUMP, plane, rows, self.dump_elems, 0] + [0] * 15)
         self.dump_elems += rows * 64
 
     def _build(self):
@@ -231,21 +238,18 @@ class FusedNeck:
         # ---- RepBlock2_1 -> n2 (sm head)
         q1 = P(2)
         self._conv([rep["rep_block2_1"][0]["deploy"]], 2, self._taps3(rep["rep_block2_1"][0]["deploy"], bic2), [q1]); F(bic2[0]); F(bic2[1])
-        n2 = P(2)
-        self._conv([rep["rep_block2_1"][1]["deploy"]], 2, self._taps3(rep["rep_block2_1"][1]["deploy"], [q1]), [n2], head=0); F(q1)
-        # ---- conv2_downsample (3 x 3, stride (1, 2), pad 1) on even / odd planes: out[k] = W0 odd[k-1] + W1 even[k] + W2 odd[k]
+        # ---- conv2_downsample (3 x 3, stride (1, 2), pad 1) on even / odd planes: out[k] = W0 odd[k-1] + W1 even[k] + W2 odd[k];
+        #      the head conv in front of it writes its output split into those planes (no n2 plane, no DEINT op)
         e2, o2 = P(3), P(3)
-        self._ew(DEINT, 3, n2, e2, o2, wp_in=lv[2]["Wp"]); F(n2)
+        self._conv([rep["rep_block2_1"][1]["deploy"]], 2, self._taps3(rep["rep_block2_1"][1]["deploy"], [q1]), [e2, o2], head=0, deint=True); F(q1)
         d2 = [P(3), P(3)]
         self._conv([n["ds2"]], 3, self._taps_s2(n["ds2"], e2, o2), d2); F(e2); F(o2)
         q2 = P(3)
         self._conv([rep["rep_block3_2"][0]["deploy"]], 3, self._taps3(rep["rep_block3_2"][0]["deploy"], p3 + d2), [q2])
         for x in p3 + d2:
             F(x)
-        n3 = P(3)
-        self._conv([rep["rep_block3_2"][1]["deploy"]], 3, self._taps3(rep["rep_block3_2"][1]["deploy"], [q2]), [n3], head=1); F(q2)
         e3, o3 = P(4), P(4)
-        self._ew(DEINT, 4, n3, e3, o3, wp_in=lv[3]["Wp"]); F(n3)
+        self._conv([rep["rep_block3_2"][1]["deploy"]], 3, self._taps3(rep["rep_block3_2"][1]["deploy"], [q2]), [e3, o3], head=1, deint=True); F(q2)
         d3 = [P(4), P(4)]
         self._conv([n["ds3"]], 4, self._taps_s2(n["ds3"], e3, o3), d3); F(e3); F(o3)
         q3 = P(4)
@@ -268,9 +272,11 @@ class FusedNeck:
         for op in self.ops:
             for f in plane_fields[op[0]]:
                 op[f] = res(op[f])
-        self.kbs = [(res(src), sh) for src, sh in self.kbs]
+        # smem-sourced K block: what the tap adds to the low descriptor word (plane offset + (guard row + shift) rows, in 16-byte
+        # units); global-sourced: the 64-channel chunk of the input map
+        self.kbs = [(src, 0) if glob else ((res(src) + (1 + sh) * 128) >> 4, 0) for src, sh, glob in self.kbs]
         self.pool_bytes = _ceil(high, 1024)
-        tables = len(self.ops) * 64 + len(self.kbs) * 8 + self.nbias * 4 + 8 + 18 * 8 + 16
+        tables = len(self.ops) * 80 + len(self.kbs) * 8 + self.nbias * 4 + 8 + 18 * 8 + 16
         self.n_slots = min(8, (SMEM_MAX - 1024 - self.pool_bytes - tables) // SLOT)
         need = 1 + max(op[1] for op in self.ops if op[0] == CONV and op[14] >= 0)     # A tiles of one K block + its weight block
         if self.n_slots < need + 1:
@@ -285,7 +291,7 @@ class FusedNeck:
             if op[0] == DUMP:
                 op[4] = self.dump_elems          # per-clip stride of the debug buffer
         self.ops_t = torch.tensor(self.ops, dtype=torch.int32, device=dev).contiguous()
-        assert self.ops_t.shape[1] == 16
+        assert self.ops_t.shape[1] == 20
         self.dbg = torch.zeros(0, dtype=torch.bfloat16, device=dev)
 
     # ------------------------------------------------------------------ launch
