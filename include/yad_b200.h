@@ -269,12 +269,15 @@ int yad_conv_flat_taps(const yad_flat_desc* d, int32_t n_steps, const int32_t* c
  *   fmaps[4]            the backbone maps layer1..layer4 in the flat layout of yad_conv_flat ([B, Wp, Hp, C] bf16)
  *   fmap_k[i]           Hp * C of map i (channels of one (b, w) column incl. the zero halo row: the H-mean is folded into K)
  *   fmap_rows_per_clip  Wp of map i
+ *   fmap_box_rows       rows of one TMA box of map i (multiple of 8, <= 128; chosen by the program: see neck_fused.py)
+ *   clips_per_unit      clips one CTA pass processes together (the program's G: 1 or 2)
  *   wblob [wrows, 64]   bf16 weight blocks ([N x 64] per K block, stacked), bias [n_bias] f32
- *   ops / kbs           the program (n_ops x 20 int32, n_kb x 2 int32; layouts in csrc/neck_fused.cu), device memory
+ *   ops / kbs           the program (n_ops x 24 int32, n_kb x 2 int32; layouts in csrc/neck_fused.cu), device memory
  *   pool_bytes, n_slots shared-memory plan: activation pool size and ring depth (16 KB slots, 3..8)
  *   heads[3]            fp32 outputs [B, head_W[i], head_ld] (sm, md, lg), first 3 * (3 + nc) channels valid
  *   dbg                 optional bf16 buffer for the program's DUMP ops (NULL in production) */
-int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_t* fmap_rows_per_clip, int64_t B,
+int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_t* fmap_rows_per_clip,
+                   const int32_t* fmap_box_rows, int64_t B, int32_t clips_per_unit,
                    const void* wblob, int64_t wrows, const float* bias, int32_t n_bias, const void* ops, int32_t n_ops,
                    const void* kbs, int32_t n_kb, int32_t pool_bytes, int32_t n_slots, float* const* heads,
                    const int32_t* head_W, int32_t head_ld, void* dbg, yad_stream_t stream);

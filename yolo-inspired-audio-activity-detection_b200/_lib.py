@@ -62,7 +62,7 @@ SIGNATURES = {
     "yad_resample_sinc": [_p, _i32, _i64, _i64, _i32, _i32, _i32, _p, _p, _i64, _p],
     "yad_hmean": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
     "yad_resize_w": [_p, _i32, _i64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p],
-    "yad_neck_fused": [C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), _i64, _p, _i64, _p, _i32, _p, _i32, _p, _i32, _i32, _i32,
+    "yad_neck_fused": [C.POINTER(_p), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i64, _i32, _p, _i64, _p, _i32, _p, _i32, _p, _i32, _i32, _i32,
                        C.POINTER(_p), C.POINTER(_i32), _i32, _p, _p],
     "yad_neck_fused_set_timeline": [_p],
     "yad_neck_fused_set_timeline_iter": [_i32],

@@ -46,13 +46,20 @@ enum { NK_CONV = 0, NK_POOLS = 1, NK_PAIRAVG = 2, NK_UP2 = 3, NK_DEINT = 4, NK_D
 //            (bit 8: DE-INTERLEAVED output for the stride-2 conv that follows: row w of clip c goes to row c * (W / 2 + 1) + w / 2
 //            of plane out_plane0 (w even) or out_plane1 (w odd) - the even / odd split folded into the epilogue),
 //            13 wrow, 14 src_global (-1: planes in smem, else input map 0..3), 15 act,
-//            16 kg = K blocks per weight-ring slot (kg * N <= 128 rows), 17..19 unused
+//            (bit 9: NO EPILOGUE - the first half of a convolution whose K is split over two ops; bit 10: ACCUMULATE onto what
+//            such an op left in TMEM),
+//            16 kg = K blocks per weight-ring slot (kg * N <= 128 rows), 17 G = clips per unit, 18 rows of one clip in the
+//            backbone's flat layout (global-sourced convs), 19 M tiles per clip (0: all clips of the unit share one tile),
+//            20 clip pitch of the next level (pair-averaged / de-interleaved outputs), 21 unit row of accumulator row 0
+//            (a convolution may cover a 128-aligned slice of the unit's rows).
+//            Rows: a UNIT = G clips processed together by one CTA pass; clip c of the unit owns rows [c * P, c * P + P) of every
+//            plane of a level (P = field 6: W + 1 for G = 1, a power of two >= W + 1 for G = 2), its cells w >= W are zero.
 //   POOLS  : 1 in, 2 out1, 3 out2, 4 out3, 5 R, 6 Wp, 7 W
 //   PAIRAVG: 1 in, 2 out, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in            (out[k] = (in[2k] + in[2k+1]) / 2)
 //   UP2    : 1 in, 2 out, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in            (bilinear x2, align_corners = False)
 //   DEINT  : 1 in, 2 out_even, 3 out_odd, 5 R_out, 6 Wp_out, 7 W_out, 8 Wp_in
 //   DUMP   : 1 plane, 2 rows, 3 destination offset (bf16 elements) in the debug buffer, 4 per-clip stride (elements)
-constexpr int NK_OP_WORDS = 20;
+constexpr int NK_OP_WORDS = 24;
 struct NkOp {
   int32_t v[NK_OP_WORDS];
 };
@@ -65,6 +72,7 @@ struct NkKb {
 struct NkParams {
   long long* tlog;     // debug timeline (yad_neck_fused_set_timeline): CTA 0 records clock64 per op, NK_TL stamps each; NULL in production
   int32_t n_ops, n_kb, n_clips, n_slots;
+  int32_t G, n_units;  // clips per unit, units = ceil(n_clips / G)
   int32_t pool_bytes, n_bias;
   int32_t head_W[3];
   int32_t head_ld;
@@ -160,21 +168,29 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     // ===================================================================== TMA producer
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      for (int clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+      for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
         for (int oi = 0; oi < p.n_ops; ++oi) {
           const NkOp& op = s_ops[oi];
           if (op.v[0] != NK_CONV) continue;
-          const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], R = op.v[5], srcg = op.v[14], kg = op.v[16];
+          const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], srcg = op.v[14], kg = op.v[16];
           const CUtensorMap* mw = N == 16 ? &map_w16 : (N == 64 ? &map_w64 : &map_w128);
           if (srcg >= 0) {
             const CUtensorMap* ma = srcg == 0 ? &map_in0 : (srcg == 1 ? &map_in1 : (srcg == 2 ? &map_in2 : &map_in3));
             const uint32_t a_bytes = (uint32_t)p.a_bytes[srcg];
+            const int P = op.v[6], G = op.v[17], Wg = op.v[18], tpc = op.v[19], t0 = op.v[21] >> 7;
             for (int k = 0; k < nkb; ++k) {
               const int c0 = s_kbs[kb0 + k].src * 64;
               for (int mt = 0; mt < n_mt; ++mt) {
                 mbar_wait(&empty_bar[slot], phase ^ 1);
-                mbar_expect_tx(&full_bar[slot], a_bytes);
-                tma_load_2d(ma, &full_bar[slot], ring + (size_t)slot * NK_SLOT, c0, clip * R + 128 * mt);
+                uint8_t* dst = ring + (size_t)slot * NK_SLOT;
+                if (tpc > 0) {          // this tile lies inside one clip: one box (rows past the clip land on its zeroed cells)
+                  const int c = (t0 + mt) / tpc, w0 = (t0 + mt - c * tpc) << 7;
+                  mbar_expect_tx(&full_bar[slot], a_bytes);
+                  tma_load_2d(ma, &full_bar[slot], dst, c0, (unit * G + c) * Wg + w0);
+                } else {                // all clips of the unit in this tile: one box of P rows per clip at row c * P
+                  mbar_expect_tx(&full_bar[slot], a_bytes * (uint32_t)G);
+                  for (int c = 0; c < G; ++c) tma_load_2d(ma, &full_bar[slot], dst + (size_t)(c * P) * 128, c0, (unit * G + c) * Wg);
+                }
                 if (++slot == (uint32_t)p.n_slots) { slot = 0; phase ^= 1; }
               }
               mbar_wait(&empty_bar[slot], phase ^ 1);
@@ -215,7 +231,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     const uint32_t ring_lo = (smem_u32(ring) >> 4) | (1u << 16);        // + 1024 * slot + 8 * N * j + 2 * kk
     const uint32_t n_slots = (uint32_t)p.n_slots;
     int iter = 0;
-    for (int clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x, ++iter) {
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++iter) {
       for (int oi = 0; oi < p.n_ops; ++oi) {
         const NkOp& op = s_ops[oi];
         if (op.v[0] == NK_CONV) {
@@ -233,7 +249,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           if (tl) p.tlog[oi * NK_TL + 0] = clock64();
           const int n_mt = op.v[1], N = op.v[2], kb0 = op.v[3], nkb = op.v[4], srcg = op.v[14], kg = op.v[16];
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-          uint32_t acc = 0u;
+          uint32_t acc = (op.v[12] & 1024) ? 1u : 0u;      // second half of a split-K convolution: onto the first half's sums
           if (srcg >= 0) {
             for (int k = 0; k < nkb; ++k) {
               uint32_t a_slot[NK_MAX_MT];
@@ -308,7 +324,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
     const int te = threadIdx.x - 64;      // 0..255
     uint32_t acc_phase = 0;
     int iter = 0;
-    for (int clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x, ++iter) {
+    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x, ++iter) {
       const bool tle = p.tlog != nullptr && blockIdx.x == 0 && iter == p.tl_iter;
       for (int oi = 0; oi < p.n_ops; ++oi) {
         const NkOp& op = s_ops[oi];
@@ -324,8 +340,9 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           tc_fence_after();
           if (tle && te == 0) p.tlog[oi * NK_TL + 2] = clock64();
           const int nb = (N + 31) >> 5;   // 32-column blocks (N = 16: one block, upper 16 columns unused)
-          for (int mt = 0; mt < n_mt; ++mt) {
-            const int r = 128 * mt + q * 32 + lane, s = r + 1;
+          const int n_mt_e = (op.v[12] & 512) ? 0 : n_mt;        // first half of a split-K convolution: the sums stay in TMEM
+          for (int mt = 0; mt < n_mt_e; ++mt) {
+            const int r = op.v[21] + 128 * mt + q * 32 + lane, s = r + 1;
             const int c = r / Wp, w = r - c * Wp;
             const bool valid = r < R && w < W;
             const bool in_plane = r < R;  // rows past the level's R rows are not part of the plane (the next plane starts there)
@@ -349,9 +366,9 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
                   x[4 * i4 + 3] = fmaxf(t3, slope * t3);
                 }
               }
-              if (head >= 0 && valid) {      // fp32 head rows [B, W, head_ld] for the decoder (N = 16)
+              if (head >= 0 && valid && unit * p.G + c < p.n_clips) {      // fp32 head rows [B, W, head_ld] for the decoder (N = 16)
                 float* hp = (head == 0 ? head0 : (head == 1 ? head1 : head2)) +
-                            ((int64_t)(clip * (R / Wp) + c) * p.head_W[head] + w) * p.head_ld;
+                            ((int64_t)(unit * p.G + c) * p.head_W[head] + w) * p.head_ld;
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4)
                   if (4 * i4 < p.head_ld) reinterpret_cast<float4*>(hp)[i4] = make_float4(x[4 * i4], x[4 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3]);
@@ -384,7 +401,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
                 // odd ones to out_plane1, both at the next level's geometry W / 2 (+ halo); the halo cell w = W (W even) lands
                 // on the halo cell of the even plane, the same thread zeroes the one of the odd plane
                 if (in_plane) {
-                  const int so = c * ((W >> 1) + 1) + (w >> 1) + 1;
+                  const int so = c * op.v[20] + (w >> 1) + 1;
                   uint8_t* pe = base + op.v[9];
                   uint8_t* po = base + op.v[10];
                   uint8_t* plane = (w & 1) ? po : pe;
@@ -501,7 +518,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           if (dbg != nullptr) {
             const uint8_t* plane = base + op.v[1];
             const int rows = op.v[2];
-            __nv_bfloat16* dst = dbg + op.v[3] + (int64_t)clip * op.v[4];
+            __nv_bfloat16* dst = dbg + op.v[3] + (int64_t)unit * op.v[4];
             for (int item = te; item < rows * 8; item += NK_EPI) {
               const int s = item >> 3, j = item & 7;
               *reinterpret_cast<uint4*>(dst + (int64_t)s * 64 + 8 * j) = *nk_chunk(const_cast<uint8_t*>(plane), s, j);
@@ -554,12 +571,15 @@ extern "C" int yad_neck_fused_set_timeline_iter(int32_t iter) {
   return YAD_OK;
 }
 
-extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_t* fmap_rows_per_clip, int64_t B,
+extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, const int32_t* fmap_rows_per_clip,
+                              const int32_t* fmap_box_rows, int64_t B, int32_t clips_per_unit,
                               const void* wblob, int64_t wrows, const float* bias, int32_t n_bias, const void* ops, int32_t n_ops,
                               const void* kbs, int32_t n_kb, int32_t pool_bytes, int32_t n_slots, float* const* heads,
                               const int32_t* head_W, int32_t head_ld, void* dbg, yad_stream_t stream) {
   using namespace yad;
-  YAD_CHECK_ARG(fmaps && fmap_k && fmap_rows_per_clip && wblob && bias && ops && kbs && heads && head_W, "yad_neck_fused: null pointer");
+  YAD_CHECK_ARG(fmaps && fmap_k && fmap_rows_per_clip && fmap_box_rows && wblob && bias && ops && kbs && heads && head_W,
+                "yad_neck_fused: null pointer");
+  YAD_CHECK_ARG(clips_per_unit >= 1 && clips_per_unit <= 4, "yad_neck_fused: 1..4 clips per unit");
   YAD_CHECK_ARG(B >= 0 && B < (1 << 22) && wrows >= 16 && n_ops >= 1 && n_ops <= 64 && n_kb >= 1 && n_kb <= 256 && n_bias >= 1,
                 "yad_neck_fused: bad sizes");
   YAD_CHECK_ARG(n_slots >= 3 && n_slots <= NK_MAX_SLOTS && pool_bytes >= 1024 && pool_bytes % 1024 == 0, "yad_neck_fused: bad ring / pool");
@@ -571,14 +591,15 @@ extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, c
   CUtensorMap mi[4], mw[3];
   uint32_t a_rows[4];
   for (int i = 0; i < 4; ++i) {
-    YAD_CHECK_ARG(fmaps[i] && fmap_k[i] % 64 == 0 && fmap_k[i] >= 64 && fmap_rows_per_clip[i] >= 1 &&
+    YAD_CHECK_ARG(fmaps[i] && fmap_k[i] % 64 == 0 && fmap_k[i] >= 64 && fmap_rows_per_clip[i] >= 1 && fmap_box_rows[i] >= 1 &&
+                      fmap_box_rows[i] <= 128 && fmap_box_rows[i] % 8 == 0 &&
                       reinterpret_cast<uintptr_t>(fmaps[i]) % 16 == 0,
                   "yad_neck_fused: bad feature map %d", i);
     const uint64_t dims[2] = {(uint64_t)fmap_k[i], (uint64_t)B * (uint64_t)fmap_rows_per_clip[i]};
     const uint64_t strides[1] = {(uint64_t)fmap_k[i] * 2};
-    // one clip's rows (rounded up to 8) when they fit one M tile: rows past the box keep stale shared-memory contents, which
-    // only reach accumulator rows >= R that no epilogue reads
-    a_rows[i] = fmap_rows_per_clip[i] <= 128 ? (uint32_t)((fmap_rows_per_clip[i] + 7) / 8 * 8) : 128u;
+    // rows of one A box (the program's choice: a clip's rows rounded up to 8, the clip pitch of a multi-clip unit, or 128); rows
+    // of a ring slot past the box keep stale shared-memory contents, which only reach accumulator rows that the epilogue zeroes
+    a_rows[i] = (uint32_t)fmap_box_rows[i];
     const uint32_t box[2] = {64u, a_rows[i]};
     int rc = encode_map_bf16(&mi[i], fmaps[i], 2, dims, strides, box);
     if (rc) return rc;
@@ -596,6 +617,8 @@ extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, c
   p.n_ops = n_ops;
   p.n_kb = n_kb;
   p.n_clips = (int)B;
+  p.G = clips_per_unit;
+  p.n_units = (int)((B + clips_per_unit - 1) / clips_per_unit);
   p.n_slots = n_slots;
   p.pool_bytes = pool_bytes;
   p.n_bias = n_bias;
@@ -604,7 +627,7 @@ extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, c
   for (int i = 0; i < 4; ++i) p.a_bytes[i] = (int32_t)(a_rows[i] * 128u);
   p.tl_iter = g_nk_tl_iter;
   const int nsm = sm_count() > 0 ? sm_count() : 148;
-  const unsigned grid = (unsigned)(B < nsm ? B : nsm);
+  const unsigned grid = (unsigned)(p.n_units < nsm ? p.n_units : nsm);
   YAD_CUDA(launch_pdl(neck_fused_kernel, dim3(grid), dim3(NK_THREADS), smem, (cudaStream_t)stream, mi[0], mi[1], mi[2], mi[3], mw[0], mw[1],
                       mw[2], p, reinterpret_cast<const NkOp*>(ops), reinterpret_cast<const NkKb*>(kbs), bias, heads[0], heads[1], heads[2],
                       reinterpret_cast<__nv_bfloat16*>(dbg)));

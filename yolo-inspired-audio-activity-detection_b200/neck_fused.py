@@ -9,6 +9,7 @@ kernel interprets the program once per clip; this module only decides WHAT runs 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -47,8 +48,7 @@ class _Pool:
         self.live.remove(i)
         self.planes[i][2] = now
 
-    def place(self) -> Tuple[List[int], int]:
-        order = sorted(range(len(self.planes)), key=lambda i: (-self.planes[i][0], self.planes[i][1]))
+    def _place_order(self, order) -> Tuple[List[int], int]:
         off = [-1] * len(self.planes)
         for i in order:
             n, b, d = self.planes[i]
@@ -61,13 +61,37 @@ class _Pool:
                 pos = max(pos, hi)
             off[i] = pos
         high = max(off[i] + self.planes[i][0] for i in range(len(self.planes)))
+        return off, high
+
+    def place(self) -> Tuple[List[int], int]:
+        """First-fit over several plane orders (largest first, by birth, by death, and seeded shuffles of the largest-first order):
+        the best packing found is kept (136 -> ~122 KB on the two-clip plan of a 60 s clip, whose liveness peak is 120 KB)."""
+        import random
+        idx = list(range(len(self.planes)))
+        orders = [sorted(idx, key=lambda i: (-self.planes[i][0], self.planes[i][1])),
+                  sorted(idx, key=lambda i: (self.planes[i][1], -self.planes[i][0])),
+                  sorted(idx, key=lambda i: (-(self.planes[i][2] - self.planes[i][1]), -self.planes[i][0])),
+                  sorted(idx, key=lambda i: (-self.planes[i][0] * (self.planes[i][2] - self.planes[i][1]), self.planes[i][1]))]
+        rng = random.Random(1234)
+        for _ in range(400):
+            o = list(orders[0])
+            for _ in range(rng.randint(1, 6)):          # a few transpositions of the largest-first order
+                a, b = rng.randrange(len(o)), rng.randrange(len(o))
+                o[a], o[b] = o[b], o[a]
+            orders.append(o)
+        best = None
+        for o in orders:
+            off, high = self._place_order(o)
+            if best is None or high < best[1]:
+                best = (off, high)
+        off, high = best
         return [o * 1024 for o in off], high * 1024
 
 
 class FusedNeck:
     """Compiled neck for one input geometry.  ``eng`` is the InferenceEngine (packed convolutions ``eng.n`` / ``eng.rep``)."""
 
-    def __init__(self, eng, Hs: Sequence[int], Ws: Sequence[int], Cs: Sequence[int], debug: bool = False):
+    def __init__(self, eng, Hs: Sequence[int], Ws: Sequence[int], Cs: Sequence[int], debug: bool = False, G: Optional[int] = None):
         self.eng, self.dev = eng, eng.dev
         self.Hs, self.Ws, self.Cs = list(Hs), list(Ws), list(Cs)
         W1, W2, W3, W4 = Ws
@@ -79,12 +103,33 @@ class FusedNeck:
         for nm, blocks in eng.rep.items():
             if any("deploy" not in b for b in blocks) or len(blocks) != 2:
                 raise NotImplementedError("fused neck: re-parameterised (deploy) RepBlocks of two blocks only")
-        self.G = 1                                              # clips per CTA pass
+        self.debug = debug
+        if G is None and os.environ.get("YAD_NECK_G"):
+            G = int(os.environ["YAD_NECK_G"])
+        last = None
+        for g in ([G] if G else [2, 1]):
+            try:
+                self._compile(g)
+                return
+            except NotImplementedError as e:
+                last = e
+        raise last
+
+    def _compile(self, G: int):
+        """G clips per CTA pass ("unit").  G = 1: clip pitch = W + 1 rows (the flat layout of the backbone).  G = 2: the clips of a
+        unit sit at a power-of-two row pitch P (P4 >= W4 + 1, P3 = 2 P4, ...), so that at levels 3 / 4 BOTH clips share one 128-row
+        M tile - the second clip costs no MMA and no epilogue pass there, and every weight block is fetched once per unit - and
+        the row pairs of the x0.5 / even-odd folds stay inside a clip.  Rows w in [W, P) of a clip are zero (halo + padding)."""
+        Ws = self.Ws
+        self.G = G                                              # clips per CTA pass
         self.lv = {}                                            # level -> geometry
+        p4 = Ws[3] + 1
+        if G > 1:
+            p4 = max(8, 1 << (p4 - 1).bit_length())         # >= one swizzle atom: a clip's TMA box starts on a 1024-byte boundary
         for i, W in enumerate(Ws):
-            Wp = W + 1
-            R = self.G * Wp
-            self.lv[i + 1] = {"W": W, "Wp": Wp, "R": R, "n_mt": (R + 127) // 128, "bytes": _ceil(R + 2, 8) * 128}
+            P = W + 1 if G == 1 else p4 << (3 - i)
+            R = G * P
+            self.lv[i + 1] = {"W": W, "Wp": P, "R": R, "n_mt": (R + 127) // 128, "bytes": _ceil(R + 2, 8) * 128}
             if self.lv[i + 1]["n_mt"] > 4:
                 raise NotImplementedError("fused neck: clip too long (more than 4 M tiles per level)")
         self.pool = _Pool()
@@ -94,7 +139,6 @@ class FusedNeck:
         self.wrows = 0
         self.biases: List[torch.Tensor] = []
         self.nbias = 0
-        self.debug = debug
         self.dumps: Dict[str, Tuple[int, int, int]] = {}        # name -> (element offset, rows, level)
         self.dump_elems = 0
         self._build()
@@ -117,15 +161,23 @@ class FusedNeck:
         self.pool.free(tok, len(self.ops))
 
     def _conv(self, cvs, level: int, kblocks, outs: List[int], head: int = -1, src_global: int = -1, pair: Sequence[bool] = (),
-              deint: bool = False):
+              deint: bool = False, no_epilogue: bool = False, accumulate: bool = False, row_base: int = 0, n_mt: Optional[int] = None):
         """kblocks: list of (src, shift, weight block [N, 64]).  pair[j]: output plane j is written pair-averaged (bilinear x0.5,
         F.interpolate in BiC's conv_c0 branch, modules/_common.py:181-182) at the NEXT level's geometry.  deint: outs = (even, odd)
-        planes at the next level's geometry - the column split that the stride-(1, 2) conv behind it reads (N <= 64)."""
-        g = self.lv[level]
+        planes at the next level's geometry - the column split that the stride-(1, 2) conv behind it reads (N <= 64).
+        no_epilogue / accumulate: a convolution whose K is split over two ops (the accumulator stays in TMEM in between, so the
+        planes the first half read can be freed before the second half's inputs are produced)."""
+        g = dict(self.lv[level])
+        if n_mt is not None:               # a slice of the unit's rows: accumulator row 0 = unit row row_base (a multiple of 128)
+            assert row_base % 128 == 0 and row_base + 128 * n_mt <= _ceil(g["R"], 128)
+            g["n_mt"] = n_mt
         N = sum(cv.cout_pad for cv in cvs)
         assert N in (16, 64, 128), N
-        assert g["n_mt"] * N <= 256, "accumulator does not fit the TMEM allocation"
-        if deint:
+        if g["n_mt"] * N > 256:
+            raise NotImplementedError("fused neck: accumulator does not fit the TMEM allocation")
+        if no_epilogue:
+            assert not outs and head < 0 and not pair and not deint
+        elif deint:
             assert N <= 64 and len(outs) == 2 and g["W"] % 2 == 0 and not pair
         else:
             assert len(outs) == (N + 63) // 64
@@ -136,13 +188,20 @@ class FusedNeck:
             self.wblocks.append(wb)
         bias = torch.cat([cv.bias.float() for cv in cvs])
         assert bias.numel() == N
-        flags = sum(1 << j for j, pr in enumerate(pair) if pr) | (256 if deint else 0)
+        flags = sum(1 << j for j, pr in enumerate(pair) if pr) | (256 if deint else 0) | (512 if no_epilogue else 0) | (1024 if accumulate else 0)
         if flags & 3:
-            assert self.G == 1 and g["W"] % 2 == 0 and N >= 64, "pair-averaged outputs: one clip per pass, even width"
-        op = [CONV, g["n_mt"], N, kb_first, len(kblocks), g["R"], g["Wp"], g["W"], self.nbias, outs[0], outs[1] if len(outs) > 1 else -1,
-              head, flags, self.wrows, src_global, ACT_LRELU,
-              1 if src_global >= 0 else max(1, 128 // N), 0, 0, 0]
-        # op[16]: K blocks per ring slot of a smem-sourced conv (<= 16 KB per slot)
+            assert g["W"] % 2 == 0 and g["Wp"] % 2 == (0 if self.G > 1 else 1) and N >= 64, "pair-averaged outputs: even width"
+        nxt = self.lv.get(level + 1)
+        Wg = self.Ws[src_global] + 1 if src_global >= 0 else 0               # rows of one clip in the backbone's flat layout
+        tpc = 0
+        if src_global >= 0:
+            tpc = g["n_mt"] if self.G == 1 else g["Wp"] // 128                # M tiles per clip (0: all clips of the unit in one tile)
+        op = [CONV, g["n_mt"], N, kb_first, len(kblocks), g["R"], g["Wp"], g["W"], self.nbias, outs[0] if outs else -1,
+              outs[1] if len(outs) > 1 else -1, head, flags, self.wrows, src_global, ACT_LRELU,
+              1 if src_global >= 0 else max(1, 128 // N),                    # 16: K blocks per ring slot (smem-sourced convs)
+              self.G, Wg, tpc,                                               # 17 clips per unit, 18 global rows per clip, 19 tiles per clip
+              nxt["Wp"] if nxt else 0, row_base, 0, 0]                       # 20 clip pitch of the next level (pair / deint outputs),
+        #                                                                      21 unit row of accumulator row 0
         for cv in cvs:
             assert cv.act == ACT_LRELU
         self.ops.append(op)
@@ -171,14 +230,14 @@ class FusedNeck:
 
     def _ew(self, typ: int, level_out: int, a: int, b: int, c: int = 0, d: int = 0, wp_in: int = 0):
         g = self.lv[level_out]
-        self.ops.append([typ, a, b, c, d, g["R"], g["Wp"], g["W"], wp_in] + [0] * 11)
+        self.ops.append([typ, a, b, c, d, g["R"], g["Wp"], g["W"], wp_in] + [0] * 15)
 
     def _dump(self, name: str, plane: int, level: int):
         if not self.debug:
             return
         rows = self.lv[level]["bytes"] // 128
         self.dumps[name] = (self.dump_elems, rows, level)
-        self.ops.append([DUMP, plane, rows, self.dump_elems, 0] + [0] * 15)
+        self.ops.append([DUMP, plane, rows, self.dump_elems, 0] + [0] * 19)
         self.dump_elems += rows * 64
 
     def _build(self):
@@ -215,10 +274,9 @@ class FusedNeck:
         u3 = [P(3), P(3)]
         for i in range(2):
             self._ew(UP2, 3, p4[i], u3[i], wp_in=lv[4]["Wp"])
-        bic3 = [P(3), P(3)]
-        self._conv([n["b3o"]], 3, self._taps1([n["b3o"]], [c1_3, c0_3, u3[0], u3[1]]), bic3)
-        for x in (c1_3, c0_3, u3[0], u3[1]):
-            F(x)
+        # the output of a convolution may overwrite its own inputs (the epilogue starts after the last MMA has retired)
+        bic3 = u3
+        self._conv([n["b3o"]], 3, self._taps1([n["b3o"]], [c1_3, c0_3, u3[0], u3[1]]), bic3); F(c1_3); F(c0_3)
         self._dump("b3_0", bic3[0], 3)
         r1 = [P(3), P(3)]
         self._conv([rep["rep_block3_1"][0]["deploy"]], 3, self._taps3(rep["rep_block3_1"][0]["deploy"], bic3), r1); F(bic3[0]); F(bic3[1])
@@ -227,17 +285,31 @@ class FusedNeck:
         self._dump("p3_0", p3[0], 3); self._dump("p3_1", p3[1], 3)
         # ---- BiC2
         c0_2 = P(2)
-        self._conv([n["b2c0"]], 1, self._taps_global([n["b2c0"]], 0), [c0_2], src_global=0, pair=(True,))
+        if lv[1]["n_mt"] > 2:
+            # the level-1 map of a unit spans more M tiles than the ring can hold A slots for: one pass per clip (the 8 weight
+            # blocks of 8 KB are streamed again), each writing its clip's rows of the pair-averaged level-2 plane
+            tiles = lv[1]["Wp"] // 128
+            assert self.G > 1 and lv[1]["Wp"] % 128 == 0 and tiles <= 2
+            for c in range(self.G):
+                self._conv([n["b2c0"]], 1, self._taps_global([n["b2c0"]], 0), [c0_2], src_global=0, pair=(True,),
+                           row_base=c * lv[1]["Wp"], n_mt=tiles)
+        else:
+            self._conv([n["b2c0"]], 1, self._taps_global([n["b2c0"]], 0), [c0_2], src_global=0, pair=(True,))
+        # BiC2's conv_out (:184) with its K split over two ops: the conv_c1 / conv_c0 halves are accumulated (and their 2 level-2
+        # planes freed) BEFORE the x2-upsampled halves are produced - the four input planes never coexist (the peak of the
+        # shared-memory plan, 88 -> 56 KB per clip, is what lets two clips share a CTA pass)
+        kb_b2o = self._taps1([n["b2o"]], [c1_2, c0_2, 0, 0])
+        self._conv([n["b2o"]], 2, kb_b2o[:2], [], no_epilogue=True); F(c1_2); F(c0_2)
         u2 = [P(2), P(2)]
         for i in range(2):
             self._ew(UP2, 2, p3[i], u2[i], wp_in=lv[3]["Wp"])
-        # the output of a convolution may overwrite its own inputs (the epilogue starts after the last MMA has retired)
         bic2 = u2
-        self._conv([n["b2o"]], 2, self._taps1([n["b2o"]], [c1_2, c0_2, u2[0], u2[1]]), bic2); F(c1_2); F(c0_2)
+        kb_b2o = self._taps1([n["b2o"]], [0, 0, u2[0], u2[1]])
+        self._conv([n["b2o"]], 2, kb_b2o[2:], bic2, accumulate=True)
         self._dump("b2_0", bic2[0], 2); self._dump("b2_1", bic2[1], 2)
-        # ---- RepBlock2_1 -> n2 (sm head)
-        q1 = P(2)
-        self._conv([rep["rep_block2_1"][0]["deploy"]], 2, self._taps3(rep["rep_block2_1"][0]["deploy"], bic2), [q1]); F(bic2[0]); F(bic2[1])
+        # ---- RepBlock2_1 -> n2 (sm head); its first conv writes over its own first input plane
+        q1 = bic2[0]
+        self._conv([rep["rep_block2_1"][0]["deploy"]], 2, self._taps3(rep["rep_block2_1"][0]["deploy"], bic2), [q1]); F(bic2[1])
         # ---- conv2_downsample (3 x 3, stride (1, 2), pad 1) on even / odd planes: out[k] = W0 odd[k-1] + W1 even[k] + W2 odd[k];
         #      the head conv in front of it writes its output split into those planes (no n2 plane, no DEINT op)
         e2, o2 = P(3), P(3)
@@ -276,7 +348,7 @@ class FusedNeck:
         # units); global-sourced: the 64-channel chunk of the input map
         self.kbs = [(src, 0) if glob else ((res(src) + (1 + sh) * 128) >> 4, 0) for src, sh, glob in self.kbs]
         self.pool_bytes = _ceil(high, 1024)
-        tables = len(self.ops) * 80 + len(self.kbs) * 8 + self.nbias * 4 + 8 + 18 * 8 + 16
+        tables = len(self.ops) * 96 + len(self.kbs) * 8 + self.nbias * 4 + 8 + 18 * 8 + 16
         self.n_slots = min(8, (SMEM_MAX - 1024 - self.pool_bytes - tables) // SLOT)
         need = 1 + max(op[1] for op in self.ops if op[0] == CONV and op[14] >= 0)     # A tiles of one K block + its weight block
         if self.n_slots < need + 1:
@@ -291,26 +363,30 @@ class FusedNeck:
             if op[0] == DUMP:
                 op[4] = self.dump_elems          # per-clip stride of the debug buffer
         self.ops_t = torch.tensor(self.ops, dtype=torch.int32, device=dev).contiguous()
-        assert self.ops_t.shape[1] == 20
+        assert self.ops_t.shape[1] == 24
         self.dbg = torch.zeros(0, dtype=torch.bfloat16, device=dev)
 
     # ------------------------------------------------------------------ launch
     def run(self, lib, fmaps: Sequence[torch.Tensor], heads: Sequence[torch.Tensor], stream, dbg: Optional[torch.Tensor] = None):
         """fmaps: the four flat backbone maps [B, Wp, Hp, C] bf16; heads: three fp32 tensors [B, 1, W, ld]."""
         B = fmaps[0].shape[0]
-        fk, fr = [], []
+        fk, fr, fb = [], [], []
         for i, f in enumerate(fmaps):
             _, Wp, Hp, Cc = f.shape
             assert f.is_contiguous() and f.dtype == torch.bfloat16 and Wp == self.Ws[i] + 1 and Cc == self.Cs[i], (i, tuple(f.shape))
             assert Hp == (self.Hs[i] + 1 if self.Hs[i] > 1 else 1)
             fk.append(Hp * Cc)
             fr.append(Wp)
+            # rows of one TMA box of map i: a whole clip (rounded up to 8 rows) when it fits an M tile, else 128; with several clips
+            # per unit the clip pitch (a power of two >= W + 1)
+            P = self.lv[i + 1]["Wp"]
+            fb.append(min(128, P if self.G > 1 else _ceil(Wp, 8)))
         ld = heads[0].shape[-1]
         for i, h in enumerate(heads):
             assert h.dtype == torch.float32 and h.is_contiguous() and h.shape[-1] == ld and h.shape[-2] == self.Ws[i + 1] and h.shape[0] == B
         fm = (C.c_void_p * 4)(*[f.data_ptr() for f in fmaps])
         hd = (C.c_void_p * 3)(*[h.data_ptr() for h in heads])
-        rc = lib.yad_neck_fused(fm, (C.c_int32 * 4)(*fk), (C.c_int32 * 4)(*fr), B, self.wblob.data_ptr(), self.wblob.shape[0],
+        rc = lib.yad_neck_fused(fm, (C.c_int32 * 4)(*fk), (C.c_int32 * 4)(*fr), (C.c_int32 * 4)(*fb), B, self.G, self.wblob.data_ptr(), self.wblob.shape[0],
                                 self.bias.data_ptr(), self.nbias, self.ops_t.data_ptr(), len(self.ops), self.kbs_t.data_ptr(), len(self.kbs),
                                 self.pool_bytes, self.n_slots, hd, (C.c_int32 * 3)(*self.Ws[1:]), ld,
                                 0 if dbg is None else dbg.data_ptr(), stream)
