@@ -16,7 +16,7 @@ def t(fn, n=10):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n
 s = eng._stream
-for nint in (60, 68, 76, 84, 92, 100, 108):
+for nint in [int(v) for v in os.environ.get("NINTS", "84,92,96,100,104,108,112").split(",")]:
     ms = t(lambda: _lib.check(eng.lib.yad_conv_stem_fused(xb.data_ptr(), xb.shape[2], B, 32, T, eng.fstem_w.data_ptr(), eng.fstem_bias.data_ptr(), cur.data_ptr(), cur.shape[2], cur.shape[1], nint, s()), 'f'))
     print('n_int', nint, 'fused main %.3f ms' % ms)
 ms = t(lambda: _lib.check(eng.lib.yad_conv_stem_fused_fixup(xs.data_ptr(), B, 32, T, eng.fstem_wvar.data_ptr(), eng.fstem_bias.data_ptr(), fx[0], fx[1], fx[2], cur.data_ptr(), cur.shape[2], cur.shape[1], s()), 'x'))

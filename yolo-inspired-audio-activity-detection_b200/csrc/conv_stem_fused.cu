@@ -18,10 +18,14 @@
 // at byte 16 r of the patch row - exactly the stride-4 window of output pixel r.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace yad {
 
-constexpr int SF_THREADS = 256;
+constexpr int SF_EPI_WARPS = 8;                // warps 0..7: epilogue; warp 8: MMA issue
+constexpr int SF_THREADS = 32 * (SF_EPI_WARPS + 2);   // + warp 9: patch producer
+constexpr int SF_MAXGRP = 12;                  // row groups of a patch (2 * rows of a class + 1 at most)
+constexpr int SF_NACC = 5;                     // accumulator slots (output rows) in TMEM: 5 x 64 columns
 constexpr int SF_SEG = 128;                    // output pixels (columns) per tile = MMA M
 constexpr int SF_KD = 19;                      // composite kernel size
 constexpr int SF_KROW = 48;                    // K per kernel row: 19 taps x 2 channels = 38, padded to 3 MMA steps of 16
@@ -49,6 +53,7 @@ struct StemFusedParams {
   int32_t cta_first[5];          // CTA ranges of the 4 row classes: class c owns blocks [cta_first[c], cta_first[c+1])
   int32_t row_first[4], row_cnt[4];
   uint32_t idesc;
+  int32_t dbg;                   // timing experiments (YAD_STEM_DBG; results are wrong with any bit set): 1 no stores, 2 no MMAs, 4 no fills
   int32_t skip_lo, skip_hi;      // output columns [0, skip_lo) and [Wo - skip_hi, Wo) are NOT written: the fix-up kernel owns them
                                  // and may then run concurrently (another stream) instead of after this kernel
 };
@@ -67,9 +72,12 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
   uint8_t* sB = sf_smem;                                   // this class's weights, core-matrix layout
   uint8_t* sP = sB + SF_B_BYTES;                           // [rows][SF_ROWB] patch
   float* s_bias = reinterpret_cast<float*>(sP + SF_MAXROWS * SF_ROWB + 256);   // +256: slack read by the last row's last windows
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(s_bias + 64);
-  uint64_t* fill_bar = mma_bar + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(fill_bar + 1);
+  uint64_t* grp_full = reinterpret_cast<uint64_t*>(s_bias + 64);          // [2][SF_MAXGRP] row group g of patch buffer b has landed
+  uint64_t* row_done = grp_full + 2 * SF_MAXGRP;                           // [2][SF_NACC] the MMAs of output row j (buffer b) have retired
+  uint64_t* acc_full = row_done + 2 * SF_NACC;                             // [SF_NACC] accumulator slot written by the tensor core
+  uint64_t* acc_empty = acc_full + SF_NACC;                                // [SF_NACC] ... drained by the 8 epilogue warps
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + SF_NACC);
+  int32_t* s_grp = reinterpret_cast<int32_t*>(tmem_ptr_smem + 2);          // [SF_MAXGRP][4]: first row, end row, first / last output row using it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int cls = 0;
@@ -83,9 +91,43 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
   const uint4* wsrc = w_classes + (size_t)cls * (SF_B_BYTES / 16);
   for (int i = tid; i < SF_B_BYTES / 16; i += SF_THREADS) reinterpret_cast<uint4*>(sB)[i] = __ldg(wsrc + i);
   if (tid < 64) s_bias[tid] = bias[tid];
+  // Row groups of the patch: maximal runs of input rows used by the same set of output rows of the class (interior class: 9 groups
+  // of 2 - 4 rows; a border class: one).  Group g is first needed by output row F(g) and free again once row L(g)'s MMAs have
+  // retired, so the producer refills the patch of the NEXT tile group by group while this tile's later rows are still being
+  // multiplied: only the 3 rows shared by the first and the last output row sit between two tiles (the whole 69 KB patch did).
+  int n_grp = 0;
+  {
+    int lo = hi_lo;
+    while (lo < hi_hi) {
+      // next boundary: the smallest window start / window end above lo
+      int nxt = hi_hi;
+      for (int j = 0; j < nrow; ++j) {
+        const int a = 4 * (ho0 + j) - 9, e = a + SF_KD;
+        if (a > lo && a < nxt) nxt = a;
+        if (e > lo && e < nxt) nxt = e;
+      }
+      int F = nrow, L = -1;
+      for (int j = 0; j < nrow; ++j) {
+        const int a = 4 * (ho0 + j) - 9;
+        if (a <= lo && lo < a + SF_KD) { F = j < F ? j : F; L = j; }
+      }
+      if (tid == 0) {
+        s_grp[4 * n_grp] = lo - hi_lo;
+        s_grp[4 * n_grp + 1] = nxt - hi_lo;
+        s_grp[4 * n_grp + 2] = F;
+        s_grp[4 * n_grp + 3] = L;
+      }
+      ++n_grp;
+      lo = nxt;
+    }
+  }
   if (tid == 0) {
-    mbar_init(mma_bar, 1);
-    mbar_init(fill_bar, 1);
+    for (int i = 0; i < 2 * SF_MAXGRP; ++i) mbar_init(&grp_full[i], 1);
+    for (int i = 0; i < 2 * SF_NACC; ++i) mbar_init(&row_done[i], 1);
+    for (int i = 0; i < SF_NACC; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], SF_EPI_WARPS);      // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, SF_TMEM_COLS);
@@ -96,83 +138,128 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();          // programmatic dependent launch: the 117 KB weight load above overlapped the frontend's tail
   pdl_trigger();
-  const uint32_t p_addr = smem_u32(sP), b_addr = smem_u32(sB);
-  const int q = warp & 3, half = warp >> 2;     // epilogue: TMEM lane quadrant, channel half
-  const int r = q * 32 + lane;                  // pixel inside the segment
-  uint32_t phase = 0;
   const int n_tiles = p.B * p.n_seg;
 
-  auto issue_fill = [&](int tl) {
-    const int sg = tl % p.n_seg, bb = tl / p.n_seg;
-    mbar_expect_tx(fill_bar, (uint32_t)prow * SF_ROWB);
-    const uint32_t* src = xb + ((int64_t)bb * p.H + hi_lo) * p.xpitch + 4 * sg * SF_SEG;
-    for (int rr = 0; rr < prow; ++rr) sf_bulk_g2s(sP + rr * SF_ROWB, src + (int64_t)rr * p.xpitch, SF_ROWB, fill_bar);
-  };
-  for (int tile = cta_in_cls; tile < n_tiles; tile += n_cta_cls) {
-    const int seg = tile % p.n_seg, b = tile / p.n_seg;
-    const int wo0 = seg * SF_SEG;
-    // (1) patch rows: the input lives as channel-interleaved bf16 words with a 9-word zero margin on the left (and zeros on the
-    //     right), so the window row of this segment is the 16-byte aligned span [4 wo0, 4 wo0 + SF_PW) of the padded row: one
-    //     bulk copy per input row, no bounds logic.  Rows outside the image are not loaded (their MMAs are skipped).
-    //     The copies of the NEXT tile are issued as soon as this tile's MMAs have finished (they overlap the epilogue).
-    if (tid == 0 && tile == cta_in_cls) issue_fill(tile);
-    mbar_wait(fill_bar, phase);
-    // (2) MMAs: one accumulator per output row of the class; kernel rows whose input row is outside the image are skipped
-    if (warp == 0) {
-      if (elect_one()) {
+  // Round 2: the tile loop is a pipeline over ACCUMULATOR SLOTS (one output row of 128 pixels x 64 channels each, 5 of them in
+  // TMEM).  Warp 8 fills the patch and issues the MMAs row by row, committing each row to its slot's barrier; the 8 epilogue
+  // warps drain a slot as soon as it is complete and hand it back.  For the interior class (5 rows per tile) the epilogue of rows
+  // 0..3 runs under the MMAs of rows 1..4 and the last row's under the next tile's patch copy and first row; for the one-row
+  // border classes up to five tiles' accumulators are in flight.  Before (fill -> all MMAs -> all epilogues, one barrier each)
+  // a 5-row tile took 15 us for 7 us of MMA.  The patch is single-buffered (75 KB next to 117 KB of weights): the copy of the
+  // next tile starts when the last MMA of this tile has retired.
+  // patch buffers: the one-row border classes need at most 14 input rows, so two of their patches fit the 35-row patch area and
+  // the copy of tile t + 1 runs under the MMAs of tile t; the interior class (35 rows) has one buffer
+  const int NP = 2 * prow <= SF_MAXROWS ? 2 : 1;
+  const uint32_t buf_bytes = (uint32_t)prow * SF_ROWB;
+  if (warp == SF_EPI_WARPS + 1) {
+    // ===================================================================== patch producer (one lane)
+    // the input lives as channel-interleaved bf16 words with a 9-word zero margin on the left (and zeros on the right), so the
+    // window row of a segment is the 16-byte aligned span [4 wo0, 4 wo0 + SF_PW) of the padded row: one bulk copy per input
+    // row, no bounds logic.  Rows outside the image are not loaded (their MMAs are skipped).
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = cta_in_cls; tile < n_tiles; tile += n_cta_cls, ++it) {
+        const int pb = NP == 2 ? (it & 1) : 0, use = NP == 2 ? (it >> 1) : it;       // use-th fill of buffer pb
+        const int sg = tile % p.n_seg, bb = tile / p.n_seg;
+        const uint32_t* src = xb + ((int64_t)bb * p.H + hi_lo) * p.xpitch + 4 * sg * SF_SEG;
+        uint8_t* dst = sP + (size_t)pb * buf_bytes;
+        for (int g = 0; g < n_grp; ++g) {
+          const int r0 = s_grp[4 * g], r1 = s_grp[4 * g + 1], L = s_grp[4 * g + 3];
+          if (use > 0) mbar_wait(&row_done[pb * SF_NACC + L], (uint32_t)(use - 1) & 1u);   // its last reader of the previous tile is done
+          uint64_t* fb = &grp_full[pb * SF_MAXGRP + g];
+          mbar_expect_tx(fb, (uint32_t)(r1 - ((p.dbg & 4) ? r1 - 1 : r0)) * SF_ROWB);
+          for (int rr = (p.dbg & 4) ? r1 - 1 : r0; rr < r1; ++rr) sf_bulk_g2s(dst + rr * SF_ROWB, src + (int64_t)rr * p.xpitch, SF_ROWB, fb);
+        }
+      }
+    }
+  } else if (warp == SF_EPI_WARPS) {
+    // ===================================================================== MMA issue (whole warp walks, one lane issues)
+    // A lone thread retires an instruction every 5 - 10 cycles and the tensor pipe queues one MMA behind the running one: the
+    // descriptors are running sums (134 sixteen-byte units per patch row, 48 per kernel row of the weights), 2 adds per MMA -
+    // the first version rebuilt each with shift / mask / or (13 instructions per MMA, 63 - 76 cycles per 48-cycle MMA).
+    constexpr uint32_t A_HI = (128u >> 4) | (1u << 14);                   // SBO 128 B, descriptor version 1, no swizzle
+    constexpr uint32_t B_HI = ((uint32_t)SF_SBO_W >> 4) | (1u << 14);
+    const uint32_t a_lo0 = ((smem_u32(sP) & 0x3FFFFu) >> 4) | ((16u >> 4) << 16);      // LBO 16 B: overlapping 32-byte windows
+    const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+    uint32_t slot = 0, sph = 0;
+    int it = 0;
+    for (int tile = cta_in_cls; tile < n_tiles; tile += n_cta_cls, ++it) {
+      const int pb = NP == 2 ? (it & 1) : 0, use = NP == 2 ? (it >> 1) : it;
+      const uint32_t a_buf = a_lo0 + (uint32_t)pb * (buf_bytes >> 4);
+      int g = 0;
+      for (int j = 0; j < nrow; ++j) {
+        while (g < n_grp && s_grp[4 * g + 2] <= j) {                       // the row groups this output row is the first to read
+          mbar_wait(&grp_full[pb * SF_MAXGRP + g], (uint32_t)use & 1u);
+          ++g;
+        }
+        mbar_wait(&acc_empty[slot], sph ^ 1);      // drained by the epilogue (free on the first lap)
         tc_fence_after();
-        for (int j = 0; j < nrow; ++j) {
+        if (elect_one()) {
+          // one accumulator per output row; kernel rows whose input row is outside the image are skipped
           const int hi_base = 4 * (ho0 + j) - 9;
+          const int dh_lo = hi_base < 0 ? -hi_base : 0, dh_hi = p.H - hi_base < SF_KD ? p.H - hi_base : SF_KD;
+          uint32_t a_lo = a_buf + (uint32_t)(hi_base + dh_lo - hi_lo) * (SF_ROWB >> 4);
+          uint32_t b_lo = b_lo0 + (uint32_t)dh_lo * 48u;                  // 3 K steps x 256 B per kernel row
+          const uint32_t d = tmem_base + slot * 64u;
           uint32_t acc = 0u;
-          for (int dh = 0; dh < SF_KD; ++dh) {
-            const int hi = hi_base + dh;
-            if (hi < 0 || hi >= p.H) continue;
-            const uint32_t a0 = p_addr + (uint32_t)(hi - hi_lo) * SF_ROWB;
-            const uint32_t b0 = b_addr + (uint32_t)(dh * 3) * 256u;
+          for (int dh = (p.dbg & 2) ? dh_hi : dh_lo; dh < dh_hi; ++dh) {
+            umma_bf16(d, ((uint64_t)A_HI << 32) | a_lo, ((uint64_t)B_HI << 32) | b_lo, p.idesc, acc);
+            umma_bf16(d, ((uint64_t)A_HI << 32) | (a_lo + 2u), ((uint64_t)B_HI << 32) | (b_lo + 16u), p.idesc, 1u);
+            umma_bf16(d, ((uint64_t)A_HI << 32) | (a_lo + 4u), ((uint64_t)B_HI << 32) | (b_lo + 32u), p.idesc, 1u);
+            acc = 1u;
+            a_lo += SF_ROWB >> 4;
+            b_lo += 48u;
+          }
+          umma_commit(&acc_full[slot]);
+          umma_commit(&row_done[pb * SF_NACC + j]);
+        }
+        __syncwarp();
+        if (++slot == SF_NACC) { slot = 0; sph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue: bias + ReLU, bf16, flat halo layout
+    // thread = (pixel r, 32-channel half); the rows of a class are adjacent in memory (h fastest)
+    const int q = warp & 3, half = warp >> 2;     // TMEM lane quadrant, channel half
+    const int r = q * 32 + lane;                  // pixel inside the segment
+    uint32_t slot = 0, sph = 0;
+    for (int tile = cta_in_cls; tile < n_tiles; tile += n_cta_cls) {
+      const int seg = tile % p.n_seg, b = tile / p.n_seg;
+      const int wo = seg * SF_SEG + r;
+      const bool ok = wo < p.Wo - p.skip_hi && wo >= p.skip_lo && !(p.dbg & 1);
+      for (int j = 0; j < nrow; ++j) {
+        mbar_wait(&acc_full[slot], sph);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64 + half * 32), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[slot])) : "memory");
+        }
+        if (ok) {
+          uint4* op = reinterpret_cast<uint4*>(out + (((int64_t)b * p.Wp + wo) * p.Hp + (ho0 + j)) * 64 + half * 32);
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              umma_bf16(tmem_base + (uint32_t)(j * 64), sf_nosw_desc(a0 + s * 32, 16, 128), sf_nosw_desc(b0 + s * 256, 128, SF_SBO_W),
-                        p.idesc, acc);
-              acc = 1u;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = half * 32 + j4 * 8 + e * 2;
+              const float f0 = fmaxf(__uint_as_float(v[j4 * 8 + e * 2]) + s_bias[c], 0.0f);
+              const float f1 = fmaxf(__uint_as_float(v[j4 * 8 + e * 2 + 1]) + s_bias[c + 1], 0.0f);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+              w[e] = *reinterpret_cast<uint32_t*>(&h2);
             }
+            op[j4] = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
-        umma_commit(mma_bar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(mma_bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    if (tid == 0 && tile + n_cta_cls < n_tiles) issue_fill(tile + n_cta_cls);   // the patch is free: the MMAs that read it are done
-    // (3) epilogue: bias + ReLU, bf16, flat halo layout; thread = (pixel r, 32-channel half); the rows of a class are adjacent
-    //     in memory (h fastest), so a thread's stores of consecutive rows are contiguous
-    const int wo = wo0 + r;
-    const bool ok = wo < p.Wo - p.skip_hi && wo >= p.skip_lo;
-    for (int j = 0; j < nrow; ++j) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + half * 32), v);
-      tmem_ld_wait();
-      if (ok) {
-        uint4* op = reinterpret_cast<uint4*>(out + (((int64_t)b * p.Wp + wo) * p.Hp + (ho0 + j)) * 64 + half * 32);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = half * 32 + j4 * 8 + e * 2;
-            const float f0 = fmaxf(__uint_as_float(v[j4 * 8 + e * 2]) + s_bias[c], 0.0f);
-            const float f1 = fmaxf(__uint_as_float(v[j4 * 8 + e * 2 + 1]) + s_bias[c + 1], 0.0f);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-            w[e] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          op[j4] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        if (++slot == SF_NACC) { slot = 0; sph ^= 1; }
       }
     }
-    tc_fence_before();
-    __syncthreads();       // accumulators drained before the next tile overwrites them / the patch is refilled
   }
+  tc_fence_before();
+  __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, SF_TMEM_COLS);
 }
 
@@ -299,7 +386,7 @@ stem_fixup_bf16_kernel(const uint32_t* __restrict__ xb, int64_t xpitch, const St
   }
 }
 
-static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + 64; }
+static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + (2 * SF_MAXGRP + 4 * SF_NACC) * 8 + 16 + SF_MAXGRP * 16; }
 
 int init_conv_stem_fused_attrs() {
   static_assert(SF_ROWB % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -341,7 +428,8 @@ static int conv_stem_fused_impl(const void* x_bf16_padded, int64_t x_pitch, int6
   for (int i = 0; i < 4; ++i) p.row_first[i] = rf[i], p.row_cnt[i] = rc[i];
   const int nsm = sm_count() > 0 ? sm_count() : 148;
   const int64_t n_tiles = B * p.n_seg;
-  int n_int = n_cta_interior > 0 ? n_cta_interior : (nsm * 62) / 100;      // measured balance point of the four classes (tools/stem_sweep.py)
+  int n_int = n_cta_interior > 0 ? n_cta_interior : (nsm * 70) / 100;      // measured balance point of the four classes (tools/stem_sweep.py;
+                                                                           // 62 % before the kernel was pipelined over accumulator slots)
   if (n_int > nsm - 3) n_int = nsm - 3;
   if (n_int < 1) n_int = 1;
   int rest = nsm - n_int;
@@ -355,6 +443,8 @@ static int conv_stem_fused_impl(const void* x_bf16_padded, int64_t x_pitch, int6
   p.cta_first[4] = n_int + n1 + n2 + n3;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   YAD_CHECK_ARG(skip_lo >= 0 && skip_hi >= 0 && skip_lo + skip_hi <= p.Wo, "yad_conv_stem_fused: bad skipped column counts");
+  static const int stem_dbg = [] { const char* e = getenv("YAD_STEM_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = stem_dbg;
   p.skip_lo = skip_lo;
   p.skip_hi = skip_hi;
   YAD_CUDA(launch_pdl(conv_stem_fused_kernel, dim3((unsigned)p.cta_first[4]), dim3(SF_THREADS), stem_fused_smem_bytes(), (cudaStream_t)stream,
