@@ -21,6 +21,8 @@
 #include "common.cuh"
 #include "fft500.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace yad {
 
@@ -697,6 +699,157 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
   }
 }
 
+// Stage B, cluster form (round 2, last session): the one-pass kernel above keeps ONE 1024-thread CTA per SM (123 KB of parked
+// dB-mel columns), so every block-wide reduction and every phase change (HBM-latency-bound load, issue-bound dB / DCT, store) idles
+// the whole SM.  Here a clip is split over a CLUSTER of two 512-thread CTAs (frames [0, T/2) and [T/2, T)); the two maxima and the
+// four moments are combined through distributed shared memory (each CTA parks its partial, one cluster barrier, both read both
+// partials in rank order: identical bits in both CTAs and for every batch position).  Two CTAs of DIFFERENT clips share an SM
+// (61 KB + 64 registers x 512 threads each), so one clip's load / reduction phases run under the other's arithmetic.
+// Same operation order per element as frontend_finish_v2_kernel; the fp64 moments are summed per half, then half 0 + half 1.
+constexpr int FB3_THREADS = 512;
+
+__device__ __forceinline__ double ld_cluster_f64(const double* p, uint32_t rank) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(mapa_u32(p, rank)) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(FB3_THREADS, 2)
+frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, const float* __restrict__ dct, float top_db,
+                          int standardise, float* __restrict__ xs, float* __restrict__ tap_meldb, float* __restrict__ tap_mfcc,
+                          float* __restrict__ tap_mfdb, uint32_t* __restrict__ xs_bf16, int64_t bf_pitch, int bf_margin) {
+  extern __shared__ __align__(16) float fb3_smem[];
+  float* s_dct = fb3_smem;                       // [32][32]
+  float* s_x = fb3_smem + FE_NMEL * FE_NMEL;     // [32][TH]
+  __shared__ float s_redf[32];
+  __shared__ double s_red4[32 * 4];
+  __shared__ __align__(8) double s_part[8];      // this CTA's partials for the cluster: 0 max of mel, 1 max of MFCC, 2..5 moments
+  const uint32_t rank = cluster_ctarank();
+  const int TH = (int)((T + 1) / 2);             // frames per CTA
+  const int lt = threadIdx.x;
+  const int64_t t = (int64_t)rank * TH + lt;
+  const bool act = lt < TH && t < T;
+  for (int i = threadIdx.x; i < FE_NMEL * FE_NMEL; i += blockDim.x) s_dct[i] = dct[i];
+  pdl_wait();          // programmatic dependent launch: stage A's mel plane is complete and visible from here
+  pdl_trigger();
+  auto fmax_op = [](float a, float c) { return fmaxf(a, c); };
+  const int64_t n_clusters = gridDim.x >> 1;
+  for (int64_t b = blockIdx.x >> 1; b < B; b += n_clusters) {
+    const float* mb = mel + b * FE_NMEL * T;
+    float* o0 = xs + (b * 2 + 0) * FE_NMEL * T;
+    float* o1 = xs + (b * 2 + 1) * FE_NMEL * T;
+    // 1: mel column -> smem, clip maximum (10 log10(max(., 1e-10)) is monotonic: the maximum of the dB plane is the dB of the maximum)
+    float mx = 0.0f;
+    if (act) {
+#pragma unroll 8
+      for (int m = 0; m < FE_NMEL; ++m) {
+        const float v = __ldg(mb + m * T + t);
+        s_x[m * TH + lt] = v;
+        mx = fmaxf(mx, v);
+      }
+    }
+    mx = block_reduce_n<float>(mx, s_redf, fmax_op, 0.0f);
+    if (threadIdx.x == 0) s_part[0] = (double)mx;
+    cluster_sync_all();
+    const float floor1 = to_db(fmaxf((float)ld_cluster_f64(&s_part[0], 0), (float)ld_cluster_f64(&s_part[0], 1))) - top_db;
+    // 2: clamped dB-mel (parked in smem), MFCC column in registers, moments of the dB-mel plane
+    float2 mf2[FE_NMEL / 2];       // MFCC column as register pairs: the DCT advances two coefficients per FFMA2
+#pragma unroll
+    for (int k = 0; k < FE_NMEL / 2; ++k) mf2[k] = make_float2(0.0f, 0.0f);
+    double s0 = 0.0, q0 = 0.0;
+    float mxf = -INFINITY;
+    if (act) {
+      for (int m = 0; m < FE_NMEL; ++m) {
+        const float x = fmaxf(to_db(s_x[m * TH + lt]), floor1);
+        s_x[m * TH + lt] = x;
+        s0 += (double)x;
+        q0 += (double)x * (double)x;
+        const float4* dr = reinterpret_cast<const float4*>(s_dct + m * FE_NMEL);
+#pragma unroll
+        for (int k4 = 0; k4 < FE_NMEL / 4; ++k4) {
+          const float4 d4 = dr[k4];
+          const float2 xx = make_float2(x, x);
+          mf2[k4 * 2 + 0] = __ffma2_rn(xx, make_float2(d4.x, d4.y), mf2[k4 * 2 + 0]);
+          mf2[k4 * 2 + 1] = __ffma2_rn(xx, make_float2(d4.z, d4.w), mf2[k4 * 2 + 1]);
+        }
+      }
+    }
+    float* mf = reinterpret_cast<float*>(mf2);      // the same registers, scalar view (all indices below are compile-time)
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < FE_NMEL; ++k) {
+        if (tap_mfcc) tap_mfcc[(b * FE_NMEL + k) * T + t] = mf[k];
+        mxf = fmaxf(mxf, mf[k]);
+      }
+    }
+    mxf = block_reduce_n<float>(mxf, s_redf, fmax_op, -INFINITY);
+    if (threadIdx.x == 0) s_part[1] = (double)mxf;
+    cluster_sync_all();
+    const float floor2 = to_db(fmaxf((float)ld_cluster_f64(&s_part[1], 0), (float)ld_cluster_f64(&s_part[1], 1))) - top_db;
+    // 3: clamped dB(MFCC) in registers and its moments
+    double s1 = 0.0, q1 = 0.0;
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < FE_NMEL; ++k) {
+        const float yf = fmaxf(to_db(mf[k]), floor2);
+        mf[k] = yf;
+        s1 += (double)yf;
+        q1 += (double)yf * (double)yf;
+      }
+    }
+    const double n_el = (double)FE_NMEL * (double)T;
+    float mu0 = 0.0f, mu1 = 0.0f, sd0 = 1.0f, sd1 = 1.0f;
+    if (standardise) {
+      double m4[4] = {s0, q0, s1, q1};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m4[i] += __shfl_xor_sync(0xffffffffu, m4[i], o);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_red4[(threadIdx.x >> 5) * 4 + i] = m4[i];
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+        double a = 0.0;
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) a += s_red4[w * 4 + threadIdx.x];
+        s_part[2 + threadIdx.x] = a;
+      }
+      cluster_sync_all();
+      const double S0 = ld_cluster_f64(&s_part[2], 0) + ld_cluster_f64(&s_part[2], 1);
+      const double Q0 = ld_cluster_f64(&s_part[3], 0) + ld_cluster_f64(&s_part[3], 1);
+      const double S1 = ld_cluster_f64(&s_part[4], 0) + ld_cluster_f64(&s_part[4], 1);
+      const double Q1 = ld_cluster_f64(&s_part[5], 0) + ld_cluster_f64(&s_part[5], 1);
+      mu0 = (float)(S0 / n_el);
+      mu1 = (float)(S1 / n_el);
+      sd0 = (float)sqrt(fmax(Q0 - S0 * S0 / n_el, 0.0) / (n_el - 1.0));
+      sd1 = (float)sqrt(fmax(Q1 - S1 * S1 / n_el, 0.0) / (n_el - 1.0));
+    }
+    // 4: standardise and write both planes once
+    const float den0 = sd0 + 1e-5f, den1 = sd1 + 1e-5f;
+    if (act) {
+#pragma unroll
+      for (int m = 0; m < FE_NMEL; ++m) {
+        const float x = s_x[m * TH + lt];
+        if (tap_meldb) tap_meldb[(b * FE_NMEL + m) * T + t] = x;
+        if (tap_mfdb) tap_mfdb[(b * FE_NMEL + m) * T + t] = mf[m];
+        const float v0 = standardise ? __fdiv_rn(x - mu0, den0) : x;
+        const float v1 = standardise ? __fdiv_rn(mf[m] - mu1, den1) : mf[m];
+        o0[m * T + t] = v0;
+        o1[m * T + t] = v1;
+        if (xs_bf16 != nullptr) {      // channel-interleaved bf16 copy with zero margins: the fused stem's patch rows (bulk-copied)
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+          xs_bf16[(b * FE_NMEL + m) * bf_pitch + bf_margin + t] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+      }
+    }
+    __syncthreads();     // s_x is reused by the next clip (s_part: see the ordering argument in DESIGN.md 5.6)
+  }
+  cluster_sync_all();    // the peer may still be reading this CTA's partials
+}
+
 static size_t fe_smem_bytes(int SX, int nnz_pad) {
   const int sxp = (SX + 16 + 7) & ~7;
   return (size_t)(2 * sxp + 2 * FE_FR_WORDS + FE_Y_WORDS + ((FE_FR * FE_P_STRIDE + 3) & ~3) + 2 * FE_NFFT + 1000 + FE_NFFT + nnz_pad +
@@ -718,6 +871,9 @@ int init_frontend_attrs() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(frontend_finish_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((FE_NMEL * FE_NMEL + FE_NMEL * FB2_MAXT) * sizeof(float)));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(frontend_finish_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)((FE_NMEL * FE_NMEL + FE_NMEL * (FB2_MAXT / 2)) * sizeof(float)));
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(frontend_mel_kernel) failed: %s", cudaGetErrorString(e));
     return YAD_ERR_CUDA;
@@ -823,6 +979,34 @@ static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const fl
   if (B == 0) return YAD_OK;
   if (T <= yad::FB2_MAXT) {     // one-pass form: thread = frame, dB-mel column in shared memory, MFCC column in registers
     const int nsm = yad::sm_count() > 0 ? yad::sm_count() : 148;
+    static const bool use_cluster = [] {
+      const char* e = getenv("YAD_FE_FINISH_CLUSTER");
+      return !(e && e[0] == '0');
+    }();
+    if (use_cluster && T >= 64) {     // a clip per cluster of two CTAs (frontend_finish_v3_kernel)
+      const int TH = (int)((T + 1) / 2);
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(2 * (B < nsm ? B : nsm)));
+      cfg.blockDim = dim3((unsigned)((TH + 31) / 32 * 32));
+      cfg.dynamicSmemBytes = (size_t)(yad::FE_NMEL * yad::FE_NMEL + yad::FE_NMEL * TH) * sizeof(float);
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[2];
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      int mode = yad::pdl_mode();
+      if (mode == 1 && cudaStreamIsCapturing(cfg.stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) mode = 0;
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = mode ? 1 : 0;
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim.x = 2;
+      attr[1].val.clusterDim.y = 1;
+      attr[1].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 2;
+      YAD_CUDA(cudaLaunchKernelEx(&cfg, yad::frontend_finish_v3_kernel, mel, B, T, dct, top_db, (int)standardise, x_spectral, tap_meldb,
+                                  tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, (int)bf_margin));
+      return YAD_OK;
+    }
     const unsigned grid = (unsigned)(B < nsm ? B : nsm);
     const unsigned threads = (unsigned)((T + 31) / 32 * 32);
     const size_t smem = (size_t)(yad::FE_NMEL * yad::FE_NMEL + yad::FE_NMEL * T) * sizeof(float);
