@@ -717,7 +717,7 @@ __device__ __forceinline__ double ld_cluster_f64(const double* p, uint32_t rank)
 __global__ void __launch_bounds__(FB3_THREADS, 2)
 frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, const float* __restrict__ dct, float top_db,
                           int standardise, float* __restrict__ xs, float* __restrict__ tap_meldb, float* __restrict__ tap_mfcc,
-                          float* __restrict__ tap_mfdb, uint32_t* __restrict__ xs_bf16, int64_t bf_pitch, int bf_margin) {
+                          float* __restrict__ tap_mfdb, uint32_t* __restrict__ xs_bf16, int64_t bf_pitch, int bf_margin, int CS) {
   extern __shared__ __align__(16) float fb3_smem[];
   float* s_dct = fb3_smem;                       // [32][32]
   float* s_x = fb3_smem + FE_NMEL * FE_NMEL;     // [32][TH]
@@ -725,7 +725,7 @@ frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
   __shared__ double s_red4[32 * 4];
   __shared__ __align__(8) double s_part[8];      // this CTA's partials for the cluster: 0 max of mel, 1 max of MFCC, 2..5 moments
   const uint32_t rank = cluster_ctarank();
-  const int TH = (int)((T + 1) / 2);             // frames per CTA
+  const int TH = (int)((T + CS - 1) / CS);       // frames per CTA (CS = CTAs per cluster = per clip)
   const int lt = threadIdx.x;
   const int64_t t = (int64_t)rank * TH + lt;
   const bool act = lt < TH && t < T;
@@ -733,8 +733,8 @@ frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
   pdl_wait();          // programmatic dependent launch: stage A's mel plane is complete and visible from here
   pdl_trigger();
   auto fmax_op = [](float a, float c) { return fmaxf(a, c); };
-  const int64_t n_clusters = gridDim.x >> 1;
-  for (int64_t b = blockIdx.x >> 1; b < B; b += n_clusters) {
+  const int64_t n_clusters = gridDim.x / CS;
+  for (int64_t b = blockIdx.x / CS; b < B; b += n_clusters) {
     const float* mb = mel + b * FE_NMEL * T;
     float* o0 = xs + (b * 2 + 0) * FE_NMEL * T;
     float* o1 = xs + (b * 2 + 1) * FE_NMEL * T;
@@ -751,7 +751,9 @@ frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
     mx = block_reduce_n<float>(mx, s_redf, fmax_op, 0.0f);
     if (threadIdx.x == 0) s_part[0] = (double)mx;
     cluster_sync_all();
-    const float floor1 = to_db(fmaxf((float)ld_cluster_f64(&s_part[0], 0), (float)ld_cluster_f64(&s_part[0], 1))) - top_db;
+    float gm = 0.0f;
+    for (int rk = 0; rk < CS; ++rk) gm = fmaxf(gm, (float)ld_cluster_f64(&s_part[0], rk));
+    const float floor1 = to_db(gm) - top_db;
     // 2: clamped dB-mel (parked in smem), MFCC column in registers, moments of the dB-mel plane
     float2 mf2[FE_NMEL / 2];       // MFCC column as register pairs: the DCT advances two coefficients per FFMA2
 #pragma unroll
@@ -785,7 +787,9 @@ frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
     mxf = block_reduce_n<float>(mxf, s_redf, fmax_op, -INFINITY);
     if (threadIdx.x == 0) s_part[1] = (double)mxf;
     cluster_sync_all();
-    const float floor2 = to_db(fmaxf((float)ld_cluster_f64(&s_part[1], 0), (float)ld_cluster_f64(&s_part[1], 1))) - top_db;
+    float gf = -INFINITY;
+    for (int rk = 0; rk < CS; ++rk) gf = fmaxf(gf, (float)ld_cluster_f64(&s_part[1], rk));
+    const float floor2 = to_db(gf) - top_db;
     // 3: clamped dB(MFCC) in registers and its moments
     double s1 = 0.0, q1 = 0.0;
     if (act) {
@@ -818,10 +822,13 @@ frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
         s_part[2 + threadIdx.x] = a;
       }
       cluster_sync_all();
-      const double S0 = ld_cluster_f64(&s_part[2], 0) + ld_cluster_f64(&s_part[2], 1);
-      const double Q0 = ld_cluster_f64(&s_part[3], 0) + ld_cluster_f64(&s_part[3], 1);
-      const double S1 = ld_cluster_f64(&s_part[4], 0) + ld_cluster_f64(&s_part[4], 1);
-      const double Q1 = ld_cluster_f64(&s_part[5], 0) + ld_cluster_f64(&s_part[5], 1);
+      double S0 = 0.0, Q0 = 0.0, S1 = 0.0, Q1 = 0.0;      // rank order: the same bits in every CTA of the cluster
+      for (int rk = 0; rk < CS; ++rk) {
+        S0 += ld_cluster_f64(&s_part[2], rk);
+        Q0 += ld_cluster_f64(&s_part[3], rk);
+        S1 += ld_cluster_f64(&s_part[4], rk);
+        Q1 += ld_cluster_f64(&s_part[5], rk);
+      }
       mu0 = (float)(S0 / n_el);
       mu1 = (float)(S1 / n_el);
       sd0 = (float)sqrt(fmax(Q0 - S0 * S0 / n_el, 0.0) / (n_el - 1.0));
@@ -984,10 +991,12 @@ static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const fl
       return !(e && e[0] == '0');
     }();
     if (use_cluster && T >= 64) {     // a clip per cluster of two CTAs (frontend_finish_v3_kernel)
-      const int TH = (int)((T + 1) / 2);
+      static const int cs_env = [] { const char* e = getenv("YAD_FE_FINISH_CS"); return e ? atoi(e) : 2; }();
+      const int CS = (cs_env == 4 && T >= 128) ? 4 : 2;
+      const int TH = (int)((T + CS - 1) / CS);
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3((unsigned)(2 * (B < nsm ? B : nsm)));
+      cfg.gridDim = dim3((unsigned)(CS * (B < nsm ? B : nsm)));
       cfg.blockDim = dim3((unsigned)((TH + 31) / 32 * 32));
       cfg.dynamicSmemBytes = (size_t)(yad::FE_NMEL * yad::FE_NMEL + yad::FE_NMEL * TH) * sizeof(float);
       cfg.stream = (cudaStream_t)stream;
@@ -998,13 +1007,13 @@ static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const fl
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = mode ? 1 : 0;
       attr[1].id = cudaLaunchAttributeClusterDimension;
-      attr[1].val.clusterDim.x = 2;
+      attr[1].val.clusterDim.x = (unsigned)CS;
       attr[1].val.clusterDim.y = 1;
       attr[1].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 2;
       YAD_CUDA(cudaLaunchKernelEx(&cfg, yad::frontend_finish_v3_kernel, mel, B, T, dct, top_db, (int)standardise, x_spectral, tap_meldb,
-                                  tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, (int)bf_margin));
+                                  tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, (int)bf_margin, CS));
       return YAD_OK;
     }
     const unsigned grid = (unsigned)(B < nsm ? B : nsm);
