@@ -714,6 +714,7 @@ __device__ __forceinline__ double ld_cluster_f64(const double* p, uint32_t rank)
   return v;
 }
 
+template <typename ACC>
 __global__ void __launch_bounds__(FB3_THREADS, 2)
 frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, const float* __restrict__ dct, float top_db,
                           int standardise, float* __restrict__ xs, float* __restrict__ tap_meldb, float* __restrict__ tap_mfcc,
@@ -758,14 +759,14 @@ frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
     float2 mf2[FE_NMEL / 2];       // MFCC column as register pairs: the DCT advances two coefficients per FFMA2
 #pragma unroll
     for (int k = 0; k < FE_NMEL / 2; ++k) mf2[k] = make_float2(0.0f, 0.0f);
-    double s0 = 0.0, q0 = 0.0;
+    ACC s0 = 0, q0 = 0;
     float mxf = -INFINITY;
     if (act) {
       for (int m = 0; m < FE_NMEL; ++m) {
         const float x = fmaxf(to_db(s_x[m * TH + lt]), floor1);
         s_x[m * TH + lt] = x;
-        s0 += (double)x;
-        q0 += (double)x * (double)x;
+        s0 += (ACC)x;
+        q0 += (ACC)x * (ACC)x;
         const float4* dr = reinterpret_cast<const float4*>(s_dct + m * FE_NMEL);
 #pragma unroll
         for (int k4 = 0; k4 < FE_NMEL / 4; ++k4) {
@@ -791,20 +792,20 @@ frontend_finish_v3_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
     for (int rk = 0; rk < CS; ++rk) gf = fmaxf(gf, (float)ld_cluster_f64(&s_part[1], rk));
     const float floor2 = to_db(gf) - top_db;
     // 3: clamped dB(MFCC) in registers and its moments
-    double s1 = 0.0, q1 = 0.0;
+    ACC s1 = 0, q1 = 0;
     if (act) {
 #pragma unroll
       for (int k = 0; k < FE_NMEL; ++k) {
         const float yf = fmaxf(to_db(mf[k]), floor2);
         mf[k] = yf;
-        s1 += (double)yf;
-        q1 += (double)yf * (double)yf;
+        s1 += (ACC)yf;
+        q1 += (ACC)yf * (ACC)yf;
       }
     }
     const double n_el = (double)FE_NMEL * (double)T;
     float mu0 = 0.0f, mu1 = 0.0f, sd0 = 1.0f, sd1 = 1.0f;
     if (standardise) {
-      double m4[4] = {s0, q0, s1, q1};
+      double m4[4] = {(double)s0, (double)q0, (double)s1, (double)q1};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -879,7 +880,10 @@ int init_frontend_attrs() {
     e = cudaFuncSetAttribute(frontend_finish_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((FE_NMEL * FE_NMEL + FE_NMEL * FB2_MAXT) * sizeof(float)));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(frontend_finish_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(frontend_finish_v3_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)((FE_NMEL * FE_NMEL + FE_NMEL * (FB2_MAXT / 2)) * sizeof(float)));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(frontend_finish_v3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((FE_NMEL * FE_NMEL + FE_NMEL * (FB2_MAXT / 2)) * sizeof(float)));
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(frontend_mel_kernel) failed: %s", cudaGetErrorString(e));
@@ -1012,7 +1016,12 @@ static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const fl
       attr[1].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 2;
-      YAD_CUDA(cudaLaunchKernelEx(&cfg, yad::frontend_finish_v3_kernel, mel, B, T, dct, top_db, (int)standardise, x_spectral, tap_meldb,
+      static const bool dbg_f32 = [] { const char* e = getenv("YAD_FE_DBG_F32ACC"); return e && e[0] == '1'; }();   // timing experiment only
+      if (dbg_f32)
+        YAD_CUDA(cudaLaunchKernelEx(&cfg, yad::frontend_finish_v3_kernel<float>, mel, B, T, dct, top_db, (int)standardise, x_spectral, tap_meldb,
+                                    tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, (int)bf_margin, CS));
+      else
+      YAD_CUDA(cudaLaunchKernelEx(&cfg, yad::frontend_finish_v3_kernel<double>, mel, B, T, dct, top_db, (int)standardise, x_spectral, tap_meldb,
                                   tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, (int)bf_margin, CS));
       return YAD_OK;
     }
