@@ -706,6 +706,7 @@ frontend_finish_v2_kernel(const float* __restrict__ mel, int64_t B, int64_t T, c
 // partials in rank order: identical bits in both CTAs and for every batch position).  Two CTAs of DIFFERENT clips share an SM
 // (61 KB + 64 registers x 512 threads each), so one clip's load / reduction phases run under the other's arithmetic.
 // Same operation order per element as frontend_finish_v2_kernel; the fp64 moments are summed per half, then half 0 + half 1.
+// (ACC = float was a timing experiment: no difference, the fp64 pipe is not what limits this kernel.)
 constexpr int FB3_THREADS = 512;
 
 __device__ __forceinline__ double ld_cluster_f64(const double* p, uint32_t rank) {
@@ -882,9 +883,6 @@ int init_frontend_attrs() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(frontend_finish_v3_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((FE_NMEL * FE_NMEL + FE_NMEL * (FB2_MAXT / 2)) * sizeof(float)));
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(frontend_finish_v3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)((FE_NMEL * FE_NMEL + FE_NMEL * (FB2_MAXT / 2)) * sizeof(float)));
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(frontend_mel_kernel) failed: %s", cudaGetErrorString(e));
     return YAD_ERR_CUDA;
@@ -1016,11 +1014,6 @@ static int frontend_finish_impl(const float* mel, int64_t B, int64_t T, const fl
       attr[1].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 2;
-      static const bool dbg_f32 = [] { const char* e = getenv("YAD_FE_DBG_F32ACC"); return e && e[0] == '1'; }();   // timing experiment only
-      if (dbg_f32)
-        YAD_CUDA(cudaLaunchKernelEx(&cfg, yad::frontend_finish_v3_kernel<float>, mel, B, T, dct, top_db, (int)standardise, x_spectral, tap_meldb,
-                                    tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, (int)bf_margin, CS));
-      else
       YAD_CUDA(cudaLaunchKernelEx(&cfg, yad::frontend_finish_v3_kernel<double>, mel, B, T, dct, top_db, (int)standardise, x_spectral, tap_meldb,
                                   tap_mfcc, tap_mfdb, reinterpret_cast<uint32_t*>(xs_bf16), bf_pitch, (int)bf_margin, CS));
       return YAD_OK;
