@@ -94,6 +94,31 @@ __device__ __forceinline__ uint64_t nk_desc(uint32_t smem_addr) {
 // the same from a precomputed low word ((address >> 4) | 1 << 16): adding 8 per row, 2 per 16 K elements needs no re-masking
 __device__ __forceinline__ uint64_t nk_desc64(uint32_t lo) { return ((uint64_t)NK_DESC_HI << 32) | (uint64_t)lo; }
 
+// element-wise maximum of 8 packed bf16 values
+__device__ __forceinline__ uint4 nk_max_bf16x8(const uint4 a, const uint4 b) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t rw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]), *reinterpret_cast<const __nv_bfloat162*>(&bw[e]));
+    rw[e] = *reinterpret_cast<const uint32_t*>(&m);
+  }
+  return make_uint4(rw[0], rw[1], rw[2], rw[3]);
+}
+// 0.75 a + 0.25 b on 8 packed bf16 values, rounded once
+__device__ __forceinline__ uint4 nk_lerp_bf16x8(const uint4 a, const uint4 b) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t rw[4];
+  const __nv_bfloat162 c75 = __floats2bfloat162_rn(0.75f, 0.75f), c25 = __floats2bfloat162_rn(0.25f, 0.25f);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 q = __hmul2(c25, *reinterpret_cast<const __nv_bfloat162*>(&bw[e]));      // exact
+    const __nv_bfloat162 m = __hfma2(c75, *reinterpret_cast<const __nv_bfloat162*>(&aw[e]), q);
+    rw[e] = *reinterpret_cast<const uint32_t*>(&m);
+  }
+  return make_uint4(rw[0], rw[1], rw[2], rw[3]);
+}
+
 // 16-byte chunk j (8 channels) of row s of a plane
 __device__ __forceinline__ uint4* nk_chunk(uint8_t* plane, int s, int j) {
   return reinterpret_cast<uint4*>(plane + s * 128 + ((j ^ (s & 7)) << 4));
@@ -128,8 +153,9 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   uint8_t* ring = base + p.pool_bytes;
   NkOp* s_ops = reinterpret_cast<NkOp*>(ring + (size_t)p.n_slots * NK_SLOT);
   NkKb* s_kbs = reinterpret_cast<NkKb*>(s_ops + p.n_ops);
-  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_kbs + p.n_kb) + 15) & ~(uintptr_t)15);   // float4 loads
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_bias + p.n_bias) + 7) & ~(uintptr_t)7);
+  // (the biases stay in global memory: 7.6 KB of shared memory buy a sixth ring slot on the two-clip plan; the epilogue's
+  // broadcast float4 loads hit L1 after a CTA's first unit)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_kbs + p.n_kb) + 7) & ~(uintptr_t)7);
   uint64_t* empty_bar = full_bar + NK_MAX_SLOTS;
   uint64_t* acc_full = empty_bar + NK_MAX_SLOTS;
   uint64_t* op_done = acc_full + 1;
@@ -139,7 +165,6 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
   // the program, the K-block list and the biases are launch constants (written once at pack time): loaded before pdl_wait
   for (int i = threadIdx.x; i < p.n_ops * NK_OP_WORDS; i += NK_THREADS) reinterpret_cast<int32_t*>(s_ops)[i] = reinterpret_cast<const int32_t*>(g_ops)[i];
   for (int i = threadIdx.x; i < p.n_kb * 2; i += NK_THREADS) reinterpret_cast<int32_t*>(s_kbs)[i] = reinterpret_cast<const int32_t*>(g_kbs)[i];
-  for (int i = threadIdx.x; i < p.n_bias; i += NK_THREADS) s_bias[i] = g_bias[i];
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_in0);
     prefetch_tmap(&map_in1);
@@ -332,7 +357,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
         const int type = op.v[0];
         if (type == NK_CONV) {
           const int n_mt = op.v[1], N = op.v[2], R = op.v[5], Wp = op.v[6], W = op.v[7], head = op.v[11], act = op.v[15];
-          const float* bias = s_bias + op.v[8];
+          const float* bias = g_bias + op.v[8];
           // act(x) = max(x, slope * x): LeakyReLU(0.2), ReLU (slope 0) and identity (slope 1) without a branch per element
           const float slope = act == YAD_ACT_LRELU02 ? 0.2f : (act == YAD_ACT_RELU ? 0.0f : 1.0f);
           mbar_wait(acc_full, acc_phase);
@@ -357,7 +382,7 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
                 if (N == 16 && i4 >= 4) {
                   x[4 * i4] = x[4 * i4 + 1] = x[4 * i4 + 2] = x[4 * i4 + 3] = 0.0f;
                 } else {
-                  const float4 bb = b4[i4];
+                  const float4 bb = __ldg(b4 + i4);
                   const float t0 = __uint_as_float(vv[4 * i4]) + bb.x, t1 = __uint_as_float(vv[4 * i4 + 1]) + bb.y;
                   const float t2 = __uint_as_float(vv[4 * i4 + 2]) + bb.z, t3 = __uint_as_float(vv[4 * i4 + 3]) + bb.w;
                   x[4 * i4] = fmaxf(t0, slope * t0);
@@ -451,64 +476,59 @@ neck_fused_kernel(const __grid_constant__ CUtensorMap map_in0, const __grid_cons
           uint8_t* o2 = base + op.v[3];
           uint8_t* o3 = base + op.v[4];
           const int R = op.v[5], Wp = op.v[6], W = op.v[7];
-          for (int item = te; item < (R + 1) * 8; item += NK_EPI) {
-            const int s = item >> 3, j = item & 7, r = s - 1;
-            const int c = r >= 0 ? r / Wp : 0, w = r - c * Wp;
-            float m1[8], m2[8], m3[8];
+          // packed bf16 maxima (HMNMX2.BF16 on the four words of a chunk: the maximum of bf16 values is exact in bf16, nothing to
+          // unpack or round): 27 instead of ~160 instructions per tap - the op was issue-bound
+          // thread = (chunk j = te & 7, rows s = te / 8 + 32 i): the chunk and the swizzle phase s & 7 are loop invariants and the
+          // (clip, column) of the row is carried along instead of divided out (the ops are latency / issue bound)
+          const int j = te & 7;
+          int r = (te >> 3) - 1, c = 0, w = r;
+          for (int s = te >> 3; s <= R; s += NK_EPI / 8, r += NK_EPI / 8, w += NK_EPI / 8) {
+            while (w >= Wp) { w -= Wp; ++c; }
+            uint4 q1 = make_uint4(0u, 0u, 0u, 0u), q2 = q1, q3 = q1;
             if (r >= 0 && w < W) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) m1[e] = m2[e] = m3[e] = -INFINITY;
+              q1 = q2 = q3 = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);      // -inf
 #pragma unroll
               for (int d = -6; d <= 6; ++d) {
                 const int x = w + d;
                 if (x < 0 || x >= W) continue;
-                float v[8];
-                nk_unpack(*nk_chunk(in, c * Wp + x + 1, j), v);
+                const uint4 v = *nk_chunk(in, c * Wp + x + 1, j);
                 const int ad = d < 0 ? -d : d;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  if (ad <= 2) m1[e] = fmaxf(m1[e], v[e]);
-                  if (ad <= 4) m2[e] = fmaxf(m2[e], v[e]);
-                  m3[e] = fmaxf(m3[e], v[e]);
-                }
+                if (ad <= 2) q1 = nk_max_bf16x8(q1, v);
+                if (ad <= 4) q2 = nk_max_bf16x8(q2, v);
+                q3 = nk_max_bf16x8(q3, v);
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) m1[e] = m2[e] = m3[e] = 0.0f;
             }
-            *nk_chunk(o1, s, j) = nk_pack(m1);
-            *nk_chunk(o2, s, j) = nk_pack(m2);
-            *nk_chunk(o3, s, j) = nk_pack(m3);
+            *nk_chunk(o1, s, j) = q1;
+            *nk_chunk(o2, s, j) = q2;
+            *nk_chunk(o3, s, j) = q3;
           }
         } else if (type == NK_PAIRAVG || type == NK_UP2 || type == NK_DEINT) {
           uint8_t* in = base + op.v[1];
           uint8_t* o1 = base + op.v[2];
           uint8_t* o2 = type == NK_DEINT ? base + op.v[3] : nullptr;
           const int R = op.v[5], Wp = op.v[6], W = op.v[7], Wpi = op.v[8];
-          for (int item = te; item < (R + 1) * 8; item += NK_EPI) {
-            const int s = item >> 3, j = item & 7, r = s - 1;
-            const int c = r >= 0 ? r / Wp : 0, w = r - c * Wp;
+          const int j = te & 7;
+          int r = (te >> 3) - 1, c = 0, w = r;
+          for (int s = te >> 3; s <= R; s += NK_EPI / 8, r += NK_EPI / 8, w += NK_EPI / 8) {
+            while (w >= Wp) { w -= Wp; ++c; }
             uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
             if (r >= 0 && w < W) {
               if (type == NK_DEINT) {
                 ra = *nk_chunk(in, c * Wpi + 2 * w + 1, j);
                 rb = *nk_chunk(in, c * Wpi + 2 * w + 2, j);
-              } else {
+              } else if (type == NK_PAIRAVG) {
                 float a[8], nb[8], v[8];
-                if (type == NK_PAIRAVG) {
-                  nk_unpack(*nk_chunk(in, c * Wpi + 2 * w + 1, j), a);
-                  nk_unpack(*nk_chunk(in, c * Wpi + 2 * w + 2, j), nb);
+                nk_unpack(*nk_chunk(in, c * Wpi + 2 * w + 1, j), a);
+                nk_unpack(*nk_chunk(in, c * Wpi + 2 * w + 2, j), nb);
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = 0.5f * a[e] + 0.5f * nb[e];
-                } else {
-                  const int Wi = W >> 1, k = w >> 1;
-                  const int k2 = (w & 1) ? (k + 1 < Wi ? k + 1 : Wi - 1) : (k > 0 ? k - 1 : 0);
-                  nk_unpack(*nk_chunk(in, c * Wpi + k + 1, j), a);
-                  nk_unpack(*nk_chunk(in, c * Wpi + k2 + 1, j), nb);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = (w & 1) ? (0.75f * a[e] + 0.25f * nb[e]) : (0.25f * nb[e] + 0.75f * a[e]);
-                }
+                for (int e = 0; e < 8; ++e) v[e] = 0.5f * a[e] + 0.5f * nb[e];
                 ra = nk_pack(v);
+              } else {
+                // bilinear x2 (align_corners = False): 0.75 x nearer + 0.25 x farther source column, one bf16 rounding - as packed
+                // bf16 FMAs (0.25 x is exact, the FMA rounds the exact sum once): 12 instead of ~60 instructions per chunk
+                const int Wi = W >> 1, k = w >> 1;
+                const int k2 = (w & 1) ? (k + 1 < Wi ? k + 1 : Wi - 1) : (k > 0 ? k - 1 : 0);
+                ra = nk_lerp_bf16x8(*nk_chunk(in, c * Wpi + k + 1, j), *nk_chunk(in, c * Wpi + k2 + 1, j));
               }
             }
             *nk_chunk(o1, s, j) = ra;
@@ -586,7 +606,7 @@ extern "C" int yad_neck_fused(const void* const* fmaps, const int32_t* fmap_k, c
   YAD_CHECK_ARG(head_ld % 4 == 0 && head_ld >= 4 && head_ld <= 16, "yad_neck_fused: head_ld must be 4..16 floats, a multiple of 4");
   if (B == 0) return YAD_OK;
   const size_t smem = 1024 + (size_t)pool_bytes + (size_t)n_slots * NK_SLOT + (size_t)n_ops * sizeof(NkOp) + (size_t)n_kb * sizeof(NkKb) +
-                      (size_t)n_bias * 4 + 8 + (2 * NK_MAX_SLOTS + 2) * 8 + 16;
+                      8 + (2 * NK_MAX_SLOTS + 2) * 8 + 16;
   YAD_CHECK_ARG(smem <= 227 * 1024, "yad_neck_fused: %zu bytes of shared memory needed", smem);
   CUtensorMap mi[4], mw[3];
   uint32_t a_rows[4];

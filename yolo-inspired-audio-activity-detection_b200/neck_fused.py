@@ -348,7 +348,7 @@ class FusedNeck:
         # units); global-sourced: the 64-channel chunk of the input map
         self.kbs = [(src, 0) if glob else ((res(src) + (1 + sh) * 128) >> 4, 0) for src, sh, glob in self.kbs]
         self.pool_bytes = _ceil(high, 1024)
-        tables = len(self.ops) * 96 + len(self.kbs) * 8 + self.nbias * 4 + 8 + 18 * 8 + 16
+        tables = len(self.ops) * 96 + len(self.kbs) * 8 + 8 + 18 * 8 + 16          # (the biases stay in global memory)
         self.n_slots = min(8, (SMEM_MAX - 1024 - self.pool_bytes - tables) // SLOT)
         need = 1 + max(op[1] for op in self.ops if op[0] == CONV and op[14] >= 0)     # A tiles of one K block + its weight block
         if self.n_slots < need + 1:
