@@ -894,7 +894,7 @@ def test_fused_stem_network_equals_two_conv_path(models, seconds, cuda_dev, monk
     assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
 
 
-@pytest.mark.parametrize("seconds,B", [(2.0, 3), (10.0, 2), (22.0, 5), (60.0, 3)])
+@pytest.mark.parametrize("seconds,B", [(2.0, 3), (10.0, 2), (22.0, 5), (60.0, 3), (120.0, 2)])
 def test_fused_neck_equals_layer_by_layer_neck(models, seconds, B, cuda_dev, monkeypatch):
     """The one-kernel neck (yad_neck_fused: H-means folded into K, every intermediate in shared memory; reference
     modules/_common.py:241-265) against the layer-by-layer neck (YAD_FUSED_NECK=0: yad_hmean + 21 convolutions + glue kernels)
@@ -917,6 +917,31 @@ def test_fused_neck_equals_layer_by_layer_neck(models, seconds, B, cuda_dev, mon
     d = (fused - plain).abs()
     assert d[..., :3].max().item() < 0.1 and d[..., :3].mean().item() < 0.01, (d[..., :3].max().item(), d[..., :3].mean().item())
     assert d[..., 3].max().item() < 0.1 and d[..., 4].max().item() < 1.0
+
+
+@pytest.mark.parametrize("seconds,B", [(2.0, 3), (22.0, 5), (60.0, 3), (60.0, 8)])
+def test_fused_neck_two_clips_per_pass_equals_one(models, seconds, B, cuda_dev, monkeypatch):
+    """Fused neck with two clips per CTA pass (the default: clips of a unit at a power-of-two row pitch, both in one M tile at
+    levels 3 / 4, one weight fetch per pair, the level-1 conv once per clip; csrc/neck_fused.cu) against one clip per pass
+    (YAD_NECK_G=1: the backbone's own W + 1 row pitch).  Same program, same K order per output row: BITWISE equal - including odd
+    batch sizes (the last unit holds one clip and one out-of-range clip) and clips whose halo / padding rows must read back zero
+    for the neighbouring clip's 3-tap convolutions (modules/_common.py:241-265)."""
+    m = models[("deploy", "bf16")]
+    L = int(22050 * seconds) // 4 * 4
+    x = synth.synth_clips(B, L, seed=1700 + int(seconds) + B, silence_tail_every=2).to(cuda_dev)
+    m._engine_cache.clear()
+    two = m(x, combine_scales=True).clone()
+    necks = [v for v in m._engine().__dict__.get("_fused_necks", {}).values() if v is not None]
+    assert necks and necks[0].G == 2
+    monkeypatch.setenv("YAD_NECK_G", "1")
+    m._engine_cache.clear()
+    one = m(x, combine_scales=True).clone()
+    necks = [v for v in m._engine().__dict__.get("_fused_necks", {}).values() if v is not None]
+    assert necks and necks[0].G == 1
+    monkeypatch.delenv("YAD_NECK_G")
+    m._engine_cache.clear()
+    assert torch.isfinite(two).all()
+    assert torch.equal(two, one), float((two - one).abs().max())
 
 
 def _run_with_env(m, x, monkeypatch, env):

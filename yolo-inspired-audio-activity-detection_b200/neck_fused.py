@@ -285,11 +285,11 @@ class FusedNeck:
         self._dump("p3_0", p3[0], 3); self._dump("p3_1", p3[1], 3)
         # ---- BiC2
         c0_2 = P(2)
-        if lv[1]["n_mt"] > 2:
+        if self.G > 1 and lv[1]["n_mt"] > 2:
             # the level-1 map of a unit spans more M tiles than the ring can hold A slots for: one pass per clip (the 8 weight
             # blocks of 8 KB are streamed again), each writing its clip's rows of the pair-averaged level-2 plane
             tiles = lv[1]["Wp"] // 128
-            assert self.G > 1 and lv[1]["Wp"] % 128 == 0 and tiles <= 2
+            assert lv[1]["Wp"] % 128 == 0 and tiles <= 2
             for c in range(self.G):
                 self._conv([n["b2c0"]], 1, self._taps_global([n["b2c0"]], 0), [c0_2], src_global=0, pair=(True,),
                            row_base=c * lv[1]["Wp"], n_mt=tiles)
