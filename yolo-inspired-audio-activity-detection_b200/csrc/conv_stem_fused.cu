@@ -76,7 +76,8 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
   uint64_t* row_done = grp_full + 2 * SF_MAXGRP;                           // [2][SF_NACC] the MMAs of output row j (buffer b) have retired
   uint64_t* acc_full = row_done + 2 * SF_NACC;                             // [SF_NACC] accumulator slot written by the tensor core
   uint64_t* acc_empty = acc_full + SF_NACC;                                // [SF_NACC] ... drained by the 8 epilogue warps
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + SF_NACC);
+  uint64_t* w_bar = acc_empty + SF_NACC;                                   // the class's weights have landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
   int32_t* s_grp = reinterpret_cast<int32_t*>(tmem_ptr_smem + 2);          // [SF_MAXGRP][4]: first row, end row, first / last output row using it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -89,7 +90,6 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
   const int prow = hi_hi - hi_lo;
 
   const uint4* wsrc = w_classes + (size_t)cls * (SF_B_BYTES / 16);
-  for (int i = tid; i < SF_B_BYTES / 16; i += SF_THREADS) reinterpret_cast<uint4*>(sB)[i] = __ldg(wsrc + i);
   if (tid < 64) s_bias[tid] = bias[tid];
   // Row groups of the patch: maximal runs of input rows used by the same set of output rows of the class (interior class: 9 groups
   // of 2 - 4 rows; a border class: one).  Group g is first needed by output row F(g) and free again once row L(g)'s MMAs have
@@ -128,14 +128,22 @@ conv_stem_fused_kernel(const uint32_t* __restrict__ xb, const StemFusedParams p,
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], SF_EPI_WARPS);      // one arrival per epilogue warp
     }
+    mbar_init(w_bar, 1);
     fence_barrier_init();
+    // this class's 114 KB of weights: bulk copies (TMA unit) instead of 23 LDG + STS rounds of the whole CTA; launch constants,
+    // so they are fetched before the programmatic-dependent-launch wait
+    mbar_expect_tx(w_bar, (uint32_t)SF_B_BYTES);
+    constexpr uint32_t W_CHUNK = 14592;                                  // SF_B_BYTES / 8
+    static_assert(SF_B_BYTES % W_CHUNK == 0 && W_CHUNK % 16 == 0, "weight chunks");
+    for (uint32_t o = 0; o < (uint32_t)SF_B_BYTES; o += W_CHUNK)
+      sf_bulk_g2s(sB + o, reinterpret_cast<const uint8_t*>(wsrc) + o, W_CHUNK, w_bar);
   }
   if (warp == 1) tmem_alloc(tmem_ptr_smem, SF_TMEM_COLS);
-  fence_proxy_async();     // the weights were written through the generic proxy; the tensor core reads them through the async one
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp == SF_EPI_WARPS) mbar_wait(w_bar, 0);     // only the MMA warp reads the weights (through the async proxy, like the copy)
   pdl_wait();          // programmatic dependent launch: the 117 KB weight load above overlapped the frontend's tail
   pdl_trigger();
   const int n_tiles = p.B * p.n_seg;
@@ -386,7 +394,7 @@ stem_fixup_bf16_kernel(const uint32_t* __restrict__ xb, int64_t xpitch, const St
   }
 }
 
-static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + (2 * SF_MAXGRP + 4 * SF_NACC) * 8 + 16 + SF_MAXGRP * 16; }
+static size_t stem_fused_smem_bytes() { return SF_B_BYTES + SF_MAXROWS * SF_ROWB + 256 + 64 * 4 + (2 * SF_MAXGRP + 4 * SF_NACC + 1) * 8 + 16 + SF_MAXGRP * 16; }
 
 int init_conv_stem_fused_attrs() {
   static_assert(SF_ROWB % 16 == 0, "bulk copies move multiples of 16 bytes");
