@@ -186,10 +186,14 @@ def test_train_mode_forward_backward_vs_live_reference(gold, ref_state_dict):
     np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-6)
     names = [str(n) for n in g["grad_names"]]
     assert sorted(names) == sorted(grads)
+    # Gradients that are zero in exact arithmetic (the bias of a conv in front of a batch-statistics BatchNorm) come out as rounding
+    # noise (~3e-8) that depends on the host's BLAS kernels: every comparison gets an absolute floor of 1e-9 of the largest
+    # gradient norm of the net (seen on the GPU box's host: 2.48e-8 against the fixture's 2.92e-8 for cspsppf.conv_1_3_4.0.conv.bias)
+    floor = 1e-9 * max(float(st[1]) for st in g["grad_stats"])
     for n, st in zip(names, g["grad_stats"]):
         mine = TH.grad_stats(grads[n])
-        np.testing.assert_allclose(mine[1], st[1], rtol=1e-4, atol=1e-9, err_msg=n)                   # L2 norm
-        np.testing.assert_allclose(mine[2:], st[2:], rtol=1e-3, atol=1e-5 * max(st[1], 1e-6), err_msg=n)   # samples
+        np.testing.assert_allclose(mine[1], st[1], rtol=1e-4, atol=max(1e-9, floor), err_msg=n)       # L2 norm
+        np.testing.assert_allclose(mine[2:], st[2:], rtol=1e-3, atol=max(1e-5 * max(st[1], 1e-6), floor), err_msg=n)   # samples
     for k in [k for k in g if k.startswith("grad:")]:
         ref = g[k]
         np.testing.assert_allclose(grads[k[5:]].numpy(), ref, rtol=1e-3, atol=1e-5 * np.abs(ref).max(), err_msg=k)
