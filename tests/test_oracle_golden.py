@@ -196,7 +196,7 @@ def test_train_mode_forward_backward_vs_live_reference(gold, ref_state_dict):
         np.testing.assert_allclose(mine[2:], st[2:], rtol=1e-3, atol=max(1e-5 * max(st[1], 1e-6), floor), err_msg=n)   # samples
     for k in [k for k in g if k.startswith("grad:")]:
         ref = g[k]
-        np.testing.assert_allclose(grads[k[5:]].numpy(), ref, rtol=1e-3, atol=1e-5 * np.abs(ref).max(), err_msg=k)
+        np.testing.assert_allclose(grads[k[5:]].numpy(), ref, rtol=1e-3, atol=max(1e-5 * np.abs(ref).max(), floor), err_msg=k)
     for k in [k[3:] for k in g if k.startswith("rm:")]:
         np.testing.assert_allclose(sd[k + ".running_mean"].numpy(), g["rm:" + k], atol=1e-6)
         np.testing.assert_allclose(sd[k + ".running_var"].numpy(), g["rv:" + k], rtol=1e-5)
