@@ -80,6 +80,80 @@ __device__ void bitonic_sort_u64(unsigned long long* keys, int n_pad) {
   }
 }
 
+// The same sort with the keys in REGISTERS (E = n / 256 per thread, key i = tid + 256 m in thread tid): exchange distances
+// j >= 256 stay inside a thread, j < 32 are warp shuffles, only j = 32 / 64 / 128 go through shared memory (two buffers in turn:
+// one barrier per such stage).  12 block barriers and ~4 k shared-memory wavefronts for n = 1024 instead of 55 and ~14 k: the
+// in-place version was half of nms_kernel's time (profiles/r02_ncu_full_nms_b512.txt).  n = 256, 512 or 1024; blockDim.x = 256.
+template <int E>
+__device__ __forceinline__ void bitonic_sort_u64_regs(unsigned long long* keys, unsigned long long* alt) {
+  constexpr int n = 256 * E;
+  const int tid = threadIdx.x;
+  unsigned long long r[E];
+#pragma unroll
+  for (int m = 0; m < E; ++m) r[m] = keys[tid + 256 * m];
+  unsigned long long* buf[2] = {keys, alt};
+  int cur = 0;
+#pragma unroll 1
+  for (int k = 2; k <= n; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 256) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const int dm = j >> 8;                    // 1 or 2
+          if (dm < E && (m & dm) == 0 && (m | dm) < E) {
+            const int i = tid + 256 * m;
+            const bool up = (i & k) == 0;
+            // partner m | dm: selected with compile-time indices
+            unsigned long long a = r[m], b = (dm == 1) ? r[(m | 1) < E ? (m | 1) : m] : r[(m | 2) < E ? (m | 2) : m];
+            const bool sw = (a > b) == up;
+            if (sw) {
+              r[m] = b;
+              if (dm == 1) r[(m | 1) < E ? (m | 1) : m] = a; else r[(m | 2) < E ? (m | 2) : m] = a;
+            }
+          }
+        }
+      } else if (j < 32) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const int i = tid + 256 * m;
+          const unsigned long long b = __shfl_xor_sync(0xffffffffu, r[m], j);
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          r[m] = keep_min ? (r[m] < b ? r[m] : b) : (r[m] > b ? r[m] : b);
+        }
+      } else {
+        unsigned long long* bf = buf[cur];
+#pragma unroll
+        for (int m = 0; m < E; ++m) bf[tid + 256 * m] = r[m];
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const int i = tid + 256 * m;
+          const unsigned long long b = bf[(tid ^ j) + 256 * m];
+          const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+          r[m] = keep_min ? (r[m] < b ? r[m] : b) : (r[m] > b ? r[m] : b);
+        }
+        cur ^= 1;
+      }
+    }
+  }
+  __syncthreads();           // the last readers of either buffer are done
+#pragma unroll
+  for (int m = 0; m < E; ++m) keys[tid + 256 * m] = r[m];
+  __syncthreads();
+}
+
+__device__ void bitonic_sort_u64_any(unsigned long long* keys, unsigned long long* alt, int n_pad) {
+  if (blockDim.x == 256 && n_pad == 1024)
+    bitonic_sort_u64_regs<4>(keys, alt);
+  else if (blockDim.x == 256 && n_pad == 512)
+    bitonic_sort_u64_regs<2>(keys, alt);
+  else if (blockDim.x == 256 && n_pad == 256)
+    bitonic_sort_u64_regs<1>(keys, alt);
+  else
+    bitonic_sort_u64(keys, n_pad);
+}
+
 __global__ void __launch_bounds__(NMS_THREADS)
 nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float conf_thr, float duration,
            float box_h, int return_start_end, int32_t* __restrict__ keep_out, int32_t* __restrict__ n_keep_out,
@@ -90,7 +164,6 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
   pdl_trigger();
   const int b = blockIdx.x;
   const int E = 3 + nc;
-  const int W = (P + 31) >> 5;  // alive-mask words
   int n_pad = 32;
   while (n_pad < P) n_pad <<= 1;
 
@@ -109,40 +182,55 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
   const float y2 = fminf(fmaxf(box_h, 0.0f), duration);  // coords.clip(0, sample_duration) also hits y2
 
   // 1. boxes + confidence (inference.py:55-64)
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-    if (i < P) {
-      const float* r = pb + (int64_t)i * E;
-      const float c = r[E - 2], w = r[E - 1];
-      const float hw = __fdiv_rn(w, 2.0f);
-      const float x1 = fminf(fmaxf(__fsub_rn(c, hw), 0.0f), duration);
-      const float x2 = fminf(fmaxf(__fadd_rn(c, hw), 0.0f), duration);
-      float mx = r[1];
-      for (int j = 1; j < nc; ++j) mx = fmaxf(mx, r[1 + j]);
-      float sum = 0.0f;
-      for (int j = 0; j < nc; ++j) sum = __fadd_rn(sum, expf(__fsub_rn(r[1 + j], mx)));
-      // softmax max element = exp(0) * (1/sum); confidence = class_score * objectness
-      const float cf = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoid_f(r[0]));
-      s_conf[i] = cf;
-      if (conf_out) conf_out[(int64_t)b * P + i] = cf;
-      if (boxes_out) {
-        boxes_out[((int64_t)b * P + i) * 2 + 0] = x1;
-        boxes_out[((int64_t)b * P + i) * 2 + 1] = x2;
-      }
-      // descending score, ascending index  ->  ascending key
-      keys[i] = ((unsigned long long)(~sortable_bits(cf)) << 32) | (unsigned)i;
-    } else {
-      keys[i] = ~0ull;
+  // Without a keep list to report (keep_out == NULL: process_model_outputs) only boxes with conf > conf_thr can reach the output, and
+  // a box below the threshold can only suppress boxes scored even lower (the scan runs in descending score order; inference.py:75-88
+  // filters after the NMS): such boxes are dropped BEFORE the sort.  The survivors keep their relative (score desc, index asc)
+  // order, so the greedy scan visits exactly the boxes it would have visited and the segments are identical - but the bitonic
+  // sort (half of this kernel's time at P = 630 -> 1024 keys) shrinks to the next power of two above the survivor count.
+  const bool prefilter = keep_out == nullptr;
+  __shared__ int s_nvalid;
+  if (threadIdx.x == 0) s_nvalid = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float* r = pb + (int64_t)i * E;
+    const float c = r[E - 2], w = r[E - 1];
+    const float hw = __fdiv_rn(w, 2.0f);
+    const float x1 = fminf(fmaxf(__fsub_rn(c, hw), 0.0f), duration);
+    const float x2 = fminf(fmaxf(__fadd_rn(c, hw), 0.0f), duration);
+    float mx = r[1];
+    for (int j = 1; j < nc; ++j) mx = fmaxf(mx, r[1 + j]);
+    float sum = 0.0f;
+    for (int j = 0; j < nc; ++j) sum = __fadd_rn(sum, expf(__fsub_rn(r[1 + j], mx)));
+    // softmax max element = exp(0) * (1/sum); confidence = class_score * objectness
+    const float cf = __fmul_rn(__fdiv_rn(1.0f, sum), sigmoid_f(r[0]));
+    s_conf[i] = cf;
+    if (conf_out) conf_out[(int64_t)b * P + i] = cf;
+    if (boxes_out) {
+      boxes_out[((int64_t)b * P + i) * 2 + 0] = x1;
+      boxes_out[((int64_t)b * P + i) * 2 + 1] = x2;
     }
-  }
-  for (int w = threadIdx.x; w < NMS_MAXP / 32; w += blockDim.x) {
-    const int lo = w << 5;
-    s_alive[w] = (lo + 32 <= P) ? 0xffffffffu : (lo >= P ? 0u : ((1u << (P - lo)) - 1u));
+    // descending score, ascending index  ->  ascending key
+    const unsigned long long key = ((unsigned long long)(~sortable_bits(cf)) << 32) | (unsigned)i;
+    if (!prefilter)
+      keys[i] = key;
+    else if (cf > conf_thr)
+      keys[atomicAdd(&s_nvalid, 1)] = key;        // any slot: the sort orders them
   }
   __syncthreads();
-  bitonic_sort_u64(keys, n_pad);
+  const int Pn = prefilter ? s_nvalid : P;         // boxes that take part in the NMS
+  const int W = (Pn + 31) >> 5;                     // alive-mask words
+  int n_sort = 32;
+  while (n_sort < Pn) n_sort <<= 1;
+  for (int i = Pn + threadIdx.x; i < n_sort; i += blockDim.x) keys[i] = ~0ull;
+  for (int w = threadIdx.x; w < NMS_MAXP / 32; w += blockDim.x) {
+    const int lo = w << 5;
+    s_alive[w] = (lo + 32 <= Pn) ? 0xffffffffu : (lo >= Pn ? 0u : ((1u << (Pn - lo)) - 1u));
+  }
+  __syncthreads();
+  bitonic_sort_u64_any(keys, reinterpret_cast<unsigned long long*>(sx1), n_sort);     // sx1 / sx2 (8 n_pad bytes) are free until step 2
 
   // 2. gather boxes in sorted order
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+  for (int i = threadIdx.x; i < Pn; i += blockDim.x) {
     const int o = (int)(keys[i] & 0xffffffffu);
     s_order[i] = o;
     const float* r = pb + (int64_t)o * E;
@@ -183,7 +271,7 @@ nms_kernel(const float* __restrict__ preds, int P, int nc, double iou_thr, float
     for (int w = (i >> 5) + warp; w < W; w += nwarps) {
       const int j = (w << 5) + lane;
       bool sup = false;
-      if (j > i && j < P) {
+      if (j > i && j < Pn) {
         const float ww = fmaxf(0.0f, __fsub_rn(fminf(x2i, sx2[j]), fmaxf(x1i, sx1[j])));
         const float inter = __fmul_rn(ww, hh);
         const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, sarea[j]), inter));
