@@ -779,7 +779,14 @@ def main():
     ceil_gbs = hostpipe.h2d_ceiling_gbs(args.e2e_chunk * CLIP_SAMPLES * 4, nchunks, dev)
     ceil_min = -parallel.max_over_ranks(-ceil_gbs, device=dev)          # the slowest rank's link sets the max-over-ranks time
     e2e_gbs = B * CLIP_SAMPLES * 4 * Ke / (ms_e / 1e3) / 1e9
+    # ... and of the very same host tensor (2.7 GB of distinct host memory per rank instead of one 170 MB buffer copied 16 times: with
+    # several GPUs pulling at once the small buffer can be served from the host's last-level cache, the batch cannot)
+    if world > 1:
+        dist.barrier()
+    ceil_d = hostpipe.h2d_ceiling_tensor_gbs(xh, args.e2e_chunk, dev)
+    ceil_d_min = -parallel.max_over_ranks(-ceil_d, device=dev)
     e2e.update({"h2d_gbs_per_gpu": e2e_gbs, "h2d_ceiling_gbs": ceil_min, "frac_of_ceiling": e2e_gbs / ceil_min if ceil_min else None,
+                "h2d_ceiling_same_tensor_gbs": ceil_d_min, "frac_of_ceiling_same_tensor": e2e_gbs / ceil_d_min if ceil_d_min else None,
                 "numa": numa, "ceiling": f"{nchunks} back-to-back pinned cudaMemcpyAsync of {args.e2e_chunk} clips each on one stream, CUDA events, "
                                          "best of 3, all ranks concurrently, min over ranks"})
     # the same call with 16-bit PCM host buffers (the sample format of audio files; x / 32768 inside the frontend kernel): half

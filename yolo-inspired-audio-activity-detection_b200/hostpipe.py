@@ -119,6 +119,32 @@ def h2d_ceiling_gbs(nbytes_per_copy: int, copies: int, device, reps: int = 3) ->
     return best
 
 
+def h2d_ceiling_tensor_gbs(x_host: torch.Tensor, chunk: int, device, reps: int = 2) -> float:
+    """Raw pinned-host -> device copy rate (GB/s) of THE batch ``run_host_batch`` gets: the same host tensor, the same chunks,
+    back to back on the copy stream into two alternating device buffers, nothing else running (best of ``reps``).  Unlike
+    ``h2d_ceiling_gbs`` (one chunk-sized source buffer copied over and over, which the host's last-level cache can serve when
+    several GPUs pull at once) every byte comes from a different place in host memory, as in the pipeline."""
+    N = x_host.shape[0]
+    chunk = max(1, min(int(chunk), N))
+    dst = [torch.empty((chunk,) + tuple(x_host.shape[1:]), device=device, dtype=x_host.dtype) for _ in range(2)]
+    st = _copy_stream(device)
+    nbytes = x_host.numel() * x_host.element_size()
+    best = 0.0
+    with torch.cuda.stream(st):
+        dst[0][:1].copy_(x_host[:1], non_blocking=True)
+        st.synchronize()
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            for i, s0 in enumerate(range(0, N, chunk)):
+                n = min(chunk, N - s0)
+                dst[i & 1][:n].copy_(x_host[s0:s0 + n], non_blocking=True)
+            b.record(st)
+            st.synchronize()
+            best = max(best, nbytes / (a.elapsed_time(b) / 1e3) / 1e9)
+    return best
+
+
 _COPY_STREAMS = {}
 
 
