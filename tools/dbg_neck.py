@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 fm = [plan[f"s{li}.1.y"] for li in range(4)]
 geoms = [(f.shape[2] - 1 if f.shape[2] > 1 else 1, f.shape[1] - 1) for f in fm]
 print("geoms", geoms, [tuple(f.shape) for f in fm])
-fn = FusedNeck(eng, [g[0] for g in geoms], [g[1] for g in geoms], [f.shape[3] for f in fm], debug=True)
+fn = FusedNeck(eng, [g[0] for g in geoms], [g[1] for g in geoms], [f.shape[3] for f in fm], debug=True, G=1)   # one clip per pass: the dumps are per clip (two clips per pass are pinned bitwise to this by tests/test_gpu_parity.py)
 print("program: ops", len(fn.ops), "kbs", len(fn.kbs), "pool", fn.pool_bytes, "slots", fn.n_slots)
 heads = [torch.full_like(h, float("nan")) for h in heads_ref]
 dbg = torch.zeros(B * fn.dump_elems, dtype=torch.bfloat16, device=dev)
