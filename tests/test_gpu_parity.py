@@ -72,6 +72,13 @@ def test_frontend_full_clip_and_ragged_lengths(models, gold, ref_state_dict, cud
     taps = {}
     m(xr.to(cuda_dev), combine_scales=True, taps=taps)
     _check_frontend(taps, O.frontend(xr, ref_state_dict))
+    # an ODD frame count above the cluster threshold of stage B (T = 125: two CTAs per clip with 63 and 62 frames; the maxima and
+    # moments cross the cluster through distributed shared memory - modules/_architecture.py:98-105, 182-189)
+    xo = synth.synth_clips(3, 173000, seed=3100, silence_tail_every=3)
+    taps = {}
+    m(xo.to(cuda_dev), combine_scales=True, taps=taps)
+    assert taps["x_spectral"].shape == (3, 2, 32, 125)
+    _check_frontend(taps, O.frontend(xo, ref_state_dict))
 
 
 # ---- the benchmarked code path: persistent CTAs running MANY groups each (the bench has ~415 groups per CTA; every test above
